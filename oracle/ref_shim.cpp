@@ -1,0 +1,232 @@
+/*
+ * ref_shim.cpp -- thin C-ABI access to the REFERENCE's own code, for tests and the CPU baseline.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Compiled (oracle/Makefile, target `ref`) together with objects built
+ * straight from /root/reference into oracle/_ref/libref_shim.so and oracle/_ref/lordfast_chaindump;
+ * no reference source is copied into this repository.  The shim only *calls* the reference:
+ *   edlibAlign / edlibFreeAlignResult   lib/edlib/edlib.h:172-192
+ *   ksw_extend2                         lib/bwa/ksw.h:107-108
+ *   alignChain_edlib                    src/LordFAST.cpp:1765 (through the reference's own hook,
+ *                                       the global function pointer `alignChain`, :107)
+ *   bwt_load/initRead/initializeFAST/readChunk/initFASTChunk/mapSeqMT/finalizeFAST
+ *                                       src/baseFAST.cpp:32-84 (the stock search loop)
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <time.h>
+#include <string>
+#include <vector>
+
+#include "Common.h"
+#include "CommandLineParser.h"
+#include "BWT.h"
+#include "LordFAST.h"
+#include "bwa.h"
+#include "edlib.h"
+extern "C" {
+#include "ksw.h"
+}
+#include "lf_oracle.h" /* lfo_seed / lfo_sam record layouts shared with the restatement */
+
+/* globals and functions the reference defines without declaring them in a header */
+extern bwaidx_t *_fmd_index;                                   /* src/BWT.cpp:32 */
+extern uint8_t _pf_char2int[128];                              /* src/LordFAST.cpp:74 */
+extern int8_t _pf_kswMatrix[25], _pf_kswMatrix_clip[25];       /* :75-76 */
+extern MapInfo *_pf_topMappings;                               /* :62 */
+extern void (*alignChain)(Chain_t &, char *, int32_t, int, SamList_t &); /* :107 */
+void alignChain_edlib(Chain_t &chain, char *query, int32_t readLen, int isRev, SamList_t &map);
+
+extern "C" {
+
+int ref_align(const char *q, int ql, const char *t, int tl, int mode, int want_path, int *ed,
+              int *endloc, unsigned char *ops, int *nops)
+{
+    EdlibAlignResult r = edlibAlign(q, ql, t, tl, edlibNewAlignConfig(-1, mode == 1 ? EDLIB_MODE_SHW : EDLIB_MODE_NW,
+                                                                       want_path ? EDLIB_TASK_PATH : EDLIB_TASK_DISTANCE));
+    *ed = r.editDistance;
+    *endloc = r.endLocations ? r.endLocations[0] : -2;
+    *nops = 0;
+    if (want_path && r.alignment) {
+        memcpy(ops, r.alignment, (size_t)r.alignmentLength);
+        *nops = r.alignmentLength;
+    }
+    edlibFreeAlignResult(r);
+    return 0;
+}
+
+int ref_extend(int qlen, const uint8_t *q, int tlen, const uint8_t *t, int m, const int8_t *mat, int o_del,
+               int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0, int *qle, int *tle)
+{
+    return ksw_extend2(qlen, q, tlen, t, m, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle, 0, 0, 0);
+}
+
+/* ---- a fabricated in-memory index so that bwt_str_pac2char / bwt_get_chr_boundaries work ---- */
+static bwaidx_t g_idx;
+static bntseq_t g_bns;
+static std::vector<bntann1_t> g_anns;
+static std::vector<std::string> g_names;
+
+static void init_tables()
+{ /* what initializeFAST sets up for the alignment stage (src/LordFAST.cpp:158-187) */
+    memset(_pf_char2int, 4, 128);
+    _pf_char2int['A'] = _pf_char2int['a'] = 0; _pf_char2int['C'] = _pf_char2int['c'] = 1;
+    _pf_char2int['G'] = _pf_char2int['g'] = 2; _pf_char2int['T'] = _pf_char2int['t'] = 3;
+    int k = 0;
+    for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) _pf_kswMatrix_clip[k++] = (i == j ? 2 : -16); _pf_kswMatrix_clip[k++] = 0; }
+    for (int j = 0; j < 5; j++) _pf_kswMatrix_clip[k++] = 0;
+    k = 0;
+    for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) _pf_kswMatrix[k++] = (i == j ? 2 : -5); _pf_kswMatrix[k++] = 0; }
+    for (int j = 0; j < 5; j++) _pf_kswMatrix[k++] = 0;
+}
+
+void ref_set_index(const uint8_t *pac, int64_t l_pac, int n_contigs, const int64_t *off, const int32_t *len)
+{
+    g_anns.assign((size_t)n_contigs, bntann1_t());
+    g_names.resize((size_t)n_contigs);
+    for (int i = 0; i < n_contigs; i++) {
+        g_names[i] = "chr" + std::to_string(i + 1);
+        g_anns[i].offset = off[i]; g_anns[i].len = len[i];
+        g_anns[i].name = (char *)g_names[i].c_str(); g_anns[i].anno = (char *)"";
+    }
+    memset(&g_bns, 0, sizeof g_bns);
+    g_bns.l_pac = l_pac; g_bns.n_seqs = n_contigs; g_bns.anns = g_anns.data();
+    memset(&g_idx, 0, sizeof g_idx);
+    g_idx.bns = &g_bns; g_idx.pac = (uint8_t *)pac;
+    _fmd_index = &g_idx;
+    init_tables();
+}
+
+static void fill_chain(Chain_t &c, std::vector<Seed_t> &store, const lfo_seed *seeds, int n)
+{
+    store.resize((size_t)n);
+    for (int i = 0; i < n; i++) { store[i].tPos = seeds[i].tPos; store[i].qPos = seeds[i].qPos; store[i].len = seeds[i].len; }
+    c.seeds = store.data(); c.chainLen = (uint32_t)n; c.score = 0;
+}
+
+static void *run_on_big_stack(void *(*fn)(void *), void *arg)
+{ /* alignChain_edlib keeps ~2 MB of arrays on its stack (src/LordFAST.cpp:1770-1781) */
+    pthread_attr_t a; pthread_t th; void *ret = NULL;
+    pthread_attr_init(&a); pthread_attr_setstacksize(&a, 32u << 20);
+    pthread_create(&th, &a, fn, arg); pthread_join(th, &ret); pthread_attr_destroy(&a);
+    return ret;
+}
+
+struct chain_call { const lfo_seed *seeds; int n; const char *query; int readLen, isRev; lfo_sam *out; int cap; int *n_out; };
+
+static void *chain_call_fn(void *p)
+{
+    chain_call *a = (chain_call *)p;
+    Chain_t c; std::vector<Seed_t> store; SamList_t map;
+    fill_chain(c, store, a->seeds, a->n);
+    alignChain_edlib(c, (char *)a->query, a->readLen, a->isRev, map);
+    int k = 0;
+    for (size_t i = 0; i < map.samList.size() && k < a->cap; i++, k++) {
+        const Sam_t &s = map.samList[i];
+        a->out[k].flag = s.flag; a->out[k].pos = s.pos; a->out[k].posEnd = s.posEnd;
+        a->out[k].qStart = s.qStart; a->out[k].qEnd = s.qEnd; a->out[k].nmCount = s.nmCount;
+        a->out[k].cigar = strdup(s.cigar.c_str()); a->out[k].md = strdup(s.md.c_str());
+    }
+    *a->n_out = k;
+    return NULL;
+}
+
+int ref_align_chain(const lfo_seed *seeds, int n, const char *query, int readLen, int isRev, lfo_sam *out, int cap, int *n_out)
+{
+    chain_call a = { seeds, n, query, readLen, isRev, out, cap, n_out };
+    run_on_big_stack(chain_call_fn, &a);
+    return 0;
+}
+
+/* ---- CPU baseline: the reference's alignChain_edlib replayed over pre-dumped chains ---- */
+struct replay_shared {
+    int n_chains; const int64_t *seed_off; const lfo_seed *seeds; const char *const *query; const int32_t *readLen;
+    const uint8_t *isRev; int next; pthread_mutex_t lock; int64_t n_sam;
+};
+
+static void *replay_worker(void *p)
+{
+    replay_shared *s = (replay_shared *)p;
+    std::vector<Seed_t> store; int64_t ns = 0;
+    for (;;) {
+        pthread_mutex_lock(&s->lock); int i = s->next++; pthread_mutex_unlock(&s->lock);
+        if (i >= s->n_chains) break;
+        Chain_t c; SamList_t map;
+        fill_chain(c, store, s->seeds + s->seed_off[i], (int)(s->seed_off[i + 1] - s->seed_off[i]));
+        alignChain_edlib(c, (char *)s->query[i], s->readLen[i], s->isRev[i], map);
+        ns += (int64_t)map.samList.size();
+    }
+    pthread_mutex_lock(&s->lock); s->n_sam += ns; pthread_mutex_unlock(&s->lock);
+    return NULL;
+}
+
+/* returns wall seconds for one pass over all chains on `nthreads` threads */
+double ref_replay_chains(int n_chains, const int64_t *seed_off, const lfo_seed *seeds, const char *const *query,
+                         const int32_t *readLen, const uint8_t *isRev, int nthreads, int64_t *n_sam)
+{
+    replay_shared s = { n_chains, seed_off, seeds, query, readLen, isRev, 0, PTHREAD_MUTEX_INITIALIZER, 0 };
+    std::vector<pthread_t> th((size_t)nthreads);
+    pthread_attr_t a; pthread_attr_init(&a); pthread_attr_setstacksize(&a, 32u << 20);
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < nthreads; i++) pthread_create(&th[i], &a, replay_worker, &s);
+    for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    pthread_attr_destroy(&a);
+    if (n_sam) *n_sam = s.n_sam;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+} /* extern "C" */
+
+/* ------------------------------------------------------------------------------------------ */
+/* lordfast_chaindump: the stock search loop with the reference's `alignChain` hook pointed at  */
+/* a recorder that forwards to alignChain_edlib and logs each chain and the records it yields.  */
+/* ------------------------------------------------------------------------------------------ */
+#ifdef LF_CHAINDUMP_MAIN
+static FILE *g_dump = NULL;
+static pthread_mutex_t g_dump_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void dump_hook(Chain_t &chain, char *query, int32_t readLen, int isRev, SamList_t &map)
+{
+    size_t before = map.samList.size();
+    alignChain_edlib(chain, query, readLen, isRev, map);
+    const char *name = "?";
+    for (int i = 0; i < THREAD_COUNT; i++)
+        if (_pf_topMappings[i].seq == query || _pf_topMappings[i].seq_rev == query) name = _pf_topMappings[i].qName;
+    pthread_mutex_lock(&g_dump_lock);
+    fprintf(g_dump, "C\t%s\t%d\t%d\t%u\t", name, readLen, isRev, chain.chainLen);
+    for (uint32_t i = 0; i < chain.chainLen; i++)
+        fprintf(g_dump, "%u,%u,%u;", chain.seeds[i].tPos, (unsigned)chain.seeds[i].qPos, (unsigned)chain.seeds[i].len);
+    fprintf(g_dump, "\n");
+    for (size_t i = before; i < map.samList.size(); i++) {
+        const Sam_t &s = map.samList[i];
+        fprintf(g_dump, "S\t%u\t%u\t%u\t%u\t%u\t%d\t%s\t%s\n", (unsigned)s.flag, s.pos, s.posEnd, s.qStart, s.qEnd, s.nmCount,
+                s.cigar.c_str(), s.md.c_str());
+    }
+    pthread_mutex_unlock(&g_dump_lock);
+}
+
+int main(int argc, char *argv[])
+{
+    const char *path = getenv("LF_CHAIN_DUMP");
+    if (parseCommandLine(argc, argv)) return EXIT_FAILURE;
+    if (indexingMode) return bwt_index(refFile) ? EXIT_FAILURE : 0;
+    g_dump = fopen(path ? path : "chains.txt", "w");
+    if (!g_dump) { perror("LF_CHAIN_DUMP"); return EXIT_FAILURE; }
+    Read *seqList; unsigned int seqListSize;
+    if (bwt_load(refFile)) return EXIT_FAILURE;
+    if (!initRead(seqFile, 100000000)) return EXIT_FAILURE;
+    initializeFAST();
+    alignChain = &dump_hook;
+    while (readChunk(&seqList, &seqListSize) > 0) {
+        initFASTChunk(seqList, seqListSize);
+        mapSeqMT();
+        releaseChunk();
+    }
+    finalizeFAST();
+    fclose(g_dump);
+    return 0;
+}
+#endif

@@ -1,0 +1,170 @@
+"""ctypes access to the checkers: oracle/liblforacle.so (our CPU restatement) and, when it was
+built in this container, oracle/_ref/libref_shim.so (the reference's own edlib / ksw /
+alignChain_edlib).  Test infrastructure only -- nothing in lordfast_b200/ imports this."""
+import ctypes as C
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liblforacle.so")
+REF_SHIM_SO = os.path.join(ORACLE_DIR, "_ref", "libref_shim.so")
+
+CLIP_MAT = (C.c_int8 * 25)(*[2 if (i == j and i < 4) else (0 if (i == 4 or j == 4) else -16)
+                            for i in range(5) for j in range(5)])
+
+
+class AlignOut(C.Structure):
+    _fields_ = [("edit_distance", C.c_int), ("end_location", C.c_int), ("n_ops", C.c_int)]
+
+
+class Sam(C.Structure):
+    _fields_ = [("flag", C.c_uint32), ("pos", C.c_uint32), ("posEnd", C.c_uint32), ("qStart", C.c_uint32),
+                ("qEnd", C.c_uint32), ("nmCount", C.c_int32), ("cigar", C.c_void_p), ("md", C.c_void_p)]
+
+
+class Seed(C.Structure):
+    _fields_ = [("tPos", C.c_uint32), ("qPos", C.c_uint32), ("len", C.c_uint32)]
+
+
+class Ref(C.Structure):
+    _fields_ = [("pac", C.c_void_p), ("l_pac", C.c_int64), ("n_contigs", C.c_int),
+                ("contig_off", C.POINTER(C.c_int64)), ("contig_len", C.POINTER(C.c_int32))]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_align", C.c_int64), ("n_extend", C.c_int64), ("cells_align", C.c_int64), ("cells_extend", C.c_int64)]
+
+
+def build_oracle():
+    src = os.path.join(ORACLE_DIR, "lf_oracle.c")
+    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    return ORACLE_SO
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(build_oracle())
+        lib.lfo_align.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(AlignOut), C.c_void_p]
+        lib.lfo_ksw_extend2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 2
+        lib.lfo_pack_ref.argtypes = [C.c_char_p, C.c_int64, C.c_void_p]
+        lib.lfo_align_chain.argtypes = [C.POINTER(Ref), C.POINTER(Seed), C.c_int, C.c_char_p, C.c_int32, C.c_int,
+                                        C.POINTER(Sam), C.c_int, C.POINTER(C.c_int), C.POINTER(Stats)]
+        lib.lfo_free_sam.argtypes = [C.POINTER(Sam), C.c_int]
+        _oracle = lib
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SHIM_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SHIM_SO)
+        lib.ref_align.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+        lib.ref_extend.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 2
+        lib.ref_set_index.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        lib.ref_align_chain.argtypes = [C.POINTER(Seed), C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(Sam), C.c_int, C.POINTER(C.c_int)]
+        lib.ref_replay_chains.restype = C.c_double
+        _ref = lib
+    return _ref
+
+
+def oracle_align(q: bytes, t: bytes, mode: int, want_path=True):
+    out = AlignOut()
+    ops = C.create_string_buffer(len(q) + len(t) + 1)
+    rc = oracle().lfo_align(q, len(q), t, len(t), mode, 1 if want_path else 0, C.byref(out), ops)
+    assert rc == 0, rc
+    return out.edit_distance, out.end_location, ops.raw[:out.n_ops]
+
+
+def ref_align(q: bytes, t: bytes, mode: int, want_path=True):
+    ed, end, n = C.c_int(), C.c_int(), C.c_int()
+    ops = C.create_string_buffer(len(q) + len(t) + 1)
+    ref().ref_align(q, len(q), t, len(t), mode, 1 if want_path else 0, C.byref(ed), C.byref(end), ops, C.byref(n))
+    return ed.value, end.value, ops.raw[:n.value]
+
+
+def _extend(fn, q: bytes, t: bytes, o_del, e_del, o_ins, e_ins, w, zdrop, h0=None, mat=CLIP_MAT, end_bonus=0):
+    qle, tle = C.c_int(), C.c_int()
+    qb, tb = C.create_string_buffer(q, len(q)), C.create_string_buffer(t, len(t))
+    sc = fn(len(q), qb, len(t), tb, 5, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop,
+            len(q) if h0 is None else h0, C.byref(qle), C.byref(tle))
+    return sc, qle.value, tle.value
+
+
+def oracle_extend(q, t, *a, **k):
+    return _extend(oracle().lfo_ksw_extend2, q, t, *a, **k)
+
+
+def ref_extend(q, t, *a, **k):
+    return _extend(ref().ref_extend, q, t, *a, **k)
+
+
+def pack_ref(seq: bytes):
+    pac = C.create_string_buffer(len(seq) // 4 + 2)
+    oracle().lfo_pack_ref(seq, len(seq), pac)
+    return pac
+
+
+class RefIndex:
+    """A packed reference plus its contig table, usable by both checkers."""
+
+    def __init__(self, seq: bytes, contig_lens=None):
+        self.seq = seq
+        self.pac = pack_ref(seq)
+        lens = contig_lens or [len(seq)]
+        assert sum(lens) == len(seq)
+        self.n = len(lens)
+        self.off = (C.c_int64 * self.n)()
+        self.len = (C.c_int32 * self.n)(*lens)
+        o = 0
+        for i, l in enumerate(lens):
+            self.off[i] = o
+            o += l
+        self.cref = Ref(C.cast(self.pac, C.c_void_p), len(seq), self.n, self.off, self.len)
+
+
+def _sam_list(arr, n):
+    out = []
+    for i in range(n):
+        s = arr[i]
+        out.append(dict(flag=s.flag, pos=s.pos, posEnd=s.posEnd, qStart=s.qStart, qEnd=s.qEnd, nm=s.nmCount,
+                        cigar=C.string_at(s.cigar).decode(), md=C.string_at(s.md).decode()))
+    return out
+
+
+def oracle_align_chain(idx: RefIndex, seeds, query: bytes, is_rev: int):
+    arr = (Seed * len(seeds))(*[Seed(*s) for s in seeds])
+    sam = (Sam * 64)()
+    n = C.c_int(0)
+    st = Stats()
+    rc = oracle().lfo_align_chain(C.byref(idx.cref), arr, len(seeds), query, len(query), is_rev, sam, 64, C.byref(n), C.byref(st))
+    assert rc == 0
+    out = _sam_list(sam, n.value)
+    oracle().lfo_free_sam(sam, n.value)
+    return out, st
+
+
+def ref_align_chain(idx: RefIndex, seeds, query: bytes, is_rev: int):
+    ref().ref_set_index(C.cast(idx.pac, C.c_void_p), len(idx.seq), idx.n, idx.off, idx.len)
+    arr = (Seed * len(seeds))(*[Seed(*s) for s in seeds])
+    sam = (Sam * 64)()
+    n = C.c_int(0)
+    ref().ref_align_chain(arr, len(seeds), query, len(query), is_rev, sam, 64, C.byref(n))
+    out = _sam_list(sam, n.value)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for i in range(n.value):
+        libc.free(sam[i].cigar)
+        libc.free(sam[i].md)
+    return out
