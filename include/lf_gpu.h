@@ -1,0 +1,167 @@
+/*
+ * lf_gpu.h -- C ABI of liblfgpu.so: lordFAST's per-candidate alignment stage as one batched
+ * B200 (sm_100a) path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * What each entry point replaces in the reference (file:line relative to vpc-ccg/lordfast):
+ *
+ *   lf_gpu_align_batch    every edlibAlign(.., edlibNewAlignConfig(-1, NW|SHW, PATH)) call that
+ *                         alignChain_edlib issues: src/LordFAST.cpp:1833 (head, SHW), :1941 (gap,
+ *                         NW), :2168 (tail, SHW) and the follow-ups :1853, :2001, :2037, :2039,
+ *                         :2084, :2184; library seam lib/edlib/edlib.h:190-192.  The reference
+ *                         fetch of the target slice (bwt_str_pac2char, src/BWT.cpp:601-607),
+ *                         reverseComplement (src/Common.cpp:57-66) and edlib's transformSequences /
+ *                         buildPeq (lib/edlib/edlib.cpp:281, :1350) are fused into the kernels.
+ *   lf_gpu_extend_batch   ksw_extend (:1848, :2180) and ksw_extend2 (:1971, :1981); library seam
+ *                         lib/bwa/ksw.h:107-108; convertChar2int / reverseComplementIntStr /
+ *                         bwt_str_pac2int (src/LordFAST.cpp:1191-1201, src/BWT.cpp:593-599) fused.
+ *   lf_gpu_init           the in-memory 2-bit reference `_fmd_index->pac` (lib/bwa/bwa.c:270-275,
+ *                         layout lib/bwa/bntseq.c:224-225) is copied to HBM once.
+ *
+ * Results are bit-identical to the reference calls: editDistance, endLocations[0] and the
+ * alignment[] op codes (lib/edlib/edlib.h:69-72, :121-166); score / qle / tle of ksw_extend2.
+ *
+ * Conventions: every function returns LF_OK (0) or a negative lf_status and never exits the
+ * process; all buffers are caller-owned; results come back in task order; a context is bound to
+ * its device set; distinct contexts may be used concurrently from different host threads, one
+ * context must not be.  There is no CPU fallback: without a CUDA device lf_gpu_init fails with
+ * LF_ERR_NO_DEVICE.
+ */
+#ifndef LF_GPU_H
+#define LF_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lf_gpu_ctx lf_gpu_ctx;
+
+typedef enum {
+    LF_OK = 0,
+    LF_ERR_NO_DEVICE = -1,   /* no usable CUDA device / driver */
+    LF_ERR_CUDA = -2,        /* a CUDA call failed; see lf_gpu_last_error */
+    LF_ERR_BAD_ARG = -3,     /* null pointer, zero-length sequence, offset out of range ... */
+    LF_ERR_OPS_CAPACITY = -4,/* `ops` buffer smaller than lf_gpu_ops_capacity() asks for */
+    LF_ERR_NOMEM = -5
+} lf_status;
+
+/* ---- inputs ------------------------------------------------------------------------------- */
+
+/* The reads of one chunk as sequenced (forward); the GPU derives reverse complements itself.
+ * bases[offsets[r] .. offsets[r+1]) is read r (ASCII; anything but upper-case ACGT never matches
+ * the reference in the edit-distance kernels, exactly as in edlib's byte comparison). */
+typedef struct {
+    const uint8_t  *bases;
+    const uint64_t *offsets; /* n_reads + 1 entries */
+    uint32_t        n_reads;
+} lf_reads;
+
+enum { LF_MODE_NW = 0, LF_MODE_SHW = 1 }; /* EDLIB_MODE_NW / EDLIB_MODE_SHW */
+
+enum {
+    LF_F_READ_REV     = 1, /* oriented read = reverse complement of the stored read (isRev)        */
+    LF_F_REVERSE_BOTH = 2, /* query and target slices are both taken right-to-left: read head
+                              (:1827-1831), head re-alignment (:1853), second split part (:2082-2084).
+                              The reference also complements both sides, which leaves equality as is. */
+    LF_F_RC_QUERY     = 4, /* only the query slice is reverse-complemented (inversion test :2038-2039) */
+    LF_F_NO_PATH      = 8  /* distance / end location only (EDLIB_TASK_DISTANCE)                    */
+};
+
+typedef struct {        /* 24 bytes */
+    uint32_t read_id;   /* index into lf_reads                                                     */
+    uint32_t q_off;     /* slice start in the ORIENTED read (the read, or its reverse complement) */
+    uint32_t q_len;     /* >= 1                                                                    */
+    uint32_t t_off;     /* slice start on the forward reference (pac coordinate)                   */
+    uint32_t t_len;     /* >= 1                                                                    */
+    uint16_t flags;     /* LF_F_*                                                                  */
+    uint8_t  mode;      /* LF_MODE_*                                                               */
+    uint8_t  reserved;
+} lf_align_task;
+
+typedef struct {        /* 24 bytes */
+    int32_t  edit_distance; /* EdlibAlignResult.editDistance                                       */
+    int32_t  end_location;  /* endLocations[0]: t_len-1 for NW; first best prefix end for SHW, may be -1 */
+    uint64_t ops_off;       /* first op of this task in the 2-bit op stream (op index, not bytes)  */
+    uint32_t ops_len;       /* alignmentLength                                                     */
+    int32_t  status;        /* 0, or a negative lf_status for this task                            */
+} lf_align_result;
+
+/* Op stream: 2 bits per op, four ops per byte, op p at bits 2*(p&3) of byte p>>2; codes are
+ * edlib's 0 = match, 1 = insert (query base only), 2 = delete (target base only), 3 = mismatch,
+ * in the order edlib returns them (left to right in the task's own orientation). */
+#define LF_OP_AT(ops, p) ((unsigned)(((const uint8_t *)(ops))[(p) >> 2] >> (((p) & 3) << 1)) & 3u)
+
+typedef struct {        /* 52 bytes; sequences described as in lf_align_task */
+    uint32_t read_id, q_off, q_len, t_off, t_len;
+    uint16_t flags;     /* LF_F_READ_REV, LF_F_REVERSE_BOTH                                        */
+    uint8_t  matrix;    /* LF_MAT_* */
+    uint8_t  reserved;
+    int32_t  o_del, e_del, o_ins, e_ins, w, zdrop, h0; /* ksw_extend2 arguments; end_bonus = 0     */
+} lf_extend_task;
+
+enum { LF_MAT_CLIP = 0 /* _pf_kswMatrix_clip: +2 / -16, N row/col 0 (src/LordFAST.cpp:82-83, 178-187) */,
+       LF_MAT_DEFAULT = 1 /* _pf_kswMatrix: +2 / -5 (:78-79, 166-176) */ };
+
+typedef struct {        /* 12 bytes */
+    int32_t score, qle, tle; /* return value, *_qle, *_tle of ksw_extend2                          */
+} lf_extend_result;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+
+/* pac: l_pac/4+1 bytes in bwa's layout (base l in byte l>>2, bits ((~l)&3)<<1).  devices == NULL
+ * or n_devices == 0 selects the current CUDA device.  The reference is replicated on every
+ * device of the set and a batch is split across them by contiguous task ranges. */
+int  lf_gpu_init(lf_gpu_ctx **ctx, const uint8_t *pac, int64_t l_pac, const int *devices, int n_devices);
+void lf_gpu_destroy(lf_gpu_ctx *ctx);
+const char *lf_gpu_last_error(const lf_gpu_ctx *ctx);
+
+/* Pinned host memory for task / result / op buffers (pageable memory works, pinned is faster). */
+void *lf_gpu_host_alloc(size_t bytes);
+void  lf_gpu_host_free(void *p);
+
+/* Bytes the caller must provide in `ops` for these tasks (a slot of q_len+t_len ops per task,
+ * rounded up to 16 ops). */
+size_t lf_gpu_ops_capacity(const lf_align_task *tasks, size_t n);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+
+/* Host buffers in, host buffers out: copies reads/tasks to the device(s), runs the alignment
+ * kernels, copies results and ops back.  `ops` may be NULL if every task has LF_F_NO_PATH. */
+int lf_gpu_align_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_align_task *tasks, size_t n,
+                       lf_align_result *res, uint8_t *ops, size_t ops_cap);
+
+int lf_gpu_extend_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_extend_task *tasks, size_t n,
+                        lf_extend_result *res);
+
+/* The same path split into its three phases, so that a caller (and bench.py) can keep a batch
+ * resident in HBM: upload -> run (any number of times) -> download. */
+int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads);
+int lf_gpu_upload_align_tasks(lf_gpu_ctx *ctx, const lf_align_task *tasks, size_t n);
+int lf_gpu_run_align(lf_gpu_ctx *ctx);  /* kernels only, on the resident batch; asynchronous */
+int lf_gpu_sync(lf_gpu_ctx *ctx);
+int lf_gpu_download_align(lf_gpu_ctx *ctx, lf_align_result *res, uint8_t *ops, size_t ops_cap);
+int lf_gpu_upload_extend_tasks(lf_gpu_ctx *ctx, const lf_extend_task *tasks, size_t n);
+int lf_gpu_run_extend(lf_gpu_ctx *ctx);
+int lf_gpu_download_extend(lf_gpu_ctx *ctx, lf_extend_result *res);
+
+/* ---- measurement hooks -------------------------------------------------------------------- */
+
+typedef struct {
+    uint64_t kernel_launches;   /* launches of our own kernels since the context was created       */
+    uint64_t align_tasks, extend_tasks;
+    uint64_t cells;             /* sum of q_len * t_len over align tasks                           */
+    uint64_t word_columns;      /* sum of ceil(q_len/32) * t_len: 16 INT32 ops each    */
+    float    last_run_ms;       /* CUDA-event time of the last lf_gpu_run_* on device 0's stream   */
+    float    last_main_kernel_ms; /* CUDA-event time of the dominant (small-task) kernels therein  */
+    uint64_t last_main_word_columns;
+} lf_gpu_stats;
+int lf_gpu_get_stats(const lf_gpu_ctx *ctx, lf_gpu_stats *out);
+
+/* INT32 issue-rate microbenchmarks on device 0 (dependent-free streams on all SMs); Top/s.
+ * which: 0 = LOP3 only, 1 = IADD3 only, 2 = LOP3+IADD3 mix, 3 = LOP3 + IMAD mix */
+int lf_gpu_int32_peak(lf_gpu_ctx *ctx, int which, double *tops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,202 @@
+"""ctypes binding of liblfgpu.so (include/lf_gpu.h) -- the host-side mirror of lordFAST's alignment
+stage operators.  PyTorch is not needed here; the library owns its CUDA stream and buffers.
+
+There is deliberately no fallback: if liblfgpu.so is missing or no CUDA device is visible the calls
+raise.  `lib_path` exists so that tests can point the same binding at the test-only emulator build.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "liblfgpu.so")
+
+LF_MODE_NW, LF_MODE_SHW = 0, 1
+LF_F_READ_REV, LF_F_REVERSE_BOTH, LF_F_RC_QUERY, LF_F_NO_PATH = 1, 2, 4, 8
+LF_MAT_CLIP, LF_MAT_DEFAULT = 0, 1
+
+ALIGN_TASK = np.dtype([("read_id", "<u4"), ("q_off", "<u4"), ("q_len", "<u4"), ("t_off", "<u4"), ("t_len", "<u4"),
+                       ("flags", "<u2"), ("mode", "u1"), ("reserved", "u1")])
+ALIGN_RESULT = np.dtype([("edit_distance", "<i4"), ("end_location", "<i4"), ("ops_off", "<u8"), ("ops_len", "<u4"),
+                         ("status", "<i4")])
+EXTEND_TASK = np.dtype([("read_id", "<u4"), ("q_off", "<u4"), ("q_len", "<u4"), ("t_off", "<u4"), ("t_len", "<u4"),
+                        ("flags", "<u2"), ("matrix", "u1"), ("reserved", "u1"), ("o_del", "<i4"), ("e_del", "<i4"),
+                        ("o_ins", "<i4"), ("e_ins", "<i4"), ("w", "<i4"), ("zdrop", "<i4"), ("h0", "<i4")])
+EXTEND_RESULT = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4")])
+assert ALIGN_TASK.itemsize == 24 and ALIGN_RESULT.itemsize == 24 and EXTEND_TASK.itemsize == 52 and EXTEND_RESULT.itemsize == 12
+
+
+class Reads(C.Structure):
+    _fields_ = [("bases", C.c_void_p), ("offsets", C.c_void_p), ("n_reads", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("align_tasks", C.c_uint64), ("extend_tasks", C.c_uint64),
+                ("cells", C.c_uint64), ("word_columns", C.c_uint64), ("last_run_ms", C.c_float),
+                ("last_main_kernel_ms", C.c_float), ("last_main_word_columns", C.c_uint64)]
+
+
+EXPORTS = ["lf_gpu_init", "lf_gpu_destroy", "lf_gpu_last_error", "lf_gpu_host_alloc", "lf_gpu_host_free",
+           "lf_gpu_ops_capacity", "lf_gpu_align_batch", "lf_gpu_extend_batch", "lf_gpu_upload_reads",
+           "lf_gpu_upload_align_tasks", "lf_gpu_run_align", "lf_gpu_sync", "lf_gpu_download_align",
+           "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",
+           "lf_gpu_int32_peak"]
+
+
+class LfGpuError(RuntimeError):
+    pass
+
+
+def load(lib_path: str | None = None) -> C.CDLL:
+    path = lib_path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise LfGpuError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback for the alignment stage)")
+    lib = C.CDLL(path)
+    vp, sz = C.c_void_p, C.c_size_t
+    lib.lf_gpu_init.argtypes = [C.POINTER(vp), vp, C.c_int64, vp, C.c_int]
+    lib.lf_gpu_destroy.argtypes = [vp]
+    lib.lf_gpu_destroy.restype = None
+    lib.lf_gpu_last_error.argtypes = [vp]
+    lib.lf_gpu_last_error.restype = C.c_char_p
+    lib.lf_gpu_host_alloc.argtypes = [sz]
+    lib.lf_gpu_host_alloc.restype = vp
+    lib.lf_gpu_host_free.argtypes = [vp]
+    lib.lf_gpu_host_free.restype = None
+    lib.lf_gpu_ops_capacity.argtypes = [vp, sz]
+    lib.lf_gpu_ops_capacity.restype = sz
+    lib.lf_gpu_align_batch.argtypes = [vp, C.POINTER(Reads), vp, sz, vp, vp, sz]
+    lib.lf_gpu_extend_batch.argtypes = [vp, C.POINTER(Reads), vp, sz, vp]
+    lib.lf_gpu_upload_reads.argtypes = [vp, C.POINTER(Reads)]
+    lib.lf_gpu_upload_align_tasks.argtypes = [vp, vp, sz]
+    lib.lf_gpu_run_align.argtypes = [vp]
+    lib.lf_gpu_sync.argtypes = [vp]
+    lib.lf_gpu_download_align.argtypes = [vp, vp, vp, sz]
+    lib.lf_gpu_upload_extend_tasks.argtypes = [vp, vp, sz]
+    lib.lf_gpu_run_extend.argtypes = [vp]
+    lib.lf_gpu_download_extend.argtypes = [vp, vp]
+    lib.lf_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.lf_gpu_int32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    return lib
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+class PinnedArray:
+    """A numpy view over pinned host memory obtained from the library."""
+
+    def __init__(self, lib, nbytes: int):
+        self.lib, self.nbytes = lib, max(int(nbytes), 1)
+        self.ptr = lib.lf_gpu_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise LfGpuError("lf_gpu_host_alloc failed")
+        self.buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+
+    def view(self, dtype, count=None):
+        a = np.frombuffer(self.buf, dtype=dtype)
+        return a if count is None else a[:count]
+
+    def free(self):
+        if self.ptr:
+            self.lib.lf_gpu_host_free(self.ptr)
+            self.ptr = None
+
+
+def decode_ops(ops: np.ndarray, off: int, n: int) -> np.ndarray:
+    """Op codes (0 match, 1 insert, 2 delete, 3 mismatch) of one task out of the 2-bit stream."""
+    p = np.arange(off, off + n, dtype=np.int64)
+    return ((ops[p >> 2] >> ((p & 3) << 1).astype(np.uint8)) & 3).astype(np.uint8)
+
+
+class LfGpu:
+    """One context: the 2-bit reference resident on the device(s) + the batched alignment calls."""
+
+    def __init__(self, pac: np.ndarray, l_pac: int, devices=None, lib_path: str | None = None):
+        self.lib = load(lib_path)
+        self.pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        if len(self.pac) < l_pac // 4 + 1:
+            raise LfGpuError("pac shorter than l_pac/4+1 bytes")
+        self.ctx = C.c_void_p()
+        dev = None
+        ndev = 0
+        if devices:
+            dev = np.asarray(devices, dtype=np.int32)
+            ndev = len(dev)
+        rc = self.lib.lf_gpu_init(C.byref(self.ctx), _ptr(self.pac), int(l_pac), _ptr(dev) if ndev else None, ndev)
+        if rc != 0:
+            self.ctx = C.c_void_p()
+            raise LfGpuError(f"lf_gpu_init failed with status {rc} (no CUDA device? there is no CPU fallback)")
+        self._keep = []
+
+    def close(self):
+        if self.ctx:
+            self.lib.lf_gpu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise LfGpuError(f"{what} failed with status {rc}: {self.lib.lf_gpu_last_error(self.ctx).decode()}")
+
+    def _reads(self, bases: np.ndarray, offsets: np.ndarray) -> Reads:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep = [bases, offsets]
+        return Reads(_ptr(bases), _ptr(offsets), len(offsets) - 1)
+
+    # ---- one-call forms (host buffers in, host buffers out) ----
+    def align_batch(self, bases, offsets, tasks: np.ndarray):
+        tasks = np.ascontiguousarray(tasks, dtype=ALIGN_TASK)
+        n = len(tasks)
+        res = np.zeros(n, dtype=ALIGN_RESULT)
+        cap = self.lib.lf_gpu_ops_capacity(_ptr(tasks), n)
+        ops = np.zeros(cap, dtype=np.uint8)
+        r = self._reads(bases, offsets)
+        self._check(self.lib.lf_gpu_align_batch(self.ctx, C.byref(r), _ptr(tasks), n, _ptr(res), _ptr(ops), cap), "lf_gpu_align_batch")
+        return res, ops
+
+    def extend_batch(self, bases, offsets, tasks: np.ndarray):
+        tasks = np.ascontiguousarray(tasks, dtype=EXTEND_TASK)
+        n = len(tasks)
+        res = np.zeros(n, dtype=EXTEND_RESULT)
+        r = self._reads(bases, offsets)
+        self._check(self.lib.lf_gpu_extend_batch(self.ctx, C.byref(r), _ptr(tasks), n, _ptr(res)), "lf_gpu_extend_batch")
+        return res
+
+    # ---- phased forms (keep a batch resident in HBM) ----
+    def upload_reads(self, bases, offsets):
+        r = self._reads(bases, offsets)
+        self._check(self.lib.lf_gpu_upload_reads(self.ctx, C.byref(r)), "lf_gpu_upload_reads")
+
+    def upload_align_tasks(self, tasks: np.ndarray):
+        assert tasks.dtype == ALIGN_TASK and tasks.flags["C_CONTIGUOUS"]
+        self._check(self.lib.lf_gpu_upload_align_tasks(self.ctx, _ptr(tasks), len(tasks)), "lf_gpu_upload_align_tasks")
+
+    def run_align(self):
+        self._check(self.lib.lf_gpu_run_align(self.ctx), "lf_gpu_run_align")
+
+    def sync(self):
+        self._check(self.lib.lf_gpu_sync(self.ctx), "lf_gpu_sync")
+
+    def download_align(self, res: np.ndarray, ops: np.ndarray):
+        self._check(self.lib.lf_gpu_download_align(self.ctx, _ptr(res), _ptr(ops), ops.nbytes), "lf_gpu_download_align")
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self.lib.lf_gpu_get_stats(self.ctx, C.byref(s)), "lf_gpu_get_stats")
+        return s
+
+    def int32_peak(self, which: int) -> float:
+        v = C.c_double()
+        self._check(self.lib.lf_gpu_int32_peak(self.ctx, which, C.byref(v)), "lf_gpu_int32_peak")
+        return v.value

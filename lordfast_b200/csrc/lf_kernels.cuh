@@ -1,0 +1,775 @@
+/*
+ * lf_kernels.cuh -- device code of the batched alignment stage (sm_100a).
+ *
+ * Kernels (all integer / bit-vector work, no tensor cores -- nothing here is a contraction):
+ *   k_pack_reads      reads (ASCII) -> three bit planes per read (lo, hi, not-ACGT), warp ballot.
+ *                     Replaces edlib's transformSequences/buildPeq (lib/edlib/edlib.cpp:281, :1350):
+ *                     Eq for a target symbol is two LOP3s on the planes.
+ *   k_align_prep      per task: size class, sort key, op-slot and scratch sizes, validation.
+ *   k_myers_small<NW> thread-per-task Myers/Hyyro bit-vector NW/SHW for q <= 32*NW rows held in
+ *                     registers as one long word (carry chain instead of per-block hin/hout), with
+ *                     checkpoints every 16 columns and a windowed recompute for the traceback.
+ *                     Replaces edlibAlign for tasks below the 1 MiB rule (edlib.cpp:101-221,
+ *                     :657-858 distance, :872-1071 traceback).
+ *   k_myers_large     warp-per-task wavefront (lane = 32-row word, lane-skewed columns, hin/hout
+ *                     by __shfl_up) for everything else, including the Hirschberg recursion with
+ *                     edlib's split rule (edlib.cpp:1090-1143, :1161-1330).
+ *   k_ksw_extend      ksw_extend2 (lib/bwa/ksw.c:380-479) with its adaptive band, z-drop and
+ *                     stale-cell behaviour kept exactly; int32 scores.
+ *
+ * The results every kernel must reproduce are pure functions of the two strings (SURVEY.md
+ * Appendix A/B): Levenshtein distance; for SHW the first target prefix (incl. the empty one, -1)
+ * reaching the minimum; the path by canonical traceback (Up > Left > Diagonal from the bottom-right
+ * corner) below the size rule 20*ceil(q/64)*t + 8*t < 2^20, else split at column t/2 on the
+ * smallest row x in [1,q-1] with L[x]+R[x]==best (then x=0, then x=q).
+ *
+ * This header is compiled by nvcc into liblfgpu.so and, for debugging without a GPU, by g++ on top
+ * of tests/emu/cuda_emu.h (test-only; never shipped).
+ */
+#pragma once
+#include <stdint.h>
+#include "lf_gpu.h"
+
+#ifndef LF_EMU
+#define LF_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char lf_dyn_smem_raw[]; type *name = (type *)lf_dyn_smem_raw
+#else
+#define LF_DYN_SMEM(type, name) EMU_DYN_SMEM(type, name)
+#endif
+
+#define LF_FULL 0xffffffffu
+#define LF_K1_BLOCK 128   /* threads per block of k_myers_small */
+#define LF_K1_C 16        /* checkpoint interval in columns */
+#define LF_NSMALL 8       /* register-resident size classes */
+#define LF_CLS_LARGE 16   /* class id of k_myers_large tasks (small classes are 2*i + shw) */
+#define LF_CLS_BAD 17
+#define LF_NCLS 18
+#define LF_LARGE_STACK 96 /* Hirschberg stack entries per warp (depth <= log2(t)+2) */
+
+__host__ __device__ __forceinline__ int lf_small_nw(int i)
+{ /* words of 32 rows held in registers by size class i */
+    return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 3 : i == 3 ? 4 : i == 4 ? 6 : i == 5 ? 8 : i == 6 ? 12 : 16;
+}
+__host__ __device__ __forceinline__ int lf_small_class(uint32_t nwords)
+{
+    return nwords <= 1 ? 0 : nwords <= 2 ? 1 : nwords <= 3 ? 2 : nwords <= 4 ? 3 : nwords <= 6 ? 4 : nwords <= 8 ? 5 : nwords <= 12 ? 6 : nwords <= 16 ? 7 : -1;
+}
+/* edlib's choice between full traceback and Hirschberg, keyed to 64-bit blocks (edlib.cpp:1117-1119) */
+__host__ __device__ __forceinline__ bool lf_is_leaf(uint32_t q, uint32_t t)
+{
+    unsigned long long b64 = (q + 63u) / 64u;
+    return 20ull * b64 * t + 8ull * t < (1ull << 20) || t < 2;
+}
+__host__ __device__ __forceinline__ uint64_t lf_plane_word_off(uint64_t read_byte_off, uint32_t r)
+{ /* first plane word of read r: one zero pad word before and (at least) one after every read */
+    return (read_byte_off >> 5) + 3ull * r + 1ull;
+}
+__host__ __device__ __forceinline__ uint32_t lf_k1_ckpt_bytes(uint32_t t, int nw)
+{
+    uint32_t nck = t ? (t - 1) / LF_K1_C : 0;
+    return (nck * (uint32_t)nw * 8u + 15u) & ~15u;
+}
+
+/* Everything a kernel needs about one resident batch. */
+struct LfDev {
+    const uint8_t *pac; int64_t l_pac;
+    const uint8_t *bases; const uint64_t *read_off; uint32_t n_reads;
+    uint32_t *plo, *phi, *pnn;             /* read bit planes */
+    const lf_align_task *tasks; uint32_t n_tasks;
+    lf_align_result *res;
+    uint32_t *ops;                         /* 2-bit op stream, 16 ops per word */
+    const uint64_t *slot_end;              /* inclusive scan of per-task slot words */
+    const uint64_t *scr_off;               /* exclusive scan of per-task scratch bytes (small classes) */
+    uint8_t *scratch;
+};
+
+struct LfCounters { /* written by k_align_prep, read back by the host (one small D2H per batch) */
+    uint32_t hist[LF_NCLS];
+    uint32_t max_q, max_t;
+    unsigned long long max_planes, cells, word_columns, small_word_columns;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* sequence access                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t lf_tsym(const uint8_t *__restrict__ pac, int64_t l)
+{ /* _get_pac, src/BWT.cpp:310 */
+    return ((uint32_t)__ldg(pac + (l >> 2)) >> ((~(uint32_t)l & 3u) << 1)) & 3u;
+}
+
+struct LfQView { int64_t bit0; int dir; uint32_t comp; }; /* element k lives at plane bit bit0 + dir*k */
+struct LfTView { int64_t t0; int dir; };                   /* element k is pac base t0 + dir*k */
+
+__device__ __forceinline__ void lf_task_views(const LfDev &d, const lf_align_task &t, LfQView &qv, LfTView &tv)
+{
+    uint64_t ro = d.read_off[t.read_id];
+    int64_t L = (int64_t)(d.read_off[t.read_id + 1] - ro);
+    int rev1 = (t.flags & (LF_F_REVERSE_BOTH | LF_F_RC_QUERY)) != 0;
+    int64_t oi0 = rev1 ? (int64_t)t.q_off + t.q_len - 1 : (int64_t)t.q_off;
+    int odir = rev1 ? -1 : 1;
+    uint32_t comp = (t.flags & LF_F_RC_QUERY) ? 1u : 0u;
+    int64_t f0 = oi0;
+    int dir = odir;
+    if (t.flags & LF_F_READ_REV) { f0 = L - 1 - oi0; dir = -odir; comp ^= 1u; }
+    qv.bit0 = (int64_t)lf_plane_word_off(ro, t.read_id) * 32 + f0;
+    qv.dir = dir;
+    qv.comp = comp ? 0xffffffffu : 0u;
+    int revt = (t.flags & LF_F_REVERSE_BOTH) != 0;
+    tv.t0 = revt ? (int64_t)t.t_off + t.t_len - 1 : (int64_t)t.t_off;
+    tv.dir = revt ? -1 : 1;
+}
+__device__ __forceinline__ LfQView lf_qsub(const LfQView &v, int64_t off, int64_t len, bool reversed)
+{
+    LfQView r = v;
+    if (!reversed) r.bit0 = v.bit0 + v.dir * off;
+    else { r.bit0 = v.bit0 + v.dir * (off + len - 1); r.dir = -v.dir; }
+    return r;
+}
+__device__ __forceinline__ LfTView lf_tsub(const LfTView &v, int64_t off, int64_t len, bool reversed)
+{
+    LfTView r = v;
+    if (!reversed) r.t0 = v.t0 + v.dir * off;
+    else { r.t0 = v.t0 + v.dir * (off + len - 1); r.dir = -v.dir; }
+    return r;
+}
+__device__ __forceinline__ uint32_t lf_bits32(const uint32_t *__restrict__ p, int64_t B)
+{ /* plane bits [B, B+32) */
+    int64_t w = B >> 5;
+    return __funnelshift_r(__ldg(p + w), __ldg(p + w + 1), (uint32_t)B & 31u);
+}
+/* 32 query elements k0..k0+31 of a view as bit planes (bit j = element k0+j) */
+__device__ __forceinline__ void lf_q32(const LfDev &d, const LfQView &v, int64_t k0, uint32_t &lo, uint32_t &hi, uint32_t &nn)
+{
+    if (v.dir > 0) {
+        int64_t B = v.bit0 + k0;
+        lo = lf_bits32(d.plo, B); hi = lf_bits32(d.phi, B); nn = lf_bits32(d.pnn, B);
+    } else {
+        int64_t B = v.bit0 - k0 - 31;
+        lo = __brev(lf_bits32(d.plo, B)); hi = __brev(lf_bits32(d.phi, B)); nn = __brev(lf_bits32(d.pnn, B));
+    }
+    lo ^= v.comp; hi ^= v.comp;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_pack_reads                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+__global__ void k_pack_reads(LfDev d)
+{
+    uint32_t r = blockIdx.x;
+    if (r >= d.n_reads) return;
+    uint64_t b0 = d.read_off[r];
+    uint64_t L = d.read_off[r + 1] - b0;
+    uint64_t po = lf_plane_word_off(b0, r);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint64_t nw = (L + 31) >> 5;
+    for (uint64_t w = (uint64_t)warp; w < nw; w += (uint64_t)nwarps) {
+        uint64_t i = w * 32 + (uint64_t)lane;
+        uint32_t c = i < L ? d.bases[b0 + i] : 0u;
+        uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+        uint32_t lo = __ballot_sync(LF_FULL, code & 1u);
+        uint32_t hi = __ballot_sync(LF_FULL, (code >> 1) & 1u);
+        uint32_t nn = __ballot_sync(LF_FULL, code >> 2);
+        if (lane == 0) { d.plo[po + w] = lo; d.phi[po + w] = hi; d.pnn[po + w] = nn; }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_align_prep                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+__host__ __device__ __forceinline__ unsigned long long lf_large_planes_bytes(uint32_t q, uint32_t t)
+{ /* bytes of traceback planes the biggest leaf below (q,t) can need: 8 B per (32-row word x step) */
+    unsigned long long n = (q + 31u) / 32u;
+    unsigned long long full = n * ((unsigned long long)t + 32ull) * 8ull;
+    unsigned long long cap = (1ull << 20) + n * 256ull + 4096ull;
+    return full < cap ? full : cap;
+}
+
+__global__ void k_align_prep(LfDev d, uint32_t *keys, uint32_t *idx, uint32_t *slot_words, uint32_t *scr_bytes, LfCounters *cnt)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_tasks) return;
+    lf_align_task t = d.tasks[i];
+    int cls = LF_CLS_BAD;
+    uint32_t scr = 0, slot = 0;
+    bool ok = t.q_len >= 1 && t.t_len >= 1 && t.read_id < d.n_reads && t.mode <= LF_MODE_SHW;
+    if (ok) {
+        uint64_t L = d.read_off[t.read_id + 1] - d.read_off[t.read_id];
+        ok = (uint64_t)t.q_off + t.q_len <= L && (int64_t)t.t_off + (int64_t)t.t_len <= d.l_pac
+             && (uint64_t)t.q_len + t.t_len < (1ull << 31);
+    }
+    if (ok) {
+        uint32_t nwords = (t.q_len + 31u) >> 5;
+        int sc = lf_small_class(nwords);
+        if (sc >= 0 && lf_is_leaf(t.q_len, t.t_len)) {
+            cls = 2 * sc + (t.mode == LF_MODE_SHW ? 1 : 0);
+            scr = lf_k1_ckpt_bytes(t.t_len, lf_small_nw(sc));
+            atomicAdd(&cnt->small_word_columns, (unsigned long long)nwords * t.t_len);
+        } else {
+            cls = LF_CLS_LARGE;
+            atomicMax(&cnt->max_q, t.q_len);
+            atomicMax(&cnt->max_t, t.t_len);
+            atomicMax(&cnt->max_planes, lf_large_planes_bytes(t.q_len, t.t_len));
+        }
+        slot = (t.flags & LF_F_NO_PATH) ? 0u : (t.q_len + t.t_len + 15u) >> 4;
+        atomicAdd(&cnt->cells, (unsigned long long)t.q_len * t.t_len);
+        atomicAdd(&cnt->word_columns, (unsigned long long)nwords * t.t_len);
+    } else {
+        lf_align_result r; r.edit_distance = -1; r.end_location = -1; r.ops_off = 0; r.ops_len = 0; r.status = LF_ERR_BAD_ARG;
+        d.res[i] = r;
+    }
+    atomicAdd(&cnt->hist[cls], 1u);
+    uint32_t tt = t.t_len < 0x7ffffffu ? t.t_len : 0x7ffffffu;
+    keys[i] = ((uint32_t)cls << 27) | (0x7ffffffu - tt); /* class-major, long targets first */
+    idx[i] = i;
+    slot_words[i] = slot;
+    scr_bytes[i] = scr;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_myers_small: thread-per-task, NW words of 32 rows in registers                            */
+/* ------------------------------------------------------------------------------------------ */
+template <int NW>
+__device__ __forceinline__ void lf_add_chain(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW])
+{ /* s = a + b over a 32*NW-bit word */
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        unsigned long long x = (unsigned long long)a[w] + b[w] + c;
+        s[w] = (uint32_t)x;
+        c = (uint32_t)(x >> 32);
+    }
+}
+
+/* Advance the whole column by one target symbol (Myers 1999 / Hyyro 2003 recurrences on one long
+ * word; the per-block hin/hout of edlib's calculateBlock, edlib.cpp:335-370, become the add carry
+ * and the bits shifted between words).  STORE additionally writes, for the WIN words starting at
+ * wtop, the two traceback planes of this column: op = 1 (up) if Pv', else 2 (left) if Ph, else
+ * 0/3 by Eq -- plane0 = low op bit, plane1 = high op bit. */
+template <int NW, bool SHW, bool STORE, int WIN>
+__device__ __forceinline__ void lf_k1_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&qlo)[NW],
+                                             const uint32_t (&qhi)[NW], const uint32_t (&qnn)[NW], uint32_t sym, int &score,
+                                             int wl, uint32_t bl, uint32_t *sm, int wtop)
+{
+    const uint32_t slo = 0u - (sym & 1u), shi = 0u - (sym >> 1);
+    uint32_t Eq[NW], a[NW], sum[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        Eq[w] = ~((qlo[w] ^ slo) | (qhi[w] ^ shi) | qnn[w]);
+        a[w] = Eq[w] & Pv[w];
+    }
+    lf_add_chain<NW>(a, Pv, sum);
+    uint32_t phc = 1u, mhc = 0u; /* row 0 of a global alignment grows by one per column */
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        uint32_t Xh = (sum[w] ^ Pv[w]) | Eq[w];
+        uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
+        uint32_t Mh = Pv[w] & Xh;
+        uint32_t Xv = Eq[w] | Mv[w];
+        if (SHW) { if (w == wl) score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u); }
+        uint32_t Phs = (Ph << 1) | phc, Mhs = (Mh << 1) | mhc;
+        phc = Ph >> 31; mhc = Mh >> 31;
+        uint32_t nPv = Mhs | ~(Xv | Phs);
+        uint32_t nMv = Phs & Xv;
+        if (STORE) {
+            int wi = w - wtop;
+            if (wi >= 0 && wi < WIN) {
+                uint32_t diagx = ~(nPv | Ph | Eq[w]);              /* diagonal step over a mismatch */
+                sm[(wi * 2 + 0) * LF_K1_BLOCK] = nPv | diagx;       /* ops 1, 3 */
+                sm[(wi * 2 + 1) * LF_K1_BLOCK] = (~nPv & Ph) | diagx; /* ops 2, 3 */
+            }
+        }
+        Pv[w] = nPv; Mv[w] = nMv;
+    }
+}
+
+template <int NW, bool SHW>
+__global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count)
+{
+    constexpr int WIN = NW < 2 ? 1 : 2;
+    constexpr int C = LF_K1_C;
+    LF_DYN_SMEM(uint32_t, smem); /* [C][WIN][2][LF_K1_BLOCK] */
+    const uint32_t tid = threadIdx.x;
+    const uint32_t gi = blockIdx.x * LF_K1_BLOCK + tid;
+    if (gi >= count) return;
+    const uint32_t ti = order[first + gi];
+    const lf_align_task task = d.tasks[ti];
+    const int q = (int)task.q_len, t = (int)task.t_len;
+    LfQView qv; LfTView tv;
+    lf_task_views(d, task, qv, tv);
+
+    uint32_t qlo[NW], qhi[NW], qnn[NW], Pv[NW], Mv[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        if (w * 32 < q) lf_q32(d, qv, (int64_t)w * 32, qlo[w], qhi[w], qnn[w]);
+        else { qlo[w] = 0; qhi[w] = 0; qnn[w] = 0xffffffffu; }
+        Pv[w] = 0xffffffffu; Mv[w] = 0u;
+    }
+    const int wl = (q - 1) >> 5;
+    const uint32_t bl = (uint32_t)(q - 1) & 31u;
+    int score = q, best = q, bestc = -1;
+    uint2 *ck = (uint2 *)(d.scratch + d.scr_off[ti]);
+
+    /* ---- forward pass: distance (+ first best prefix for SHW), checkpoints every C columns ---- */
+    int64_t tpos = tv.t0;
+    for (int c = 0; c < t; c++) {
+        if ((c & (C - 1)) == 0 && c) {
+            uint2 *dst = ck + (size_t)(c / C - 1) * NW;
+#pragma unroll
+            for (int w = 0; w < NW; w++) dst[w] = make_uint2(Pv[w], Mv[w]);
+        }
+        uint32_t sym = lf_tsym(d.pac, tpos);
+        tpos += tv.dir;
+        lf_k1_column<NW, SHW, false, WIN>(Pv, Mv, qlo, qhi, qnn, sym, score, wl, bl, nullptr, 0);
+        if (SHW) { if (score < best) { best = score; bestc = c; } }
+    }
+    int ed, end;
+    if (SHW) { ed = best; end = bestc; }
+    else {
+        ed = t;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            uint32_t m = w < wl ? 0xffffffffu : w == wl ? (0xffffffffu >> (31u - bl)) : 0u;
+            ed += __popc(Pv[w] & m) - __popc(Mv[w] & m);
+        }
+        end = t - 1;
+    }
+    lf_align_result r;
+    r.edit_distance = ed; r.end_location = end; r.status = 0;
+    const uint64_t slot_hi = d.slot_end[ti] * 16ull; /* one past the last op position of the slot */
+    if (task.flags & LF_F_NO_PATH) { r.ops_off = slot_hi; r.ops_len = 0; d.res[ti] = r; return; }
+
+    /* ---- traceback: recompute 16-column blocks from their checkpoint, keep a WIN-word window of
+     *      the op planes in shared memory, walk Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
+    uint64_t p = slot_hi;
+    uint32_t cur = 0;
+#define LF_EMIT(op) do { --p; cur |= (uint32_t)(op) << (((uint32_t)p & 15u) << 1); if (((uint32_t)p & 15u) == 0u) { d.ops[p >> 4] = cur; cur = 0; } } while (0)
+    int i = q, j = end + 1;
+    uint32_t *smt = smem + tid;
+    while (i > 0 && j > 0) {
+        const int c1 = j, c0 = ((j - 1) / C) * C;
+        const int whi = (i - 1) >> 5;
+        const int wtop = whi - WIN + 1 > 0 ? whi - WIN + 1 : 0;
+        if (c0 == 0) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) { Pv[w] = 0xffffffffu; Mv[w] = 0u; }
+        } else {
+            const uint2 *src = ck + (size_t)(c0 / C - 1) * NW;
+#pragma unroll
+            for (int w = 0; w < NW; w++) { uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; }
+        }
+        tpos = tv.t0 + (int64_t)tv.dir * c0;
+        for (int c = c0; c < c1; c++) {
+            uint32_t sym = lf_tsym(d.pac, tpos);
+            tpos += tv.dir;
+            lf_k1_column<NW, false, true, WIN>(Pv, Mv, qlo, qhi, qnn, sym, score, wl, bl, smt + (size_t)(c - c0) * WIN * 2 * LF_K1_BLOCK, wtop);
+        }
+        const int rowmin = wtop * 32;
+        while (i > 0 && j > c0 && (i - 1) >= rowmin) {
+            const int rr = i - 1;
+            const uint32_t *cell = smt + (size_t)(((j - 1 - c0) * WIN + ((rr >> 5) - wtop)) * 2) * LF_K1_BLOCK;
+            uint32_t b = (uint32_t)rr & 31u;
+            uint32_t op = ((cell[0] >> b) & 1u) | (((cell[LF_K1_BLOCK] >> b) & 1u) << 1);
+            LF_EMIT(op);
+            i -= (op != 2u);
+            j -= (op != 1u);
+        }
+    }
+    while (i > 0) { LF_EMIT(1u); i--; } /* left column: the rest of the query is inserted   */
+    while (j > 0) { LF_EMIT(2u); j--; } /* top row: the rest of the target is deleted        */
+    if ((uint32_t)p & 15u) d.ops[p >> 4] = cur;
+#undef LF_EMIT
+    r.ops_off = p; r.ops_len = (uint32_t)(slot_hi - p);
+    d.res[ti] = r;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_myers_large: warp-per-task wavefront + Hirschberg                                         */
+/* ------------------------------------------------------------------------------------------ */
+struct LfLargeCfg {
+    uint8_t *base;              /* scratch of all warp slots */
+    unsigned long long stride;  /* bytes per warp slot */
+    unsigned long long off_hb, off_L, off_R, off_opsb, off_stack; /* planes start at 0 */
+    uint32_t *queue;            /* work counter */
+};
+
+enum { LF_PASS_STORE = 1, LF_PASS_SHW = 2, LF_PASS_COL = 4 };
+
+struct LfPassOut { int ed, best, bestc; };
+
+/* One wavefront pass over (query view, target view).  Lane l of strip s owns rows 32*(32s+l)..+31
+ * and at step k works on column k-l; hout and the target symbol travel to lane l+1 by __shfl_up.
+ * Strips of 32 words run one after the other, chained through hb[] (hout below the strip's last
+ * row for every column).  Returns D(ql, tl) in .ed; with LF_PASS_SHW also the minimum of the last
+ * row and the first column reaching it; LF_PASS_COL writes D(x, tl), x = 0..ql, to col[];
+ * LF_PASS_STORE writes the traceback planes: uint2 at planes[strip_base + step*nv + lane]. */
+__device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
+                                                  uint2 *planes, int8_t *hb, int32_t *col)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = (ql + 31) >> 5;
+    const int S = (n + 31) >> 5;
+    const int wl = (ql - 1) >> 5;
+    const uint32_t bl = (uint32_t)(ql - 1) & 31u;
+    int score = ql, best = ql, bestc = -1; /* tracked by the lane owning row ql-1 */
+    int colbase = tl;                      /* D(32*w, tl) carried across strips */
+    unsigned long long sbase = 0;
+    if ((flags & LF_PASS_COL) && lane == 0) col[0] = tl;
+    for (int s = 0; s < S; s++) {
+        const int w = s * 32 + lane;
+        const int nv = n - s * 32 < 32 ? n - s * 32 : 32;
+        const bool valid = lane < nv;
+        uint32_t lo = 0, hi = 0, nn = 0xffffffffu;
+        if (valid) lf_q32(d, qv, (int64_t)w * 32, lo, hi, nn);
+        uint32_t Pv = 0xffffffffu, Mv = 0u;
+        uint32_t pay = 0; /* (hout+1) | sym<<2 produced by this lane in the previous step */
+        const int nsteps = tl + nv - 1;
+        for (int step = 0; step < nsteps; step++) {
+            uint32_t in = __shfl_up_sync(LF_FULL, pay, 1);
+            uint32_t sym; int hin;
+            if (lane == 0) {
+                sym = step < tl ? lf_tsym(d.pac, tv.t0 + (int64_t)tv.dir * step) : 0u;
+                hin = (s == 0 || step >= tl) ? 1 : (int)hb[step];
+            } else { sym = in >> 2; hin = (int)(in & 3u) - 1; }
+            const int c = step - lane;
+            const bool act = valid && c >= 0 && c < tl;
+            int hout = 0;
+            if (act) {
+                const uint32_t slo = 0u - (sym & 1u), shi = 0u - (sym >> 1);
+                const uint32_t Eq = ~((lo ^ slo) | (hi ^ shi) | nn);
+                const uint32_t hneg = hin < 0 ? 1u : 0u, hpos = hin > 0 ? 1u : 0u;
+                const uint32_t Xv = Eq | Mv;
+                const uint32_t Eq2 = Eq | hneg;
+                const uint32_t Xh = (((Eq2 & Pv) + Pv) ^ Pv) | Eq2;
+                const uint32_t Ph = Mv | ~(Xh | Pv);
+                const uint32_t Mh = Pv & Xh;
+                hout = (int)(Ph >> 31) - (int)(Mh >> 31);
+                if ((flags & LF_PASS_SHW) && w == wl) {
+                    score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u);
+                    if (score < best) { best = score; bestc = c; }
+                }
+                const uint32_t Phs = (Ph << 1) | hpos, Mhs = (Mh << 1) | hneg;
+                const uint32_t nPv = Mhs | ~(Xv | Phs);
+                const uint32_t nMv = Phs & Xv;
+                if (flags & LF_PASS_STORE) {
+                    const uint32_t diagx = ~(nPv | Ph | Eq);
+                    planes[sbase + (unsigned long long)step * nv + lane] = make_uint2(nPv | diagx, (~nPv & Ph) | diagx);
+                }
+                Pv = nPv; Mv = nMv;
+                if (lane == nv - 1 && s + 1 < S) hb[c] = (int8_t)hout;
+            }
+            pay = (uint32_t)(hout + 1) | (sym << 2);
+        }
+        sbase += (unsigned long long)nsteps * nv;
+        /* last column of this strip: vertical deltas -> absolute values */
+        uint32_t m = !valid ? 0u : w < wl ? 0xffffffffu : w == wl ? (0xffffffffu >> (31u - bl)) : 0u;
+        int cnt = __popc(Pv & m) - __popc(Mv & m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(LF_FULL, incl, o); if (lane >= o) incl += v; }
+        if (flags & LF_PASS_COL) {
+            if (valid) {
+                int v = colbase + incl - cnt;
+                int rows = ql - w * 32 < 32 ? ql - w * 32 : 32;
+                for (int b = 0; b < rows; b++) { v += (int)((Pv >> b) & 1u) - (int)((Mv >> b) & 1u); col[w * 32 + b + 1] = v; }
+            }
+        }
+        colbase += __shfl_sync(LF_FULL, incl, 31);
+        __syncwarp();
+    }
+    LfPassOut o;
+    o.ed = colbase;
+    const int owner = wl & 31;
+    o.best = __shfl_sync(LF_FULL, best, owner);
+    o.bestc = __shfl_sync(LF_FULL, bestc, owner);
+    return o;
+}
+
+/* Canonical traceback over stored planes; every lane walks the same path (uniform loads), lane 0
+ * writes one byte per op right-aligned below `hi_pos`.  Returns the number of ops. */
+__device__ __forceinline__ int lf_large_traceback(const uint2 *planes, int ql, int tl, uint8_t *opsb, long long hi_pos)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = (ql + 31) >> 5;
+    long long p = hi_pos;
+    int i = ql, j = tl;
+    while (i > 0 && j > 0) {
+        const int rr = i - 1, w = rr >> 5, s = w >> 5, l = w & 31;
+        const int nv = n - s * 32 < 32 ? n - s * 32 : 32;
+        const unsigned long long sb = (unsigned long long)s * (unsigned long long)(tl + 31) * 32ull;
+        const uint2 v = planes[sb + (unsigned long long)(j - 1 + l) * nv + l];
+        const uint32_t b = (uint32_t)rr & 31u;
+        const uint32_t op = ((v.x >> b) & 1u) | (((v.y >> b) & 1u) << 1);
+        --p;
+        if (lane == 0) opsb[p] = (uint8_t)op;
+        i -= (op != 2u);
+        j -= (op != 1u);
+    }
+    while (i > 0) { --p; if (lane == 0) opsb[p] = 1; i--; }
+    while (j > 0) { --p; if (lane == 0) opsb[p] = 2; j--; }
+    __syncwarp();
+    return (int)(hi_pos - p);
+}
+
+__device__ __forceinline__ void lf_warp_fill(uint8_t *dst, int n, uint8_t v)
+{
+    for (int k = threadIdx.x & 31; k < n; k += 32) dst[k] = v;
+    __syncwarp();
+}
+__device__ __forceinline__ void lf_warp_move_down(uint8_t *buf, long long dst, long long src, int n)
+{ /* dst <= src; chunks of 32 are read by every lane before any lane writes */
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < n; k += 32) {
+        uint8_t v = (k + lane < n) ? buf[src + k + lane] : 0;
+        __syncwarp();
+        if (k + lane < n) buf[dst + k + lane] = v;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const LfLargeCfg &cfg, uint8_t *scr)
+{
+    const int lane = threadIdx.x & 31;
+    const lf_align_task task = d.tasks[ti];
+    const int q = (int)task.q_len, t = (int)task.t_len;
+    LfQView qv; LfTView tv;
+    lf_task_views(d, task, qv, tv);
+    uint2 *planes = (uint2 *)scr;
+    int8_t *hb = (int8_t *)(scr + cfg.off_hb);
+    int32_t *Lc = (int32_t *)(scr + cfg.off_L), *Rc = (int32_t *)(scr + cfg.off_R);
+    uint8_t *opsb = scr + cfg.off_opsb;
+    int32_t *stack = (int32_t *)(scr + cfg.off_stack);
+
+    const bool shw = task.mode == LF_MODE_SHW;
+    const bool want = !(task.flags & LF_F_NO_PATH);
+    int ed, end;
+    bool stored = false; /* planes of the whole task are already in `planes` */
+    if (!shw && want && lf_is_leaf((uint32_t)q, (uint32_t)t)) {
+        LfPassOut o = lf_wave_pass(d, qv, q, tv, t, LF_PASS_STORE, planes, hb, nullptr);
+        ed = o.ed; end = t - 1; stored = true;
+    } else {
+        LfPassOut o = lf_wave_pass(d, qv, q, tv, t, shw ? LF_PASS_SHW : 0, planes, hb, nullptr);
+        if (shw) { ed = o.best; end = o.bestc; } else { ed = o.ed; end = t - 1; }
+    }
+    const uint64_t slot_hi = d.slot_end[ti] * 16ull;
+    lf_align_result r;
+    r.edit_distance = ed; r.end_location = end; r.status = 0; r.ops_len = 0; r.ops_off = slot_hi;
+    if (!want) { if (lane == 0) d.res[ti] = r; return; }
+
+    /* ---- path: obtainAlignment (edlib.cpp:1090-1143) with an explicit stack ---- */
+    const int teff = end + 1;
+    long long outpos = 0;
+    int sp = 0;
+    if (lane == 0) { stack[0] = 0; stack[1] = q; stack[2] = 0; stack[3] = teff; stack[4] = ed; }
+    sp = 1;
+    __syncwarp();
+    int status = 0;
+    while (sp > 0) {
+        sp--;
+        const int qo = stack[sp * 5 + 0], ql = stack[sp * 5 + 1], to = stack[sp * 5 + 2], tl = stack[sp * 5 + 3], best = stack[sp * 5 + 4];
+        __syncwarp();
+        if (ql == 0) { lf_warp_fill(opsb + outpos, tl, 2); outpos += tl; continue; }
+        if (tl == 0) { lf_warp_fill(opsb + outpos, ql, 1); outpos += ql; continue; }
+        if (lf_is_leaf((uint32_t)ql, (uint32_t)tl)) {
+            if (!stored) {
+                LfQView sq = lf_qsub(qv, qo, ql, false);
+                LfTView st = lf_tsub(tv, to, tl, false);
+                lf_wave_pass(d, sq, ql, st, tl, LF_PASS_STORE, planes, hb, nullptr);
+                __syncwarp();
+            }
+            const long long hi_pos = (long long)qo + to + ql + tl;
+            const int nops = lf_large_traceback(planes, ql, tl, opsb, hi_pos);
+            lf_warp_move_down(opsb, outpos, hi_pos - nops, nops);
+            outpos += nops;
+            stored = false;
+            continue;
+        }
+        /* split at column tl/2 (edlib.cpp:1176-1196) */
+        const int lw = tl / 2, rw = tl - lw;
+        lf_wave_pass(d, lf_qsub(qv, qo, ql, false), ql, lf_tsub(tv, to, lw, false), lw, LF_PASS_COL, planes, hb, Lc);
+        lf_wave_pass(d, lf_qsub(qv, qo, ql, true), ql, lf_tsub(tv, to + lw, rw, true), rw, LF_PASS_COL, planes, hb, Rc);
+        __syncwarp();
+        /* smallest interior row, then the top boundary, then the bottom one (edlib.cpp:1257-1289) */
+        int x = -1;
+        for (int x0 = 1; x0 <= ql - 1 && x < 0; x0 += 32) {
+            const int xx = x0 + lane;
+            const bool hit = xx <= ql - 1 && Lc[xx] + Rc[ql - xx] == best;
+            const uint32_t bal = __ballot_sync(LF_FULL, hit);
+            if (bal) x = x0 + __ffs((int)bal) - 1;
+        }
+        int ls, rs;
+        if (x >= 0) { ls = Lc[x]; rs = Rc[ql - x]; }
+        else if (lw + Rc[ql] == best) { x = 0; ls = lw; rs = Rc[ql]; }
+        else if (Lc[ql] + rw == best) { x = ql; ls = Lc[ql]; rs = rw; }
+        else { status = LF_ERR_CUDA; break; } /* cannot happen for a correct distance */
+        __syncwarp();
+        if (sp + 2 > LF_LARGE_STACK) { status = LF_ERR_NOMEM; break; }
+        if (lane == 0) {
+            stack[sp * 5 + 0] = qo + x; stack[sp * 5 + 1] = ql - x; stack[sp * 5 + 2] = to + lw; stack[sp * 5 + 3] = rw; stack[sp * 5 + 4] = rs;
+            stack[sp * 5 + 5] = qo; stack[sp * 5 + 6] = x; stack[sp * 5 + 7] = to; stack[sp * 5 + 8] = lw; stack[sp * 5 + 9] = ls;
+        }
+        sp += 2;
+        __syncwarp();
+    }
+    /* pack one byte per op into the 2-bit stream, left-aligned in the task's slot */
+    const uint64_t slot_lo_w = d.slot_end[ti] - ((uint32_t)(q + t + 15) >> 4);
+    const long long nwords = (outpos + 15) >> 4;
+    for (long long wi = lane; wi < nwords; wi += 32) {
+        uint32_t word = 0;
+        for (int k = 0; k < 16; k++) { long long pp = wi * 16 + k; if (pp < outpos) word |= (uint32_t)opsb[pp] << (2 * k); }
+        d.ops[slot_lo_w + (uint64_t)wi] = word;
+    }
+    r.ops_off = slot_lo_w * 16ull; r.ops_len = (uint32_t)outpos; r.status = status;
+    if (lane == 0) d.res[ti] = r;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) k_myers_large(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, LfLargeCfg cfg)
+{
+    const int lane = threadIdx.x & 31;
+    uint8_t *scr = cfg.base + (unsigned long long)blockIdx.x * cfg.stride;
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(cfg.queue, 1u);
+        k = __shfl_sync(LF_FULL, k, 0);
+        if (k >= count) break;
+        lf_large_task(d, order[first + k], cfg, scr);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_ksw_extend: ksw_extend2 (lib/bwa/ksw.c:380-479), one thread per task                      */
+/* ------------------------------------------------------------------------------------------ */
+struct LfExtDev {
+    const uint8_t *pac; int64_t l_pac;
+    const uint8_t *bases; const uint64_t *read_off; uint32_t n_reads;
+    const lf_extend_task *tasks; uint32_t n_tasks;
+    lf_extend_result *res;
+    const uint64_t *scr_off; /* exclusive scan of (q_len+1) */
+    int2 *scratch;           /* {H diagonal feed, E} per query column */
+};
+
+__device__ __forceinline__ uint32_t lf_char2int(uint32_t c)
+{ /* src/LordFAST.cpp:158-164 */
+    return (c == 'A' || c == 'a') ? 0u : (c == 'C' || c == 'c') ? 1u : (c == 'G' || c == 'g') ? 2u : (c == 'T' || c == 't') ? 3u : 4u;
+}
+
+__global__ void k_extend_prep(LfExtDev d, uint32_t *scr_items)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_tasks) return;
+    lf_extend_task t = d.tasks[i];
+    bool ok = t.q_len >= 1 && t.t_len >= 1 && t.read_id < d.n_reads && t.h0 > 0 && t.e_del > 0 && t.e_ins > 0;
+    if (ok) {
+        uint64_t L = d.read_off[t.read_id + 1] - d.read_off[t.read_id];
+        ok = (uint64_t)t.q_off + t.q_len <= L && (int64_t)t.t_off + (int64_t)t.t_len <= d.l_pac;
+    }
+    scr_items[i] = ok ? t.q_len + 1u : 0u;
+}
+
+__global__ void k_ksw_extend(LfExtDev d)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_tasks) return;
+    const lf_extend_task t = d.tasks[i];
+    lf_extend_result out; out.score = -1; out.qle = 0; out.tle = 0;
+    const uint64_t so = d.scr_off[i];
+    if (d.scr_off[i + 1] == so) { d.res[i] = out; return; } /* rejected by k_extend_prep */
+    int2 *eh = d.scratch + so;
+    const int qlen = (int)t.q_len, tlen = (int)t.t_len;
+    /* query byte k: oriented index -> stored read index */
+    const uint64_t ro = d.read_off[t.read_id];
+    const int64_t L = (int64_t)(d.read_off[t.read_id + 1] - ro);
+    const int rev1 = (t.flags & LF_F_REVERSE_BOTH) != 0;
+    int64_t f0 = rev1 ? (int64_t)t.q_off + qlen - 1 : (int64_t)t.q_off;
+    int qdir = rev1 ? -1 : 1;
+    uint32_t comp = 0;
+    if (t.flags & LF_F_READ_REV) { f0 = L - 1 - f0; qdir = -qdir; comp = 1; }
+    const int64_t t0 = rev1 ? (int64_t)t.t_off + tlen - 1 : (int64_t)t.t_off;
+    const int tdir = rev1 ? -1 : 1;
+    const int smatch = 2, smis = t.matrix == LF_MAT_DEFAULT ? -5 : -16;
+    const int o_del = t.o_del, e_del = t.e_del, o_ins = t.o_ins, e_ins = t.e_ins, h0 = t.h0, zdrop = t.zdrop;
+    const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    int w = t.w;
+    /* first row (ksw.c:395-397); cells not reached stay zero like the reference's calloc */
+    for (int j = 0; j <= qlen; j++) eh[j] = int2{0, 0};
+    eh[0].x = h0;
+    if (qlen >= 1) eh[1].x = h0 > oe_ins ? h0 - oe_ins : 0;
+    for (int j = 2; j <= qlen && eh[j - 1].x > e_ins; j++) eh[j].x = eh[j - 1].x - e_ins;
+    /* band clamp (ksw.c:399-407), max matrix entry is the match score */
+    {
+        int lim = (int)((double)(qlen * smatch - o_ins) / e_ins + 1.);
+        lim = lim > 1 ? lim : 1; w = w < lim ? w : lim;
+        lim = (int)((double)(qlen * smatch - o_del) / e_del + 1.);
+        lim = lim > 1 ? lim : 1; w = w < lim ? w : lim;
+    }
+    int best = h0, best_i = -1, best_j = -1, beg = 0, end = qlen;
+    for (int r = 0; r < tlen; r++) {
+        int f = 0, left, rowmax = 0, rowmax_j = -1;
+        const uint32_t tc = lf_tsym(d.pac, t0 + (int64_t)tdir * r);
+        if (beg < r - w) beg = r - w;
+        if (end > r + w + 1) end = r + w + 1;
+        if (end > qlen) end = qlen;
+        if (beg == 0) { left = h0 - (o_del + e_del * (r + 1)); if (left < 0) left = 0; } else left = 0;
+        int j;
+        for (j = beg; j < end; j++) {
+            int2 c = eh[j];
+            uint32_t qc = lf_char2int(d.bases[ro + (uint64_t)(f0 + (int64_t)qdir * j)]);
+            if (comp && qc < 4u) qc = 3u - qc;
+            int M = c.x, e = c.y;
+            const int sc = qc > 3u ? 0 : (qc == tc ? smatch : smis);
+            M = M ? M + sc : 0;
+            int h = M > e ? M : e;
+            h = h > f ? h : f;
+            eh[j].x = left;
+            left = h;
+            rowmax_j = rowmax > h ? rowmax_j : j; /* ties go to the later column (ksw.c:437) */
+            rowmax = rowmax > h ? rowmax : h;
+            int tt = M - oe_del; tt = tt > 0 ? tt : 0;
+            e -= e_del; e = e > tt ? e : tt;
+            eh[j].y = e;
+            tt = M - oe_ins; tt = tt > 0 ? tt : 0;
+            f -= e_ins; f = f > tt ? f : tt;
+        }
+        eh[end] = int2{left, 0};
+        if (rowmax == 0) break;
+        if (rowmax > best) { best = rowmax; best_i = r; best_j = rowmax_j; }
+        else if (zdrop > 0) {
+            const int di = r - best_i, dj = rowmax_j - best_j;
+            if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) break; }
+            else { if (best - rowmax - (dj - di) * e_ins > zdrop) break; }
+        }
+        for (j = beg; j < end && eh[j].x == 0 && eh[j].y == 0; j++) {}
+        beg = j;
+        for (j = end; j >= beg && eh[j].x == 0 && eh[j].y == 0; j--) {}
+        end = j + 2 < qlen ? j + 2 : qlen;
+    }
+    out.score = best; out.qle = best_j + 1; out.tle = best_i + 1;
+    d.res[i] = out;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* INT32 issue-rate microbenchmark (roofline denominator; MEASURED_PEAKS.json has no INT32 figure) */
+/* ------------------------------------------------------------------------------------------ */
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_int32_peak(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = seed + threadIdx.x * 8u + (uint32_t)k;
+    uint32_t m = seed ^ 0x9e3779b9u, n = seed * 3u + 1u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (WHICH == 0) a[k] = (a[k] & m) ^ n;                               /* LOP3 */
+                else if (WHICH == 1) a[k] = a[k] + m + n;                            /* IADD3 */
+                else if (WHICH == 2) { if (k & 1) a[k] = (a[k] & m) ^ n; else a[k] = a[k] + m + n; }
+                else { if (k & 1) a[k] = (a[k] & m) ^ n; else a[k] = a[k] * m + n; } /* LOP3 + IMAD */
+            }
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x ^= a[k];
+    if (x == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = x; /* keeps the loop alive */
+}

@@ -1,0 +1,462 @@
+/*
+ * lf_pipeline.inl -- host side of liblfgpu.so: the C ABI of include/lf_gpu.h on top of the kernels
+ * in lf_kernels.cuh.  Included by lfgpu.cu (nvcc, the product) and by tests/emu/lfgpu_emu.cpp
+ * (g++ + fiber emulator, test-only) so that the orchestration below is exercised in both.
+ *
+ * Per batch and per device:
+ *   upload   reads (bytes + offsets) and tasks -> HBM; k_pack_reads builds the bit planes
+ *   run      k_align_prep -> radix sort by (size class, target length) -> scans for op slots and
+ *            checkpoint scratch -> one small D2H of the class histogram -> k_myers_small<NW,SHW>
+ *            per non-empty class -> k_myers_large on a persistent grid of warp slots
+ *   download results (24 B / task) and the 2-bit op stream
+ * A batch is split over the context's devices by contiguous task ranges; the reference and the
+ * reads are replicated, no collective is involved.
+ */
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "lf_gpu.h"
+#include "lf_backend.h"
+#include "lf_kernels.cuh"
+
+struct DevState {
+    int dev = 0;
+    lfb_stream stream = 0;
+    lfb_event ev[4] = {};
+    LfbBuf pac, bases, read_off, plo, phi, pnn;
+    LfbBuf tasks, res, ops, keys, keys2, idx, idx2, slot_words, scr_bytes, slot_end, scr_off, scratch, large_scr, counters, queue;
+    LfbBuf etasks, eres, escr_items, escr_off, escr;
+    LfbTemp tmp;
+    void *pinned = nullptr; /* LfCounters + two totals */
+    uint32_t n_reads = 0; uint64_t total_bases = 0;
+    size_t task_first = 0; uint32_t n_tasks = 0; uint64_t ops_words = 0;
+    size_t etask_first = 0; uint32_t n_etasks = 0;
+    bool ran = false;
+};
+
+struct lf_gpu_ctx {
+    std::vector<DevState> devs;
+    int64_t l_pac = 0;
+    std::string err;
+    lf_gpu_stats stats = {};
+};
+
+namespace {
+
+struct HostTotals { LfCounters cnt; unsigned long long slot_total, scr_total; };
+
+#ifndef LF_EMU
+int set_dev(const DevState &d) { return cudaSetDevice(d.dev) == cudaSuccess ? 0 : -2; }
+#else
+int set_dev(const DevState &) { return 0; }
+#endif
+
+int fail(lf_gpu_ctx *c, int code, const char *msg)
+{
+    if (c) c->err = std::string(msg) + (lfb_errbuf[0] ? std::string(": ") + lfb_errbuf : std::string());
+    return code;
+}
+#define LF_TRY(expr) do { int rc_ = (expr); if (rc_ != 0) return fail(ctx, rc_ == -5 ? LF_ERR_NOMEM : LF_ERR_CUDA, #expr); } while (0)
+
+LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
+{
+    LfDev v;
+    v.pac = d.pac.as<uint8_t>(); v.l_pac = ctx->l_pac;
+    v.bases = d.bases.as<uint8_t>(); v.read_off = d.read_off.as<uint64_t>(); v.n_reads = d.n_reads;
+    v.plo = d.plo.as<uint32_t>(); v.phi = d.phi.as<uint32_t>(); v.pnn = d.pnn.as<uint32_t>();
+    v.tasks = d.tasks.as<lf_align_task>(); v.n_tasks = d.n_tasks;
+    v.res = d.res.as<lf_align_result>();
+    v.ops = d.ops.as<uint32_t>();
+    v.slot_end = d.slot_end.as<uint64_t>();
+    v.scr_off = d.scr_off.as<uint64_t>();
+    v.scratch = d.scratch.as<uint8_t>();
+    return v;
+}
+
+template <int CI, bool SHW>
+void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s)
+{
+    constexpr int NW = CI == 0 ? 1 : CI == 1 ? 2 : CI == 2 ? 3 : CI == 3 ? 4 : CI == 4 ? 6 : CI == 5 ? 8 : CI == 6 ? 12 : 16;
+    constexpr int WIN = NW < 2 ? 1 : 2;
+    const size_t smem = (size_t)LF_K1_C * WIN * 2 * LF_K1_BLOCK * sizeof(uint32_t);
+    const uint32_t grid = (count + LF_K1_BLOCK - 1) / LF_K1_BLOCK;
+    auto kern = k_myers_small<NW, SHW>;
+    LFB_LAUNCH(kern, grid, LF_K1_BLOCK, smem, s, v, order, first, count);
+}
+
+void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s)
+{
+    switch (cls) {
+    case 0: launch_small<0, false>(v, order, first, count, s); break;  case 1: launch_small<0, true>(v, order, first, count, s); break;
+    case 2: launch_small<1, false>(v, order, first, count, s); break;  case 3: launch_small<1, true>(v, order, first, count, s); break;
+    case 4: launch_small<2, false>(v, order, first, count, s); break;  case 5: launch_small<2, true>(v, order, first, count, s); break;
+    case 6: launch_small<3, false>(v, order, first, count, s); break;  case 7: launch_small<3, true>(v, order, first, count, s); break;
+    case 8: launch_small<4, false>(v, order, first, count, s); break;  case 9: launch_small<4, true>(v, order, first, count, s); break;
+    case 10: launch_small<5, false>(v, order, first, count, s); break; case 11: launch_small<5, true>(v, order, first, count, s); break;
+    case 12: launch_small<6, false>(v, order, first, count, s); break; case 13: launch_small<6, true>(v, order, first, count, s); break;
+    case 14: launch_small<7, false>(v, order, first, count, s); break; case 15: launch_small<7, true>(v, order, first, count, s); break;
+    default: break;
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
+{
+    if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+    d.ran = false;
+    d.ops_words = 0;
+    if (d.n_tasks == 0) { d.ran = true; return LF_OK; }
+    const size_t n = d.n_tasks;
+    lfb_stream s = d.stream;
+    LF_TRY(d.keys.reserve(n * 4)); LF_TRY(d.keys2.reserve(n * 4)); LF_TRY(d.idx.reserve(n * 4)); LF_TRY(d.idx2.reserve(n * 4));
+    LF_TRY(d.slot_words.reserve(n * 4)); LF_TRY(d.scr_bytes.reserve(n * 4));
+    LF_TRY(d.slot_end.reserve(n * 8)); LF_TRY(d.scr_off.reserve((n + 1) * 8));
+    LF_TRY(d.res.reserve(n * sizeof(lf_align_result)));
+    LF_TRY(d.counters.reserve(sizeof(LfCounters))); LF_TRY(d.queue.reserve(64));
+    LF_TRY(lfb_memset(d.counters.p, 0, sizeof(LfCounters), s));
+    LF_TRY(lfb_memset(d.queue.p, 0, 64, s));
+#ifndef LF_EMU
+    cudaEventRecord(d.ev[0], s);
+#endif
+    LfDev v = make_dev(ctx, d);
+    LFB_LAUNCH(k_align_prep, (unsigned)((n + 255) / 256), 256, 0, s, v, d.keys.as<uint32_t>(), d.idx.as<uint32_t>(),
+               d.slot_words.as<uint32_t>(), d.scr_bytes.as<uint32_t>(), d.counters.as<LfCounters>());
+    LF_TRY(lfb_sort_pairs(d.tmp, d.keys.as<uint32_t>(), d.keys2.as<uint32_t>(), d.idx.as<uint32_t>(), d.idx2.as<uint32_t>(), n, s));
+    LF_TRY(lfb_scan_incl(d.tmp, d.slot_words.as<uint32_t>(), d.slot_end.as<unsigned long long>(), n, s));
+    LF_TRY(lfb_scan_excl_total(d.tmp, d.scr_bytes.as<uint32_t>(), d.scr_off.as<unsigned long long>(), n, s));
+    HostTotals *ht = (HostTotals *)d.pinned;
+    LF_TRY(lfb_d2h(&ht->cnt, d.counters.p, sizeof(LfCounters), s));
+    LF_TRY(lfb_d2h(&ht->slot_total, d.slot_end.as<unsigned long long>() + (n - 1), 8, s));
+    LF_TRY(lfb_d2h(&ht->scr_total, d.scr_off.as<unsigned long long>() + n, 8, s));
+    LF_TRY(lfb_sync(s)); /* the one host round trip of a batch: class sizes decide the launches */
+    d.ops_words = ht->slot_total;
+    LF_TRY(d.ops.reserve((size_t)ht->slot_total * 4 + 64));
+    LF_TRY(d.scratch.reserve((size_t)ht->scr_total + 64));
+    v = make_dev(ctx, d);
+
+    ctx->stats.align_tasks += n;
+    ctx->stats.cells += ht->cnt.cells;
+    ctx->stats.word_columns += ht->cnt.word_columns;
+    ctx->stats.last_main_word_columns = ht->cnt.small_word_columns;
+
+#ifndef LF_EMU
+    cudaEventRecord(d.ev[2], s);
+#endif
+    uint32_t first = 0;
+    for (int cls = 0; cls < LF_CLS_LARGE; cls++) {
+        const uint32_t count = ht->cnt.hist[cls];
+        if (count) launch_small_class(cls, v, d.idx2.as<uint32_t>(), first, count, s);
+        first += count;
+    }
+#ifndef LF_EMU
+    cudaEventRecord(d.ev[3], s);
+#endif
+    const uint32_t nlarge = ht->cnt.hist[LF_CLS_LARGE];
+    if (nlarge) {
+        LfLargeCfg cfg;
+        const size_t mq = ht->cnt.max_q, mt = ht->cnt.max_t;
+        size_t off = align_up((size_t)ht->cnt.max_planes + 256, 256);
+        cfg.off_hb = off; off = align_up(off + mt + 64, 256);
+        cfg.off_L = off; off = align_up(off + (mq + 2) * 4, 256);
+        cfg.off_R = off; off = align_up(off + (mq + 2) * 4, 256);
+        cfg.off_opsb = off; off = align_up(off + mq + mt + 64, 256);
+        cfg.off_stack = off; off = align_up(off + LF_LARGE_STACK * 5 * 4, 256);
+        cfg.stride = off;
+        /* persistent grid of warp slots; bounded so that the scratch stays within a few GB */
+        size_t slots = 148 * 8;
+        const size_t budget = (size_t)6 << 30;
+        if (slots * cfg.stride > budget) slots = budget / cfg.stride;
+        if (slots < 1) slots = 1;
+        if (slots > nlarge) slots = nlarge;
+        LF_TRY(d.large_scr.reserve(slots * cfg.stride));
+        cfg.base = d.large_scr.as<uint8_t>();
+        cfg.queue = d.queue.as<uint32_t>();
+        LFB_LAUNCH(k_myers_large, (unsigned)slots, 32, 0, s, v, d.idx2.as<uint32_t>(), first, nlarge, cfg);
+    }
+#ifndef LF_EMU
+    cudaEventRecord(d.ev[1], s);
+#endif
+    LF_TRY(lfb_last_error());
+    d.ran = true;
+    return LF_OK;
+}
+
+} // namespace
+
+/* ---------------------------------------------------------------------------------------------- */
+extern "C" {
+
+int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *devices, int n_devices)
+{
+    if (!out || !pac || l_pac <= 0) return LF_ERR_BAD_ARG;
+    *out = nullptr;
+    lfb_errbuf[0] = 0;
+    std::vector<int> devs;
+#ifndef LF_EMU
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return LF_ERR_NO_DEVICE;
+    if (!devices || n_devices <= 0) { int cur = 0; if (cudaGetDevice(&cur) != cudaSuccess) return LF_ERR_NO_DEVICE; devs.push_back(cur); }
+    else for (int i = 0; i < n_devices; i++) { if (devices[i] < 0 || devices[i] >= count) return LF_ERR_BAD_ARG; devs.push_back(devices[i]); }
+#else
+    (void)devices; (void)n_devices;
+    devs.push_back(0);
+#endif
+    lf_gpu_ctx *ctx = new lf_gpu_ctx();
+    ctx->l_pac = l_pac;
+    ctx->devs.resize(devs.size());
+    const size_t pac_bytes = (size_t)(l_pac / 4 + 1);
+    for (size_t i = 0; i < devs.size(); i++) {
+        DevState &d = ctx->devs[i];
+        d.dev = devs[i];
+        if (set_dev(d)) { delete ctx; return LF_ERR_NO_DEVICE; }
+#ifndef LF_EMU
+        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; }
+        for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
+#endif
+        d.pinned = lfb_host_alloc(sizeof(HostTotals));
+        if (!d.pinned || d.pac.reserve(pac_bytes + 16)) { lf_gpu_destroy(ctx); return LF_ERR_NOMEM; }
+        if (lfb_memset(d.pac.p, 0, pac_bytes + 16, d.stream) || lfb_h2d(d.pac.p, pac, pac_bytes, d.stream) || lfb_sync(d.stream)) { lf_gpu_destroy(ctx); return LF_ERR_CUDA; }
+    }
+    *out = ctx;
+    return LF_OK;
+}
+
+void lf_gpu_destroy(lf_gpu_ctx *ctx)
+{
+    if (!ctx) return;
+    for (DevState &d : ctx->devs) {
+        set_dev(d);
+        LfbBuf *bufs[] = { &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
+                           &d.slot_words, &d.scr_bytes, &d.slot_end, &d.scr_off, &d.scratch, &d.large_scr, &d.counters, &d.queue,
+                           &d.etasks, &d.eres, &d.escr_items, &d.escr_off, &d.escr };
+        for (LfbBuf *b : bufs) b->release();
+        lfb_free(d.tmp.p);
+        lfb_host_free(d.pinned);
+#ifndef LF_EMU
+        for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
+        if (d.stream) cudaStreamDestroy(d.stream);
+#endif
+    }
+    delete ctx;
+}
+
+const char *lf_gpu_last_error(const lf_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void *lf_gpu_host_alloc(size_t bytes) { return lfb_host_alloc(bytes); }
+void lf_gpu_host_free(void *p) { lfb_host_free(p); }
+
+size_t lf_gpu_ops_capacity(const lf_align_task *tasks, size_t n)
+{
+    size_t words = 0;
+    for (size_t i = 0; i < n; i++)
+        if (!(tasks[i].flags & LF_F_NO_PATH)) words += ((size_t)tasks[i].q_len + tasks[i].t_len + 15) >> 4;
+    return words * 4 + 64;
+}
+
+int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads)
+{
+    if (!ctx || !reads || !reads->offsets || (!reads->bases && reads->n_reads)) return LF_ERR_BAD_ARG;
+    const uint32_t nr = reads->n_reads;
+    const uint64_t total = reads->offsets[nr];
+    const size_t pwords = (size_t)(total >> 5) + 3 * (size_t)nr + 8;
+    for (DevState &d : ctx->devs) {
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        LF_TRY(d.bases.reserve(total + 64)); LF_TRY(d.read_off.reserve(((size_t)nr + 1) * 8));
+        LF_TRY(d.plo.reserve(pwords * 4)); LF_TRY(d.phi.reserve(pwords * 4)); LF_TRY(d.pnn.reserve(pwords * 4));
+        LF_TRY(lfb_h2d(d.bases.p, reads->bases, total, d.stream));
+        LF_TRY(lfb_h2d(d.read_off.p, reads->offsets, ((size_t)nr + 1) * 8, d.stream));
+        LF_TRY(lfb_memset(d.plo.p, 0, pwords * 4, d.stream)); LF_TRY(lfb_memset(d.phi.p, 0, pwords * 4, d.stream));
+        LF_TRY(lfb_memset(d.pnn.p, 0xff, pwords * 4, d.stream));
+        d.n_reads = nr; d.total_bases = total;
+        if (nr) {
+            LfDev v = make_dev(ctx, d);
+            LFB_LAUNCH(k_pack_reads, nr, 128, 0, d.stream, v);
+        }
+    }
+    return LF_OK;
+}
+
+int lf_gpu_upload_align_tasks(lf_gpu_ctx *ctx, const lf_align_task *tasks, size_t n)
+{
+    if (!ctx || (!tasks && n) || n > 0x7fffffffu) return LF_ERR_BAD_ARG;
+    const size_t nd = ctx->devs.size();
+    for (size_t k = 0; k < nd; k++) {
+        DevState &d = ctx->devs[k];
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        const size_t lo = n * k / nd, hi = n * (k + 1) / nd;
+        d.task_first = lo; d.n_tasks = (uint32_t)(hi - lo); d.ran = false;
+        LF_TRY(d.tasks.reserve((hi - lo) * sizeof(lf_align_task)));
+        if (hi > lo) LF_TRY(lfb_h2d(d.tasks.p, tasks + lo, (hi - lo) * sizeof(lf_align_task), d.stream));
+    }
+    return LF_OK;
+}
+
+int lf_gpu_run_align(lf_gpu_ctx *ctx)
+{
+    if (!ctx) return LF_ERR_BAD_ARG;
+    /* the per-batch host sync inside run_align_dev serialises devices of one context; callers that
+     * want several GPUs busy use one context (one process) per GPU, as bench.py does */
+    for (DevState &d : ctx->devs) { int rc = run_align_dev(ctx, d); if (rc) return rc; }
+    ctx->stats.kernel_launches = lfb_launches;
+    return LF_OK;
+}
+
+int lf_gpu_sync(lf_gpu_ctx *ctx)
+{
+    if (!ctx) return LF_ERR_BAD_ARG;
+    for (DevState &d : ctx->devs) { if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice"); LF_TRY(lfb_sync(d.stream)); }
+#ifndef LF_EMU
+    DevState &d0 = ctx->devs[0];
+    if (d0.ran && d0.n_tasks) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, d0.ev[0], d0.ev[1]) == cudaSuccess) ctx->stats.last_run_ms = ms;
+        if (cudaEventElapsedTime(&ms, d0.ev[2], d0.ev[3]) == cudaSuccess) ctx->stats.last_main_kernel_ms = ms;
+    }
+#endif
+    return LF_OK;
+}
+
+int lf_gpu_download_align(lf_gpu_ctx *ctx, lf_align_result *res, uint8_t *ops, size_t ops_cap)
+{
+    if (!ctx || !res) return LF_ERR_BAD_ARG;
+    uint64_t base_words = 0;
+    for (DevState &d : ctx->devs) {
+        if (!d.ran) return fail(ctx, LF_ERR_BAD_ARG, "download before run");
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        if (d.n_tasks == 0) continue;
+        if (d.ops_words) {
+            if (!ops || (base_words + d.ops_words) * 4 > ops_cap) return fail(ctx, LF_ERR_OPS_CAPACITY, "ops buffer too small");
+            LF_TRY(lfb_d2h(ops + base_words * 4, d.ops.p, (size_t)d.ops_words * 4, d.stream));
+        }
+        LF_TRY(lfb_d2h(res + d.task_first, d.res.p, (size_t)d.n_tasks * sizeof(lf_align_result), d.stream));
+        base_words += d.ops_words;
+    }
+    base_words = 0;
+    for (DevState &d : ctx->devs) {
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        LF_TRY(lfb_sync(d.stream));
+        if (base_words) for (size_t i = 0; i < d.n_tasks; i++) res[d.task_first + i].ops_off += base_words * 16;
+        base_words += d.ops_words;
+    }
+    return LF_OK;
+}
+
+int lf_gpu_align_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_align_task *tasks, size_t n,
+                       lf_align_result *res, uint8_t *ops, size_t ops_cap)
+{
+    int rc;
+    if (n == 0) return LF_OK;
+    if ((rc = lf_gpu_upload_reads(ctx, reads)) != 0) return rc;
+    if ((rc = lf_gpu_upload_align_tasks(ctx, tasks, n)) != 0) return rc;
+    if ((rc = lf_gpu_run_align(ctx)) != 0) return rc;
+    if ((rc = lf_gpu_download_align(ctx, res, ops, ops_cap)) != 0) return rc;
+    return lf_gpu_sync(ctx);
+}
+
+/* ---- extension ---- */
+int lf_gpu_upload_extend_tasks(lf_gpu_ctx *ctx, const lf_extend_task *tasks, size_t n)
+{
+    if (!ctx || (!tasks && n) || n > 0x7fffffffu) return LF_ERR_BAD_ARG;
+    const size_t nd = ctx->devs.size();
+    for (size_t k = 0; k < nd; k++) {
+        DevState &d = ctx->devs[k];
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        const size_t lo = n * k / nd, hi = n * (k + 1) / nd;
+        d.etask_first = lo; d.n_etasks = (uint32_t)(hi - lo);
+        LF_TRY(d.etasks.reserve((hi - lo) * sizeof(lf_extend_task)));
+        if (hi > lo) LF_TRY(lfb_h2d(d.etasks.p, tasks + lo, (hi - lo) * sizeof(lf_extend_task), d.stream));
+    }
+    return LF_OK;
+}
+
+int lf_gpu_run_extend(lf_gpu_ctx *ctx)
+{
+    if (!ctx) return LF_ERR_BAD_ARG;
+    for (DevState &d : ctx->devs) {
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        const size_t n = d.n_etasks;
+        if (!n) continue;
+        lfb_stream s = d.stream;
+        LF_TRY(d.eres.reserve(n * sizeof(lf_extend_result)));
+        LF_TRY(d.escr_items.reserve(n * 4)); LF_TRY(d.escr_off.reserve((n + 1) * 8));
+        LfExtDev v;
+        v.pac = d.pac.as<uint8_t>(); v.l_pac = ctx->l_pac; v.bases = d.bases.as<uint8_t>(); v.read_off = d.read_off.as<uint64_t>(); v.n_reads = d.n_reads;
+        v.tasks = d.etasks.as<lf_extend_task>(); v.n_tasks = (uint32_t)n; v.res = d.eres.as<lf_extend_result>();
+        v.scr_off = d.escr_off.as<uint64_t>(); v.scratch = nullptr;
+        LFB_LAUNCH(k_extend_prep, (unsigned)((n + 255) / 256), 256, 0, s, v, d.escr_items.as<uint32_t>());
+        LF_TRY(lfb_scan_excl_total(d.tmp, d.escr_items.as<uint32_t>(), d.escr_off.as<unsigned long long>(), n, s));
+        HostTotals *ht = (HostTotals *)d.pinned;
+        LF_TRY(lfb_d2h(&ht->scr_total, d.escr_off.as<unsigned long long>() + n, 8, s));
+        LF_TRY(lfb_sync(s));
+        LF_TRY(d.escr.reserve((size_t)ht->scr_total * sizeof(int2) + 64));
+        v.scratch = d.escr.as<int2>();
+        LFB_LAUNCH(k_ksw_extend, (unsigned)((n + 63) / 64), 64, 0, s, v);
+        LF_TRY(lfb_last_error());
+        ctx->stats.extend_tasks += n;
+    }
+    ctx->stats.kernel_launches = lfb_launches;
+    return LF_OK;
+}
+
+int lf_gpu_download_extend(lf_gpu_ctx *ctx, lf_extend_result *res)
+{
+    if (!ctx || !res) return LF_ERR_BAD_ARG;
+    for (DevState &d : ctx->devs) {
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        if (d.n_etasks) LF_TRY(lfb_d2h(res + d.etask_first, d.eres.p, (size_t)d.n_etasks * sizeof(lf_extend_result), d.stream));
+    }
+    return lf_gpu_sync(ctx);
+}
+
+int lf_gpu_extend_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_extend_task *tasks, size_t n, lf_extend_result *res)
+{
+    int rc;
+    if (n == 0) return LF_OK;
+    if (reads && (rc = lf_gpu_upload_reads(ctx, reads)) != 0) return rc; /* reads == NULL: keep the resident chunk */
+    if ((rc = lf_gpu_upload_extend_tasks(ctx, tasks, n)) != 0) return rc;
+    if ((rc = lf_gpu_run_extend(ctx)) != 0) return rc;
+    return lf_gpu_download_extend(ctx, res);
+}
+
+int lf_gpu_get_stats(const lf_gpu_ctx *ctx, lf_gpu_stats *out)
+{
+    if (!ctx || !out) return LF_ERR_BAD_ARG;
+    *out = ctx->stats;
+    out->kernel_launches = lfb_launches;
+    return LF_OK;
+}
+
+int lf_gpu_int32_peak(lf_gpu_ctx *ctx, int which, double *tops)
+{
+    if (!ctx || !tops || which < 0 || which > 3) return LF_ERR_BAD_ARG;
+    DevState &d = ctx->devs[0];
+    if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+    const int grid = 148 * 8, block = 256, iters = 4096;
+    LF_TRY(d.queue.reserve(64));
+    uint32_t *sink = d.queue.as<uint32_t>();
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+#ifndef LF_EMU
+        cudaEventRecord(d.ev[0], d.stream);
+#endif
+        switch (which) {
+        case 0: { auto kern = k_int32_peak<0>; LFB_LAUNCH(kern, grid, block, 0, d.stream, sink, iters, 12345u + rep); } break;
+        case 1: { auto kern = k_int32_peak<1>; LFB_LAUNCH(kern, grid, block, 0, d.stream, sink, iters, 12345u + rep); } break;
+        case 2: { auto kern = k_int32_peak<2>; LFB_LAUNCH(kern, grid, block, 0, d.stream, sink, iters, 12345u + rep); } break;
+        default: { auto kern = k_int32_peak<3>; LFB_LAUNCH(kern, grid, block, 0, d.stream, sink, iters, 12345u + rep); } break;
+        }
+#ifndef LF_EMU
+        cudaEventRecord(d.ev[1], d.stream);
+        LF_TRY(lfb_sync(d.stream));
+        float ms = 0; cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]);
+        if (rep && ms < best_ms) best_ms = ms;
+#else
+        best_ms = 1.0f;
+#endif
+    }
+    *tops = (double)grid * block * (double)iters * 64.0 / (best_ms * 1e-3) / 1e12;
+    return LF_OK;
+}
+
+} /* extern "C" */

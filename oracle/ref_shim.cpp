@@ -110,7 +110,10 @@ static void *run_on_big_stack(void *(*fn)(void *), void *arg)
 { /* alignChain_edlib keeps ~2 MB of arrays on its stack (src/LordFAST.cpp:1770-1781) */
     pthread_attr_t a; pthread_t th; void *ret = NULL;
     pthread_attr_init(&a); pthread_attr_setstacksize(&a, 32u << 20);
-    pthread_create(&th, &a, fn, arg); pthread_join(th, &ret); pthread_attr_destroy(&a);
+    int rc = pthread_create(&th, &a, fn, arg);
+    if (rc != 0) { fprintf(stderr, "[ref_shim] pthread_create failed (%d); running inline\n", rc); ret = fn(arg); }
+    else pthread_join(th, &ret);
+    pthread_attr_destroy(&a);
     return ret;
 }
 

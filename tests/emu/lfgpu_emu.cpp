@@ -1,0 +1,4 @@
+/* TEST-ONLY build of the host pipeline + kernels on the fiber emulator (see cuda_emu.h).
+ * Produces tests/emu/liblfgpu_emu_testonly.so; nothing under lordfast_b200/ loads it. */
+#include "cuda_emu.h"
+#include "../../lordfast_b200/csrc/lf_pipeline.inl"
