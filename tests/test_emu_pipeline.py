@@ -1,0 +1,91 @@
+"""The kernel + pipeline SOURCE run on the test-only fiber emulator (tests/emu) against the oracle.
+This is a debugging aid for a container without a GPU; the parity tests proper are test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from _common import CODE, build_emu, check_align, load_ksw, load_pairs, pairs_as_batch
+import _oracle as O
+from lordfast_b200 import api, sim
+from lordfast_b200.chain_tasks import workload_tasks
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    return build_emu()
+
+
+def test_emu_golden_pairs(emu_lib):
+    pairs = [p for p in load_pairs() if set(p["t"]) <= set("ACGT") and len(p["q"]) * len(p["t"]) < 1_500_000]
+    ref, reads, tasks = pairs_as_batch(pairs)
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    bad, res, ops = check_align(g, reads, ref, tasks)
+    assert not bad
+    for i, p in enumerate(pairs):  # and against the reference's recorded answers
+        assert (int(res[i]["edit_distance"]), int(res[i]["end_location"])) == (p["ed"], p["end"])
+        assert "".join(str(c) for c in api.decode_ops(ops, int(res[i]["ops_off"]), int(res[i]["ops_len"]))) == p["ops"]
+    g.close()
+
+
+def test_emu_random_tasks_all_flags(emu_lib):
+    rng = np.random.default_rng(5)
+    ref = sim.make_reference(30000, 3)
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    reads = []
+    for i in range(8):
+        L = int(rng.integers(300, 1500)); s = int(rng.integers(100, len(ref) - L - 100))
+        reads.append(sim._channel(ref[s:s + L], 0.15, rng)[0])
+    r0 = reads[0].copy(); r0[5] = ord("N"); r0[17] = ord("a"); reads[0] = r0
+    tasks = []
+    qlens = [1, 2, 31, 32, 33, 64, 65, 96, 97, 129, 200, 257, 385, 513, 600]
+    for k in range(150):
+        rid = int(rng.integers(0, len(reads))); L = len(reads[rid])
+        ql = int(min(qlens[k % len(qlens)], L)); qo = int(rng.integers(0, L - ql + 1))
+        tl = max(1, int(ql * rng.uniform(0.5, 1.5)) + int(rng.integers(-3, 4)))
+        to = int(rng.integers(0, len(ref) - tl))
+        flags = int(rng.choice([0, 1, 2, 3, 4, 5])) | (8 if k % 23 == 0 else 0)
+        tasks.append((rid, qo, ql, to, tl, flags, int(rng.integers(0, 2)), 0))
+    tasks = np.array(tasks, dtype=api.ALIGN_TASK)
+    bad, _, _ = check_align(g, reads, ref, tasks)
+    assert not bad
+    g.close()
+
+
+def test_emu_bad_tasks_are_flagged(emu_lib):
+    ref = sim.make_reference(2000, 1)
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    reads = [ref[100:200].copy()]
+    tasks = np.array([(0, 0, 50, 0, 60, 0, 0, 0), (0, 90, 50, 0, 60, 0, 0, 0), (0, 0, 0, 0, 60, 0, 0, 0), (0, 0, 10, 1990, 60, 0, 0, 0), (3, 0, 10, 0, 60, 0, 0, 0)],
+                     dtype=api.ALIGN_TASK)
+    offs = np.array([0, 100], dtype=np.uint64)
+    res, ops = g.align_batch(reads[0], offs, tasks)
+    assert int(res[0]["status"]) == 0
+    assert [int(s) for s in res["status"][1:]] == [-3, -3, -3, -3]
+    g.close()
+
+
+def test_emu_workload_tasks(emu_lib):
+    w = sim.make_workload(100_000, 6, 2500, 0.15, 0.15, seed=2, sv_frac=0.5)
+    tasks, chain, kind = workload_tasks(w)
+    g = api.LfGpu(w.pac, len(w.ref), lib_path=emu_lib)
+    reads = [w.reads[w.read_off[i]:w.read_off[i + 1]] for i in range(w.n_reads)]
+    bad, _, _ = check_align(g, reads, w.ref, tasks)
+    assert not bad
+    g.close()
+
+
+def test_emu_extend(emu_lib):
+    cases = [c for c in load_ksw() if len(c["q"]) < 1000][:30]
+    tcat, reads, tasks, off = [], [], [], 0
+    for k, c in enumerate(cases):
+        t = np.frombuffer(c["t"].encode(), dtype=np.uint8)
+        tcat.append(t); reads.append(np.frombuffer(c["q"].encode(), dtype=np.uint8))
+        p = c["prm"]
+        tasks.append((k, 0, len(c["q"]), off, len(t), 0, 0, 0, p[0], p[1], p[2], p[3], p[4], p[5], len(c["q"])))
+        off += len(t)
+    ref = np.concatenate(tcat)
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64); offs[1:] = np.cumsum([len(r) for r in reads])
+    er = g.extend_batch(np.concatenate(reads), offs, np.array(tasks, dtype=api.EXTEND_TASK))
+    for k, c in enumerate(cases):
+        assert (int(er[k]["score"]), int(er[k]["qle"]), int(er[k]["tle"])) == (c["score"], c["qle"], c["tle"])
+    g.close()
