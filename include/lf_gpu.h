@@ -144,6 +144,41 @@ int lf_gpu_upload_extend_tasks(lf_gpu_ctx *ctx, const lf_extend_task *tasks, siz
 int lf_gpu_run_extend(lf_gpu_ctx *ctx);
 int lf_gpu_download_extend(lf_gpu_ctx *ctx, lf_extend_result *res);
 
+/* ---- the chain-level operator -------------------------------------------------------------- */
+
+/* alignChain_edlib (src/LordFAST.cpp:1765-2258, reached through the reference's hook
+ * `void (*alignChain)(Chain_t&, char*, int32_t, int, SamList_t&)`, :107) for a whole chunk of
+ * candidate chains: round-1 alignments, the clip / split triggers (evaluated on the host with the
+ * reference's float expressions), ksw extensions, follow-up alignments, and the reference's
+ * CIGAR / MD accumulation.  One lf_sam_record per Sam_t the reference would push to map.samList,
+ * in chain order.  The caller (lordFAST's alignWin, :1063-1083) computes alnScore / totalScore from
+ * nmCount, qStart, qEnd exactly as today. */
+typedef struct { uint32_t tPos, qPos, len; } lf_seed;      /* Seed_t (src/LordFAST.h:30-35), bit-fields unpacked */
+typedef struct {                                          /* Chain_t + the call's query / isRev arguments */
+    uint64_t seed_off;   /* first seed in the seeds array                                           */
+    uint32_t n_seeds;    /* chainLen, >= 2 (alignWin only calls alignChain then, :1063)              */
+    uint32_t read_id;    /* index into lf_reads                                                     */
+    uint32_t is_rev;     /* 1: query = reverse complement of the stored read                        */
+    uint32_t reserved;
+} lf_chain;
+typedef struct { const int64_t *offset; const int32_t *len; int32_t n; } lf_contigs; /* bns->anns[] offsets / lengths */
+typedef struct {         /* Sam_t fields alignChain_edlib fills (src/LordFAST.h:81-100) */
+    uint32_t chain_id, flag, pos, posEnd, qStart, qEnd;
+    int32_t  nmCount;
+    uint32_t cigar_len, md_len;
+    uint64_t cigar_off, md_off; /* NUL-terminated strings inside lf_chain_results_text() */
+} lf_sam_record;
+typedef struct { uint64_t round1_tasks, round2_extends, round3_tasks, records; } lf_chain_stats;
+typedef struct lf_chain_results lf_chain_results;         /* library-owned, free with lf_chain_results_free */
+
+/* pac_host: the same 2-bit reference that was given to lf_gpu_init (MD strings need reference bases). */
+int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs *contigs, const lf_seed *seeds,
+                        const lf_chain *chains, size_t n_chains, const uint8_t *pac_host, lf_chain_results **out);
+const lf_sam_record *lf_chain_results_records(const lf_chain_results *r, size_t *n);
+const char *lf_chain_results_text(const lf_chain_results *r, size_t *bytes);
+int  lf_chain_results_stats(const lf_chain_results *r, lf_chain_stats *out);
+void lf_chain_results_free(lf_chain_results *r);
+
 /* ---- measurement hooks -------------------------------------------------------------------- */
 
 typedef struct {

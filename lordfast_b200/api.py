@@ -26,11 +26,24 @@ EXTEND_TASK = np.dtype([("read_id", "<u4"), ("q_off", "<u4"), ("q_len", "<u4"), 
                         ("flags", "<u2"), ("matrix", "u1"), ("reserved", "u1"), ("o_del", "<i4"), ("e_del", "<i4"),
                         ("o_ins", "<i4"), ("e_ins", "<i4"), ("w", "<i4"), ("zdrop", "<i4"), ("h0", "<i4")])
 EXTEND_RESULT = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4")])
+SEED = np.dtype([("tPos", "<u4"), ("qPos", "<u4"), ("len", "<u4")])
+CHAIN = np.dtype([("seed_off", "<u8"), ("n_seeds", "<u4"), ("read_id", "<u4"), ("is_rev", "<u4"), ("reserved", "<u4")])
+SAM_RECORD = np.dtype([("chain_id", "<u4"), ("flag", "<u4"), ("pos", "<u4"), ("posEnd", "<u4"), ("qStart", "<u4"), ("qEnd", "<u4"),
+                       ("nmCount", "<i4"), ("cigar_len", "<u4"), ("md_len", "<u4"), ("_pad", "<u4"), ("cigar_off", "<u8"), ("md_off", "<u8")])
+assert SEED.itemsize == 12 and CHAIN.itemsize == 24 and SAM_RECORD.itemsize == 56
 assert ALIGN_TASK.itemsize == 24 and ALIGN_RESULT.itemsize == 24 and EXTEND_TASK.itemsize == 52 and EXTEND_RESULT.itemsize == 12
 
 
 class Reads(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("offsets", C.c_void_p), ("n_reads", C.c_uint32)]
+
+
+class Contigs(C.Structure):
+    _fields_ = [("offset", C.c_void_p), ("len", C.c_void_p), ("n", C.c_int32)]
+
+
+class ChainStats(C.Structure):
+    _fields_ = [("round1_tasks", C.c_uint64), ("round2_extends", C.c_uint64), ("round3_tasks", C.c_uint64), ("records", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -43,7 +56,8 @@ EXPORTS = ["lf_gpu_init", "lf_gpu_destroy", "lf_gpu_last_error", "lf_gpu_host_al
            "lf_gpu_ops_capacity", "lf_gpu_align_batch", "lf_gpu_extend_batch", "lf_gpu_upload_reads",
            "lf_gpu_upload_align_tasks", "lf_gpu_run_align", "lf_gpu_sync", "lf_gpu_download_align",
            "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",
-           "lf_gpu_int32_peak"]
+           "lf_gpu_int32_peak", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
+           "lf_chain_results_stats", "lf_chain_results_free"]
 
 
 class LfGpuError(RuntimeError):
@@ -80,6 +94,14 @@ def load(lib_path: str | None = None) -> C.CDLL:
     lib.lf_gpu_download_extend.argtypes = [vp, vp]
     lib.lf_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.lf_gpu_int32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.lf_gpu_align_chains.argtypes = [vp, C.POINTER(Reads), C.POINTER(Contigs), vp, vp, sz, vp, C.POINTER(vp)]
+    lib.lf_chain_results_records.argtypes = [vp, C.POINTER(sz)]
+    lib.lf_chain_results_records.restype = vp
+    lib.lf_chain_results_text.argtypes = [vp, C.POINTER(sz)]
+    lib.lf_chain_results_text.restype = vp
+    lib.lf_chain_results_stats.argtypes = [vp, C.POINTER(ChainStats)]
+    lib.lf_chain_results_free.argtypes = [vp]
+    lib.lf_chain_results_free.restype = None
     return lib
 
 
@@ -173,6 +195,27 @@ class LfGpu:
         self._check(self.lib.lf_gpu_extend_batch(self.ctx, C.byref(r), _ptr(tasks), n, _ptr(res)), "lf_gpu_extend_batch")
         return res
 
+    def align_chains(self, bases, offsets, contig_off, contig_len, seeds: np.ndarray, chains: np.ndarray, want_text=True):
+        """alignChain_edlib for a chunk of chains.  Returns (records, text bytes, ChainStats)."""
+        seeds = np.ascontiguousarray(seeds, dtype=SEED)
+        chains = np.ascontiguousarray(chains, dtype=CHAIN)
+        co = np.ascontiguousarray(contig_off, dtype=np.int64)
+        cl = np.ascontiguousarray(contig_len, dtype=np.int32)
+        r = self._reads(bases, offsets)
+        cg = Contigs(_ptr(co), _ptr(cl), len(co))
+        out = C.c_void_p()
+        self._check(self.lib.lf_gpu_align_chains(self.ctx, C.byref(r), C.byref(cg), _ptr(seeds), _ptr(chains), len(chains),
+                                                 _ptr(self.pac), C.byref(out)), "lf_gpu_align_chains")
+        n, nb = C.c_size_t(), C.c_size_t()
+        rp = self.lib.lf_chain_results_records(out, C.byref(n))
+        tp = self.lib.lf_chain_results_text(out, C.byref(nb))
+        recs = np.frombuffer((C.c_uint8 * (n.value * SAM_RECORD.itemsize)).from_address(rp), dtype=SAM_RECORD).copy() if n.value else np.zeros(0, dtype=SAM_RECORD)
+        text = bytes((C.c_uint8 * nb.value).from_address(tp)) if (want_text and nb.value) else b""
+        st = ChainStats()
+        self.lib.lf_chain_results_stats(out, C.byref(st))
+        self.lib.lf_chain_results_free(out)
+        return recs, text, st
+
     # ---- phased forms (keep a batch resident in HBM) ----
     def upload_reads(self, bases, offsets):
         r = self._reads(bases, offsets)
@@ -200,3 +243,26 @@ class LfGpu:
         v = C.c_double()
         self._check(self.lib.lf_gpu_int32_peak(self.ctx, which, C.byref(v)), "lf_gpu_int32_peak")
         return v.value
+
+
+def records_to_dicts(recs: np.ndarray, text: bytes):
+    """lf_sam_record rows -> the dict form the tests compare with the reference's Sam_t dumps."""
+    out = []
+    for r in recs:
+        out.append(dict(chain=int(r["chain_id"]), flag=int(r["flag"]), pos=int(r["pos"]), posEnd=int(r["posEnd"]), qStart=int(r["qStart"]),
+                        qEnd=int(r["qEnd"]), nm=int(r["nmCount"]),
+                        cigar=text[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["cigar_len"])].decode(),
+                        md=text[int(r["md_off"]):int(r["md_off"]) + int(r["md_len"])].decode()))
+    return out
+
+
+def workload_chains(w):
+    """sim.Workload -> (seeds, chains) arrays for LfGpu.align_chains (one chain per read)."""
+    seeds = np.zeros(len(w.seeds), dtype=SEED)
+    seeds["tPos"], seeds["qPos"], seeds["len"] = w.seeds[:, 0], w.seeds[:, 1], w.seeds[:, 2]
+    chains = np.zeros(w.n_reads, dtype=CHAIN)
+    chains["seed_off"] = w.seed_off[:-1]
+    chains["n_seeds"] = np.diff(w.seed_off)
+    chains["read_id"] = np.arange(w.n_reads)
+    chains["is_rev"] = w.is_rev
+    return seeds, chains

@@ -751,20 +751,22 @@ __global__ void k_ksw_extend(LfExtDev d)
 /* ------------------------------------------------------------------------------------------ */
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_int32_peak(uint32_t *out, int iters, uint32_t seed)
-{
+{ /* 8 registers updated round-robin, every instruction with three distinct live register inputs so
+   * that ptxas can neither fold two of them into one LOP3/IADD3 nor strength-reduce the loop; the
+   * committed SASS (profiles/) shows 64 LOP3 / IADD3 / IMAD per iteration. */
     uint32_t a[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) a[k] = seed + threadIdx.x * 8u + (uint32_t)k;
-    uint32_t m = seed ^ 0x9e3779b9u, n = seed * 3u + 1u;
+    for (int k = 0; k < 8; k++) a[k] = seed * (uint32_t)(k + 3) + threadIdx.x * 8u + (uint32_t)k;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                if (WHICH == 0) a[k] = (a[k] & m) ^ n;                               /* LOP3 */
-                else if (WHICH == 1) a[k] = a[k] + m + n;                            /* IADD3 */
-                else if (WHICH == 2) { if (k & 1) a[k] = (a[k] & m) ^ n; else a[k] = a[k] + m + n; }
-                else { if (k & 1) a[k] = (a[k] & m) ^ n; else a[k] = a[k] * m + n; } /* LOP3 + IMAD */
+                const uint32_t x = a[(k + 3) & 7], y = a[(k + 5) & 7];
+                if (WHICH == 0) a[k] = (a[k] & x) ^ y;                                        /* LOP3  */
+                else if (WHICH == 1) a[k] = a[k] + x + y;                                     /* IADD3 */
+                else if (WHICH == 2) { if (k & 1) a[k] = (a[k] & x) ^ y; else a[k] = a[k] + x + y; }
+                else { if (k & 1) a[k] = (a[k] & x) ^ y; else a[k] = a[k] * x + y; }          /* LOP3 + IMAD */
             }
         }
     }

@@ -460,3 +460,5 @@ int lf_gpu_int32_peak(lf_gpu_ctx *ctx, int which, double *tops)
 }
 
 } /* extern "C" */
+
+#include "lf_chain.inl"

@@ -1,0 +1,93 @@
+"""lf_gpu_align_chains (the batched alignChain_edlib) against the Sam_t records the reference itself
+produced for the golden chains, and against the oracle's chain restatement on simulated SV reads.
+CPU runs go through the test-only emulator; the -m gpu runs through liblfgpu.so on the device."""
+import numpy as np
+import pytest
+
+import _oracle as O
+from _common import build_emu, load_chains
+from lordfast_b200 import api, sim
+
+
+def _golden(lib_path):
+    z, chains = load_chains()
+    l_pac = int(z["l_pac"])
+    g = api.LfGpu(z["pac"], l_pac, lib_path=lib_path)
+    seeds, ch = [], []
+    for c in chains:
+        ch.append((len(seeds), len(c["seeds"]), c["read"], c["isRev"], 0))
+        seeds.extend(tuple(s) for s in c["seeds"])
+    recs, text, st = g.align_chains(z["reads"], z["read_off"].astype(np.uint64), [0], [l_pac],
+                                    np.array(seeds, dtype=api.SEED), np.array(ch, dtype=api.CHAIN))
+    got = api.records_to_dicts(recs, text)
+    exp = []
+    for ci, c in enumerate(chains):
+        for s in c["sam"]:
+            d = dict(chain=ci); d.update(s); exp.append(d)
+    assert got == exp
+    assert st.round2_extends > 0 and st.round3_tasks > 0  # the clip / split rounds really ran
+    g.close()
+
+
+def _simulated(lib_path, n_reads, read_len, ref_len):
+    w = sim.make_workload(ref_len, n_reads, read_len, 0.12, 0.15, seed=21, sv_frac=0.5)
+    g = api.LfGpu(w.pac, len(w.ref), lib_path=lib_path)
+    seeds, chains = api.workload_chains(w)
+    recs, text, st = g.align_chains(w.reads, w.read_off.astype(np.uint64), w.contig_off, w.contig_len, seeds, chains)
+    got = api.records_to_dicts(recs, text)
+    idx = O.RefIndex(w.ref.tobytes())
+    exp = []
+    for i in range(w.n_reads):
+        a, _ = O.oracle_align_chain(idx, [tuple(int(x) for x in s) for s in w.chain(i)], w.oriented(i).tobytes(), int(w.is_rev[i]))
+        for s in a:
+            d = dict(chain=i); d.update(s); exp.append(d)
+    assert got == exp
+    g.close()
+    return st
+
+
+def test_emu_chain_operator_golden():
+    _golden(build_emu())
+
+
+def test_emu_chain_operator_simulated():
+    _simulated(build_emu(), 10, 2500, 120_000)
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_golden():
+    _golden(None)
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_simulated_config1():
+    st = _simulated(None, 200, 10_000, 1_000_000)
+    assert st.round2_extends > 0
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_two_contigs_edges():
+    """Chains next to contig boundaries: the head / tail guards (:1825, :2163) must soft-clip."""
+    rng = np.random.default_rng(3)
+    ref = sim.make_reference(60_000, 8)
+    contig_off, contig_len = [0, 25_000], [25_000, 35_000]
+    reads, seeds, chains = [], [], []
+    idx = O.RefIndex(ref.tobytes(), contig_len)
+    exp = []
+    for k, (start, L) in enumerate([(5, 3000), (25_010, 3000), (21_990, 3000), (56_990, 3000), (40_000, 2000)]):
+        o, qpos, clean = sim._channel(ref[start:start + L], 0.12, rng)
+        s = sim._anchors(qpos, clean, start, 0, 14, rng)
+        if k % 2:
+            o = np.concatenate([sim.ACGT[rng.integers(0, 4, size=40, dtype=np.uint8)], o]); s[:, 1] += 40
+        rev = k % 2
+        reads.append(sim.revcomp(o) if rev else o)
+        chains.append((len(seeds), len(s), k, rev, 0))
+        seeds.extend(tuple(int(x) for x in r) for r in s)
+        a, _ = O.oracle_align_chain(idx, [tuple(int(x) for x in r) for r in s], o.tobytes(), rev)
+        for r in a:
+            d = dict(chain=k); d.update(r); exp.append(d)
+    off = np.zeros(len(reads) + 1, dtype=np.uint64); off[1:] = np.cumsum([len(r) for r in reads])
+    g = api.LfGpu(sim.pack_pac(ref), len(ref))
+    recs, text, st = g.align_chains(np.concatenate(reads), off, contig_off, contig_len, np.array(seeds, dtype=api.SEED), np.array(chains, dtype=api.CHAIN))
+    assert api.records_to_dicts(recs, text) == exp
+    g.close()
