@@ -96,6 +96,35 @@ __device__ __forceinline__ uint32_t lf_tsym(const uint8_t *__restrict__ pac, int
     return ((uint32_t)__ldg(pac + (l >> 2)) >> ((~(uint32_t)l & 3u) << 1)) & 3u;
 }
 
+/* Sequential reader of the 2-bit reference: one aligned 32-bit load covers 16 columns and the next
+ * word is requested one refill ahead, so the load latency (the per-column byte load was the top
+ * long-scoreboard stall of the first version) is off the dependency chain. */
+struct LfTCursor {
+    const uint32_t *p32; int64_t widx; uint32_t buf, nxt; int left, dir;
+    __device__ __forceinline__ static uint32_t be(uint32_t v)
+    { /* bytes hold bases MSB-first: make base j of the word sit at bits 31-2j .. 30-2j */
+        return __byte_perm(v, 0u, 0x0123u);
+    }
+    __device__ __forceinline__ void init(const uint8_t *pac, int64_t l, int d)
+    {
+        p32 = (const uint32_t *)pac; dir = d; widx = l >> 4;
+        const int j = (int)(l & 15);
+        buf = be(__ldg(p32 + widx));
+        if (d > 0) { buf <<= 2 * j; left = 16 - j; widx++; }
+        else { buf >>= 2 * (15 - j); left = j + 1; widx--; }
+        nxt = be(__ldg(p32 + (widx < 0 ? 0 : widx)));
+    }
+    __device__ __forceinline__ uint32_t next()
+    {
+        if (left == 0) { buf = nxt; left = 16; widx += dir; nxt = be(__ldg(p32 + (widx < 0 ? 0 : widx))); }
+        uint32_t sym;
+        if (dir > 0) { sym = buf >> 30; buf <<= 2; }
+        else { sym = buf & 3u; buf >>= 2; }
+        left--;
+        return sym;
+    }
+};
+
 struct LfQView { int64_t bit0; int dir; uint32_t comp; }; /* element k lives at plane bit bit0 + dir*k */
 struct LfTView { int64_t t0; int dir; };                   /* element k is pac base t0 + dir*k */
 
@@ -183,45 +212,64 @@ __host__ __device__ __forceinline__ unsigned long long lf_large_planes_bytes(uin
     return full < cap ? full : cap;
 }
 
-__global__ void k_align_prep(LfDev d, uint32_t *keys, uint32_t *idx, uint32_t *slot_words, uint32_t *scr_bytes, LfCounters *cnt)
+__global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uint32_t *idx, uint32_t *slot_words, uint32_t *scr_bytes, LfCounters *cnt)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n_tasks) return;
-    lf_align_task t = d.tasks[i];
-    int cls = LF_CLS_BAD;
-    uint32_t scr = 0, slot = 0;
-    bool ok = t.q_len >= 1 && t.t_len >= 1 && t.read_id < d.n_reads && t.mode <= LF_MODE_SHW;
-    if (ok) {
-        uint64_t L = d.read_off[t.read_id + 1] - d.read_off[t.read_id];
-        ok = (uint64_t)t.q_off + t.q_len <= L && (int64_t)t.t_off + (int64_t)t.t_len <= d.l_pac
-             && (uint64_t)t.q_len + t.t_len < (1ull << 31);
-    }
-    if (ok) {
-        uint32_t nwords = (t.q_len + 31u) >> 5;
-        int sc = lf_small_class(nwords);
-        if (sc >= 0 && lf_is_leaf(t.q_len, t.t_len)) {
-            cls = 2 * sc + (t.mode == LF_MODE_SHW ? 1 : 0);
-            scr = lf_k1_ckpt_bytes(t.t_len, lf_small_nw(sc));
-            atomicAdd(&cnt->small_word_columns, (unsigned long long)nwords * t.t_len);
-        } else {
-            cls = LF_CLS_LARGE;
-            atomicMax(&cnt->max_q, t.q_len);
-            atomicMax(&cnt->max_t, t.t_len);
-            atomicMax(&cnt->max_planes, lf_large_planes_bytes(t.q_len, t.t_len));
+    /* per-block partial sums in shared memory, one global atomic per counter per block (2.4 M tasks
+     * hitting the same four addresses cost 5.5 ms in the first version of this kernel) */
+    __shared__ uint32_t s_hist[LF_NCLS];
+    __shared__ uint32_t s_maxq, s_maxt;
+    __shared__ unsigned long long s_maxp, s_cells, s_wc, s_swc;
+    if (threadIdx.x < LF_NCLS) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_maxq = 0; s_maxt = 0; s_maxp = 0; s_cells = 0; s_wc = 0; s_swc = 0; }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.n_tasks) {
+        lf_align_task t = d.tasks[i];
+        int cls = LF_CLS_BAD;
+        uint32_t scr = 0, slot = 0;
+        bool ok = t.q_len >= 1 && t.t_len >= 1 && t.read_id < d.n_reads && t.mode <= LF_MODE_SHW;
+        if (ok) {
+            uint64_t L = d.read_off[t.read_id + 1] - d.read_off[t.read_id];
+            ok = (uint64_t)t.q_off + t.q_len <= L && (int64_t)t.t_off + (int64_t)t.t_len <= d.l_pac
+                 && (uint64_t)t.q_len + t.t_len < (1ull << 31);
         }
-        slot = (t.flags & LF_F_NO_PATH) ? 0u : (t.q_len + t.t_len + 15u) >> 4;
-        atomicAdd(&cnt->cells, (unsigned long long)t.q_len * t.t_len);
-        atomicAdd(&cnt->word_columns, (unsigned long long)nwords * t.t_len);
-    } else {
-        lf_align_result r; r.edit_distance = -1; r.end_location = -1; r.ops_off = 0; r.ops_len = 0; r.status = LF_ERR_BAD_ARG;
-        d.res[i] = r;
+        if (ok) {
+            uint32_t nwords = (t.q_len + 31u) >> 5;
+            int sc = lf_small_class(nwords);
+            if (sc >= 0 && lf_is_leaf(t.q_len, t.t_len)) {
+                cls = 2 * sc + (t.mode == LF_MODE_SHW ? 1 : 0);
+                scr = lf_k1_ckpt_bytes(t.t_len, lf_small_nw(sc));
+                atomicAdd(&s_swc, (unsigned long long)nwords * t.t_len);
+            } else {
+                cls = LF_CLS_LARGE;
+                atomicMax(&s_maxq, t.q_len);
+                atomicMax(&s_maxt, t.t_len);
+                atomicMax(&s_maxp, lf_large_planes_bytes(t.q_len, t.t_len));
+            }
+            slot = (t.flags & LF_F_NO_PATH) ? 0u : (t.q_len + t.t_len + 15u) >> 4;
+            atomicAdd(&s_cells, (unsigned long long)t.q_len * t.t_len);
+            atomicAdd(&s_wc, (unsigned long long)nwords * t.t_len);
+        } else {
+            lf_align_result r; r.edit_distance = -1; r.end_location = -1; r.ops_off = 0; r.ops_len = 0; r.status = LF_ERR_BAD_ARG;
+            d.res[i] = r;
+        }
+        atomicAdd(&s_hist[cls], 1u);
+        uint32_t tt = t.t_len < 0x7ffffffu ? t.t_len : 0x7ffffffu;
+        keys[i] = ((uint32_t)cls << 27) | (0x7ffffffu - tt); /* class-major, long targets first */
+        idx[i] = i;
+        slot_words[i] = slot;
+        scr_bytes[i] = scr;
     }
-    atomicAdd(&cnt->hist[cls], 1u);
-    uint32_t tt = t.t_len < 0x7ffffffu ? t.t_len : 0x7ffffffu;
-    keys[i] = ((uint32_t)cls << 27) | (0x7ffffffu - tt); /* class-major, long targets first */
-    idx[i] = i;
-    slot_words[i] = slot;
-    scr_bytes[i] = scr;
+    __syncthreads();
+    if (threadIdx.x < LF_NCLS && s_hist[threadIdx.x]) atomicAdd(&cnt->hist[threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (s_maxq) atomicMax(&cnt->max_q, s_maxq);
+        if (s_maxt) atomicMax(&cnt->max_t, s_maxt);
+        if (s_maxp) atomicMax(&cnt->max_planes, s_maxp);
+        atomicAdd(&cnt->cells, s_cells);
+        atomicAdd(&cnt->word_columns, s_wc);
+        atomicAdd(&cnt->small_word_columns, s_swc);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -309,15 +357,15 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
     uint2 *ck = (uint2 *)(d.scratch + d.scr_off[ti]);
 
     /* ---- forward pass: distance (+ first best prefix for SHW), checkpoints every C columns ---- */
-    int64_t tpos = tv.t0;
+    LfTCursor tc;
+    tc.init(d.pac, tv.t0, tv.dir);
     for (int c = 0; c < t; c++) {
         if ((c & (C - 1)) == 0 && c) {
             uint2 *dst = ck + (size_t)(c / C - 1) * NW;
 #pragma unroll
             for (int w = 0; w < NW; w++) dst[w] = make_uint2(Pv[w], Mv[w]);
         }
-        uint32_t sym = lf_tsym(d.pac, tpos);
-        tpos += tv.dir;
+        const uint32_t sym = tc.next();
         lf_k1_column<NW, SHW, false, WIN>(Pv, Mv, qlo, qhi, qnn, sym, score, wl, bl, nullptr, 0);
         if (SHW) { if (score < best) { best = score; bestc = c; } }
     }
@@ -356,10 +404,9 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
 #pragma unroll
             for (int w = 0; w < NW; w++) { uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; }
         }
-        tpos = tv.t0 + (int64_t)tv.dir * c0;
+        tc.init(d.pac, tv.t0 + (int64_t)tv.dir * c0, tv.dir);
         for (int c = c0; c < c1; c++) {
-            uint32_t sym = lf_tsym(d.pac, tpos);
-            tpos += tv.dir;
+            const uint32_t sym = tc.next();
             lf_k1_column<NW, false, true, WIN>(Pv, Mv, qlo, qhi, qnn, sym, score, wl, bl, smt + (size_t)(c - c0) * WIN * 2 * LF_K1_BLOCK, wtop);
         }
         const int rowmin = wtop * 32;
@@ -422,12 +469,23 @@ __device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView 
         uint32_t Pv = 0xffffffffu, Mv = 0u;
         uint32_t pay = 0; /* (hout+1) | sym<<2 produced by this lane in the previous step */
         const int nsteps = tl + nv - 1;
+        LfTCursor tc;      /* lane 0 feeds the wavefront: target symbols 16 per load, one word ahead */
+        uint32_t hbw = 0, hbn = 0; /* ... and the strip boundary 4 columns per load, one word ahead */
+        const uint32_t *hb32 = (const uint32_t *)hb;
+        if (lane == 0) {
+            tc.init(d.pac, tv.t0, tv.dir);
+            if (s > 0) { hbw = hb32[0]; hbn = hb32[1]; }
+        }
         for (int step = 0; step < nsteps; step++) {
             uint32_t in = __shfl_up_sync(LF_FULL, pay, 1);
             uint32_t sym; int hin;
             if (lane == 0) {
-                sym = step < tl ? lf_tsym(d.pac, tv.t0 + (int64_t)tv.dir * step) : 0u;
-                hin = (s == 0 || step >= tl) ? 1 : (int)hb[step];
+                sym = step < tl ? tc.next() : 0u;
+                hin = 1;
+                if (s > 0) {
+                    if ((step & 3) == 0 && step) { hbw = hbn; hbn = hb32[(step >> 2) + 1]; }
+                    if (step < tl) hin = (int)(int8_t)(hbw >> ((step & 3) << 3));
+                }
             } else { sym = in >> 2; hin = (int)(in & 3u) - 1; }
             const int c = step - lane;
             const bool act = valid && c >= 0 && c < tl;
@@ -487,21 +545,30 @@ __device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView 
  * writes one byte per op right-aligned below `hi_pos`.  Returns the number of ops. */
 __device__ __forceinline__ int lf_large_traceback(const uint2 *planes, int ql, int tl, uint8_t *opsb, long long hi_pos)
 {
+    /* The walk is serial, so its cost is latency: the 32 lanes fetch the plane words of the next 32
+     * columns of the current word-row at once and the walk then reads them by shuffle instead of
+     * taking an L2 round trip per step. */
     const int lane = threadIdx.x & 31;
     const int n = (ql + 31) >> 5;
     long long p = hi_pos;
     int i = ql, j = tl;
     while (i > 0 && j > 0) {
-        const int rr = i - 1, w = rr >> 5, s = w >> 5, l = w & 31;
+        const int w = (i - 1) >> 5, s = w >> 5, l = w & 31;
         const int nv = n - s * 32 < 32 ? n - s * 32 : 32;
         const unsigned long long sb = (unsigned long long)s * (unsigned long long)(tl + 31) * 32ull;
-        const uint2 v = planes[sb + (unsigned long long)(j - 1 + l) * nv + l];
-        const uint32_t b = (uint32_t)rr & 31u;
-        const uint32_t op = ((v.x >> b) & 1u) | (((v.y >> b) & 1u) << 1);
-        --p;
-        if (lane == 0) opsb[p] = (uint8_t)op;
-        i -= (op != 2u);
-        j -= (op != 1u);
+        const int jt = j, col = j - 1 - lane;
+        uint2 v = make_uint2(0u, 0u);
+        if (col >= 0) v = planes[sb + (unsigned long long)(col + l) * nv + l];
+        while (i > 0 && j > 0 && ((i - 1) >> 5) == w && jt - j < 32) {
+            const int k = jt - j;
+            const uint32_t x = __shfl_sync(LF_FULL, v.x, k), y = __shfl_sync(LF_FULL, v.y, k);
+            const uint32_t b = (uint32_t)(i - 1) & 31u;
+            const uint32_t op = ((x >> b) & 1u) | (((y >> b) & 1u) << 1);
+            --p;
+            if (lane == 0) opsb[p] = (uint8_t)op;
+            i -= (op != 2u);
+            j -= (op != 1u);
+        }
     }
     while (i > 0) { --p; if (lane == 0) opsb[p] = 1; i--; }
     while (j > 0) { --p; if (lane == 0) opsb[p] = 2; j--; }

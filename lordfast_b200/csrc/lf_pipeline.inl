@@ -19,10 +19,13 @@
 #include "lf_backend.h"
 #include "lf_kernels.cuh"
 
+#define LF_NSUB 8
 struct DevState {
     int dev = 0;
     lfb_stream stream = 0;
     lfb_event ev[4] = {};
+    lfb_stream sub[LF_NSUB] = {};   /* size classes run concurrently: their grids are small */
+    lfb_event sub_ev[LF_NSUB] = {};
     LfbBuf pac, bases, read_off, plo, phi, pnn;
     LfbBuf tasks, res, ops, keys, keys2, idx, idx2, slot_words, scr_bytes, slot_end, scr_off, scratch, large_scr, counters, queue;
     LfbBuf etasks, eres, escr_items, escr_off, escr;
@@ -138,20 +141,15 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     ctx->stats.align_tasks += n;
     ctx->stats.cells += ht->cnt.cells;
     ctx->stats.word_columns += ht->cnt.word_columns;
-    ctx->stats.last_main_word_columns = ht->cnt.small_word_columns;
+    ctx->stats.last_main_word_columns = ht->cnt.word_columns; /* all alignment kernels of the step run concurrently */
 
 #ifndef LF_EMU
     cudaEventRecord(d.ev[2], s);
+    for (int k = 0; k < LF_NSUB; k++) cudaStreamWaitEvent(d.sub[k], d.ev[2], 0);
 #endif
-    uint32_t first = 0;
-    for (int cls = 0; cls < LF_CLS_LARGE; cls++) {
-        const uint32_t count = ht->cnt.hist[cls];
-        if (count) launch_small_class(cls, v, d.idx2.as<uint32_t>(), first, count, s);
-        first += count;
-    }
-#ifndef LF_EMU
-    cudaEventRecord(d.ev[3], s);
-#endif
+    /* the large-task kernel first, on its own stream: few warps, long latency, overlaps everything else */
+    uint32_t nsmall = 0;
+    for (int cls = 0; cls < LF_CLS_LARGE; cls++) nsmall += ht->cnt.hist[cls];
     const uint32_t nlarge = ht->cnt.hist[LF_CLS_LARGE];
     if (nlarge) {
         LfLargeCfg cfg;
@@ -164,17 +162,32 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         cfg.off_stack = off; off = align_up(off + LF_LARGE_STACK * 5 * 4, 256);
         cfg.stride = off;
         /* persistent grid of warp slots; bounded so that the scratch stays within a few GB */
-        size_t slots = 148 * 8;
-        const size_t budget = (size_t)6 << 30;
+        size_t slots = 148 * 16;
+        const size_t budget = (size_t)8 << 30;
         if (slots * cfg.stride > budget) slots = budget / cfg.stride;
         if (slots < 1) slots = 1;
         if (slots > nlarge) slots = nlarge;
         LF_TRY(d.large_scr.reserve(slots * cfg.stride));
         cfg.base = d.large_scr.as<uint8_t>();
         cfg.queue = d.queue.as<uint32_t>();
-        LFB_LAUNCH(k_myers_large, (unsigned)slots, 32, 0, s, v, d.idx2.as<uint32_t>(), first, nlarge, cfg);
+        LFB_LAUNCH(k_myers_large, (unsigned)slots, 32, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg);
+    }
+    /* small classes, biggest register footprint first, spread over the other streams */
+    {
+        uint32_t firsts[LF_CLS_LARGE];
+        uint32_t first = 0;
+        for (int cls = 0; cls < LF_CLS_LARGE; cls++) { firsts[cls] = first; first += ht->cnt.hist[cls]; }
+        int k = 0;
+        for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) {
+            const uint32_t count = ht->cnt.hist[cls];
+            if (!count) continue;
+            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, d.sub[1 + (k % (LF_NSUB - 1))]);
+            k++;
+        }
     }
 #ifndef LF_EMU
+    for (int k = 0; k < LF_NSUB; k++) { cudaEventRecord(d.sub_ev[k], d.sub[k]); cudaStreamWaitEvent(s, d.sub_ev[k], 0); }
+    cudaEventRecord(d.ev[3], s);
     cudaEventRecord(d.ev[1], s);
 #endif
     LF_TRY(lfb_last_error());
@@ -213,6 +226,7 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
 #ifndef LF_EMU
         if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; }
         for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
+        for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; } cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
 #endif
         d.pinned = lfb_host_alloc(sizeof(HostTotals));
         if (!d.pinned || d.pac.reserve(pac_bytes + 16)) { lf_gpu_destroy(ctx); return LF_ERR_NOMEM; }
@@ -235,6 +249,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
         lfb_host_free(d.pinned);
 #ifndef LF_EMU
         for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
+        for (int k = 0; k < LF_NSUB; k++) { if (d.sub_ev[k]) cudaEventDestroy(d.sub_ev[k]); if (d.sub[k]) cudaStreamDestroy(d.sub[k]); }
         if (d.stream) cudaStreamDestroy(d.stream);
 #endif
     }

@@ -142,6 +142,8 @@ static inline unsigned __brev(unsigned x)
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{ unsigned long long src = ((unsigned long long)b << 32) | a; unsigned r = 0; for (int k = 0; k < 4; k++) { unsigned n = (sel >> (4 * k)) & 7u; r |= (unsigned)((src >> (8 * n)) & 0xffu) << (8 * k); } return r; }
 
 template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = (T)(o + v); return o; }
 template <typename T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
