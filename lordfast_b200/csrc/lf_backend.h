@@ -55,9 +55,9 @@ static inline int lfb_temp(LfbTemp &t, size_t need) { if (need > t.cap) { lfb_fr
 static inline int lfb_sort_pairs(LfbTemp &tmp, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, size_t n, lfb_stream s)
 {
     size_t need = 0;
-    LFB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, need, kin, kout, vin, vout, (int)n, 0, 32, s));
+    LFB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, need, kin, kout, vin, vout, (int)n, LF_KEY_SHIFT, 32, s));
     if (lfb_temp(tmp, need)) return -2;
-    LFB_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, need, kin, kout, vin, vout, (int)n, 0, 32, s));
+    LFB_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, need, kin, kout, vin, vout, (int)n, LF_KEY_SHIFT, 32, s));
     return 0;
 }
 struct LfbU32ToU64 { __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; } };

@@ -43,6 +43,7 @@
 #define LF_CLS_LARGE 16   /* class id of k_myers_large tasks (small classes are 2*i + shw) */
 #define LF_CLS_BAD 17
 #define LF_NCLS 18
+#define LF_KEY_SHIFT 19    /* sort keys use bits [19,32): 5 bits of class, 8 bits of length bucket */
 #define LF_LARGE_STACK 96 /* Hirschberg stack entries per warp (depth <= log2(t)+2) */
 
 __host__ __device__ __forceinline__ int lf_small_nw(int i)
@@ -113,6 +114,13 @@ struct LfTCursor {
         if (d > 0) { buf <<= 2 * j; left = 16 - j; widx++; }
         else { buf >>= 2 * (15 - j); left = j + 1; widx--; }
         nxt = be(__ldg(p32 + (widx < 0 ? 0 : widx)));
+    }
+    __device__ __forceinline__ void next_masks(uint32_t &slo, uint32_t &shi)
+    { /* all-ones / all-zeros masks of the two bits of the next symbol */
+        if (left == 0) { buf = nxt; left = 16; widx += dir; nxt = be(__ldg(p32 + (widx < 0 ? 0 : widx))); }
+        if (dir > 0) { shi = (uint32_t)((int32_t)buf >> 31); slo = (uint32_t)((int32_t)(buf << 1) >> 31); buf <<= 2; }
+        else { slo = 0u - (buf & 1u); shi = 0u - ((buf >> 1) & 1u); buf >>= 2; }
+        left--;
     }
     __device__ __forceinline__ uint32_t next()
     {
@@ -206,9 +214,9 @@ __global__ void k_pack_reads(LfDev d)
 /* ------------------------------------------------------------------------------------------ */
 __host__ __device__ __forceinline__ unsigned long long lf_large_planes_bytes(uint32_t q, uint32_t t)
 { /* bytes of traceback planes the biggest leaf below (q,t) can need: 8 B per (32-row word x step) */
-    unsigned long long n = (q + 31u) / 32u;
+    unsigned long long n = (q + 31u) / 32u + 8u; /* lanes are padded to whole groups of up to 8 words */
     unsigned long long full = n * ((unsigned long long)t + 32ull) * 8ull;
-    unsigned long long cap = (1ull << 20) + n * 256ull + 4096ull;
+    unsigned long long cap = (1ull << 20) + n * 512ull + 8192ull;
     return full < cap ? full : cap;
 }
 
@@ -254,8 +262,13 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
             d.res[i] = r;
         }
         atomicAdd(&s_hist[cls], 1u);
-        uint32_t tt = t.t_len < 0x7ffffffu ? t.t_len : 0x7ffffffu;
-        keys[i] = ((uint32_t)cls << 27) | (0x7ffffffu - tt); /* class-major, long targets first */
+        /* class-major, long targets first; the target length is quantised to 1/8 octave so that a warp's
+         * 32 tasks run nearly the same number of columns, and inside a bucket the (stable) sort keeps the
+         * submission order, i.e. neighbouring lanes work on neighbouring reads and result slots */
+        const uint32_t tl = t.t_len ? t.t_len : 1u;
+        const uint32_t e = 31u - (uint32_t)__clz((int)tl);
+        const uint32_t m = e >= 3u ? (tl >> (e - 3u)) & 7u : (tl << (3u - e)) & 7u;
+        keys[i] = ((uint32_t)cls << 27) | ((255u - (e * 8u + m)) << LF_KEY_SHIFT);
         idx[i] = i;
         slot_words[i] = slot;
         scr_bytes[i] = scr;
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
 /* ------------------------------------------------------------------------------------------ */
 template <int NW>
 __device__ __forceinline__ void lf_add_chain(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW])
-{ /* s = a + b over a 32*NW-bit word */
+{ /* s = a + b over a 32*NW-bit word (portable form; the device build uses the asm chains below) */
     uint32_t c = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) {
@@ -286,46 +299,186 @@ __device__ __forceinline__ void lf_add_chain(const uint32_t (&a)[NW], const uint
         c = (uint32_t)(x >> 32);
     }
 }
+template <int NW>
+__device__ __forceinline__ void lf_add_chain_cin(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW], uint32_t cin)
+{ /* s = a + b + cin (cin in {0,1}) */
+    uint32_t c = cin;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        unsigned long long x = (unsigned long long)a[w] + b[w] + c;
+        s[w] = (uint32_t)x;
+        c = (uint32_t)(x >> 32);
+    }
+}
+/* generated by the snippet in DESIGN.md (carry chains as one asm block each: IADD3 + IADD3.X per word) */
+#if defined(__CUDA_ARCH__)
+template <> __device__ __forceinline__ void lf_add_chain_cin<1>(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&s)[1], uint32_t cin) { s[0] = a[0] + b[0] + cin; }
+template <> __device__ __forceinline__ void lf_add_chain<2>(const uint32_t (&a)[2], const uint32_t (&b)[2], uint32_t (&s)[2])
+{
+    asm("add.cc.u32 %0, %2, %4;\n\t"
+        "addc.u32 %1, %3, %5;"
+        : "=&r"(s[0]),"=&r"(s[1])
+        : "r"(a[0]),"r"(a[1]),"r"(b[0]),"r"(b[1]));
+}
+template <> __device__ __forceinline__ void lf_add_chain<3>(const uint32_t (&a)[3], const uint32_t (&b)[3], uint32_t (&s)[3])
+{
+    asm("add.cc.u32 %0, %3, %6;\n\t"
+        "addc.cc.u32 %1, %4, %7;\n\t"
+        "addc.u32 %2, %5, %8;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2])
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(b[0]),"r"(b[1]),"r"(b[2]));
+}
+template <> __device__ __forceinline__ void lf_add_chain<4>(const uint32_t (&a)[4], const uint32_t (&b)[4], uint32_t (&s)[4])
+{
+    asm("add.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, %9;\n\t"
+        "addc.cc.u32 %2, %6, %10;\n\t"
+        "addc.u32 %3, %7, %11;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3])
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]));
+}
+template <> __device__ __forceinline__ void lf_add_chain<6>(const uint32_t (&a)[6], const uint32_t (&b)[6], uint32_t (&s)[6])
+{
+    asm("add.cc.u32 %0, %6, %12;\n\t"
+        "addc.cc.u32 %1, %7, %13;\n\t"
+        "addc.cc.u32 %2, %8, %14;\n\t"
+        "addc.cc.u32 %3, %9, %15;\n\t"
+        "addc.cc.u32 %4, %10, %16;\n\t"
+        "addc.u32 %5, %11, %17;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3]),"=&r"(s[4]),"=&r"(s[5])
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(a[4]),"r"(a[5]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]),"r"(b[4]),"r"(b[5]));
+}
+template <> __device__ __forceinline__ void lf_add_chain<8>(const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t (&s)[8])
+{
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3]),"=&r"(s[4]),"=&r"(s[5]),"=&r"(s[6]),"=&r"(s[7])
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(a[4]),"r"(a[5]),"r"(a[6]),"r"(a[7]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]),"r"(b[4]),"r"(b[5]),"r"(b[6]),"r"(b[7]));
+}
+template <> __device__ __forceinline__ void lf_add_chain<12>(const uint32_t (&a)[12], const uint32_t (&b)[12], uint32_t (&s)[12])
+{
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, %33;\n\t"
+        "addc.cc.u32 %10, %22, %34;\n\t"
+        "addc.u32 %11, %23, %35;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3]),"=&r"(s[4]),"=&r"(s[5]),"=&r"(s[6]),"=&r"(s[7]),"=&r"(s[8]),"=&r"(s[9]),"=&r"(s[10]),"=&r"(s[11])
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(a[4]),"r"(a[5]),"r"(a[6]),"r"(a[7]),"r"(a[8]),"r"(a[9]),"r"(a[10]),"r"(a[11]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]),"r"(b[4]),"r"(b[5]),"r"(b[6]),"r"(b[7]),"r"(b[8]),"r"(b[9]),"r"(b[10]),"r"(b[11]));
+}
+template <> __device__ __forceinline__ void lf_add_chain<16>(const uint32_t (&a)[16], const uint32_t (&b)[16], uint32_t (&s)[16])
+{
+    asm("add.cc.u32 %0, %16, %32;\n\t"
+        "addc.cc.u32 %1, %17, %33;\n\t"
+        "addc.cc.u32 %2, %18, %34;\n\t"
+        "addc.cc.u32 %3, %19, %35;\n\t"
+        "addc.cc.u32 %4, %20, %36;\n\t"
+        "addc.cc.u32 %5, %21, %37;\n\t"
+        "addc.cc.u32 %6, %22, %38;\n\t"
+        "addc.cc.u32 %7, %23, %39;\n\t"
+        "addc.cc.u32 %8, %24, %40;\n\t"
+        "addc.cc.u32 %9, %25, %41;\n\t"
+        "addc.cc.u32 %10, %26, %42;\n\t"
+        "addc.cc.u32 %11, %27, %43;\n\t"
+        "addc.cc.u32 %12, %28, %44;\n\t"
+        "addc.cc.u32 %13, %29, %45;\n\t"
+        "addc.cc.u32 %14, %30, %46;\n\t"
+        "addc.u32 %15, %31, %47;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3]),"=&r"(s[4]),"=&r"(s[5]),"=&r"(s[6]),"=&r"(s[7]),"=&r"(s[8]),"=&r"(s[9]),"=&r"(s[10]),"=&r"(s[11]),"=&r"(s[12]),"=&r"(s[13]),"=&r"(s[14]),"=&r"(s[15])
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(a[4]),"r"(a[5]),"r"(a[6]),"r"(a[7]),"r"(a[8]),"r"(a[9]),"r"(a[10]),"r"(a[11]),"r"(a[12]),"r"(a[13]),"r"(a[14]),"r"(a[15]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]),"r"(b[4]),"r"(b[5]),"r"(b[6]),"r"(b[7]),"r"(b[8]),"r"(b[9]),"r"(b[10]),"r"(b[11]),"r"(b[12]),"r"(b[13]),"r"(b[14]),"r"(b[15]));
+}
+template <> __device__ __forceinline__ void lf_add_chain_cin<2>(const uint32_t (&a)[2], const uint32_t (&b)[2], uint32_t (&s)[2], uint32_t cin)
+{
+    uint32_t tmp;
+    asm("add.cc.u32 %2, %7, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %3, %5;\n\t"
+        "addc.u32 %1, %4, %6;"
+        : "=&r"(s[0]),"=&r"(s[1]), "=&r"(tmp)
+        : "r"(a[0]),"r"(a[1]),"r"(b[0]),"r"(b[1]), "r"(cin));
+}
+template <> __device__ __forceinline__ void lf_add_chain_cin<4>(const uint32_t (&a)[4], const uint32_t (&b)[4], uint32_t (&s)[4], uint32_t cin)
+{
+    uint32_t tmp;
+    asm("add.cc.u32 %4, %13, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.u32 %3, %8, %12;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3]), "=&r"(tmp)
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]), "r"(cin));
+}
+template <> __device__ __forceinline__ void lf_add_chain_cin<8>(const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t (&s)[8], uint32_t cin)
+{
+    uint32_t tmp;
+    asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.u32 %7, %16, %24;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3]),"=&r"(s[4]),"=&r"(s[5]),"=&r"(s[6]),"=&r"(s[7]), "=&r"(tmp)
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(a[4]),"r"(a[5]),"r"(a[6]),"r"(a[7]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]),"r"(b[4]),"r"(b[5]),"r"(b[6]),"r"(b[7]), "r"(cin));
+}
+#endif
 
 /* Advance the whole column by one target symbol (Myers 1999 / Hyyro 2003 recurrences on one long
  * word; the per-block hin/hout of edlib's calculateBlock, edlib.cpp:335-370, become the add carry
- * and the bits shifted between words).  STORE additionally writes, for the WIN words starting at
- * wtop, the two traceback planes of this column: op = 1 (up) if Pv', else 2 (left) if Ph, else
- * 0/3 by Eq -- plane0 = low op bit, plane1 = high op bit. */
+ * and the bits funnel-shifted between words): 12 integer instructions per word.
+ * STORE additionally writes, for the WIN words starting at wtop, the two traceback planes of this
+ * column: op = 1 (up) if Pv', else 2 (left) if Ph, else 0/3 by Eq -- plane0 = low op bit, plane1 =
+ * high op bit -- and skips the words below the window (w > whi), which the walk can never reach. */
 template <int NW, bool SHW, bool STORE, int WIN>
 __device__ __forceinline__ void lf_k1_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&qlo)[NW],
-                                             const uint32_t (&qhi)[NW], const uint32_t (&qnn)[NW], uint32_t sym, int &score,
-                                             int wl, uint32_t bl, uint32_t *sm, int wtop)
+                                             const uint32_t (&qhi)[NW], const uint32_t (&qnn)[NW], uint32_t slo, uint32_t shi, int &score,
+                                             int wl, uint32_t bl, uint32_t *sm, int wtop, int whi)
 {
-    const uint32_t slo = 0u - (sym & 1u), shi = 0u - (sym >> 1);
     uint32_t Eq[NW], a[NW], sum[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        Eq[w] = ~((qlo[w] ^ slo) | (qhi[w] ^ shi) | qnn[w]);
-        a[w] = Eq[w] & Pv[w];
+        if (!STORE || w <= whi) {
+            Eq[w] = ~((qlo[w] ^ slo) | (qhi[w] ^ shi) | qnn[w]);
+            a[w] = Eq[w] & Pv[w];
+        } else { Eq[w] = 0; a[w] = 0; }
     }
     lf_add_chain<NW>(a, Pv, sum);
-    uint32_t phc = 1u, mhc = 0u; /* row 0 of a global alignment grows by one per column */
+    uint32_t pPh = 0x80000000u, pMh = 0u; /* row 0 of a global alignment grows by one per column */
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        uint32_t Xh = (sum[w] ^ Pv[w]) | Eq[w];
-        uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
-        uint32_t Mh = Pv[w] & Xh;
-        uint32_t Xv = Eq[w] | Mv[w];
-        if (SHW) { if (w == wl) score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u); }
-        uint32_t Phs = (Ph << 1) | phc, Mhs = (Mh << 1) | mhc;
-        phc = Ph >> 31; mhc = Mh >> 31;
-        uint32_t nPv = Mhs | ~(Xv | Phs);
-        uint32_t nMv = Phs & Xv;
-        if (STORE) {
-            int wi = w - wtop;
-            if (wi >= 0 && wi < WIN) {
-                uint32_t diagx = ~(nPv | Ph | Eq[w]);              /* diagonal step over a mismatch */
-                sm[(wi * 2 + 0) * LF_K1_BLOCK] = nPv | diagx;       /* ops 1, 3 */
-                sm[(wi * 2 + 1) * LF_K1_BLOCK] = (~nPv & Ph) | diagx; /* ops 2, 3 */
+        if (!STORE || w <= whi) {
+            const uint32_t Xh = (sum[w] ^ Pv[w]) | Eq[w];
+            const uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
+            const uint32_t Mh = Pv[w] & Xh;
+            const uint32_t Xv = Eq[w] | Mv[w];
+            if (SHW) { if (w == wl) score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u); }
+            const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
+            pPh = Ph; pMh = Mh;
+            const uint32_t nPv = Mhs | ~(Xv | Phs);
+            const uint32_t nMv = Phs & Xv;
+            if (STORE) {
+                const int wi = w - wtop;
+                if (wi >= 0 && wi < WIN) {
+                    const uint32_t diagx = ~(nPv | Ph | Eq[w]);              /* diagonal step over a mismatch */
+                    sm[(wi * 2 + 0) * LF_K1_BLOCK] = nPv | diagx;         /* ops 1, 3 */
+                    sm[(wi * 2 + 1) * LF_K1_BLOCK] = (~nPv & Ph) | diagx; /* ops 2, 3 */
+                }
             }
+            Pv[w] = nPv; Mv[w] = nMv;
         }
-        Pv[w] = nPv; Mv[w] = nMv;
     }
 }
 
@@ -365,8 +518,9 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
 #pragma unroll
             for (int w = 0; w < NW; w++) dst[w] = make_uint2(Pv[w], Mv[w]);
         }
-        const uint32_t sym = tc.next();
-        lf_k1_column<NW, SHW, false, WIN>(Pv, Mv, qlo, qhi, qnn, sym, score, wl, bl, nullptr, 0);
+        uint32_t slo, shi;
+        tc.next_masks(slo, shi);
+        lf_k1_column<NW, SHW, false, WIN>(Pv, Mv, qlo, qhi, qnn, slo, shi, score, wl, bl, nullptr, 0, NW);
         if (SHW) { if (score < best) { best = score; bestc = c; } }
     }
     int ed, end;
@@ -387,11 +541,13 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
 
     /* ---- traceback: recompute 16-column blocks from their checkpoint, keep a WIN-word window of
      *      the op planes in shared memory, walk Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
-    uint64_t p = slot_hi;
-    uint32_t cur = 0;
-#define LF_EMIT(op) do { --p; cur |= (uint32_t)(op) << (((uint32_t)p & 15u) << 1); if (((uint32_t)p & 15u) == 0u) { d.ops[p >> 4] = cur; cur = 0; } } while (0)
+    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1; /* word the next (right-most free) op goes to */
+    uint32_t cur = 0, nops = 0;
+    int sh = 30;
+#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
     int i = q, j = end + 1;
     uint32_t *smt = smem + tid;
+    constexpr int CS = WIN * 2 * LF_K1_BLOCK; /* shared-memory words per column */
     while (i > 0 && j > 0) {
         const int c1 = j, c0 = ((j - 1) / C) * C;
         const int whi = (i - 1) >> 5;
@@ -402,28 +558,38 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
         } else {
             const uint2 *src = ck + (size_t)(c0 / C - 1) * NW;
 #pragma unroll
-            for (int w = 0; w < NW; w++) { uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; }
+            for (int w = 0; w < NW; w++) { if (w <= whi) { uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; } }
         }
         tc.init(d.pac, tv.t0 + (int64_t)tv.dir * c0, tv.dir);
         for (int c = c0; c < c1; c++) {
-            const uint32_t sym = tc.next();
-            lf_k1_column<NW, false, true, WIN>(Pv, Mv, qlo, qhi, qnn, sym, score, wl, bl, smt + (size_t)(c - c0) * WIN * 2 * LF_K1_BLOCK, wtop);
+            uint32_t slo, shi;
+            tc.next_masks(slo, shi);
+            lf_k1_column<NW, false, true, WIN>(Pv, Mv, qlo, qhi, qnn, slo, shi, score, wl, bl, smt + (size_t)(c - c0) * CS, wtop, whi);
         }
+        /* walk inside the window, one word-row at a time */
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
-            const int rr = i - 1;
-            const uint32_t *cell = smt + (size_t)(((j - 1 - c0) * WIN + ((rr >> 5) - wtop)) * 2) * LF_K1_BLOCK;
-            uint32_t b = (uint32_t)rr & 31u;
-            uint32_t op = ((cell[0] >> b) & 1u) | (((cell[LF_K1_BLOCK] >> b) & 1u) << 1);
-            LF_EMIT(op);
-            i -= (op != 2u);
-            j -= (op != 1u);
+            const int wrow = (i - 1) >> 5;
+            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * LF_K1_BLOCK;
+            int b = (i - 1) & 31;
+            do {
+                const uint32_t x0 = cell[0] >> b, x1 = cell[LF_K1_BLOCK] >> b;
+                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
+                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
+                LF_EMIT(op);
+                b -= 1 - stay_row;
+                j -= 1 - stay_col;
+                cell -= (1 - stay_col) * CS;
+            } while (b >= 0 && j > c0);
+            i = wrow * 32 + b + 1;
         }
     }
     while (i > 0) { LF_EMIT(1u); i--; } /* left column: the rest of the query is inserted   */
     while (j > 0) { LF_EMIT(2u); j--; } /* top row: the rest of the target is deleted        */
-    if ((uint32_t)p & 15u) d.ops[p >> 4] = cur;
+    if (sh != 30) *wptr = cur;
 #undef LF_EMIT
+    const uint64_t p = slot_hi - nops;
     r.ops_off = p; r.ops_len = (uint32_t)(slot_hi - p);
     d.res[ti] = r;
 }
@@ -442,31 +608,47 @@ enum { LF_PASS_STORE = 1, LF_PASS_SHW = 2, LF_PASS_COL = 4 };
 
 struct LfPassOut { int ed, best, bestc; };
 
-/* One wavefront pass over (query view, target view).  Lane l of strip s owns rows 32*(32s+l)..+31
- * and at step k works on column k-l; hout and the target symbol travel to lane l+1 by __shfl_up.
- * Strips of 32 words run one after the other, chained through hb[] (hout below the strip's last
- * row for every column).  Returns D(ql, tl) in .ed; with LF_PASS_SHW also the minimum of the last
- * row and the first column reaching it; LF_PASS_COL writes D(x, tl), x = 0..ql, to col[];
- * LF_PASS_STORE writes the traceback planes: uint2 at planes[strip_base + step*nv + lane]. */
-__device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
-                                                  uint2 *planes, int8_t *hb, int32_t *col)
+/* words of 32 rows each lane owns in a wavefront pass over a query of ql rows */
+__host__ __device__ __forceinline__ int lf_wpl(int ql)
+{
+    const int n = (ql + 31) >> 5;
+    return n <= 32 ? 1 : n <= 64 ? 2 : n <= 128 ? 4 : 8;
+}
+
+/* One wavefront pass over (query view, target view).  Lane l of strip s owns WPL consecutive words
+ * (32*WPL rows) as one long word (carry chain inside the lane) and at step k works on column k-l;
+ * hout and the target symbol travel to lane l+1 by __shfl_up, where hout enters as the add's carry-in
+ * and the bits shifted into Ph/Mh.  Strips of 32*WPL words run one after the other, chained through
+ * hb[] (only queries above 8192 rows need a second strip).  Returns D(ql, tl) in .ed; with
+ * LF_PASS_SHW also the minimum of the last row and the first column reaching it; LF_PASS_COL writes
+ * D(x, tl), x = 0..ql, to col[]; LF_PASS_STORE writes the traceback planes as uint2 at
+ * planes[strip_base + (step*nv + lane)*WPL + k]. */
+template <int WPL>
+__device__ __forceinline__ LfPassOut lf_wave_pass_t(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
+                                                    uint2 *planes, int8_t *hb, int32_t *col)
 {
     const int lane = threadIdx.x & 31;
     const int n = (ql + 31) >> 5;
-    const int S = (n + 31) >> 5;
+    const int SW = 32 * WPL;                   /* words per strip */
+    const int S = (n + SW - 1) / SW;
     const int wl = (ql - 1) >> 5;
     const uint32_t bl = (uint32_t)(ql - 1) & 31u;
-    int score = ql, best = ql, bestc = -1; /* tracked by the lane owning row ql-1 */
-    int colbase = tl;                      /* D(32*w, tl) carried across strips */
+    int score = ql, best = ql, bestc = -1;     /* tracked by the lane owning row ql-1 */
+    int colbase = tl;                          /* D(first row of the strip, tl) carried across strips */
     unsigned long long sbase = 0;
     if ((flags & LF_PASS_COL) && lane == 0) col[0] = tl;
     for (int s = 0; s < S; s++) {
-        const int w = s * 32 + lane;
-        const int nv = n - s * 32 < 32 ? n - s * 32 : 32;
+        const int w0 = (s * 32 + lane) * WPL;
+        const int nvw = n - s * SW < SW ? n - s * SW : SW;
+        const int nv = (nvw + WPL - 1) / WPL;
         const bool valid = lane < nv;
-        uint32_t lo = 0, hi = 0, nn = 0xffffffffu;
-        if (valid) lf_q32(d, qv, (int64_t)w * 32, lo, hi, nn);
-        uint32_t Pv = 0xffffffffu, Mv = 0u;
+        uint32_t lo[WPL], hi[WPL], nn[WPL], Pv[WPL], Mv[WPL];
+#pragma unroll
+        for (int k = 0; k < WPL; k++) {
+            lo[k] = 0; hi[k] = 0; nn[k] = 0xffffffffu;
+            if (valid && w0 + k < n) lf_q32(d, qv, (int64_t)(w0 + k) * 32, lo[k], hi[k], nn[k]);
+            Pv[k] = 0xffffffffu; Mv[k] = 0u;
+        }
         uint32_t pay = 0; /* (hout+1) | sym<<2 produced by this lane in the previous step */
         const int nsteps = tl + nv - 1;
         LfTCursor tc;      /* lane 0 feeds the wavefront: target symbols 16 per load, one word ahead */
@@ -477,7 +659,7 @@ __device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView 
             if (s > 0) { hbw = hb32[0]; hbn = hb32[1]; }
         }
         for (int step = 0; step < nsteps; step++) {
-            uint32_t in = __shfl_up_sync(LF_FULL, pay, 1);
+            const uint32_t in = __shfl_up_sync(LF_FULL, pay, 1);
             uint32_t sym; int hin;
             if (lane == 0) {
                 sym = step < tl ? tc.next() : 0u;
@@ -492,42 +674,63 @@ __device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView 
             int hout = 0;
             if (act) {
                 const uint32_t slo = 0u - (sym & 1u), shi = 0u - (sym >> 1);
-                const uint32_t Eq = ~((lo ^ slo) | (hi ^ shi) | nn);
-                const uint32_t hneg = hin < 0 ? 1u : 0u, hpos = hin > 0 ? 1u : 0u;
-                const uint32_t Xv = Eq | Mv;
-                const uint32_t Eq2 = Eq | hneg;
-                const uint32_t Xh = (((Eq2 & Pv) + Pv) ^ Pv) | Eq2;
-                const uint32_t Ph = Mv | ~(Xh | Pv);
-                const uint32_t Mh = Pv & Xh;
-                hout = (int)(Ph >> 31) - (int)(Mh >> 31);
-                if ((flags & LF_PASS_SHW) && w == wl) {
-                    score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u);
-                    if (score < best) { best = score; bestc = c; }
+                uint32_t Eq[WPL], a[WPL], sum[WPL];
+#pragma unroll
+                for (int k = 0; k < WPL; k++) {
+                    Eq[k] = ~((lo[k] ^ slo) | (hi[k] ^ shi) | nn[k]);
+                    a[k] = Eq[k] & Pv[k];
                 }
-                const uint32_t Phs = (Ph << 1) | hpos, Mhs = (Mh << 1) | hneg;
-                const uint32_t nPv = Mhs | ~(Xv | Phs);
-                const uint32_t nMv = Phs & Xv;
-                if (flags & LF_PASS_STORE) {
-                    const uint32_t diagx = ~(nPv | Ph | Eq);
-                    planes[sbase + (unsigned long long)step * nv + lane] = make_uint2(nPv | diagx, (~nPv & Ph) | diagx);
+                const uint32_t hneg = hin < 0 ? 1u : 0u;
+                lf_add_chain_cin<WPL>(a, Pv, sum, hneg);   /* hin = -1 enters as the carry-in */
+                uint32_t pPh = hin > 0 ? 0x80000000u : 0u, pMh = hneg << 31;
+                uint2 *dst = planes + sbase + ((unsigned long long)step * nv + lane) * WPL;
+#pragma unroll
+                for (int k = 0; k < WPL; k++) {
+                    const uint32_t Xh = (sum[k] ^ Pv[k]) | Eq[k] | (k == 0 ? hneg : 0u);
+                    const uint32_t Ph = Mv[k] | ~(Xh | Pv[k]);
+                    const uint32_t Mh = Pv[k] & Xh;
+                    const uint32_t Xv = Eq[k] | Mv[k];
+                    if ((flags & LF_PASS_SHW) && w0 + k == wl) {
+                        score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u);
+                        if (score < best) { best = score; bestc = c; }
+                    }
+                    const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
+                    pPh = Ph; pMh = Mh;
+                    const uint32_t nPv = Mhs | ~(Xv | Phs);
+                    const uint32_t nMv = Phs & Xv;
+                    if (flags & LF_PASS_STORE) {
+                        const uint32_t diagx = ~(nPv | Ph | Eq[k]);
+                        dst[k] = make_uint2(nPv | diagx, (~nPv & Ph) | diagx);
+                    }
+                    Pv[k] = nPv; Mv[k] = nMv;
                 }
-                Pv = nPv; Mv = nMv;
+                const uint32_t phc = pPh >> 31, mhc = pMh >> 31;
+                hout = (int)phc - (int)mhc;
                 if (lane == nv - 1 && s + 1 < S) hb[c] = (int8_t)hout;
             }
             pay = (uint32_t)(hout + 1) | (sym << 2);
         }
-        sbase += (unsigned long long)nsteps * nv;
+        sbase += (unsigned long long)nsteps * nv * WPL;
         /* last column of this strip: vertical deltas -> absolute values */
-        uint32_t m = !valid ? 0u : w < wl ? 0xffffffffu : w == wl ? (0xffffffffu >> (31u - bl)) : 0u;
-        int cnt = __popc(Pv & m) - __popc(Mv & m);
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; k++) {
+            const int w = w0 + k;
+            const uint32_t m = !valid ? 0u : w < wl ? 0xffffffffu : w == wl ? (0xffffffffu >> (31u - bl)) : 0u;
+            cnt += __popc(Pv[k] & m) - __popc(Mv[k] & m);
+        }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(LF_FULL, incl, o); if (lane >= o) incl += v; }
         if (flags & LF_PASS_COL) {
             if (valid) {
                 int v = colbase + incl - cnt;
-                int rows = ql - w * 32 < 32 ? ql - w * 32 : 32;
-                for (int b = 0; b < rows; b++) { v += (int)((Pv >> b) & 1u) - (int)((Mv >> b) & 1u); col[w * 32 + b + 1] = v; }
+#pragma unroll
+                for (int k = 0; k < WPL; k++) {
+                    const int w = w0 + k;
+                    const int rows = ql - w * 32 < 32 ? ql - w * 32 : 32;
+                    for (int b = 0; b < rows; b++) { v += (int)((Pv[k] >> b) & 1u) - (int)((Mv[k] >> b) & 1u); col[w * 32 + b + 1] = v; }
+                }
             }
         }
         colbase += __shfl_sync(LF_FULL, incl, 31);
@@ -535,33 +738,45 @@ __device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView 
     }
     LfPassOut o;
     o.ed = colbase;
-    const int owner = wl & 31;
+    const int owner = ((wl % SW) / WPL) & 31;
     o.best = __shfl_sync(LF_FULL, best, owner);
     o.bestc = __shfl_sync(LF_FULL, bestc, owner);
     return o;
 }
 
-/* Canonical traceback over stored planes; every lane walks the same path (uniform loads), lane 0
- * writes one byte per op right-aligned below `hi_pos`.  Returns the number of ops. */
+__device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
+                                                  uint2 *planes, int8_t *hb, int32_t *col)
+{
+    switch (lf_wpl(ql)) {
+    case 1: return lf_wave_pass_t<1>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    case 2: return lf_wave_pass_t<2>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    case 4: return lf_wave_pass_t<4>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    default: return lf_wave_pass_t<8>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    }
+}
+
+/* Canonical traceback over stored planes.  The walk is serial, so its cost is latency: the 32
+ * lanes fetch the plane words of the next 32 columns of the current word-row at once and the walk
+ * then reads them by shuffle instead of taking an L2 round trip per step.  Every lane walks the same
+ * path; lane 0 writes one byte per op right-aligned below `hi_pos`.  Returns the number of ops. */
 __device__ __forceinline__ int lf_large_traceback(const uint2 *planes, int ql, int tl, uint8_t *opsb, long long hi_pos)
 {
-    /* The walk is serial, so its cost is latency: the 32 lanes fetch the plane words of the next 32
-     * columns of the current word-row at once and the walk then reads them by shuffle instead of
-     * taking an L2 round trip per step. */
     const int lane = threadIdx.x & 31;
     const int n = (ql + 31) >> 5;
+    const int WPL = lf_wpl(ql), SW = 32 * WPL;
     long long p = hi_pos;
     int i = ql, j = tl;
     while (i > 0 && j > 0) {
-        const int w = (i - 1) >> 5, s = w >> 5, l = w & 31;
-        const int nv = n - s * 32 < 32 ? n - s * 32 : 32;
-        const unsigned long long sb = (unsigned long long)s * (unsigned long long)(tl + 31) * 32ull;
-        const int jt = j, col = j - 1 - lane;
+        const int w = (i - 1) >> 5, s = w / SW, l = (w % SW) / WPL, k = w % WPL;
+        const int nvw = n - s * SW < SW ? n - s * SW : SW;
+        const int nv = (nvw + WPL - 1) / WPL;
+        const unsigned long long sb = (unsigned long long)s * (unsigned long long)(tl + 31) * 32ull * (unsigned long long)WPL;
+        const int jt = j, colr = j - 1 - lane;
         uint2 v = make_uint2(0u, 0u);
-        if (col >= 0) v = planes[sb + (unsigned long long)(col + l) * nv + l];
+        if (colr >= 0) v = planes[sb + ((unsigned long long)(colr + l) * nv + l) * WPL + k];
         while (i > 0 && j > 0 && ((i - 1) >> 5) == w && jt - j < 32) {
-            const int k = jt - j;
-            const uint32_t x = __shfl_sync(LF_FULL, v.x, k), y = __shfl_sync(LF_FULL, v.y, k);
+            const int kk = jt - j;
+            const uint32_t x = __shfl_sync(LF_FULL, v.x, kk), y = __shfl_sync(LF_FULL, v.y, kk);
             const uint32_t b = (uint32_t)(i - 1) & 31u;
             const uint32_t op = ((x >> b) & 1u) | (((y >> b) & 1u) << 1);
             --p;
@@ -609,9 +824,12 @@ __device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const
     const bool want = !(task.flags & LF_F_NO_PATH);
     int ed, end;
     bool stored = false; /* planes of the whole task are already in `planes` */
+    bool ed_known = true;
     if (!shw && want && lf_is_leaf((uint32_t)q, (uint32_t)t)) {
         LfPassOut o = lf_wave_pass(d, qv, q, tv, t, LF_PASS_STORE, planes, hb, nullptr);
         ed = o.ed; end = t - 1; stored = true;
+    } else if (!shw && want) {
+        ed = -1; end = t - 1; ed_known = false; /* the first split yields min_x L[x]+R[x] = the distance */
     } else {
         LfPassOut o = lf_wave_pass(d, qv, q, tv, t, shw ? LF_PASS_SHW : 0, planes, hb, nullptr);
         if (shw) { ed = o.best; end = o.bestc; } else { ed = o.ed; end = t - 1; }
@@ -631,7 +849,7 @@ __device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const
     int status = 0;
     while (sp > 0) {
         sp--;
-        const int qo = stack[sp * 5 + 0], ql = stack[sp * 5 + 1], to = stack[sp * 5 + 2], tl = stack[sp * 5 + 3], best = stack[sp * 5 + 4];
+        const int qo = stack[sp * 5 + 0], ql = stack[sp * 5 + 1], to = stack[sp * 5 + 2], tl = stack[sp * 5 + 3], best_in = stack[sp * 5 + 4];
         __syncwarp();
         if (ql == 0) { lf_warp_fill(opsb + outpos, tl, 2); outpos += tl; continue; }
         if (tl == 0) { lf_warp_fill(opsb + outpos, ql, 1); outpos += ql; continue; }
@@ -654,6 +872,14 @@ __device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const
         lf_wave_pass(d, lf_qsub(qv, qo, ql, false), ql, lf_tsub(tv, to, lw, false), lw, LF_PASS_COL, planes, hb, Lc);
         lf_wave_pass(d, lf_qsub(qv, qo, ql, true), ql, lf_tsub(tv, to + lw, rw, true), rw, LF_PASS_COL, planes, hb, Rc);
         __syncwarp();
+        int best = best_in;
+        if (!ed_known) { /* distance of the whole task = min over all split rows */
+            int m = 0x7fffffff;
+            for (int x0 = lane; x0 <= ql; x0 += 32) { const int v = Lc[x0] + Rc[ql - x0]; m = v < m ? v : m; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { const int v = __shfl_xor_sync(LF_FULL, m, o); m = v < m ? v : m; }
+            best = m; ed = m; ed_known = true;
+        }
         /* smallest interior row, then the top boundary, then the bottom one (edlib.cpp:1257-1289) */
         int x = -1;
         for (int x0 = 1; x0 <= ql - 1 && x < 0; x0 += 32) {
@@ -684,6 +910,7 @@ __device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const
         for (int k = 0; k < 16; k++) { long long pp = wi * 16 + k; if (pp < outpos) word |= (uint32_t)opsb[pp] << (2 * k); }
         d.ops[slot_lo_w + (uint64_t)wi] = word;
     }
+    r.edit_distance = ed;
     r.ops_off = slot_lo_w * 16ull; r.ops_len = (uint32_t)outpos; r.status = status;
     if (lane == 0) d.res[ti] = r;
     __syncwarp();

@@ -16,8 +16,8 @@
 #include <string>
 #include <vector>
 #include "lf_gpu.h"
-#include "lf_backend.h"
 #include "lf_kernels.cuh"
+#include "lf_backend.h"
 
 #define LF_NSUB 8
 struct DevState {

@@ -89,3 +89,31 @@ def test_emu_extend(emu_lib):
     for k, c in enumerate(cases):
         assert (int(er[k]["score"]), int(er[k]["qle"]), int(er[k]["tle"])) == (c["score"], c["qle"], c["tle"])
     g.close()
+
+
+def test_emu_large_and_hirschberg_tasks(emu_lib):
+    """k_myers_large: several words per lane, two strips (q > 8192 rows), SHW with a late best column,
+    and the Hirschberg recursion (sizes above edlib's 1 MiB rule)."""
+    rng = np.random.default_rng(9)
+    ref = sim.make_reference(40000, 4)
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    reads, src = [], []
+    for L in (700, 1500, 2600, 9000):
+        s = int(rng.integers(100, 20000))
+        reads.append(sim._channel(ref[s:s + L], 0.15, rng)[0]); src.append(s)
+    tasks = []
+    for rid in range(4):
+        L = len(reads[rid]); s = src[rid]; tl = int(L / 1.045)
+        if rid < 3:
+            tasks.append((rid, 0, L, s, tl, 0, 0, 0))
+            tasks.append((rid, 0, L, s, tl + 20, 0, 1, 0))
+            tasks.append((rid, 0, L, s, tl, 2, 0, 0))
+            tasks.append((rid, 0, L, int(rng.integers(0, 10000)), max(2, L // 2), 0, 1, 0))
+    tasks.append((3, 0, len(reads[3]), src[3], 300, 0, 0, 0))    # 2 strips of 8 words per lane, leaf
+    tasks.append((3, 0, len(reads[3]), src[3], 320, 1, 1, 0))    # same, SHW, reverse strand
+    tasks.append((3, 0, len(reads[3]), src[3], 700, 0, 0, 0))    # 2 strips + Hirschberg
+    tasks.append((1, 0, 40, 100, 27000, 0, 0, 0))                # one word, very long target, Hirschberg
+    tasks = np.array(tasks, dtype=api.ALIGN_TASK)
+    bad, _, _ = check_align(g, reads, ref, tasks)
+    assert not bad, bad
+    g.close()
