@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2_4.6Mbp_20kx10k", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sv-frac", type=float, default=0.10, help="fraction of SV/chimera reads (0.10 = the configured mix)")
     return ap.parse_args()
 
 
@@ -87,11 +88,11 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(name, seed):
+def make_inputs(name, seed, sv_frac=0.10):
     from lordfast_b200 import sim
     from lordfast_b200.chain_tasks import workload_tasks
     ref_len, n_reads, read_len, e0, e1 = WORKLOADS[name]
-    w = sim.make_workload(ref_len, n_reads, read_len, e0, e1, seed=seed, sv_frac=0.10)
+    w = sim.make_workload(ref_len, n_reads, read_len, e0, e1, seed=seed, sv_frac=sv_frac)
     tasks, chain, kind = workload_tasks(w)
     return w, tasks
 
@@ -168,7 +169,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from lordfast_b200 import api
 
-    w, tasks = make_inputs(wl_name, seed=100 + rank)  # every rank gets its own chunk of the same size
+    w, tasks = make_inputs(wl_name, seed=100 + rank, sv_frac=a.sv_frac)  # every rank gets its own chunk of the same size
     g = api.LfGpu(w.pac, len(w.ref))
     n = len(tasks)
     total_bases = w.total_bases

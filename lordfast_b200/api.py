@@ -65,7 +65,7 @@ class LfGpuError(RuntimeError):
 
 
 def load(lib_path: str | None = None) -> C.CDLL:
-    path = lib_path or DEFAULT_LIB
+    path = lib_path or os.environ.get("LFGPU_LIB") or DEFAULT_LIB  # LFGPU_LIB: another CUDA build of the same library (kernel experiments)
     if not os.path.exists(path):
         raise LfGpuError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                          "(there is no CPU fallback for the alignment stage)")

@@ -38,7 +38,9 @@
 
 #define LF_FULL 0xffffffffu
 #define LF_K1_BLOCK 128   /* threads per block of k_myers_small */
-#define LF_K1_C 16        /* checkpoint interval in columns */
+#ifndef LF_K1_C
+#define LF_K1_C 8         /* checkpoint interval in columns */
+#endif
 #define LF_NSMALL 8       /* register-resident size classes */
 #define LF_CLS_LARGE 16   /* class id of k_myers_large tasks (small classes are 2*i + shw) */
 #define LF_CLS_BAD 17
@@ -441,44 +443,60 @@ template <> __device__ __forceinline__ void lf_add_chain_cin<8>(const uint32_t (
  * and the bits funnel-shifted between words): 12 integer instructions per word.
  * STORE additionally writes, for the WIN words starting at wtop, the two traceback planes of this
  * column: op = 1 (up) if Pv', else 2 (left) if Ph, else 0/3 by Eq -- plane0 = low op bit, plane1 =
- * high op bit -- and skips the words below the window (w > whi), which the walk can never reach. */
-template <int NW, bool SHW, bool STORE, int WIN>
+ * high op bit.  The recompute instantiates this with NW = the number of words down to the window
+ * (words below it can never be reached by the walk) and only the last SPAN words can be window words. */
+template <int NW, bool SHW, bool STORE, int WIN, int SPAN>
 __device__ __forceinline__ void lf_k1_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&qlo)[NW],
                                              const uint32_t (&qhi)[NW], const uint32_t (&qnn)[NW], uint32_t slo, uint32_t shi, int &score,
-                                             int wl, uint32_t bl, uint32_t *sm, int wtop, int whi)
+                                             int wl, uint32_t bl, uint32_t *sm, int wtop)
 {
     uint32_t Eq[NW], a[NW], sum[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        if (!STORE || w <= whi) {
-            Eq[w] = ~((qlo[w] ^ slo) | (qhi[w] ^ shi) | qnn[w]);
-            a[w] = Eq[w] & Pv[w];
-        } else { Eq[w] = 0; a[w] = 0; }
+        Eq[w] = ~((qlo[w] ^ slo) | (qhi[w] ^ shi) | qnn[w]);
+        a[w] = Eq[w] & Pv[w];
     }
     lf_add_chain<NW>(a, Pv, sum);
     uint32_t pPh = 0x80000000u, pMh = 0u; /* row 0 of a global alignment grows by one per column */
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        if (!STORE || w <= whi) {
-            const uint32_t Xh = (sum[w] ^ Pv[w]) | Eq[w];
-            const uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
-            const uint32_t Mh = Pv[w] & Xh;
-            const uint32_t Xv = Eq[w] | Mv[w];
-            if (SHW) { if (w == wl) score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u); }
-            const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
-            pPh = Ph; pMh = Mh;
-            const uint32_t nPv = Mhs | ~(Xv | Phs);
-            const uint32_t nMv = Phs & Xv;
-            if (STORE) {
-                const int wi = w - wtop;
-                if (wi >= 0 && wi < WIN) {
-                    const uint32_t diagx = ~(nPv | Ph | Eq[w]);              /* diagonal step over a mismatch */
-                    sm[(wi * 2 + 0) * LF_K1_BLOCK] = nPv | diagx;         /* ops 1, 3 */
-                    sm[(wi * 2 + 1) * LF_K1_BLOCK] = (~nPv & Ph) | diagx; /* ops 2, 3 */
-                }
+        const uint32_t Xh = (sum[w] ^ Pv[w]) | Eq[w];
+        const uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
+        const uint32_t Mh = Pv[w] & Xh;
+        const uint32_t Xv = Eq[w] | Mv[w];
+        if (SHW) { if (w == wl) score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u); }
+        const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
+        pPh = Ph; pMh = Mh;
+        const uint32_t nPv = Mhs | ~(Xv | Phs);
+        const uint32_t nMv = Phs & Xv;
+        if (STORE && w + SPAN >= NW) {
+            const unsigned wi = (unsigned)(w - wtop);
+            if (wi < (unsigned)WIN) {
+                const uint32_t diagx = ~(nPv | Ph | Eq[w]);              /* diagonal step over a mismatch */
+                sm[(wi * 2 + 0) * LF_K1_BLOCK] = nPv | diagx;         /* ops 1, 3 */
+                sm[(wi * 2 + 1) * LF_K1_BLOCK] = (~nPv & Ph) | diagx; /* ops 2, 3 */
             }
-            Pv[w] = nPv; Mv[w] = nMv;
         }
+        Pv[w] = nPv; Mv[w] = nMv;
+    }
+}
+
+/* Recompute columns [c0, c1) from the state in Pv/Mv, touching only the first NWC words. */
+template <int NW, int NWC, int WIN, int SPAN>
+__device__ __forceinline__ void lf_k1_recompute(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&qlo)[NW], const uint32_t (&qhi)[NW],
+                                                const uint32_t (&qnn)[NW], LfTCursor &tc, int ncols, uint32_t *smt, int wtop)
+{
+    static_assert(NWC <= NW, "");
+    uint32_t (&P)[NWC] = reinterpret_cast<uint32_t (&)[NWC]>(Pv);
+    uint32_t (&M)[NWC] = reinterpret_cast<uint32_t (&)[NWC]>(Mv);
+    const uint32_t (&L)[NWC] = reinterpret_cast<const uint32_t (&)[NWC]>(qlo);
+    const uint32_t (&H)[NWC] = reinterpret_cast<const uint32_t (&)[NWC]>(qhi);
+    const uint32_t (&N)[NWC] = reinterpret_cast<const uint32_t (&)[NWC]>(qnn);
+    int dummy = 0;
+    for (int c = 0; c < ncols; c++) {
+        uint32_t slo, shi;
+        tc.next_masks(slo, shi);
+        lf_k1_column<NWC, false, true, WIN, SPAN>(P, M, L, H, N, slo, shi, dummy, 0, 0u, smt + (size_t)c * (WIN * 2 * LF_K1_BLOCK), wtop);
     }
 }
 
@@ -520,7 +538,7 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
         }
         uint32_t slo, shi;
         tc.next_masks(slo, shi);
-        lf_k1_column<NW, SHW, false, WIN>(Pv, Mv, qlo, qhi, qnn, slo, shi, score, wl, bl, nullptr, 0, NW);
+        lf_k1_column<NW, SHW, false, WIN, 0>(Pv, Mv, qlo, qhi, qnn, slo, shi, score, wl, bl, nullptr, 0);
         if (SHW) { if (score < best) { best = score; bestc = c; } }
     }
     int ed, end;
@@ -561,10 +579,15 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
             for (int w = 0; w < NW; w++) { if (w <= whi) { uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; } }
         }
         tc.init(d.pac, tv.t0 + (int64_t)tv.dir * c0, tv.dir);
-        for (int c = c0; c < c1; c++) {
-            uint32_t slo, shi;
-            tc.next_masks(slo, shi);
-            lf_k1_column<NW, false, true, WIN>(Pv, Mv, qlo, qhi, qnn, slo, shi, score, wl, bl, smt + (size_t)(c - c0) * CS, wtop, whi);
+        {
+            /* words 0..whi only, in compile-time sized variants (a quarter of the class width each) */
+            constexpr int G = NW >= 8 ? NW / 4 : NW == 6 ? 2 : 1;
+            constexpr int SPAN = G + 1 < NW ? G + 1 : NW;
+            const int ncols = c1 - c0;
+            if (NW > G && whi < G) lf_k1_recompute<NW, G, WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
+            else if (NW > 2 * G && whi < 2 * G) lf_k1_recompute<NW, (2 * G < NW ? 2 * G : NW), WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
+            else if (NW > 3 * G && whi < 3 * G) lf_k1_recompute<NW, (3 * G < NW ? 3 * G : NW), WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
+            else lf_k1_recompute<NW, NW, WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
         }
         /* walk inside the window, one word-row at a time */
         const int rowmin = wtop * 32;

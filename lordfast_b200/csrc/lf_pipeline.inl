@@ -19,7 +19,9 @@
 #include "lf_kernels.cuh"
 #include "lf_backend.h"
 
-#define LF_NSUB 8
+#ifndef LF_NSUB
+#define LF_NSUB 18
+#endif
 struct DevState {
     int dev = 0;
     lfb_stream stream = 0;
