@@ -1080,10 +1080,15 @@ __global__ void __launch_bounds__(256) k_int32_peak(uint32_t *out, int iters, ui
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const uint32_t x = a[(k + 3) & 7], y = a[(k + 5) & 7];
-                if (WHICH == 0) a[k] = (a[k] & x) ^ y;                                        /* LOP3  */
-                else if (WHICH == 1) a[k] = a[k] + x + y;                                     /* IADD3 */
-                else if (WHICH == 2) { if (k & 1) a[k] = (a[k] & x) ^ y; else a[k] = a[k] + x + y; }
-                else { if (k & 1) a[k] = (a[k] & x) ^ y; else a[k] = a[k] * x + y; }          /* LOP3 + IMAD */
+                const bool lop = WHICH == 0 || ((WHICH == 2 || WHICH == 3) && (k & 1));
+                if (lop) {
+#if defined(__CUDA_ARCH__)
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x78;" : "+r"(a[k]) : "r"(x), "r"(y)); /* a ^ (x & y): one LOP3 */
+#else
+                    a[k] = a[k] ^ (x & y);
+#endif
+                } else if (WHICH == 1 || WHICH == 2) a[k] = a[k] + x + y;                        /* IADD3 */
+                else a[k] = a[k] * x + y;                                                      /* IMAD  */
             }
         }
     }
