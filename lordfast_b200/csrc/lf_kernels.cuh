@@ -638,18 +638,23 @@ __host__ __device__ __forceinline__ int lf_wpl(int ql)
     return n <= 32 ? 1 : n <= 64 ? 2 : n <= 128 ? 4 : 8;
 }
 
+#define LF_WAVE_CB 8 /* columns a lane advances per wavefront step */
+
 /* One wavefront pass over (query view, target view).  Lane l of strip s owns WPL consecutive words
- * (32*WPL rows) as one long word (carry chain inside the lane) and at step k works on column k-l;
- * hout and the target symbol travel to lane l+1 by __shfl_up, where hout enters as the add's carry-in
- * and the bits shifted into Ph/Mh.  Strips of 32*WPL words run one after the other, chained through
- * hb[] (only queries above 8192 rows need a second strip).  Returns D(ql, tl) in .ed; with
- * LF_PASS_SHW also the minimum of the last row and the first column reaching it; LF_PASS_COL writes
- * D(x, tl), x = 0..ql, to col[]; LF_PASS_STORE writes the traceback planes as uint2 at
- * planes[strip_base + (step*nv + lane)*WPL + k]. */
+ * (32*WPL rows) as one long word (carry chain inside the lane) and at step k works on the block of
+ * LF_WAVE_CB columns number k-l, so the __shfl_up that hands the 8 hout values (2 bits each) to lane
+ * l+1 is paid once per 8 columns and the critical path is ~(t + 8*lanes) column latencies instead of
+ * t shuffle round trips.  hout enters the next lane as the add's carry-in and the bits shifted into
+ * Ph/Mh.  Every lane reads the target through its own cursor.  Strips of 32*WPL words run one after
+ * the other, chained through hb[] (only queries above 8192 rows need a second strip).
+ * Returns D(ql, tl) in .ed; with LF_PASS_SHW also the minimum of the last row and the first column
+ * reaching it; LF_PASS_COL writes D(x, tl), x = 0..ql, to col[]; LF_PASS_STORE writes the traceback
+ * planes as uint2 at planes[strip_base + (column*nv + lane)*WPL + k]. */
 template <int WPL>
 __device__ __forceinline__ LfPassOut lf_wave_pass_t(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
                                                     uint2 *planes, int8_t *hb, int32_t *col)
 {
+    constexpr int CB = LF_WAVE_CB;
     const int lane = threadIdx.x & 31;
     const int n = (ql + 31) >> 5;
     const int SW = 32 * WPL;                   /* words per strip */
@@ -660,6 +665,7 @@ __device__ __forceinline__ LfPassOut lf_wave_pass_t(const LfDev &d, const LfQVie
     int colbase = tl;                          /* D(first row of the strip, tl) carried across strips */
     unsigned long long sbase = 0;
     if ((flags & LF_PASS_COL) && lane == 0) col[0] = tl;
+    const int nblocks = (tl + CB - 1) / CB;
     for (int s = 0; s < S; s++) {
         const int w0 = (s * 32 + lane) * WPL;
         const int nvw = n - s * SW < SW ? n - s * SW : SW;
@@ -672,68 +678,64 @@ __device__ __forceinline__ LfPassOut lf_wave_pass_t(const LfDev &d, const LfQVie
             if (valid && w0 + k < n) lf_q32(d, qv, (int64_t)(w0 + k) * 32, lo[k], hi[k], nn[k]);
             Pv[k] = 0xffffffffu; Mv[k] = 0u;
         }
-        uint32_t pay = 0; /* (hout+1) | sym<<2 produced by this lane in the previous step */
-        const int nsteps = tl + nv - 1;
-        LfTCursor tc;      /* lane 0 feeds the wavefront: target symbols 16 per load, one word ahead */
-        uint32_t hbw = 0, hbn = 0; /* ... and the strip boundary 4 columns per load, one word ahead */
-        const uint32_t *hb32 = (const uint32_t *)hb;
-        if (lane == 0) {
-            tc.init(d.pac, tv.t0, tv.dir);
-            if (s > 0) { hbw = hb32[0]; hbn = hb32[1]; }
-        }
+        uint32_t pay = 0; /* (hout+1) of the 8 columns this lane did in the previous step, 2 bits each */
+        const int nsteps = nblocks + nv - 1;
+        LfTCursor tc;
+        tc.init(d.pac, tv.t0, tv.dir); /* every lane starts at column 0 when its first block arrives */
         for (int step = 0; step < nsteps; step++) {
-            const uint32_t in = __shfl_up_sync(LF_FULL, pay, 1);
-            uint32_t sym; int hin;
-            if (lane == 0) {
-                sym = step < tl ? tc.next() : 0u;
-                hin = 1;
-                if (s > 0) {
-                    if ((step & 3) == 0 && step) { hbw = hbn; hbn = hb32[(step >> 2) + 1]; }
-                    if (step < tl) hin = (int)(int8_t)(hbw >> ((step & 3) << 3));
-                }
-            } else { sym = in >> 2; hin = (int)(in & 3u) - 1; }
-            const int c = step - lane;
-            const bool act = valid && c >= 0 && c < tl;
-            int hout = 0;
+            uint32_t in = __shfl_up_sync(LF_FULL, pay, 1);
+            const int cb = step - lane;
+            const bool act = valid && cb >= 0 && cb < nblocks;
+            pay = 0;
             if (act) {
-                const uint32_t slo = 0u - (sym & 1u), shi = 0u - (sym >> 1);
-                uint32_t Eq[WPL], a[WPL], sum[WPL];
-#pragma unroll
-                for (int k = 0; k < WPL; k++) {
-                    Eq[k] = ~((lo[k] ^ slo) | (hi[k] ^ shi) | nn[k]);
-                    a[k] = Eq[k] & Pv[k];
+                const int cbase = cb * CB;
+                if (lane == 0) { /* row 0 of the strip: +1 per column, or the previous strip's bottom row */
+                    in = 0xaaaau;
+                    if (s > 0) { in = 0; for (int ci = 0; ci < CB && cbase + ci < tl; ci++) in |= (uint32_t)((int)hb[cbase + ci] + 1) << (2 * ci); }
                 }
-                const uint32_t hneg = hin < 0 ? 1u : 0u;
-                lf_add_chain_cin<WPL>(a, Pv, sum, hneg);   /* hin = -1 enters as the carry-in */
-                uint32_t pPh = hin > 0 ? 0x80000000u : 0u, pMh = hneg << 31;
-                uint2 *dst = planes + sbase + ((unsigned long long)step * nv + lane) * WPL;
+                const int ncol = tl - cbase < CB ? tl - cbase : CB;
+                for (int ci = 0; ci < ncol; ci++) {
+                    const int c = cbase + ci;
+                    const int hin = (int)((in >> (2 * ci)) & 3u) - 1;
+                    uint32_t slo, shi;
+                    tc.next_masks(slo, shi);
+                    uint32_t Eq[WPL], a[WPL], sum[WPL];
 #pragma unroll
-                for (int k = 0; k < WPL; k++) {
-                    const uint32_t Xh = (sum[k] ^ Pv[k]) | Eq[k] | (k == 0 ? hneg : 0u);
-                    const uint32_t Ph = Mv[k] | ~(Xh | Pv[k]);
-                    const uint32_t Mh = Pv[k] & Xh;
-                    const uint32_t Xv = Eq[k] | Mv[k];
-                    if ((flags & LF_PASS_SHW) && w0 + k == wl) {
-                        score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u);
-                        if (score < best) { best = score; bestc = c; }
+                    for (int k = 0; k < WPL; k++) {
+                        Eq[k] = ~((lo[k] ^ slo) | (hi[k] ^ shi) | nn[k]);
+                        a[k] = Eq[k] & Pv[k];
                     }
-                    const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
-                    pPh = Ph; pMh = Mh;
-                    const uint32_t nPv = Mhs | ~(Xv | Phs);
-                    const uint32_t nMv = Phs & Xv;
-                    if (flags & LF_PASS_STORE) {
-                        const uint32_t diagx = ~(nPv | Ph | Eq[k]);
-                        dst[k] = make_uint2(nPv | diagx, (~nPv & Ph) | diagx);
+                    const uint32_t hneg = hin < 0 ? 1u : 0u;
+                    lf_add_chain_cin<WPL>(a, Pv, sum, hneg);   /* hin = -1 enters as the carry-in */
+                    uint32_t pPh = hin > 0 ? 0x80000000u : 0u, pMh = hneg << 31;
+                    uint2 *dst = planes + sbase + ((unsigned long long)c * nv + lane) * WPL;
+#pragma unroll
+                    for (int k = 0; k < WPL; k++) {
+                        const uint32_t Xh = (sum[k] ^ Pv[k]) | Eq[k] | (k == 0 ? hneg : 0u);
+                        const uint32_t Ph = Mv[k] | ~(Xh | Pv[k]);
+                        const uint32_t Mh = Pv[k] & Xh;
+                        const uint32_t Xv = Eq[k] | Mv[k];
+                        if ((flags & LF_PASS_SHW) && w0 + k == wl) {
+                            score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u);
+                            if (score < best) { best = score; bestc = c; }
+                        }
+                        const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
+                        pPh = Ph; pMh = Mh;
+                        const uint32_t nPv = Mhs | ~(Xv | Phs);
+                        const uint32_t nMv = Phs & Xv;
+                        if (flags & LF_PASS_STORE) {
+                            const uint32_t diagx = ~(nPv | Ph | Eq[k]);
+                            dst[k] = make_uint2(nPv | diagx, (~nPv & Ph) | diagx);
+                        }
+                        Pv[k] = nPv; Mv[k] = nMv;
                     }
-                    Pv[k] = nPv; Mv[k] = nMv;
+                    const int hout = (int)(pPh >> 31) - (int)(pMh >> 31);
+                    pay |= (uint32_t)(hout + 1) << (2 * ci);
+                    if (lane == nv - 1 && s + 1 < S) hb[c] = (int8_t)hout;
                 }
-                const uint32_t phc = pPh >> 31, mhc = pMh >> 31;
-                hout = (int)phc - (int)mhc;
-                if (lane == nv - 1 && s + 1 < S) hb[c] = (int8_t)hout;
             }
-            pay = (uint32_t)(hout + 1) | (sym << 2);
         }
-        sbase += (unsigned long long)nsteps * nv * WPL;
+        sbase += (unsigned long long)tl * nv * WPL;
         /* last column of this strip: vertical deltas -> absolute values */
         int cnt = 0;
 #pragma unroll
@@ -793,10 +795,10 @@ __device__ __forceinline__ int lf_large_traceback(const uint2 *planes, int ql, i
         const int w = (i - 1) >> 5, s = w / SW, l = (w % SW) / WPL, k = w % WPL;
         const int nvw = n - s * SW < SW ? n - s * SW : SW;
         const int nv = (nvw + WPL - 1) / WPL;
-        const unsigned long long sb = (unsigned long long)s * (unsigned long long)(tl + 31) * 32ull * (unsigned long long)WPL;
+        const unsigned long long sb = (unsigned long long)s * (unsigned long long)tl * 32ull * (unsigned long long)WPL;
         const int jt = j, colr = j - 1 - lane;
         uint2 v = make_uint2(0u, 0u);
-        if (colr >= 0) v = planes[sb + ((unsigned long long)(colr + l) * nv + l) * WPL + k];
+        if (colr >= 0) v = planes[sb + ((unsigned long long)colr * nv + l) * WPL + k];
         while (i > 0 && j > 0 && ((i - 1) >> 5) == w && jt - j < 32) {
             const int kk = jt - j;
             const uint32_t x = __shfl_sync(LF_FULL, v.x, kk), y = __shfl_sync(LF_FULL, v.y, kk);
