@@ -30,6 +30,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per size-class stream; before torch starts CUDA
 
 WORKLOADS = {
     # name: (ref_len, n_reads, read_len, err_lo, err_hi)
@@ -209,6 +210,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     st = g.stats()
+    tl_start, tl_end = g.class_timeline()
     launches = int(st.kernel_launches - l0)
     main_wc = int(st.last_main_word_columns)
     # device-event time per step (prep + sort + scans + kernels, on the library's stream)
@@ -227,19 +229,41 @@ def main():
         e2e_step()
     barrier()
     e2e_wall = time.perf_counter() - t1
+    # ---- chain-level e2e: lf_gpu_align_chains (the batched alignChain_edlib): chains in, Sam_t records out ----
+    seeds_a, chains_a = api.workload_chains(w)
+    cg = api.Contigs(w.contig_off.ctypes.data, w.contig_len.ctypes.data, len(w.contig_off))
+    pac_ptr = g.pac.ctypes.data
+
+    def chain_step():
+        out = C.c_void_p()
+        rc = g.lib.lf_gpu_align_chains(g.ctx, C.byref(reads_struct), C.byref(cg), seeds_a.ctypes.data, chains_a.ctypes.data, len(chains_a), pac_ptr, C.byref(out))
+        if rc != 0:
+            raise SystemExit(f"lf_gpu_align_chains failed: {rc} {g.lib.lf_gpu_last_error(g.ctx).decode()}")
+        nrec = C.c_size_t()
+        g.lib.lf_chain_results_records(out, C.byref(nrec))
+        g.lib.lf_chain_results_free(out)
+        return nrec.value
+    chain_step()
+    barrier()
+    t2 = time.perf_counter()
+    nrec = 0
+    for _ in range(max(2, a.steps // 4)):
+        nrec = chain_step()
+    barrier()
+    chain_ms = (time.perf_counter() - t2) / max(2, a.steps // 4) * 1e3
     clocks = sampler.finish() if rank == 0 else None
     ops_bytes = int(h_res["ops_len"].astype(np.int64).sum() // 4)
     h2d = int(w.reads.nbytes + read_off.nbytes + tasks.nbytes)
     d2h = int(n * api.ALIGN_RESULT.itemsize + int(st_ops_words(g, h_res)) * 4)
 
     # max over ranks
-    tt = torch.tensor([step_ms, e2e_wall / a.steps * 1e3, wall / a.steps * 1e3], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([step_ms, e2e_wall / a.steps * 1e3, wall / a.steps * 1e3, chain_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     bases_all = torch.tensor([float(total_bases)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(bases_all, op=dist.ReduceOp.SUM)
-    step_ms_max, e2e_ms_max, wall_ms_max = [float(x) for x in tt.tolist()]
+    step_ms_max, e2e_ms_max, wall_ms_max, chain_ms_max = [float(x) for x in tt.tolist()]
     bases_sum = float(bases_all.item())
 
     if rank == 0:
@@ -262,12 +286,16 @@ def main():
                        "device_ms_per_step": step_ms_max},
             "gcups": cells * world / (wall_ms_max * 1e-3) / 1e9,
             "e2e": {"value": e2e_v, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max},
+            "e2e_chains": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chain_ms_max, "records_per_gpu": int(nrec),
+                           "what": "lf_gpu_align_chains: chains + reads from host memory in, CIGAR/MD/NM records out (3 GPU rounds + host emit)"},
             "gpu_launches": launches,
             "roofline": {"bound": "int32", "kernel": "alignment kernels of a step (k_myers_small<NW,SHW> x16 classes + k_myers_large, concurrent streams)", "achieved": achieved, "peak": peak,
                          "unit": "Top/s", "frac": achieved / peak if peak else None, "traffic": None,
                          "algorithmic_ops_per_launch_set": 16.0 * main_wc, "kernel_ms": mk_ms,
                          "peak_source": "lf_gpu_int32_peak (IADD3 stream, 64 SASS-verified ops/iteration) measured in this run", "int32_peaks_tops": peaks},
             "clocks": clocks,
+            "class_timeline_ms": {("large" if c == 16 else f"NW{[1,2,3,4,6,8,12,16][c // 2]}{'_shw' if c % 2 else ''}"): [round(float(tl_start[c]), 3), round(float(tl_end[c]), 3)]
+                                  for c in range(17) if tl_end[c] >= 0},
         }
         if not a.no_cpu_baseline:
             v, kind, cores, sample = cpu_reference_rate(w, os.cpu_count() or 1, max_chains=4000)

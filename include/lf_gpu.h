@@ -192,6 +192,11 @@ typedef struct {
 } lf_gpu_stats;
 int lf_gpu_get_stats(const lf_gpu_ctx *ctx, lf_gpu_stats *out);
 
+/* Timeline of the last lf_gpu_run_align on device 0: start / end (ms after the first launch) of each size-class
+ * kernel; index 2*i+shw for the register classes (NW = 1,2,3,4,6,8,12,16), 16 = large-task kernel; -1 = not run.
+ * n >= 18. */
+int lf_gpu_class_timeline(lf_gpu_ctx *ctx, float *start_ms, float *end_ms, int n);
+
 /* INT32 issue-rate microbenchmarks on device 0 (dependent-free streams on all SMs); Top/s.
  * which: 0 = LOP3 only, 1 = IADD3 only, 2 = LOP3+IADD3 mix, 3 = LOP3 + IMAD mix */
 int lf_gpu_int32_peak(lf_gpu_ctx *ctx, int which, double *tops);

@@ -11,6 +11,9 @@ import os
 
 import numpy as np
 
+# the size-class kernels run on 18 streams; give each its own hardware queue (must be set before CUDA starts)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "liblfgpu.so")
 
@@ -56,7 +59,7 @@ EXPORTS = ["lf_gpu_init", "lf_gpu_destroy", "lf_gpu_last_error", "lf_gpu_host_al
            "lf_gpu_ops_capacity", "lf_gpu_align_batch", "lf_gpu_extend_batch", "lf_gpu_upload_reads",
            "lf_gpu_upload_align_tasks", "lf_gpu_run_align", "lf_gpu_sync", "lf_gpu_download_align",
            "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",
-           "lf_gpu_int32_peak", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
+           "lf_gpu_int32_peak", "lf_gpu_class_timeline", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
            "lf_chain_results_stats", "lf_chain_results_free"]
 
 
@@ -94,6 +97,7 @@ def load(lib_path: str | None = None) -> C.CDLL:
     lib.lf_gpu_download_extend.argtypes = [vp, vp]
     lib.lf_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.lf_gpu_int32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.lf_gpu_class_timeline.argtypes = [vp, vp, vp, C.c_int]
     lib.lf_gpu_align_chains.argtypes = [vp, C.POINTER(Reads), C.POINTER(Contigs), vp, vp, sz, vp, C.POINTER(vp)]
     lib.lf_chain_results_records.argtypes = [vp, C.POINTER(sz)]
     lib.lf_chain_results_records.restype = vp
@@ -238,6 +242,11 @@ class LfGpu:
         s = Stats()
         self._check(self.lib.lf_gpu_get_stats(self.ctx, C.byref(s)), "lf_gpu_get_stats")
         return s
+
+    def class_timeline(self):
+        a = np.zeros(18, dtype=np.float32); b = np.zeros(18, dtype=np.float32)
+        self._check(self.lib.lf_gpu_class_timeline(self.ctx, _ptr(a), _ptr(b), 18), "lf_gpu_class_timeline")
+        return a, b
 
     def int32_peak(self, which: int) -> float:
         v = C.c_double()

@@ -28,6 +28,8 @@ struct DevState {
     lfb_event ev[4] = {};
     lfb_stream sub[LF_NSUB] = {};   /* size classes run concurrently: their grids are small */
     lfb_event sub_ev[LF_NSUB] = {};
+    lfb_event cls_ev[LF_NCLS][2] = {};   /* start / end of every class kernel (timeline hook) */
+    bool cls_ran[LF_NCLS] = {};
     LfbBuf pac, bases, read_off, plo, phi, pnn;
     LfbBuf tasks, res, ops, keys, keys2, idx, idx2, slot_words, scr_bytes, slot_end, scr_off, scratch, large_scr, counters, queue;
     LfbBuf etasks, eres, escr_items, escr_off, escr;
@@ -172,8 +174,15 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         LF_TRY(d.large_scr.reserve(slots * cfg.stride));
         cfg.base = d.large_scr.as<uint8_t>();
         cfg.queue = d.queue.as<uint32_t>();
+#ifndef LF_EMU
+        cudaEventRecord(d.cls_ev[LF_CLS_LARGE][0], d.sub[0]);
+#endif
         LFB_LAUNCH(k_myers_large, (unsigned)slots, 32, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg);
+#ifndef LF_EMU
+        cudaEventRecord(d.cls_ev[LF_CLS_LARGE][1], d.sub[0]);
+#endif
     }
+    for (int c = 0; c < LF_NCLS; c++) d.cls_ran[c] = c < LF_CLS_LARGE ? ht->cnt.hist[c] != 0 : (c == LF_CLS_LARGE && nlarge != 0);
     /* small classes, biggest register footprint first, spread over the other streams */
     {
         uint32_t firsts[LF_CLS_LARGE];
@@ -183,7 +192,14 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) {
             const uint32_t count = ht->cnt.hist[cls];
             if (!count) continue;
-            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, d.sub[1 + (k % (LF_NSUB - 1))]);
+            lfb_stream st = d.sub[1 + (k % (LF_NSUB - 1))];
+#ifndef LF_EMU
+            cudaEventRecord(d.cls_ev[cls][0], st);
+#endif
+            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, st);
+#ifndef LF_EMU
+            cudaEventRecord(d.cls_ev[cls][1], st);
+#endif
             k++;
         }
     }
@@ -209,6 +225,9 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
     lfb_errbuf[0] = 0;
     std::vector<int> devs;
 #ifndef LF_EMU
+    /* one hardware queue per class stream (the default of 8 connections serialises 18 streams in pairs);
+     * only effective if no CUDA context exists yet -- bench.py / api.py also set it before CUDA starts */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return LF_ERR_NO_DEVICE;
     if (!devices || n_devices <= 0) { int cur = 0; if (cudaGetDevice(&cur) != cudaSuccess) return LF_ERR_NO_DEVICE; devs.push_back(cur); }
@@ -229,6 +248,7 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
         if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; }
         for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
         for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; } cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
+        for (int c = 0; c < LF_NCLS; c++) { cudaEventCreate(&d.cls_ev[c][0]); cudaEventCreate(&d.cls_ev[c][1]); }
 #endif
         d.pinned = lfb_host_alloc(sizeof(HostTotals));
         if (!d.pinned || d.pac.reserve(pac_bytes + 16)) { lf_gpu_destroy(ctx); return LF_ERR_NOMEM; }
@@ -252,6 +272,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
 #ifndef LF_EMU
         for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         for (int k = 0; k < LF_NSUB; k++) { if (d.sub_ev[k]) cudaEventDestroy(d.sub_ev[k]); if (d.sub[k]) cudaStreamDestroy(d.sub[k]); }
+        for (int c = 0; c < LF_NCLS; c++) { if (d.cls_ev[c][0]) cudaEventDestroy(d.cls_ev[c][0]); if (d.cls_ev[c][1]) cudaEventDestroy(d.cls_ev[c][1]); }
         if (d.stream) cudaStreamDestroy(d.stream);
 #endif
     }
@@ -441,6 +462,22 @@ int lf_gpu_get_stats(const lf_gpu_ctx *ctx, lf_gpu_stats *out)
     if (!ctx || !out) return LF_ERR_BAD_ARG;
     *out = ctx->stats;
     out->kernel_launches = lfb_launches;
+    return LF_OK;
+}
+
+int lf_gpu_class_timeline(lf_gpu_ctx *ctx, float *start_ms, float *end_ms, int n)
+{ /* start / end of each size-class kernel of the last run on device 0, relative to the first launch; -1 = not run */
+    if (!ctx || !start_ms || !end_ms || n < LF_NCLS) return LF_ERR_BAD_ARG;
+    DevState &d = ctx->devs[0];
+    for (int c = 0; c < n; c++) { start_ms[c] = -1.f; end_ms[c] = -1.f; }
+#ifndef LF_EMU
+    if (!d.ran) return LF_OK;
+    for (int c = 0; c < LF_NCLS; c++) {
+        if (!d.cls_ran[c]) continue;
+        cudaEventElapsedTime(&start_ms[c], d.ev[2], d.cls_ev[c][0]);
+        cudaEventElapsedTime(&end_ms[c], d.ev[2], d.cls_ev[c][1]);
+    }
+#endif
     return LF_OK;
 }
 
