@@ -241,14 +241,16 @@ def main():
             raise SystemExit(f"lf_gpu_align_chains failed: {rc} {g.lib.lf_gpu_last_error(g.ctx).decode()}")
         nrec = C.c_size_t()
         g.lib.lf_chain_results_records(out, C.byref(nrec))
+        cst = api.ChainStats()
+        g.lib.lf_chain_results_stats(out, C.byref(cst))
         g.lib.lf_chain_results_free(out)
-        return nrec.value
+        return nrec.value, cst
     chain_step()
     barrier()
     t2 = time.perf_counter()
-    nrec = 0
+    nrec, cst = 0, None
     for _ in range(max(2, a.steps // 4)):
-        nrec = chain_step()
+        nrec, cst = chain_step()
     barrier()
     chain_ms = (time.perf_counter() - t2) / max(2, a.steps // 4) * 1e3
     clocks = sampler.finish() if rank == 0 else None
@@ -287,6 +289,8 @@ def main():
             "gcups": cells * world / (wall_ms_max * 1e-3) / 1e9,
             "e2e": {"value": e2e_v, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max},
             "e2e_chains": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chain_ms_max, "records_per_gpu": int(nrec),
+                           "host_phase_ms": {"tasks": round(cst.ms_tasks, 2), "round1": round(cst.ms_round1, 2), "rounds2_3": round(cst.ms_rounds23, 2), "emit": round(cst.ms_emit, 2)},
+                           "rounds": {"round1_tasks": int(cst.round1_tasks), "round2_extends": int(cst.round2_extends), "round3_tasks": int(cst.round3_tasks)},
                            "what": "lf_gpu_align_chains: chains + reads from host memory in, CIGAR/MD/NM records out (3 GPU rounds + host emit)"},
             "gpu_launches": launches,
             "roofline": {"bound": "int32", "kernel": "alignment kernels of a step (k_myers_small<NW,SHW> x16 classes + k_myers_large, concurrent streams)", "achieved": achieved, "peak": peak,

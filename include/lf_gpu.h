@@ -168,7 +168,10 @@ typedef struct {         /* Sam_t fields alignChain_edlib fills (src/LordFAST.h:
     uint32_t cigar_len, md_len;
     uint64_t cigar_off, md_off; /* NUL-terminated strings inside lf_chain_results_text() */
 } lf_sam_record;
-typedef struct { uint64_t round1_tasks, round2_extends, round3_tasks, records; } lf_chain_stats;
+typedef struct {
+    uint64_t round1_tasks, round2_extends, round3_tasks, records;
+    float ms_tasks, ms_round1, ms_rounds23, ms_emit; /* host wall time of the phases of the call */
+} lf_chain_stats;
 typedef struct lf_chain_results lf_chain_results;         /* library-owned, free with lf_chain_results_free */
 
 /* pac_host: the same 2-bit reference that was given to lf_gpu_init (MD strings need reference bases). */

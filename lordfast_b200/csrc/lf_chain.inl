@@ -16,6 +16,7 @@
  * Included by lf_pipeline.inl (so it is part of liblfgpu.so and of the test-only emulator build).
  */
 #include <thread>
+#include <time.h>
 
 struct lf_chain_results {
     std::vector<lf_sam_record> recs;
@@ -77,20 +78,98 @@ inline lf_extend_task mk_ext(uint32_t rid, uint32_t qo, uint32_t ql, uint32_t to
 
 inline char pac_base(const uint8_t *pac, uint32_t l) { return "ACGT"[(pac[l >> 2] >> ((~l & 3) << 1)) & 3]; }
 
-/* expanded per-op buffers of one record, as the reference's two deques hold them */
+inline void put_num(std::string &s, long v) { char t[24]; int n = snprintf(t, sizeof t, "%ld", v); s.append(t, (size_t)n); }
+
+/* One record's CIGAR and MD, built as run-length strings while the pieces arrive in forward order.
+ * Same output as edlibCigar_toString (:1596-1626: leading / trailing insert runs print as soft
+ * clips) and edlibMD_toString (:1717-1763) applied to the reference's per-op deques, without
+ * materialising one char per op.  Runs of matches in the 2-bit op stream are skipped a word at a time. */
 struct RecBuf {
     std::string cig, md;
-    void clear() { cig.clear(); md.clear(); }
-    void run(char c, size_t n) { cig.append(n, c); md.append(n, c == 'I' ? '-' : '='); }
-    void del_run(const uint8_t *pac, uint32_t t0, uint32_t n) { cig.append(n, 'D'); for (uint32_t k = 0; k < n; k++) md.push_back(pac_base(pac, t0 + k)); }
+    char cch; long cnum; int cnops;  /* CIGAR run in progress */
+    long mnum; char mlast;           /* MD: matches since the last printed item; last move class */
+    RecBuf() { clear(); }
+    void clear() { cig.clear(); md.clear(); cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '='; }
+    inline void cig_run(char c, long n)
+    {
+        if (n <= 0) return;
+        if (c == cch) { cnum += n; return; }
+        if (cch) { put_num(cig, cnum); cig.push_back((cnops == 0 && cch == 'I') ? 'S' : cch); cnops++; }
+        cch = c; cnum = n;
+    }
+    inline void md_match(long n) { if (n > 0) { mnum += n; mlast = '='; } }
+    inline void md_ins(long n) { if (n > 0) mlast = 'I'; }
+    inline void md_mismatch(char b) { put_num(md, mnum); mnum = 0; md.push_back(b); mlast = 'X'; }
+    inline void md_del(char b) { if (mlast != 'D') { put_num(md, mnum); mnum = 0; md.push_back('^'); } md.push_back(b); mlast = 'D'; }
+    void run(char c, size_t n) { cig_run(c, (long)n); if (c == 'I') md_ins((long)n); else md_match((long)n); }
+    void del_run(const uint8_t *pac, uint32_t t0, uint32_t n) { cig_run('D', (long)n); for (uint32_t k = 0; k < n; k++) md_del(pac_base(pac, t0 + k)); }
+    void finish(std::string &out_cig, std::string &out_md)
+    {
+        if (cnum) { put_num(cig, cnum); cig.push_back(cch == 'I' ? 'S' : cch); }
+        put_num(md, mnum);
+        out_cig.swap(cig); out_md.swap(md);
+    }
     /* ops of one alignment; reversed = the task ran right-to-left (pushfront in the reference);
      * t0 = forward reference position of the first target base the segment covers */
     void segment(const uint8_t *ops, const lf_align_result &r, bool reversed, const uint8_t *pac, uint32_t t0)
     {
         uint32_t tp = t0;
+        uint32_t k = 0;
+        const uint32_t n = r.ops_len;
+        while (k < n) {
+            /* count the run of matches starting at op k, up to 28 ops per 64-bit load */
+            long run = 0;
+            for (;;) {
+                if (k >= n) break;
+                uint64_t w; unsigned avail;
+                if (!reversed) {
+                    const uint64_t p = r.ops_off + k;
+                    memcpy(&w, ops + (p >> 2), 8);
+                    w >>= ((p & 3) << 1);
+                    avail = 32 - (unsigned)(p & 3);            /* ops available in w, lowest first */
+                    if (avail > n - k) avail = n - k;
+                    unsigned z = w ? (unsigned)(__builtin_ctzll(w) >> 1) : 32u;
+                    if (z >= avail) { run += avail; k += avail; continue; }
+                    run += z; k += z;
+                    break;
+                } else {
+                    const uint64_t p = r.ops_off + (n - 1 - k);  /* current op, walking down */
+                    const uint64_t byte = p >> 2;
+                    const uint64_t lo = byte >= 7 ? byte - 7 : 0; /* the op stream is preceded by >= 0 bytes; clamp */
+                    memcpy(&w, ops + lo, 8);
+                    const unsigned top = (unsigned)((byte - lo) * 4 + (p & 3)); /* index of op p inside w */
+                    w <<= (62 - 2 * top);                        /* op p now in the two highest bits */
+                    avail = top + 1;
+                    if (avail > n - k) avail = n - k;
+                    unsigned z = w ? (unsigned)(__builtin_clzll(w) >> 1) : 32u;
+                    if (z >= avail) { run += avail; k += avail; continue; }
+                    run += z; k += z;
+                    break;
+                }
+            }
+            if (run) { cig_run('M', run); md_match(run); tp += (uint32_t)run; }
+            if (k >= n) break;
+            const uint64_t p = reversed ? r.ops_off + (n - 1 - k) : r.ops_off + k;
+            const unsigned op = LF_OP_AT(ops, p);
+            k++;
+            if (op == 1) { cig_run('I', 1); md_ins(1); }
+            else if (op == 2) { cig_run('D', 1); md_del(pac_base(pac, tp)); tp++; }
+            else { cig_run('M', 1); md_mismatch(pac_base(pac, tp)); tp++; } /* op 3 (op 0 cannot get here) */
+        }
+    }
+};
+
+/* The reference's accepted-inversion record pairs MD and CIGAR positions out of step (:2056-2057:
+ * the trailing clip goes to the END of the CIGAR deque but to the BEGINNING of the MD deque), so that one
+ * record type is built the reference's way, one char per op. */
+struct SlowRec {
+    std::string cig, md;
+    void run(char c, size_t n) { cig.append(n, c); md.append(n, c == 'I' ? '-' : '='); }
+    void segment(const uint8_t *ops, const lf_align_result &r, const uint8_t *pac, uint32_t t0)
+    {
+        uint32_t tp = t0;
         for (uint32_t k = 0; k < r.ops_len; k++) {
-            uint64_t p = reversed ? r.ops_off + (r.ops_len - 1 - k) : r.ops_off + k;
-            unsigned op = LF_OP_AT(ops, p);
+            const unsigned op = LF_OP_AT(ops, r.ops_off + k);
             switch (op) {
             case 0: cig.push_back('M'); md.push_back('='); tp++; break;
             case 1: cig.push_back('I'); md.push_back('-'); break;
@@ -99,46 +178,83 @@ struct RecBuf {
             }
         }
     }
+    void finish(std::string &out_cig, std::string &out_md)
+    {
+        char ch = 0; long num = 0; int nops = 0;
+        for (size_t i = 0; i < cig.size(); i++) {
+            if (cig[i] != ch) {
+                if (ch != 0) { put_num(out_cig, num); out_cig.push_back((nops == 0 && ch == 'I') ? 'S' : ch); nops++; }
+                num = 1; ch = cig[i];
+            } else num++;
+        }
+        if (num) { put_num(out_cig, num); out_cig.push_back(ch == 'I' ? 'S' : ch); }
+        long mnum = 0; char last = '=';
+        for (size_t i = 0; i < md.size(); i++) {
+            char m = md[i], c = cig[i];
+            if (m == '=') { mnum++; last = '='; }
+            else if (m == '-') { last = 'I'; }
+            else if (c == 'M') { put_num(out_md, mnum); mnum = 0; out_md.push_back(m); last = 'X'; }
+            else if (c == 'D') { if (last != 'D') { put_num(out_md, mnum); mnum = 0; out_md.push_back('^'); } out_md.push_back(m); last = 'D'; }
+        }
+        put_num(out_md, mnum);
+    }
 };
-
-inline void put_num(std::string &s, long v) { char t[24]; int n = snprintf(t, sizeof t, "%ld", v); s.append(t, (size_t)n); }
-
-void cigar_to_string(const std::string &cig, std::string &out)
-{ /* edlibCigar_toString, :1596-1626: leading / trailing insert runs print as soft clips */
-    char ch = 0; long num = 0; int nops = 0;
-    for (size_t i = 0; i < cig.size(); i++) {
-        if (cig[i] != ch) {
-            if (ch != 0) { put_num(out, num); out.push_back((nops == 0 && ch == 'I') ? 'S' : ch); nops++; }
-            num = 1; ch = cig[i];
-        } else num++;
-    }
-    if (num) { put_num(out, num); out.push_back(ch == 'I' ? 'S' : ch); }
-}
-void md_to_string(const std::string &md, const std::string &cig, std::string &out)
-{ /* edlibMD_toString, :1717-1763 */
-    long num = 0; char last = '=';
-    for (size_t i = 0; i < md.size(); i++) {
-        char m = md[i], c = cig[i];
-        if (m == '=') { num++; last = '='; }
-        else if (m == '-') { last = 'I'; }
-        else if (c == 'M') { put_num(out, num); num = 0; out.push_back(m); last = 'X'; }
-        else if (c == 'D') { if (last != 'D') { put_num(out, num); num = 0; out.push_back('^'); } out.push_back(m); last = 'D'; }
-    }
-    put_num(out, num);
-}
 
 struct Emit {
     std::vector<lf_sam_record> recs;
-    std::string text;
-    void push(uint32_t chain_id, uint32_t flag, uint32_t pos, uint32_t posEnd, uint32_t qStart, uint32_t qEnd, int32_t nm, const RecBuf &b)
+    std::string text, tc, tm;
+    void push_strings(uint32_t chain_id, uint32_t flag, uint32_t pos, uint32_t posEnd, uint32_t qStart, uint32_t qEnd, int32_t nm)
     {
         lf_sam_record r;
         r.chain_id = chain_id; r.flag = flag; r.pos = pos; r.posEnd = posEnd; r.qStart = qStart; r.qEnd = qEnd; r.nmCount = nm;
-        r.cigar_off = text.size(); cigar_to_string(b.cig, text); r.cigar_len = (uint32_t)(text.size() - r.cigar_off); text.push_back('\0');
-        r.md_off = text.size(); md_to_string(b.md, b.cig, text); r.md_len = (uint32_t)(text.size() - r.md_off); text.push_back('\0');
+        r.cigar_off = text.size(); text.append(tc); r.cigar_len = (uint32_t)tc.size(); text.push_back('\0');
+        r.md_off = text.size(); text.append(tm); r.md_len = (uint32_t)tm.size(); text.push_back('\0');
         recs.push_back(r);
     }
+    void push(uint32_t chain_id, uint32_t flag, uint32_t pos, uint32_t posEnd, uint32_t qStart, uint32_t qEnd, int32_t nm, RecBuf &b)
+    {
+        tc.clear(); tm.clear();
+        b.finish(tc, tm);
+        push_strings(chain_id, flag, pos, posEnd, qStart, qEnd, nm);
+    }
 };
+
+/* grow-only pinned host buffer kept in the context between calls */
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+    void *reserve(size_t need) { if (need > cap) { lfb_host_free(p); cap = need + need / 4 + 4096; p = lfb_host_alloc(cap); if (!p) cap = 0; } return p; }
+    void release() { lfb_host_free(p); p = nullptr; cap = 0; }
+};
+struct ChainScratch { PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2; };
+ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
+
+template <typename F>
+void parallel_for(size_t n, unsigned nthreads, F fn)
+{ /* fn(tid, lo, hi) over contiguous ranges */
+    if (nthreads <= 1 || n < 256) { fn(0u, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; t++) th.emplace_back(fn, t, n * t / nthreads, n * (t + 1) / nthreads);
+    for (auto &t : th) t.join();
+}
+
+double now_ms()
+{
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+void chain_scratch_free_fn(void *p)
+{
+    ChainScratch *s = (ChainScratch *)p;
+    PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2 };
+    for (PinBuf *b : all) b->release();
+    delete s;
+}
+ChainScratch &chain_scratch(lf_gpu_ctx *ctx)
+{
+    if (!ctx->chain_scratch) { ctx->chain_scratch = new ChainScratch(); ctx->chain_scratch_free = chain_scratch_free_fn; }
+    return *(ChainScratch *)ctx->chain_scratch;
+}
 
 } // namespace
 
@@ -151,68 +267,106 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     *out = nullptr;
     lf_chain_results *R = new lf_chain_results();
     memset(&R->stats, 0, sizeof R->stats);
+    ChainScratch &S = chain_scratch(ctx);
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
     int rc;
+    const double tm0 = now_ms();
 #define LF_CH(expr) do { rc = (expr); if (rc != 0) { delete R; return rc; } } while (0)
-    LF_CH(lf_gpu_upload_reads(ctx, reads));
+    LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
 
     /* ---------------- round 1: tasks known from the chains alone ---------------- */
     std::vector<ChainPlan> plan(n_chains);
-    size_t total_seeds = 0;
-    for (size_t c = 0; c < n_chains; c++) { if (chains[c].n_seeds < 2 || chains[c].read_id >= reads->n_reads) { delete R; return LF_ERR_BAD_ARG; } total_seeds += chains[c].n_seeds; }
-    std::vector<lf_align_task> t1;
-    t1.reserve(total_seeds + 2 * n_chains);
-    std::vector<int32_t> gap_task;  /* per (chain, seed i): round-1 task of the gap after seed i, or -1 */
-    std::vector<uint64_t> gap_base(n_chains + 1, 0);
-    gap_task.reserve(total_seeds);
+    std::vector<uint64_t> gap_base(n_chains + 1, 0), task_base(n_chains + 1, 0);
     for (size_t c = 0; c < n_chains; c++) {
-        const lf_chain &ch = chains[c];
-        const lf_seed *s = seeds + ch.seed_off;
-        const uint32_t n = ch.n_seeds;
-        const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
-        const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
-        ChainPlan &p = plan[c];
-        int rid = pos2rid(contigs, ((int64_t)s[0].tPos + (int64_t)s[n - 1].tPos) >> 1, ctx->l_pac); /* BWT.cpp:653-660 */
-        if (rid < 0) { delete R; return LF_ERR_BAD_ARG; }
-        p.chrBeg = (uint32_t)contigs->offset[rid];
-        p.chrEnd = (uint32_t)(contigs->offset[rid] + contigs->len[rid] - 1);
-        const int32_t a = (int32_t)s[0].qPos;
-        if (a > 0 && (int64_t)s[0].tPos - (a + 20) >= (int64_t)p.chrBeg) {                       /* :1823-1825 */
-            p.head_guard = true; p.head_task = (int32_t)t1.size();
-            t1.push_back(mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH, LF_MODE_SHW));
-        }
-        gap_base[c] = gap_task.size();
-        for (uint32_t i = 0; i + 1 < n; i++) {
-            const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
-            const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
-            if (ql > 0 && tl > 0) { gap_task.push_back((int32_t)t1.size()); t1.push_back(mk_task(ch.read_id, qs, (uint32_t)ql, ts, (uint32_t)tl, strand, LF_MODE_NW)); }
-            else gap_task.push_back(-1);
-        }
-        gap_task.push_back(-1);
-        const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
-        const int32_t b = (int32_t)readLen - (int32_t)qs;
-        if (b > 0 && s[n - 1].tPos + s[n - 1].len + (uint32_t)(b + 20) - 1 <= p.chrEnd) {          /* :2161-2163 */
-            p.tail_guard = true; p.tail_task = (int32_t)t1.size();
-            t1.push_back(mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand, LF_MODE_SHW));
-        }
+        if (chains[c].n_seeds < 2 || chains[c].read_id >= reads->n_reads) { delete R; return LF_ERR_BAD_ARG; }
+        gap_base[c + 1] = gap_base[c] + chains[c].n_seeds;
     }
-    gap_base[n_chains] = gap_task.size();
-    std::vector<lf_align_result> r1(t1.size());
-    std::vector<uint8_t> ops1(lf_gpu_ops_capacity(t1.data(), t1.size()));
-    if (!t1.empty()) {
-        LF_CH(lf_gpu_upload_align_tasks(ctx, t1.data(), t1.size()));
+    const size_t total_seeds = gap_base[n_chains];
+    std::vector<int32_t> gap_task(total_seeds, -1); /* per (chain, seed i): round-1 task of the gap after seed i, or -1 */
+    std::vector<uint32_t> ntask(n_chains, 0);
+    bool bad_rid = false;
+    /* pass A: boundaries, guards and task counts per chain */
+    parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
+        for (size_t c = lo; c < hi; c++) {
+            const lf_chain &ch = chains[c];
+            const lf_seed *s = seeds + ch.seed_off;
+            const uint32_t n = ch.n_seeds;
+            const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
+            ChainPlan &p = plan[c];
+            int rid = pos2rid(contigs, ((int64_t)s[0].tPos + (int64_t)s[n - 1].tPos) >> 1, ctx->l_pac); /* BWT.cpp:653-660 */
+            if (rid < 0) { bad_rid = true; continue; }
+            p.chrBeg = (uint32_t)contigs->offset[rid];
+            p.chrEnd = (uint32_t)(contigs->offset[rid] + contigs->len[rid] - 1);
+            uint32_t cnt = 0;
+            const int32_t a = (int32_t)s[0].qPos;
+            p.head_guard = a > 0 && (int64_t)s[0].tPos - (a + 20) >= (int64_t)p.chrBeg;                       /* :1823-1825 */
+            cnt += p.head_guard;
+            for (uint32_t i = 0; i + 1 < n; i++) {
+                const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
+                cnt += ((int32_t)(s[i + 1].qPos - qs) > 0 && (int32_t)(s[i + 1].tPos - ts) > 0);
+            }
+            const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
+            const int32_t b = (int32_t)readLen - (int32_t)qs;
+            p.tail_guard = b > 0 && s[n - 1].tPos + s[n - 1].len + (uint32_t)(b + 20) - 1 <= p.chrEnd;         /* :2161-2163 */
+            cnt += p.tail_guard;
+            ntask[c] = cnt;
+        }
+    });
+    if (bad_rid) { delete R; return LF_ERR_BAD_ARG; }
+    for (size_t c = 0; c < n_chains; c++) task_base[c + 1] = task_base[c] + ntask[c];
+    const size_t n1 = task_base[n_chains];
+    lf_align_task *t1 = (lf_align_task *)S.t1.reserve((n1 + 1) * sizeof(lf_align_task));
+    lf_align_result *r1 = (lf_align_result *)S.r1.reserve((n1 + 1) * sizeof(lf_align_result));
+    if (!t1 || !r1) { delete R; return LF_ERR_NOMEM; }
+    /* pass B: fill */
+    parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
+        for (size_t c = lo; c < hi; c++) {
+            const lf_chain &ch = chains[c];
+            const lf_seed *s = seeds + ch.seed_off;
+            const uint32_t n = ch.n_seeds;
+            const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
+            const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
+            ChainPlan &p = plan[c];
+            size_t k = task_base[c];
+            const int32_t a = (int32_t)s[0].qPos;
+            if (p.head_guard) {
+                p.head_task = (int32_t)k;
+                t1[k++] = mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH, LF_MODE_SHW);
+            }
+            for (uint32_t i = 0; i + 1 < n; i++) {
+                const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
+                const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
+                if (ql > 0 && tl > 0) { gap_task[gap_base[c] + i] = (int32_t)k; t1[k++] = mk_task(ch.read_id, qs, (uint32_t)ql, ts, (uint32_t)tl, strand, LF_MODE_NW); }
+            }
+            if (p.tail_guard) {
+                const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
+                const int32_t b = (int32_t)readLen - (int32_t)qs;
+                p.tail_task = (int32_t)k;
+                t1[k++] = mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand, LF_MODE_SHW);
+            }
+        }
+    });
+    const size_t cap1 = lf_gpu_ops_capacity(t1, n1);
+    uint8_t *ops1 = (uint8_t *)S.ops1.reserve(cap1 + 64);
+    if (!ops1) { delete R; return LF_ERR_NOMEM; }
+    const double tm1 = now_ms();
+    if (n1) {
+        LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
         LF_CH(lf_gpu_run_align(ctx));
-        LF_CH(lf_gpu_download_align(ctx, r1.data(), ops1.data(), ops1.size()));
+        LF_CH(lf_gpu_download_align(ctx, r1, ops1, cap1));
     }
-    R->stats.round1_tasks = t1.size();
+    R->stats.round1_tasks = n1;
+    const double tm2 = now_ms();
 
     /* ---------------- round 2: triggers -> extensions ---------------- */
     std::vector<lf_extend_task> e2;
     std::vector<ClipInfo> clips;
     std::vector<SplitInfo> splits;
-    std::vector<int32_t> gap_split(gap_task.size(), -1);
+    std::vector<int32_t> gap_split(total_seeds, -1);
     for (size_t c = 0; c < n_chains; c++) {
         const lf_chain &ch = chains[c];
-        const lf_seed *s = seeds + ch.seed_off;
         const uint32_t n = ch.n_seeds;
         const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
         ChainPlan &p = plan[c];
@@ -261,11 +415,16 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     /* ---------------- round 3: follow-up alignments ---------------- */
     std::vector<lf_align_task> t3;
     for (size_t c = 0; c < n_chains; c++) {
+        ChainPlan &p = plan[c];
+        if (p.head_clip < 0 && p.tail_clip < 0) {
+            bool any = false;
+            for (uint64_t g = gap_base[c]; g < gap_base[c + 1] && !any; g++) any = gap_split[g] >= 0;
+            if (!any) continue;
+        }
         const lf_chain &ch = chains[c];
         const lf_seed *s = seeds + ch.seed_off;
         const uint32_t n = ch.n_seeds;
         const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
-        ChainPlan &p = plan[c];
         if (p.head_clip >= 0) {
             ClipInfo &ci = clips[(size_t)p.head_clip];
             const lf_align_task &t = t1[(size_t)p.head_task];
@@ -312,27 +471,27 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             }
         }
     }
-    std::vector<lf_align_result> r3(t3.size());
-    std::vector<uint8_t> ops3(lf_gpu_ops_capacity(t3.data(), t3.size()));
-    if (!t3.empty()) {
-        LF_CH(lf_gpu_upload_align_tasks(ctx, t3.data(), t3.size()));
+    const size_t n3 = t3.size();
+    const size_t cap3 = lf_gpu_ops_capacity(t3.data(), n3);
+    lf_align_result *r3 = (lf_align_result *)S.r3.reserve((n3 + 1) * sizeof(lf_align_result));
+    uint8_t *ops3 = (uint8_t *)S.ops3.reserve(cap3 + 64);
+    if (!r3 || !ops3) { delete R; return LF_ERR_NOMEM; }
+    if (n3) {
+        LF_CH(lf_gpu_upload_align_tasks(ctx, t3.data(), n3));
         LF_CH(lf_gpu_run_align(ctx));
-        LF_CH(lf_gpu_download_align(ctx, r3.data(), ops3.data(), ops3.size()));
+        LF_CH(lf_gpu_download_align(ctx, r3, ops3, cap3));
     }
     LF_CH(lf_gpu_sync(ctx));
-    R->stats.round3_tasks = t3.size();
+    R->stats.round3_tasks = n3;
+    const double tm3 = now_ms();
 #undef LF_CH
 
     /* ---------------- emit: the reference's accumulation, chain by chain ---------------- */
-    unsigned nthreads = std::thread::hardware_concurrency();
-    if (nthreads < 1) nthreads = 1;
-    if (nthreads > 64) nthreads = 64;
     if (n_chains < 64) nthreads = 1;
     std::vector<Emit> parts(nthreads);
-    auto work = [&](unsigned tid) {
+    auto work = [&](unsigned tid, size_t c_lo, size_t c_hi) {
         Emit &E = parts[tid];
         RecBuf B;
-        const size_t c_lo = n_chains * tid / nthreads, c_hi = n_chains * (tid + 1) / nthreads;
         for (size_t c = c_lo; c < c_hi; c++) {
             const lf_chain &ch = chains[c];
             const lf_seed *s = seeds + ch.seed_off;
@@ -351,13 +510,13 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     if (ci && ci->t3 >= 0) {
                         const lf_align_result &r = r3[(size_t)ci->t3];
                         B.run('I', (size_t)(a - ci->qle));
-                        B.segment(ops3.data(), r, true, pac_host, s[0].tPos - (uint32_t)(r.end_location + 1));
+                        B.segment(ops3, r, true, pac_host, s[0].tPos - (uint32_t)(r.end_location + 1));
                         editScore -= r.edit_distance;
                         pos = s[0].tPos - (uint32_t)r.end_location - 1;
                         qStart = s[0].qPos - (uint32_t)ci->qle;
                     } else {
                         const lf_align_result &r = r1[(size_t)p.head_task];
-                        B.segment(ops1.data(), r, true, pac_host, s[0].tPos - (uint32_t)(r.end_location + 1));
+                        B.segment(ops1, r, true, pac_host, s[0].tPos - (uint32_t)(r.end_location + 1));
                         editScore -= r.edit_distance;
                         pos = s[0].tPos - (uint32_t)r.end_location - 1;
                         qStart = 0;
@@ -379,7 +538,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     if (si && si->split) {
                         if (si->t_first >= 0) {
                             const lf_align_result &r = r3[(size_t)si->t_first];
-                            B.segment(ops3.data(), r, false, pac_host, ts);
+                            B.segment(ops3, r, false, pac_host, ts);
                             editScore -= r.edit_distance;
                         }
                         B.run('I', (size_t)(readLen - si->qs2));
@@ -391,18 +550,20 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                             const int32_t ql2 = (int32_t)(si->qe2 - si->qs2);
                             if ((1 - ((double)rr.edit_distance / ql2)) > (1 - ((double)rf.edit_distance / ql2))
                                 && (1 - ((double)rr.edit_distance / ql2)) > kReverseSim) {                /* :2040-2041 */
-                                B.run('I', (size_t)si->qs2);
-                                B.segment(ops3.data(), rr, false, pac_host, si->ts2);
-                                B.cig.append((size_t)(readLen - si->qe2), 'I');
-                                B.md.insert((size_t)0, (size_t)(readLen - si->qe2), '-');              /* sic, :2056-2057 */
-                                E.push((uint32_t)c, flag_opp, si->ts2, si->te2, si->qs2, si->qe2, -rr.edit_distance, B);
-                                B.clear();
+                                SlowRec Q;
+                                Q.run('I', (size_t)si->qs2);
+                                Q.segment(ops3, rr, pac_host, si->ts2);
+                                Q.cig.append((size_t)(readLen - si->qe2), 'I');
+                                Q.md.insert((size_t)0, (size_t)(readLen - si->qe2), '-');              /* sic, :2056-2057 */
+                                E.tc.clear(); E.tm.clear();
+                                Q.finish(E.tc, E.tm);
+                                E.push_strings((uint32_t)c, flag_opp, si->ts2, si->te2, si->qs2, si->qe2, -rr.edit_distance);
                             }
                         }
                         B.run('I', (size_t)si->qe2);
                         if (si->t_second >= 0) {
                             const lf_align_result &r = r3[(size_t)si->t_second];
-                            B.segment(ops3.data(), r, true, pac_host, si->te2);
+                            B.segment(ops3, r, true, pac_host, si->te2);
                             editScore -= r.edit_distance;
                         }
                         flag = flag_norm; pos = si->te2; qStart = si->qe2;
@@ -410,7 +571,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     } else {
                         const lf_align_result &r = r1[(size_t)gt];
                         editScore -= r.edit_distance;
-                        B.segment(ops1.data(), r, false, pac_host, ts);
+                        B.segment(ops1, r, false, pac_host, ts);
                     }
                 } else if (ql > 0) { B.run('I', (size_t)ql); editScore -= ql; }
                 else { B.del_run(pac_host, ts, (uint32_t)tl); editScore -= tl; }
@@ -428,7 +589,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     const ClipInfo *ci = p.tail_clip >= 0 ? &clips[(size_t)p.tail_clip] : nullptr;
                     if (ci && ci->t3 >= 0) {
                         const lf_align_result &r = r3[(size_t)ci->t3];
-                        B.segment(ops3.data(), r, false, pac_host, ts);
+                        B.segment(ops3, r, false, pac_host, ts);
                         editScore -= r.edit_distance;
                         posEnd = ts + (uint32_t)r.end_location;
                         qEnd = qs + (uint32_t)ci->qle;
@@ -436,7 +597,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     } else {
                         const lf_align_result &r = r1[(size_t)p.tail_task];
                         editScore -= r.edit_distance;
-                        B.segment(ops1.data(), r, false, pac_host, ts);
+                        B.segment(ops1, r, false, pac_host, ts);
                         posEnd = ts + (uint32_t)r.end_location;
                         qEnd = readLen;
                     }
@@ -445,12 +606,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             E.push((uint32_t)c, flag, pos, posEnd, qStart, qEnd, editScore, B);
         }
     };
-    if (nthreads == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nthreads; t++) th.emplace_back(work, t);
-        for (auto &t : th) t.join();
-    }
+    parallel_for(n_chains, nthreads, work);
     size_t nrec = 0, ntext = 0;
     for (Emit &E : parts) { nrec += E.recs.size(); ntext += E.text.size(); }
     R->recs.reserve(nrec); R->text.reserve(ntext);
@@ -460,6 +616,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         for (lf_sam_record r : E.recs) { r.cigar_off += base; r.md_off += base; R->recs.push_back(r); }
     }
     R->stats.records = R->recs.size();
+    const double tm4 = now_ms();
+    R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm4 - tm3);
     *out = R;
     return LF_OK;
 }

@@ -43,6 +43,8 @@ struct DevState {
 
 struct lf_gpu_ctx {
     std::vector<DevState> devs;
+    void *chain_scratch = nullptr; /* lf_chain.inl: pinned staging kept between calls */
+    void (*chain_scratch_free)(void *) = nullptr;
     int64_t l_pac = 0;
     std::string err;
     lf_gpu_stats stats = {};
@@ -261,6 +263,7 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
 void lf_gpu_destroy(lf_gpu_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
     for (DevState &d : ctx->devs) {
         set_dev(d);
         LfbBuf *bufs[] = { &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
