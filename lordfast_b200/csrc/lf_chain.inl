@@ -78,7 +78,16 @@ inline lf_extend_task mk_ext(uint32_t rid, uint32_t qo, uint32_t ql, uint32_t to
 
 inline char pac_base(const uint8_t *pac, uint32_t l) { return "ACGT"[(pac[l >> 2] >> ((~l & 3) << 1)) & 3]; }
 
-inline void put_num(std::string &s, long v) { char t[24]; int n = snprintf(t, sizeof t, "%ld", v); s.append(t, (size_t)n); }
+inline void put_num(std::string &s, long v)
+{ /* decimal digits without snprintf: this runs once per CIGAR / MD run, tens of millions of times per chunk */
+    char t[24]; int n = 0;
+    unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+    do { t[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) t[n++] = '-';
+    char r[24];
+    for (int k = 0; k < n; k++) r[k] = t[n - 1 - k];
+    s.append(r, (size_t)n);
+}
 
 /* One record's CIGAR and MD, built as run-length strings while the pieces arrive in forward order.
  * Same output as edlibCigar_toString (:1596-1626: leading / trailing insert runs print as soft
@@ -89,7 +98,7 @@ struct RecBuf {
     char cch; long cnum; int cnops;  /* CIGAR run in progress */
     long mnum; char mlast;           /* MD: matches since the last printed item; last move class */
     RecBuf() { clear(); }
-    void clear() { cig.clear(); md.clear(); cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '='; }
+    void clear() { cig.clear(); md.clear(); cig.reserve(4096); md.reserve(4096); cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '='; }
     inline void cig_run(char c, long n)
     {
         if (n <= 0) return;

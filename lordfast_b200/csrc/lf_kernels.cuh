@@ -981,20 +981,34 @@ __global__ void k_extend_prep(LfExtDev d, uint32_t *scr_items)
         uint64_t L = d.read_off[t.read_id + 1] - d.read_off[t.read_id];
         ok = (uint64_t)t.q_off + t.q_len <= L && (int64_t)t.t_off + (int64_t)t.t_len <= d.l_pac;
     }
-    scr_items[i] = ok ? t.q_len + 1u : 0u;
+    scr_items[i] = ok ? t.q_len + 1u + (t.q_len + 7u) / 8u + 1u : 0u; /* eh[] + one query code byte per column */
 }
 
-__global__ void k_ksw_extend(LfExtDev d)
+__device__ __forceinline__ int lf_warp_max(int v)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const int t = __shfl_xor_sync(LF_FULL, v, o); v = t > v ? t : v; }
+    return v;
+}
+
+/* One warp per task.  The reference's row loop is kept row by row (band re-trim, m==0 and z-drop exits
+ * are row-sequential), but inside a row the 32 lanes take 32 consecutive columns at a time: E and the
+ * diagonal feed come from the previous row, and F(i,j+1) = max(F(i,j)-e_ins, max(M-oe_ins,0)) does not
+ * depend on H, so with u = F + j*e_ins it is a prefix maximum (5 shuffles per 32 columns).  eh[] lives in
+ * global scratch and is read/written coalesced; cells outside [beg,end] keep their old contents exactly
+ * as in the reference. */
+__global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= d.n_tasks) return;
     const lf_extend_task t = d.tasks[i];
     lf_extend_result out; out.score = -1; out.qle = 0; out.tle = 0;
     const uint64_t so = d.scr_off[i];
-    if (d.scr_off[i + 1] == so) { d.res[i] = out; return; } /* rejected by k_extend_prep */
+    if (d.scr_off[i + 1] == so) { if (lane == 0) d.res[i] = out; return; } /* rejected by k_extend_prep */
     int2 *eh = d.scratch + so;
     const int qlen = (int)t.q_len, tlen = (int)t.t_len;
-    /* query byte k: oriented index -> stored read index */
+    uint8_t *qcode = (uint8_t *)(eh + qlen + 1);
     const uint64_t ro = d.read_off[t.read_id];
     const int64_t L = (int64_t)(d.read_off[t.read_id + 1] - ro);
     const int rev1 = (t.flags & LF_F_REVERSE_BOTH) != 0;
@@ -1008,47 +1022,93 @@ __global__ void k_ksw_extend(LfExtDev d)
     const int o_del = t.o_del, e_del = t.e_del, o_ins = t.o_ins, e_ins = t.e_ins, h0 = t.h0, zdrop = t.zdrop;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
     int w = t.w;
-    /* first row (ksw.c:395-397); cells not reached stay zero like the reference's calloc */
-    for (int j = 0; j <= qlen; j++) eh[j] = int2{0, 0};
-    eh[0].x = h0;
-    if (qlen >= 1) eh[1].x = h0 > oe_ins ? h0 - oe_ins : 0;
-    for (int j = 2; j <= qlen && eh[j - 1].x > e_ins; j++) eh[j].x = eh[j - 1].x - e_ins;
-    /* band clamp (ksw.c:399-407), max matrix entry is the match score */
-    {
+    /* query codes (src/LordFAST.cpp:158-164, 1191-1201) and the first row (ksw.c:395-397) */
+    for (int j = lane; j <= qlen; j += 32) {
+        if (j < qlen) {
+            uint32_t qc = lf_char2int(d.bases[ro + (uint64_t)(f0 + (int64_t)qdir * j)]);
+            if (comp && qc < 4u) qc = 3u - qc;
+            qcode[j] = (uint8_t)qc;
+        }
+        int hv;
+        if (j == 0) hv = h0;
+        else if (j == 1) hv = h0 > oe_ins ? h0 - oe_ins : 0;
+        else { const int prev = h0 - oe_ins - (j - 2) * e_ins; hv = (h0 > oe_ins && prev > e_ins) ? prev - e_ins : 0; }
+        eh[j] = int2{hv, 0};
+    }
+    __syncwarp();
+    {   /* band clamp (ksw.c:399-407), max matrix entry is the match score */
         int lim = (int)((double)(qlen * smatch - o_ins) / e_ins + 1.);
         lim = lim > 1 ? lim : 1; w = w < lim ? w : lim;
         lim = (int)((double)(qlen * smatch - o_del) / e_del + 1.);
         lim = lim > 1 ? lim : 1; w = w < lim ? w : lim;
     }
+    const int NEG = -(1 << 29);
     int best = h0, best_i = -1, best_j = -1, beg = 0, end = qlen;
+    LfTCursor tcur;
+    tcur.init(d.pac, t0, tdir);
     for (int r = 0; r < tlen; r++) {
-        int f = 0, left, rowmax = 0, rowmax_j = -1;
-        const uint32_t tc = lf_tsym(d.pac, t0 + (int64_t)tdir * r);
+        const uint32_t tc = tcur.next();
         if (beg < r - w) beg = r - w;
         if (end > r + w + 1) end = r + w + 1;
         if (end > qlen) end = qlen;
-        if (beg == 0) { left = h0 - (o_del + e_del * (r + 1)); if (left < 0) left = 0; } else left = 0;
-        int j;
-        for (j = beg; j < end; j++) {
-            int2 c = eh[j];
-            uint32_t qc = lf_char2int(d.bases[ro + (uint64_t)(f0 + (int64_t)qdir * j)]);
-            if (comp && qc < 4u) qc = 3u - qc;
-            int M = c.x, e = c.y;
-            const int sc = qc > 3u ? 0 : (qc == tc ? smatch : smis);
-            M = M ? M + sc : 0;
+        int h1 = 0;
+        if (beg == 0) { h1 = h0 - (o_del + e_del * (r + 1)); if (h1 < 0) h1 = 0; }
+        int carry_u = 0;            /* u = F + (j-beg)*e_ins at the start of the round; F(i,beg) = 0 */
+        int prev_h = h1;            /* H(i, j-1) for the first lane of the round */
+        int rowmax = 0, rowmax_j = -1, first_nz = -1, last_nz = -1, h_last = h1;
+        const int width = end - beg;
+        for (int k0 = 0; k0 < width; k0 += 32) {
+            const int rr = k0 + lane, j = beg + rr;
+            const bool act = rr < width;
+            int M = 0, e = 0;
+            if (act) {
+                const int2 c = eh[j];
+                const uint32_t qc = qcode[j];
+                const int sc = qc > 3u ? 0 : (qc == tc ? smatch : smis);
+                M = c.x ? c.x + sc : 0;
+                e = c.y;
+            }
+            int g = M - oe_ins; g = g > 0 ? g : 0;
+            const int v = act ? g + (rr + 1) * e_ins : NEG;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(LF_FULL, incl, o); if (lane >= o && x > incl) incl = x; }
+            int excl = __shfl_up_sync(LF_FULL, incl, 1);
+            if (lane == 0) excl = NEG;
+            const int u = carry_u > excl ? carry_u : excl;
+            const int f = u - rr * e_ins;
+            const int tot = __shfl_sync(LF_FULL, incl, 31);
+            carry_u = carry_u > tot ? carry_u : tot;
             int h = M > e ? M : e;
             h = h > f ? h : f;
-            eh[j].x = left;
-            left = h;
-            rowmax_j = rowmax > h ? rowmax_j : j; /* ties go to the later column (ksw.c:437) */
-            rowmax = rowmax > h ? rowmax : h;
-            int tt = M - oe_del; tt = tt > 0 ? tt : 0;
-            e -= e_del; e = e > tt ? e : tt;
-            eh[j].y = e;
-            tt = M - oe_ins; tt = tt > 0 ? tt : 0;
-            f -= e_ins; f = f > tt ? f : tt;
+            if (!act) h = -1;
+            int hprev = __shfl_up_sync(LF_FULL, h, 1);
+            if (lane == 0) hprev = prev_h;
+            int en = 0;
+            if (act) {
+                int tt = M - oe_del; tt = tt > 0 ? tt : 0;
+                en = e - e_del; en = en > tt ? en : tt;
+                eh[j] = int2{hprev, en};
+            }
+            /* row maximum, ties to the later column (ksw.c:437) */
+            const int mk = lf_warp_max(h);
+            if (mk >= rowmax && mk >= 0) {
+                const uint32_t bal = __ballot_sync(LF_FULL, act && h == mk);
+                rowmax_j = beg + k0 + (31 - __clz((int)bal));
+                rowmax = mk;
+            }
+            /* cells that stay non-zero, for the band re-trim (ksw.c:466-469) */
+            const uint32_t nzb = __ballot_sync(LF_FULL, act && (hprev != 0 || en != 0));
+            if (nzb) {
+                if (first_nz < 0) first_nz = beg + k0 + __ffs((int)nzb) - 1;
+                last_nz = beg + k0 + (31 - __clz((int)nzb));
+            }
+            const int nact = width - k0 < 32 ? width - k0 : 32;
+            h_last = __shfl_sync(LF_FULL, h, nact - 1);
+            prev_h = h_last;
         }
-        eh[end] = int2{left, 0};
+        if (lane == 0) eh[end] = int2{h_last, 0};
+        __syncwarp();
         if (rowmax == 0) break;
         if (rowmax > best) { best = rowmax; best_i = r; best_j = rowmax_j; }
         else if (zdrop > 0) {
@@ -1056,13 +1116,14 @@ __global__ void k_ksw_extend(LfExtDev d)
             if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) break; }
             else { if (best - rowmax - (dj - di) * e_ins > zdrop) break; }
         }
-        for (j = beg; j < end && eh[j].x == 0 && eh[j].y == 0; j++) {}
-        beg = j;
-        for (j = end; j >= beg && eh[j].x == 0 && eh[j].y == 0; j--) {}
-        end = j + 2 < qlen ? j + 2 : qlen;
+        if (h_last != 0) last_nz = end;
+        const int nbeg = first_nz >= 0 ? first_nz : end;
+        const int jl = last_nz >= nbeg ? last_nz : nbeg - 1;
+        beg = nbeg;
+        end = jl + 2 < qlen ? jl + 2 : qlen;
     }
     out.score = best; out.qle = best_j + 1; out.tle = best_i + 1;
-    d.res[i] = out;
+    if (lane == 0) d.res[i] = out;
 }
 
 /* ------------------------------------------------------------------------------------------ */

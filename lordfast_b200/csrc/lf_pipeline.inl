@@ -432,7 +432,7 @@ int lf_gpu_run_extend(lf_gpu_ctx *ctx)
         LF_TRY(lfb_sync(s));
         LF_TRY(d.escr.reserve((size_t)ht->scr_total * sizeof(int2) + 64));
         v.scratch = d.escr.as<int2>();
-        LFB_LAUNCH(k_ksw_extend, (unsigned)((n + 63) / 64), 64, 0, s, v);
+        LFB_LAUNCH(k_ksw_extend, (unsigned)((n + 3) / 4), 128, 0, s, v); /* one warp per task */
         LF_TRY(lfb_last_error());
         ctx->stats.extend_tasks += n;
     }
