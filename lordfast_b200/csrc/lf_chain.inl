@@ -79,7 +79,7 @@ inline lf_extend_task mk_ext(uint32_t rid, uint32_t qo, uint32_t ql, uint32_t to
 inline char pac_base(const uint8_t *pac, uint32_t l) { return "ACGT"[(pac[l >> 2] >> ((~l & 3) << 1)) & 3]; }
 
 inline void put_num(std::string &s, long v)
-{ /* decimal digits without snprintf: this runs once per CIGAR / MD run, tens of millions of times per chunk */
+{ /* used by the rare one-char-per-op record type only */
     char t[24]; int n = 0;
     unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
     do { t[n++] = (char)('0' + u % 10); u /= 10; } while (u);
@@ -88,35 +88,54 @@ inline void put_num(std::string &s, long v)
     for (int k = 0; k < n; k++) r[k] = t[n - 1 - k];
     s.append(r, (size_t)n);
 }
+inline char *put_num(char *p, unsigned long u)
+{ /* decimal digits straight into the output buffer; one and two digit numbers dominate */
+    if (u < 10) { *p++ = (char)('0' + u); return p; }
+    if (u < 100) { *p++ = (char)('0' + u / 10); *p++ = (char)('0' + u % 10); return p; }
+    char t[24]; int n = 0;
+    do { t[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (n) *p++ = t[--n];
+    return p;
+}
 
 /* One record's CIGAR and MD, built as run-length strings while the pieces arrive in forward order.
  * Same output as edlibCigar_toString (:1596-1626: leading / trailing insert runs print as soft
  * clips) and edlibMD_toString (:1717-1763) applied to the reference's per-op deques, without
- * materialising one char per op.  Runs of matches in the 2-bit op stream are skipped a word at a time. */
+ * materialising one char per op: runs of matches in the 2-bit op stream are skipped a word at a time and
+ * the text goes straight into per-thread buffers sized from the number of ops (<= 12 bytes per op). */
 struct RecBuf {
-    std::string cig, md;
+    std::vector<char> cbuf, mbuf;
+    char *cp, *mp;
     char cch; long cnum; int cnops;  /* CIGAR run in progress */
     long mnum; char mlast;           /* MD: matches since the last printed item; last move class */
-    RecBuf() { clear(); }
-    void clear() { cig.clear(); md.clear(); cig.reserve(4096); md.reserve(4096); cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '='; }
+    RecBuf() : cp(nullptr), mp(nullptr) { }
+    void begin(size_t max_ops)
+    {
+        const size_t need = 12 * max_ops + 256;
+        if (cbuf.size() < need) { cbuf.resize(need); mbuf.resize(need); }
+        cp = cbuf.data(); mp = mbuf.data();
+        cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '=';
+    }
+    void clear() { cp = cbuf.data(); mp = mbuf.data(); cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '='; }
     inline void cig_run(char c, long n)
     {
         if (n <= 0) return;
         if (c == cch) { cnum += n; return; }
-        if (cch) { put_num(cig, cnum); cig.push_back((cnops == 0 && cch == 'I') ? 'S' : cch); cnops++; }
+        if (cch) { cp = put_num(cp, (unsigned long)cnum); *cp++ = (cnops == 0 && cch == 'I') ? 'S' : cch; cnops++; }
         cch = c; cnum = n;
     }
     inline void md_match(long n) { if (n > 0) { mnum += n; mlast = '='; } }
     inline void md_ins(long n) { if (n > 0) mlast = 'I'; }
-    inline void md_mismatch(char b) { put_num(md, mnum); mnum = 0; md.push_back(b); mlast = 'X'; }
-    inline void md_del(char b) { if (mlast != 'D') { put_num(md, mnum); mnum = 0; md.push_back('^'); } md.push_back(b); mlast = 'D'; }
+    inline void md_mismatch(char b) { mp = put_num(mp, (unsigned long)mnum); mnum = 0; *mp++ = b; mlast = 'X'; }
+    inline void md_del(char b) { if (mlast != 'D') { mp = put_num(mp, (unsigned long)mnum); mnum = 0; *mp++ = '^'; } *mp++ = b; mlast = 'D'; }
     void run(char c, size_t n) { cig_run(c, (long)n); if (c == 'I') md_ins((long)n); else md_match((long)n); }
     void del_run(const uint8_t *pac, uint32_t t0, uint32_t n) { cig_run('D', (long)n); for (uint32_t k = 0; k < n; k++) md_del(pac_base(pac, t0 + k)); }
     void finish(std::string &out_cig, std::string &out_md)
     {
-        if (cnum) { put_num(cig, cnum); cig.push_back(cch == 'I' ? 'S' : cch); }
-        put_num(md, mnum);
-        out_cig.swap(cig); out_md.swap(md);
+        if (cnum) { cp = put_num(cp, (unsigned long)cnum); *cp++ = cch == 'I' ? 'S' : cch; }
+        mp = put_num(mp, (unsigned long)mnum);
+        out_cig.assign(cbuf.data(), (size_t)(cp - cbuf.data()));
+        out_md.assign(mbuf.data(), (size_t)(mp - mbuf.data()));
     }
     /* ops of one alignment; reversed = the task ran right-to-left (pushfront in the reference);
      * t0 = forward reference position of the first target base the segment covers */
@@ -126,7 +145,7 @@ struct RecBuf {
         uint32_t k = 0;
         const uint32_t n = r.ops_len;
         while (k < n) {
-            /* count the run of matches starting at op k, up to 28 ops per 64-bit load */
+            /* count the run of matches starting at op k, up to 32 ops per 64-bit load */
             long run = 0;
             for (;;) {
                 if (k >= n) break;
@@ -144,7 +163,7 @@ struct RecBuf {
                 } else {
                     const uint64_t p = r.ops_off + (n - 1 - k);  /* current op, walking down */
                     const uint64_t byte = p >> 2;
-                    const uint64_t lo = byte >= 7 ? byte - 7 : 0; /* the op stream is preceded by >= 0 bytes; clamp */
+                    const uint64_t lo = byte >= 7 ? byte - 7 : 0;
                     memcpy(&w, ops + lo, 8);
                     const unsigned top = (unsigned)((byte - lo) * 4 + (p & 3)); /* index of op p inside w */
                     w <<= (62 - 2 * top);                        /* op p now in the two highest bits */
@@ -295,6 +314,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     const size_t total_seeds = gap_base[n_chains];
     std::vector<int32_t> gap_task(total_seeds, -1); /* per (chain, seed i): round-1 task of the gap after seed i, or -1 */
     std::vector<uint32_t> ntask(n_chains, 0);
+    std::vector<uint64_t> nslot(n_chains, 0); /* op-slot words of the chain's round-1 tasks */
     bool bad_rid = false;
     /* pass A: boundaries, guards and task counts per chain */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
@@ -309,18 +329,20 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             p.chrBeg = (uint32_t)contigs->offset[rid];
             p.chrEnd = (uint32_t)(contigs->offset[rid] + contigs->len[rid] - 1);
             uint32_t cnt = 0;
+            uint64_t slots = 0;
             const int32_t a = (int32_t)s[0].qPos;
             p.head_guard = a > 0 && (int64_t)s[0].tPos - (a + 20) >= (int64_t)p.chrBeg;                       /* :1823-1825 */
-            cnt += p.head_guard;
+            if (p.head_guard) { cnt++; slots += ((uint64_t)(2 * a + 20) + 15) >> 4; }
             for (uint32_t i = 0; i + 1 < n; i++) {
                 const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
-                cnt += ((int32_t)(s[i + 1].qPos - qs) > 0 && (int32_t)(s[i + 1].tPos - ts) > 0);
+                const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
+                if (ql > 0 && tl > 0) { cnt++; slots += ((uint64_t)ql + (uint64_t)tl + 15) >> 4; }
             }
             const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
             const int32_t b = (int32_t)readLen - (int32_t)qs;
             p.tail_guard = b > 0 && s[n - 1].tPos + s[n - 1].len + (uint32_t)(b + 20) - 1 <= p.chrEnd;         /* :2161-2163 */
-            cnt += p.tail_guard;
-            ntask[c] = cnt;
+            if (p.tail_guard) { cnt++; slots += ((uint64_t)(2 * b + 20) + 15) >> 4; }
+            ntask[c] = cnt; nslot[c] = slots;
         }
     });
     if (bad_rid) { delete R; return LF_ERR_BAD_ARG; }
@@ -357,7 +379,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             }
         }
     });
-    const size_t cap1 = lf_gpu_ops_capacity(t1, n1);
+    size_t cap1 = 64;
+    for (size_t c = 0; c < n_chains; c++) cap1 += nslot[c] * 4;
     uint8_t *ops1 = (uint8_t *)S.ops1.reserve(cap1 + 64);
     if (!ops1) { delete R; return LF_ERR_NOMEM; }
     const double tm1 = now_ms();
@@ -510,7 +533,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             const uint32_t flag_norm = ch.is_rev ? 16u : 0u, flag_opp = ch.is_rev ? 0u : 16u;
             uint32_t flag = flag_norm, pos = s[0].tPos, qStart = s[0].qPos, posEnd = 0, qEnd = 0;
             int32_t editScore = 0;
-            B.clear();
+            /* every op of a record consumes a read base or a reference base of the chain's span (+ clips) */
+            B.begin(3 * (size_t)readLen + (size_t)(s[n - 1].tPos + s[n - 1].len - s[0].tPos) + 4096);
             /* head (:1820-1899) */
             const int32_t a = (int32_t)s[0].qPos;
             if (a > 0) {
