@@ -289,7 +289,7 @@ def main():
             "gcups": cells * world / (wall_ms_max * 1e-3) / 1e9,
             "e2e": {"value": e2e_v, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max},
             "e2e_chains": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chain_ms_max, "records_per_gpu": int(nrec),
-                           "host_phase_ms": {"tasks": round(cst.ms_tasks, 2), "round1": round(cst.ms_round1, 2), "rounds2_3": round(cst.ms_rounds23, 2), "emit": round(cst.ms_emit, 2)},
+                           "host_phase_ms": {"tasks": round(cst.ms_tasks, 2), "round1": round(cst.ms_round1, 2), "rounds2_3": round(cst.ms_rounds23, 2), "emit": round(cst.ms_emit, 2), "merge": round(cst.ms_merge, 2)},
                            "rounds": {"round1_tasks": int(cst.round1_tasks), "round2_extends": int(cst.round2_extends), "round3_tasks": int(cst.round3_tasks)},
                            "what": "lf_gpu_align_chains: chains + reads from host memory in, CIGAR/MD/NM records out (3 GPU rounds + host emit)"},
             "gpu_launches": launches,

@@ -170,7 +170,8 @@ typedef struct {         /* Sam_t fields alignChain_edlib fills (src/LordFAST.h:
 } lf_sam_record;
 typedef struct {
     uint64_t round1_tasks, round2_extends, round3_tasks, records;
-    float ms_tasks, ms_round1, ms_rounds23, ms_emit; /* host wall time of the phases of the call */
+    float ms_tasks, ms_round1, ms_rounds23, ms_emit, ms_merge; /* host wall time of the phases of the call */
+    float reserved;
 } lf_chain_stats;
 typedef struct lf_chain_results lf_chain_results;         /* library-owned, free with lf_chain_results_free */
 

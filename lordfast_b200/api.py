@@ -47,7 +47,7 @@ class Contigs(C.Structure):
 
 class ChainStats(C.Structure):
     _fields_ = [("round1_tasks", C.c_uint64), ("round2_extends", C.c_uint64), ("round3_tasks", C.c_uint64), ("records", C.c_uint64),
-                ("ms_tasks", C.c_float), ("ms_round1", C.c_float), ("ms_rounds23", C.c_float), ("ms_emit", C.c_float)]
+                ("ms_tasks", C.c_float), ("ms_round1", C.c_float), ("ms_rounds23", C.c_float), ("ms_emit", C.c_float), ("ms_merge", C.c_float), ("reserved", C.c_float)]
 
 
 class Stats(C.Structure):

@@ -257,9 +257,9 @@ struct ChainScratch { PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2; };
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
 
 template <typename F>
-void parallel_for(size_t n, unsigned nthreads, F fn)
+void parallel_for(size_t n, unsigned nthreads, F fn, size_t serial_below = 256)
 { /* fn(tid, lo, hi) over contiguous ranges */
-    if (nthreads <= 1 || n < 256) { fn(0u, (size_t)0, n); return; }
+    if (nthreads <= 1 || n < serial_below) { fn(0u, (size_t)0, n); return; }
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nthreads; t++) th.emplace_back(fn, t, n * t / nthreads, n * (t + 1) / nthreads);
     for (auto &t : th) t.join();
@@ -523,6 +523,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<Emit> parts(nthreads);
     auto work = [&](unsigned tid, size_t c_lo, size_t c_hi) {
         Emit &E = parts[tid];
+        E.text.reserve((size_t)((cap1 + cap3) / (nthreads ? nthreads : 1)) + 4096); /* text is shorter than the 2-bit op stream */
         RecBuf B;
         for (size_t c = c_lo; c < c_hi; c++) {
             const lf_chain &ch = chains[c];
@@ -640,17 +641,22 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         }
     };
     parallel_for(n_chains, nthreads, work);
-    size_t nrec = 0, ntext = 0;
-    for (Emit &E : parts) { nrec += E.recs.size(); ntext += E.text.size(); }
-    R->recs.reserve(nrec); R->text.reserve(ntext);
-    for (Emit &E : parts) {
-        const uint64_t base = R->text.size();
-        R->text.append(E.text);
-        for (lf_sam_record r : E.recs) { r.cigar_off += base; r.md_off += base; R->recs.push_back(r); }
-    }
+    const double tm3b = now_ms();
+    /* merge the per-thread parts: sizes first, then every thread copies its own text and rebases its records */
+    std::vector<size_t> rec_base(parts.size() + 1, 0), text_base(parts.size() + 1, 0);
+    for (size_t k = 0; k < parts.size(); k++) { rec_base[k + 1] = rec_base[k] + parts[k].recs.size(); text_base[k + 1] = text_base[k] + parts[k].text.size(); }
+    R->recs.resize(rec_base.back());
+    R->text.resize(text_base.back());
+    parallel_for(parts.size(), (unsigned)parts.size(), [&](unsigned, size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++) {
+            Emit &E = parts[k];
+            if (!E.text.empty()) memcpy(&R->text[text_base[k]], E.text.data(), E.text.size());
+            for (size_t j = 0; j < E.recs.size(); j++) { lf_sam_record r = E.recs[j]; r.cigar_off += text_base[k]; r.md_off += text_base[k]; R->recs[rec_base[k] + j] = r; }
+        }
+    }, 2);
     R->stats.records = R->recs.size();
     const double tm4 = now_ms();
-    R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm4 - tm3);
+    R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm3b - tm3); R->stats.ms_merge = (float)(tm4 - tm3b);
     *out = R;
     return LF_OK;
 }
