@@ -19,9 +19,10 @@
 #include <time.h>
 
 struct lf_chain_results {
-    std::vector<lf_sam_record> recs;
-    std::string text;
+    lf_sam_record *recs = nullptr; size_t n_recs = 0;
+    char *text = nullptr; size_t text_bytes = 0;   /* raw buffers: filled by the emit threads, never zero-filled first */
     lf_chain_stats stats;
+    ~lf_chain_results() { free(recs); free(text); }
 };
 
 namespace {
@@ -645,24 +646,26 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     /* merge the per-thread parts: sizes first, then every thread copies its own text and rebases its records */
     std::vector<size_t> rec_base(parts.size() + 1, 0), text_base(parts.size() + 1, 0);
     for (size_t k = 0; k < parts.size(); k++) { rec_base[k + 1] = rec_base[k] + parts[k].recs.size(); text_base[k + 1] = text_base[k] + parts[k].text.size(); }
-    R->recs.resize(rec_base.back());
-    R->text.resize(text_base.back());
+    R->n_recs = rec_base.back(); R->text_bytes = text_base.back();
+    R->recs = (lf_sam_record *)malloc((R->n_recs + 1) * sizeof(lf_sam_record));
+    R->text = (char *)malloc(R->text_bytes + 1);
+    if (!R->recs || !R->text) { delete R; return LF_ERR_NOMEM; }
     parallel_for(parts.size(), (unsigned)parts.size(), [&](unsigned, size_t lo, size_t hi) {
         for (size_t k = lo; k < hi; k++) {
             Emit &E = parts[k];
-            if (!E.text.empty()) memcpy(&R->text[text_base[k]], E.text.data(), E.text.size());
+            if (!E.text.empty()) memcpy(R->text + text_base[k], E.text.data(), E.text.size());
             for (size_t j = 0; j < E.recs.size(); j++) { lf_sam_record r = E.recs[j]; r.cigar_off += text_base[k]; r.md_off += text_base[k]; R->recs[rec_base[k] + j] = r; }
         }
     }, 2);
-    R->stats.records = R->recs.size();
+    R->stats.records = R->n_recs;
     const double tm4 = now_ms();
     R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm3b - tm3); R->stats.ms_merge = (float)(tm4 - tm3b);
     *out = R;
     return LF_OK;
 }
 
-const lf_sam_record *lf_chain_results_records(const lf_chain_results *r, size_t *n) { if (n) *n = r ? r->recs.size() : 0; return r ? r->recs.data() : nullptr; }
-const char *lf_chain_results_text(const lf_chain_results *r, size_t *bytes) { if (bytes) *bytes = r ? r->text.size() : 0; return r ? r->text.data() : nullptr; }
+const lf_sam_record *lf_chain_results_records(const lf_chain_results *r, size_t *n) { if (n) *n = r ? r->n_recs : 0; return r ? r->recs : nullptr; }
+const char *lf_chain_results_text(const lf_chain_results *r, size_t *bytes) { if (bytes) *bytes = r ? r->text_bytes : 0; return r ? r->text : nullptr; }
 int lf_chain_results_stats(const lf_chain_results *r, lf_chain_stats *out) { if (!r || !out) return LF_ERR_BAD_ARG; *out = r->stats; return LF_OK; }
 void lf_chain_results_free(lf_chain_results *r) { delete r; }
 

@@ -1,6 +1,32 @@
 /* TEST-ONLY: fiber scheduler of the CUDA emulator (see cuda_emu.h). */
 #include "cuda_emu.h"
 
+#if !defined(__x86_64__)
+#error "the test-only CUDA emulator has an x86-64 context switch"
+#endif
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq (%rsi), %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+
 namespace emu {
 Block *g_blk = nullptr;
 size_t g_stack_bytes = 256 * 1024;
@@ -20,7 +46,8 @@ void fiber_entry()
     b->warp_live[(size_t)w]--;
     if (b->warp_live[(size_t)w] && b->warp_arrived[(size_t)w] == b->warp_live[(size_t)w]) { b->warp_arrived[(size_t)w] = 0; b->warp_gen[(size_t)w]++; }
     if (b->live && b->block_arrived == b->live) { b->block_arrived = 0; b->block_gen++; }
-    swapcontext(&f.ctx, &b->sched);
+    emu_switch(&f.ctx, &b->sched);
+    abort(); /* a finished fiber is never resumed */
 }
 
 void launch(emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void()> &body)
@@ -44,11 +71,14 @@ void launch(emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void
                     f.tid = emu_dim3((unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((size_t)block.x * block.y)));
                     if (g_stacks.size() <= t) g_stacks.push_back((char *)malloc(g_stack_bytes));
                     f.stack = g_stacks[t];
-                    getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = f.stack;
-                    f.ctx.uc_stack.ss_size = g_stack_bytes;
-                    f.ctx.uc_link = &blk.sched;
-                    makecontext(&f.ctx, fiber_entry, 0);
+                    {   /* initial frame: six callee-saved slots, the entry address `ret` jumps to, a fake return slot */
+                        uintptr_t top = ((uintptr_t)f.stack + g_stack_bytes) & ~(uintptr_t)15;
+                        void **sp = (void **)(top - 64);
+                        for (int k = 0; k < 6; k++) sp[k] = nullptr;
+                        sp[6] = (void *)&fiber_entry;
+                        sp[7] = nullptr;
+                        f.ctx.sp = sp;
+                    }
                     blk.warp_live[t >> 5]++;
                 }
                 size_t remaining = nthreads, stalled = 0;
@@ -57,7 +87,7 @@ void launch(emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void
                     for (size_t t = 0; t < nthreads; t++) {
                         if (blk.fibers[t].done) continue;
                         blk.cur = (int)t;
-                        swapcontext(&blk.sched, &blk.fibers[t].ctx);
+                        emu_switch(&blk.sched, &blk.fibers[t].ctx);
                         if (blk.fibers[t].done) remaining--;
                     }
                     /* a round in which no barrier opened and no thread finished means every live thread is

@@ -15,7 +15,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <ucontext.h>
 #include <algorithm>
 #include <functional>
 #include <vector>
@@ -39,8 +38,13 @@ static inline uint2 make_uint2(uint32_t a, uint32_t b) { uint2 r = { a, b }; ret
 static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { uint4 r = { a, b, c, d }; return r; }
 
 namespace emu {
+/* minimal x86-64 context switch (callee-saved registers + stack pointer); ucontext's swapcontext makes a
+ * sigprocmask system call per switch, which made shuffle-heavy kernels take minutes to emulate */
+struct Ctx { void *sp; };
+extern "C" void emu_switch(Ctx *from, Ctx *to);
+
 struct Fiber {
-    ucontext_t ctx;
+    Ctx ctx;
     char *stack = nullptr;
     bool done = false;
     emu_dim3 tid;
@@ -50,7 +54,7 @@ struct Fiber {
 };
 struct Block {
     std::vector<Fiber> fibers;
-    ucontext_t sched;
+    Ctx sched;
     int cur = -1;
     emu_dim3 bid, bdim, gdim;
     std::vector<unsigned> warp_arrived, warp_gen; /* per warp */
@@ -64,7 +68,7 @@ extern size_t g_stack_bytes;
 extern unsigned long g_progress;
 
 inline Fiber &self() { return g_blk->fibers[(size_t)g_blk->cur]; }
-inline void yield() { swapcontext(&self().ctx, &g_blk->sched); }
+inline void yield() { emu_switch(&self().ctx, &g_blk->sched); }
 inline int lane_id() { return g_blk->cur & 31; }
 inline int warp_id() { return g_blk->cur >> 5; }
 
