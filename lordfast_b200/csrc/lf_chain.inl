@@ -15,14 +15,40 @@
  *
  * Included by lf_pipeline.inl (so it is part of liblfgpu.so and of the test-only emulator build).
  */
+#include <mutex>
 #include <thread>
 #include <time.h>
 
+/* Result text is ~1.2 bytes per read base (240 MB per 20k x 10 kbp chunk); mapping that much fresh memory costs more
+ * in page faults than filling it, so freed result buffers are parked here and reused by the next call. */
+struct LfBufPool {
+    std::mutex mu;
+    struct Item { void *p; size_t cap; };
+    std::vector<Item> items;
+    void *get(size_t need, size_t *cap)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < items.size(); i++)
+            if (items[i].cap >= need) { void *p = items[i].p; *cap = items[i].cap; items.erase(items.begin() + (long)i); return p; }
+        if (!items.empty()) { free(items.back().p); items.pop_back(); }
+        *cap = need + need / 8 + 4096;
+        return malloc(*cap);
+    }
+    void put(void *p, size_t cap)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (items.size() >= 4) { free(p); return; }
+        items.push_back(Item{p, cap});
+    }
+};
+static LfBufPool g_result_pool;
+
 struct lf_chain_results {
-    lf_sam_record *recs = nullptr; size_t n_recs = 0;
-    char *text = nullptr; size_t text_bytes = 0;   /* raw buffers: filled by the emit threads, never zero-filled first */
+    lf_sam_record *recs = nullptr; size_t n_recs = 0, recs_cap = 0;
+    char *text = nullptr; size_t text_bytes = 0, text_cap = 0;
     lf_chain_stats stats;
-    ~lf_chain_results() { free(recs); free(text); }
+    ~lf_chain_results() { g_result_pool.put(recs, recs_cap); g_result_pool.put(text, text_cap); }
 };
 
 namespace {
@@ -254,7 +280,8 @@ struct PinBuf {
     void *reserve(size_t need) { if (need > cap) { lfb_host_free(p); cap = need + need / 4 + 4096; p = lfb_host_alloc(cap); if (!p) cap = 0; } return p; }
     void release() { lfb_host_free(p); p = nullptr; cap = 0; }
 };
-struct ChainScratch { PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2; };
+struct Emit;
+struct ChainScratch { PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2; std::vector<Emit> *parts = nullptr; };
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
 
 template <typename F>
@@ -277,6 +304,7 @@ void chain_scratch_free_fn(void *p)
     ChainScratch *s = (ChainScratch *)p;
     PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2 };
     for (PinBuf *b : all) b->release();
+    delete s->parts;
     delete s;
 }
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx)
@@ -521,7 +549,10 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
 
     /* ---------------- emit: the reference's accumulation, chain by chain ---------------- */
     if (n_chains < 64) nthreads = 1;
-    std::vector<Emit> parts(nthreads);
+    if (!S.parts) S.parts = new std::vector<Emit>();
+    std::vector<Emit> &parts = *S.parts;   /* kept between calls: their buffers are already mapped */
+    if (parts.size() != nthreads) parts.resize(nthreads);
+    for (Emit &E : parts) { E.recs.clear(); E.text.clear(); }
     auto work = [&](unsigned tid, size_t c_lo, size_t c_hi) {
         Emit &E = parts[tid];
         E.text.reserve((size_t)((cap1 + cap3) / (nthreads ? nthreads : 1)) + 4096); /* text is shorter than the 2-bit op stream */
@@ -647,8 +678,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<size_t> rec_base(parts.size() + 1, 0), text_base(parts.size() + 1, 0);
     for (size_t k = 0; k < parts.size(); k++) { rec_base[k + 1] = rec_base[k] + parts[k].recs.size(); text_base[k + 1] = text_base[k] + parts[k].text.size(); }
     R->n_recs = rec_base.back(); R->text_bytes = text_base.back();
-    R->recs = (lf_sam_record *)malloc((R->n_recs + 1) * sizeof(lf_sam_record));
-    R->text = (char *)malloc(R->text_bytes + 1);
+    R->recs = (lf_sam_record *)g_result_pool.get((R->n_recs + 1) * sizeof(lf_sam_record), &R->recs_cap);
+    R->text = (char *)g_result_pool.get(R->text_bytes + 1, &R->text_cap);
     if (!R->recs || !R->text) { delete R; return LF_ERR_NOMEM; }
     parallel_for(parts.size(), (unsigned)parts.size(), [&](unsigned, size_t lo, size_t hi) {
         for (size_t k = lo; k < hi; k++) {
