@@ -28,9 +28,11 @@ struct LfBufPool {
     void *get(size_t need, size_t *cap)
     {
         std::lock_guard<std::mutex> g(mu);
-        for (size_t i = 0; i < items.size(); i++)
-            if (items[i].cap >= need) { void *p = items[i].p; *cap = items[i].cap; items.erase(items.begin() + (long)i); return p; }
-        if (!items.empty()) { free(items.back().p); items.pop_back(); }
+        size_t bi = items.size();
+        for (size_t i = 0; i < items.size(); i++)   /* best fit: the record array must not grab the text buffer */
+            if (items[i].cap >= need && (bi == items.size() || items[i].cap < items[bi].cap)) bi = i;
+        if (bi < items.size()) { void *p = items[bi].p; *cap = items[bi].cap; items.erase(items.begin() + (long)bi); return p; }
+        if (items.size() >= 4) { free(items.back().p); items.pop_back(); }
         *cap = need + need / 8 + 4096;
         return malloc(*cap);
     }
@@ -257,18 +259,21 @@ struct SlowRec {
 
 struct Emit {
     std::vector<lf_sam_record> recs;
-    std::string text, tc, tm;
+    std::string tc, tm;
+    RecBuf B;                 /* kept between calls together with the vectors above: no fresh pages per call */
+    char *base = nullptr, *cur = nullptr, *lim = nullptr; /* this thread's slice of the result text buffer */
+    bool overflow = false;
     void push_strings(uint32_t chain_id, uint32_t flag, uint32_t pos, uint32_t posEnd, uint32_t qStart, uint32_t qEnd, int32_t nm)
     {
         lf_sam_record r;
         r.chain_id = chain_id; r.flag = flag; r.pos = pos; r.posEnd = posEnd; r.qStart = qStart; r.qEnd = qEnd; r.nmCount = nm;
-        r.cigar_off = text.size(); text.append(tc); r.cigar_len = (uint32_t)tc.size(); text.push_back('\0');
-        r.md_off = text.size(); text.append(tm); r.md_len = (uint32_t)tm.size(); text.push_back('\0');
+        if (cur + tc.size() + tm.size() + 2 > lim) { overflow = true; return; }
+        r.cigar_off = (uint64_t)(cur - base); memcpy(cur, tc.data(), tc.size()); cur += tc.size(); *cur++ = '\0'; r.cigar_len = (uint32_t)tc.size();
+        r.md_off = (uint64_t)(cur - base); memcpy(cur, tm.data(), tm.size()); cur += tm.size(); *cur++ = '\0'; r.md_len = (uint32_t)tm.size();
         recs.push_back(r);
     }
     void push(uint32_t chain_id, uint32_t flag, uint32_t pos, uint32_t posEnd, uint32_t qStart, uint32_t qEnd, int32_t nm, RecBuf &b)
     {
-        tc.clear(); tm.clear();
         b.finish(tc, tm);
         push_strings(chain_id, flag, pos, posEnd, qStart, qEnd, nm);
     }
@@ -280,7 +285,6 @@ struct PinBuf {
     void *reserve(size_t need) { if (need > cap) { lfb_host_free(p); cap = need + need / 4 + 4096; p = lfb_host_alloc(cap); if (!p) cap = 0; } return p; }
     void release() { lfb_host_free(p); p = nullptr; cap = 0; }
 };
-struct Emit;
 struct ChainScratch { PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2; std::vector<Emit> *parts = nullptr; };
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
 
@@ -552,11 +556,42 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     if (!S.parts) S.parts = new std::vector<Emit>();
     std::vector<Emit> &parts = *S.parts;   /* kept between calls: their buffers are already mapped */
     if (parts.size() != nthreads) parts.resize(nthreads);
-    for (Emit &E : parts) { E.recs.clear(); E.text.clear(); }
+    /* Upper bound of a chain's text: every non-match op and every run boundary costs at most 16 bytes in
+     * CIGAR + MD together; non-match ops = the edit distances, run boundaries <= 2 per piece.  The result
+     * buffer is sliced by these bounds so that the emit threads write their records in place (no merge). */
+    std::vector<uint64_t> tbound(n_chains + 1, 0);
+    for (size_t c = 0; c < n_chains; c++) {
+        uint64_t ev = 4ull * chains[c].n_seeds + 64;
+        if (plan[c].head_task >= 0) ev += (uint64_t)r1[(size_t)plan[c].head_task].edit_distance;
+        if (plan[c].tail_task >= 0) ev += (uint64_t)r1[(size_t)plan[c].tail_task].edit_distance;
+        for (uint64_t g = gap_base[c]; g < gap_base[c + 1]; g++) {
+            if (gap_task[g] >= 0) ev += (uint64_t)r1[(size_t)gap_task[g]].edit_distance;
+            if (gap_split[g] >= 0) { /* a split re-aligns its pieces: distances of the round-3 tasks, plus up to three records */
+                const SplitInfo &si = splits[(size_t)gap_split[g]];
+                const int32_t ids[4] = { si.t_first, si.t_mid_f, si.t_mid_r, si.t_second };
+                for (int32_t id : ids) if (id >= 0) ev += (uint64_t)r3[(size_t)id].edit_distance + r3[(size_t)id].ops_len / 4 + 64;
+                ev += 256;
+            }
+        }
+        const lf_seed *sd = seeds + chains[c].seed_off;   /* pure insert / delete gaps print one item per deleted base */
+        ev += (uint64_t)(sd[chains[c].n_seeds - 1].tPos - sd[0].tPos) / 8;
+        if (plan[c].head_clip >= 0 && clips[(size_t)plan[c].head_clip].t3 >= 0) ev += (uint64_t)r3[(size_t)clips[(size_t)plan[c].head_clip].t3].edit_distance;
+        if (plan[c].tail_clip >= 0 && clips[(size_t)plan[c].tail_clip].t3 >= 0) ev += (uint64_t)r3[(size_t)clips[(size_t)plan[c].tail_clip].t3].edit_distance;
+        tbound[c + 1] = tbound[c] + 16 * ev;
+    }
+    R->text_bytes = tbound[n_chains];
+    R->text = (char *)g_result_pool.get(R->text_bytes + 1, &R->text_cap);
+    if (!R->text) { delete R; return LF_ERR_NOMEM; }
+    for (unsigned t = 0; t < nthreads; t++) {
+        Emit &E = parts[t];
+        E.recs.clear(); E.overflow = false;
+        E.base = R->text;
+        E.cur = R->text + tbound[n_chains * t / nthreads];
+        E.lim = R->text + tbound[n_chains * (t + 1) / nthreads];
+    }
     auto work = [&](unsigned tid, size_t c_lo, size_t c_hi) {
         Emit &E = parts[tid];
-        E.text.reserve((size_t)((cap1 + cap3) / (nthreads ? nthreads : 1)) + 4096); /* text is shorter than the 2-bit op stream */
-        RecBuf B;
+        RecBuf &B = E.B;
         for (size_t c = c_lo; c < c_hi; c++) {
             const lf_chain &ch = chains[c];
             const lf_seed *s = seeds + ch.seed_off;
@@ -674,20 +709,16 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     };
     parallel_for(n_chains, nthreads, work);
     const double tm3b = now_ms();
-    /* merge the per-thread parts: sizes first, then every thread copies its own text and rebases its records */
-    std::vector<size_t> rec_base(parts.size() + 1, 0), text_base(parts.size() + 1, 0);
-    for (size_t k = 0; k < parts.size(); k++) { rec_base[k + 1] = rec_base[k] + parts[k].recs.size(); text_base[k + 1] = text_base[k] + parts[k].text.size(); }
-    R->n_recs = rec_base.back(); R->text_bytes = text_base.back();
-    R->recs = (lf_sam_record *)g_result_pool.get((R->n_recs + 1) * sizeof(lf_sam_record), &R->recs_cap);
-    R->text = (char *)g_result_pool.get(R->text_bytes + 1, &R->text_cap);
-    if (!R->recs || !R->text) { delete R; return LF_ERR_NOMEM; }
-    parallel_for(parts.size(), (unsigned)parts.size(), [&](unsigned, size_t lo, size_t hi) {
-        for (size_t k = lo; k < hi; k++) {
-            Emit &E = parts[k];
-            if (!E.text.empty()) memcpy(R->text + text_base[k], E.text.data(), E.text.size());
-            for (size_t j = 0; j < E.recs.size(); j++) { lf_sam_record r = E.recs[j]; r.cigar_off += text_base[k]; r.md_off += text_base[k]; R->recs[rec_base[k] + j] = r; }
-        }
-    }, 2);
+    /* records of all threads, in chain order (the text is already in place) */
+    size_t nrec = 0;
+    bool overflow = false;
+    for (Emit &E : parts) { nrec += E.recs.size(); overflow |= E.overflow; }
+    if (overflow) { delete R; return fail(ctx, LF_ERR_NOMEM, "chain text bound exceeded"); }
+    R->n_recs = nrec;
+    R->recs = (lf_sam_record *)g_result_pool.get((nrec + 1) * sizeof(lf_sam_record), &R->recs_cap);
+    if (!R->recs) { delete R; return LF_ERR_NOMEM; }
+    nrec = 0;
+    for (Emit &E : parts) { if (!E.recs.empty()) memcpy(R->recs + nrec, E.recs.data(), E.recs.size() * sizeof(lf_sam_record)); nrec += E.recs.size(); }
     R->stats.records = R->n_recs;
     const double tm4 = now_ms();
     R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm3b - tm3); R->stats.ms_merge = (float)(tm4 - tm3b);
