@@ -721,6 +721,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     for (Emit &E : parts) { if (!E.recs.empty()) memcpy(R->recs + nrec, E.recs.data(), E.recs.size() * sizeof(lf_sam_record)); nrec += E.recs.size(); }
     R->stats.records = R->n_recs;
     const double tm4 = now_ms();
+    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] tasks %.2f r1 %.2f r23 %.2f emit %.2f gather %.2f (threads %u, recs %zu, text bound %zu MB)\n",
+                                          tm1 - tm0, tm2 - tm1, tm3 - tm2, tm3b - tm3, tm4 - tm3b, nthreads, R->n_recs, R->text_bytes >> 20);
     R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm3b - tm3); R->stats.ms_merge = (float)(tm4 - tm3b);
     *out = R;
     return LF_OK;
