@@ -267,7 +267,7 @@ struct Emit {
     {
         lf_sam_record r;
         r.chain_id = chain_id; r.flag = flag; r.pos = pos; r.posEnd = posEnd; r.qStart = qStart; r.qEnd = qEnd; r.nmCount = nm;
-        if (cur + tc.size() + tm.size() + 2 > lim) { overflow = true; return; }
+        if (cur + tc.size() + tm.size() + 2 > lim) { if (!overflow && getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] text bound exceeded at chain %u: cigar %zu md %zu left %ld\n", chain_id, tc.size(), tm.size(), (long)(lim - cur)); overflow = true; return; }
         r.cigar_off = (uint64_t)(cur - base); memcpy(cur, tc.data(), tc.size()); cur += tc.size(); *cur++ = '\0'; r.cigar_len = (uint32_t)tc.size();
         r.md_off = (uint64_t)(cur - base); memcpy(cur, tm.data(), tm.size()); cur += tm.size(); *cur++ = '\0'; r.md_len = (uint32_t)tm.size();
         recs.push_back(r);
@@ -552,7 +552,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
 #undef LF_CH
 
     /* ---------------- emit: the reference's accumulation, chain by chain ---------------- */
-    if (n_chains < 64) nthreads = 1;
+    if (n_chains < 256) nthreads = 1; /* same threshold as parallel_for's serial mode: one part, one slice */
     if (!S.parts) S.parts = new std::vector<Emit>();
     std::vector<Emit> &parts = *S.parts;   /* kept between calls: their buffers are already mapped */
     if (parts.size() != nthreads) parts.resize(nthreads);
@@ -707,7 +707,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             E.push((uint32_t)c, flag, pos, posEnd, qStart, qEnd, editScore, B);
         }
     };
-    parallel_for(n_chains, nthreads, work);
+    parallel_for(n_chains, nthreads, work, 256);
     const double tm3b = now_ms();
     /* records of all threads, in chain order (the text is already in place) */
     size_t nrec = 0;
