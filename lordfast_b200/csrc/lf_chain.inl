@@ -22,6 +22,9 @@
 /* Result text is ~1.2 bytes per read base (240 MB per 20k x 10 kbp chunk); mapping that much fresh memory costs more
  * in page faults than filling it, so freed result buffers are parked here and reused by the next call. */
 struct LfBufPool {
+    bool pinned = false;   /* pinned host memory (D2H target of the GPU emit) or plain malloc */
+    void *raw_alloc(size_t n) { return pinned ? lfb_host_alloc(n) : malloc(n); }
+    void raw_free(void *p) { if (pinned) lfb_host_free(p); else free(p); }
     std::mutex mu;
     struct Item { void *p; size_t cap; };
     std::vector<Item> items;
@@ -32,25 +35,27 @@ struct LfBufPool {
         for (size_t i = 0; i < items.size(); i++)   /* best fit: the record array must not grab the text buffer */
             if (items[i].cap >= need && (bi == items.size() || items[i].cap < items[bi].cap)) bi = i;
         if (bi < items.size()) { void *p = items[bi].p; *cap = items[bi].cap; items.erase(items.begin() + (long)bi); return p; }
-        if (items.size() >= 4) { free(items.back().p); items.pop_back(); }
+        if (items.size() >= 4) { raw_free(items.back().p); items.pop_back(); }
         *cap = need + need / 8 + 4096;
-        return malloc(*cap);
+        return raw_alloc(*cap);
     }
     void put(void *p, size_t cap)
     {
         if (!p) return;
         std::lock_guard<std::mutex> g(mu);
-        if (items.size() >= 4) { free(p); return; }
+        if (items.size() >= 4) { raw_free(p); return; }
         items.push_back(Item{p, cap});
     }
 };
 static LfBufPool g_result_pool;
+static LfBufPool g_result_pool_pinned;
 
 struct lf_chain_results {
     lf_sam_record *recs = nullptr; size_t n_recs = 0, recs_cap = 0;
     char *text = nullptr; size_t text_bytes = 0, text_cap = 0;
     lf_chain_stats stats;
-    ~lf_chain_results() { g_result_pool.put(recs, recs_cap); g_result_pool.put(text, text_cap); }
+    bool pinned = false;
+    ~lf_chain_results() { LfBufPool &P = pinned ? g_result_pool_pinned : g_result_pool; P.put(recs, recs_cap); P.put(text, text_cap); }
 };
 
 namespace {
@@ -285,7 +290,12 @@ struct PinBuf {
     void *reserve(size_t need) { if (need > cap) { lfb_host_free(p); cap = need + need / 4 + 4096; p = lfb_host_alloc(cap); if (!p) cap = 0; } return p; }
     void release() { lfb_host_free(p); p = nullptr; cap = 0; }
 };
-struct ChainScratch { PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2; std::vector<Emit> *parts = nullptr; };
+struct ChainScratch {
+    PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2, ed1;
+    std::vector<Emit> *parts = nullptr;
+    /* device side of the GPU emit */
+    LfbBuf d_chains, d_seeds, d_task_base, d_guards, d_clip, d_split_begin, d_splits, d_nrec, d_cigb, d_mdb, d_rec_off, d_cig_off, d_md_off, d_recs, d_text, d_ed;
+};
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
 
 template <typename F>
@@ -306,8 +316,11 @@ double now_ms()
 void chain_scratch_free_fn(void *p)
 {
     ChainScratch *s = (ChainScratch *)p;
-    PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2 };
+    PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2, &s->ed1 };
     for (PinBuf *b : all) b->release();
+    LfbBuf *dall[] = { &s->d_chains, &s->d_seeds, &s->d_task_base, &s->d_guards, &s->d_clip, &s->d_split_begin, &s->d_splits, &s->d_nrec, &s->d_cigb, &s->d_mdb,
+                       &s->d_rec_off, &s->d_cig_off, &s->d_md_off, &s->d_recs, &s->d_text, &s->d_ed };
+    for (LfbBuf *b : dall) b->release();
     delete s->parts;
     delete s;
 }
@@ -335,7 +348,18 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     int rc;
     const double tm0 = now_ms();
 #define LF_CH(expr) do { rc = (expr); if (rc != 0) { delete R; return rc; } } while (0)
+    /* CIGAR / MD assembly runs on the GPU (k_emit_chains) when the context drives one device; a context over
+     * several devices assembles on host threads from the 2-bit op stream (LF_CHAIN_HOST_EMIT=1 forces that). */
+    const bool gpu_emit = ctx->devs.size() == 1 && !getenv("LF_CHAIN_HOST_EMIT");
+    g_result_pool_pinned.pinned = true;
     LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
+    if (gpu_emit) {
+        DevState &d = ctx->devs[0];
+        size_t ns = 0;
+        for (size_t c = 0; c < n_chains; c++) { const size_t e = (size_t)chains[c].seed_off + chains[c].n_seeds; if (e > ns) ns = e; }
+        if (S.d_chains.reserve(n_chains * sizeof(lf_chain) + 64) || S.d_seeds.reserve(ns * sizeof(lf_seed) + 64)) { delete R; return LF_ERR_NOMEM; }
+        if (lfb_h2d(S.d_chains.p, chains, n_chains * sizeof(lf_chain), d.stream) || lfb_h2d(S.d_seeds.p, seeds, ns * sizeof(lf_seed), d.stream)) { delete R; return LF_ERR_CUDA; }
+    }
 
     /* ---------------- round 1: tasks known from the chains alone ---------------- */
     std::vector<ChainPlan> plan(n_chains);
@@ -382,8 +406,10 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     for (size_t c = 0; c < n_chains; c++) task_base[c + 1] = task_base[c] + ntask[c];
     const size_t n1 = task_base[n_chains];
     lf_align_task *t1 = (lf_align_task *)S.t1.reserve((n1 + 1) * sizeof(lf_align_task));
-    lf_align_result *r1 = (lf_align_result *)S.r1.reserve((n1 + 1) * sizeof(lf_align_result));
-    if (!t1 || !r1) { delete R; return LF_ERR_NOMEM; }
+    lf_align_result *r1 = gpu_emit ? nullptr : (lf_align_result *)S.r1.reserve((n1 + 1) * sizeof(lf_align_result));
+    int32_t *ed1 = gpu_emit ? (int32_t *)S.ed1.reserve((n1 + 1) * sizeof(int32_t)) : nullptr;
+    if (!t1 || (!r1 && !ed1)) { delete R; return LF_ERR_NOMEM; }
+    auto ed_of = [&](size_t i) -> int32_t { return gpu_emit ? ed1[i] : r1[i].edit_distance; };
     /* pass B: fill */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
         for (size_t c = lo; c < hi; c++) {
@@ -414,13 +440,19 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     });
     size_t cap1 = 64;
     for (size_t c = 0; c < n_chains; c++) cap1 += nslot[c] * 4;
-    uint8_t *ops1 = (uint8_t *)S.ops1.reserve(cap1 + 64);
-    if (!ops1) { delete R; return LF_ERR_NOMEM; }
+    uint8_t *ops1 = gpu_emit ? nullptr : (uint8_t *)S.ops1.reserve(cap1 + 64);
+    if (!gpu_emit && !ops1) { delete R; return LF_ERR_NOMEM; }
     const double tm1 = now_ms();
     if (n1) {
         LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
         LF_CH(lf_gpu_run_align(ctx));
-        LF_CH(lf_gpu_download_align(ctx, r1, ops1, cap1));
+        if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r1, ops1, cap1));
+        else { /* results and ops stay in HBM; only the distances come back for the trigger tests */
+            DevState &d = ctx->devs[0];
+            if (S.d_ed.reserve((n1 + 1) * 4)) { delete R; return LF_ERR_NOMEM; }
+            LFB_LAUNCH(k_gather_ed, (unsigned)((n1 + 255) / 256), 256, 0, d.stream, d.res.as<lf_align_result>(), S.d_ed.as<int32_t>(), (uint32_t)n1);
+            if (lfb_d2h(ed1, S.d_ed.p, n1 * 4, d.stream) || lfb_sync(d.stream)) { delete R; return LF_ERR_CUDA; }
+        }
     }
     R->stats.round1_tasks = n1;
     const double tm2 = now_ms();
@@ -437,7 +469,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         ChainPlan &p = plan[c];
         if (p.head_task >= 0) {
             const lf_align_task &t = t1[(size_t)p.head_task];
-            const int32_t len = (int32_t)t.q_len, ed = r1[(size_t)p.head_task].edit_distance;
+            const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.head_task);
             if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :1840 */
                 p.head_clip = (int32_t)clips.size();
                 clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
@@ -448,7 +480,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             const int32_t gt = gap_task[gap_base[c] + i];
             if (gt < 0) continue;
             const lf_align_task &t = t1[(size_t)gt];
-            const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len, ed = r1[(size_t)gt].edit_distance;
+            const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len, ed = ed_of((size_t)gt);
             if (abs(ql - tl) >= kSplitLen && (1 - ((float)ed / ql)) < kSplitSim) {                 /* :1952 */
                 gap_split[gap_base[c] + i] = (int32_t)splits.size();
                 SplitInfo si; memset(&si, 0, sizeof si);
@@ -461,7 +493,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         }
         if (p.tail_task >= 0) {
             const lf_align_task &t = t1[(size_t)p.tail_task];
-            const int32_t len = (int32_t)t.q_len, ed = r1[(size_t)p.tail_task].edit_distance;
+            const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.tail_task);
             if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :2175 */
                 p.tail_clip = (int32_t)clips.size();
                 clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
@@ -539,19 +571,107 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     const size_t n3 = t3.size();
     const size_t cap3 = lf_gpu_ops_capacity(t3.data(), n3);
     lf_align_result *r3 = (lf_align_result *)S.r3.reserve((n3 + 1) * sizeof(lf_align_result));
-    uint8_t *ops3 = (uint8_t *)S.ops3.reserve(cap3 + 64);
-    if (!r3 || !ops3) { delete R; return LF_ERR_NOMEM; }
+    uint8_t *ops3 = gpu_emit ? nullptr : (uint8_t *)S.ops3.reserve(cap3 + 64);
+    if (!r3 || (!gpu_emit && !ops3)) { delete R; return LF_ERR_NOMEM; }
+    if (gpu_emit) { /* keep the round-1 results and op stream in HBM: round 3 gets its own pair of buffers */
+        DevState &d = ctx->devs[0];
+        std::swap(d.res, d.res_keep); std::swap(d.ops, d.ops_keep);
+    }
     if (n3) {
         LF_CH(lf_gpu_upload_align_tasks(ctx, t3.data(), n3));
         LF_CH(lf_gpu_run_align(ctx));
-        LF_CH(lf_gpu_download_align(ctx, r3, ops3, cap3));
+        if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r3, ops3, cap3));
+        else { DevState &d = ctx->devs[0]; if (lfb_d2h(r3, d.res.p, n3 * sizeof(lf_align_result), d.stream)) { delete R; return LF_ERR_CUDA; } }
     }
     LF_CH(lf_gpu_sync(ctx));
     R->stats.round3_tasks = n3;
     const double tm3 = now_ms();
 #undef LF_CH
 
-    /* ---------------- emit: the reference's accumulation, chain by chain ---------------- */
+    if (gpu_emit) {
+        /* ---------------- emit on the GPU: k_emit_chains (count) -> scans -> k_emit_chains (write) ---------------- */
+        DevState &d = ctx->devs[0];
+        lfb_stream st = d.stream;
+        std::vector<uint8_t> guards(n_chains);
+        std::vector<int32_t> clipv(4 * n_chains, -1);
+        std::vector<uint32_t> split_begin(n_chains + 1, 0);
+        std::vector<LfSplitDev> sdev;
+        for (size_t c = 0; c < n_chains; c++) {
+            const ChainPlan &p = plan[c];
+            guards[c] = (uint8_t)((p.head_guard ? 1 : 0) | (p.tail_guard ? 2 : 0));
+            if (p.head_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.head_clip]; clipv[4 * c + 0] = ci.t3; clipv[4 * c + 1] = ci.qle; }
+            if (p.tail_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.tail_clip]; clipv[4 * c + 2] = ci.t3; clipv[4 * c + 3] = ci.qle; }
+            split_begin[c] = (uint32_t)sdev.size();
+            if (p.head_clip >= 0 || p.tail_clip >= 0 || true) {
+                for (uint64_t g = gap_base[c]; g < gap_base[c + 1]; g++) {
+                    if (gap_split[g] < 0) continue;
+                    const SplitInfo &si = splits[(size_t)gap_split[g]];
+                    LfSplitDev v; memset(&v, 0, sizeof v);
+                    v.gap_i = (uint32_t)(g - gap_base[c]); v.t_first = si.t_first; v.t_mid_r = si.t_mid_r; v.t_second = si.t_second;
+                    v.qs2 = si.qs2; v.ts2 = si.ts2; v.qe2 = si.qe2; v.te2 = si.te2; v.split = si.split ? 1u : 0u; v.inv = 0;
+                    if (si.split && si.t_mid_f >= 0) {
+                        const lf_align_result &rf = r3[(size_t)si.t_mid_f], &rr = r3[(size_t)si.t_mid_r];
+                        const int32_t ql2 = (int32_t)(si.qe2 - si.qs2);
+                        if ((1 - ((double)rr.edit_distance / ql2)) > (1 - ((double)rf.edit_distance / ql2))
+                            && (1 - ((double)rr.edit_distance / ql2)) > kReverseSim) v.inv = 1;                /* :2040-2041 */
+                    }
+                    sdev.push_back(v);
+                }
+            }
+        }
+        split_begin[n_chains] = (uint32_t)sdev.size();
+#define LF_G(expr) do { if ((expr) != 0) { delete R; return fail(ctx, LF_ERR_CUDA, #expr); } } while (0)
+        LF_G(S.d_task_base.reserve((n_chains + 1) * 8)); LF_G(S.d_guards.reserve(n_chains + 64)); LF_G(S.d_clip.reserve(4 * n_chains * 4 + 64));
+        LF_G(S.d_split_begin.reserve((n_chains + 1) * 4)); LF_G(S.d_splits.reserve((sdev.size() + 1) * sizeof(LfSplitDev)));
+        LF_G(S.d_nrec.reserve(n_chains * 4 + 64)); LF_G(S.d_cigb.reserve(n_chains * 4 + 64)); LF_G(S.d_mdb.reserve(n_chains * 4 + 64));
+        LF_G(S.d_rec_off.reserve((n_chains + 1) * 8)); LF_G(S.d_cig_off.reserve((n_chains + 1) * 8)); LF_G(S.d_md_off.reserve((n_chains + 1) * 8));
+        LF_G(lfb_h2d(S.d_task_base.p, task_base.data(), (n_chains + 1) * 8, st)); LF_G(lfb_h2d(S.d_guards.p, guards.data(), n_chains, st));
+        LF_G(lfb_h2d(S.d_clip.p, clipv.data(), 4 * n_chains * 4, st)); LF_G(lfb_h2d(S.d_split_begin.p, split_begin.data(), (n_chains + 1) * 4, st));
+        if (!sdev.empty()) LF_G(lfb_h2d(S.d_splits.p, sdev.data(), sdev.size() * sizeof(LfSplitDev), st));
+        LfEmitDev E;
+        memset(&E, 0, sizeof E);
+        E.pac = d.pac.as<uint8_t>(); E.chains = S.d_chains.as<lf_chain>(); E.seeds = S.d_seeds.as<lf_seed>(); E.n_chains = (uint32_t)n_chains;
+        E.read_off = d.read_off.as<uint64_t>(); E.task_base = S.d_task_base.as<uint64_t>(); E.guards = S.d_guards.as<uint8_t>();
+        E.clip = S.d_clip.as<int32_t>(); E.split_begin = S.d_split_begin.as<uint32_t>(); E.splits = S.d_splits.as<LfSplitDev>();
+        E.r1 = d.res_keep.as<lf_align_result>(); E.ops1 = d.ops_keep.as<uint32_t>();
+        E.r3 = d.res.as<lf_align_result>(); E.ops3 = d.ops.as<uint32_t>();
+        E.nrec = S.d_nrec.as<uint32_t>(); E.cig_bytes = S.d_cigb.as<uint32_t>(); E.md_bytes = S.d_mdb.as<uint32_t>();
+        const unsigned grid = (unsigned)((n_chains + 127) / 128);
+        { auto kern = k_emit_chains<false>; LFB_LAUNCH(kern, grid, 128, 0, st, E); }
+        LF_G(lfb_scan_excl_total(d.tmp, E.nrec, S.d_rec_off.as<unsigned long long>(), n_chains, st));
+        LF_G(lfb_scan_excl_total(d.tmp, E.cig_bytes, S.d_cig_off.as<unsigned long long>(), n_chains, st));
+        LF_G(lfb_scan_excl_total(d.tmp, E.md_bytes, S.d_md_off.as<unsigned long long>(), n_chains, st));
+        unsigned long long *tot = (unsigned long long *)d.pinned; /* three totals */
+        LF_G(lfb_d2h(&tot[0], S.d_rec_off.as<unsigned long long>() + n_chains, 8, st));
+        LF_G(lfb_d2h(&tot[1], S.d_cig_off.as<unsigned long long>() + n_chains, 8, st));
+        LF_G(lfb_d2h(&tot[2], S.d_md_off.as<unsigned long long>() + n_chains, 8, st));
+        LF_G(lfb_sync(st));
+        const size_t nrec = (size_t)tot[0], ncig = (size_t)tot[1], nmd = (size_t)tot[2];
+        LF_G(S.d_recs.reserve((nrec + 1) * sizeof(lf_sam_record))); LF_G(S.d_text.reserve(ncig + nmd + 64));
+        E.rec_off = S.d_rec_off.as<uint64_t>(); E.cig_off = S.d_cig_off.as<uint64_t>(); E.md_off = S.d_md_off.as<uint64_t>();
+        E.recs = S.d_recs.as<lf_sam_record>(); E.text = S.d_text.as<char>(); E.md_region = ncig;
+        { auto kern = k_emit_chains<true>; LFB_LAUNCH(kern, grid, 128, 0, st, E); }
+        R->pinned = true;
+        R->n_recs = nrec; R->text_bytes = ncig + nmd;
+        R->recs = (lf_sam_record *)g_result_pool_pinned.get((nrec + 1) * sizeof(lf_sam_record), &R->recs_cap);
+        R->text = (char *)g_result_pool_pinned.get(ncig + nmd + 1, &R->text_cap);
+        if (!R->recs || !R->text) { delete R; return LF_ERR_NOMEM; }
+        LF_G(lfb_d2h(R->recs, S.d_recs.p, nrec * sizeof(lf_sam_record), st));
+        LF_G(lfb_d2h(R->text, S.d_text.p, ncig + nmd, st));
+        LF_G(lfb_sync(st));
+        LF_G(lfb_last_error());
+#undef LF_G
+        std::swap(d.res, d.res_keep); std::swap(d.ops, d.ops_keep); /* hand the bigger pair back to the next round 1 */
+        ctx->stats.kernel_launches = lfb_launches;
+        R->stats.records = nrec;
+        const double tm4 = now_ms();
+        R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm4 - tm3); R->stats.ms_merge = 0.f;
+        if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] gpu emit: tasks %.2f r1 %.2f r23 %.2f emit %.2f (recs %zu, text %zu MB)\n", tm1 - tm0, tm2 - tm1, tm3 - tm2, tm4 - tm3, nrec, (ncig + nmd) >> 20);
+        *out = R;
+        return LF_OK;
+    }
+
+    /* ---------------- emit on host threads: the reference's accumulation, chain by chain ---------------- */
     if (n_chains < 256) nthreads = 1; /* same threshold as parallel_for's serial mode: one part, one slice */
     if (!S.parts) S.parts = new std::vector<Emit>();
     std::vector<Emit> &parts = *S.parts;   /* kept between calls: their buffers are already mapped */

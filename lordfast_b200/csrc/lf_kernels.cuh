@@ -1160,3 +1160,292 @@ __global__ void __launch_bounds__(256) k_int32_peak(uint32_t *out, int iters, ui
     for (int k = 0; k < 8; k++) x ^= a[k];
     if (x == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = x; /* keeps the loop alive */
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_emit_chains: the reference's CIGAR / MD accumulation on the GPU       */
+/* ------------------------------------------------------------------------------------------ */
+/* One thread per chain walks the chain exactly as alignChain_edlib does (src/LordFAST.cpp:1820-2249),
+ * reading the 2-bit op streams of the round-1 and round-3 alignments, and produces run-length CIGAR
+ * (edlibCigar_toString :1596-1626) and MD (edlibMD_toString :1717-1763) text.  Two passes with the same
+ * code: WRITE = false counts records and bytes per chain, a scan places them, WRITE = true writes.
+ * CIGARs and MDs go to two regions of one text buffer so both can be built in one sweep. */
+struct LfSplitDev {
+    uint32_t gap_i;                                  /* index of the seed before the gap, inside its chain */
+    int32_t t_first, t_mid_r, t_second;              /* round-3 task indices or -1 */
+    uint32_t qs2, ts2, qe2, te2;
+    uint32_t split, inv;                             /* extensions did not cross / inversion accepted (host decides, double math) */
+};
+struct LfEmitDev {
+    const uint8_t *pac;
+    const lf_chain *chains; const lf_seed *seeds; uint32_t n_chains;
+    const uint64_t *read_off;
+    const uint64_t *task_base;     /* round-1 task index of the chain's first task */
+    const uint8_t *guards;         /* bit 0: head aligned, bit 1: tail aligned (else soft clip) */
+    const int32_t *clip;           /* 4 per chain: head t3, head qle, tail t3, tail qle (t3 < 0: keep the round-1 alignment) */
+    const uint32_t *split_begin;   /* n_chains + 1 */
+    const LfSplitDev *splits;
+    const lf_align_result *r1; const uint32_t *ops1;
+    const lf_align_result *r3; const uint32_t *ops3;
+    /* pass 1 out */
+    uint32_t *nrec, *cig_bytes, *md_bytes;
+    /* pass 2 in/out */
+    const uint64_t *rec_off, *cig_off, *md_off;
+    lf_sam_record *recs; char *text; uint64_t md_region;
+};
+
+template <bool WRITE>
+struct LfRecDev {
+    char *cp, *mp;             /* write cursors (WRITE) */
+    uint64_t cn, mn;           /* bytes so far in this record */
+    char cch; int cnum; int cnops; int mnum; char mlast;
+    __device__ __forceinline__ void reset() { cn = 0; mn = 0; cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '='; }
+    __device__ __forceinline__ void putc_c(char c) { if (WRITE) *cp++ = c; cn++; }
+    __device__ __forceinline__ void putc_m(char c) { if (WRITE) *mp++ = c; mn++; }
+    __device__ __forceinline__ void num_c(uint32_t u)
+    {
+        char t[12]; int n = 0;
+        do { t[n++] = (char)('0' + u % 10u); u /= 10u; } while (u);
+        while (n) putc_c(t[--n]);
+    }
+    __device__ __forceinline__ void num_m(uint32_t u)
+    {
+        char t[12]; int n = 0;
+        do { t[n++] = (char)('0' + u % 10u); u /= 10u; } while (u);
+        while (n) putc_m(t[--n]);
+    }
+    __device__ __forceinline__ void cig_run(char c, int n)
+    {
+        if (n <= 0) return;
+        if (c == cch) { cnum += n; return; }
+        if (cch) { num_c((uint32_t)cnum); putc_c((cnops == 0 && cch == 'I') ? 'S' : cch); cnops++; }
+        cch = c; cnum = n;
+    }
+    __device__ __forceinline__ void md_match(int n) { if (n > 0) { mnum += n; mlast = '='; } }
+    __device__ __forceinline__ void md_ins(int n) { if (n > 0) mlast = 'I'; }
+    __device__ __forceinline__ void md_mismatch(char b) { num_m((uint32_t)mnum); mnum = 0; putc_m(b); mlast = 'X'; }
+    __device__ __forceinline__ void md_del(char b) { if (mlast != 'D') { num_m((uint32_t)mnum); mnum = 0; putc_m('^'); } putc_m(b); mlast = 'D'; }
+    __device__ __forceinline__ void run(char c, int n) { cig_run(c, n); if (c == 'I') md_ins(n); else md_match(n); }
+    __device__ __forceinline__ void finish()
+    {
+        if (cnum) { num_c((uint32_t)cnum); putc_c(cch == 'I' ? 'S' : cch); }
+        num_m((uint32_t)mnum);
+        putc_c('\0'); putc_m('\0');
+    }
+};
+
+__device__ __forceinline__ uint32_t lf_op_at(const uint32_t *ops, uint64_t p) { return (ops[p >> 4] >> (((uint32_t)p & 15u) << 1)) & 3u; }
+__device__ __forceinline__ char lf_pac_char(const uint8_t *pac, uint32_t l) { const uint32_t c = lf_tsym(pac, (int64_t)l); return c == 0 ? 'A' : c == 1 ? 'C' : c == 2 ? 'G' : 'T'; }
+
+/* ops of one alignment appended to the record; reversed = the task ran right-to-left; t0 = forward
+ * reference position of the first target base covered.  Runs of matches are skipped a word at a time. */
+template <bool WRITE>
+__device__ __forceinline__ void lf_emit_segment(LfRecDev<WRITE> &B, const uint32_t *ops, const lf_align_result &r, bool reversed, const uint8_t *pac, uint32_t t0)
+{
+    uint32_t tp = t0, k = 0;
+    const uint32_t n = r.ops_len;
+    while (k < n) {
+        int run = 0;
+        for (;;) {
+            if (k >= n) break;
+            uint32_t z, avail;
+            if (!reversed) {
+                const uint64_t p = r.ops_off + k;
+                const uint32_t sh = ((uint32_t)p & 15u) << 1;
+                const uint32_t w = ops[p >> 4] >> sh;
+                avail = 16u - ((uint32_t)p & 15u);
+                if (avail > n - k) avail = n - k;
+                z = w ? (uint32_t)(__ffs((int)w) - 1) >> 1 : 16u;
+            } else {
+                const uint64_t p = r.ops_off + (n - 1 - k);
+                const uint32_t top = (uint32_t)p & 15u;
+                const uint32_t w = ops[p >> 4] << (30u - 2u * top);
+                avail = top + 1u;
+                if (avail > n - k) avail = n - k;
+                z = w ? (uint32_t)__clz((int)w) >> 1 : 16u;
+            }
+            if (z >= avail) { run += (int)avail; k += avail; continue; }
+            run += (int)z; k += z;
+            break;
+        }
+        if (run) { B.cig_run('M', run); B.md_match(run); tp += (uint32_t)run; }
+        if (k >= n) break;
+        const uint64_t p = reversed ? r.ops_off + (n - 1 - k) : r.ops_off + k;
+        const uint32_t op = lf_op_at(ops, p);
+        k++;
+        if (op == 1u) { B.cig_run('I', 1); B.md_ins(1); }
+        else if (op == 2u) { B.cig_run('D', 1); B.md_del(lf_pac_char(pac, tp)); tp++; }
+        else { B.cig_run('M', 1); B.md_mismatch(lf_pac_char(pac, tp)); tp++; }
+    }
+}
+
+/* The accepted-inversion record: the reference appends the trailing clip to the END of the CIGAR deque but
+ * to the BEGINNING of the MD deque (:2056-2057), so MD and CIGAR positions pair up out of step.  Emulated
+ * index by index: cigar = I^a ops I^b, md = '-'^b '-'^a mdops. */
+template <bool WRITE>
+__device__ __forceinline__ void lf_emit_inversion(LfRecDev<WRITE> &B, const uint32_t *ops, const lf_align_result &r, const uint8_t *pac, uint32_t t0, uint32_t a, uint32_t b)
+{
+    const uint32_t n = r.ops_len, total = a + n + b;
+    /* CIGAR: plain run-length of the cigar chars */
+    B.cig_run('I', (int)a);
+    for (uint32_t k = 0; k < n; k++) { const uint32_t op = lf_op_at(ops, r.ops_off + k); B.cig_run(op == 1u ? 'I' : op == 2u ? 'D' : 'M', 1); }
+    B.cig_run('I', (int)b);
+    /* MD from the (md[i], cigar[i]) pairs */
+    uint32_t tp = t0;
+    for (uint32_t i = a + b; i < total; i++) {
+        const uint32_t opm = lf_op_at(ops, r.ops_off + (i - a - b));      /* op whose MD char sits at position i */
+        char m;
+        if (opm == 0u) { m = '='; tp++; } else if (opm == 1u) m = '-'; else { m = lf_pac_char(pac, tp); tp++; }
+        char c;                                                          /* cigar char at position i */
+        if (i < a) c = 'I';
+        else if (i < a + n) { const uint32_t opc = lf_op_at(ops, r.ops_off + (i - a)); c = opc == 1u ? 'I' : opc == 2u ? 'D' : 'M'; }
+        else c = 'I';
+        if (m == '=') { B.mnum++; B.mlast = '='; }
+        else if (m == '-') { B.mlast = 'I'; }
+        else if (c == 'M') { B.md_mismatch(m); }
+        else if (c == 'D') { B.md_del(m); }
+    }
+    if (a + b > 0) { /* the leading '-' entries only set last = 'I' when nothing followed them */ if (total == a + b) B.mlast = 'I'; }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) k_emit_chains(LfEmitDev d)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.n_chains) return;
+    const lf_chain ch = d.chains[c];
+    const lf_seed *s = d.seeds + ch.seed_off;
+    const uint32_t n = ch.n_seeds;
+    const uint32_t readLen = (uint32_t)(d.read_off[ch.read_id + 1] - d.read_off[ch.read_id]);
+    const uint32_t flag_norm = ch.is_rev ? 16u : 0u, flag_opp = ch.is_rev ? 0u : 16u;
+    const uint8_t guards = d.guards[c];
+    const int32_t *clip = d.clip + 4 * (size_t)c;
+    uint32_t sp = d.split_begin[c];
+    const uint32_t sp_end = d.split_begin[c + 1];
+    uint64_t tk = d.task_base[c];   /* next round-1 task of this chain */
+
+    LfRecDev<WRITE> B;
+    B.reset();
+    uint64_t rec_i = 0, cig_base = 0, md_base = 0;   /* WRITE: where this chain's output starts */
+    uint32_t nrec = 0;
+    uint64_t cig_tot = 0, md_tot = 0;
+    if (WRITE) {
+        rec_i = d.rec_off[c]; cig_base = d.cig_off[c]; md_base = d.md_region + d.md_off[c];
+        B.cp = d.text + cig_base; B.mp = d.text + md_base;
+    }
+    uint32_t flag = flag_norm, pos = s[0].tPos, qStart = s[0].qPos, posEnd = 0, qEnd = 0;
+    int32_t editScore = 0;
+#define LF_PUSH(FLAG, POS, POSEND, QS, QE, NM) do { \
+        B.finish(); \
+        if (WRITE) { lf_sam_record rr_; rr_.chain_id = c; rr_.flag = (FLAG); rr_.pos = (POS); rr_.posEnd = (POSEND); rr_.qStart = (QS); rr_.qEnd = (QE); rr_.nmCount = (NM); \
+            rr_.cigar_off = cig_base + cig_tot; rr_.cigar_len = (uint32_t)(B.cn - 1); rr_.md_off = md_base + md_tot; rr_.md_len = (uint32_t)(B.mn - 1); d.recs[rec_i + nrec] = rr_; } \
+        cig_tot += B.cn; md_tot += B.mn; nrec++; } while (0)
+    /* head (:1820-1899) */
+    const int32_t a = (int32_t)s[0].qPos;
+    if (a > 0) {
+        if (guards & 1) {
+            const uint64_t head_task = tk++;
+            if (clip[0] >= 0) {
+                const lf_align_result r = d.r3[clip[0]];
+                B.run('I', a - clip[1]);
+                lf_emit_segment<WRITE>(B, d.ops3, r, true, d.pac, s[0].tPos - (uint32_t)(r.end_location + 1));
+                editScore -= r.edit_distance;
+                pos = s[0].tPos - (uint32_t)r.end_location - 1;
+                qStart = s[0].qPos - (uint32_t)clip[1];
+            } else {
+                const lf_align_result r = d.r1[head_task];
+                lf_emit_segment<WRITE>(B, d.ops1, r, true, d.pac, s[0].tPos - (uint32_t)(r.end_location + 1));
+                editScore -= r.edit_distance;
+                pos = s[0].tPos - (uint32_t)r.end_location - 1;
+                qStart = 0;
+            }
+        } else B.run('I', a);
+    }
+    /* anchors and gaps (:1901-2137) */
+    int numAnchorsSoFar = 1;
+    uint32_t i = 0;
+    for (; i + 1 < n; i++) {
+        const lf_seed si0 = s[i], si1 = s[i + 1];
+        B.run('M', (int)si0.len);
+        const uint32_t qs = si0.qPos + si0.len, ts = si0.tPos + si0.len;
+        const uint32_t qe = si1.qPos, te = si1.tPos;
+        const int32_t ql = (int32_t)(qe - qs), tl = (int32_t)(te - ts);
+        if (ql > 0 && tl > 0) {
+            const uint64_t gt = tk++;
+            const LfSplitDev *sv = nullptr;
+            if (sp < sp_end && d.splits[sp].gap_i == i) sv = &d.splits[sp++];
+            if (sv && sv->split) {
+                if (sv->t_first >= 0) {
+                    const lf_align_result r = d.r3[sv->t_first];
+                    lf_emit_segment<WRITE>(B, d.ops3, r, false, d.pac, ts);
+                    editScore -= r.edit_distance;
+                }
+                B.run('I', (int)(readLen - sv->qs2));
+                posEnd = sv->ts2; qEnd = sv->qs2;
+                if (numAnchorsSoFar > 1) { LF_PUSH(flag, pos, posEnd, qStart, qEnd, editScore); if (WRITE) { B.cp = d.text + cig_base + cig_tot; B.mp = d.text + md_base + md_tot; } }
+                else if (WRITE) { B.cp = d.text + cig_base + cig_tot; B.mp = d.text + md_base + md_tot; } /* dropped record: rewind */
+                B.reset(); editScore = 0;
+                if (sv->inv) {
+                    const lf_align_result rr = d.r3[sv->t_mid_r];
+                    lf_emit_inversion<WRITE>(B, d.ops3, rr, d.pac, sv->ts2, sv->qs2, readLen - sv->qe2);
+                    LF_PUSH(flag_opp, sv->ts2, sv->te2, sv->qs2, sv->qe2, -rr.edit_distance);
+                    if (WRITE) { B.cp = d.text + cig_base + cig_tot; B.mp = d.text + md_base + md_tot; }
+                    B.reset();
+                }
+                B.run('I', (int)sv->qe2);
+                if (sv->t_second >= 0) {
+                    const lf_align_result r = d.r3[sv->t_second];
+                    lf_emit_segment<WRITE>(B, d.ops3, r, true, d.pac, sv->te2);
+                    editScore -= r.edit_distance;
+                }
+                flag = flag_norm; pos = sv->te2; qStart = sv->qe2;
+                numAnchorsSoFar = 0;
+            } else {
+                const lf_align_result r = d.r1[gt];
+                editScore -= r.edit_distance;
+                lf_emit_segment<WRITE>(B, d.ops1, r, false, d.pac, ts);
+            }
+        } else if (ql > 0) { B.run('I', ql); editScore -= ql; }
+        else {
+            B.cig_run('D', tl);
+            for (int32_t k = 0; k < tl; k++) B.md_del(lf_pac_char(d.pac, ts + (uint32_t)k));
+            editScore -= tl;
+        }
+        numAnchorsSoFar++;
+    }
+    const lf_seed sl = s[i];
+    B.run('M', (int)sl.len);
+    posEnd = sl.tPos + sl.len - 1;
+    qEnd = sl.qPos + sl.len - 1;                 /* inclusive, :2155 */
+    /* tail (:2157-2230) */
+    const uint32_t qs = sl.qPos + sl.len;
+    const int32_t b = (int32_t)readLen - (int32_t)qs;
+    if (b > 0) {
+        if (guards & 2) {
+            const uint32_t ts = sl.tPos + sl.len;
+            const uint64_t tail_task = tk++;
+            if (clip[2] >= 0) {
+                const lf_align_result r = d.r3[clip[2]];
+                lf_emit_segment<WRITE>(B, d.ops3, r, false, d.pac, ts);
+                editScore -= r.edit_distance;
+                posEnd = ts + (uint32_t)r.end_location;
+                qEnd = qs + (uint32_t)clip[3];
+                B.run('I', b - clip[3]);
+            } else {
+                const lf_align_result r = d.r1[tail_task];
+                editScore -= r.edit_distance;
+                lf_emit_segment<WRITE>(B, d.ops1, r, false, d.pac, ts);
+                posEnd = ts + (uint32_t)r.end_location;
+                qEnd = readLen;
+            }
+        } else B.run('I', b);
+    }
+    LF_PUSH(flag, pos, posEnd, qStart, qEnd, editScore);
+#undef LF_PUSH
+    if (!WRITE) { d.nrec[c] = nrec; d.cig_bytes[c] = (uint32_t)cig_tot; d.md_bytes[c] = (uint32_t)md_tot; }
+}
+
+__global__ void k_gather_ed(const lf_align_result *res, int32_t *ed, uint32_t n)
+{ /* the host only needs the distances to evaluate the clip / split triggers */
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ed[i] = res[i].edit_distance;
+}

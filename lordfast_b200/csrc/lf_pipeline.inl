@@ -31,6 +31,7 @@ struct DevState {
     lfb_event cls_ev[LF_NCLS][2] = {};   /* start / end of every class kernel (timeline hook) */
     bool cls_ran[LF_NCLS] = {};
     LfbBuf pac, bases, read_off, plo, phi, pnn;
+    LfbBuf res_keep, ops_keep;   /* lf_chain.inl parks the round-1 results / op stream here while round 3 runs */
     LfbBuf tasks, res, ops, keys, keys2, idx, idx2, slot_words, scr_bytes, slot_end, scr_off, scratch, large_scr, counters, queue;
     LfbBuf etasks, eres, escr_items, escr_off, escr;
     LfbTemp tmp;
@@ -266,7 +267,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
     if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
     for (DevState &d : ctx->devs) {
         set_dev(d);
-        LfbBuf *bufs[] = { &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
+        LfbBuf *bufs[] = { &d.res_keep, &d.ops_keep, &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
                            &d.slot_words, &d.scr_bytes, &d.slot_end, &d.scr_off, &d.scratch, &d.large_scr, &d.counters, &d.queue,
                            &d.etasks, &d.eres, &d.escr_items, &d.escr_off, &d.escr };
         for (LfbBuf *b : bufs) b->release();

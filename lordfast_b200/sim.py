@@ -113,8 +113,8 @@ def simulate_read(ref: np.ndarray, read_len: int, e: float, rng, kind: str = "pl
     sv = 0
     if kind == "deletion":
         sv = 600
-    elif kind == "inversion":
-        sv = 1500
+    elif kind in ("inversion", "inversion_del"):
+        sv = 1500  # room for either variant
     margin = 64
     start = int(rng.integers(lo + margin, max(lo + margin + 1, hi - span - sv - margin)))
     if kind in ("plain", "junk_head", "junk_tail"):
@@ -137,6 +137,12 @@ def simulate_read(ref: np.ndarray, read_len: int, e: float, rng, kind: str = "pl
     elif kind == "insertion":
         b0 = start + half
         mid = ACGT[rng.integers(0, 4, size=600, dtype=np.uint8)]
+    elif kind == "inversion_del":
+        # 800 bp inverted (nearly error-free) followed by a 240 bp deletion: the gap is dissimilar enough for lordFAST's
+        # split test (|q-t| >= 80, similarity < 0.40) and its reverse complement aligns above 0.60, so the
+        # accepted-inversion branch (src/LordFAST.cpp:2040-2074) is taken
+        b0 = start + half + 800 + 240
+        mid, _, _ = _channel(revcomp(ref[start + half:start + half + 800]), 0.02, rng)
     else:  # inversion: 1.5 kbp of the reference comes through reverse-complemented
         b0 = start + half + 1500
         mid, _, _ = _channel(revcomp(ref[start + half:start + half + 1500]), e, rng)
@@ -178,7 +184,7 @@ class Workload:
 
 
 def make_workload(ref_len: int, n_reads: int, read_len: int, err_lo: float, err_hi: float, seed: int = 1,
-                  sv_frac: float = 0.10, ref: np.ndarray | None = None) -> Workload:
+                  sv_frac: float = 0.10, ref: np.ndarray | None = None, sv_kinds=SV_KINDS) -> Workload:
     rng = np.random.default_rng(seed + 7919)
     if ref is None:
         ref = make_reference(ref_len, seed)
@@ -187,7 +193,7 @@ def make_workload(ref_len: int, n_reads: int, read_len: int, err_lo: float, err_
         e = float(rng.uniform(err_lo, err_hi))
         kind = "plain"
         if rng.random() < sv_frac:
-            kind = SV_KINDS[int(rng.integers(0, len(SV_KINDS)))]
+            kind = sv_kinds[int(rng.integers(0, len(sv_kinds)))]
         for _ in range(20):  # a chain needs at least two anchors
             o, s = simulate_read(ref, read_len, e, rng, kind)
             if len(s) >= 2:

@@ -30,7 +30,7 @@ def _golden(lib_path):
 
 
 def _simulated(lib_path, n_reads, read_len, ref_len):
-    w = sim.make_workload(ref_len, n_reads, read_len, 0.12, 0.15, seed=21, sv_frac=0.5)
+    w = sim.make_workload(ref_len, n_reads, read_len, 0.12, 0.15, seed=21, sv_frac=0.6, sv_kinds=sim.SV_KINDS + ("inversion_del", "inversion_del"))
     g = api.LfGpu(w.pac, len(w.ref), lib_path=lib_path)
     seeds, chains = api.workload_chains(w)
     recs, text, st = g.align_chains(w.reads, w.read_off.astype(np.uint64), w.contig_off, w.contig_len, seeds, chains)
@@ -42,6 +42,8 @@ def _simulated(lib_path, n_reads, read_len, ref_len):
         for s in a:
             d = dict(chain=i); d.update(s); exp.append(d)
     assert got == exp
+    # the accepted-inversion branch (MD / CIGAR out of step, src/LordFAST.cpp:2056-2057) is exercised
+    assert any((r["flag"] & 16) != (16 if w.is_rev[r["chain"]] else 0) for r in exp)
     g.close()
     return st
 
@@ -51,7 +53,21 @@ def test_emu_chain_operator_golden():
 
 
 def test_emu_chain_operator_simulated():
-    _simulated(build_emu(), 10, 2500, 120_000)
+    _simulated(build_emu(), 14, 3000, 120_000)
+
+
+def test_emu_chain_operator_host_emit(monkeypatch):
+    """The alternative emit path (host threads from the 2-bit op stream, used by multi-device contexts)."""
+    monkeypatch.setenv("LF_CHAIN_HOST_EMIT", "1")
+    _golden(build_emu())
+    _simulated(build_emu(), 14, 3000, 120_000)
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_host_emit(monkeypatch):
+    monkeypatch.setenv("LF_CHAIN_HOST_EMIT", "1")
+    _golden(None)
+    _simulated(None, 300, 6_000, 1_000_000)
 
 
 @pytest.mark.gpu

@@ -95,13 +95,15 @@ def test_oracle_vs_reference_random():
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 def test_oracle_chain_vs_reference():
-    w = sim.make_workload(400_000, 60, 5000, 0.12, 0.15, seed=3, sv_frac=0.4)
+    w = sim.make_workload(400_000, 60, 5000, 0.12, 0.15, seed=3, sv_frac=0.5, sv_kinds=sim.SV_KINDS + ("inversion_del",))
     idx = O.RefIndex(w.ref.tobytes())
     nex = 0
+    ninv = 0
     for i in range(w.n_reads):
         seeds = [tuple(int(x) for x in s) for s in w.chain(i)]
         q = w.oriented(i).tobytes()
         a, st = O.oracle_align_chain(idx, seeds, q, int(w.is_rev[i]))
         assert a == O.ref_align_chain(idx, seeds, q, int(w.is_rev[i]))
         nex += st.n_extend
-    assert nex > 0
+        ninv += any((r["flag"] & 16) != (16 if w.is_rev[i] else 0) for r in a)
+    assert nex > 0 and ninv > 0  # clip / split rounds and the accepted-inversion branch are covered
