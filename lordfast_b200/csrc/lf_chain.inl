@@ -291,7 +291,7 @@ struct PinBuf {
     void release() { lfb_host_free(p); p = nullptr; cap = 0; }
 };
 struct ChainScratch {
-    PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2, ed1;
+    PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2, ed1, seeds_stage;
     std::vector<Emit> *parts = nullptr;
     /* device side of the GPU emit */
     LfbBuf d_chains, d_seeds, d_task_base, d_guards, d_clip, d_split_begin, d_splits, d_nrec, d_cigb, d_mdb, d_rec_off, d_cig_off, d_md_off, d_recs, d_text, d_ed;
@@ -316,7 +316,7 @@ double now_ms()
 void chain_scratch_free_fn(void *p)
 {
     ChainScratch *s = (ChainScratch *)p;
-    PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2, &s->ed1 };
+    PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2, &s->ed1, &s->seeds_stage };
     for (PinBuf *b : all) b->release();
     LfbBuf *dall[] = { &s->d_chains, &s->d_seeds, &s->d_task_base, &s->d_guards, &s->d_clip, &s->d_split_begin, &s->d_splits, &s->d_nrec, &s->d_cigb, &s->d_mdb,
                        &s->d_rec_off, &s->d_cig_off, &s->d_md_off, &s->d_recs, &s->d_text, &s->d_ed };
@@ -358,7 +358,14 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         size_t ns = 0;
         for (size_t c = 0; c < n_chains; c++) { const size_t e = (size_t)chains[c].seed_off + chains[c].n_seeds; if (e > ns) ns = e; }
         if (S.d_chains.reserve(n_chains * sizeof(lf_chain) + 64) || S.d_seeds.reserve(ns * sizeof(lf_seed) + 64)) { delete R; return LF_ERR_NOMEM; }
-        if (lfb_h2d(S.d_chains.p, chains, n_chains * sizeof(lf_chain), d.stream) || lfb_h2d(S.d_seeds.p, seeds, ns * sizeof(lf_seed), d.stream)) { delete R; return LF_ERR_CUDA; }
+        /* the caller's seed array is ordinary (pageable) memory: stage it through pinned memory with all host
+         * threads so that the copy to the device is asynchronous and overlaps the task generation */
+        char *stage = (char *)S.seeds_stage.reserve(ns * sizeof(lf_seed) + n_chains * sizeof(lf_chain) + 64);
+        if (!stage) { delete R; return LF_ERR_NOMEM; }
+        const size_t sb = ns * sizeof(lf_seed);
+        parallel_for(sb, nthreads, [&](unsigned, size_t lo, size_t hi) { memcpy(stage + lo, (const char *)seeds + lo, hi - lo); }, 1 << 20);
+        memcpy(stage + sb, chains, n_chains * sizeof(lf_chain));
+        if (lfb_h2d(S.d_seeds.p, stage, sb, d.stream) || lfb_h2d(S.d_chains.p, stage + sb, n_chains * sizeof(lf_chain), d.stream)) { delete R; return LF_ERR_CUDA; }
     }
 
     /* ---------------- round 1: tasks known from the chains alone ---------------- */
@@ -462,42 +469,65 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<ClipInfo> clips;
     std::vector<SplitInfo> splits;
     std::vector<int32_t> gap_split(total_seeds, -1);
-    for (size_t c = 0; c < n_chains; c++) {
-        const lf_chain &ch = chains[c];
-        const uint32_t n = ch.n_seeds;
-        const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
-        ChainPlan &p = plan[c];
-        if (p.head_task >= 0) {
-            const lf_align_task &t = t1[(size_t)p.head_task];
-            const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.head_task);
-            if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :1840 */
-                p.head_clip = (int32_t)clips.size();
-                clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
-                e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, true));
+    {   /* every thread scans a contiguous range of chains into its own lists; indices are rebased when the
+         * lists are concatenated in thread (= chain) order, so the result equals the serial scan */
+        struct Local { std::vector<lf_extend_task> e2; std::vector<ClipInfo> clips; std::vector<SplitInfo> splits; size_t c_lo = 0, c_hi = 0; };
+        const unsigned nt = n_chains < 256 ? 1u : nthreads;
+        std::vector<Local> loc(nt);
+        parallel_for(n_chains, nt, [&](unsigned tid, size_t lo, size_t hi) {
+            Local &Lc = loc[tid];
+            Lc.c_lo = lo; Lc.c_hi = hi;
+            for (size_t c = lo; c < hi; c++) {
+                const lf_chain &ch = chains[c];
+                const uint32_t n = ch.n_seeds;
+                const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
+                ChainPlan &p = plan[c];
+                if (p.head_task >= 0) {
+                    const lf_align_task &t = t1[(size_t)p.head_task];
+                    const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.head_task);
+                    if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :1840 */
+                        p.head_clip = (int32_t)Lc.clips.size();
+                        Lc.clips.push_back(ClipInfo{ (int32_t)Lc.e2.size(), -1, 0, 0 });
+                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, true));
+                    }
+                }
+                for (uint32_t i = 0; i + 1 < n; i++) {
+                    const int32_t gt = gap_task[gap_base[c] + i];
+                    if (gt < 0) continue;
+                    const lf_align_task &t = t1[(size_t)gt];
+                    const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len, ed = ed_of((size_t)gt);
+                    if (abs(ql - tl) >= kSplitLen && (1 - ((float)ed / ql)) < kSplitSim) {                 /* :1952 */
+                        gap_split[gap_base[c] + i] = (int32_t)Lc.splits.size();
+                        SplitInfo si; memset(&si, 0, sizeof si);
+                        si.seed_idx = (uint32_t)(ch.seed_off + i); si.ext_f = (int32_t)Lc.e2.size(); si.ext_r = si.ext_f + 1;
+                        si.t_first = si.t_mid_f = si.t_mid_r = si.t_second = -1; si.split = false;
+                        Lc.splits.push_back(si);
+                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, false));
+                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, false));
+                    }
+                }
+                if (p.tail_task >= 0) {
+                    const lf_align_task &t = t1[(size_t)p.tail_task];
+                    const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.tail_task);
+                    if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :2175 */
+                        p.tail_clip = (int32_t)Lc.clips.size();
+                        Lc.clips.push_back(ClipInfo{ (int32_t)Lc.e2.size(), -1, 0, 0 });
+                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true));
+                    }
+                }
             }
-        }
-        for (uint32_t i = 0; i + 1 < n; i++) {
-            const int32_t gt = gap_task[gap_base[c] + i];
-            if (gt < 0) continue;
-            const lf_align_task &t = t1[(size_t)gt];
-            const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len, ed = ed_of((size_t)gt);
-            if (abs(ql - tl) >= kSplitLen && (1 - ((float)ed / ql)) < kSplitSim) {                 /* :1952 */
-                gap_split[gap_base[c] + i] = (int32_t)splits.size();
-                SplitInfo si; memset(&si, 0, sizeof si);
-                si.seed_idx = (uint32_t)(ch.seed_off + i); si.ext_f = (int32_t)e2.size(); si.ext_r = si.ext_f + 1;
-                si.t_first = si.t_mid_f = si.t_mid_r = si.t_second = -1; si.split = false;
-                splits.push_back(si);
-                e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, false));
-                e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, false));
-            }
-        }
-        if (p.tail_task >= 0) {
-            const lf_align_task &t = t1[(size_t)p.tail_task];
-            const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.tail_task);
-            if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :2175 */
-                p.tail_clip = (int32_t)clips.size();
-                clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
-                e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true));
+        });
+        for (Local &Lc : loc) {
+            const int32_t be = (int32_t)e2.size(), bc = (int32_t)clips.size(), bs = (int32_t)splits.size();
+            for (ClipInfo ci : Lc.clips) { ci.ext += be; clips.push_back(ci); }
+            for (SplitInfo si : Lc.splits) { si.ext_f += be; si.ext_r += be; splits.push_back(si); }
+            e2.insert(e2.end(), Lc.e2.begin(), Lc.e2.end());
+            if (bc || bs) {
+                for (size_t c = Lc.c_lo; c < Lc.c_hi; c++) {
+                    if (plan[c].head_clip >= 0) plan[c].head_clip += bc;
+                    if (plan[c].tail_clip >= 0) plan[c].tail_clip += bc;
+                    if (bs) for (uint64_t g = gap_base[c]; g < gap_base[c + 1]; g++) if (gap_split[g] >= 0) gap_split[g] += bs;
+                }
             }
         }
     }

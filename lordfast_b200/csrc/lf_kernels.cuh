@@ -1169,6 +1169,15 @@ __global__ void __launch_bounds__(256) k_int32_peak(uint32_t *out, int iters, ui
  * (edlibCigar_toString :1596-1626) and MD (edlibMD_toString :1717-1763) text.  Two passes with the same
  * code: WRITE = false counts records and bytes per chain, a scan places them, WRITE = true writes.
  * CIGARs and MDs go to two regions of one text buffer so both can be built in one sweep. */
+__device__ __forceinline__ void lf_prefetch(const void *p)
+{ /* pull a line towards L1 without blocking: the emit walk is one dependent miss after another otherwise */
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+
 struct LfSplitDev {
     uint32_t gap_i;                                  /* index of the seed before the gap, inside its chain */
     int32_t t_first, t_mid_r, t_second;              /* round-3 task indices or -1 */
@@ -1363,6 +1372,10 @@ __global__ void __launch_bounds__(128) k_emit_chains(LfEmitDev d)
     /* anchors and gaps (:1901-2137) */
     int numAnchorsSoFar = 1;
     uint32_t i = 0;
+    const uint64_t tk_end = d.task_base[c + 1];
+    lf_align_result rnext;           /* result of the chain's next round-1 task, loaded one gap ahead */
+    rnext.ops_off = 0; rnext.ops_len = 0; rnext.edit_distance = 0; rnext.end_location = 0; rnext.status = 0;
+    if (tk < tk_end) rnext = d.r1[tk];
     for (; i + 1 < n; i++) {
         const lf_seed si0 = s[i], si1 = s[i + 1];
         B.run('M', (int)si0.len);
@@ -1371,6 +1384,13 @@ __global__ void __launch_bounds__(128) k_emit_chains(LfEmitDev d)
         const int32_t ql = (int32_t)(qe - qs), tl = (int32_t)(te - ts);
         if (ql > 0 && tl > 0) {
             const uint64_t gt = tk++;
+            const lf_align_result rcur = rnext;
+            if (tk < tk_end) {   /* next task: fetch its result now, and warm the lines its ops and reference bytes live in */
+                rnext = d.r1[tk];
+                lf_prefetch(d.ops1 + (rnext.ops_off >> 4));
+                lf_prefetch(d.pac + ((si1.tPos + si1.len) >> 2));
+                lf_prefetch(s + i + 3);
+            }
             const LfSplitDev *sv = nullptr;
             if (sp < sp_end && d.splits[sp].gap_i == i) sv = &d.splits[sp++];
             if (sv && sv->split) {
@@ -1400,9 +1420,9 @@ __global__ void __launch_bounds__(128) k_emit_chains(LfEmitDev d)
                 flag = flag_norm; pos = sv->te2; qStart = sv->qe2;
                 numAnchorsSoFar = 0;
             } else {
-                const lf_align_result r = d.r1[gt];
-                editScore -= r.edit_distance;
-                lf_emit_segment<WRITE>(B, d.ops1, r, false, d.pac, ts);
+                (void)gt;
+                editScore -= rcur.edit_distance;
+                lf_emit_segment<WRITE>(B, d.ops1, rcur, false, d.pac, ts);
             }
         } else if (ql > 0) { B.run('I', ql); editScore -= ql; }
         else {
