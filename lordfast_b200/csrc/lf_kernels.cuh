@@ -83,6 +83,7 @@ struct LfDev {
     const uint64_t *slot_end;              /* inclusive scan of per-task slot words */
     const uint64_t *scr_off;               /* exclusive scan of per-task scratch bytes (small classes) */
     uint8_t *scratch;
+    uint8_t *planes;                       /* op planes of k_myers_band, one region per warp group */
 };
 
 struct LfCounters { /* written by k_align_prep, read back by the host (one small D2H per batch) */
@@ -501,7 +502,7 @@ __device__ __forceinline__ void lf_k1_recompute(uint32_t (&Pv)[NW], uint32_t (&M
 }
 
 template <int NW, bool SHW>
-__global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count)
+__global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, uint32_t retry_only)
 {
     constexpr int WIN = NW < 2 ? 1 : 2;
     constexpr int C = LF_K1_C;
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
     const uint32_t gi = blockIdx.x * LF_K1_BLOCK + tid;
     if (gi >= count) return;
     const uint32_t ti = order[first + gi];
+    if (retry_only && d.res[ti].status != 1 /* LF_RETRY */) return; /* only what the banded kernel could not certify */
     const lf_align_task task = d.tasks[ti];
     const int q = (int)task.q_len, t = (int)task.t_len;
     LfQView qv; LfTView tv;
@@ -1468,4 +1470,236 @@ __global__ void k_gather_ed(const lf_align_result *res, int32_t *ed, uint32_t n)
 { /* the host only needs the distances to evaluate the clip / split triggers */
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) ed[i] = res[i].edit_distance;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_myers_band: register-resident Myers with a sliding word band and op planes kept in HBM      */
+/* ------------------------------------------------------------------------------------------ */
+/* Second-generation small-task kernel.  Two changes against k_myers_small:
+ *  (1) The traceback no longer recomputes: the forward pass writes the two op planes of every column to
+ *      HBM in a warp-interleaved layout ([column][window word][lane], 256 contiguous bytes per warp store),
+ *      and the walk loads its 2-word window for 8 columns at a time.  (Recompute was 42 % of the executed
+ *      instructions; the stores are asynchronous and coalesced.)
+ *  (2) BANDED: only NB consecutive words (a band of 32*NB rows that slides down the diagonal one word at a
+ *      time) are computed and stored, as edlib does with its block band.  Cells outside the band are treated
+ *      as "+1 per step" (upper bounds).  With x = 16*(NB-1)-4 rows guaranteed between the straight line
+ *      (0,0)-(q,t) and the band edges, a path leaving the band costs >= 2*(x+1) - |q-t| edits, so a computed
+ *      distance d <= 32*(NB-1) - 7 - |q-t| proves that no optimal path leaves the band: d, and every
+ *      Up/Left/Diagonal test on the path, are then exact (the results are
+ *      band-independent).  Tasks that fail the test are flagged LF_RETRY and redone by the full-width
+ *      k_myers_small. */
+#define LF_RETRY 1
+#ifdef LF_EMU
+static unsigned long lf_emu_band_ok = 0, lf_emu_band_retry = 0; /* test-only visibility into the certificate */
+#define LF_BAND_COUNT(x) ((x)++)
+#else
+#define LF_BAND_COUNT(x) ((void)0)
+#endif
+#define LF_BAND_C 8
+
+__host__ __device__ __forceinline__ uint32_t lf_bucket_hi(uint32_t t)
+{ /* largest target length in t's sort bucket (1/8 octave, see k_align_prep) */
+    if (t < 8u) return t ? t : 1u;
+    uint32_t e = 31u;
+    while (!(t >> e)) e--;
+    const uint32_t m = (t >> (e - 3u)) & 7u;
+    return ((9u + m) << (e - 3u)) - 1u;
+}
+
+struct LfGroupCfg { uint32_t first[LF_CLS_LARGE], count[LF_CLS_LARGE], gbase[LF_CLS_LARGE + 1], nb[LF_CLS_LARGE]; };
+
+__global__ void k_group_scratch(LfDev d, const uint32_t *__restrict__ order, LfGroupCfg cfg, uint32_t *gbytes)
+{ /* one thread per warp group (32 consecutive sorted tasks of one class): bytes of its plane region */
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= cfg.gbase[LF_CLS_LARGE]) return;
+    int cls = 0;
+    while (cls + 1 < LF_CLS_LARGE && g >= cfg.gbase[cls + 1]) cls++;
+    const uint32_t wg = g - cfg.gbase[cls];
+    uint32_t bytes = 0;
+    if (cfg.nb[cls]) {
+        const uint32_t t = d.tasks[order[cfg.first[cls] + wg * 32u]].t_len; /* sorted: the group's first task has its largest bucket */
+        bytes = lf_bucket_hi(t) * cfg.nb[cls] * 256u;
+    }
+    gbytes[g] = bytes;
+}
+
+template <int NB, bool SHW>
+__device__ __forceinline__ void lf_band_column(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], const uint32_t (&qlo)[NB], const uint32_t (&qhi)[NB],
+                                               const uint32_t (&qnn)[NB], uint32_t slo, uint32_t shi, int &score, int wl_rel, uint32_t bl, uint2 *dst)
+{
+    uint32_t Eq[NB], a[NB], sum[NB];
+#pragma unroll
+    for (int w = 0; w < NB; w++) {
+        Eq[w] = ~((qlo[w] ^ slo) | (qhi[w] ^ shi) | qnn[w]);
+        a[w] = Eq[w] & Pv[w];
+    }
+    lf_add_chain<NB>(a, Pv, sum);
+    uint32_t pPh = 0x80000000u, pMh = 0u; /* the row above the band grows by one per column (true for row 0, an upper bound otherwise) */
+#pragma unroll
+    for (int w = 0; w < NB; w++) {
+        const uint32_t Xh = (sum[w] ^ Pv[w]) | Eq[w];
+        const uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
+        const uint32_t Mh = Pv[w] & Xh;
+        const uint32_t Xv = Eq[w] | Mv[w];
+        if (SHW) { if (w == wl_rel) score += (int)((Ph >> bl) & 1u) - (int)((Mh >> bl) & 1u); }
+        const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
+        pPh = Ph; pMh = Mh;
+        const uint32_t nPv = Mhs | ~(Xv | Phs);
+        const uint32_t nMv = Phs & Xv;
+        const uint32_t diagx = ~(nPv | Ph | Eq[w]);
+        dst[w * 32] = make_uint2(nPv | diagx, (~nPv & Ph) | diagx);
+        Pv[w] = nPv; Mv[w] = nMv;
+    }
+}
+
+template <int NB, bool BANDED, bool SHW>
+__global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, uint32_t gbase,
+                                                    const unsigned long long *__restrict__ goff)
+{
+    static_assert(!(BANDED && SHW), "prefix-mode tasks run unbanded");
+    constexpr int WIN = NB < 2 ? 1 : 2;
+    constexpr int C = LF_BAND_C;
+    LF_DYN_SMEM(uint32_t, smem); /* [C][WIN][2][128] */
+    const uint32_t tid = threadIdx.x;
+    const uint32_t gi = blockIdx.x * 128u + tid;
+    if (gi >= count) return;
+    const uint32_t ti = order[first + gi];
+    const lf_align_task task = d.tasks[ti];
+    const int q = (int)task.q_len, t = (int)task.t_len;
+    const int nw = (q + 31) >> 5;
+    lf_align_result r;
+    r.status = 0; r.ops_len = 0;
+    const uint64_t slot_hi = d.slot_end[ti] * 16ull;
+    r.ops_off = slot_hi;
+    const int kmax = BANDED ? (nw > NB ? nw - NB : 0) : 0;
+    const int dq = q / t, dr = q % t;           /* the line's row advances dq (+1 on carry) per column */
+    if (BANDED && kmax > 0) {
+        const int dlt = q > t ? q - t : t - q;
+        if (dq >= 32 || 32 * (NB - 1) - 7 - dlt < 0) { LF_BAND_COUNT(lf_emu_band_retry); r.edit_distance = -1; r.end_location = -1; r.status = LF_RETRY; d.res[ti] = r; return; }
+    }
+    LfQView qv; LfTView tv;
+    lf_task_views(d, task, qv, tv);
+    uint2 *G = (uint2 *)(d.planes + goff[gbase + (gi >> 5)]) + (tid & 31u); /* element (column c, band word j) at G[(c*NB + j)*32] */
+
+    uint32_t qlo[NB], qhi[NB], qnn[NB], Pv[NB], Mv[NB];
+#pragma unroll
+    for (int w = 0; w < NB; w++) {
+        if (w < nw) lf_q32(d, qv, (int64_t)w * 32, qlo[w], qhi[w], qnn[w]);
+        else { qlo[w] = 0; qhi[w] = 0; qnn[w] = 0xffffffffu; }
+        Pv[w] = 0xffffffffu; Mv[w] = 0u;
+    }
+    const int wl = (q - 1) >> 5;
+    const uint32_t bl = (uint32_t)(q - 1) & 31u;
+    int score = q, best = q, bestc = -1;
+    int k = 0;                 /* top word of the band */
+    int rline = 0, racc = 0;   /* floor((c+1)*q/t) and its remainder */
+    int top = 0;               /* D(32k, c) carried along the band's upper edge */
+
+    LfTCursor tc;
+    tc.init(d.pac, tv.t0, tv.dir);
+    for (int c = 0; c < t; c++) {
+        if (BANDED) {
+            rline += dq; racc += dr;
+            if (racc >= t) { racc -= t; rline++; }
+            int kn = (rline - 16 * NB + 16) >> 5;
+            kn = kn < 0 ? 0 : kn > kmax ? kmax : kn;
+            if (kn != k) { /* slide one word down: the top word's vertical deltas move into `top` */
+                top += __popc(Pv[0]) - __popc(Mv[0]);
+#pragma unroll
+                for (int w = 0; w + 1 < NB; w++) { Pv[w] = Pv[w + 1]; Mv[w] = Mv[w + 1]; qlo[w] = qlo[w + 1]; qhi[w] = qhi[w + 1]; qnn[w] = qnn[w + 1]; }
+                Pv[NB - 1] = 0xffffffffu; Mv[NB - 1] = 0u;
+                k++;
+                if (k + NB - 1 < nw) lf_q32(d, qv, (int64_t)(k + NB - 1) * 32, qlo[NB - 1], qhi[NB - 1], qnn[NB - 1]);
+                else { qlo[NB - 1] = 0; qhi[NB - 1] = 0; qnn[NB - 1] = 0xffffffffu; }
+            }
+        }
+        uint32_t slo, shi;
+        tc.next_masks(slo, shi);
+        lf_band_column<NB, SHW>(Pv, Mv, qlo, qhi, qnn, slo, shi, score, wl, bl, G + (size_t)c * (NB * 32));
+        if (SHW) { if (score < best) { best = score; bestc = c; } }
+    }
+    int ed, end;
+    if (SHW) { ed = best; end = bestc; }
+    else {
+        ed = t + top;
+#pragma unroll
+        for (int w = 0; w < NB; w++) {
+            const int wa = k + w;
+            const uint32_t m = wa < wl ? 0xffffffffu : wa == wl ? (0xffffffffu >> (31u - bl)) : 0u;
+            ed += __popc(Pv[w] & m) - __popc(Mv[w] & m);
+        }
+        end = t - 1;
+    }
+    if (BANDED && kmax > 0) {
+        const int dlt = q > t ? q - t : t - q;
+        if (ed > 32 * (NB - 1) - 7 - dlt) { LF_BAND_COUNT(lf_emu_band_retry); r.edit_distance = -1; r.end_location = -1; r.status = LF_RETRY; d.res[ti] = r; return; }
+        LF_BAND_COUNT(lf_emu_band_ok);
+    }
+    r.edit_distance = ed; r.end_location = end;
+    if (task.flags & LF_F_NO_PATH) { d.res[ti] = r; return; }
+
+    /* ---- traceback over the stored planes: Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
+    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1;
+    uint32_t cur = 0, nops = 0;
+    int sh = 30;
+#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
+    int i = q, j = end + 1;
+    uint32_t *smt = smem + tid;
+    constexpr int CS = WIN * 2 * 128;
+    bool lost = false;
+    while (i > 0 && j > 0) {
+        const int c1 = j, c0 = ((j - 1) / C) * C;
+        const int whi = (i - 1) >> 5;
+        const int wtop = whi - WIN + 1 > 0 ? whi - WIN + 1 : 0; /* absolute words wtop .. wtop+WIN-1 */
+        /* band position at column c0, then incrementally */
+        int kc = 0, rl = 0, ra = 0;
+        if (BANDED && kmax > 0) {
+            const long long num = (long long)(c0 + 1) * q;
+            rl = (int)(num / t); ra = (int)(num % t);
+            kc = (rl - 16 * NB + 16) >> 5; kc = kc < 0 ? 0 : kc > kmax ? kmax : kc;
+        }
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            if (c0 + cc < c1) {
+#pragma unroll
+                for (int wi = 0; wi < WIN; wi++) {
+                    const int rel = wtop + wi - kc;
+                    uint2 v = make_uint2(0u, 0u);
+                    if (rel >= 0 && rel < NB) v = G[((size_t)(c0 + cc) * NB + rel) * 32];
+                    smt[(cc * WIN + wi) * 2 * 128] = v.x;
+                    smt[((cc * WIN + wi) * 2 + 1) * 128] = v.y;
+                }
+                if (BANDED && kmax > 0) {
+                    rl += dq; ra += dr;
+                    if (ra >= t) { ra -= t; rl++; }
+                    kc = (rl - 16 * NB + 16) >> 5; kc = kc < 0 ? 0 : kc > kmax ? kmax : kc;
+                }
+            }
+        }
+        const int rowmin = wtop * 32;
+        while (i > 0 && j > c0 && (i - 1) >= rowmin) {
+            const int wrow = (i - 1) >> 5;
+            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * 128;
+            int b = (i - 1) & 31;
+            do {
+                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
+                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+                const int stay_col = (int)(x0 & ~x1 & 1u);
+                const int stay_row = (int)(x1 & ~x0 & 1u);
+                LF_EMIT(op);
+                b -= 1 - stay_row;
+                j -= 1 - stay_col;
+                cell -= (1 - stay_col) * CS;
+            } while (b >= 0 && j > c0);
+            i = wrow * 32 + b + 1;
+        }
+        if (nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
+    }
+    while (i > 0 && !lost) { LF_EMIT(1u); i--; }
+    while (j > 0 && !lost) { LF_EMIT(2u); j--; }
+    if (sh != 30) *wptr = cur;
+#undef LF_EMIT
+    if (lost) { r.edit_distance = -1; r.end_location = -1; r.status = LF_RETRY; r.ops_len = 0; d.res[ti] = r; return; }
+    r.ops_off = slot_hi - nops; r.ops_len = nops;
+    d.res[ti] = r;
 }

@@ -31,6 +31,7 @@ struct DevState {
     lfb_event cls_ev[LF_NCLS][2] = {};   /* start / end of every class kernel (timeline hook) */
     bool cls_ran[LF_NCLS] = {};
     LfbBuf pac, bases, read_off, plo, phi, pnn;
+    LfbBuf planes, gbytes, goff;   /* k_myers_band: plane regions per warp group */
     LfbBuf res_keep, ops_keep;   /* lf_chain.inl parks the round-1 results / op stream here while round 3 runs */
     LfbBuf tasks, res, ops, keys, keys2, idx, idx2, slot_words, scr_bytes, slot_end, scr_off, scratch, large_scr, counters, queue;
     LfbBuf etasks, eres, escr_items, escr_off, escr;
@@ -80,31 +81,61 @@ LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
     v.slot_end = d.slot_end.as<uint64_t>();
     v.scr_off = d.scr_off.as<uint64_t>();
     v.scratch = d.scratch.as<uint8_t>();
+    v.planes = d.planes.as<uint8_t>();
     return v;
 }
 
 template <int CI, bool SHW>
-void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s)
+void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, uint32_t retry_only)
 {
     constexpr int NW = CI == 0 ? 1 : CI == 1 ? 2 : CI == 2 ? 3 : CI == 3 ? 4 : CI == 4 ? 6 : CI == 5 ? 8 : CI == 6 ? 12 : 16;
     constexpr int WIN = NW < 2 ? 1 : 2;
     const size_t smem = (size_t)LF_K1_C * WIN * 2 * LF_K1_BLOCK * sizeof(uint32_t);
     const uint32_t grid = (count + LF_K1_BLOCK - 1) / LF_K1_BLOCK;
     auto kern = k_myers_small<NW, SHW>;
-    LFB_LAUNCH(kern, grid, LF_K1_BLOCK, smem, s, v, order, first, count);
+    LFB_LAUNCH(kern, grid, LF_K1_BLOCK, smem, s, v, order, first, count, retry_only);
 }
 
-void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s)
+template <int NB, bool BANDED, bool SHW>
+void launch_band(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase, const unsigned long long *goff, lfb_stream s)
+{
+    constexpr int WIN = NB < 2 ? 1 : 2;
+    const size_t smem = (size_t)LF_BAND_C * WIN * 2 * 128 * sizeof(uint32_t);
+    const uint32_t grid = (count + 127) / 128;
+    auto kern = k_myers_band<NB, BANDED, SHW>;
+    LFB_LAUNCH(kern, grid, 128, smem, s, v, order, first, count, gbase, goff);
+}
+
+/* band width (32-row words) the class is run with by k_myers_band; 0 = full-width k_myers_small only */
+int band_nb(int cls)
+{
+    const int sc = cls >> 1, shw = cls & 1;
+    if (sc <= 3) return sc + 1;                 /* q <= 128: the whole column, no banding (NW and SHW) */
+    if (shw) return 0;                          /* long prefix-mode tasks: full width */
+    return sc == 4 ? 3 : sc == 7 ? 5 : 4;       /* q <= 192 / 256, 384 / 512 */
+}
+
+void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase,
+                        const unsigned long long *goff, lfb_stream s)
 {
     switch (cls) {
-    case 0: launch_small<0, false>(v, order, first, count, s); break;  case 1: launch_small<0, true>(v, order, first, count, s); break;
-    case 2: launch_small<1, false>(v, order, first, count, s); break;  case 3: launch_small<1, true>(v, order, first, count, s); break;
-    case 4: launch_small<2, false>(v, order, first, count, s); break;  case 5: launch_small<2, true>(v, order, first, count, s); break;
-    case 6: launch_small<3, false>(v, order, first, count, s); break;  case 7: launch_small<3, true>(v, order, first, count, s); break;
-    case 8: launch_small<4, false>(v, order, first, count, s); break;  case 9: launch_small<4, true>(v, order, first, count, s); break;
-    case 10: launch_small<5, false>(v, order, first, count, s); break; case 11: launch_small<5, true>(v, order, first, count, s); break;
-    case 12: launch_small<6, false>(v, order, first, count, s); break; case 13: launch_small<6, true>(v, order, first, count, s); break;
-    case 14: launch_small<7, false>(v, order, first, count, s); break; case 15: launch_small<7, true>(v, order, first, count, s); break;
+    case 0: launch_band<1, false, false>(v, order, first, count, gbase, goff, s); break;
+    case 1: launch_band<1, false, true>(v, order, first, count, gbase, goff, s); break;
+    case 2: launch_band<2, false, false>(v, order, first, count, gbase, goff, s); break;
+    case 3: launch_band<2, false, true>(v, order, first, count, gbase, goff, s); break;
+    case 4: launch_band<3, false, false>(v, order, first, count, gbase, goff, s); break;
+    case 5: launch_band<3, false, true>(v, order, first, count, gbase, goff, s); break;
+    case 6: launch_band<4, false, false>(v, order, first, count, gbase, goff, s); break;
+    case 7: launch_band<4, false, true>(v, order, first, count, gbase, goff, s); break;
+    /* banded first, then the full-width kernel over the same list for the tasks flagged LF_RETRY */
+    case 8: launch_band<3, true, false>(v, order, first, count, gbase, goff, s); launch_small<4, false>(v, order, first, count, s, 1); break;
+    case 10: launch_band<4, true, false>(v, order, first, count, gbase, goff, s); launch_small<5, false>(v, order, first, count, s, 1); break;
+    case 12: launch_band<4, true, false>(v, order, first, count, gbase, goff, s); launch_small<6, false>(v, order, first, count, s, 1); break;
+    case 14: launch_band<5, true, false>(v, order, first, count, gbase, goff, s); launch_small<7, false>(v, order, first, count, s, 1); break;
+    case 9: launch_small<4, true>(v, order, first, count, s, 0); break;
+    case 11: launch_small<5, true>(v, order, first, count, s, 0); break;
+    case 13: launch_small<6, true>(v, order, first, count, s, 0); break;
+    case 15: launch_small<7, true>(v, order, first, count, s, 0); break;
     default: break;
     }
 }
@@ -143,6 +174,26 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     d.ops_words = ht->slot_total;
     LF_TRY(d.ops.reserve((size_t)ht->slot_total * 4 + 64));
     LF_TRY(d.scratch.reserve((size_t)ht->scr_total + 64));
+    /* plane regions of k_myers_band: one per warp group (32 consecutive sorted tasks of a class) */
+    LfGroupCfg gc;
+    {
+        uint32_t first = 0, g = 0;
+        for (int cls = 0; cls < LF_CLS_LARGE; cls++) {
+            gc.first[cls] = first; gc.count[cls] = ht->cnt.hist[cls]; gc.gbase[cls] = g; gc.nb[cls] = (uint32_t)band_nb(cls);
+            first += ht->cnt.hist[cls]; g += (ht->cnt.hist[cls] + 31) / 32;
+        }
+        gc.gbase[LF_CLS_LARGE] = g;
+    }
+    const uint32_t ngroups = gc.gbase[LF_CLS_LARGE];
+    if (ngroups) {
+        LF_TRY(d.gbytes.reserve((size_t)ngroups * 4 + 64)); LF_TRY(d.goff.reserve(((size_t)ngroups + 1) * 8));
+        v = make_dev(ctx, d);
+        LFB_LAUNCH(k_group_scratch, (ngroups + 255) / 256, 256, 0, s, v, d.idx2.as<uint32_t>(), gc, d.gbytes.as<uint32_t>());
+        LF_TRY(lfb_scan_excl_total(d.tmp, d.gbytes.as<uint32_t>(), d.goff.as<unsigned long long>(), ngroups, s));
+        LF_TRY(lfb_d2h(&ht->scr_total, d.goff.as<unsigned long long>() + ngroups, 8, s));
+        LF_TRY(lfb_sync(s));
+        LF_TRY(d.planes.reserve((size_t)ht->scr_total + 256));
+    }
     v = make_dev(ctx, d);
 
     ctx->stats.align_tasks += n;
@@ -199,7 +250,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
-            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, st);
+            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, gc.gbase[cls], d.goff.as<unsigned long long>(), st);
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][1], st);
 #endif
@@ -267,7 +318,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
     if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
     for (DevState &d : ctx->devs) {
         set_dev(d);
-        LfbBuf *bufs[] = { &d.res_keep, &d.ops_keep, &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
+        LfbBuf *bufs[] = { &d.planes, &d.gbytes, &d.goff, &d.res_keep, &d.ops_keep, &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
                            &d.slot_words, &d.scr_bytes, &d.slot_end, &d.scr_off, &d.scratch, &d.large_scr, &d.counters, &d.queue,
                            &d.etasks, &d.eres, &d.escr_items, &d.escr_off, &d.escr };
         for (LfbBuf *b : bufs) b->release();
