@@ -502,7 +502,7 @@ __device__ __forceinline__ void lf_k1_recompute(uint32_t (&Pv)[NW], uint32_t (&M
 }
 
 template <int NW, bool SHW>
-__global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, uint32_t retry_only)
+__global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, const uint32_t *__restrict__ retry_count)
 {
     constexpr int WIN = NW < 2 ? 1 : 2;
     constexpr int C = LF_K1_C;
@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
     const uint32_t tid = threadIdx.x;
     const uint32_t gi = blockIdx.x * LF_K1_BLOCK + tid;
     if (gi >= count) return;
+    if (retry_count && gi >= *retry_count) return; /* `order` is then the dense list k_myers_band appended its uncertified tasks to */
     const uint32_t ti = order[first + gi];
-    if (retry_only && d.res[ti].status != 1 /* LF_RETRY */) return; /* only what the banded kernel could not certify */
     const lf_align_task task = d.tasks[ti];
     const int q = (int)task.q_len, t = (int)task.t_len;
     LfQView qv; LfTView tv;
@@ -1554,7 +1554,7 @@ __device__ __forceinline__ void lf_band_column(uint32_t (&Pv)[NB], uint32_t (&Mv
 
 template <int NB, bool BANDED, bool SHW>
 __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, uint32_t gbase,
-                                                    const unsigned long long *__restrict__ goff)
+                                                    const unsigned long long *__restrict__ goff, uint32_t *retry_list, uint32_t *retry_count)
 {
     static_assert(!(BANDED && SHW), "prefix-mode tasks run unbanded");
     constexpr int WIN = NB < 2 ? 1 : 2;
@@ -1575,7 +1575,7 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
     const int dq = q / t, dr = q % t;           /* the line's row advances dq (+1 on carry) per column */
     if (BANDED && kmax > 0) {
         const int dlt = q > t ? q - t : t - q;
-        if (dq >= 32 || 32 * (NB - 1) - 7 - dlt < 0) { LF_BAND_COUNT(lf_emu_band_retry); r.edit_distance = -1; r.end_location = -1; r.status = LF_RETRY; d.res[ti] = r; return; }
+        if (dq >= 32 || 32 * (NB - 1) - 7 - dlt < 0) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
     }
     LfQView qv; LfTView tv;
     lf_task_views(d, task, qv, tv);
@@ -1632,7 +1632,7 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
     }
     if (BANDED && kmax > 0) {
         const int dlt = q > t ? q - t : t - q;
-        if (ed > 32 * (NB - 1) - 7 - dlt) { LF_BAND_COUNT(lf_emu_band_retry); r.edit_distance = -1; r.end_location = -1; r.status = LF_RETRY; d.res[ti] = r; return; }
+        if (ed > 32 * (NB - 1) - 7 - dlt) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
         LF_BAND_COUNT(lf_emu_band_ok);
     }
     r.edit_distance = ed; r.end_location = end;
@@ -1647,12 +1647,13 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
     uint32_t *smt = smem + tid;
     constexpr int CS = WIN * 2 * 128;
     bool lost = false;
-    while (i > 0 && j > 0) {
-        const int c1 = j, c0 = ((j - 1) / C) * C;
-        const int whi = (i - 1) >> 5;
-        const int wtop = whi - WIN + 1 > 0 ? whi - WIN + 1 : 0; /* absolute words wtop .. wtop+WIN-1 */
-        /* band position at column c0, then incrementally */
-        int kc = 0, rl = 0, ra = 0;
+    /* plane words of one block (C columns x WIN words) travel global -> registers -> shared memory; the registers
+     * for the NEXT block are requested before the current block is walked, so the HBM/L2 latency hides behind
+     * the walk.  The next block's window is predicted from the current row; a wrong guess only costs a reload. */
+    uint2 pre[C * WIN];
+    int pre_c0 = -1, pre_wtop = 0;
+    auto load_block = [&](int c0, int ncol, int wtop) {
+        int kc = 0, rl = 0, ra = 0; /* band position at column c0, then incrementally */
         if (BANDED && kmax > 0) {
             const long long num = (long long)(c0 + 1) * q;
             rl = (int)(num / t); ra = (int)(num % t);
@@ -1660,22 +1661,35 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
         }
 #pragma unroll
         for (int cc = 0; cc < C; cc++) {
-            if (c0 + cc < c1) {
 #pragma unroll
-                for (int wi = 0; wi < WIN; wi++) {
-                    const int rel = wtop + wi - kc;
-                    uint2 v = make_uint2(0u, 0u);
-                    if (rel >= 0 && rel < NB) v = G[((size_t)(c0 + cc) * NB + rel) * 32];
-                    smt[(cc * WIN + wi) * 2 * 128] = v.x;
-                    smt[((cc * WIN + wi) * 2 + 1) * 128] = v.y;
-                }
-                if (BANDED && kmax > 0) {
-                    rl += dq; ra += dr;
-                    if (ra >= t) { ra -= t; rl++; }
-                    kc = (rl - 16 * NB + 16) >> 5; kc = kc < 0 ? 0 : kc > kmax ? kmax : kc;
-                }
+            for (int wi = 0; wi < WIN; wi++) {
+                const int rel = wtop + wi - kc;
+                uint2 v = make_uint2(0u, 0u);
+                if (cc < ncol && rel >= 0 && rel < NB) v = G[((size_t)(c0 + cc) * NB + rel) * 32];
+                pre[cc * WIN + wi] = v;
+            }
+            if (BANDED && kmax > 0) {
+                rl += dq; ra += dr;
+                if (ra >= t) { ra -= t; rl++; }
+                kc = (rl - 16 * NB + 16) >> 5; kc = kc < 0 ? 0 : kc > kmax ? kmax : kc;
             }
         }
+    };
+    while (i > 0 && j > 0) {
+        const int c1 = j, c0 = ((j - 1) / C) * C;
+        const int whi = (i - 1) >> 5;
+        int wtop = whi - WIN + 1 > 0 ? whi - WIN + 1 : 0; /* absolute words wtop .. wtop+WIN-1 */
+        if (pre_c0 == c0 && c1 == c0 + C && whi >= pre_wtop && whi < pre_wtop + WIN) wtop = pre_wtop; /* the prefetched block fits */
+        else load_block(c0, c1 - c0, wtop);
+#pragma unroll
+        for (int e = 0; e < C * WIN; e++) { smt[e * 2 * 128] = pre[e].x; smt[(e * 2 + 1) * 128] = pre[e].y; }
+        if (c0 > 0) { /* request the block to the left now; it is consumed after this block's walk */
+            const int ip = i - 1 - C > 0 ? i - 1 - C : 0;
+            const int wp = ip >> 5;
+            pre_wtop = wp - WIN + 1 > 0 ? wp - WIN + 1 : 0;
+            pre_c0 = c0 - C;
+            load_block(pre_c0, C, pre_wtop);
+        } else pre_c0 = -1;
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
             const int wrow = (i - 1) >> 5;
@@ -1699,7 +1713,7 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
     while (j > 0 && !lost) { LF_EMIT(2u); j--; }
     if (sh != 30) *wptr = cur;
 #undef LF_EMIT
-    if (lost) { r.edit_distance = -1; r.end_location = -1; r.status = LF_RETRY; r.ops_len = 0; d.res[ti] = r; return; }
+    if (lost) { retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
     r.ops_off = slot_hi - nops; r.ops_len = nops;
     d.res[ti] = r;
 }

@@ -86,26 +86,30 @@ LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
 }
 
 template <int CI, bool SHW>
-void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, uint32_t retry_only)
+void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, const uint32_t *retry_count)
 {
     constexpr int NW = CI == 0 ? 1 : CI == 1 ? 2 : CI == 2 ? 3 : CI == 3 ? 4 : CI == 4 ? 6 : CI == 5 ? 8 : CI == 6 ? 12 : 16;
     constexpr int WIN = NW < 2 ? 1 : 2;
     const size_t smem = (size_t)LF_K1_C * WIN * 2 * LF_K1_BLOCK * sizeof(uint32_t);
     const uint32_t grid = (count + LF_K1_BLOCK - 1) / LF_K1_BLOCK;
     auto kern = k_myers_small<NW, SHW>;
-    LFB_LAUNCH(kern, grid, LF_K1_BLOCK, smem, s, v, order, first, count, retry_only);
+    LFB_LAUNCH(kern, grid, LF_K1_BLOCK, smem, s, v, order, first, count, retry_count);
 }
 
 template <int NB, bool BANDED, bool SHW>
-void launch_band(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase, const unsigned long long *goff, lfb_stream s)
+void launch_band(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase, const unsigned long long *goff, lfb_stream s,
+                 uint32_t *retry_list, uint32_t *retry_count)
 {
     constexpr int WIN = NB < 2 ? 1 : 2;
     const size_t smem = (size_t)LF_BAND_C * WIN * 2 * 128 * sizeof(uint32_t);
     const uint32_t grid = (count + 127) / 128;
     auto kern = k_myers_band<NB, BANDED, SHW>;
-    LFB_LAUNCH(kern, grid, 128, smem, s, v, order, first, count, gbase, goff);
+    LFB_LAUNCH(kern, grid, 128, smem, s, v, order, first, count, gbase, goff, retry_list, retry_count);
 }
 
+#ifndef LF_BAND_MASK_DEFAULT
+#define LF_BAND_MASK_DEFAULT 0x00ff
+#endif
 /* band width (32-row words) the class is run with by k_myers_band; 0 = full-width k_myers_small only */
 int band_nb(int cls)
 {
@@ -115,27 +119,54 @@ int band_nb(int cls)
     return sc == 4 ? 3 : sc == 7 ? 5 : 4;       /* q <= 192 / 256, 384 / 512 */
 }
 
-void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase,
-                        const unsigned long long *goff, lfb_stream s)
+/* Which classes run k_myers_band (bit = class id); the others run the full-width k_myers_small.  Measured on B200
+ * (profiles/r01g_band_mask_sweep.txt): keeping the op planes in HBM instead of recomputing them is a small win for
+ * the unbanded classes (q <= 128), while the banded variant + full-width retry loses to the full-width kernel on
+ * the SV-rich workload, so it stays off by default.  LF_BAND_MASK overrides (tests run 0xffff on the emulator). */
+uint32_t band_mask()
 {
+    const char *e = getenv("LF_BAND_MASK");
+    return e ? (uint32_t)strtoul(e, nullptr, 0) : (uint32_t)LF_BAND_MASK_DEFAULT;
+}
+
+void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase,
+                        const unsigned long long *goff, lfb_stream s, uint32_t *rl, uint32_t *rc, uint32_t bmask)
+{   /* rl: retry list (indexed like `order`), rc: this class's retry counter */
+    if (band_nb(cls) && (bmask >> cls & 1u)) {
+        switch (cls) {
+        case 0: launch_band<1, false, false>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        case 1: launch_band<1, false, true>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        case 2: launch_band<2, false, false>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        case 3: launch_band<2, false, true>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        case 4: launch_band<3, false, false>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        case 5: launch_band<3, false, true>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        case 6: launch_band<4, false, false>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        case 7: launch_band<4, false, true>(v, order, first, count, gbase, goff, s, rl, rc); return;
+        /* banded first, then the full-width kernel over the dense list of tasks the band could not certify */
+        case 8: launch_band<3, true, false>(v, order, first, count, gbase, goff, s, rl, rc); launch_small<4, false>(v, rl, first, count, s, rc); return;
+        case 10: launch_band<4, true, false>(v, order, first, count, gbase, goff, s, rl, rc); launch_small<5, false>(v, rl, first, count, s, rc); return;
+        case 12: launch_band<4, true, false>(v, order, first, count, gbase, goff, s, rl, rc); launch_small<6, false>(v, rl, first, count, s, rc); return;
+        case 14: launch_band<5, true, false>(v, order, first, count, gbase, goff, s, rl, rc); launch_small<7, false>(v, rl, first, count, s, rc); return;
+        default: break;
+        }
+    }
     switch (cls) {
-    case 0: launch_band<1, false, false>(v, order, first, count, gbase, goff, s); break;
-    case 1: launch_band<1, false, true>(v, order, first, count, gbase, goff, s); break;
-    case 2: launch_band<2, false, false>(v, order, first, count, gbase, goff, s); break;
-    case 3: launch_band<2, false, true>(v, order, first, count, gbase, goff, s); break;
-    case 4: launch_band<3, false, false>(v, order, first, count, gbase, goff, s); break;
-    case 5: launch_band<3, false, true>(v, order, first, count, gbase, goff, s); break;
-    case 6: launch_band<4, false, false>(v, order, first, count, gbase, goff, s); break;
-    case 7: launch_band<4, false, true>(v, order, first, count, gbase, goff, s); break;
-    /* banded first, then the full-width kernel over the same list for the tasks flagged LF_RETRY */
-    case 8: launch_band<3, true, false>(v, order, first, count, gbase, goff, s); launch_small<4, false>(v, order, first, count, s, 1); break;
-    case 10: launch_band<4, true, false>(v, order, first, count, gbase, goff, s); launch_small<5, false>(v, order, first, count, s, 1); break;
-    case 12: launch_band<4, true, false>(v, order, first, count, gbase, goff, s); launch_small<6, false>(v, order, first, count, s, 1); break;
-    case 14: launch_band<5, true, false>(v, order, first, count, gbase, goff, s); launch_small<7, false>(v, order, first, count, s, 1); break;
-    case 9: launch_small<4, true>(v, order, first, count, s, 0); break;
-    case 11: launch_small<5, true>(v, order, first, count, s, 0); break;
-    case 13: launch_small<6, true>(v, order, first, count, s, 0); break;
-    case 15: launch_small<7, true>(v, order, first, count, s, 0); break;
+    case 0: launch_small<0, false>(v, order, first, count, s, nullptr); break;
+    case 1: launch_small<0, true>(v, order, first, count, s, nullptr); break;
+    case 2: launch_small<1, false>(v, order, first, count, s, nullptr); break;
+    case 3: launch_small<1, true>(v, order, first, count, s, nullptr); break;
+    case 4: launch_small<2, false>(v, order, first, count, s, nullptr); break;
+    case 5: launch_small<2, true>(v, order, first, count, s, nullptr); break;
+    case 6: launch_small<3, false>(v, order, first, count, s, nullptr); break;
+    case 7: launch_small<3, true>(v, order, first, count, s, nullptr); break;
+    case 8: launch_small<4, false>(v, order, first, count, s, nullptr); break;
+    case 9: launch_small<4, true>(v, order, first, count, s, nullptr); break;
+    case 10: launch_small<5, false>(v, order, first, count, s, nullptr); break;
+    case 11: launch_small<5, true>(v, order, first, count, s, nullptr); break;
+    case 12: launch_small<6, false>(v, order, first, count, s, nullptr); break;
+    case 13: launch_small<6, true>(v, order, first, count, s, nullptr); break;
+    case 14: launch_small<7, false>(v, order, first, count, s, nullptr); break;
+    case 15: launch_small<7, true>(v, order, first, count, s, nullptr); break;
     default: break;
     }
 }
@@ -154,9 +185,9 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     LF_TRY(d.slot_words.reserve(n * 4)); LF_TRY(d.scr_bytes.reserve(n * 4));
     LF_TRY(d.slot_end.reserve(n * 8)); LF_TRY(d.scr_off.reserve((n + 1) * 8));
     LF_TRY(d.res.reserve(n * sizeof(lf_align_result)));
-    LF_TRY(d.counters.reserve(sizeof(LfCounters))); LF_TRY(d.queue.reserve(64));
+    LF_TRY(d.counters.reserve(sizeof(LfCounters))); LF_TRY(d.queue.reserve(256)); /* [0]: large-task work counter, [1+cls]: retry counters */
     LF_TRY(lfb_memset(d.counters.p, 0, sizeof(LfCounters), s));
-    LF_TRY(lfb_memset(d.queue.p, 0, 64, s));
+    LF_TRY(lfb_memset(d.queue.p, 0, 256, s));
 #ifndef LF_EMU
     cudaEventRecord(d.ev[0], s);
 #endif
@@ -176,10 +207,11 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     LF_TRY(d.scratch.reserve((size_t)ht->scr_total + 64));
     /* plane regions of k_myers_band: one per warp group (32 consecutive sorted tasks of a class) */
     LfGroupCfg gc;
+    const uint32_t bmask = band_mask();
     {
         uint32_t first = 0, g = 0;
         for (int cls = 0; cls < LF_CLS_LARGE; cls++) {
-            gc.first[cls] = first; gc.count[cls] = ht->cnt.hist[cls]; gc.gbase[cls] = g; gc.nb[cls] = (uint32_t)band_nb(cls);
+            gc.first[cls] = first; gc.count[cls] = ht->cnt.hist[cls]; gc.gbase[cls] = g; gc.nb[cls] = (bmask >> cls & 1u) ? (uint32_t)band_nb(cls) : 0u;
             first += ht->cnt.hist[cls]; g += (ht->cnt.hist[cls] + 31) / 32;
         }
         gc.gbase[LF_CLS_LARGE] = g;
@@ -250,7 +282,8 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
-            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, gc.gbase[cls], d.goff.as<unsigned long long>(), st);
+            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, gc.gbase[cls], d.goff.as<unsigned long long>(), st,
+                               d.idx.as<uint32_t>() /* input of the sort, free by now */, d.queue.as<uint32_t>() + 1 + cls, bmask);
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][1], st);
 #endif

@@ -117,3 +117,52 @@ def test_emu_large_and_hirschberg_tasks(emu_lib):
     bad, _, _ = check_align(g, reads, ref, tasks)
     assert not bad, bad
     g.close()
+
+
+def _band_stress_batch(rng, ref, n):
+    """Pairs of 129..512 rows whose optimal path bulges off the straight diagonal: block indels that a
+    sliding band of 3-5 words sometimes covers and sometimes does not."""
+    reads, tasks, pos = [], [], 1000
+    for k in range(n):
+        L = int(rng.integers(129, 520))
+        t = ref[pos:pos + L]
+        q = sim.mutate_pair(t, float(rng.choice([0.02, 0.06, 0.10, 0.14])), rng)
+        kind, junk = k % 5, lambda m: sim.ACGT[rng.integers(0, 4, size=m, dtype=np.uint8)]
+        if kind == 1:
+            m = int(rng.integers(10, 60)); at = int(rng.integers(0, len(q)))
+            q = np.concatenate([q[:at], junk(m), q[at:]])
+        elif kind == 2:
+            m = int(rng.integers(10, 60)); at = int(rng.integers(0, max(1, len(q) - m)))
+            q = np.concatenate([q[:at], q[at + m:]])
+        elif kind == 3:
+            m = int(rng.integers(10, 45)); a1 = int(rng.integers(0, len(q) // 3)); a2 = int(rng.integers(2 * len(q) // 3, len(q) - m - 1))
+            q = np.concatenate([q[:a1], junk(m), q[a1:a2], q[a2 + m:]])
+        elif kind == 4:
+            m = int(rng.integers(10, 45)); a1 = int(rng.integers(0, len(q) // 3)); a2 = int(rng.integers(2 * len(q) // 3, len(q) - 1))
+            q = np.concatenate([q[:a1], q[a1 + m:a2], junk(m), q[a2:]])
+        q = q[:512]
+        if len(q) < 1:
+            continue
+        reads.append(q)
+        tasks.append((len(reads) - 1, 0, len(q), pos, L, int(rng.integers(0, 2)) * 2, 0, 0))
+        pos += L + 20
+    return reads, np.array(tasks, dtype=api.ALIGN_TASK)
+
+
+def test_emu_banded_classes_certificate_and_retry(emu_lib, monkeypatch):
+    """k_myers_band with the sliding band switched on for every class it supports (off by default for q > 128):
+    certified tasks and tasks redone full-width must both match the oracle."""
+    import ctypes as C
+    monkeypatch.setenv("LF_BAND_MASK", "0xffff")
+    rng = np.random.default_rng(4)
+    ref = sim.make_reference(200_000, 5)
+    reads, tasks = _band_stress_batch(rng, ref, 300)
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    ok0, rt0 = C.c_ulong(), C.c_ulong()
+    g.lib.lf_emu_band_counts(C.byref(ok0), C.byref(rt0))
+    bad, _, _ = check_align(g, reads, ref, tasks)
+    assert not bad
+    ok, rt = C.c_ulong(), C.c_ulong()
+    g.lib.lf_emu_band_counts(C.byref(ok), C.byref(rt))
+    assert ok.value - ok0.value > 50 and rt.value - rt0.value > 20  # both outcomes exercised
+    g.close()

@@ -49,8 +49,12 @@ def test_gpu_random_tasks_all_flags():
     g.close()
 
 
-def test_gpu_similar_pairs_every_length():
-    """query = mutated target for every q from 1 to 560 (all register classes and their edges)."""
+@pytest.mark.parametrize("band_mask", [None, "0x0", "0xffff"])
+def test_gpu_similar_pairs_every_length(band_mask, monkeypatch):
+    """query = mutated target for every q from 1 to 560 (all register classes and their edges); with the
+    default kernel mapping, with k_myers_small everywhere and with k_myers_band (banded + retry) everywhere."""
+    if band_mask is not None:
+        monkeypatch.setenv("LF_BAND_MASK", band_mask)
     rng = np.random.default_rng(77)
     ref = sim.make_reference(400_000, 9)
     reads, tasks, pos = [], [], 1000
