@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 
 #ifndef LF_EMU
 #include <cuda_runtime.h>
@@ -31,7 +32,7 @@ typedef int lfb_event;
 #endif
 
 static thread_local char lfb_errbuf[512];
-static uint64_t lfb_launches = 0;
+static std::atomic<uint64_t> lfb_launches{0}; /* kernels launched by this library (the early emit launches from its own thread) */
 static int lfb_fail(const char *what, const char *where)
 {
     snprintf(lfb_errbuf, sizeof lfb_errbuf, "%s at %s", what, where);

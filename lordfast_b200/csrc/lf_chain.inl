@@ -290,11 +290,31 @@ struct PinBuf {
     void *reserve(size_t need) { if (need > cap) { lfb_host_free(p); cap = need + need / 4 + 4096; p = lfb_host_alloc(cap); if (!p) cap = 0; } return p; }
     void release() { lfb_host_free(p); p = nullptr; cap = 0; }
 };
+/* Device and pinned scratch of one emit list (k_emit_slots sizing pass -> scans -> writing pass). */
+struct EmitSet {
+    LfbBuf d_list, d_nrec, d_cigb, d_mdb, d_rec_off, d_cig_off, d_md_off, d_recs, d_text;
+    LfbTemp tmp;
+    PinBuf tot, h_recs;
+    lfb_stream st = 0; bool have_stream = false;
+    size_t n = 0, nrec = 0, ncig = 0, nmd = 0;
+    void release()
+    {
+        LfbBuf *all[] = { &d_list, &d_nrec, &d_cigb, &d_mdb, &d_rec_off, &d_cig_off, &d_md_off, &d_recs, &d_text };
+        for (LfbBuf *b : all) b->release();
+        lfb_free(tmp.p); tmp.p = nullptr; tmp.cap = 0;
+        tot.release(); h_recs.release();
+#ifndef LF_EMU
+        if (have_stream) cudaStreamDestroy(st);
+#endif
+        have_stream = false;
+    }
+};
 struct ChainScratch {
     PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2, ed1, seeds_stage;
     std::vector<Emit> *parts = nullptr;
     /* device side of the GPU emit */
-    LfbBuf d_chains, d_seeds, d_task_base, d_guards, d_clip, d_split_begin, d_splits, d_nrec, d_cigb, d_mdb, d_rec_off, d_cig_off, d_md_off, d_recs, d_text, d_ed;
+    EmitSet es[2];          /* [0]: chains no trigger fired for (emitted while rounds 2-3 run), [1]: the rest */
+    LfbBuf d_chains, d_seeds, d_task_base, d_guards, d_clip, d_split_begin, d_splits, d_nrec, d_cigb, d_mdb, d_rec_off, d_cig_off, d_md_off, d_recs, d_text, d_ed, d_slot_base, d_slot_info, d_slot_task;
 };
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
 
@@ -319,8 +339,9 @@ void chain_scratch_free_fn(void *p)
     PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2, &s->ed1, &s->seeds_stage };
     for (PinBuf *b : all) b->release();
     LfbBuf *dall[] = { &s->d_chains, &s->d_seeds, &s->d_task_base, &s->d_guards, &s->d_clip, &s->d_split_begin, &s->d_splits, &s->d_nrec, &s->d_cigb, &s->d_mdb,
-                       &s->d_rec_off, &s->d_cig_off, &s->d_md_off, &s->d_recs, &s->d_text, &s->d_ed };
+                       &s->d_rec_off, &s->d_cig_off, &s->d_md_off, &s->d_recs, &s->d_text, &s->d_ed, &s->d_slot_base, &s->d_slot_info, &s->d_slot_task };
     for (LfbBuf *b : dall) b->release();
+    s->es[0].release(); s->es[1].release();
     delete s->parts;
     delete s;
 }
@@ -329,6 +350,55 @@ ChainScratch &chain_scratch(lf_gpu_ctx *ctx)
     if (!ctx->chain_scratch) { ctx->chain_scratch = new ChainScratch(); ctx->chain_scratch_free = chain_scratch_free_fn; }
     return *(ChainScratch *)ctx->chain_scratch;
 }
+
+
+/* ---- GPU emit of one list of chains: k_emit_slots sizing pass -> scans -> writing pass ---- */
+int emit_size(EmitSet &es, LfEmitDev &E, const uint32_t *list, size_t n)
+{
+    lfb_stream st = es.st;
+    es.n = n; es.nrec = es.ncig = es.nmd = 0;
+    if (!n) return 0;
+    if (es.d_list.reserve(n * 4 + 64) || es.d_nrec.reserve(n * 4 + 64) || es.d_cigb.reserve(n * 4 + 64) || es.d_mdb.reserve(n * 4 + 64)
+        || es.d_rec_off.reserve((n + 1) * 8) || es.d_cig_off.reserve((n + 1) * 8) || es.d_md_off.reserve((n + 1) * 8)) return LF_ERR_NOMEM;
+    unsigned long long *tot = (unsigned long long *)es.tot.reserve(64);
+    if (!tot) return LF_ERR_NOMEM;
+    if (lfb_h2d(es.d_list.p, list, n * 4, st)) return LF_ERR_CUDA;
+    E.chain_list = es.d_list.as<uint32_t>(); E.n_chains = (uint32_t)n;
+    E.nrec = es.d_nrec.as<uint32_t>(); E.cig_bytes = es.d_cigb.as<uint32_t>(); E.md_bytes = es.d_mdb.as<uint32_t>();
+    { auto kern = k_emit_slots<false>; LFB_LAUNCH(kern, (unsigned)n, LF_EMIT_BLOCK, 0, st, E); }   /* one block per chain, one thread per slot */
+    if (lfb_scan_excl_total(es.tmp, E.nrec, es.d_rec_off.as<unsigned long long>(), n, st)
+        || lfb_scan_excl_total(es.tmp, E.cig_bytes, es.d_cig_off.as<unsigned long long>(), n, st)
+        || lfb_scan_excl_total(es.tmp, E.md_bytes, es.d_md_off.as<unsigned long long>(), n, st)) return LF_ERR_CUDA;
+    if (lfb_d2h(&tot[0], es.d_rec_off.as<unsigned long long>() + n, 8, st) || lfb_d2h(&tot[1], es.d_cig_off.as<unsigned long long>() + n, 8, st)
+        || lfb_d2h(&tot[2], es.d_md_off.as<unsigned long long>() + n, 8, st) || lfb_sync(st)) return LF_ERR_CUDA;
+    es.nrec = (size_t)tot[0]; es.ncig = (size_t)tot[1]; es.nmd = (size_t)tot[2];
+    return 0;
+}
+
+/* writes the list's text to text_dst (host; the bytes land at offset out_base of the caller-visible buffer) and
+ * its records to es.h_recs; asynchronous on es.st */
+int emit_write(EmitSet &es, LfEmitDev &E, char *text_dst, uint64_t out_base)
+{
+    if (!es.n) return 0;
+    lfb_stream st = es.st;
+    if (es.d_recs.reserve((es.nrec + 1) * sizeof(lf_sam_record)) || es.d_text.reserve(es.ncig + es.nmd + 64)) return LF_ERR_NOMEM;
+    lf_sam_record *hr = (lf_sam_record *)es.h_recs.reserve((es.nrec + 1) * sizeof(lf_sam_record));
+    if (!hr) return LF_ERR_NOMEM;
+    E.rec_off = es.d_rec_off.as<uint64_t>(); E.cig_off = es.d_cig_off.as<uint64_t>(); E.md_off = es.d_md_off.as<uint64_t>();
+    E.recs = es.d_recs.as<lf_sam_record>(); E.text = es.d_text.as<char>(); E.out_base = out_base;
+    { auto kern = k_emit_slots<true>; LFB_LAUNCH(kern, (unsigned)es.n, LF_EMIT_BLOCK, 0, st, E); }
+    if (lfb_d2h(hr, es.d_recs.p, es.nrec * sizeof(lf_sam_record), st) || lfb_d2h(text_dst, es.d_text.p, es.ncig + es.nmd, st)) return LF_ERR_CUDA;
+    return 0;
+}
+
+/* the early emit (chains no trigger fired for) runs on its own host thread and stream while rounds 2-3 go on */
+struct EarlyEmit {
+    std::thread th;
+    char *text = nullptr; size_t cap = 0;
+    int rc = 0;
+    void join() { if (th.joinable()) th.join(); }
+    ~EarlyEmit() { join(); if (text) g_result_pool_pinned.put(text, cap); }
+};
 
 } // namespace
 
@@ -348,7 +418,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     int rc;
     const double tm0 = now_ms();
 #define LF_CH(expr) do { rc = (expr); if (rc != 0) { delete R; return rc; } } while (0)
-    /* CIGAR / MD assembly runs on the GPU (k_emit_chains) when the context drives one device; a context over
+    /* CIGAR / MD assembly runs on the GPU (k_emit_slots) when the context drives one device; a context over
      * several devices assembles on host threads from the 2-bit op stream (LF_CHAIN_HOST_EMIT=1 forces that). */
     const bool gpu_emit = ctx->devs.size() == 1 && !getenv("LF_CHAIN_HOST_EMIT");
     g_result_pool_pinned.pinned = true;
@@ -445,6 +515,21 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             }
         }
     });
+    /* per-chain inputs of the GPU emit that are known now */
+    std::vector<uint64_t> slot_base;   /* a chain of n anchors has n + 1 slots: head, n - 1 gaps, tail */
+    std::vector<uint8_t> guards;
+    size_t n_slots = 0;
+    if (gpu_emit) {
+        DevState &d = ctx->devs[0];
+        slot_base.resize(n_chains + 1); guards.resize(n_chains + 1);
+        for (size_t c = 0; c <= n_chains; c++) slot_base[c] = gap_base[c] + c;
+        for (size_t c = 0; c < n_chains; c++) guards[c] = (uint8_t)((plan[c].head_guard ? 1 : 0) | (plan[c].tail_guard ? 2 : 0));
+        n_slots = (size_t)slot_base[n_chains];
+        if (S.d_task_base.reserve((n_chains + 1) * 8) || S.d_slot_base.reserve((n_chains + 1) * 8) || S.d_guards.reserve(n_chains + 64)
+            || S.d_slot_info.reserve((n_slots + 1) * sizeof(LfSlotInfo)) || S.d_slot_task.reserve((n_slots + 1) * 4)) { delete R; return LF_ERR_NOMEM; }
+        if (lfb_h2d(S.d_task_base.p, task_base.data(), (n_chains + 1) * 8, d.stream) || lfb_h2d(S.d_slot_base.p, slot_base.data(), (n_chains + 1) * 8, d.stream)
+            || lfb_h2d(S.d_guards.p, guards.data(), n_chains, d.stream)) { delete R; return LF_ERR_CUDA; }
+    }
     size_t cap1 = 64;
     for (size_t c = 0; c < n_chains; c++) cap1 += nslot[c] * 4;
     uint8_t *ops1 = gpu_emit ? nullptr : (uint8_t *)S.ops1.reserve(cap1 + 64);
@@ -469,9 +554,10 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<ClipInfo> clips;
     std::vector<SplitInfo> splits;
     std::vector<int32_t> gap_split(total_seeds, -1);
+    std::vector<uint32_t> dirty_list, clean_list;   /* chains a trigger fired for (ascending), and the others */
     {   /* every thread scans a contiguous range of chains into its own lists; indices are rebased when the
          * lists are concatenated in thread (= chain) order, so the result equals the serial scan */
-        struct Local { std::vector<lf_extend_task> e2; std::vector<ClipInfo> clips; std::vector<SplitInfo> splits; size_t c_lo = 0, c_hi = 0; };
+        struct Local { std::vector<lf_extend_task> e2; std::vector<ClipInfo> clips; std::vector<SplitInfo> splits; std::vector<uint32_t> dirty; size_t c_lo = 0, c_hi = 0; };
         const unsigned nt = n_chains < 256 ? 1u : nthreads;
         std::vector<Local> loc(nt);
         parallel_for(n_chains, nt, [&](unsigned tid, size_t lo, size_t hi) {
@@ -482,6 +568,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                 const uint32_t n = ch.n_seeds;
                 const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
                 ChainPlan &p = plan[c];
+                const size_t e2_before = Lc.e2.size();
                 if (p.head_task >= 0) {
                     const lf_align_task &t = t1[(size_t)p.head_task];
                     const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.head_task);
@@ -515,6 +602,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                         Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true));
                     }
                 }
+                if (Lc.e2.size() != e2_before) Lc.dirty.push_back((uint32_t)c);   /* a trigger fired: rounds 2-3 decide this chain */
             }
         });
         for (Local &Lc : loc) {
@@ -522,6 +610,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             for (ClipInfo ci : Lc.clips) { ci.ext += be; clips.push_back(ci); }
             for (SplitInfo si : Lc.splits) { si.ext_f += be; si.ext_r += be; splits.push_back(si); }
             e2.insert(e2.end(), Lc.e2.begin(), Lc.e2.end());
+            dirty_list.insert(dirty_list.end(), Lc.dirty.begin(), Lc.dirty.end());
             if (bc || bs) {
                 for (size_t c = Lc.c_lo; c < Lc.c_hi; c++) {
                     if (plan[c].head_clip >= 0) plan[c].head_clip += bc;
@@ -530,6 +619,44 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                 }
             }
         }
+    }
+    /* ---- chains no trigger fired for are final after round 1: their CIGAR / MD assembly (its own stream and
+     *      host thread) overlaps rounds 2-3 ---- */
+    EarlyEmit early;
+    LfEmitDev E0;
+    memset(&E0, 0, sizeof E0);
+    size_t clean_slots = 0;
+    if (gpu_emit) {
+        DevState &d = ctx->devs[0];
+        clean_list.reserve(n_chains - dirty_list.size());
+        { size_t k = 0; for (size_t c = 0; c < n_chains; c++) { if (k < dirty_list.size() && dirty_list[k] == c) { k++; continue; } clean_list.push_back((uint32_t)c); clean_slots += chains[c].n_seeds + 1; } }
+        E0.pac = d.pac.as<uint8_t>(); E0.chains = S.d_chains.as<lf_chain>(); E0.seeds = S.d_seeds.as<lf_seed>();
+        E0.read_off = d.read_off.as<uint64_t>(); E0.task_base = S.d_task_base.as<uint64_t>(); E0.slot_base = S.d_slot_base.as<uint64_t>();
+        E0.guards = S.d_guards.as<uint8_t>();
+        E0.r1 = d.res.as<lf_align_result>(); E0.ops1 = d.ops.as<uint32_t>();   /* round 3 will run in the other pair of buffers */
+        E0.slot_info = S.d_slot_info.as<LfSlotInfo>(); E0.slot_task = S.d_slot_task.as<uint32_t>();
+        EmitSet &es = S.es[0];
+#ifndef LF_EMU
+        if (!es.have_stream) { if (cudaStreamCreateWithFlags(&es.st, cudaStreamNonBlocking) != cudaSuccess) { delete R; return LF_ERR_CUDA; } es.have_stream = true; }
+#endif
+        const size_t dirty_slots = n_slots - clean_slots;
+        auto run_early = [&, dirty_slots]() {
+            if (set_dev(d)) { early.rc = LF_ERR_CUDA; return; }
+            LfEmitDev E = E0;
+            if ((early.rc = emit_size(es, E, clean_list.data(), clean_list.size())) != 0) return;
+            /* one text buffer for both lists: the late list is appended, its size estimated from this one */
+            const size_t bytes = es.ncig + es.nmd;
+            const size_t est_late = dirty_slots ? (size_t)((double)bytes * ((double)dirty_slots / (double)(clean_slots ? clean_slots : 1)) * 1.5) + (1u << 16) : 0;
+            early.text = (char *)g_result_pool_pinned.get(bytes + est_late + 1, &early.cap);
+            if (!early.text) { early.rc = LF_ERR_NOMEM; return; }
+            if ((early.rc = emit_write(es, E, early.text, 0)) != 0) return;
+            if (lfb_sync(es.st)) early.rc = LF_ERR_CUDA;
+        };
+#ifndef LF_EMU
+        early.th = std::thread(run_early);
+#else
+        run_early();   /* the emulator is single-threaded */
+#endif
     }
     std::vector<lf_extend_result> x2(e2.size());
     if (!e2.empty()) {
@@ -541,13 +668,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
 
     /* ---------------- round 3: follow-up alignments ---------------- */
     std::vector<lf_align_task> t3;
-    for (size_t c = 0; c < n_chains; c++) {
+    for (const uint32_t c : dirty_list) {
         ChainPlan &p = plan[c];
-        if (p.head_clip < 0 && p.tail_clip < 0) {
-            bool any = false;
-            for (uint64_t g = gap_base[c]; g < gap_base[c + 1] && !any; g++) any = gap_split[g] >= 0;
-            if (!any) continue;
-        }
         const lf_chain &ch = chains[c];
         const lf_seed *s = seeds + ch.seed_off;
         const uint32_t n = ch.n_seeds;
@@ -619,20 +741,26 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
 #undef LF_CH
 
     if (gpu_emit) {
-        /* ---------------- emit on the GPU: k_emit_chains (count) -> scans -> k_emit_chains (write) ---------------- */
+        /* ---------------- late emit on the GPU: the chains rounds 2-3 worked on ---------------- */
         DevState &d = ctx->devs[0];
         lfb_stream st = d.stream;
-        std::vector<uint8_t> guards(n_chains);
-        std::vector<int32_t> clipv(4 * n_chains, -1);
-        std::vector<uint32_t> split_begin(n_chains + 1, 0);
-        std::vector<LfSplitDev> sdev;
-        for (size_t c = 0; c < n_chains; c++) {
-            const ChainPlan &p = plan[c];
-            guards[c] = (uint8_t)((p.head_guard ? 1 : 0) | (p.tail_guard ? 2 : 0));
-            if (p.head_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.head_clip]; clipv[4 * c + 0] = ci.t3; clipv[4 * c + 1] = ci.qle; }
-            if (p.tail_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.tail_clip]; clipv[4 * c + 2] = ci.t3; clipv[4 * c + 3] = ci.qle; }
-            split_begin[c] = (uint32_t)sdev.size();
-            if (p.head_clip >= 0 || p.tail_clip >= 0 || true) {
+        EmitSet &es0 = S.es[0], &es1 = S.es[1];
+        es1.st = st;
+#define LF_G(expr) do { if ((expr) != 0) { delete R; return fail(ctx, LF_ERR_CUDA, #expr); } } while (0)
+        LfEmitDev E1 = E0;
+        const size_t n_dirty = dirty_list.size();
+        if (n_dirty) {
+            std::vector<int32_t> clipv(4 * n_chains, -1);
+            std::vector<uint32_t> split_begin(n_chains + 1, 0);
+            std::vector<LfSplitDev> sdev;
+            size_t k = 0;
+            for (size_t c = 0; c < n_chains; c++) {
+                split_begin[c] = (uint32_t)sdev.size();
+                if (k >= n_dirty || dirty_list[k] != c) continue;
+                k++;
+                const ChainPlan &p = plan[c];
+                if (p.head_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.head_clip]; clipv[4 * c + 0] = ci.t3; clipv[4 * c + 1] = ci.qle; }
+                if (p.tail_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.tail_clip]; clipv[4 * c + 2] = ci.t3; clipv[4 * c + 3] = ci.qle; }
                 for (uint64_t g = gap_base[c]; g < gap_base[c + 1]; g++) {
                     if (gap_split[g] < 0) continue;
                     const SplitInfo &si = splits[(size_t)gap_split[g]];
@@ -648,55 +776,55 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     sdev.push_back(v);
                 }
             }
-        }
-        split_begin[n_chains] = (uint32_t)sdev.size();
-#define LF_G(expr) do { if ((expr) != 0) { delete R; return fail(ctx, LF_ERR_CUDA, #expr); } } while (0)
-        LF_G(S.d_task_base.reserve((n_chains + 1) * 8)); LF_G(S.d_guards.reserve(n_chains + 64)); LF_G(S.d_clip.reserve(4 * n_chains * 4 + 64));
-        LF_G(S.d_split_begin.reserve((n_chains + 1) * 4)); LF_G(S.d_splits.reserve((sdev.size() + 1) * sizeof(LfSplitDev)));
-        LF_G(S.d_nrec.reserve(n_chains * 4 + 64)); LF_G(S.d_cigb.reserve(n_chains * 4 + 64)); LF_G(S.d_mdb.reserve(n_chains * 4 + 64));
-        LF_G(S.d_rec_off.reserve((n_chains + 1) * 8)); LF_G(S.d_cig_off.reserve((n_chains + 1) * 8)); LF_G(S.d_md_off.reserve((n_chains + 1) * 8));
-        LF_G(lfb_h2d(S.d_task_base.p, task_base.data(), (n_chains + 1) * 8, st)); LF_G(lfb_h2d(S.d_guards.p, guards.data(), n_chains, st));
-        LF_G(lfb_h2d(S.d_clip.p, clipv.data(), 4 * n_chains * 4, st)); LF_G(lfb_h2d(S.d_split_begin.p, split_begin.data(), (n_chains + 1) * 4, st));
-        if (!sdev.empty()) LF_G(lfb_h2d(S.d_splits.p, sdev.data(), sdev.size() * sizeof(LfSplitDev), st));
-        LfEmitDev E;
-        memset(&E, 0, sizeof E);
-        E.pac = d.pac.as<uint8_t>(); E.chains = S.d_chains.as<lf_chain>(); E.seeds = S.d_seeds.as<lf_seed>(); E.n_chains = (uint32_t)n_chains;
-        E.read_off = d.read_off.as<uint64_t>(); E.task_base = S.d_task_base.as<uint64_t>(); E.guards = S.d_guards.as<uint8_t>();
-        E.clip = S.d_clip.as<int32_t>(); E.split_begin = S.d_split_begin.as<uint32_t>(); E.splits = S.d_splits.as<LfSplitDev>();
-        E.r1 = d.res_keep.as<lf_align_result>(); E.ops1 = d.ops_keep.as<uint32_t>();
-        E.r3 = d.res.as<lf_align_result>(); E.ops3 = d.ops.as<uint32_t>();
-        E.nrec = S.d_nrec.as<uint32_t>(); E.cig_bytes = S.d_cigb.as<uint32_t>(); E.md_bytes = S.d_mdb.as<uint32_t>();
-        const unsigned grid = (unsigned)((n_chains + 127) / 128);
-        { auto kern = k_emit_chains<false>; LFB_LAUNCH(kern, grid, 128, 0, st, E); }
-        LF_G(lfb_scan_excl_total(d.tmp, E.nrec, S.d_rec_off.as<unsigned long long>(), n_chains, st));
-        LF_G(lfb_scan_excl_total(d.tmp, E.cig_bytes, S.d_cig_off.as<unsigned long long>(), n_chains, st));
-        LF_G(lfb_scan_excl_total(d.tmp, E.md_bytes, S.d_md_off.as<unsigned long long>(), n_chains, st));
-        unsigned long long *tot = (unsigned long long *)d.pinned; /* three totals */
-        LF_G(lfb_d2h(&tot[0], S.d_rec_off.as<unsigned long long>() + n_chains, 8, st));
-        LF_G(lfb_d2h(&tot[1], S.d_cig_off.as<unsigned long long>() + n_chains, 8, st));
-        LF_G(lfb_d2h(&tot[2], S.d_md_off.as<unsigned long long>() + n_chains, 8, st));
-        LF_G(lfb_sync(st));
-        const size_t nrec = (size_t)tot[0], ncig = (size_t)tot[1], nmd = (size_t)tot[2];
-        LF_G(S.d_recs.reserve((nrec + 1) * sizeof(lf_sam_record))); LF_G(S.d_text.reserve(ncig + nmd + 64));
-        E.rec_off = S.d_rec_off.as<uint64_t>(); E.cig_off = S.d_cig_off.as<uint64_t>(); E.md_off = S.d_md_off.as<uint64_t>();
-        E.recs = S.d_recs.as<lf_sam_record>(); E.text = S.d_text.as<char>(); E.md_region = ncig;
-        { auto kern = k_emit_chains<true>; LFB_LAUNCH(kern, grid, 128, 0, st, E); }
+            split_begin[n_chains] = (uint32_t)sdev.size();
+            LF_G(S.d_clip.reserve(4 * n_chains * 4 + 64)); LF_G(S.d_split_begin.reserve((n_chains + 1) * 4)); LF_G(S.d_splits.reserve((sdev.size() + 1) * sizeof(LfSplitDev)));
+            LF_G(lfb_h2d(S.d_clip.p, clipv.data(), 4 * n_chains * 4, st)); LF_G(lfb_h2d(S.d_split_begin.p, split_begin.data(), (n_chains + 1) * 4, st));
+            if (!sdev.empty()) LF_G(lfb_h2d(S.d_splits.p, sdev.data(), sdev.size() * sizeof(LfSplitDev), st));
+            E1.clip = S.d_clip.as<int32_t>(); E1.split_begin = S.d_split_begin.as<uint32_t>(); E1.splits = S.d_splits.as<LfSplitDev>();
+            E1.r3 = d.res.as<lf_align_result>(); E1.ops3 = d.ops.as<uint32_t>();
+            LF_G(emit_size(es1, E1, dirty_list.data(), n_dirty));
+        } else { es1.n = es1.nrec = es1.ncig = es1.nmd = 0; }
+        early.join();
+        if (early.rc != 0) { delete R; return fail(ctx, early.rc, "early emit"); }
+        const size_t bytes0 = es0.n ? es0.ncig + es0.nmd : 0, bytes1 = es1.ncig + es1.nmd;
         R->pinned = true;
-        R->n_recs = nrec; R->text_bytes = ncig + nmd;
-        R->recs = (lf_sam_record *)g_result_pool_pinned.get((nrec + 1) * sizeof(lf_sam_record), &R->recs_cap);
-        R->text = (char *)g_result_pool_pinned.get(ncig + nmd + 1, &R->text_cap);
-        if (!R->recs || !R->text) { delete R; return LF_ERR_NOMEM; }
-        LF_G(lfb_d2h(R->recs, S.d_recs.p, nrec * sizeof(lf_sam_record), st));
-        LF_G(lfb_d2h(R->text, S.d_text.p, ncig + nmd, st));
-        LF_G(lfb_sync(st));
+        R->text = early.text; R->text_cap = early.cap; early.text = nullptr;
+        if (!R->text || bytes0 + bytes1 + 1 > R->text_cap) {   /* the estimate fell short (or there was no early list): move to a bigger buffer */
+            size_t cap = 0;
+            char *nt = (char *)g_result_pool_pinned.get(bytes0 + bytes1 + 1, &cap);
+            if (!nt) { delete R; return LF_ERR_NOMEM; }
+            if (R->text) {
+                parallel_for(bytes0, nthreads, [&](unsigned, size_t lo, size_t hi) { memcpy(nt + lo, R->text + lo, hi - lo); }, 1 << 20);
+                g_result_pool_pinned.put(R->text, R->text_cap);
+            }
+            R->text = nt; R->text_cap = cap;
+        }
+        if (n_dirty) { LF_G(emit_write(es1, E1, R->text + bytes0, bytes0)); LF_G(lfb_sync(st)); }
         LF_G(lfb_last_error());
 #undef LF_G
+        /* records of the two lists, merged back into chain order */
+        const size_t nrec = (es0.n ? es0.nrec : 0) + es1.nrec;
+        R->n_recs = nrec; R->text_bytes = bytes0 + bytes1;
+        R->recs = (lf_sam_record *)g_result_pool_pinned.get((nrec + 1) * sizeof(lf_sam_record), &R->recs_cap);
+        if (!R->recs) { delete R; return LF_ERR_NOMEM; }
+        {
+            const lf_sam_record *a = (const lf_sam_record *)es0.h_recs.p, *b = (const lf_sam_record *)es1.h_recs.p;
+            const size_t na = es0.n ? es0.nrec : 0, nb = es1.nrec;
+            size_t ia = 0, ib = 0, o = 0;
+            while (ia < na && ib < nb) {
+                if (a[ia].chain_id < b[ib].chain_id) { const uint32_t c = a[ia].chain_id; while (ia < na && a[ia].chain_id == c) R->recs[o++] = a[ia++]; }
+                else { const uint32_t c = b[ib].chain_id; while (ib < nb && b[ib].chain_id == c) R->recs[o++] = b[ib++]; }
+            }
+            if (ia < na) { memcpy(R->recs + o, a + ia, (na - ia) * sizeof(lf_sam_record)); o += na - ia; }
+            if (ib < nb) { memcpy(R->recs + o, b + ib, (nb - ib) * sizeof(lf_sam_record)); o += nb - ib; }
+        }
         std::swap(d.res, d.res_keep); std::swap(d.ops, d.ops_keep); /* hand the bigger pair back to the next round 1 */
         ctx->stats.kernel_launches = lfb_launches;
         R->stats.records = nrec;
         const double tm4 = now_ms();
         R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm4 - tm3); R->stats.ms_merge = 0.f;
-        if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] gpu emit: tasks %.2f r1 %.2f r23 %.2f emit %.2f (recs %zu, text %zu MB)\n", tm1 - tm0, tm2 - tm1, tm3 - tm2, tm4 - tm3, nrec, (ncig + nmd) >> 20);
+        if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] gpu emit: tasks %.2f r1 %.2f r23 %.2f late emit %.2f (chains %zu early + %zu late, recs %zu, text %zu MB)\n",
+                                              tm1 - tm0, tm2 - tm1, tm3 - tm2, tm4 - tm3, clean_list.size(), n_dirty, nrec, (bytes0 + bytes1) >> 20);
         *out = R;
         return LF_OK;
     }

@@ -1164,82 +1164,119 @@ __global__ void __launch_bounds__(256) k_int32_peak(uint32_t *out, int iters, ui
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* k_emit_chains: the reference's CIGAR / MD accumulation on the GPU       */
+/* k_emit_slots: the reference's CIGAR / MD accumulation on the GPU        */
 /* ------------------------------------------------------------------------------------------ */
-/* One thread per chain walks the chain exactly as alignChain_edlib does (src/LordFAST.cpp:1820-2249),
- * reading the 2-bit op streams of the round-1 and round-3 alignments, and produces run-length CIGAR
- * (edlibCigar_toString :1596-1626) and MD (edlibMD_toString :1717-1763) text.  Two passes with the same
- * code: WRITE = false counts records and bytes per chain, a scan places them, WRITE = true writes.
- * CIGARs and MDs go to two regions of one text buffer so both can be built in one sweep. */
-__device__ __forceinline__ void lf_prefetch(const void *p)
-{ /* pull a line towards L1 without blocking: the emit walk is one dependent miss after another otherwise */
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#else
-    (void)p;
-#endif
-}
-
+/* alignChain_edlib (src/LordFAST.cpp:1820-2249) appends, per chain: the head alignment, then for every
+ * anchor its match run and the alignment of the gap behind it, then the tail, into run-length CIGAR
+ * (edlibCigar_toString :1596-1626) and MD (edlibMD_toString :1717-1763) text.  That is a serial walk of
+ * ~12 k ops per 10 kbp chain; here it is cut into SLOTS -- slot 0 = head, slot k = anchor k-1 and the gap
+ * behind it, slot n = last anchor + tail -- with one block per chain and one thread per slot.
+ *
+ * What couples neighbouring slots is small, because every slot but the head starts with an anchor's match
+ * run: (a) a run of 'M' left open at the end of a slot merges with that match run, so its length is handed on
+ * (carry_c), and (b) the matches counted since the last MD event are handed on the same way (carry_m).  A slot
+ * that consists of matches only passes both through.  Only the digits of the first number a slot writes depend
+ * on the carry.  Two kernels, same walk:
+ *   k_emit_slots<false>  walks every slot with carry 0, resolves the carries inside the block, sizes every
+ *                        slot's text, scans the sizes, and stores (carry_c, carry_m, off_c, off_m, task) per slot
+ *                        plus records / bytes per chain;
+ *   (host: three scans over the per-chain totals place the chains)
+ *   k_emit_slots<true>   walks again with the stored carries and writes the text in place; thread 0 then
+ *                        assembles the chain's records (a split gap closes one record and opens the next;
+ *                        records with fewer than two anchors are dropped, :1991 / :2063).
+ * CIGARs and MDs go to two regions of one text buffer. */
 struct LfSplitDev {
     uint32_t gap_i;                                  /* index of the seed before the gap, inside its chain */
     int32_t t_first, t_mid_r, t_second;              /* round-3 task indices or -1 */
     uint32_t qs2, ts2, qe2, te2;
     uint32_t split, inv;                             /* extensions did not cross / inversion accepted (host decides, double math) */
 };
+struct LfSlotInfo { uint32_t carry_c, carry_m, off_c, off_m; };
 struct LfEmitDev {
     const uint8_t *pac;
     const lf_chain *chains; const lf_seed *seeds; uint32_t n_chains;
+    const uint32_t *chain_list;    /* block b works on chain chain_list[b] (nullptr: chain b); per-list arrays are indexed by b */
     const uint64_t *read_off;
     const uint64_t *task_base;     /* round-1 task index of the chain's first task */
+    const uint64_t *slot_base;     /* sum of (n_seeds + 1) over the chains before this one */
     const uint8_t *guards;         /* bit 0: head aligned, bit 1: tail aligned (else soft clip) */
-    const int32_t *clip;           /* 4 per chain: head t3, head qle, tail t3, tail qle (t3 < 0: keep the round-1 alignment) */
-    const uint32_t *split_begin;   /* n_chains + 1 */
+    const int32_t *clip;           /* 4 per chain: head t3, head qle, tail t3, tail qle (t3 < 0: keep the round-1 alignment); nullptr: none */
+    const uint32_t *split_begin;   /* n_chains + 1; nullptr: no chain of the list has a split */
     const LfSplitDev *splits;
     const lf_align_result *r1; const uint32_t *ops1;
     const lf_align_result *r3; const uint32_t *ops3;
-    /* pass 1 out */
+    LfSlotInfo *slot_info; uint32_t *slot_task;   /* per slot, written by the sizing pass */
+    /* sizing pass out, per list entry */
     uint32_t *nrec, *cig_bytes, *md_bytes;
-    /* pass 2 in/out */
+    /* writing pass in/out; rec_off / cig_off / md_off are exclusive scans over the list with the total last */
     const uint64_t *rec_off, *cig_off, *md_off;
-    lf_sam_record *recs; char *text; uint64_t md_region;
+    lf_sam_record *recs; char *text;   /* this list's records and text: all CIGARs, then all MDs */
+    uint64_t out_base;                 /* offset of text[0] in the caller-visible text buffer (goes into the records) */
 };
 
+__device__ __forceinline__ uint32_t lf_ndigits(uint32_t u)
+{
+    return u < 10u ? 1u : u < 100u ? 2u : u < 1000u ? 3u : u < 10000u ? 4u : u < 100000u ? 5u : u < 1000000u ? 6u : u < 10000000u ? 7u : u < 100000000u ? 8u : u < 1000000000u ? 9u : 10u;
+}
+
+/* Text builder of one slot.  WRITE = false only counts, and leaves out the digits of the first CIGAR number
+ * and of the first MD number when they depend on the carry (deferred: cfirst / mfirst hold the local part). */
 template <bool WRITE>
-struct LfRecDev {
-    char *cp, *mp;             /* write cursors (WRITE) */
-    uint64_t cn, mn;           /* bytes so far in this record */
-    char cch; int cnum; int cnops; int mnum; char mlast;
-    __device__ __forceinline__ void reset() { cn = 0; mn = 0; cch = 0; cnum = 0; cnops = 0; mnum = 0; mlast = '='; }
+struct LfSlotB {
+    char *cp, *mp;
+    uint32_t cn, mn;
+    char cch, mlast;
+    uint32_t cnum, cnops, mnum;
+    bool cdef, mdef;
+    uint32_t cfirst, mfirst;
+    __device__ __forceinline__ void start(bool fresh, uint32_t carry_c, uint32_t carry_m)
+    {
+        mlast = '='; cfirst = 0; mfirst = 0;
+        if (fresh) { cch = 0; cnum = 0; cnops = 0; mnum = 0; cdef = false; mdef = false; }
+        else { cch = 'M'; cnum = carry_c; cnops = 1; mnum = carry_m; cdef = !WRITE; mdef = !WRITE; }
+    }
     __device__ __forceinline__ void putc_c(char c) { if (WRITE) *cp++ = c; cn++; }
     __device__ __forceinline__ void putc_m(char c) { if (WRITE) *mp++ = c; mn++; }
     __device__ __forceinline__ void num_c(uint32_t u)
     {
+        if (!WRITE) { if (cdef) { cfirst = u; cdef = false; } else cn += lf_ndigits(u); return; }
         char t[12]; int n = 0;
         do { t[n++] = (char)('0' + u % 10u); u /= 10u; } while (u);
         while (n) putc_c(t[--n]);
     }
     __device__ __forceinline__ void num_m(uint32_t u)
     {
+        if (!WRITE) { if (mdef) { mfirst = u; mdef = false; } else mn += lf_ndigits(u); return; }
         char t[12]; int n = 0;
         do { t[n++] = (char)('0' + u % 10u); u /= 10u; } while (u);
         while (n) putc_m(t[--n]);
     }
+    __device__ __forceinline__ void flush_c(bool last)
+    {
+        if (!cnum) return;
+        num_c(cnum);
+        putc_c(((last || cnops == 0) && cch == 'I') ? 'S' : cch);
+        cnops++; cnum = 0;
+    }
     __device__ __forceinline__ void cig_run(char c, int n)
     {
         if (n <= 0) return;
-        if (c == cch) { cnum += n; return; }
-        if (cch) { num_c((uint32_t)cnum); putc_c((cnops == 0 && cch == 'I') ? 'S' : cch); cnops++; }
-        cch = c; cnum = n;
+        if (c == cch) { cnum += (uint32_t)n; return; }
+        flush_c(false);
+        cch = c; cnum = (uint32_t)n;
     }
-    __device__ __forceinline__ void md_match(int n) { if (n > 0) { mnum += n; mlast = '='; } }
+    __device__ __forceinline__ void md_match(int n) { if (n > 0) { mnum += (uint32_t)n; mlast = '='; } }
     __device__ __forceinline__ void md_ins(int n) { if (n > 0) mlast = 'I'; }
-    __device__ __forceinline__ void md_mismatch(char b) { num_m((uint32_t)mnum); mnum = 0; putc_m(b); mlast = 'X'; }
-    __device__ __forceinline__ void md_del(char b) { if (mlast != 'D') { num_m((uint32_t)mnum); mnum = 0; putc_m('^'); } putc_m(b); mlast = 'D'; }
+    __device__ __forceinline__ void md_mismatch(char b) { num_m(mnum); mnum = 0; putc_m(b); mlast = 'X'; }
+    __device__ __forceinline__ void md_del(char b) { if (mlast != 'D') { num_m(mnum); mnum = 0; putc_m('^'); } putc_m(b); mlast = 'D'; }
     __device__ __forceinline__ void run(char c, int n) { cig_run(c, n); if (c == 'I') md_ins(n); else md_match(n); }
+    /* end of a slot inside a record: a trailing I / D run cannot merge with the anchor that follows */
+    __device__ __forceinline__ void end_slot() { if (cch != 'M') { flush_c(false); cch = 0; } }
+    /* end of a record */
     __device__ __forceinline__ void finish()
     {
-        if (cnum) { num_c((uint32_t)cnum); putc_c(cch == 'I' ? 'S' : cch); }
-        num_m((uint32_t)mnum);
+        flush_c(true);
+        num_m(mnum);
         putc_c('\0'); putc_m('\0');
     }
 };
@@ -1249,8 +1286,8 @@ __device__ __forceinline__ char lf_pac_char(const uint8_t *pac, uint32_t l) { co
 
 /* ops of one alignment appended to the record; reversed = the task ran right-to-left; t0 = forward
  * reference position of the first target base covered.  Runs of matches are skipped a word at a time. */
-template <bool WRITE>
-__device__ __forceinline__ void lf_emit_segment(LfRecDev<WRITE> &B, const uint32_t *ops, const lf_align_result &r, bool reversed, const uint8_t *pac, uint32_t t0)
+template <class BT>
+__device__ __forceinline__ void lf_emit_segment(BT &B, const uint32_t *ops, const lf_align_result &r, bool reversed, const uint8_t *pac, uint32_t t0)
 {
     uint32_t tp = t0, k = 0;
     const uint32_t n = r.ops_len;
@@ -1292,8 +1329,8 @@ __device__ __forceinline__ void lf_emit_segment(LfRecDev<WRITE> &B, const uint32
 /* The accepted-inversion record: the reference appends the trailing clip to the END of the CIGAR deque but
  * to the BEGINNING of the MD deque (:2056-2057), so MD and CIGAR positions pair up out of step.  Emulated
  * index by index: cigar = I^a ops I^b, md = '-'^b '-'^a mdops. */
-template <bool WRITE>
-__device__ __forceinline__ void lf_emit_inversion(LfRecDev<WRITE> &B, const uint32_t *ops, const lf_align_result &r, const uint8_t *pac, uint32_t t0, uint32_t a, uint32_t b)
+template <class BT>
+__device__ __forceinline__ void lf_emit_inversion(BT &B, const uint32_t *ops, const lf_align_result &r, const uint8_t *pac, uint32_t t0, uint32_t a, uint32_t b)
 {
     const uint32_t n = r.ops_len, total = a + n + b;
     /* CIGAR: plain run-length of the cigar chars */
@@ -1318,152 +1355,317 @@ __device__ __forceinline__ void lf_emit_inversion(LfRecDev<WRITE> &B, const uint
     if (a + b > 0) { /* the leading '-' entries only set last = 'I' when nothing followed them */ if (total == a + b) B.mlast = 'I'; }
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(128) k_emit_chains(LfEmitDev d)
+#define LF_EMIT_BLOCK 128
+#define LF_EMIT_STAGE 12288u   /* bytes of CIGAR (and of MD) text one round of slots may stage in shared memory */
+enum { LF_SL_HEAD = 1, LF_SL_PUSH = 2, LF_SL_INV = 4, LF_SL_SPLIT = 8, LF_SL_FINAL = 16 };
+
+/* what thread 0 needs from a slot to assemble the chain's records (writing pass) */
+struct LfSlotRec {
+    uint32_t flags;
+    uint32_t endc, endm;       /* text offsets (chain-relative) just behind the part that closes a record */
+    uint32_t invc, invm;       /* ... and behind the inversion record */
+    uint32_t startc, startm;   /* ... where the record opened by a split starts */
+    int32_t ed_pre, ed_inv, ed_post;
+    uint32_t posEnd, qEnd, newpos, newqs;
+};
+
+/* exclusive prefix sum over the block; `total` = sum over all threads.  ws: LF_EMIT_BLOCK / 32 + 1 words. */
+__device__ __forceinline__ uint32_t lf_block_excl_scan(uint32_t v, uint32_t *ws, uint32_t &total)
 {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d.n_chains) return;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(LF_FULL, incl, o); if (lane >= (uint32_t)o) incl += u; }
+    __syncthreads();               /* ws may still be read from the previous scan */
+    if (lane == 31u) ws[wid] = incl;
+    __syncthreads();
+    uint32_t base = 0; total = 0;
+#pragma unroll
+    for (int w = 0; w < LF_EMIT_BLOCK / 32; w++) { const uint32_t t = ws[w]; if ((uint32_t)w < wid) base += t; total += t; }
+    return base + incl - v;
+}
+
+/* block-wide copy of len bytes from shared memory to global memory; src and dst agree modulo 16 */
+__device__ __forceinline__ void lf_stage_copy_out(char *dst, const char *src, uint32_t len)
+{
+    const uint32_t tid = threadIdx.x;
+    uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    if (head > len) head = len;
+    if (tid < head) dst[tid] = src[tid];
+    const uint32_t body = (len - head) >> 4;
+    const uint4 *s4 = (const uint4 *)(src + head);
+    uint4 *d4 = (uint4 *)(dst + head);
+    for (uint32_t x = tid; x < body; x += LF_EMIT_BLOCK) d4[x] = s4[x];
+    const uint32_t done = head + (body << 4);
+    if (tid < len - done) dst[done + tid] = src[done + tid];
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(LF_EMIT_BLOCK) k_emit_slots(LfEmitDev d)
+{
+    __shared__ uint32_t s_ws[LF_EMIT_BLOCK / 32 + 1];
+    __shared__ uint32_t s_tail_c[LF_EMIT_BLOCK], s_tail_m[LF_EMIT_BLOCK];
+    __shared__ uint8_t s_pass[LF_EMIT_BLOCK];
+    __shared__ LfSlotRec s_rec[WRITE ? LF_EMIT_BLOCK : 1];
+    __shared__ uint4 s_stage_c4[WRITE ? LF_EMIT_STAGE / 16 : 1], s_stage_m4[WRITE ? LF_EMIT_STAGE / 16 : 1];
+    char *const s_stage_c = (char *)s_stage_c4, *const s_stage_m = (char *)s_stage_m4;
+    __shared__ uint32_t s_nrec;
+    const uint32_t li = blockIdx.x, tid = threadIdx.x;
+    const uint32_t c = d.chain_list ? d.chain_list[li] : li;
     const lf_chain ch = d.chains[c];
     const lf_seed *s = d.seeds + ch.seed_off;
-    const uint32_t n = ch.n_seeds;
+    const uint32_t n = ch.n_seeds, nslots = n + 1;
     const uint32_t readLen = (uint32_t)(d.read_off[ch.read_id + 1] - d.read_off[ch.read_id]);
     const uint32_t flag_norm = ch.is_rev ? 16u : 0u, flag_opp = ch.is_rev ? 0u : 16u;
     const uint8_t guards = d.guards[c];
-    const int32_t *clip = d.clip + 4 * (size_t)c;
-    uint32_t sp = d.split_begin[c];
-    const uint32_t sp_end = d.split_begin[c + 1];
-    uint64_t tk = d.task_base[c];   /* next round-1 task of this chain */
+    int32_t clip[4] = { -1, -1, -1, -1 };
+    if (d.clip) { clip[0] = d.clip[4 * (size_t)c]; clip[1] = d.clip[4 * (size_t)c + 1]; clip[2] = d.clip[4 * (size_t)c + 2]; clip[3] = d.clip[4 * (size_t)c + 3]; }
+    const uint32_t sp_begin = d.split_begin ? d.split_begin[c] : 0u, sp_end = d.split_begin ? d.split_begin[c + 1] : 0u;
+    const uint64_t task0 = d.task_base[c], slot0 = d.slot_base[c];
+    /* does the chain's first record die at gap 0 (fewer than two anchors)? */
+    bool head_dropped = false;
+    for (uint32_t sp = sp_begin; sp < sp_end; sp++) if (d.splits[sp].split) { head_dropped = d.splits[sp].gap_i == 0; break; }
 
-    LfRecDev<WRITE> B;
-    B.reset();
-    uint64_t rec_i = 0, cig_base = 0, md_base = 0;   /* WRITE: where this chain's output starts */
-    uint32_t nrec = 0;
-    uint64_t cig_tot = 0, md_tot = 0;
-    if (WRITE) {
-        rec_i = d.rec_off[c]; cig_base = d.cig_off[c]; md_base = d.md_region + d.md_off[c];
-        B.cp = d.text + cig_base; B.mp = d.text + md_base;
-    }
-    uint32_t flag = flag_norm, pos = s[0].tPos, qStart = s[0].qPos, posEnd = 0, qEnd = 0;
-    int32_t editScore = 0;
-#define LF_PUSH(FLAG, POS, POSEND, QS, QE, NM) do { \
-        B.finish(); \
-        if (WRITE) { lf_sam_record rr_; rr_.chain_id = c; rr_.flag = (FLAG); rr_.pos = (POS); rr_.posEnd = (POSEND); rr_.qStart = (QS); rr_.qEnd = (QE); rr_.nmCount = (NM); \
-            rr_.cigar_off = cig_base + cig_tot; rr_.cigar_len = (uint32_t)(B.cn - 1); rr_.md_off = md_base + md_tot; rr_.md_len = (uint32_t)(B.mn - 1); d.recs[rec_i + nrec] = rr_; } \
-        cig_tot += B.cn; md_tot += B.mn; nrec++; } while (0)
-    /* head (:1820-1899) */
-    const int32_t a = (int32_t)s[0].qPos;
-    if (a > 0) {
-        if (guards & 1) {
-            const uint64_t head_task = tk++;
-            if (clip[0] >= 0) {
-                const lf_align_result r = d.r3[clip[0]];
-                B.run('I', a - clip[1]);
-                lf_emit_segment<WRITE>(B, d.ops3, r, true, d.pac, s[0].tPos - (uint32_t)(r.end_location + 1));
-                editScore -= r.edit_distance;
-                pos = s[0].tPos - (uint32_t)r.end_location - 1;
-                qStart = s[0].qPos - (uint32_t)clip[1];
-            } else {
-                const lf_align_result r = d.r1[head_task];
-                lf_emit_segment<WRITE>(B, d.ops1, r, true, d.pac, s[0].tPos - (uint32_t)(r.end_location + 1));
-                editScore -= r.edit_distance;
-                pos = s[0].tPos - (uint32_t)r.end_location - 1;
-                qStart = 0;
-            }
-        } else B.run('I', a);
-    }
-    /* anchors and gaps (:1901-2137) */
-    int numAnchorsSoFar = 1;
-    uint32_t i = 0;
-    const uint64_t tk_end = d.task_base[c + 1];
-    lf_align_result rnext;           /* result of the chain's next round-1 task, loaded one gap ahead */
-    rnext.ops_off = 0; rnext.ops_len = 0; rnext.edit_distance = 0; rnext.end_location = 0; rnext.status = 0;
-    if (tk < tk_end) rnext = d.r1[tk];
-    for (; i + 1 < n; i++) {
-        const lf_seed si0 = s[i], si1 = s[i + 1];
-        B.run('M', (int)si0.len);
-        const uint32_t qs = si0.qPos + si0.len, ts = si0.tPos + si0.len;
-        const uint32_t qe = si1.qPos, te = si1.tPos;
-        const int32_t ql = (int32_t)(qe - qs), tl = (int32_t)(te - ts);
-        if (ql > 0 && tl > 0) {
-            const uint64_t gt = tk++;
-            const lf_align_result rcur = rnext;
-            if (tk < tk_end) {   /* next task: fetch its result now, and warm the lines its ops and reference bytes live in */
-                rnext = d.r1[tk];
-                lf_prefetch(d.ops1 + (rnext.ops_off >> 4));
-                lf_prefetch(d.pac + ((si1.tPos + si1.len) >> 2));
-                lf_prefetch(s + i + 3);
-            }
-            const LfSplitDev *sv = nullptr;
-            if (sp < sp_end && d.splits[sp].gap_i == i) sv = &d.splits[sp++];
-            if (sv && sv->split) {
-                if (sv->t_first >= 0) {
-                    const lf_align_result r = d.r3[sv->t_first];
-                    lf_emit_segment<WRITE>(B, d.ops3, r, false, d.pac, ts);
-                    editScore -= r.edit_distance;
-                }
-                B.run('I', (int)(readLen - sv->qs2));
-                posEnd = sv->ts2; qEnd = sv->qs2;
-                if (numAnchorsSoFar > 1) { LF_PUSH(flag, pos, posEnd, qStart, qEnd, editScore); if (WRITE) { B.cp = d.text + cig_base + cig_tot; B.mp = d.text + md_base + md_tot; } }
-                else if (WRITE) { B.cp = d.text + cig_base + cig_tot; B.mp = d.text + md_base + md_tot; } /* dropped record: rewind */
-                B.reset(); editScore = 0;
-                if (sv->inv) {
-                    const lf_align_result rr = d.r3[sv->t_mid_r];
-                    lf_emit_inversion<WRITE>(B, d.ops3, rr, d.pac, sv->ts2, sv->qs2, readLen - sv->qe2);
-                    LF_PUSH(flag_opp, sv->ts2, sv->te2, sv->qs2, sv->qe2, -rr.edit_distance);
-                    if (WRITE) { B.cp = d.text + cig_base + cig_tot; B.mp = d.text + md_base + md_tot; }
-                    B.reset();
-                }
-                B.run('I', (int)sv->qe2);
-                if (sv->t_second >= 0) {
-                    const lf_align_result r = d.r3[sv->t_second];
-                    lf_emit_segment<WRITE>(B, d.ops3, r, true, d.pac, sv->te2);
-                    editScore -= r.edit_distance;
-                }
-                flag = flag_norm; pos = sv->te2; qStart = sv->qe2;
-                numAnchorsSoFar = 0;
-            } else {
-                (void)gt;
-                editScore -= rcur.edit_distance;
-                lf_emit_segment<WRITE>(B, d.ops1, rcur, false, d.pac, ts);
-            }
-        } else if (ql > 0) { B.run('I', ql); editScore -= ql; }
-        else {
-            B.cig_run('D', tl);
-            for (int32_t k = 0; k < tl; k++) B.md_del(lf_pac_char(d.pac, ts + (uint32_t)k));
-            editScore -= tl;
+    /* running state across rounds of LF_EMIT_BLOCK slots (uniform over the block) */
+    uint32_t run_tasks = 0, run_c = 0, run_m = 0, run_carry_c = 0, run_carry_m = 0;
+    if (!WRITE && tid == 0) s_nrec = 0;
+    /* thread 0 only (writing pass) */
+    uint32_t cur_startc = 0, cur_startm = 0, cur_pos = 0, cur_qs = 0, rec_n = 0;
+    int32_t acc_ed = 0;
+    uint64_t cig_base = 0, md_base = 0, rec_base = 0;
+    if (WRITE) { cig_base = d.cig_off[li]; md_base = d.cig_off[d.n_chains] + d.md_off[li]; rec_base = d.rec_off[li]; }
+
+    for (uint32_t base = 0; base < nslots; base += LF_EMIT_BLOCK) {
+        const uint32_t k = base + tid;
+        const bool active = k < nslots;
+        /* ---- geometry of the slot ---- */
+        lf_seed s0; s0.tPos = 0; s0.qPos = 0; s0.len = 0;
+        lf_seed s1 = s0;
+        int32_t ql = 0, tl = 0;
+        bool has_task = false;
+        if (active) {
+            if (k == 0) { s1 = s[0]; has_task = s1.qPos > 0 && (guards & 1); }
+            else if (k < n) { s0 = s[k - 1]; s1 = s[k]; ql = (int32_t)(s1.qPos - (s0.qPos + s0.len)); tl = (int32_t)(s1.tPos - (s0.tPos + s0.len)); has_task = ql > 0 && tl > 0; }
+            else { s0 = s[n - 1]; has_task = (int32_t)readLen - (int32_t)(s0.qPos + s0.len) > 0 && (guards & 2); }
         }
-        numAnchorsSoFar++;
-    }
-    const lf_seed sl = s[i];
-    B.run('M', (int)sl.len);
-    posEnd = sl.tPos + sl.len - 1;
-    qEnd = sl.qPos + sl.len - 1;                 /* inclusive, :2155 */
-    /* tail (:2157-2230) */
-    const uint32_t qs = sl.qPos + sl.len;
-    const int32_t b = (int32_t)readLen - (int32_t)qs;
-    if (b > 0) {
-        if (guards & 2) {
-            const uint32_t ts = sl.tPos + sl.len;
-            const uint64_t tail_task = tk++;
-            if (clip[2] >= 0) {
-                const lf_align_result r = d.r3[clip[2]];
-                lf_emit_segment<WRITE>(B, d.ops3, r, false, d.pac, ts);
-                editScore -= r.edit_distance;
-                posEnd = ts + (uint32_t)r.end_location;
-                qEnd = qs + (uint32_t)clip[3];
-                B.run('I', b - clip[3]);
-            } else {
-                const lf_align_result r = d.r1[tail_task];
-                editScore -= r.edit_distance;
-                lf_emit_segment<WRITE>(B, d.ops1, r, false, d.pac, ts);
-                posEnd = ts + (uint32_t)r.end_location;
-                qEnd = readLen;
+        uint32_t trel, carry_c = 0, carry_m = 0, off_c = 0, off_m = 0;
+        if (!WRITE) {
+            uint32_t tot;
+            trel = run_tasks + lf_block_excl_scan(has_task ? 1u : 0u, s_ws, tot);
+            run_tasks += tot;
+        } else {
+            trel = 0;
+            if (active) { const LfSlotInfo si = d.slot_info[slot0 + k]; carry_c = si.carry_c; carry_m = si.carry_m; off_c = si.off_c; off_m = si.off_m; trel = d.slot_task[slot0 + k]; }
+        }
+        /* ---- where this round's text goes: staged in shared memory and copied out in 16-byte pieces when it
+         *      fits, else (long deletions, inversion records) written in place byte by byte ---- */
+        uint32_t rnd_c0 = 0, rnd_c1 = 0, rnd_m0 = 0, rnd_m1 = 0;   /* chain-relative byte span of the round */
+        bool staged = false;
+        if (WRITE) {
+            const LfSlotInfo f = d.slot_info[slot0 + base];
+            rnd_c0 = f.off_c; rnd_m0 = f.off_m;
+            if (base + LF_EMIT_BLOCK < nslots) { const LfSlotInfo g = d.slot_info[slot0 + base + LF_EMIT_BLOCK]; rnd_c1 = g.off_c; rnd_m1 = g.off_m; }
+            else { rnd_c1 = (uint32_t)(d.cig_off[li + 1] - d.cig_off[li]); rnd_m1 = (uint32_t)(d.md_off[li + 1] - d.md_off[li]); }
+            staged = rnd_c1 - rnd_c0 + 16u <= LF_EMIT_STAGE && rnd_m1 - rnd_m0 + 16u <= LF_EMIT_STAGE;
+        }
+        /* a staged byte sits at the same address modulo 16 as its destination, so the copy-out is aligned */
+        const uint32_t sk_c = WRITE ? (uint32_t)((uintptr_t)(d.text + cig_base + rnd_c0) & 15u) : 0u, sk_m = WRITE ? (uint32_t)((uintptr_t)(d.text + md_base + rnd_m0) & 15u) : 0u;
+        /* ---- walk: every part of a slot is  run(c1, n1) . [alignment ops | deleted bases] . run(c3, n3) ---- */
+        LfSlotB<WRITE> B;
+        B.cn = 0; B.mn = 0; B.cp = nullptr; B.mp = nullptr;
+        if (WRITE) {
+            if (staged) { B.cp = s_stage_c + sk_c + (off_c - rnd_c0); B.mp = s_stage_m + sk_m + (off_m - rnd_m0); }
+            else { B.cp = d.text + cig_base + off_c; B.mp = d.text + md_base + off_m; }
+        }
+        uint32_t flags = 0;
+        uint32_t pre_c = 0, pre_m = 0, inv_c = 0, inv_m = 0;     /* bytes behind the pre part / the inversion record */
+        uint32_t cfirst = 0, mfirst = 0; bool cclosed = false, mclosed = false;
+        uint32_t tail_c = 0, tail_m = 0; bool pass_c = false, pass_m = false;
+        int32_t ed_pre = 0, ed_inv = 0, ed_post = 0;
+        uint32_t posEnd = 0, qEnd = 0, newpos = 0, newqs = 0;
+        uint32_t my_nrec = 0;
+        if (active) {
+            const uint64_t task = task0 + trel;
+            /* part descriptors: [0] belongs to the record the slot starts in, [1] to the record a split opens */
+            bool on[2] = { false, false }, fresh[2] = { false, true }, fin[2] = { false, false }, rev[2] = { false, false };
+            char c1[2] = { 'M', 'I' }, c3[2] = { 'I', 'I' };
+            int32_t n1[2] = { 0, 0 }, n3[2] = { 0, 0 }, seg[2] = { 0, 0 }, dtl = 0;   /* seg: 0 none, 1 round-1 ops, 3 round-3 ops, 2 deleted bases */
+            int32_t rix[2] = { 0, 0 };
+            uint32_t t0[2] = { 0, 0 };
+            const LfSplitDev *sv = nullptr;
+            if (k == 0) {                                   /* head (:1820-1899) */
+                flags |= LF_SL_HEAD;
+                newpos = s1.tPos; newqs = s1.qPos;
+                const int32_t a = (int32_t)s1.qPos;
+                fresh[0] = true; c1[0] = 'I';
+                if (a > 0 && !head_dropped) {
+                    on[0] = true;
+                    if (guards & 1) {
+                        rev[0] = true;
+                        if (clip[0] >= 0) { n1[0] = a - clip[1]; seg[0] = 3; rix[0] = clip[0]; newqs = s1.qPos - (uint32_t)clip[1]; }
+                        else { seg[0] = 1; newqs = 0; }
+                    } else n1[0] = a;
+                }
+            } else if (k < n) {                             /* anchor k-1 and the gap behind it (:1901-2137) */
+                const uint32_t i = k - 1;
+                const uint32_t ts = s0.tPos + s0.len;
+                uint32_t svi = 0;
+                if (has_task) for (uint32_t sp = sp_begin; sp < sp_end; sp++) if (d.splits[sp].gap_i == i) { sv = &d.splits[sp]; svi = sp; break; }
+                if (sv && !sv->split) sv = nullptr;
+                n1[0] = (int32_t)s0.len; t0[0] = ts;
+                if (sv) {
+                    flags |= LF_SL_SPLIT;
+                    /* anchors in the record this gap closes, and in the one it opens: fewer than two -> dropped */
+                    bool drop_pre = i == 0, drop_post = false;
+                    for (uint32_t sp = svi; sp > sp_begin; sp--) if (d.splits[sp - 1].split) { drop_pre = i - d.splits[sp - 1].gap_i <= 1u; break; }
+                    for (uint32_t sp = svi + 1; sp < sp_end; sp++) if (d.splits[sp].split) { drop_post = d.splits[sp].gap_i == i + 1u; break; }
+                    posEnd = sv->ts2; qEnd = sv->qs2; newpos = sv->te2; newqs = sv->qe2;
+                    on[0] = !drop_pre; fin[0] = true;
+                    if (sv->t_first >= 0) { seg[0] = 3; rix[0] = sv->t_first; }
+                    n3[0] = (int32_t)(readLen - sv->qs2);
+                    on[1] = !drop_post;
+                    n1[1] = (int32_t)sv->qe2;
+                    if (sv->t_second >= 0) { seg[1] = 3; rix[1] = sv->t_second; rev[1] = true; t0[1] = sv->te2; }
+                } else {
+                    on[0] = true;
+                    if (has_task) seg[0] = 1;
+                    else if (ql > 0) { n3[0] = ql; ed_pre -= ql; }
+                    else { seg[0] = 2; dtl = tl; ed_pre -= tl; }
+                }
+            } else {                                        /* last anchor and the tail (:2139-2230) */
+                flags |= LF_SL_FINAL;
+                on[0] = true; fin[0] = true;
+                n1[0] = (int32_t)s0.len;
+                posEnd = s0.tPos + s0.len - 1;
+                qEnd = s0.qPos + s0.len - 1;                /* inclusive, :2155 */
+                const uint32_t qs = s0.qPos + s0.len;
+                const int32_t b = (int32_t)readLen - (int32_t)qs;
+                t0[0] = s0.tPos + s0.len;
+                if (b > 0) {
+                    if (guards & 2) {
+                        if (clip[2] >= 0) { seg[0] = 3; rix[0] = clip[2]; qEnd = qs + (uint32_t)clip[3]; n3[0] = b - clip[3]; }
+                        else { seg[0] = 1; qEnd = readLen; }
+                    } else n3[0] = b;
+                }
             }
-        } else B.run('I', b);
+#pragma unroll 1
+            for (int p = 0; p < 2; p++) {
+                if (p == 1) {
+                    pre_c = B.cn; pre_m = B.mn;
+                    if (sv && sv->inv) {                    /* the inversion record sits between the two parts */
+                        const lf_align_result rr = d.r3[sv->t_mid_r];
+                        B.start(true, 0, 0);
+                        lf_emit_inversion(B, d.ops3, rr, d.pac, sv->ts2, sv->qs2, readLen - sv->qe2);
+                        B.finish();
+                        ed_inv = -rr.edit_distance;
+                        flags |= LF_SL_INV; my_nrec++;
+                    }
+                    inv_c = B.cn; inv_m = B.mn;
+                }
+                if (!on[p]) continue;
+                B.start(fresh[p], carry_c, carry_m);
+                B.run(c1[p], n1[p]);
+                if (seg[p] == 2) {
+                    B.cig_run('D', dtl);
+                    for (int32_t x = 0; x < dtl; x++) B.md_del(lf_pac_char(d.pac, t0[p] + (uint32_t)x));
+                } else if (seg[p]) {
+                    const lf_align_result r = seg[p] == 1 ? d.r1[task] : d.r3[rix[p]];
+                    const int32_t e = r.edit_distance;
+                    if (p == 0) ed_pre -= e; else ed_post -= e;
+                    uint32_t tt = t0[p];
+                    if (k == 0) { tt = s1.tPos - (uint32_t)(r.end_location + 1); newpos = tt; }
+                    else if (k == n) posEnd = tt + (uint32_t)r.end_location;
+                    lf_emit_segment(B, seg[p] == 1 ? d.ops1 : d.ops3, r, rev[p], d.pac, tt);
+                }
+                B.run(c3[p], n3[p]);
+                if (fin[p]) { B.finish(); my_nrec++; if (k < n) flags |= LF_SL_PUSH; }
+                else B.end_slot();
+                if (p == 0 && !fresh[0]) {
+                    cfirst = B.cfirst; mfirst = B.mfirst;
+                    cclosed = !WRITE && !B.cdef; mclosed = !WRITE && !B.mdef;
+                    pass_c = !WRITE && B.cdef; pass_m = !WRITE && B.mdef;
+                }
+                if (!fin[p]) { tail_c = B.cch == 'M' ? B.cnum : 0u; tail_m = B.mnum; }
+            }
+        }
+        if (!WRITE) {
+            /* ---- carries: the open 'M' run / match count at the end of the previous slot ---- */
+            s_tail_c[tid] = tail_c; s_tail_m[tid] = tail_m;
+            s_pass[tid] = (uint8_t)((pass_c ? 1 : 0) | (pass_m ? 2 : 0));
+            __syncthreads();
+            if (active) {
+                uint32_t acc = 0; int j = (int)tid - 1;
+                for (; j >= 0; j--) { acc += s_tail_c[j]; if (!(s_pass[j] & 1)) break; }
+                carry_c = j < 0 ? acc + run_carry_c : acc;
+                acc = 0; j = (int)tid - 1;
+                for (; j >= 0; j--) { acc += s_tail_m[j]; if (!(s_pass[j] & 2)) break; }
+                carry_m = j < 0 ? acc + run_carry_m : acc;
+            }
+            /* the round hands its last slot's state on */
+            const uint32_t lastt = (nslots - base < LF_EMIT_BLOCK ? nslots - base : LF_EMIT_BLOCK) - 1;
+            const uint32_t nxt_c = pass_c ? carry_c + tail_c : tail_c, nxt_m = pass_m ? carry_m + tail_m : tail_m;
+            __syncthreads();
+            if (tid == lastt) { s_tail_c[0] = nxt_c; s_tail_m[0] = nxt_m; }
+            __syncthreads();
+            run_carry_c = s_tail_c[0]; run_carry_m = s_tail_m[0];
+            /* ---- sizes and offsets ---- */
+            uint32_t bytes_c = 0, bytes_m = 0;
+            if (active) {
+                const uint32_t post_c = B.cn - inv_c, post_m = B.mn - inv_m;
+                bytes_c = pre_c + (cclosed ? lf_ndigits(carry_c + cfirst) : 0u) + (inv_c - pre_c) + post_c;
+                bytes_m = pre_m + (mclosed ? lf_ndigits(carry_m + mfirst) : 0u) + (inv_m - pre_m) + post_m;
+            }
+            uint32_t tot_c, tot_m;
+            const uint32_t oc = run_c + lf_block_excl_scan(bytes_c, s_ws, tot_c);
+            const uint32_t om = run_m + lf_block_excl_scan(bytes_m, s_ws, tot_m);
+            run_c += tot_c; run_m += tot_m;
+            if (active) {
+                LfSlotInfo si; si.carry_c = carry_c; si.carry_m = carry_m; si.off_c = oc; si.off_m = om;
+                d.slot_info[slot0 + k] = si; d.slot_task[slot0 + k] = trel;
+                if (my_nrec) atomicAdd(&s_nrec, my_nrec);
+            }
+            __syncthreads();
+        } else {
+            if (staged) {   /* ---- staged text -> HBM, 16 bytes per thread and step ---- */
+                __syncthreads();
+                lf_stage_copy_out(d.text + cig_base + rnd_c0, s_stage_c + sk_c, rnd_c1 - rnd_c0);
+                lf_stage_copy_out(d.text + md_base + rnd_m0, s_stage_m + sk_m, rnd_m1 - rnd_m0);
+            }
+            /* ---- records: thread 0 walks the round's slots in order ---- */
+            LfSlotRec R;
+            R.flags = active ? flags : 0u;
+            R.endc = off_c + pre_c; R.endm = off_m + pre_m;
+            R.invc = off_c + inv_c; R.invm = off_m + inv_m;
+            R.startc = R.invc; R.startm = R.invm;
+            R.ed_pre = ed_pre; R.ed_inv = ed_inv; R.ed_post = ed_post;
+            R.posEnd = posEnd; R.qEnd = qEnd; R.newpos = newpos; R.newqs = newqs;
+            s_rec[tid] = R;
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t cnt = nslots - base < LF_EMIT_BLOCK ? nslots - base : LF_EMIT_BLOCK;
+                for (uint32_t x = 0; x < cnt; x++) {
+                    const LfSlotRec &Q = s_rec[x];
+                    if (Q.flags & LF_SL_HEAD) { cur_pos = Q.newpos; cur_qs = Q.newqs; acc_ed = Q.ed_pre; continue; }
+                    acc_ed += Q.ed_pre;
+                    if (Q.flags & (LF_SL_PUSH | LF_SL_FINAL)) {
+                        lf_sam_record rr; rr.chain_id = c; rr.flag = flag_norm; rr.pos = cur_pos; rr.posEnd = Q.posEnd; rr.qStart = cur_qs; rr.qEnd = Q.qEnd; rr.nmCount = acc_ed;
+                        rr.cigar_off = d.out_base + cig_base + cur_startc; rr.cigar_len = Q.endc - cur_startc - 1u;
+                        rr.md_off = d.out_base + md_base + cur_startm; rr.md_len = Q.endm - cur_startm - 1u;
+                        d.recs[rec_base + rec_n++] = rr;
+                    }
+                    if (Q.flags & LF_SL_INV) {
+                        lf_sam_record rr; rr.chain_id = c; rr.flag = flag_opp; rr.pos = Q.posEnd; rr.posEnd = Q.newpos; rr.qStart = Q.qEnd; rr.qEnd = Q.newqs; rr.nmCount = Q.ed_inv;
+                        rr.cigar_off = d.out_base + cig_base + Q.endc; rr.cigar_len = Q.invc - Q.endc - 1u;
+                        rr.md_off = d.out_base + md_base + Q.endm; rr.md_len = Q.invm - Q.endm - 1u;
+                        d.recs[rec_base + rec_n++] = rr;
+                    }
+                    if (Q.flags & LF_SL_SPLIT) { cur_startc = Q.startc; cur_startm = Q.startm; cur_pos = Q.newpos; cur_qs = Q.newqs; acc_ed = Q.ed_post; }
+                }
+            }
+            __syncthreads();
+        }
     }
-    LF_PUSH(flag, pos, posEnd, qStart, qEnd, editScore);
-#undef LF_PUSH
-    if (!WRITE) { d.nrec[c] = nrec; d.cig_bytes[c] = (uint32_t)cig_tot; d.md_bytes[c] = (uint32_t)md_tot; }
+    if (!WRITE && tid == 0) { d.nrec[li] = s_nrec; d.cig_bytes[li] = run_c; d.md_bytes[li] = run_m; }
 }
 
 __global__ void k_gather_ed(const lf_align_result *res, int32_t *ed, uint32_t n)

@@ -85,3 +85,46 @@ def pairs_as_batch(pairs):
         off += len(t)
     ref = np.concatenate(tcat)
     return ref, reads, np.array(tasks, dtype=api.ALIGN_TASK)
+
+
+def craft_chains(ref, seed=3):
+    """Reads stitched from reference pieces with 400 bp deletions between them, with sparse exact anchors.
+    Pieces holding a single anchor make records of fewer than two anchors, which the reference drops
+    (src/LordFAST.cpp:1991 / :2063); error-free stretches make anchor + gap units that are matches only, so
+    CIGAR / MD runs merge across many anchors.  Returns [(read, [(tPos, qPos, len), ...]), ...]."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    layouts = [[1500, 40, 1500], [40, 1500], [1500, 40], [1200, 130, 1200], [40, 40, 1500], [900, 40, 40, 900], [2000], [700, 700]]
+    for li, lay in enumerate(layouts):
+        for noisy in (0, 1, 2):
+            tpos = int(rng.integers(1000, 3000)) + 6000 * (li % 4)
+            read, seeds, qpos = [], [], 0
+            for L in lay:
+                piece = ref[tpos:tpos + L].copy()
+                anchors = [(L - 14) // 2] if L <= 60 else [10, L - 30] if L <= 140 else list(range(5, L - 20, 55))
+                prot = np.zeros(L, bool)
+                for a in anchors:
+                    prot[a:a + 14] = True
+                if noisy:
+                    cand = np.flatnonzero(~prot)
+                    k = max(1, len(cand) // (12 if noisy == 1 else 40))
+                    for x in rng.choice(cand, size=min(k, len(cand)), replace=False):
+                        piece[x] = sim.ACGT[(int(np.searchsorted(sim.ACGT, piece[x])) + 1 + int(rng.integers(0, 3))) % 4]
+                seeds += [(tpos + a, qpos + a, 14) for a in anchors]
+                read.append(piece)
+                qpos += L
+                tpos += L + 400
+            q = np.concatenate(read)
+            if noisy == 2:  # junk at both ends: the head / tail alignments and their clips take part
+                h, t = sim.ACGT[rng.integers(0, 4, size=30, dtype=np.uint8)], sim.ACGT[rng.integers(0, 4, size=25, dtype=np.uint8)]
+                q = np.concatenate([h, q, t])
+                seeds = [(a, b + 30, c) for a, b, c in seeds]
+            cases.append((q, seeds))
+    return cases
+
+
+CRAFTED_REF = (40_000, 12)  # sim.make_reference(length, seed) of the crafted chains
+
+
+def load_crafted():
+    return json.load(open(os.path.join(GOLDEN, "chains_crafted.json")))

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import _oracle as O
-from _common import build_emu, load_chains
+from _common import CRAFTED_REF, build_emu, load_chains, load_crafted
 from lordfast_b200 import api, sim
 
 
@@ -29,7 +29,7 @@ def _golden(lib_path):
     g.close()
 
 
-def _simulated(lib_path, n_reads, read_len, ref_len):
+def _simulated(lib_path, n_reads, read_len, ref_len, need_inversion=True):
     w = sim.make_workload(ref_len, n_reads, read_len, 0.12, 0.15, seed=21, sv_frac=0.6, sv_kinds=sim.SV_KINDS + ("inversion_del", "inversion_del"))
     g = api.LfGpu(w.pac, len(w.ref), lib_path=lib_path)
     seeds, chains = api.workload_chains(w)
@@ -43,9 +43,58 @@ def _simulated(lib_path, n_reads, read_len, ref_len):
             d = dict(chain=i); d.update(s); exp.append(d)
     assert got == exp
     # the accepted-inversion branch (MD / CIGAR out of step, src/LordFAST.cpp:2056-2057) is exercised
-    assert any((r["flag"] & 16) != (16 if w.is_rev[r["chain"]] else 0) for r in exp)
+    assert not need_inversion or any((r["flag"] & 16) != (16 if w.is_rev[r["chain"]] else 0) for r in exp)
     g.close()
     return st
+
+
+def _crafted(lib_path):
+    """Hand-built chains with the reference's recorded answers (tests/golden/make_crafted_chains.py): records
+    dropped for having fewer than two anchors, splits in adjacent gaps, error-free stretches."""
+    ref = sim.make_reference(*CRAFTED_REF)
+    cases = load_crafted()
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=lib_path)
+    reads = [np.frombuffer(c["read"].encode(), dtype=np.uint8) for c in cases]
+    read_off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    seeds, ch = [], []
+    for i, c in enumerate(cases):
+        ch.append((len(seeds), len(c["seeds"]), i, 0, 0))
+        seeds.extend(tuple(s) for s in c["seeds"])
+    recs, text, st = g.align_chains(np.concatenate(reads), read_off, [0], [len(ref)], np.array(seeds, dtype=api.SEED), np.array(ch, dtype=api.CHAIN))
+    got = api.records_to_dicts(recs, text)
+    exp = []
+    for ci, c in enumerate(cases):
+        for s in c["sam"]:
+            d = dict(chain=ci); d.update(s); exp.append(d)
+    assert got == exp
+    assert any(len(c["sam"]) == 2 and len(c["seeds"]) > 50 for c in cases)  # a dropped middle record is in the set
+    g.close()
+
+
+def test_oracle_crafted_chains():
+    ref = sim.make_reference(*CRAFTED_REF)
+    idx = O.RefIndex(ref.tobytes())
+    for c in load_crafted():
+        a, _ = O.oracle_align_chain(idx, [tuple(s) for s in c["seeds"]], c["read"].encode(), 0)
+        assert a == c["sam"]
+
+
+def test_emu_chain_operator_crafted(monkeypatch):
+    _crafted(build_emu())
+    monkeypatch.setenv("LF_CHAIN_HOST_EMIT", "1")
+    _crafted(build_emu())
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_crafted(monkeypatch):
+    _crafted(None)
+    monkeypatch.setenv("LF_CHAIN_HOST_EMIT", "1")
+    _crafted(None)
+
+
+def test_emu_chain_operator_long_reads():
+    """More anchors than one block has threads: the slot carries cross rounds."""
+    _simulated(build_emu(), 4, 14_000, 300_000, need_inversion=False)
 
 
 def test_emu_chain_operator_golden():
