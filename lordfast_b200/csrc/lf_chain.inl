@@ -15,6 +15,7 @@
  *
  * Included by lf_pipeline.inl (so it is part of liblfgpu.so and of the test-only emulator build).
  */
+#include <algorithm>
 #include <mutex>
 #include <thread>
 #include <time.h>
@@ -65,6 +66,8 @@ const double kClipSim = 0.75, kSplitSim = 0.40, kReverseSim = 0.60;
 
 struct SplitInfo {
     uint32_t seed_idx;     /* global index of the seed that precedes the gap */
+    uint32_t gap_i;        /* ... and its index inside the chain */
+    int32_t task;          /* the gap's round-1 task */
     int32_t ext_f, ext_r;  /* extend task indices */
     int32_t t_first, t_mid_f, t_mid_r, t_second; /* round-3 task indices or -1 */
     uint32_t qs2, ts2, qe2, te2;
@@ -75,6 +78,7 @@ struct ClipInfo { int32_t ext; int32_t t3; int32_t qle, tle; };
 struct ChainPlan {
     int32_t head_task = -1, tail_task = -1;   /* round-1 task indices */
     int32_t head_clip = -1, tail_clip = -1;   /* index into clips */
+    int32_t split_lo = 0, split_hi = 0;       /* the chain's entries in splits (gap order) */
     uint32_t chrBeg = 0, chrEnd = 0;
     bool head_guard = false, tail_guard = false;
 };
@@ -446,7 +450,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         gap_base[c + 1] = gap_base[c] + chains[c].n_seeds;
     }
     const size_t total_seeds = gap_base[n_chains];
-    std::vector<int32_t> gap_task(total_seeds, -1); /* per (chain, seed i): round-1 task of the gap after seed i, or -1 */
+    /* per (chain, seed i): round-1 task of the gap after seed i, or -1 -- only the host emit walks these */
+    std::vector<int32_t> gap_task(gpu_emit ? 0 : total_seeds, -1);
     std::vector<uint32_t> ntask(n_chains, 0);
     std::vector<uint64_t> nslot(n_chains, 0); /* op-slot words of the chain's round-1 tasks */
     bool bad_rid = false;
@@ -484,9 +489,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     const size_t n1 = task_base[n_chains];
     lf_align_task *t1 = (lf_align_task *)S.t1.reserve((n1 + 1) * sizeof(lf_align_task));
     lf_align_result *r1 = gpu_emit ? nullptr : (lf_align_result *)S.r1.reserve((n1 + 1) * sizeof(lf_align_result));
-    int32_t *ed1 = gpu_emit ? (int32_t *)S.ed1.reserve((n1 + 1) * sizeof(int32_t)) : nullptr;
-    if (!t1 || (!r1 && !ed1)) { delete R; return LF_ERR_NOMEM; }
-    auto ed_of = [&](size_t i) -> int32_t { return gpu_emit ? ed1[i] : r1[i].edit_distance; };
+    if (!t1 || (!gpu_emit && !r1)) { delete R; return LF_ERR_NOMEM; }
+    std::vector<uint32_t> trig;   /* round-1 tasks whose result fires a clip / split trigger, ascending */
     /* pass B: fill */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
         for (size_t c = lo; c < hi; c++) {
@@ -505,7 +509,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             for (uint32_t i = 0; i + 1 < n; i++) {
                 const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
                 const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
-                if (ql > 0 && tl > 0) { gap_task[gap_base[c] + i] = (int32_t)k; t1[k++] = mk_task(ch.read_id, qs, (uint32_t)ql, ts, (uint32_t)tl, strand, LF_MODE_NW); }
+                if (ql > 0 && tl > 0) { if (!gpu_emit) gap_task[gap_base[c] + i] = (int32_t)k; t1[k++] = mk_task(ch.read_id, qs, (uint32_t)ql, ts, (uint32_t)tl, strand, LF_MODE_NW); }
             }
             if (p.tail_guard) {
                 const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
@@ -539,12 +543,41 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
         LF_CH(lf_gpu_run_align(ctx));
         if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r1, ops1, cap1));
-        else { /* results and ops stay in HBM; only the distances come back for the trigger tests */
+        else { /* results and ops stay in HBM; the trigger tests run there and only the hits come back */
             DevState &d = ctx->devs[0];
-            if (S.d_ed.reserve((n1 + 1) * 4)) { delete R; return LF_ERR_NOMEM; }
-            LFB_LAUNCH(k_gather_ed, (unsigned)((n1 + 255) / 256), 256, 0, d.stream, d.res.as<lf_align_result>(), S.d_ed.as<int32_t>(), (uint32_t)n1);
-            if (lfb_d2h(ed1, S.d_ed.p, n1 * 4, d.stream) || lfb_sync(d.stream)) { delete R; return LF_ERR_CUDA; }
+            const uint32_t cap = 1u << 16;
+            if (S.d_ed.reserve(((size_t)cap + 1) * 4)) { delete R; return LF_ERR_NOMEM; }
+            uint32_t *hl = (uint32_t *)S.ed1.reserve(((size_t)cap + 1) * 4);
+            if (!hl) { delete R; return LF_ERR_NOMEM; }
+            uint32_t *dl = S.d_ed.as<uint32_t>();   /* [0]: count, [1..]: task indices */
+            if (lfb_memset(dl, 0, 4, d.stream)) { delete R; return LF_ERR_CUDA; }
+            LFB_LAUNCH(k_chain_triggers, (unsigned)((n1 + 255) / 256), 256, 0, d.stream, d.tasks.as<lf_align_task>(), d.res.as<lf_align_result>(), (uint32_t)n1, dl + 1, dl, cap);
+            if (lfb_d2h(hl, dl, 4, d.stream) || lfb_sync(d.stream)) { delete R; return LF_ERR_CUDA; }
+            size_t nt = hl[0];
+            if (nt > cap) {   /* more hits than the list holds: run again with room for all */
+                if (S.d_ed.reserve((nt + 1) * 4) || !(hl = (uint32_t *)S.ed1.reserve((nt + 1) * 4))) { delete R; return LF_ERR_NOMEM; }
+                dl = S.d_ed.as<uint32_t>();
+                if (lfb_memset(dl, 0, 4, d.stream)) { delete R; return LF_ERR_CUDA; }
+                LFB_LAUNCH(k_chain_triggers, (unsigned)((n1 + 255) / 256), 256, 0, d.stream, d.tasks.as<lf_align_task>(), d.res.as<lf_align_result>(), (uint32_t)n1, dl + 1, dl, (uint32_t)nt);
+            }
+            if (nt && (lfb_d2h(hl + 1, dl + 1, nt * 4, d.stream) || lfb_sync(d.stream))) { delete R; return LF_ERR_CUDA; }
+            trig.assign(hl + 1, hl + 1 + nt);
+            std::sort(trig.begin(), trig.end());
         }
+    }
+    if (!gpu_emit && n1) {   /* host copy of the results: the same tests, all host threads */
+        std::vector<std::vector<uint32_t>> part(nthreads);
+        parallel_for(n1, nthreads, [&](unsigned tid, size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++) {
+                const lf_align_task &t = t1[i];
+                const int32_t ed = r1[i].edit_distance, ql = (int32_t)t.q_len, tl = (int32_t)t.t_len;
+                bool hit;
+                if (t.mode == LF_MODE_SHW) hit = ql > kClipLen && (1 - ((float)ed / ql)) < kClipSim;      /* :1840 / :2175 */
+                else hit = abs(ql - tl) >= kSplitLen && (1 - ((float)ed / ql)) < kSplitSim;               /* :1952 */
+                if (hit) part[tid].push_back((uint32_t)i);
+            }
+        });
+        for (auto &v : part) trig.insert(trig.end(), v.begin(), v.end());
     }
     R->stats.round1_tasks = n1;
     const double tm2 = now_ms();
@@ -553,73 +586,52 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<lf_extend_task> e2;
     std::vector<ClipInfo> clips;
     std::vector<SplitInfo> splits;
-    std::vector<int32_t> gap_split(total_seeds, -1);
+    std::vector<int32_t> gap_split(gpu_emit ? 0 : total_seeds, -1);   /* per (chain, seed i): index into splits, host emit only */
     std::vector<uint32_t> dirty_list, clean_list;   /* chains a trigger fired for (ascending), and the others */
-    {   /* every thread scans a contiguous range of chains into its own lists; indices are rebased when the
-         * lists are concatenated in thread (= chain) order, so the result equals the serial scan */
-        struct Local { std::vector<lf_extend_task> e2; std::vector<ClipInfo> clips; std::vector<SplitInfo> splits; std::vector<uint32_t> dirty; size_t c_lo = 0, c_hi = 0; };
-        const unsigned nt = n_chains < 256 ? 1u : nthreads;
-        std::vector<Local> loc(nt);
-        parallel_for(n_chains, nt, [&](unsigned tid, size_t lo, size_t hi) {
-            Local &Lc = loc[tid];
-            Lc.c_lo = lo; Lc.c_hi = hi;
-            for (size_t c = lo; c < hi; c++) {
-                const lf_chain &ch = chains[c];
-                const uint32_t n = ch.n_seeds;
-                const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
-                ChainPlan &p = plan[c];
-                const size_t e2_before = Lc.e2.size();
-                if (p.head_task >= 0) {
-                    const lf_align_task &t = t1[(size_t)p.head_task];
-                    const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.head_task);
-                    if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :1840 */
-                        p.head_clip = (int32_t)Lc.clips.size();
-                        Lc.clips.push_back(ClipInfo{ (int32_t)Lc.e2.size(), -1, 0, 0 });
-                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, true));
+    {   /* the few thousand hits, in task (= chain, then head / gaps / tail) order: the order of the serial scan */
+        size_t k = 0;
+        while (k < trig.size()) {
+            const uint32_t c = (uint32_t)(std::upper_bound(task_base.begin(), task_base.end(), (uint64_t)trig[k]) - task_base.begin() - 1);
+            const lf_chain &ch = chains[c];
+            const uint32_t n = ch.n_seeds;
+            const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
+            ChainPlan &p = plan[c];
+            dirty_list.push_back(c);
+            p.split_lo = (int32_t)splits.size();
+            const lf_seed *sd = seeds + ch.seed_off;
+            uint32_t gi = 0;   /* gaps are visited in order: the chain's hits are ascending too */
+            int64_t gtask = (int64_t)task_base[c] + (p.head_task >= 0 ? 1 : 0) - 1;   /* task of the last gap passed */
+            for (; k < trig.size() && trig[k] < task_base[c + 1]; k++) {
+                const int32_t ti = (int32_t)trig[k];
+                const lf_align_task &t = t1[(size_t)ti];
+                if (ti == p.head_task) {
+                    p.head_clip = (int32_t)clips.size();
+                    clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
+                    e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, true));
+                } else if (ti == p.tail_task) {
+                    p.tail_clip = (int32_t)clips.size();
+                    clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
+                    e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true));
+                } else {
+                    for (;; gi++) {   /* the gap whose task this is: gaps get their tasks in order */
+                        const int32_t ql = (int32_t)(sd[gi + 1].qPos - (sd[gi].qPos + sd[gi].len)), tl = (int32_t)(sd[gi + 1].tPos - (sd[gi].tPos + sd[gi].len));
+                        if (ql > 0 && tl > 0 && ++gtask == ti) break;
                     }
-                }
-                for (uint32_t i = 0; i + 1 < n; i++) {
-                    const int32_t gt = gap_task[gap_base[c] + i];
-                    if (gt < 0) continue;
-                    const lf_align_task &t = t1[(size_t)gt];
-                    const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len, ed = ed_of((size_t)gt);
-                    if (abs(ql - tl) >= kSplitLen && (1 - ((float)ed / ql)) < kSplitSim) {                 /* :1952 */
-                        gap_split[gap_base[c] + i] = (int32_t)Lc.splits.size();
-                        SplitInfo si; memset(&si, 0, sizeof si);
-                        si.seed_idx = (uint32_t)(ch.seed_off + i); si.ext_f = (int32_t)Lc.e2.size(); si.ext_r = si.ext_f + 1;
-                        si.t_first = si.t_mid_f = si.t_mid_r = si.t_second = -1; si.split = false;
-                        Lc.splits.push_back(si);
-                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, false));
-                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, false));
-                    }
-                }
-                if (p.tail_task >= 0) {
-                    const lf_align_task &t = t1[(size_t)p.tail_task];
-                    const int32_t len = (int32_t)t.q_len, ed = ed_of((size_t)p.tail_task);
-                    if (len > kClipLen && (1 - ((float)ed / len)) < kClipSim) {                            /* :2175 */
-                        p.tail_clip = (int32_t)Lc.clips.size();
-                        Lc.clips.push_back(ClipInfo{ (int32_t)Lc.e2.size(), -1, 0, 0 });
-                        Lc.e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true));
-                    }
-                }
-                if (Lc.e2.size() != e2_before) Lc.dirty.push_back((uint32_t)c);   /* a trigger fired: rounds 2-3 decide this chain */
-            }
-        });
-        for (Local &Lc : loc) {
-            const int32_t be = (int32_t)e2.size(), bc = (int32_t)clips.size(), bs = (int32_t)splits.size();
-            for (ClipInfo ci : Lc.clips) { ci.ext += be; clips.push_back(ci); }
-            for (SplitInfo si : Lc.splits) { si.ext_f += be; si.ext_r += be; splits.push_back(si); }
-            e2.insert(e2.end(), Lc.e2.begin(), Lc.e2.end());
-            dirty_list.insert(dirty_list.end(), Lc.dirty.begin(), Lc.dirty.end());
-            if (bc || bs) {
-                for (size_t c = Lc.c_lo; c < Lc.c_hi; c++) {
-                    if (plan[c].head_clip >= 0) plan[c].head_clip += bc;
-                    if (plan[c].tail_clip >= 0) plan[c].tail_clip += bc;
-                    if (bs) for (uint64_t g = gap_base[c]; g < gap_base[c + 1]; g++) if (gap_split[g] >= 0) gap_split[g] += bs;
+                    if (!gpu_emit) gap_split[gap_base[c] + gi] = (int32_t)splits.size();
+                    SplitInfo si; memset(&si, 0, sizeof si);
+                    si.gap_i = gi; si.task = ti;
+                    gi++;
+                    si.seed_idx = (uint32_t)(ch.seed_off + si.gap_i); si.ext_f = (int32_t)e2.size(); si.ext_r = si.ext_f + 1;
+                    si.t_first = si.t_mid_f = si.t_mid_r = si.t_second = -1; si.split = false;
+                    splits.push_back(si);
+                    e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, false));
+                    e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, false));
                 }
             }
+            p.split_hi = (int32_t)splits.size();
         }
     }
+    const double tq0 = now_ms();
     /* ---- chains no trigger fired for are final after round 1: their CIGAR / MD assembly (its own stream and
      *      host thread) overlaps rounds 2-3 ---- */
     EarlyEmit early;
@@ -658,6 +670,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         run_early();   /* the emulator is single-threaded */
 #endif
     }
+    const double tq1 = now_ms();
     std::vector<lf_extend_result> x2(e2.size());
     if (!e2.empty()) {
         LF_CH(lf_gpu_upload_extend_tasks(ctx, e2.data(), e2.size()));
@@ -665,6 +678,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         LF_CH(lf_gpu_download_extend(ctx, x2.data()));
     }
     R->stats.round2_extends = e2.size();
+    const double tq2 = now_ms();
 
     /* ---------------- round 3: follow-up alignments ---------------- */
     std::vector<lf_align_task> t3;
@@ -684,11 +698,9 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                                      strand | LF_F_REVERSE_BOTH, LF_MODE_NW));
             }
         }
-        for (uint32_t i = 0; i + 1 < n; i++) {
-            const int32_t sx = gap_split[gap_base[c] + i];
-            if (sx < 0) continue;
+        for (int32_t sx = p.split_lo; sx < p.split_hi; sx++) {
             SplitInfo &si = splits[(size_t)sx];
-            const lf_align_task &t = t1[(size_t)gap_task[gap_base[c] + i]];
+            const lf_align_task &t = t1[(size_t)si.task];
             const uint32_t qs = t.q_off, ts = t.t_off, qe = qs + t.q_len, te = ts + t.t_len;
             si.qs2 = qs + (uint32_t)x2[(size_t)si.ext_f].qle; si.ts2 = ts + (uint32_t)x2[(size_t)si.ext_f].tle;   /* :1972-1973 */
             si.qe2 = qe - (uint32_t)x2[(size_t)si.ext_r].qle; si.te2 = te - (uint32_t)x2[(size_t)si.ext_r].tle;   /* :1982-1983 */
@@ -720,6 +732,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             }
         }
     }
+    const double tq3 = now_ms();
     const size_t n3 = t3.size();
     const size_t cap3 = lf_gpu_ops_capacity(t3.data(), n3);
     lf_align_result *r3 = (lf_align_result *)S.r3.reserve((n3 + 1) * sizeof(lf_align_result));
@@ -738,6 +751,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     LF_CH(lf_gpu_sync(ctx));
     R->stats.round3_tasks = n3;
     const double tm3 = now_ms();
+    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] r23: trigger scan %.2f, early-emit start %.2f, round 2 %.2f, round-3 tasks %.2f, round 3 %.2f\n", tq0 - tm2, tq1 - tq0, tq2 - tq1, tq3 - tq2, tm3 - tq3);
 #undef LF_CH
 
     if (gpu_emit) {
@@ -761,11 +775,10 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                 const ChainPlan &p = plan[c];
                 if (p.head_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.head_clip]; clipv[4 * c + 0] = ci.t3; clipv[4 * c + 1] = ci.qle; }
                 if (p.tail_clip >= 0) { const ClipInfo &ci = clips[(size_t)p.tail_clip]; clipv[4 * c + 2] = ci.t3; clipv[4 * c + 3] = ci.qle; }
-                for (uint64_t g = gap_base[c]; g < gap_base[c + 1]; g++) {
-                    if (gap_split[g] < 0) continue;
-                    const SplitInfo &si = splits[(size_t)gap_split[g]];
+                for (int32_t sx = p.split_lo; sx < p.split_hi; sx++) {
+                    const SplitInfo &si = splits[(size_t)sx];
                     LfSplitDev v; memset(&v, 0, sizeof v);
-                    v.gap_i = (uint32_t)(g - gap_base[c]); v.t_first = si.t_first; v.t_mid_r = si.t_mid_r; v.t_second = si.t_second;
+                    v.gap_i = si.gap_i; v.t_first = si.t_first; v.t_mid_r = si.t_mid_r; v.t_second = si.t_second;
                     v.qs2 = si.qs2; v.ts2 = si.ts2; v.qe2 = si.qe2; v.te2 = si.te2; v.split = si.split ? 1u : 0u; v.inv = 0;
                     if (si.split && si.t_mid_f >= 0) {
                         const lf_align_result &rf = r3[(size_t)si.t_mid_f], &rr = r3[(size_t)si.t_mid_r];

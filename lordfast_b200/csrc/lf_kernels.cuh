@@ -996,9 +996,12 @@ __device__ __forceinline__ int lf_warp_max(int v)
 /* One warp per task.  The reference's row loop is kept row by row (band re-trim, m==0 and z-drop exits
  * are row-sequential), but inside a row the 32 lanes take 32 consecutive columns at a time: E and the
  * diagonal feed come from the previous row, and F(i,j+1) = max(F(i,j)-e_ins, max(M-oe_ins,0)) does not
- * depend on H, so with u = F + j*e_ins it is a prefix maximum (5 shuffles per 32 columns).  eh[] lives in
- * global scratch and is read/written coalesced; cells outside [beg,end] keep their old contents exactly
- * as in the reference. */
+ * depend on H, so with u = F + j*e_ins it is a prefix maximum (5 shuffles per 32 columns).  Cells outside
+ * [beg,end] keep their old contents exactly as in the reference (it reads such stale cells when the band
+ * widens again).  eh[] is a ring of LF_KSW_RING columns in shared memory when the band fits (2w+2 <= ring: a
+ * column and the column one ring length later are then never live together; columns are initialised with the
+ * first-row values, ksw.c:395-397, when the band first reaches them), else the task's global scratch. */
+#define LF_KSW_RING 256
 __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
 {
     const int lane = threadIdx.x & 31;
@@ -1008,6 +1011,7 @@ __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
     lf_extend_result out; out.score = -1; out.qle = 0; out.tle = 0;
     const uint64_t so = d.scr_off[i];
     if (d.scr_off[i + 1] == so) { if (lane == 0) d.res[i] = out; return; } /* rejected by k_extend_prep */
+    __shared__ int2 s_ring[4][LF_KSW_RING];
     int2 *eh = d.scratch + so;
     const int qlen = (int)t.q_len, tlen = (int)t.t_len;
     uint8_t *qcode = (uint8_t *)(eh + qlen + 1);
@@ -1024,26 +1028,33 @@ __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
     const int o_del = t.o_del, e_del = t.e_del, o_ins = t.o_ins, e_ins = t.e_ins, h0 = t.h0, zdrop = t.zdrop;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
     int w = t.w;
-    /* query codes (src/LordFAST.cpp:158-164, 1191-1201) and the first row (ksw.c:395-397) */
-    for (int j = lane; j <= qlen; j += 32) {
-        if (j < qlen) {
-            uint32_t qc = lf_char2int(d.bases[ro + (uint64_t)(f0 + (int64_t)qdir * j)]);
-            if (comp && qc < 4u) qc = 3u - qc;
-            qcode[j] = (uint8_t)qc;
-        }
-        int hv;
-        if (j == 0) hv = h0;
-        else if (j == 1) hv = h0 > oe_ins ? h0 - oe_ins : 0;
-        else { const int prev = h0 - oe_ins - (j - 2) * e_ins; hv = (h0 > oe_ins && prev > e_ins) ? prev - e_ins : 0; }
-        eh[j] = int2{hv, 0};
-    }
-    __syncwarp();
     {   /* band clamp (ksw.c:399-407), max matrix entry is the match score */
         int lim = (int)((double)(qlen * smatch - o_ins) / e_ins + 1.);
         lim = lim > 1 ? lim : 1; w = w < lim ? w : lim;
         lim = (int)((double)(qlen * smatch - o_del) / e_del + 1.);
         lim = lim > 1 ? lim : 1; w = w < lim ? w : lim;
     }
+    const bool ring = 2 * w + 2 <= LF_KSW_RING;
+    const uint32_t jm = ring ? (uint32_t)(LF_KSW_RING - 1) : 0xffffffffu;   /* column -> cell index */
+    if (ring) eh = s_ring[threadIdx.x >> 5];
+    auto first_row = [&](int j) {   /* ksw.c:395-397 */
+        int hv;
+        if (j == 0) hv = h0;
+        else if (j == 1) hv = h0 > oe_ins ? h0 - oe_ins : 0;
+        else { const int prev = h0 - oe_ins - (j - 2) * e_ins; hv = (h0 > oe_ins && prev > e_ins) ? prev - e_ins : 0; }
+        return int2{hv, 0};
+    };
+    /* query codes (src/LordFAST.cpp:158-164, 1191-1201) and, without the ring, the whole first row */
+    for (int j = lane; j <= qlen; j += 32) {
+        if (j < qlen) {
+            uint32_t qc = lf_char2int(d.bases[ro + (uint64_t)(f0 + (int64_t)qdir * j)]);
+            if (comp && qc < 4u) qc = 3u - qc;
+            qcode[j] = (uint8_t)qc;
+        }
+        if (!ring) eh[j] = first_row(j);
+    }
+    int hi_init = 0;   /* ring: columns below hi_init hold first-row or later values */
+    __syncwarp();
     const int NEG = -(1 << 29);
     int best = h0, best_i = -1, best_j = -1, beg = 0, end = qlen;
     LfTCursor tcur;
@@ -1053,6 +1064,11 @@ __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
         if (beg < r - w) beg = r - w;
         if (end > r + w + 1) end = r + w + 1;
         if (end > qlen) end = qlen;
+        if (ring && hi_init < end) {
+            for (int j = hi_init + lane; j < end; j += 32) eh[(uint32_t)j & jm] = first_row(j);
+            hi_init = end;
+            __syncwarp();
+        }
         int h1 = 0;
         if (beg == 0) { h1 = h0 - (o_del + e_del * (r + 1)); if (h1 < 0) h1 = 0; }
         int carry_u = 0;            /* u = F + (j-beg)*e_ins at the start of the round; F(i,beg) = 0 */
@@ -1064,7 +1080,7 @@ __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
             const bool act = rr < width;
             int M = 0, e = 0;
             if (act) {
-                const int2 c = eh[j];
+                const int2 c = eh[(uint32_t)j & jm];
                 const uint32_t qc = qcode[j];
                 const int sc = qc > 3u ? 0 : (qc == tc ? smatch : smis);
                 M = c.x ? c.x + sc : 0;
@@ -1090,7 +1106,7 @@ __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
             if (act) {
                 int tt = M - oe_del; tt = tt > 0 ? tt : 0;
                 en = e - e_del; en = en > tt ? en : tt;
-                eh[j] = int2{hprev, en};
+                eh[(uint32_t)j & jm] = int2{hprev, en};
             }
             /* row maximum, ties to the later column (ksw.c:437) */
             const int mk = lf_warp_max(h);
@@ -1109,7 +1125,8 @@ __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
             h_last = __shfl_sync(LF_FULL, h, nact - 1);
             prev_h = h_last;
         }
-        if (lane == 0) eh[end] = int2{h_last, 0};
+        if (lane == 0) eh[(uint32_t)end & jm] = int2{h_last, 0};
+        if (hi_init < end + 1) hi_init = end + 1;
         __syncwarp();
         if (rowmax == 0) break;
         if (rowmax > best) { best = rowmax; best_i = r; best_j = rowmax_j; }
@@ -1668,10 +1685,22 @@ __global__ void __launch_bounds__(LF_EMIT_BLOCK) k_emit_slots(LfEmitDev d)
     if (!WRITE && tid == 0) { d.nrec[li] = s_nrec; d.cig_bytes[li] = run_c; d.md_bytes[li] = run_m; }
 }
 
-__global__ void k_gather_ed(const lf_align_result *res, int32_t *ed, uint32_t n)
-{ /* the host only needs the distances to evaluate the clip / split triggers */
+/* The clip / split trigger tests of alignChain_edlib on the round-1 results (src/LordFAST.cpp:1840, :1952,
+ * :2175), in the reference's own arithmetic: the similarity is computed in float and compared with a double
+ * constant.  Head and tail tasks are the prefix-mode ones.  Triggered task indices are appended to `list`
+ * (unordered; the host sorts the few thousand entries). */
+__global__ void k_chain_triggers(const lf_align_task *tasks, const lf_align_result *res, uint32_t n, uint32_t *list, uint32_t *count, uint32_t cap)
+{
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ed[i] = res[i].edit_distance;
+    if (i >= n) return;
+    const lf_align_task t = tasks[i];
+    const int32_t ed = res[i].edit_distance;
+    const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len;
+    const double sim = (double)(1 - ((float)ed / ql));
+    bool trig;
+    if (t.mode == LF_MODE_SHW) trig = ql > 500 && sim < 0.75;
+    else { const int32_t dl = ql > tl ? ql - tl : tl - ql; trig = dl >= 80 && sim < 0.40; }
+    if (trig) { const uint32_t p = atomicAdd(count, 1u); if (p < cap) list[p] = i; }
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -88,6 +88,14 @@ def test_emu_extend(emu_lib):
     er = g.extend_batch(np.concatenate(reads), offs, np.array(tasks, dtype=api.EXTEND_TASK))
     for k, c in enumerate(cases):
         assert (int(er[k]["score"]), int(er[k]["qle"]), int(er[k]["tle"])) == (c["score"], c["qle"], c["tle"])
+    # the same pairs with a band too wide for the shared-memory ring (eh[] in global scratch), against the oracle
+    wide = np.array(tasks, dtype=api.EXTEND_TASK)
+    wide["w"] = 300
+    er = g.extend_batch(np.concatenate(reads), offs, wide)
+    for k, c in enumerate(cases):
+        p = c["prm"]
+        exp = O.oracle_extend(CODE[reads[k]].tobytes(), CODE[tcat[k]].tobytes(), p[0], p[1], p[2], p[3], 300, p[5])
+        assert exp == (int(er[k]["score"]), int(er[k]["qle"]), int(er[k]["tle"]))
     g.close()
 
 

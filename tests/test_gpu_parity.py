@@ -121,7 +121,7 @@ def test_gpu_extend_golden_and_random():
         ql = int(rng.integers(20, min(L, 1800))); qo = int(rng.integers(0, L - ql + 1))
         to = int(rng.integers(0, len(w.ref) - ql - 40)) if k % 2 else int(w.chain(rid)[0][0])
         fl = int(rng.choice([0, 2])) | (1 if w.is_rev[rid] else 0)
-        prm = (0, 1, 0, 1, 40, 40) if k % 3 else (8, 1, 4, 1, 100, 200)
+        prm = (8, 1, 4, 1, 300, 200) if k % 7 == 0 else (0, 1, 0, 1, 40, 40) if k % 3 else (8, 1, 4, 1, 100, 200)  # w = 300: no shared-memory ring
         et.append((rid, qo, ql, to, ql + 20, fl, 0, 0) + prm + (ql,))
     et = np.array(et, dtype=api.EXTEND_TASK)
     g2 = api.LfGpu(w.pac, len(w.ref))
