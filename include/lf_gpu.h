@@ -197,8 +197,8 @@ typedef struct {
 int lf_gpu_get_stats(const lf_gpu_ctx *ctx, lf_gpu_stats *out);
 
 /* Timeline of the last lf_gpu_run_align on device 0: start / end (ms after the first launch) of each size-class
- * kernel; index 2*i+shw for the register classes (NW = 1,2,3,4,6,8,12,16), 16 = large-task kernel; -1 = not run.
- * n >= 18. */
+ * kernel; index 2*i+shw for the register classes (NW = 1,2,3,4,6,8,12,16), 16 = large-task kernel, 18..21 = the
+ * banded register classes (near-diagonal global tasks of NW = 6,8,12,16); -1 = not run.  n >= 22. */
 int lf_gpu_class_timeline(lf_gpu_ctx *ctx, float *start_ms, float *end_ms, int n);
 
 /* INT32 issue-rate microbenchmarks on device 0 (dependent-free streams on all SMs); Top/s.

@@ -11,6 +11,7 @@ import os
 
 import numpy as np
 
+N_CLASSES = 22  # LF_NCLS: 16 register classes, large, bad, 4 banded register classes
 # the size-class kernels run on 18 streams; give each its own hardware queue (must be set before CUDA starts)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
@@ -245,8 +246,8 @@ class LfGpu:
         return s
 
     def class_timeline(self):
-        a = np.zeros(18, dtype=np.float32); b = np.zeros(18, dtype=np.float32)
-        self._check(self.lib.lf_gpu_class_timeline(self.ctx, _ptr(a), _ptr(b), 18), "lf_gpu_class_timeline")
+        a = np.zeros(N_CLASSES, dtype=np.float32); b = np.zeros(N_CLASSES, dtype=np.float32)
+        self._check(self.lib.lf_gpu_class_timeline(self.ctx, _ptr(a), _ptr(b), N_CLASSES), "lf_gpu_class_timeline")
         return a, b
 
     def int32_peak(self, which: int) -> float:

@@ -44,7 +44,8 @@
 #define LF_NSMALL 8       /* register-resident size classes */
 #define LF_CLS_LARGE 16   /* class id of k_myers_large tasks (small classes are 2*i + shw) */
 #define LF_CLS_BAD 17
-#define LF_NCLS 18
+#define LF_CLS_BANDREG0 18 /* 18..21: global-mode tasks of size classes 4..7 that k_myers_bandreg runs in a sliding band */
+#define LF_NCLS 22
 #define LF_KEY_SHIFT 19    /* sort keys use bits [19,32): 5 bits of class, 8 bits of length bucket */
 #define LF_LARGE_STACK 96 /* Hirschberg stack entries per warp (depth <= log2(t)+2) */
 
@@ -72,6 +73,13 @@ __host__ __device__ __forceinline__ uint32_t lf_k1_ckpt_bytes(uint32_t t, int nw
     return (nck * (uint32_t)nw * 8u + 15u) & ~15u;
 }
 
+__host__ __device__ __forceinline__ int lf_bandreg_nb(int sc) { return sc == 4 ? 3 : sc == 7 ? 5 : 4; } /* band words for q <= 192 | 256, 384 | 512 */
+__host__ __device__ __forceinline__ bool lf_bandreg_eligible(uint32_t q, uint32_t t, int sc)
+{ /* near-diagonal enough for the band certificate of k_myers_bandreg to have room for the usual 15 % distance */
+    const int dlt = q > t ? (int)(q - t) : (int)(t - q);
+    return sc >= 4 && 3 * dlt <= 32 * (lf_bandreg_nb(sc) - 1) - 7 && q / t < 32u;
+}
+
 /* Everything a kernel needs about one resident batch. */
 struct LfDev {
     const uint8_t *pac; int64_t l_pac;
@@ -84,6 +92,7 @@ struct LfDev {
     const uint64_t *scr_off;               /* exclusive scan of per-task scratch bytes (small classes) */
     uint8_t *scratch;
     uint8_t *planes;                       /* op planes of k_myers_band, one region per warp group */
+    uint32_t bandreg;                      /* != 0: near-diagonal global tasks with 128 < q <= 512 go to k_myers_bandreg */
 };
 
 struct LfCounters { /* written by k_align_prep, read back by the host (one small D2H per batch) */
@@ -249,6 +258,7 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
             int sc = lf_small_class(nwords);
             if (sc >= 0 && lf_is_leaf(t.q_len, t.t_len)) {
                 cls = 2 * sc + (t.mode == LF_MODE_SHW ? 1 : 0);
+                if (d.bandreg && t.mode == LF_MODE_NW && lf_bandreg_eligible(t.q_len, t.t_len, sc)) cls = LF_CLS_BANDREG0 + sc - 4;
                 scr = lf_k1_ckpt_bytes(t.t_len, lf_small_nw(sc));
                 atomicAdd(&s_swc, (unsigned long long)nwords * t.t_len);
             } else {
@@ -339,6 +349,16 @@ template <> __device__ __forceinline__ void lf_add_chain<4>(const uint32_t (&a)[
         "addc.u32 %3, %7, %11;"
         : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3])
         : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]));
+}
+template <> __device__ __forceinline__ void lf_add_chain<5>(const uint32_t (&a)[5], const uint32_t (&b)[5], uint32_t (&s)[5])
+{
+    asm("add.cc.u32 %0, %5, %10;\n\t"
+        "addc.cc.u32 %1, %6, %11;\n\t"
+        "addc.cc.u32 %2, %7, %12;\n\t"
+        "addc.cc.u32 %3, %8, %13;\n\t"
+        "addc.u32 %4, %9, %14;"
+        : "=&r"(s[0]),"=&r"(s[1]),"=&r"(s[2]),"=&r"(s[3]),"=&r"(s[4])
+        : "r"(a[0]),"r"(a[1]),"r"(a[2]),"r"(a[3]),"r"(a[4]),"r"(b[0]),"r"(b[1]),"r"(b[2]),"r"(b[3]),"r"(b[4]));
 }
 template <> __device__ __forceinline__ void lf_add_chain<6>(const uint32_t (&a)[6], const uint32_t (&b)[6], uint32_t (&s)[6])
 {
@@ -1931,6 +1951,277 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
                 const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
                 const int stay_col = (int)(x0 & ~x1 & 1u);
                 const int stay_row = (int)(x1 & ~x0 & 1u);
+                LF_EMIT(op);
+                b -= 1 - stay_row;
+                j -= 1 - stay_col;
+                cell -= (1 - stay_col) * CS;
+            } while (b >= 0 && j > c0);
+            i = wrow * 32 + b + 1;
+        }
+        if (nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
+    }
+    while (i > 0 && !lost) { LF_EMIT(1u); i--; }
+    while (j > 0 && !lost) { LF_EMIT(2u); j--; }
+    if (sh != 30) *wptr = cur;
+#undef LF_EMIT
+    if (lost) { retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
+    r.ops_off = slot_hi - nops; r.ops_len = nops;
+    d.res[ti] = r;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* k_myers_bandreg: thread per task, NB-word sliding band held in registers                    */
+/* ------------------------------------------------------------------------------------------ */
+/* Global-mode gap tasks with 128 < q <= 512 hold 54 % of the stage's word-columns (profiles/r02a) and are
+ * near-diagonal (|q-t| small, distance ~0.15 q), so only a band of NB words around the line (0,0)-(q,t) can
+ * hold an optimal path -- the Ukkonen argument behind edlib's own band (edlib.cpp:722-760).  This kernel is
+ * k_myers_small restricted to that band: the band geometry and the certificate are k_myers_band's (see the
+ * comment above LF_RETRY: a distance d <= 32*(NB-1) - 7 - |q-t| proves that no optimal path leaves the band,
+ * which makes d and every Up/Left/Diagonal test on the path exact), but nothing per column goes to HBM:
+ *   forward    NB words per column, (Pv,Mv) of the band checkpointed every 8 columns; blocks of 8 columns in
+ *              which the band does not slide (3 of 4 when q ~ t) run fully unrolled: the 8 target symbols are
+ *              one funnel shift out of a 64-bit window of the 2-bit reference, strand handled once per word.
+ *   traceback  per 8-column block: restore the checkpoint, recompute the band with the two op planes of a
+ *              2-word window written to shared memory, walk Up > Left > Diagonal inside the window.
+ * Tasks that fail the certificate are appended to the retry list and redone full width by k_myers_small.
+ * k_align_prep routes only tasks with 3*|q-t| <= 32*(NB-1)-7 here (classes LF_CLS_BANDREG0..+3). */
+/* The 2-bit reference as a stream in task order: the next 16 symbols are the top 32 bits of a 64-bit window
+ * (first symbol at bits 31:30), whatever the strand; the word after next is requested one refill ahead. */
+struct LfTStream {
+    const uint32_t *p32; int64_t widx; uint32_t cur, nxt; int off, dir;
+    __device__ __forceinline__ uint32_t norm(uint32_t v) const
+    {
+        v = __byte_perm(v, 0u, 0x0123u);   /* base j of the word at bits 31-2j .. 30-2j */
+        if (dir < 0) { v = __brev(v); v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); } /* base 15 first */
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t *pac, int64_t l, int d)
+    {
+        p32 = (const uint32_t *)pac; dir = d; widx = l >> 4;
+        const int j = (int)(l & 15);
+        cur = norm(__ldg(p32 + widx));
+        off = d > 0 ? 2 * j : 2 * (15 - j);
+        widx += d;
+        nxt = norm(__ldg(p32 + (widx < 0 ? 0 : widx)));
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, (uint32_t)off); }
+    __device__ __forceinline__ void advance(int n)
+    { /* n <= 16 symbols consumed */
+        off += 2 * n;
+        if (off >= 32) { off -= 32; cur = nxt; widx += dir; nxt = norm(__ldg(p32 + (widx < 0 ? 0 : widx))); }
+    }
+};
+
+/* not-Eq of 32 query rows against one target symbol: two 3-input LOP3s (the compiler's own association of
+ * the five inputs costs three) */
+__device__ __forceinline__ uint32_t lf_neq(uint32_t qlo, uint32_t qhi, uint32_t qnn, uint32_t slo, uint32_t shi)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t x, r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xbe;" : "=r"(x) : "r"(qlo), "r"(slo), "r"(qnn)); /* (a ^ b) | c */
+    asm("lop3.b32 %0, %1, %2, %3, 0xf6;" : "=r"(r) : "r"(x), "r"(qhi), "r"(shi));   /* a | (b ^ c) */
+    return r;
+#else
+    return (qlo ^ slo) | qnn | (qhi ^ shi);
+#endif
+}
+
+template <int NB, bool STORE>
+__device__ __forceinline__ void lf_bandreg_column(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], const uint32_t (&qlo)[NB], const uint32_t (&qhi)[NB],
+                                                  const uint32_t (&qnn)[NB], uint32_t slo, uint32_t shi, uint32_t *sm, int wrel0)
+{ /* STORE: band words wrel0, wrel0+1 are the window words 0, 1 of this column */
+    uint32_t nEq[NB], a[NB], sum[NB];
+#pragma unroll
+    for (int w = 0; w < NB; w++) {
+        nEq[w] = lf_neq(qlo[w], qhi[w], qnn[w], slo, shi);
+        a[w] = Pv[w] & ~nEq[w];
+    }
+    lf_add_chain<NB>(a, Pv, sum);
+    uint32_t pPh = 0x80000000u, pMh = 0u; /* the row above the band grows by one per column (exact for row 0, an upper bound otherwise) */
+#pragma unroll
+    for (int w = 0; w < NB; w++) {
+        const uint32_t Xh = (sum[w] ^ Pv[w]) | ~nEq[w];
+        const uint32_t Ph = Mv[w] | ~(Xh | Pv[w]);
+        const uint32_t Mh = Pv[w] & Xh;
+        const uint32_t Xv = ~nEq[w] | Mv[w];
+        const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
+        pPh = Ph; pMh = Mh;
+        const uint32_t nPv = Mhs | ~(Xv | Phs);
+        const uint32_t nMv = Phs & Xv;
+        if (STORE) {
+            const unsigned wi = (unsigned)(w - wrel0);
+            if (wi < 2u) {
+                const uint32_t diagx = ~(nPv | Ph) & nEq[w];          /* diagonal step over a mismatch */
+                sm[(wi * 2 + 0) * 128] = nPv | diagx;               /* ops 1, 3 */
+                sm[(wi * 2 + 1) * 128] = (~nPv & Ph) | diagx;       /* ops 2, 3 */
+            }
+        }
+        Pv[w] = nPv; Mv[w] = nMv;
+    }
+}
+
+/* One block of n <= 8 columns starting with the stream window tb.  (rline, racc) = divmod(c*q, t) of the
+ * block's first column c on entry and of c+n on exit; k follows the band.  FWD accumulates the vertical
+ * deltas that leave through the top of the band (the distance needs them); STORE writes the window planes. */
+template <int NB, bool FWD, bool STORE>
+__device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], uint32_t (&qlo)[NB], uint32_t (&qhi)[NB], uint32_t (&qnn)[NB],
+                                                 uint32_t tb, int n, int &k, int &rline, int &racc, int &top, int t, int dq, int dr, int q8, int r8,
+                                                 int kmax, int nw, const LfDev &d, const LfQView &qv, uint32_t *smt, int wtop)
+{
+    constexpr int C = 8;
+    constexpr int CS = 2 * 2 * 128;
+    int rl8 = rline + q8, ra8 = racc + r8;
+    if (ra8 >= t) { ra8 -= t; rl8++; }
+    int kn8 = (rl8 - 16 * NB + 16) >> 5;
+    kn8 = kn8 < 0 ? 0 : kn8 > kmax ? kmax : kn8;
+    if (n == C && kn8 == k) { /* the band stays where it is */
+        const int wrel0 = wtop - k;
+#pragma unroll
+        for (int e = 0; e < C; e++) {
+            const uint32_t shi = (uint32_t)((int32_t)(tb << (2 * e)) >> 31), slo = (uint32_t)((int32_t)(tb << (2 * e + 1)) >> 31);
+            lf_bandreg_column<NB, STORE>(Pv, Mv, qlo, qhi, qnn, slo, shi, STORE ? smt + e * CS : nullptr, wrel0);
+        }
+        rline = rl8; racc = ra8;
+        return;
+    }
+    for (int e = 0; e < n; e++) {
+        rline += dq; racc += dr;
+        if (racc >= t) { racc -= t; rline++; }
+        int kn = (rline - 16 * NB + 16) >> 5;
+        kn = kn < 0 ? 0 : kn > kmax ? kmax : kn;
+        if (kn != k) { /* slide one word down: the top word's vertical deltas move into `top` */
+            if (FWD) top += __popc(Pv[0]) - __popc(Mv[0]);
+#pragma unroll
+            for (int w = 0; w + 1 < NB; w++) { Pv[w] = Pv[w + 1]; Mv[w] = Mv[w + 1]; qlo[w] = qlo[w + 1]; qhi[w] = qhi[w + 1]; qnn[w] = qnn[w + 1]; }
+            Pv[NB - 1] = 0xffffffffu; Mv[NB - 1] = 0u;
+            k++;
+            if (k + NB - 1 < nw) lf_q32(d, qv, (int64_t)(k + NB - 1) * 32, qlo[NB - 1], qhi[NB - 1], qnn[NB - 1]);
+            else { qlo[NB - 1] = 0; qhi[NB - 1] = 0; qnn[NB - 1] = 0xffffffffu; }
+        }
+        const uint32_t shi = (uint32_t)((int32_t)tb >> 31), slo = (uint32_t)((int32_t)(tb << 1) >> 31);
+        tb <<= 2;
+        lf_bandreg_column<NB, STORE>(Pv, Mv, qlo, qhi, qnn, slo, shi, STORE ? smt + e * CS : nullptr, wtop - k);
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count,
+                                                       uint32_t *retry_list, uint32_t *retry_count)
+{
+    constexpr int C = 8;
+    constexpr int CS = 2 * 2 * 128; /* shared-memory words per column: [2 window words][2 planes][128 threads] */
+    LF_DYN_SMEM(uint32_t, smem);    /* [C][2][2][128] */
+    const uint32_t tid = threadIdx.x;
+    const uint32_t gi = blockIdx.x * 128u + tid;
+    if (gi >= count) return;
+    const uint32_t ti = order[first + gi];
+    const lf_align_task task = d.tasks[ti];
+    const int q = (int)task.q_len, t = (int)task.t_len;
+    const int nw = (q + 31) >> 5;
+    const int kmax = nw > NB ? nw - NB : 0;   /* 0: the band is the whole column and the result needs no certificate */
+    const int dlt = q > t ? q - t : t - q;
+    const int cert = 32 * (NB - 1) - 7 - dlt;
+    const int dq = q / t, dr = q % t;         /* the line's row advances dq (+1 on carry) per column */
+    if (kmax > 0 && (dq >= 32 || cert < 0)) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
+    const int q8 = (int)((8u * (uint32_t)q) / (uint32_t)t), r8 = (int)((8u * (uint32_t)q) % (uint32_t)t);
+    LfQView qv; LfTView tv;
+    lf_task_views(d, task, qv, tv);
+
+    uint32_t qlo[NB], qhi[NB], qnn[NB], Pv[NB], Mv[NB];
+#pragma unroll
+    for (int w = 0; w < NB; w++) {
+        if (w < nw) lf_q32(d, qv, (int64_t)w * 32, qlo[w], qhi[w], qnn[w]);
+        else { qlo[w] = 0; qhi[w] = 0; qnn[w] = 0xffffffffu; }
+        Pv[w] = 0xffffffffu; Mv[w] = 0u;
+    }
+    const int wl = (q - 1) >> 5;
+    const uint32_t bl = (uint32_t)(q - 1) & 31u;
+    int k = 0, rline = 0, racc = 0, top = 0;
+    uint2 *ck = (uint2 *)(d.scratch + d.scr_off[ti]);
+
+    /* ---- forward pass ---- */
+    LfTStream ts;
+    ts.init(d.pac, tv.t0, tv.dir);
+    for (int c = 0; c < t; c += C) {
+        const int n = t - c < C ? t - c : C;
+        if (c) {
+            uint2 *dst = ck + (size_t)(c / C - 1) * NB;
+#pragma unroll
+            for (int w = 0; w < NB; w++) dst[w] = make_uint2(Pv[w], Mv[w]);
+        }
+        const uint32_t tb = ts.peek();
+        ts.advance(n);
+        lf_bandreg_block<NB, true, false>(Pv, Mv, qlo, qhi, qnn, tb, n, k, rline, racc, top, t, dq, dr, q8, r8, kmax, nw, d, qv, nullptr, 0);
+    }
+    int ed = t + top;
+#pragma unroll
+    for (int w = 0; w < NB; w++) {
+        const int wa = k + w;
+        const uint32_t m = wa < wl ? 0xffffffffu : wa == wl ? (0xffffffffu >> (31u - bl)) : 0u;
+        ed += __popc(Pv[w] & m) - __popc(Mv[w] & m);
+    }
+    if (kmax > 0) {
+        if (ed > cert) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
+        LF_BAND_COUNT(lf_emu_band_ok);
+    }
+    lf_align_result r;
+    r.edit_distance = ed; r.end_location = t - 1; r.status = 0;
+    const uint64_t slot_hi = d.slot_end[ti] * 16ull;
+    if (task.flags & LF_F_NO_PATH) { r.ops_off = slot_hi; r.ops_len = 0; d.res[ti] = r; return; }
+
+    /* ---- traceback: Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
+    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1;
+    uint32_t cur = 0, nops = 0;
+    int sh = 30;
+#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
+    int i = q, j = t;
+    uint32_t *smt = smem + tid;
+    int bc0 = ((t - 1) / C) * C;                 /* block the band bookkeeping below refers to */
+    int rl0 = (int)(((uint32_t)bc0 * (uint32_t)q) / (uint32_t)t), ra0 = (int)(((uint32_t)bc0 * (uint32_t)q) % (uint32_t)t);
+    bool lost = false;
+    while (i > 0 && j > 0) {
+        const int c1 = j, c0 = ((j - 1) / C) * C;
+        while (bc0 > c0) { bc0 -= C; rl0 -= q8; ra0 -= r8; if (ra0 < 0) { ra0 += t; rl0--; } }
+        int k0 = (rl0 - 16 * NB + 16) >> 5;       /* band position after column c0-1 */
+        k0 = k0 < 0 ? 0 : k0 > kmax ? kmax : k0;
+        while (k != k0) { /* bring the query words of that band position into the registers */
+            if (k > k0) {
+                k--;
+#pragma unroll
+                for (int w = NB - 1; w > 0; w--) { qlo[w] = qlo[w - 1]; qhi[w] = qhi[w - 1]; qnn[w] = qnn[w - 1]; }
+                lf_q32(d, qv, (int64_t)k * 32, qlo[0], qhi[0], qnn[0]);
+            } else {
+#pragma unroll
+                for (int w = 0; w + 1 < NB; w++) { qlo[w] = qlo[w + 1]; qhi[w] = qhi[w + 1]; qnn[w] = qnn[w + 1]; }
+                k++;
+                if (k + NB - 1 < nw) lf_q32(d, qv, (int64_t)(k + NB - 1) * 32, qlo[NB - 1], qhi[NB - 1], qnn[NB - 1]);
+                else { qlo[NB - 1] = 0; qhi[NB - 1] = 0; qnn[NB - 1] = 0xffffffffu; }
+            }
+        }
+        if (c0 == 0) {
+#pragma unroll
+            for (int w = 0; w < NB; w++) { Pv[w] = 0xffffffffu; Mv[w] = 0u; }
+        } else {
+            const uint2 *src = ck + (size_t)(c0 / C - 1) * NB;
+#pragma unroll
+            for (int w = 0; w < NB; w++) { const uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; }
+        }
+        const int whi = (i - 1) >> 5;
+        const int wtop = whi - 1 > 0 ? whi - 1 : 0;
+        ts.init(d.pac, tv.t0 + (int64_t)tv.dir * c0, tv.dir);
+        rline = rl0; racc = ra0;
+        lf_bandreg_block<NB, false, true>(Pv, Mv, qlo, qhi, qnn, ts.peek(), c1 - c0, k, rline, racc, top, t, dq, dr, q8, r8, kmax, nw, d, qv, smt, wtop);
+        /* walk inside the window, one word-row at a time */
+        const int rowmin = wtop * 32;
+        while (i > 0 && j > c0 && (i - 1) >= rowmin) {
+            const int wrow = (i - 1) >> 5;
+            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * 2 + (wrow - wtop)) * 2 * 128;
+            int b = (i - 1) & 31;
+            do {
+                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
+                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
+                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
                 LF_EMIT(op);
                 b -= 1 - stay_row;
                 j -= 1 - stay_col;

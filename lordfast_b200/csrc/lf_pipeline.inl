@@ -69,6 +69,14 @@ int fail(lf_gpu_ctx *c, int code, const char *msg)
 }
 #define LF_TRY(expr) do { int rc_ = (expr); if (rc_ != 0) return fail(ctx, rc_ == -5 ? LF_ERR_NOMEM : LF_ERR_CUDA, #expr); } while (0)
 
+/* k_myers_bandreg for the near-diagonal global tasks with 128 < q <= 512 (LF_BANDREG=0 turns it off: those tasks
+ * then run full width in k_myers_small, which is also the retry path of the ones the band cannot certify) */
+bool bandreg_on()
+{
+    const char *e = getenv("LF_BANDREG");
+    return !e || atoi(e) != 0;
+}
+
 LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
 {
     LfDev v;
@@ -82,6 +90,7 @@ LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
     v.scr_off = d.scr_off.as<uint64_t>();
     v.scratch = d.scratch.as<uint8_t>();
     v.planes = d.planes.as<uint8_t>();
+    v.bandreg = bandreg_on() ? 1u : 0u;
     return v;
 }
 
@@ -94,6 +103,14 @@ void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_
     const uint32_t grid = (count + LF_K1_BLOCK - 1) / LF_K1_BLOCK;
     auto kern = k_myers_small<NW, SHW>;
     LFB_LAUNCH(kern, grid, LF_K1_BLOCK, smem, s, v, order, first, count, retry_count);
+}
+
+template <int NB>
+void launch_bandreg(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, uint32_t *retry_list, uint32_t *retry_count)
+{
+    const size_t smem = (size_t)8 * 2 * 2 * 128 * sizeof(uint32_t);
+    auto kern = k_myers_bandreg<NB>;
+    LFB_LAUNCH(kern, (count + 127) / 128, 128, smem, s, v, order, first, count, retry_list, retry_count);
 }
 
 template <int NB, bool BANDED, bool SHW>
@@ -132,7 +149,7 @@ uint32_t band_mask()
 void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase,
                         const unsigned long long *goff, lfb_stream s, uint32_t *rl, uint32_t *rc, uint32_t bmask)
 {   /* rl: retry list (indexed like `order`), rc: this class's retry counter */
-    if (band_nb(cls) && (bmask >> cls & 1u)) {
+    if (cls < LF_CLS_LARGE && band_nb(cls) && (bmask >> cls & 1u)) {
         switch (cls) {
         case 0: launch_band<1, false, false>(v, order, first, count, gbase, goff, s, rl, rc); return;
         case 1: launch_band<1, false, true>(v, order, first, count, gbase, goff, s, rl, rc); return;
@@ -151,6 +168,11 @@ void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t
         }
     }
     switch (cls) {
+    /* sliding band in registers, then the full-width kernel over the dense list of tasks the band could not certify */
+    case LF_CLS_BANDREG0 + 0: launch_bandreg<3>(v, order, first, count, s, rl, rc); launch_small<4, false>(v, rl, first, count, s, rc); break;
+    case LF_CLS_BANDREG0 + 1: launch_bandreg<4>(v, order, first, count, s, rl, rc); launch_small<5, false>(v, rl, first, count, s, rc); break;
+    case LF_CLS_BANDREG0 + 2: launch_bandreg<4>(v, order, first, count, s, rl, rc); launch_small<6, false>(v, rl, first, count, s, rc); break;
+    case LF_CLS_BANDREG0 + 3: launch_bandreg<5>(v, order, first, count, s, rl, rc); launch_small<7, false>(v, rl, first, count, s, rc); break;
     case 0: launch_small<0, false>(v, order, first, count, s, nullptr); break;
     case 1: launch_small<0, true>(v, order, first, count, s, nullptr); break;
     case 2: launch_small<1, false>(v, order, first, count, s, nullptr); break;
@@ -268,21 +290,25 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][1], d.sub[0]);
 #endif
     }
-    for (int c = 0; c < LF_NCLS; c++) d.cls_ran[c] = c < LF_CLS_LARGE ? ht->cnt.hist[c] != 0 : (c == LF_CLS_LARGE && nlarge != 0);
-    /* small classes, biggest register footprint first, spread over the other streams */
+    for (int c = 0; c < LF_NCLS; c++) d.cls_ran[c] = c == LF_CLS_BAD ? false : c == LF_CLS_LARGE ? nlarge != 0 : ht->cnt.hist[c] != 0;
+    /* thread-per-task classes, the ones with the longest tasks first, spread over the other streams */
     {
-        uint32_t firsts[LF_CLS_LARGE];
+        uint32_t firsts[LF_NCLS];
         uint32_t first = 0;
-        for (int cls = 0; cls < LF_CLS_LARGE; cls++) { firsts[cls] = first; first += ht->cnt.hist[cls]; }
+        for (int cls = 0; cls < LF_NCLS; cls++) { firsts[cls] = first; first += ht->cnt.hist[cls]; }   /* sorted order = class id order */
         int k = 0;
-        for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) {
+        int seq[LF_NCLS], nseq = 0;
+        for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
+        for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) seq[nseq++] = cls;
+        for (int si = 0; si < nseq; si++) {
+            const int cls = seq[si];
             const uint32_t count = ht->cnt.hist[cls];
             if (!count) continue;
             lfb_stream st = d.sub[1 + (k % (LF_NSUB - 1))];
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
-            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, gc.gbase[cls], d.goff.as<unsigned long long>(), st,
+            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, cls < LF_CLS_LARGE ? gc.gbase[cls] : 0u, d.goff.as<unsigned long long>(), st,
                                d.idx.as<uint32_t>() /* input of the sort, free by now */, d.queue.as<uint32_t>() + 1 + cls, bmask);
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][1], st);

@@ -174,3 +174,54 @@ def test_emu_banded_classes_certificate_and_retry(emu_lib, monkeypatch):
     g.lib.lf_emu_band_counts(C.byref(ok), C.byref(rt))
     assert ok.value - ok0.value > 50 and rt.value - rt0.value > 20  # both outcomes exercised
     g.close()
+
+
+def _near_diagonal_batch(rng, ref, n, lo=129, hi=512):
+    """Gap-like pairs (query = target through the error channel) of every class k_myers_bandreg serves, all
+    strand / direction flags."""
+    reads, tasks, pos = [], [], 500
+    for k in range(n):
+        L = int(rng.integers(lo, hi + 8))
+        t = ref[pos:pos + L]
+        q = sim.mutate_pair(t, float(rng.choice([0.0, 0.05, 0.12, 0.15, 0.22])), rng)[:hi]
+        if len(q) < 1:
+            continue
+        flags = int(rng.choice([0, api.LF_F_READ_REV, api.LF_F_REVERSE_BOTH, api.LF_F_READ_REV | api.LF_F_REVERSE_BOTH,
+                                api.LF_F_RC_QUERY, api.LF_F_NO_PATH]))
+        if flags & api.LF_F_READ_REV:
+            q = sim.revcomp(q)
+        if flags & api.LF_F_REVERSE_BOTH:
+            q = q[::-1]  # the task reads both slices right-to-left: lay the stored read out so that the pair stays similar
+        if flags & api.LF_F_RC_QUERY:
+            q = sim.revcomp(q)
+        reads.append(np.ascontiguousarray(q))
+        tasks.append((len(reads) - 1, 0, len(q), pos, L, flags, 0, 0))
+        pos += L + int(rng.integers(0, 40))
+    return reads, np.array(tasks, dtype=api.ALIGN_TASK)
+
+
+@pytest.mark.parametrize("bandreg", ["1", "0"])
+def test_emu_bandreg_near_diagonal(emu_lib, monkeypatch, bandreg):
+    """k_myers_bandreg (sliding register band, checkpoints + recompute) on near-diagonal global tasks of 129..512
+    rows, and the same batch with the kernel switched off (full width): both must match the oracle."""
+    import ctypes as C
+    monkeypatch.setenv("LF_BANDREG", bandreg)
+    rng = np.random.default_rng(21)
+    ref = sim.make_reference(300_000, 6)
+    reads, tasks = _near_diagonal_batch(rng, ref, 420)
+    r2, t2 = _band_stress_batch(rng, ref, 120)
+    t2["read_id"] += len(reads)
+    reads, tasks = reads + r2, np.concatenate([tasks, t2])
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    ok0, rt0 = C.c_ulong(), C.c_ulong()
+    g.lib.lf_emu_band_counts(C.byref(ok0), C.byref(rt0))
+    bad, res, _ = check_align(g, reads, ref, tasks)
+    assert not bad, bad[:10]
+    ok, rt = C.c_ulong(), C.c_ulong()
+    g.lib.lf_emu_band_counts(C.byref(ok), C.byref(rt))
+    if bandreg == "1":
+        assert ok.value - ok0.value > 250, (ok.value - ok0.value, rt.value - rt0.value)   # certified in the band
+        assert rt.value - rt0.value > 5                                                    # and some redone full width
+    else:
+        assert ok.value == ok0.value
+    g.close()

@@ -196,3 +196,23 @@ def test_gpu_full_size_properties():
         assert np.array_equal(api.decode_ops(oo, int(rr[k]["ops_off"]), int(rr[k]["ops_len"])),
                               api.decode_ops(ops, int(res[i]["ops_off"]), int(res[i]["ops_len"])))
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bandreg", ["1", "0"])
+def test_gpu_bandreg_near_diagonal(bandreg, monkeypatch):
+    """k_myers_bandreg (sliding band in registers) on 4000 near-diagonal global tasks of 129..512 rows with every
+    strand / direction flag, plus pairs whose path bulges out of the band (redone full width); and the same batch
+    with the kernel switched off.  Bit-exact against the oracle both ways."""
+    from test_emu_pipeline import _band_stress_batch, _near_diagonal_batch
+    monkeypatch.setenv("LF_BANDREG", bandreg)
+    rng = np.random.default_rng(31)
+    ref = sim.make_reference(3_000_000, 8)
+    reads, tasks = _near_diagonal_batch(rng, ref, 4000)
+    r2, t2 = _band_stress_batch(rng, ref, 600)
+    t2["read_id"] += len(reads)
+    reads, tasks = reads + r2, np.concatenate([tasks, t2])
+    g = api.LfGpu(sim.pack_pac(ref), len(ref))
+    bad, _, _ = check_align(g, reads, ref, tasks)
+    assert not bad, bad[:10]
+    g.close()
