@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=65536)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--check", type=int, default=24, help="pairs per point verified against the oracle")
+    ap.add_argument("--lengths", type=int, nargs="*", help="target lengths instead of the config-5 list")
+    ap.add_argument("--divs", type=float, nargs="*", help="divergences instead of the config-5 list")
+    ap.add_argument("--nw-only", action="store_true", help="skip the SHW variant and the ksw_extend2 points")
     a = ap.parse_args()
     import _oracle as O
     from lordfast_b200 import api, sim
@@ -40,6 +43,10 @@ def main():
     divs = [0.05, 0.10, 0.15, 0.20]
     if a.quick:
         lengths, divs = [100, 500, 2000], [0.15]
+    if a.lengths:
+        lengths = a.lengths
+    if a.divs:
+        divs = a.divs
     rows = []
     for L in lengths:
         n = max(256, min(a.pairs, int(2.0e9 // (L * L)) if L >= 2000 else a.pairs))  # bound memory / time for the big squares
@@ -50,7 +57,7 @@ def main():
             off = np.zeros(n_src + 1, dtype=np.uint64); off[1:] = np.cumsum([len(r) for r in reads])
             bases = np.concatenate(reads)
             qlen = np.diff(off).astype(np.uint32)
-            for mode, extra in ((api.LF_MODE_NW, 0), (api.LF_MODE_SHW, 20)):
+            for mode, extra in (((api.LF_MODE_NW, 0),) if a.nw_only else ((api.LF_MODE_NW, 0), (api.LF_MODE_SHW, 20))):
                 t = np.zeros(n, dtype=api.ALIGN_TASK)
                 idx = np.arange(n) % n_src
                 t["read_id"], t["q_off"], t["q_len"] = idx, 0, qlen[idx]
@@ -83,7 +90,7 @@ def main():
     code = np.zeros(256, dtype=np.uint8)
     for i, ch in enumerate(b"ACGT"):
         code[ch] = i
-    for L in ([500, 2000] if a.quick else [500, 2000, 10000]):
+    for L in ([] if a.nw_only else [500, 2000] if a.quick else [500, 2000, 10000]):
         n = min(a.pairs, 16384 if L >= 10000 else a.pairs)
         n_src = min(n, 2048)
         starts = rng.integers(0, ref_len - L - 64, size=n_src)

@@ -20,7 +20,16 @@
 typedef cudaStream_t lfb_stream;
 typedef cudaEvent_t lfb_event;
 #define LFB_CHECK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return lfb_fail(cudaGetErrorString(e_), #expr); } while (0)
-#define LFB_LAUNCH(kern, grid, block, smem, stream, ...) do { kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); lfb_launches++; } while (0)
+/* Preferred shared-memory carve-out (percent of the SM's 256 KB L1/shared array) asked for by every kernel of the
+ * library.  The size-class kernels run concurrently and the split is per-SM state; measured on B200 with the config-2
+ * step (profiles/r02c_carveout_bandreg.txt): driver default 1.97 ms, 25 % 1.98, 50 % 1.84, 75 % 1.95, 100 % 2.34 --
+ * the checkpoints and op planes live on L1 hits, so all-shared is the worst choice.  LF_CARVEOUT overrides (-1 = leave
+ * the driver default). */
+static inline int lfb_carveout() { static int v = -2; if (v == -2) { const char *e = getenv("LF_CARVEOUT"); v = e ? atoi(e) : 50; } return v; }
+#define LFB_LAUNCH(kern, grid, block, smem, stream, ...) do { \
+        static bool lfb_once_ = false; \
+        if (!lfb_once_) { if (lfb_carveout() >= 0) cudaFuncSetAttribute((const void *)(kern), cudaFuncAttributePreferredSharedMemoryCarveout, lfb_carveout()); lfb_once_ = true; } \
+        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); lfb_launches++; } while (0)
 #else
 #include <algorithm>
 #include <numeric>

@@ -92,7 +92,7 @@ struct LfDev {
     const uint64_t *scr_off;               /* exclusive scan of per-task scratch bytes (small classes) */
     uint8_t *scratch;
     uint8_t *planes;                       /* op planes of k_myers_band, one region per warp group */
-    uint32_t bandreg;                      /* != 0: near-diagonal global tasks with 128 < q <= 512 go to k_myers_bandreg */
+    uint32_t bandreg;                      /* bit i: near-diagonal global tasks of size class 4+i (128 < q <= 512) go to k_myers_bandreg */
 };
 
 struct LfCounters { /* written by k_align_prep, read back by the host (one small D2H per batch) */
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
             int sc = lf_small_class(nwords);
             if (sc >= 0 && lf_is_leaf(t.q_len, t.t_len)) {
                 cls = 2 * sc + (t.mode == LF_MODE_SHW ? 1 : 0);
-                if (d.bandreg && t.mode == LF_MODE_NW && lf_bandreg_eligible(t.q_len, t.t_len, sc)) cls = LF_CLS_BANDREG0 + sc - 4;
+                if (sc >= 4 && (d.bandreg >> (sc - 4) & 1u) && t.mode == LF_MODE_NW && lf_bandreg_eligible(t.q_len, t.t_len, sc)) cls = LF_CLS_BANDREG0 + sc - 4;
                 scr = lf_k1_ckpt_bytes(t.t_len, lf_small_nw(sc));
                 atomicAdd(&s_swc, (unsigned long long)nwords * t.t_len);
             } else {
@@ -963,9 +963,13 @@ __device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) k_myers_large(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, LfLargeCfg cfg)
-{
+__global__ void __launch_bounds__(32) k_myers_large(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, LfLargeCfg cfg,
+                                                    const uint32_t *__restrict__ count_ptr)
+{   /* count_ptr != nullptr: `order + first` is a dense list whose length a previous kernel on the stream left there (the
+     * tasks k_myers_bandreg could not certify: a warp finishes one of them in a fraction of the time a single thread
+     * of the full-width kernel would, and that latency is the tail of the step) */
     const int lane = threadIdx.x & 31;
+    if (count_ptr) count = *count_ptr;
     uint8_t *scr = cfg.base + (unsigned long long)blockIdx.x * cfg.stride;
     for (;;) {
         uint32_t k = 0;
@@ -2060,57 +2064,72 @@ __device__ __forceinline__ void lf_bandreg_column(uint32_t (&Pv)[NB], uint32_t (
     }
 }
 
-/* One block of n <= 8 columns starting with the stream window tb.  (rline, racc) = divmod(c*q, t) of the
- * block's first column c on entry and of c+n on exit; k follows the band.  FWD accumulates the vertical
- * deltas that leave through the top of the band (the distance needs them); STORE writes the window planes. */
-template <int NB, bool FWD, bool STORE>
-__device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], uint32_t (&qlo)[NB], uint32_t (&qhi)[NB], uint32_t (&qnn)[NB],
-                                                 uint32_t tb, int n, int &k, int &rline, int &racc, int &top, int t, int dq, int dr, int q8, int r8,
-                                                 int kmax, int nw, const LfDev &d, const LfQView &qv, uint32_t *smt, int wtop)
+/* Column at whose start the band slides from k to k+1: the first c with floor((c+1)*q/t) - 16*NB + 16 >= 32*(k+1)
+ * (the per-column rule of k_myers_band, solved for c: one division per slide instead of a test per column). */
+template <int NB>
+__device__ __forceinline__ int lf_bandreg_next_slide(int k, int kmax, int q, int t)
 {
-    constexpr int C = 8;
+    if (k >= kmax) return 0x7fffffff;
+    const uint32_t R = (uint32_t)(32 * (k + 1) + 16 * NB - 16);
+    return (int)((R * (uint32_t)t + (uint32_t)q - 1u) / (uint32_t)q) - 1;
+}
+
+/* One block of n <= 8 columns starting at column c with the stream window tb.  A slide (register moves plus the
+ * plane words of one more query word) sits behind a test that is uniform for the warp unless one of its tasks
+ * slides at this very column.
+ * FWD accumulates the vertical deltas that leave through the top of the band (the distance needs them); STORE
+ * writes the window planes. */
+template <int NBF, int NB, bool FWD, bool STORE, bool FULL>
+__device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv_)[NBF], uint32_t (&Mv_)[NBF], uint32_t (&qlo_)[NBF], uint32_t (&qhi_)[NBF], uint32_t (&qnn_)[NBF],
+                                                 uint32_t tb, int c, int n, int &k, int &cslide, int &top, int q, int t, int kmax,
+                                                 const LfDev &d, const LfQView &qv, uint32_t *smt, int wtop)
+{ /* NBF: words of the band; NB <= NBF: the top words of it this call computes (the traceback needs none below its row:
+   * a word only feeds the words under it, and a word that slides in uncomputed lies below the row as well) */
+    static_assert(NB <= NBF, "");
+    uint32_t (&Pv)[NB] = reinterpret_cast<uint32_t (&)[NB]>(Pv_);
+    uint32_t (&Mv)[NB] = reinterpret_cast<uint32_t (&)[NB]>(Mv_);
+    uint32_t (&qlo)[NB] = reinterpret_cast<uint32_t (&)[NB]>(qlo_);
+    uint32_t (&qhi)[NB] = reinterpret_cast<uint32_t (&)[NB]>(qhi_);
+    uint32_t (&qnn)[NB] = reinterpret_cast<uint32_t (&)[NB]>(qnn_);
     constexpr int CS = 2 * 2 * 128;
-    int rl8 = rline + q8, ra8 = racc + r8;
-    if (ra8 >= t) { ra8 -= t; rl8++; }
-    int kn8 = (rl8 - 16 * NB + 16) >> 5;
-    kn8 = kn8 < 0 ? 0 : kn8 > kmax ? kmax : kn8;
-    if (n == C && kn8 == k) { /* the band stays where it is */
-        const int wrel0 = wtop - k;
-#pragma unroll
-        for (int e = 0; e < C; e++) {
-            const uint32_t shi = (uint32_t)((int32_t)(tb << (2 * e)) >> 31), slo = (uint32_t)((int32_t)(tb << (2 * e + 1)) >> 31);
-            lf_bandreg_column<NB, STORE>(Pv, Mv, qlo, qhi, qnn, slo, shi, STORE ? smt + e * CS : nullptr, wrel0);
+    const int es = cslide - c;                         /* the block slides before its column es, if 0 <= es < n */
+    const int nn = FULL ? 8 : n;
+    /* One copy of the column body (unrolled by two) and one of the slide: ~20 size-class kernels share an SM's
+     * instruction cache when the classes run concurrently, and fully unrolled 8-column bodies (13-50 KB per kernel)
+     * made all of them stall on instruction fetches. */
+    int e = 0;
+    int stop = (unsigned)es < (unsigned)nn ? es : nn;
+    for (;;) {
+#pragma unroll 2
+        for (; e < stop; e++) {
+            const uint32_t shi = (uint32_t)((int32_t)tb >> 31), slo = (uint32_t)((int32_t)(tb << 1) >> 31);
+            tb <<= 2;
+            lf_bandreg_column<NB, STORE>(Pv, Mv, qlo, qhi, qnn, slo, shi, STORE ? smt + e * CS : nullptr, wtop - k);
         }
-        rline = rl8; racc = ra8;
-        return;
-    }
-    for (int e = 0; e < n; e++) {
-        rline += dq; racc += dr;
-        if (racc >= t) { racc -= t; rline++; }
-        int kn = (rline - 16 * NB + 16) >> 5;
-        kn = kn < 0 ? 0 : kn > kmax ? kmax : kn;
-        if (kn != k) { /* slide one word down: the top word's vertical deltas move into `top` */
-            if (FWD) top += __popc(Pv[0]) - __popc(Mv[0]);
+        if (e >= nn) break;
+        /* slide one word down: the top word's vertical deltas move into `top` */
+        if (FWD) top += __popc(Pv[0]) - __popc(Mv[0]);
 #pragma unroll
-            for (int w = 0; w + 1 < NB; w++) { Pv[w] = Pv[w + 1]; Mv[w] = Mv[w + 1]; qlo[w] = qlo[w + 1]; qhi[w] = qhi[w + 1]; qnn[w] = qnn[w + 1]; }
-            Pv[NB - 1] = 0xffffffffu; Mv[NB - 1] = 0u;
-            k++;
-            if (k + NB - 1 < nw) lf_q32(d, qv, (int64_t)(k + NB - 1) * 32, qlo[NB - 1], qhi[NB - 1], qnn[NB - 1]);
-            else { qlo[NB - 1] = 0; qhi[NB - 1] = 0; qnn[NB - 1] = 0xffffffffu; }
-        }
-        const uint32_t shi = (uint32_t)((int32_t)tb >> 31), slo = (uint32_t)((int32_t)(tb << 1) >> 31);
-        tb <<= 2;
-        lf_bandreg_column<NB, STORE>(Pv, Mv, qlo, qhi, qnn, slo, shi, STORE ? smt + e * CS : nullptr, wtop - k);
+        for (int w = 0; w + 1 < NB; w++) { Pv[w] = Pv[w + 1]; Mv[w] = Mv[w + 1]; }
+        Pv[NB - 1] = 0xffffffffu; Mv[NB - 1] = 0u;
+#pragma unroll
+        for (int w = 0; w + 1 < NBF; w++) { qlo_[w] = qlo_[w + 1]; qhi_[w] = qhi_[w + 1]; qnn_[w] = qnn_[w + 1]; }   /* the query words of the whole band stay in step */
+        k++;
+        lf_q32(d, qv, (int64_t)(k + NBF - 1) * 32, qlo_[NBF - 1], qhi_[NBF - 1], qnn_[NBF - 1]);   /* k <= kmax: word k+NBF-1 <= nw-1 */
+        stop = nn;
     }
+    /* slides are more than 8 columns apart (q < 4t: 32 rows of the line take more than 8 columns), so a block holds
+     * at most one and the next one is looked up once, here */
+    if ((unsigned)es < (unsigned)n) cslide = lf_bandreg_next_slide<NBF>(k, kmax, q, t);
 }
 
 template <int NB>
 __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count,
-                                                       uint32_t *retry_list, uint32_t *retry_count)
+                                                       uint32_t *retry_list, uint32_t *retry_count, int nwmax)
 {
     constexpr int C = 8;
     constexpr int CS = 2 * 2 * 128; /* shared-memory words per column: [2 window words][2 planes][128 threads] */
-    LF_DYN_SMEM(uint32_t, smem);    /* [C][2][2][128] */
+    LF_DYN_SMEM(uint32_t, smem);    /* window planes [C][2][2][128] */
     const uint32_t tid = threadIdx.x;
     const uint32_t gi = blockIdx.x * 128u + tid;
     if (gi >= count) return;
@@ -2121,12 +2140,11 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     const int kmax = nw > NB ? nw - NB : 0;   /* 0: the band is the whole column and the result needs no certificate */
     const int dlt = q > t ? q - t : t - q;
     const int cert = 32 * (NB - 1) - 7 - dlt;
-    const int dq = q / t, dr = q % t;         /* the line's row advances dq (+1 on carry) per column */
-    if (kmax > 0 && (dq >= 32 || cert < 0)) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
-    const int q8 = (int)((8u * (uint32_t)q) / (uint32_t)t), r8 = (int)((8u * (uint32_t)q) % (uint32_t)t);
+    if (nw > nwmax || (kmax > 0 && (q >= 4 * t || cert < 0))) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
     LfQView qv; LfTView tv;
     lf_task_views(d, task, qv, tv);
 
+    uint32_t *smt = smem + tid;
     uint32_t qlo[NB], qhi[NB], qnn[NB], Pv[NB], Mv[NB];
 #pragma unroll
     for (int w = 0; w < NB; w++) {
@@ -2136,22 +2154,31 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     }
     const int wl = (q - 1) >> 5;
     const uint32_t bl = (uint32_t)(q - 1) & 31u;
-    int k = 0, rline = 0, racc = 0, top = 0;
+    int k = 0, top = 0;
+    int cslide = lf_bandreg_next_slide<NB>(0, kmax, q, t);
     uint2 *ck = (uint2 *)(d.scratch + d.scr_off[ti]);
 
     /* ---- forward pass ---- */
     LfTStream ts;
     ts.init(d.pac, tv.t0, tv.dir);
-    for (int c = 0; c < t; c += C) {
-        const int n = t - c < C ? t - c : C;
+    int c = 0;
+    for (; c + C <= t; c += C) {
         if (c) {
             uint2 *dst = ck + (size_t)(c / C - 1) * NB;
 #pragma unroll
             for (int w = 0; w < NB; w++) dst[w] = make_uint2(Pv[w], Mv[w]);
         }
         const uint32_t tb = ts.peek();
-        ts.advance(n);
-        lf_bandreg_block<NB, true, false>(Pv, Mv, qlo, qhi, qnn, tb, n, k, rline, racc, top, t, dq, dr, q8, r8, kmax, nw, d, qv, nullptr, 0);
+        ts.advance(C);
+        lf_bandreg_block<NB, NB, true, false, true>(Pv, Mv, qlo, qhi, qnn, tb, c, C, k, cslide, top, q, t, kmax, d, qv, nullptr, 0);
+    }
+    if (c < t) {
+        if (c) {
+            uint2 *dst = ck + (size_t)(c / C - 1) * NB;
+#pragma unroll
+            for (int w = 0; w < NB; w++) dst[w] = make_uint2(Pv[w], Mv[w]);
+        }
+        lf_bandreg_block<NB, NB, true, false, false>(Pv, Mv, qlo, qhi, qnn, ts.peek(), c, t - c, k, cslide, top, q, t, kmax, d, qv, nullptr, 0);
     }
     int ed = t + top;
 #pragma unroll
@@ -2175,16 +2202,17 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     int sh = 30;
 #define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
     int i = q, j = t;
-    uint32_t *smt = smem + tid;
+    const int q8 = (int)((8u * (uint32_t)q) / (uint32_t)t), r8 = (int)((8u * (uint32_t)q) % (uint32_t)t);
     int bc0 = ((t - 1) / C) * C;                 /* block the band bookkeeping below refers to */
     int rl0 = (int)(((uint32_t)bc0 * (uint32_t)q) / (uint32_t)t), ra0 = (int)(((uint32_t)bc0 * (uint32_t)q) % (uint32_t)t);
+    int ks = -1, cs_of_ks = 0;                   /* memo of lf_bandreg_next_slide */
     bool lost = false;
     while (i > 0 && j > 0) {
         const int c1 = j, c0 = ((j - 1) / C) * C;
         while (bc0 > c0) { bc0 -= C; rl0 -= q8; ra0 -= r8; if (ra0 < 0) { ra0 += t; rl0--; } }
-        int k0 = (rl0 - 16 * NB + 16) >> 5;       /* band position after column c0-1 */
+        int k0 = (rl0 - 16 * NB + 16) >> 5;       /* band position after column c0-1: floor(c0*q/t) decides */
         k0 = k0 < 0 ? 0 : k0 > kmax ? kmax : k0;
-        while (k != k0) { /* bring the query words of that band position into the registers */
+        while (k != k0) { /* bring the query words of that band position into the registers (one word per ~32 columns) */
             if (k > k0) {
                 k--;
 #pragma unroll
@@ -2198,19 +2226,26 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
                 else { qlo[NB - 1] = 0; qhi[NB - 1] = 0; qnn[NB - 1] = 0xffffffffu; }
             }
         }
+        if (ks != k0) { ks = k0; cs_of_ks = lf_bandreg_next_slide<NB>(k0, kmax, q, t); }
+        cslide = cs_of_ks;
+        const int whi = (i - 1) >> 5;
+        const int wtop = whi - 1 > 0 ? whi - 1 : 0;
+        const int need = whi - k0 + 1;            /* band words down to the row the walk stands on */
         if (c0 == 0) {
 #pragma unroll
             for (int w = 0; w < NB; w++) { Pv[w] = 0xffffffffu; Mv[w] = 0u; }
         } else {
             const uint2 *src = ck + (size_t)(c0 / C - 1) * NB;
 #pragma unroll
-            for (int w = 0; w < NB; w++) { const uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; }
+            for (int w = 0; w < NB; w++) { if (w < need) { const uint2 v = src[w]; Pv[w] = v.x; Mv[w] = v.y; } }
         }
-        const int whi = (i - 1) >> 5;
-        const int wtop = whi - 1 > 0 ? whi - 1 : 0;
         ts.init(d.pac, tv.t0 + (int64_t)tv.dir * c0, tv.dir);
-        rline = rl0; racc = ra0;
-        lf_bandreg_block<NB, false, true>(Pv, Mv, qlo, qhi, qnn, ts.peek(), c1 - c0, k, rline, racc, top, t, dq, dr, q8, r8, kmax, nw, d, qv, smt, wtop);
+        const uint32_t tb = ts.peek();
+        constexpr int N1 = NB > 2 ? NB - 1 : NB, N2 = NB > 3 ? NB - 2 : N1;
+        if (c1 - c0 != C) lf_bandreg_block<NB, NB, false, true, false>(Pv, Mv, qlo, qhi, qnn, tb, c0, c1 - c0, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else if (N2 < N1 && need <= N2) lf_bandreg_block<NB, N2, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else if (N1 < NB && need <= N1) lf_bandreg_block<NB, N1, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else lf_bandreg_block<NB, NB, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         /* walk inside the window, one word-row at a time */
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {

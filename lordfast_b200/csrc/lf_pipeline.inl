@@ -20,7 +20,7 @@
 #include "lf_backend.h"
 
 #ifndef LF_NSUB
-#define LF_NSUB 18
+#define LF_NSUB 24
 #endif
 struct DevState {
     int dev = 0;
@@ -32,6 +32,7 @@ struct DevState {
     bool cls_ran[LF_NCLS] = {};
     LfbBuf pac, bases, read_off, plo, phi, pnn;
     LfbBuf planes, gbytes, goff;   /* k_myers_band: plane regions per warp group */
+    LfbBuf retry_scr;              /* warp slots of the k_myers_large instances that redo what k_myers_bandreg could not certify */
     LfbBuf res_keep, ops_keep;   /* lf_chain.inl parks the round-1 results / op stream here while round 3 runs */
     LfbBuf tasks, res, ops, keys, keys2, idx, idx2, slot_words, scr_bytes, slot_end, scr_off, scratch, large_scr, counters, queue;
     LfbBuf etasks, eres, escr_items, escr_off, escr;
@@ -69,12 +70,21 @@ int fail(lf_gpu_ctx *c, int code, const char *msg)
 }
 #define LF_TRY(expr) do { int rc_ = (expr); if (rc_ != 0) return fail(ctx, rc_ == -5 ? LF_ERR_NOMEM : LF_ERR_CUDA, #expr); } while (0)
 
-/* k_myers_bandreg for the near-diagonal global tasks with 128 < q <= 512 (LF_BANDREG=0 turns it off: those tasks
- * then run full width in k_myers_small, which is also the retry path of the ones the band cannot certify) */
-bool bandreg_on()
-{
+#ifndef LF_BANDREG_DEFAULT
+#define LF_BANDREG_DEFAULT 0xe   /* NW = 8, 12, 16 classes; measured neutral for NW = 6 in the config-2 mix (profiles/r02c) */
+#endif
+/* Size classes whose near-diagonal global tasks run in k_myers_bandreg (LF_BANDREG overrides; the other tasks of
+ * 128 < q <= 512 run full width in k_myers_small, which is also the retry path of the tasks the band cannot certify) */
+uint32_t bandreg_on()
+{   /* bit i: size class 4+i (NW = 6, 8, 12, 16) */
     const char *e = getenv("LF_BANDREG");
-    return !e || atoi(e) != 0;
+    return e ? (uint32_t)strtoul(e, nullptr, 0) & 15u : (uint32_t)LF_BANDREG_DEFAULT;
+}
+
+bool bandreg_small()
+{
+    const char *e = getenv("LF_BANDREG_SMALL");
+    return e && atoi(e) != 0;
 }
 
 LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
@@ -90,9 +100,12 @@ LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
     v.scr_off = d.scr_off.as<uint64_t>();
     v.scratch = d.scratch.as<uint8_t>();
     v.planes = d.planes.as<uint8_t>();
-    v.bandreg = bandreg_on() ? 1u : 0u;
+    v.bandreg = bandreg_on();
     return v;
 }
+
+size_t align_up(size_t v, size_t a);
+LfLargeCfg large_cfg(size_t mq, size_t mt, size_t max_planes);
 
 template <int CI, bool SHW>
 void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, const uint32_t *retry_count)
@@ -106,11 +119,11 @@ void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_
 }
 
 template <int NB>
-void launch_bandreg(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, uint32_t *retry_list, uint32_t *retry_count)
-{
+void launch_bandreg(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, uint32_t *retry_list, uint32_t *retry_count, int nwmax)
+{   /* shared memory: the window planes of 8 columns, as much as the other size-class kernels use */
     const size_t smem = (size_t)8 * 2 * 2 * 128 * sizeof(uint32_t);
     auto kern = k_myers_bandreg<NB>;
-    LFB_LAUNCH(kern, (count + 127) / 128, 128, smem, s, v, order, first, count, retry_list, retry_count);
+    LFB_LAUNCH(kern, (count + 127) / 128, 128, smem, s, v, order, first, count, retry_list, retry_count, nwmax);
 }
 
 template <int NB, bool BANDED, bool SHW>
@@ -149,6 +162,14 @@ uint32_t band_mask()
 void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase,
                         const unsigned long long *goff, lfb_stream s, uint32_t *rl, uint32_t *rc, uint32_t bmask)
 {   /* rl: retry list (indexed like `order`), rc: this class's retry counter */
+    if (cls < 8 && !(cls & 1) && bandreg_small()) {   /* global-mode tasks of q <= 128: the band is the whole column (no slides, no certificate) */
+        switch (cls) {
+        case 0: launch_bandreg<1>(v, order, first, count, s, rl, rc, 1); return;
+        case 2: launch_bandreg<2>(v, order, first, count, s, rl, rc, 2); return;
+        case 4: launch_bandreg<3>(v, order, first, count, s, rl, rc, 3); return;
+        case 6: launch_bandreg<4>(v, order, first, count, s, rl, rc, 4); return;
+        }
+    }
     if (cls < LF_CLS_LARGE && band_nb(cls) && (bmask >> cls & 1u)) {
         switch (cls) {
         case 0: launch_band<1, false, false>(v, order, first, count, gbase, goff, s, rl, rc); return;
@@ -168,11 +189,11 @@ void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t
         }
     }
     switch (cls) {
-    /* sliding band in registers, then the full-width kernel over the dense list of tasks the band could not certify */
-    case LF_CLS_BANDREG0 + 0: launch_bandreg<3>(v, order, first, count, s, rl, rc); launch_small<4, false>(v, rl, first, count, s, rc); break;
-    case LF_CLS_BANDREG0 + 1: launch_bandreg<4>(v, order, first, count, s, rl, rc); launch_small<5, false>(v, rl, first, count, s, rc); break;
-    case LF_CLS_BANDREG0 + 2: launch_bandreg<4>(v, order, first, count, s, rl, rc); launch_small<6, false>(v, rl, first, count, s, rc); break;
-    case LF_CLS_BANDREG0 + 3: launch_bandreg<5>(v, order, first, count, s, rl, rc); launch_small<7, false>(v, rl, first, count, s, rc); break;
+    /* sliding band in registers; the caller then runs k_myers_large over the dense list of tasks the band could not certify */
+    case LF_CLS_BANDREG0 + 0: launch_bandreg<3>(v, order, first, count, s, rl, rc, 6); break;
+    case LF_CLS_BANDREG0 + 1: launch_bandreg<4>(v, order, first, count, s, rl, rc, 8); break;
+    case LF_CLS_BANDREG0 + 2: launch_bandreg<4>(v, order, first, count, s, rl, rc, 12); break;
+    case LF_CLS_BANDREG0 + 3: launch_bandreg<5>(v, order, first, count, s, rl, rc, 16); break;
     case 0: launch_small<0, false>(v, order, first, count, s, nullptr); break;
     case 1: launch_small<0, true>(v, order, first, count, s, nullptr); break;
     case 2: launch_small<1, false>(v, order, first, count, s, nullptr); break;
@@ -194,6 +215,20 @@ void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+LfLargeCfg large_cfg(size_t mq, size_t mt, size_t max_planes)
+{   /* layout of one warp slot of k_myers_large for tasks of up to mq x mt */
+    LfLargeCfg cfg;
+    size_t off = align_up(max_planes + 256, 256);
+    cfg.off_hb = off; off = align_up(off + mt + 64, 256);
+    cfg.off_L = off; off = align_up(off + (mq + 2) * 4, 256);
+    cfg.off_R = off; off = align_up(off + (mq + 2) * 4, 256);
+    cfg.off_opsb = off; off = align_up(off + mq + mt + 64, 256);
+    cfg.off_stack = off; off = align_up(off + LF_LARGE_STACK * 5 * 4, 256);
+    cfg.stride = off;
+    cfg.base = nullptr; cfg.queue = nullptr;
+    return cfg;
+}
 
 int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 {
@@ -264,15 +299,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     for (int cls = 0; cls < LF_CLS_LARGE; cls++) nsmall += ht->cnt.hist[cls];
     const uint32_t nlarge = ht->cnt.hist[LF_CLS_LARGE];
     if (nlarge) {
-        LfLargeCfg cfg;
-        const size_t mq = ht->cnt.max_q, mt = ht->cnt.max_t;
-        size_t off = align_up((size_t)ht->cnt.max_planes + 256, 256);
-        cfg.off_hb = off; off = align_up(off + mt + 64, 256);
-        cfg.off_L = off; off = align_up(off + (mq + 2) * 4, 256);
-        cfg.off_R = off; off = align_up(off + (mq + 2) * 4, 256);
-        cfg.off_opsb = off; off = align_up(off + mq + mt + 64, 256);
-        cfg.off_stack = off; off = align_up(off + LF_LARGE_STACK * 5 * 4, 256);
-        cfg.stride = off;
+        LfLargeCfg cfg = large_cfg(ht->cnt.max_q, ht->cnt.max_t, ht->cnt.max_planes);
         /* persistent grid of warp slots; bounded so that the scratch stays within a few GB */
         size_t slots = 148 * 16;
         const size_t budget = (size_t)8 << 30;
@@ -285,7 +312,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][0], d.sub[0]);
 #endif
-        LFB_LAUNCH(k_myers_large, (unsigned)slots, 32, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg);
+        LFB_LAUNCH(k_myers_large, (unsigned)slots, 32, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg, (const uint32_t *)nullptr);
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][1], d.sub[0]);
 #endif
@@ -298,18 +325,28 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         for (int cls = 0; cls < LF_NCLS; cls++) { firsts[cls] = first; first += ht->cnt.hist[cls]; }   /* sorted order = class id order */
         int k = 0;
         int seq[LF_NCLS], nseq = 0;
+        const bool serial = getenv("LF_SERIAL") != nullptr;
         for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
         for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) seq[nseq++] = cls;
         for (int si = 0; si < nseq; si++) {
             const int cls = seq[si];
             const uint32_t count = ht->cnt.hist[cls];
             if (!count) continue;
-            lfb_stream st = d.sub[1 + (k % (LF_NSUB - 1))];
+            lfb_stream st = serial ? d.sub[1] : d.sub[1 + (k % (LF_NSUB - 1))];   /* LF_SERIAL=1: one class at a time (per-class durations for profiling) */
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
             launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, cls < LF_CLS_LARGE ? gc.gbase[cls] : 0u, d.goff.as<unsigned long long>(), st,
                                d.idx.as<uint32_t>() /* input of the sort, free by now */, d.queue.as<uint32_t>() + 1 + cls, bmask);
+            if (cls >= LF_CLS_BANDREG0) {   /* the uncertified few: warp per task, on the same stream */
+                const int bi = cls - LF_CLS_BANDREG0;
+                LfLargeCfg rcfg = large_cfg(512, 640, (size_t)lf_large_planes_bytes(512, 640));   /* eligible tasks: q <= 512, |q-t| <= 40 */
+                const size_t rslots = 148;
+                LF_TRY(d.retry_scr.reserve(4 * rslots * rcfg.stride));
+                rcfg.base = d.retry_scr.as<uint8_t>() + (size_t)bi * rslots * rcfg.stride;
+                rcfg.queue = d.queue.as<uint32_t>() + 32 + bi;
+                LFB_LAUNCH(k_myers_large, (unsigned)rslots, 32, 0, st, v, d.idx.as<uint32_t>(), firsts[cls], count, rcfg, (const uint32_t *)(d.queue.as<uint32_t>() + 1 + cls));
+            }
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][1], st);
 #endif

@@ -200,7 +200,7 @@ def _near_diagonal_batch(rng, ref, n, lo=129, hi=512):
     return reads, np.array(tasks, dtype=api.ALIGN_TASK)
 
 
-@pytest.mark.parametrize("bandreg", ["1", "0"])
+@pytest.mark.parametrize("bandreg", ["0xf", "0"])
 def test_emu_bandreg_near_diagonal(emu_lib, monkeypatch, bandreg):
     """k_myers_bandreg (sliding register band, checkpoints + recompute) on near-diagonal global tasks of 129..512
     rows, and the same batch with the kernel switched off (full width): both must match the oracle."""
@@ -219,7 +219,7 @@ def test_emu_bandreg_near_diagonal(emu_lib, monkeypatch, bandreg):
     assert not bad, bad[:10]
     ok, rt = C.c_ulong(), C.c_ulong()
     g.lib.lf_emu_band_counts(C.byref(ok), C.byref(rt))
-    if bandreg == "1":
+    if bandreg == "0xf":
         assert ok.value - ok0.value > 250, (ok.value - ok0.value, rt.value - rt0.value)   # certified in the band
         assert rt.value - rt0.value > 5                                                    # and some redone full width
     else:

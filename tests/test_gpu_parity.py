@@ -199,7 +199,7 @@ def test_gpu_full_size_properties():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bandreg", ["1", "0"])
+@pytest.mark.parametrize("bandreg", ["0xf", "0"])
 def test_gpu_bandreg_near_diagonal(bandreg, monkeypatch):
     """k_myers_bandreg (sliding band in registers) on 4000 near-diagonal global tasks of 129..512 rows with every
     strand / direction flag, plus pairs whose path bulges out of the band (redone full width); and the same batch
