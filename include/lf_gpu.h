@@ -115,6 +115,11 @@ int  lf_gpu_init(lf_gpu_ctx **ctx, const uint8_t *pac, int64_t l_pac, const int 
 void lf_gpu_destroy(lf_gpu_ctx *ctx);
 const char *lf_gpu_last_error(const lf_gpu_ctx *ctx);
 
+/* Starts CUDA (driver, context, module load: seconds on a cold box) on a background thread and returns at once, so
+ * that it overlaps the caller's own start-up -- lordFAST calls it first thing and then loads its index
+ * (bwt_load, src/baseFAST.cpp:56); lf_gpu_init joins it.  Optional; safe to call more than once. */
+void lf_gpu_prewarm(void);
+
 /* Pinned host memory for task / result / op buffers (pageable memory works, pinned is faster). */
 void *lf_gpu_host_alloc(size_t bytes);
 void  lf_gpu_host_free(void *p);

@@ -26,10 +26,30 @@
 #include "LordFAST.cpp" /* -I$(REF)/src : the reference's own file, read where it lies */
 #undef mapSeqMT
 
+#include <thread>
 #include "bwa.h"
 #include "lf_gpu.h"
 
 extern bwaidx_t *_fmd_index; /* src/BWT.cpp:32 */
+
+/* CUDA start-up (seconds on a cold box) overlaps the index load: this runs before main() of src/baseFAST.cpp */
+__attribute__((constructor)) static void lfglue_prewarm(int argc, char **argv, char **)
+{
+    for (int i = 1; i < argc; i++) if (!strcmp(argv[i], "--search") || !strcmp(argv[i], "-S")) {
+        /* the driver initialises every GPU it can see (seconds on an 8-GPU box): show it only the ones asked for */
+        if (!getenv("CUDA_VISIBLE_DEVICES")) {
+            const char *e = getenv("LF_GPU_DEVICES");
+            setenv("CUDA_VISIBLE_DEVICES", e ? e : "0", 0);
+            if (e) { /* the library then sees them renumbered 0..n-1 */
+                std::string r; int n = 1; for (const char *p = e; *p; p++) n += *p == ',';
+                for (int k = 0; k < n; k++) { if (k) r += ","; r += std::to_string(k); }
+                setenv("LF_GPU_DEVICES", r.c_str(), 1);
+            }
+        }
+        lf_gpu_prewarm();
+        return;
+    }
+}
 
 namespace lfglue {
 
@@ -162,12 +182,12 @@ static void finish_window(const Worker &W, const WinPlan &wp, uint32_t rLen, Sam
     const uint64_t c = W.chain_base + (uint64_t)wp.chain;
     for (uint64_t k = g_rec_first[c]; k < g_rec_first[c + 1]; k++) {
         const lf_sam_record &r = g_rec[k];
-        Sam_t s;
+        map.samList.emplace_back();
+        Sam_t &s = map.samList.back();
         s.flag = (uint16_t)r.flag; s.pos = r.pos; s.posEnd = r.posEnd;
         s.qStart = r.qStart; s.qEnd = r.qEnd; s.nmCount = r.nmCount;
         s.cigar.assign(g_text + r.cigar_off, r.cigar_len);
         s.md.assign(g_text + r.md_off, r.md_len);
-        map.samList.push_back(s);
     }
     map.totalScore = 0;
     if (map.samList.empty()) return; /* the reference indexes an empty list here (:1073); never seen */
@@ -237,8 +257,10 @@ void mapSeqMT()
         int ndev = 0, devs[16];
         if (const char *e = getenv("LF_GPU_DEVICES")) /* e.g. "0,1,2,3"; default: the current device */
             for (char *p = (char *)e; *p && ndev < 16;) { devs[ndev++] = (int)strtol(p, &p, 10); if (*p == ',') p++; }
+        const double ti = now_ms();
         int rc = lf_gpu_init(&g_ctx, _fmd_index->pac, _fmd_index->bns->l_pac, ndev ? devs : nullptr, ndev);
         if (rc != LF_OK) die("lf_gpu_init", rc);
+        fprintf(stderr, "[lordfast-gpu: lf_gpu_init %.1f ms] ", now_ms() - ti);
     }
     const double t0 = now_ms();
     g_workers.assign(THREAD_COUNT, Worker());
@@ -257,9 +279,23 @@ void mapSeqMT()
     }
     std::vector<uint64_t> off(_pf_seqListSize + 1, 0);
     for (int r = 0; r < _pf_seqListSize; r++) off[r + 1] = off[r] + *_pf_seqList[r].length;
-    uint8_t *bases = (uint8_t *)lf_gpu_host_alloc(off[_pf_seqListSize] + 1);
-    if (!bases) die("lf_gpu_host_alloc", LF_ERR_NOMEM);
-    for (int r = 0; r < _pf_seqListSize; r++) memcpy(bases + off[r], _pf_seqList[r].seq, *_pf_seqList[r].length);
+    static uint8_t *bases = nullptr;   /* pinned, kept between chunks (pinning 100 MB costs tens of ms) */
+    static size_t bases_cap = 0;
+    if (off[_pf_seqListSize] + 1 > bases_cap) {
+        if (bases) lf_gpu_host_free(bases);
+        bases_cap = (off[_pf_seqListSize] + 1) * 5 / 4;
+        bases = (uint8_t *)lf_gpu_host_alloc(bases_cap);
+        if (!bases) die("lf_gpu_host_alloc", LF_ERR_NOMEM);
+    }
+    {   /* gather with all host threads */
+        std::vector<std::thread> th;
+        const int nt = THREAD_COUNT > 1 ? THREAD_COUNT : 1;
+        for (int k = 0; k < nt; k++) th.emplace_back([&, k] {
+            for (int r = (int)((int64_t)_pf_seqListSize * k / nt); r < (int)((int64_t)_pf_seqListSize * (k + 1) / nt); r++)
+                memcpy(bases + off[r], _pf_seqList[r].seq, *_pf_seqList[r].length);
+        });
+        for (auto &t : th) t.join();
+    }
     const bntseq_t *bns = _fmd_index->bns;
     std::vector<int64_t> coff(bns->n_seqs);
     std::vector<int32_t> clen(bns->n_seqs);
@@ -283,7 +319,6 @@ void mapSeqMT()
 
     run_threads(emit);
     if (res) lf_chain_results_free(res);
-    lf_gpu_host_free(bases);
     const double t3 = now_ms();
     g_ms[0] += t1 - t0; g_ms[1] += t2 - t1; g_ms[2] += t3 - t2;
     fprintf(stderr, "[lordfast-gpu: %llu chains, front-end %.1f ms, GPU alignment stage %.1f ms, scoring+SAM %.1f ms] ",

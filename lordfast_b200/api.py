@@ -57,7 +57,7 @@ class Stats(C.Structure):
                 ("last_main_kernel_ms", C.c_float), ("last_main_word_columns", C.c_uint64)]
 
 
-EXPORTS = ["lf_gpu_init", "lf_gpu_destroy", "lf_gpu_last_error", "lf_gpu_host_alloc", "lf_gpu_host_free",
+EXPORTS = ["lf_gpu_init", "lf_gpu_prewarm", "lf_gpu_destroy", "lf_gpu_last_error", "lf_gpu_host_alloc", "lf_gpu_host_free",
            "lf_gpu_ops_capacity", "lf_gpu_align_batch", "lf_gpu_extend_batch", "lf_gpu_upload_reads",
            "lf_gpu_upload_align_tasks", "lf_gpu_run_align", "lf_gpu_sync", "lf_gpu_download_align",
            "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",

@@ -13,7 +13,9 @@
  * reads are replicated, no collective is involved.
  */
 #include <stdio.h>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "lf_gpu.h"
 #include "lf_kernels.cuh"
@@ -326,13 +328,15 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         int k = 0;
         int seq[LF_NCLS], nseq = 0;
         const bool serial = getenv("LF_SERIAL") != nullptr;
+        int nstreams = getenv("LF_STREAMS") ? atoi(getenv("LF_STREAMS")) : LF_NSUB - 1;   /* class kernels in flight at once */
+        if (nstreams < 1 || nstreams > LF_NSUB - 1) nstreams = LF_NSUB - 1;
         for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
         for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) seq[nseq++] = cls;
         for (int si = 0; si < nseq; si++) {
             const int cls = seq[si];
             const uint32_t count = ht->cnt.hist[cls];
             if (!count) continue;
-            lfb_stream st = serial ? d.sub[1] : d.sub[1 + (k % (LF_NSUB - 1))];   /* LF_SERIAL=1: one class at a time (per-class durations for profiling) */
+            lfb_stream st = serial ? d.sub[1] : d.sub[1 + (k % nstreams)];   /* LF_SERIAL=1: one class at a time (per-class durations for profiling) */
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
@@ -366,11 +370,20 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 } // namespace
 
 /* ---------------------------------------------------------------------------------------------- */
+#ifndef LF_EMU
+static std::mutex g_prewarm_mu;
+static std::thread g_prewarm;
+static bool g_prewarm_started = false;
+#endif
+
 extern "C" {
 
 int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *devices, int n_devices)
 {
     if (!out || !pac || l_pac <= 0) return LF_ERR_BAD_ARG;
+#ifndef LF_EMU
+    { std::lock_guard<std::mutex> g(g_prewarm_mu); if (g_prewarm.joinable()) g_prewarm.join(); }
+#endif
     *out = nullptr;
     lfb_errbuf[0] = 0;
     std::vector<int> devs;
@@ -431,6 +444,23 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
 }
 
 const char *lf_gpu_last_error(const lf_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void lf_gpu_prewarm(void)
+{
+#ifndef LF_EMU
+    std::lock_guard<std::mutex> g(g_prewarm_mu);
+    if (g_prewarm_started) return;
+    g_prewarm_started = true;
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    g_prewarm = std::thread([] {
+        cudaFree(nullptr);                                  /* driver + primary context */
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, (const void *)k_pack_reads);   /* module load */
+        void *p = nullptr;                                  /* first pinned allocation maps the host-memory machinery */
+        if (cudaMallocHost(&p, 1 << 20) == cudaSuccess) cudaFreeHost(p);
+    });
+#endif
+}
 
 void *lf_gpu_host_alloc(size_t bytes) { return lfb_host_alloc(bytes); }
 void lf_gpu_host_free(void *p) { lfb_host_free(p); }

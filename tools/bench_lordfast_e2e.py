@@ -27,7 +27,8 @@ def run(binary, tmp, out, threads, extra):
     wall = time.time() - t0
     mapping = sum(float(x) for x in re.findall(r"done in ([0-9.]+) seconds", p.stderr))
     phases = [tuple(float(v) for v in m) for m in re.findall(r"front-end ([0-9.]+) ms, GPU alignment stage ([0-9.]+) ms, scoring\+SAM ([0-9.]+) ms", p.stderr)]
-    return wall, mapping, phases
+    init = re.findall(r"lf_gpu_init ([0-9.]+) ms", p.stderr)
+    return wall, mapping, phases, float(init[0]) if init else 0.0
 
 
 def main():
@@ -40,12 +41,18 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("-t", "--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--replicate", type=int, default=1, help="write the read set this many times (renamed copies): longer runs, several chunks")
     ap.add_argument("extra", nargs="*")
     a = ap.parse_args()
     tmp = tempfile.mkdtemp(prefix="lfe2e")
     subprocess.check_call([sys.executable, os.path.join(ROOT, "integration", "make_dataset.py"), tmp, "--ref-len", str(a.ref_len), "--reads", str(a.reads),
                            "--read-len", str(a.read_len), "--err", str(a.err[0]), str(a.err[1]), "--sv-frac", str(a.sv_frac), "--seed", str(a.seed)],
                           stdout=subprocess.DEVNULL)
+    if a.replicate > 1:
+        body = open(os.path.join(tmp, "reads.fa")).read()
+        with open(os.path.join(tmp, "reads.fa"), "w") as f:
+            for k in range(a.replicate):
+                f.write(body.replace(">r", ">c%d_r" % k))
     bases = sum(len(l) - 1 for l in open(os.path.join(tmp, "reads.fa")) if not l.startswith(">"))
     t0 = time.time()
     subprocess.check_call([REF_BIN, "--index", "ref.fa"], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -61,10 +68,12 @@ def main():
     ph = best["gpu"][2]
     print(json.dumps({
         "what": "lordfast --search -t N end to end: reference CPU binary vs the same program with the alignment stage on the GPU",
-        "workload": {"ref_len": a.ref_len, "reads": a.reads, "read_len": a.read_len, "err": list(a.err), "sv_frac": a.sv_frac, "read_bases": bases},
+        "workload": {"ref_len": a.ref_len, "reads": a.reads * a.replicate, "replicate": a.replicate, "read_len": a.read_len, "err": list(a.err), "sv_frac": a.sv_frac, "read_bases": bases},
         "threads": a.threads, "host_cores": os.cpu_count(), "index_s": round(t_index, 2),
         "cpu": {"mapping_s": best["cpu"][1], "wall_s": round(best["cpu"][0], 2), "mbp_per_s": round(bases / 1e6 / best["cpu"][1], 2)},
         "gpu": {"mapping_s": best["gpu"][1], "wall_s": round(best["gpu"][0], 2), "mbp_per_s": round(bases / 1e6 / best["gpu"][1], 2),
+                "chunks": len(ph), "lf_gpu_init_ms": best["gpu"][3],
+                "gpu_stage_ms_per_chunk": [p[1] for p in ph],
                 "phases_ms": {"front_end_cpu": sum(p[0] for p in ph), "gpu_alignment_stage": sum(p[1] for p in ph), "scoring_and_sam_cpu": sum(p[2] for p in ph)}},
         "speedup_mapping": round(best["cpu"][1] / best["gpu"][1], 2),
         "sam_records": len(sa), "sam_identical_sorted": sa == sb,
