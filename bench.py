@@ -239,18 +239,19 @@ def main():
         rc = g.lib.lf_gpu_align_chains(g.ctx, C.byref(reads_struct), C.byref(cg), seeds_a.ctypes.data, chains_a.ctypes.data, len(chains_a), pac_ptr, C.byref(out))
         if rc != 0:
             raise SystemExit(f"lf_gpu_align_chains failed: {rc} {g.lib.lf_gpu_last_error(g.ctx).decode()}")
-        nrec = C.c_size_t()
+        nrec, tbytes = C.c_size_t(), C.c_size_t()
         g.lib.lf_chain_results_records(out, C.byref(nrec))
+        g.lib.lf_chain_results_text(out, C.byref(tbytes))
         cst = api.ChainStats()
         g.lib.lf_chain_results_stats(out, C.byref(cst))
         g.lib.lf_chain_results_free(out)
-        return nrec.value, cst
+        return nrec.value, cst, tbytes.value
     chain_step()
     barrier()
     t2 = time.perf_counter()
-    nrec, cst = 0, None
+    nrec, cst, chain_text_bytes = 0, None, 0
     for _ in range(max(2, a.steps // 4)):
-        nrec, cst = chain_step()
+        nrec, cst, chain_text_bytes = chain_step()
     barrier()
     chain_ms = (time.perf_counter() - t2) / max(2, a.steps // 4) * 1e3
     clocks = sampler.finish() if rank == 0 else None
@@ -289,7 +290,8 @@ def main():
             "gcups": cells * world / (wall_ms_max * 1e-3) / 1e9,
             # headline: the reference-facing operator (batched alignChain_edlib), host buffers in, CIGAR/MD/NM records out
             "e2e": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chain_ms_max,
-                    "h2d_bytes_per_step": h2d + int(seeds_a.nbytes + chains_a.nbytes), "d2h_bytes_per_step": d2h, "call": "lf_gpu_align_chains"},
+                    # in: reads + offsets + seeds + chains + the round-1 task list the library derives on the host; out: CIGAR/MD text + records
+                    "h2d_bytes_per_step": h2d + int(seeds_a.nbytes + chains_a.nbytes), "d2h_bytes_per_step": int(chain_text_bytes) + int(nrec) * 56, "call": "lf_gpu_align_chains"},
             "e2e_align_batch": {"value": e2e_v, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max,
                                 "call": "lf_gpu_align_batch (round-1 tasks only: task list in, distances + 2-bit op stream out)"},
             "e2e_chains": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chain_ms_max, "records_per_gpu": int(nrec),

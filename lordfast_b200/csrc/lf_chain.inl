@@ -385,13 +385,18 @@ int emit_write(EmitSet &es, LfEmitDev &E, char *text_dst, uint64_t out_base)
 {
     if (!es.n) return 0;
     lfb_stream st = es.st;
-    if (es.d_recs.reserve((es.nrec + 1) * sizeof(lf_sam_record)) || es.d_text.reserve(es.ncig + es.nmd + 64)) return LF_ERR_NOMEM;
+    /* text_dst is pinned host memory, which the device addresses directly (unified addressing): the kernel's staged,
+     * 16-byte coalesced stores go straight over PCIe while it runs, instead of to HBM and then through a copy of the
+     * whole text (110 MB per config-2 chunk) after it.  LF_EMIT_NO_ZEROCOPY=1 restores the copy. */
+    static const bool zero_copy = !getenv("LF_EMIT_NO_ZEROCOPY");
+    if (es.d_recs.reserve((es.nrec + 1) * sizeof(lf_sam_record)) || (!zero_copy && es.d_text.reserve(es.ncig + es.nmd + 64))) return LF_ERR_NOMEM;
     lf_sam_record *hr = (lf_sam_record *)es.h_recs.reserve((es.nrec + 1) * sizeof(lf_sam_record));
     if (!hr) return LF_ERR_NOMEM;
     E.rec_off = es.d_rec_off.as<uint64_t>(); E.cig_off = es.d_cig_off.as<uint64_t>(); E.md_off = es.d_md_off.as<uint64_t>();
-    E.recs = es.d_recs.as<lf_sam_record>(); E.text = es.d_text.as<char>(); E.out_base = out_base;
+    E.recs = es.d_recs.as<lf_sam_record>(); E.text = zero_copy ? text_dst : es.d_text.as<char>(); E.out_base = out_base;
     { auto kern = k_emit_slots<true>; LFB_LAUNCH(kern, (unsigned)es.n, LF_EMIT_BLOCK, 0, st, E); }
-    if (lfb_d2h(hr, es.d_recs.p, es.nrec * sizeof(lf_sam_record), st) || lfb_d2h(text_dst, es.d_text.p, es.ncig + es.nmd, st)) return LF_ERR_CUDA;
+    if (lfb_d2h(hr, es.d_recs.p, es.nrec * sizeof(lf_sam_record), st)) return LF_ERR_CUDA;
+    if (!zero_copy && lfb_d2h(text_dst, es.d_text.p, es.ncig + es.nmd, st)) return LF_ERR_CUDA;
     return 0;
 }
 
@@ -491,6 +496,10 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     lf_align_result *r1 = gpu_emit ? nullptr : (lf_align_result *)S.r1.reserve((n1 + 1) * sizeof(lf_align_result));
     if (!t1 || (!gpu_emit && !r1)) { delete R; return LF_ERR_NOMEM; }
     std::vector<uint32_t> trig;   /* round-1 tasks whose result fires a clip / split trigger, ascending */
+    const bool spec = gpu_emit && !getenv("LF_CHAIN_NO_SPEC");
+    std::vector<uint32_t> cand_ti, cand_ext;   /* speculative round 2: candidate round-1 tasks (ascending) and their first extension */
+    std::vector<lf_extend_task> se2;
+    lf_extend_result *sx2 = nullptr;
     /* pass B: fill */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
         for (size_t c = lo; c < hi; c++) {
@@ -541,7 +550,42 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     const double tm1 = now_ms();
     if (n1) {
         LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
-        LF_CH(lf_gpu_run_align(ctx));
+        const double tr0 = now_ms();
+        LF_CH(lf_gpu_run_align(ctx));   /* returns once the class kernels are launched (its class-count sync has waited for the uploads) */
+        if (spec) {
+            /* Speculative round 2: the clip / split triggers can only fire for tasks whose LENGTHS qualify (:1840 / :2175
+             * ql > 500, :1952 |ql - tl| >= 80), which is known now.  Their extensions (a superset of what round 2 will
+             * ask for, and nearly the same set) run on their own high-priority stream beside the round-1 kernels, so
+             * round 2 costs no GPU round trip. */
+            std::vector<std::vector<uint32_t>> part(nthreads);
+            parallel_for(n1, nthreads, [&](unsigned tid, size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; i++) {
+                    const lf_align_task &t = t1[i];
+                    const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len;
+                    if (t.mode == LF_MODE_SHW ? ql > kClipLen : abs(ql - tl) >= kSplitLen) part[tid].push_back((uint32_t)i);
+                }
+            });
+            for (auto &v : part) cand_ti.insert(cand_ti.end(), v.begin(), v.end());   /* ascending: the parts are consecutive ranges */
+            cand_ext.reserve(cand_ti.size());
+            for (const uint32_t ti : cand_ti) {
+                const lf_align_task &t = t1[ti];
+                cand_ext.push_back((uint32_t)se2.size());
+                if (t.mode == LF_MODE_SHW) se2.push_back(mk_ext(t.read_id, t.q_off, t.q_len, t.t_off, t.t_len, t.flags, true));   /* head tasks carry REVERSE_BOTH already */
+                else {
+                    const unsigned strand = t.flags & LF_F_READ_REV;
+                    se2.push_back(mk_ext(t.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, false));
+                    se2.push_back(mk_ext(t.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, false));
+                }
+            }
+            if (!se2.empty()) {
+                lf_extend_task *pe = (lf_extend_task *)S.e2.reserve(se2.size() * sizeof(lf_extend_task));
+                sx2 = (lf_extend_result *)S.x2.reserve((se2.size() + 1) * sizeof(lf_extend_result));
+                if (!pe || !sx2) { delete R; return LF_ERR_NOMEM; }
+                memcpy(pe, se2.data(), se2.size() * sizeof(lf_extend_task));
+                LF_CH(spec_extend_start(ctx, pe, se2.size(), sx2));
+            }
+        }
+        if (getenv("LF_CHAIN_TRACE")) { const double tr1 = now_ms(); lf_gpu_sync(ctx); fprintf(stderr, "[lf_chain] r1: enqueue uploads %.2f, run_align returns after %.2f (its class-count sync waits for the uploads), kernels drained after %.2f more\n", tr0 - tm1, tr1 - tr0, now_ms() - tr1); }
         if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r1, ops1, cap1));
         else { /* results and ops stay in HBM; the trigger tests run there and only the hits come back */
             DevState &d = ctx->devs[0];
@@ -584,6 +628,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
 
     /* ---------------- round 2: triggers -> extensions ---------------- */
     std::vector<lf_extend_task> e2;
+    std::vector<uint32_t> e2_src;   /* per extension: 2 * round-1 task + (1: the reversed one of a split pair) */
     std::vector<ClipInfo> clips;
     std::vector<SplitInfo> splits;
     std::vector<int32_t> gap_split(gpu_emit ? 0 : total_seeds, -1);   /* per (chain, seed i): index into splits, host emit only */
@@ -608,10 +653,12 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     p.head_clip = (int32_t)clips.size();
                     clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
                     e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, true));
+                    e2_src.push_back(2u * (uint32_t)ti);
                 } else if (ti == p.tail_task) {
                     p.tail_clip = (int32_t)clips.size();
                     clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
                     e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true));
+                    e2_src.push_back(2u * (uint32_t)ti);
                 } else {
                     for (;; gi++) {   /* the gap whose task this is: gaps get their tasks in order */
                         const int32_t ql = (int32_t)(sd[gi + 1].qPos - (sd[gi].qPos + sd[gi].len)), tl = (int32_t)(sd[gi + 1].tPos - (sd[gi].tPos + sd[gi].len));
@@ -626,6 +673,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                     splits.push_back(si);
                     e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, false));
                     e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, false));
+                    e2_src.push_back(2u * (uint32_t)ti); e2_src.push_back(2u * (uint32_t)ti + 1u);
                 }
             }
             p.split_hi = (int32_t)splits.size();
@@ -672,7 +720,17 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     }
     const double tq1 = now_ms();
     std::vector<lf_extend_result> x2(e2.size());
-    if (!e2.empty()) {
+    bool have_x2 = e2.empty();
+    if (spec && !e2.empty()) {   /* the extensions have been running since before round 1: pick the results */
+        LF_CH(spec_extend_wait(ctx));
+        have_x2 = true;
+        for (size_t k = 0; k < e2.size() && have_x2; k++) {
+            const auto it = std::lower_bound(cand_ti.begin(), cand_ti.end(), e2_src[k] >> 1);
+            if (it == cand_ti.end() || *it != (e2_src[k] >> 1)) { have_x2 = false; break; }   /* cannot happen: the triggers imply the length tests */
+            x2[k] = sx2[cand_ext[(size_t)(it - cand_ti.begin())] + (e2_src[k] & 1u)];
+        }
+    } else if (spec) LF_CH(spec_extend_wait(ctx));
+    if (!have_x2) {
         LF_CH(lf_gpu_upload_extend_tasks(ctx, e2.data(), e2.size()));
         LF_CH(lf_gpu_run_extend(ctx));
         LF_CH(lf_gpu_download_extend(ctx, x2.data()));

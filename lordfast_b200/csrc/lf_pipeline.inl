@@ -27,6 +27,8 @@
 struct DevState {
     int dev = 0;
     lfb_stream stream = 0;
+    lfb_stream ext_stream = 0;      /* speculative extensions of the chain operator run beside round 1 */
+    lfb_event ext_ev = 0;
     lfb_event ev[4] = {};
     lfb_stream sub[LF_NSUB] = {};   /* size classes run concurrently: their grids are small */
     lfb_event sub_ev[LF_NSUB] = {};
@@ -410,6 +412,12 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
 #ifndef LF_EMU
         if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; }
         for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
+        {   /* highest priority: its few long-latency warps must not queue behind the round-1 grids */
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&d.ext_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; }
+        }
+        cudaEventCreateWithFlags(&d.ext_ev, cudaEventDisableTiming);
         for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; } cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
         for (int c = 0; c < LF_NCLS; c++) { cudaEventCreate(&d.cls_ev[c][0]); cudaEventCreate(&d.cls_ev[c][1]); }
 #endif
@@ -436,6 +444,8 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
 #ifndef LF_EMU
         for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         for (int k = 0; k < LF_NSUB; k++) { if (d.sub_ev[k]) cudaEventDestroy(d.sub_ev[k]); if (d.sub[k]) cudaStreamDestroy(d.sub[k]); }
+        if (d.ext_ev) cudaEventDestroy(d.ext_ev);
+        if (d.ext_stream) cudaStreamDestroy(d.ext_stream);
         for (int c = 0; c < LF_NCLS; c++) { if (d.cls_ev[c][0]) cudaEventDestroy(d.cls_ev[c][0]); if (d.cls_ev[c][1]) cudaEventDestroy(d.cls_ev[c][1]); }
         if (d.stream) cudaStreamDestroy(d.stream);
 #endif
@@ -589,32 +599,69 @@ int lf_gpu_upload_extend_tasks(lf_gpu_ctx *ctx, const lf_extend_task *tasks, siz
     return LF_OK;
 }
 
+static int run_extend_dev(lf_gpu_ctx *ctx, DevState &d, lfb_stream s, size_t scr_bound = 0)
+{   /* scr_bound != 0: the caller's bound on the scratch items (sum of what k_extend_prep asks for): no host round trip */
+    const size_t n = d.n_etasks;
+    if (!n) return LF_OK;
+    LF_TRY(d.eres.reserve(n * sizeof(lf_extend_result)));
+    LF_TRY(d.escr_items.reserve(n * 4)); LF_TRY(d.escr_off.reserve((n + 1) * 8));
+    LfExtDev v;
+    v.pac = d.pac.as<uint8_t>(); v.l_pac = ctx->l_pac; v.bases = d.bases.as<uint8_t>(); v.read_off = d.read_off.as<uint64_t>(); v.n_reads = d.n_reads;
+    v.tasks = d.etasks.as<lf_extend_task>(); v.n_tasks = (uint32_t)n; v.res = d.eres.as<lf_extend_result>();
+    v.scr_off = d.escr_off.as<uint64_t>(); v.scratch = nullptr;
+    LFB_LAUNCH(k_extend_prep, (unsigned)((n + 255) / 256), 256, 0, s, v, d.escr_items.as<uint32_t>());
+    LF_TRY(lfb_scan_excl_total(d.tmp, d.escr_items.as<uint32_t>(), d.escr_off.as<unsigned long long>(), n, s));
+    if (scr_bound) LF_TRY(d.escr.reserve(scr_bound * sizeof(int2) + 64));
+    else {
+        HostTotals *ht = (HostTotals *)d.pinned;
+        LF_TRY(lfb_d2h(&ht->scr_total, d.escr_off.as<unsigned long long>() + n, 8, s));
+        LF_TRY(lfb_sync(s));
+        LF_TRY(d.escr.reserve((size_t)ht->scr_total * sizeof(int2) + 64));
+    }
+    v.scratch = d.escr.as<int2>();
+    LFB_LAUNCH(k_ksw_extend, (unsigned)((n + 3) / 4), 128, 0, s, v); /* one warp per task */
+    LF_TRY(lfb_last_error());
+    ctx->stats.extend_tasks += n;
+    return LF_OK;
+}
+
 int lf_gpu_run_extend(lf_gpu_ctx *ctx)
 {
     if (!ctx) return LF_ERR_BAD_ARG;
     for (DevState &d : ctx->devs) {
         if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
-        const size_t n = d.n_etasks;
-        if (!n) continue;
-        lfb_stream s = d.stream;
-        LF_TRY(d.eres.reserve(n * sizeof(lf_extend_result)));
-        LF_TRY(d.escr_items.reserve(n * 4)); LF_TRY(d.escr_off.reserve((n + 1) * 8));
-        LfExtDev v;
-        v.pac = d.pac.as<uint8_t>(); v.l_pac = ctx->l_pac; v.bases = d.bases.as<uint8_t>(); v.read_off = d.read_off.as<uint64_t>(); v.n_reads = d.n_reads;
-        v.tasks = d.etasks.as<lf_extend_task>(); v.n_tasks = (uint32_t)n; v.res = d.eres.as<lf_extend_result>();
-        v.scr_off = d.escr_off.as<uint64_t>(); v.scratch = nullptr;
-        LFB_LAUNCH(k_extend_prep, (unsigned)((n + 255) / 256), 256, 0, s, v, d.escr_items.as<uint32_t>());
-        LF_TRY(lfb_scan_excl_total(d.tmp, d.escr_items.as<uint32_t>(), d.escr_off.as<unsigned long long>(), n, s));
-        HostTotals *ht = (HostTotals *)d.pinned;
-        LF_TRY(lfb_d2h(&ht->scr_total, d.escr_off.as<unsigned long long>() + n, 8, s));
-        LF_TRY(lfb_sync(s));
-        LF_TRY(d.escr.reserve((size_t)ht->scr_total * sizeof(int2) + 64));
-        v.scratch = d.escr.as<int2>();
-        LFB_LAUNCH(k_ksw_extend, (unsigned)((n + 3) / 4), 128, 0, s, v); /* one warp per task */
-        LF_TRY(lfb_last_error());
-        ctx->stats.extend_tasks += n;
+        int rc = run_extend_dev(ctx, d, d.stream);
+        if (rc) return rc;
     }
     ctx->stats.kernel_launches = lfb_launches;
+    return LF_OK;
+}
+
+/* Chain operator, single-device contexts: extensions on their own stream, started once everything enqueued on the main
+ * stream so far (reads, round-1 tasks) has arrived, running beside the round-1 kernels, without a host round trip;
+ * results go to `out` (pinned) asynchronously -- spec_extend_wait() before reading them. */
+static int spec_extend_start(lf_gpu_ctx *ctx, const lf_extend_task *tasks, size_t n, lf_extend_result *out)
+{
+    DevState &d = ctx->devs[0];
+    if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+    d.etask_first = 0; d.n_etasks = (uint32_t)n;
+    if (!n) return LF_OK;
+    LF_TRY(d.etasks.reserve(n * sizeof(lf_extend_task)));
+    /* no wait on the main stream: the caller starts this after lf_gpu_run_align, whose class-count sync has already
+     * waited for the reads and tasks to arrive, and waiting now would put the extensions behind the round-1 kernels */
+    LF_TRY(lfb_h2d(d.etasks.p, tasks, n * sizeof(lf_extend_task), d.ext_stream));
+    size_t bound = 0;
+    for (size_t i = 0; i < n; i++) bound += (size_t)tasks[i].q_len + 1u + ((size_t)tasks[i].q_len + 7u) / 8u + 1u;   /* k_extend_prep's figure */
+    int rc = run_extend_dev(ctx, d, d.ext_stream, bound);
+    if (rc) return rc;
+    LF_TRY(lfb_d2h(out, d.eres.p, n * sizeof(lf_extend_result), d.ext_stream));
+    return LF_OK;
+}
+static int spec_extend_wait(lf_gpu_ctx *ctx)
+{
+    DevState &d = ctx->devs[0];
+    if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+    LF_TRY(lfb_sync(d.ext_stream));
     return LF_OK;
 }
 
