@@ -422,6 +422,11 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     memset(&R->stats, 0, sizeof R->stats);
     ChainScratch &S = chain_scratch(ctx);
     unsigned nthreads = std::thread::hardware_concurrency();
+    {   /* one process per GPU (torchrun): the host cores are shared by LOCAL_WORLD_SIZE of these calls; LF_HOST_THREADS overrides */
+        const char *e = getenv("LF_HOST_THREADS"), *lw = getenv("LOCAL_WORLD_SIZE");
+        if (e && atoi(e) > 0) nthreads = (unsigned)atoi(e);
+        else if (lw && atoi(lw) > 1) nthreads = nthreads / (unsigned)atoi(lw);
+    }
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
     int rc;
