@@ -36,7 +36,7 @@ struct LfBufPool {
         for (size_t i = 0; i < items.size(); i++)   /* best fit: the record array must not grab the text buffer */
             if (items[i].cap >= need && (bi == items.size() || items[i].cap < items[bi].cap)) bi = i;
         if (bi < items.size()) { void *p = items[bi].p; *cap = items[bi].cap; items.erase(items.begin() + (long)bi); return p; }
-        if (items.size() >= 4) { raw_free(items.back().p); items.pop_back(); }
+        if (items.size() >= 16) { raw_free(items.back().p); items.pop_back(); }
         *cap = need + need / 8 + 4096;
         return raw_alloc(*cap);
     }
@@ -44,7 +44,7 @@ struct LfBufPool {
     {
         if (!p) return;
         std::lock_guard<std::mutex> g(mu);
-        if (items.size() >= 4) { raw_free(p); return; }
+        if (items.size() >= 16) { raw_free(p); return; }   /* room for several concurrent calls (contexts): freeing pinned memory synchronises the device */
         items.push_back(Item{p, cap});
     }
 };
