@@ -388,7 +388,7 @@ int emit_write(EmitSet &es, LfEmitDev &E, char *text_dst, uint64_t out_base)
     /* text_dst is pinned host memory, which the device addresses directly (unified addressing): the kernel's staged,
      * 16-byte coalesced stores go straight over PCIe while it runs, instead of to HBM and then through a copy of the
      * whole text (110 MB per config-2 chunk) after it.  LF_EMIT_NO_ZEROCOPY=1 restores the copy. */
-    static const bool zero_copy = !getenv("LF_EMIT_NO_ZEROCOPY");
+    const bool zero_copy = !getenv("LF_EMIT_NO_ZEROCOPY");
     if (es.d_recs.reserve((es.nrec + 1) * sizeof(lf_sam_record)) || (!zero_copy && es.d_text.reserve(es.ncig + es.nmd + 64))) return LF_ERR_NOMEM;
     lf_sam_record *hr = (lf_sam_record *)es.h_recs.reserve((es.nrec + 1) * sizeof(lf_sam_record));
     if (!hr) return LF_ERR_NOMEM;
@@ -463,6 +463,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     /* per (chain, seed i): round-1 task of the gap after seed i, or -1 -- only the host emit walks these */
     std::vector<int32_t> gap_task(gpu_emit ? 0 : total_seeds, -1);
     std::vector<uint32_t> ntask(n_chains, 0);
+    std::vector<uint8_t> hascand(n_chains, 0);   /* the chain holds a task whose lengths qualify for a clip / split trigger */
     std::vector<uint64_t> nslot(n_chains, 0); /* op-slot words of the chain's round-1 tasks */
     bool bad_rid = false;
     /* pass A: boundaries, guards and task counts per chain */
@@ -481,25 +482,29 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             uint64_t slots = 0;
             const int32_t a = (int32_t)s[0].qPos;
             p.head_guard = a > 0 && (int64_t)s[0].tPos - (a + 20) >= (int64_t)p.chrBeg;                       /* :1823-1825 */
-            if (p.head_guard) { cnt++; slots += ((uint64_t)(2 * a + 20) + 15) >> 4; }
+            bool cand = false;
+            if (p.head_guard) { cnt++; slots += ((uint64_t)(2 * a + 20) + 15) >> 4; cand |= a > kClipLen; }
             for (uint32_t i = 0; i + 1 < n; i++) {
                 const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
                 const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
-                if (ql > 0 && tl > 0) { cnt++; slots += ((uint64_t)ql + (uint64_t)tl + 15) >> 4; }
+                if (ql > 0 && tl > 0) { cnt++; slots += ((uint64_t)ql + (uint64_t)tl + 15) >> 4; cand |= abs(ql - tl) >= kSplitLen; }
             }
             const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
             const int32_t b = (int32_t)readLen - (int32_t)qs;
             p.tail_guard = b > 0 && s[n - 1].tPos + s[n - 1].len + (uint32_t)(b + 20) - 1 <= p.chrEnd;         /* :2161-2163 */
-            if (p.tail_guard) { cnt++; slots += ((uint64_t)(2 * b + 20) + 15) >> 4; }
-            ntask[c] = cnt; nslot[c] = slots;
+            if (p.tail_guard) { cnt++; slots += ((uint64_t)(2 * b + 20) + 15) >> 4; cand |= b > kClipLen; }
+            ntask[c] = cnt; nslot[c] = slots; hascand[c] = cand ? 1 : 0;
         }
     });
     if (bad_rid) { delete R; return LF_ERR_BAD_ARG; }
     for (size_t c = 0; c < n_chains; c++) task_base[c + 1] = task_base[c] + ntask[c];
     const size_t n1 = task_base[n_chains];
-    lf_align_task *t1 = (lf_align_task *)S.t1.reserve((n1 + 1) * sizeof(lf_align_task));
+    /* single-device contexts: the task list is generated on the device (k_chain_tasks); the host only needs the few
+     * tasks a trigger fires for, and re-derives those from the chain (task_at below) */
+    const bool dev_tasks = gpu_emit && !getenv("LF_CHAIN_HOST_TASKS");
+    lf_align_task *t1 = dev_tasks ? nullptr : (lf_align_task *)S.t1.reserve((n1 + 1) * sizeof(lf_align_task));
     lf_align_result *r1 = gpu_emit ? nullptr : (lf_align_result *)S.r1.reserve((n1 + 1) * sizeof(lf_align_result));
-    if (!t1 || (!gpu_emit && !r1)) { delete R; return LF_ERR_NOMEM; }
+    if ((!dev_tasks && !t1) || (!gpu_emit && !r1)) { delete R; return LF_ERR_NOMEM; }
     std::vector<uint32_t> trig;   /* round-1 tasks whose result fires a clip / split trigger, ascending */
     const bool spec = gpu_emit && !getenv("LF_CHAIN_NO_SPEC");
     std::vector<uint32_t> cand_ti, cand_ext;   /* speculative round 2: candidate round-1 tasks (ascending) and their first extension */
@@ -516,6 +521,11 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             ChainPlan &p = plan[c];
             size_t k = task_base[c];
             const int32_t a = (int32_t)s[0].qPos;
+            if (dev_tasks) {   /* only the positions of the head and tail tasks */
+                if (p.head_guard) p.head_task = (int32_t)task_base[c];
+                if (p.tail_guard) p.tail_task = (int32_t)task_base[c + 1] - 1;
+                continue;
+            }
             if (p.head_guard) {
                 p.head_task = (int32_t)k;
                 t1[k++] = mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH, LF_MODE_SHW);
@@ -533,6 +543,31 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             }
         }
     });
+    /* round-1 task ti of chain c, from the chain itself (the order of pass B / k_chain_tasks: head, gaps, tail) */
+    auto task_at = [&](size_t c, size_t ti) -> lf_align_task {
+        if (!dev_tasks) return t1[ti];
+        const lf_chain &ch = chains[c];
+        const lf_seed *s = seeds + ch.seed_off;
+        const uint32_t n = ch.n_seeds;
+        const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
+        const ChainPlan &p = plan[c];
+        size_t k = task_base[c];
+        if (p.head_guard) {
+            const int32_t a = (int32_t)s[0].qPos;
+            if (k == ti) return mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH, LF_MODE_SHW);
+            k++;
+        }
+        for (uint32_t i = 0; i + 1 < n; i++) {
+            const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
+            const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
+            if (ql > 0 && tl > 0) { if (k == ti) return mk_task(ch.read_id, qs, (uint32_t)ql, ts, (uint32_t)tl, strand, LF_MODE_NW); k++; }
+        }
+        const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
+        const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
+        const int32_t b = (int32_t)readLen - (int32_t)qs;
+        return mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand, LF_MODE_SHW);
+    };
+    auto chain_of = [&](size_t ti) -> size_t { return (size_t)(std::upper_bound(task_base.begin(), task_base.end(), (uint64_t)ti) - task_base.begin() - 1); };
     /* per-chain inputs of the GPU emit that are known now */
     std::vector<uint64_t> slot_base;   /* a chain of n anchors has n + 1 slots: head, n - 1 gaps, tail */
     std::vector<uint8_t> guards;
@@ -554,7 +589,13 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     if (!gpu_emit && !ops1) { delete R; return LF_ERR_NOMEM; }
     const double tm1 = now_ms();
     if (n1) {
-        LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
+        if (dev_tasks) {
+            DevState &d = ctx->devs[0];
+            lf_align_task *dt = resident_tasks_alloc(ctx, n1);
+            if (!dt) { delete R; return LF_ERR_NOMEM; }
+            LFB_LAUNCH(k_chain_tasks, (unsigned)((n_chains + 3) / 4), 128, 0, d.stream, S.d_chains.as<lf_chain>(), S.d_seeds.as<lf_seed>(), d.read_off.as<uint64_t>(),
+                       S.d_task_base.as<uint64_t>(), S.d_guards.as<uint8_t>(), (uint32_t)n_chains, dt);
+        } else LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
         const double tr0 = now_ms();
         LF_CH(lf_gpu_run_align(ctx));   /* returns once the class kernels are launched (its class-count sync has waited for the uploads) */
         if (spec) {
@@ -562,18 +603,52 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
              * ql > 500, :1952 |ql - tl| >= 80), which is known now.  Their extensions (a superset of what round 2 will
              * ask for, and nearly the same set) run on their own high-priority stream beside the round-1 kernels, so
              * round 2 costs no GPU round trip. */
-            std::vector<std::vector<uint32_t>> part(nthreads);
-            parallel_for(n1, nthreads, [&](unsigned tid, size_t lo, size_t hi) {
-                for (size_t i = lo; i < hi; i++) {
-                    const lf_align_task &t = t1[i];
-                    const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len;
-                    if (t.mode == LF_MODE_SHW ? ql > kClipLen : abs(ql - tl) >= kSplitLen) part[tid].push_back((uint32_t)i);
+            std::vector<lf_align_task> cand_task;
+            if (dev_tasks) {   /* pass A has marked the chains that hold a candidate: walk those */
+                for (size_t c = 0; c < n_chains; c++) {
+                    if (!hascand[c]) continue;
+                    /* one walk over the chain in task order (head, gaps, tail), as in task_at */
+                    const lf_chain &ch = chains[c];
+                    const lf_seed *s = seeds + ch.seed_off;
+                    const uint32_t n = ch.n_seeds;
+                    const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
+                    const ChainPlan &p = plan[c];
+                    size_t k = task_base[c];
+                    if (p.head_guard) {
+                        const int32_t a = (int32_t)s[0].qPos;
+                        if (a > kClipLen) { cand_ti.push_back((uint32_t)k); cand_task.push_back(mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH, LF_MODE_SHW)); }
+                        k++;
+                    }
+                    for (uint32_t i = 0; i + 1 < n; i++) {
+                        const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
+                        const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
+                        if (ql > 0 && tl > 0) {
+                            if (abs(ql - tl) >= kSplitLen) { cand_ti.push_back((uint32_t)k); cand_task.push_back(mk_task(ch.read_id, qs, (uint32_t)ql, ts, (uint32_t)tl, strand, LF_MODE_NW)); }
+                            k++;
+                        }
+                    }
+                    if (p.tail_guard) {
+                        const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
+                        const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
+                        const int32_t b = (int32_t)readLen - (int32_t)qs;
+                        if (b > kClipLen) { cand_ti.push_back((uint32_t)k); cand_task.push_back(mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand, LF_MODE_SHW)); }
+                    }
                 }
-            });
-            for (auto &v : part) cand_ti.insert(cand_ti.end(), v.begin(), v.end());   /* ascending: the parts are consecutive ranges */
+            } else {
+                std::vector<std::vector<uint32_t>> part(nthreads);
+                parallel_for(n1, nthreads, [&](unsigned tid, size_t lo, size_t hi) {
+                    for (size_t i = lo; i < hi; i++) {
+                        const lf_align_task &t = t1[i];
+                        const int32_t ql = (int32_t)t.q_len, tl = (int32_t)t.t_len;
+                        if (t.mode == LF_MODE_SHW ? ql > kClipLen : abs(ql - tl) >= kSplitLen) part[tid].push_back((uint32_t)i);
+                    }
+                });
+                for (auto &v : part) cand_ti.insert(cand_ti.end(), v.begin(), v.end());   /* ascending: the parts are consecutive ranges */
+                for (const uint32_t ti : cand_ti) cand_task.push_back(t1[ti]);
+            }
             cand_ext.reserve(cand_ti.size());
-            for (const uint32_t ti : cand_ti) {
-                const lf_align_task &t = t1[ti];
+            for (size_t x = 0; x < cand_ti.size(); x++) {
+                const lf_align_task &t = cand_task[x];
                 cand_ext.push_back((uint32_t)se2.size());
                 if (t.mode == LF_MODE_SHW) se2.push_back(mk_ext(t.read_id, t.q_off, t.q_len, t.t_off, t.t_len, t.flags, true));   /* head tasks carry REVERSE_BOTH already */
                 else {
@@ -653,7 +728,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             int64_t gtask = (int64_t)task_base[c] + (p.head_task >= 0 ? 1 : 0) - 1;   /* task of the last gap passed */
             for (; k < trig.size() && trig[k] < task_base[c + 1]; k++) {
                 const int32_t ti = (int32_t)trig[k];
-                const lf_align_task &t = t1[(size_t)ti];
+                const lf_align_task t = task_at(c, (size_t)ti);
                 if (ti == p.head_task) {
                     p.head_clip = (int32_t)clips.size();
                     clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
@@ -753,7 +828,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
         if (p.head_clip >= 0) {
             ClipInfo &ci = clips[(size_t)p.head_clip];
-            const lf_align_task &t = t1[(size_t)p.head_task];
+            const lf_align_task t = task_at(c, (size_t)p.head_task);
             ci.qle = x2[(size_t)ci.ext].qle; ci.tle = x2[(size_t)ci.ext].tle;
             if (ci.qle > 0 && ci.qle < (int32_t)t.q_len) {                                         /* :1850-1853 */
                 ci.t3 = (int32_t)t3.size();
@@ -763,7 +838,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         }
         for (int32_t sx = p.split_lo; sx < p.split_hi; sx++) {
             SplitInfo &si = splits[(size_t)sx];
-            const lf_align_task &t = t1[(size_t)si.task];
+            const lf_align_task t = task_at(c, (size_t)si.task);
             const uint32_t qs = t.q_off, ts = t.t_off, qe = qs + t.q_len, te = ts + t.t_len;
             si.qs2 = qs + (uint32_t)x2[(size_t)si.ext_f].qle; si.ts2 = ts + (uint32_t)x2[(size_t)si.ext_f].tle;   /* :1972-1973 */
             si.qe2 = qe - (uint32_t)x2[(size_t)si.ext_r].qle; si.te2 = te - (uint32_t)x2[(size_t)si.ext_r].tle;   /* :1982-1983 */
@@ -787,7 +862,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         }
         if (p.tail_clip >= 0) {
             ClipInfo &ci = clips[(size_t)p.tail_clip];
-            const lf_align_task &t = t1[(size_t)p.tail_task];
+            const lf_align_task t = task_at(c, (size_t)p.tail_task);
             ci.qle = x2[(size_t)ci.ext].qle; ci.tle = x2[(size_t)ci.ext].tle;
             if (ci.qle > 0 && ci.qle < (int32_t)t.q_len) {                                         /* :2181-2184 */
                 ci.t3 = (int32_t)t3.size();

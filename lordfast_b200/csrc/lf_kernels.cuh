@@ -1713,6 +1713,55 @@ __global__ void __launch_bounds__(LF_EMIT_BLOCK) k_emit_slots(LfEmitDev d)
  * :2175), in the reference's own arithmetic: the similarity is computed in float and compared with a double
  * constant.  Head and tail tasks are the prefix-mode ones.  Triggered task indices are appended to `list`
  * (unordered; the host sorts the few thousand entries). */
+/* Round-1 tasks of a chunk of chains, written where k_align_prep expects them (alignChain_edlib's own calls: head SHW
+ * :1827-1833, one NW per gap with query and target bases :1936-1941, tail SHW :2164-2168).  One warp per chain; the
+ * host has only counted (task_base) and decided the chromosome-boundary guards.  59 MB of tasks per config-2 chunk
+ * neither get built on host threads nor cross PCIe. */
+__global__ void __launch_bounds__(128) k_chain_tasks(const lf_chain *__restrict__ chains, const lf_seed *__restrict__ seeds, const uint64_t *__restrict__ read_off,
+                                                     const uint64_t *__restrict__ task_base, const uint8_t *__restrict__ guards, uint32_t n_chains, lf_align_task *out)
+{
+    const uint32_t c = blockIdx.x * 4u + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (c >= n_chains) return;
+    const lf_chain ch = chains[c];
+    const lf_seed *s = seeds + ch.seed_off;
+    const uint32_t n = ch.n_seeds;
+    const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
+    const uint32_t g = guards[c];
+    uint64_t k = task_base[c];
+    lf_align_task t;
+    t.read_id = ch.read_id; t.reserved = 0;
+    if (g & 1u) {
+        if (lane == 0) {
+            const uint32_t a = s[0].qPos;
+            t.q_off = 0; t.q_len = a; t.t_off = s[0].tPos - (a + 20u); t.t_len = a + 20u; t.flags = (uint16_t)(strand | LF_F_REVERSE_BOTH); t.mode = LF_MODE_SHW;
+            out[k] = t;
+        }
+        k++;
+    }
+    for (uint32_t i0 = 0; i0 + 1 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool is = false;
+        if (i + 1 < n) {
+            const lf_seed s0 = s[i], s1 = s[i + 1];
+            const uint32_t qs = s0.qPos + s0.len, ts = s0.tPos + s0.len;
+            const int32_t ql = (int32_t)(s1.qPos - qs), tl = (int32_t)(s1.tPos - ts);
+            is = ql > 0 && tl > 0;
+            t.q_off = qs; t.q_len = (uint32_t)ql; t.t_off = ts; t.t_len = (uint32_t)tl; t.flags = (uint16_t)strand; t.mode = LF_MODE_NW;
+        }
+        const uint32_t bal = __ballot_sync(LF_FULL, is);
+        if (is) out[k + (uint64_t)__popc(bal & ((1u << lane) - 1u))] = t;
+        k += (uint64_t)__popc(bal);
+    }
+    if ((g & 2u) && lane == 0) {
+        const lf_seed sl = s[n - 1];
+        const uint32_t qs = sl.qPos + sl.len;
+        const uint32_t b = (uint32_t)(read_off[ch.read_id + 1] - read_off[ch.read_id]) - qs;
+        t.q_off = qs; t.q_len = b; t.t_off = sl.tPos + sl.len; t.t_len = b + 20u; t.flags = (uint16_t)strand; t.mode = LF_MODE_SHW;
+        out[k] = t;
+    }
+}
+
 __global__ void k_chain_triggers(const lf_align_task *tasks, const lf_align_result *res, uint32_t n, uint32_t *list, uint32_t *count, uint32_t cap)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

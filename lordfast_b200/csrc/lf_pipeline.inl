@@ -521,6 +521,17 @@ int lf_gpu_upload_align_tasks(lf_gpu_ctx *ctx, const lf_align_task *tasks, size_
     return LF_OK;
 }
 
+/* Chain operator, single-device contexts: the round-1 tasks are written by k_chain_tasks straight into the device's
+ * task array; this sizes it and makes it the resident batch. */
+static lf_align_task *resident_tasks_alloc(lf_gpu_ctx *ctx, size_t n)
+{
+    DevState &d = ctx->devs[0];
+    if (set_dev(d)) return nullptr;
+    if (d.tasks.reserve((n + 1) * sizeof(lf_align_task))) return nullptr;
+    d.task_first = 0; d.n_tasks = (uint32_t)n; d.ran = false;
+    return d.tasks.as<lf_align_task>();
+}
+
 int lf_gpu_run_align(lf_gpu_ctx *ctx)
 {
     if (!ctx) return LF_ERR_BAD_ARG;

@@ -156,3 +156,21 @@ def test_gpu_chain_operator_two_contigs_edges():
     recs, text, st = g.align_chains(np.concatenate(reads), off, contig_off, contig_len, np.array(seeds, dtype=api.SEED), np.array(chains, dtype=api.CHAIN))
     assert api.records_to_dicts(recs, text) == exp
     g.close()
+
+
+@pytest.mark.parametrize("env", ["LF_CHAIN_NO_SPEC", "LF_CHAIN_HOST_TASKS", "LF_EMIT_NO_ZEROCOPY"])
+def test_emu_chain_operator_fallback_paths(monkeypatch, env):
+    """The non-default variants of the single-device path: round 2 as its own GPU round trip instead of the speculative
+    extensions, round-1 tasks built on host threads instead of by k_chain_tasks, emit text through a staging copy."""
+    monkeypatch.setenv(env, "1")
+    _crafted(build_emu())
+    _golden(build_emu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", ["LF_CHAIN_NO_SPEC", "LF_CHAIN_HOST_TASKS", "LF_EMIT_NO_ZEROCOPY"])
+def test_gpu_chain_operator_fallback_paths(monkeypatch, env):
+    monkeypatch.setenv(env, "1")
+    _crafted(None)
+    _golden(None)
+    _simulated(None, 200, 6_000, 1_000_000)
