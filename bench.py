@@ -335,8 +335,8 @@ def main():
             # headline: the reference-facing operator (batched alignChain_edlib), host buffers in, CIGAR/MD/NM records out
             "e2e": {"value": bases_sum / 1e6 / (chainK_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chainK_ms_max, "calls_per_step": K,
                     "single_call": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "ms_per_step": chain_ms_max},
-                    # in: reads + offsets + seeds + chains + the round-1 task list the library derives on the host; out: CIGAR/MD text + records
-                    "h2d_bytes_per_step": h2d + int(seeds_a.nbytes + chains_a.nbytes), "d2h_bytes_per_step": int(chain_text_bytes) + int(nrec) * 56, "call": "lf_gpu_align_chains"},
+                    # in: reads + offsets + seeds + chains + 17 B of per-chain bases / guards (the round-1 tasks are generated on the device); out: CIGAR/MD text + records
+                    "h2d_bytes_per_step": int(w.reads.nbytes + read_off.nbytes + seeds_a.nbytes + chains_a.nbytes) + 17 * len(chains_a), "d2h_bytes_per_step": int(chain_text_bytes) + int(nrec) * 56, "call": "lf_gpu_align_chains"},
             "e2e_align_batch": {"value": e2e_v, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max,
                                 "call": "lf_gpu_align_batch (round-1 tasks only: task list in, distances + 2-bit op stream out)"},
             "e2e_chains": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chain_ms_max, "records_per_gpu": int(nrec),

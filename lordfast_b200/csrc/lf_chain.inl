@@ -16,6 +16,8 @@
  * Included by lf_pipeline.inl (so it is part of liblfgpu.so and of the test-only emulator build).
  */
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <time.h>
@@ -313,8 +315,10 @@ struct EmitSet {
         have_stream = false;
     }
 };
+struct LfWorkers;
 struct ChainScratch {
-    PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2, ed1, seeds_stage;
+    LfWorkers *workers = nullptr;
+    PinBuf t1, r1, ops1, t3, r3, ops3, e2, x2, ed1, seeds_stage, meta_stage;
     std::vector<Emit> *parts = nullptr;
     /* device side of the GPU emit */
     EmitSet es[2];          /* [0]: chains no trigger fired for (emitted while rounds 2-3 run), [1]: the rest */
@@ -322,10 +326,62 @@ struct ChainScratch {
 };
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
 
+/* Host workers of one context, kept between calls: a call runs half a dozen short parallel loops, and starting 16
+ * threads for each of them cost more (0.5 ms a loop) than the loops themselves. */
+struct LfWorkers {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(unsigned)> job;
+    unsigned long gen = 0;
+    unsigned active = 0, pending = 0;
+    bool stop = false;
+    void ensure(unsigned n)
+    {
+        while (th.size() < n) {
+            const unsigned id = (unsigned)th.size();
+            th.emplace_back([this, id] {
+                unsigned long seen = 0;
+                for (;;) {
+                    std::function<void(unsigned)> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv_go.wait(lk, [&] { return stop || (gen != seen && id < active); });
+                        if (stop) return;
+                        seen = gen;
+                        f = job;
+                    }
+                    f(id);
+                    { std::lock_guard<std::mutex> lk(mu); if (--pending == 0) cv_done.notify_all(); }
+                }
+            });
+        }
+    }
+    void run(unsigned n, const std::function<void(unsigned)> &f)
+    {   /* f(0 .. n-1), each on its own worker; returns when all are done */
+        ensure(n);
+        std::unique_lock<std::mutex> lk(mu);
+        job = f; active = n; pending = n; gen++;
+        cv_go.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+        active = 0;
+    }
+    ~LfWorkers()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_go.notify_all();
+        for (auto &t : th) t.join();
+    }
+};
+static thread_local LfWorkers *tl_workers = nullptr;   /* set by lf_gpu_align_chains for the calling thread */
+
 template <typename F>
 void parallel_for(size_t n, unsigned nthreads, F fn, size_t serial_below = 256)
 { /* fn(tid, lo, hi) over contiguous ranges */
     if (nthreads <= 1 || n < serial_below) { fn(0u, (size_t)0, n); return; }
+#ifndef LF_EMU
+    if (tl_workers) { tl_workers->run(nthreads, [&](unsigned t) { fn(t, n * t / nthreads, n * (t + 1) / nthreads); }); return; }
+#endif
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nthreads; t++) th.emplace_back(fn, t, n * t / nthreads, n * (t + 1) / nthreads);
     for (auto &t : th) t.join();
@@ -340,13 +396,14 @@ double now_ms()
 void chain_scratch_free_fn(void *p)
 {
     ChainScratch *s = (ChainScratch *)p;
-    PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2, &s->ed1, &s->seeds_stage };
+    PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2, &s->ed1, &s->seeds_stage, &s->meta_stage };
     for (PinBuf *b : all) b->release();
     LfbBuf *dall[] = { &s->d_chains, &s->d_seeds, &s->d_task_base, &s->d_guards, &s->d_clip, &s->d_split_begin, &s->d_splits, &s->d_nrec, &s->d_cigb, &s->d_mdb,
                        &s->d_rec_off, &s->d_cig_off, &s->d_md_off, &s->d_recs, &s->d_text, &s->d_ed, &s->d_slot_base, &s->d_slot_info, &s->d_slot_task };
     for (LfbBuf *b : dall) b->release();
     s->es[0].release(); s->es[1].release();
     delete s->parts;
+    delete s->workers;
     delete s;
 }
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx)
@@ -421,6 +478,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     lf_chain_results *R = new lf_chain_results();
     memset(&R->stats, 0, sizeof R->stats);
     ChainScratch &S = chain_scratch(ctx);
+    if (!S.workers) S.workers = new LfWorkers();
+    struct WorkersScope { LfWorkers *prev; WorkersScope(LfWorkers *w) : prev(tl_workers) { tl_workers = w; } ~WorkersScope() { tl_workers = prev; } } workers_scope(S.workers);
     unsigned nthreads = std::thread::hardware_concurrency();
     {   /* one process per GPU (torchrun): the host cores are shared by LOCAL_WORLD_SIZE of these calls; LF_HOST_THREADS overrides */
         const char *e = getenv("LF_HOST_THREADS"), *lw = getenv("LOCAL_WORLD_SIZE");
@@ -437,6 +496,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     const bool gpu_emit = ctx->devs.size() == 1 && !getenv("LF_CHAIN_HOST_EMIT");
     g_result_pool_pinned.pinned = true;
     LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
+    const double tt1 = now_ms();
     if (gpu_emit) {
         DevState &d = ctx->devs[0];
         size_t ns = 0;
@@ -466,6 +526,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<uint8_t> hascand(n_chains, 0);   /* the chain holds a task whose lengths qualify for a clip / split trigger */
     std::vector<uint64_t> nslot(n_chains, 0); /* op-slot words of the chain's round-1 tasks */
     bool bad_rid = false;
+    const double tt2 = now_ms();
     /* pass A: boundaries, guards and task counts per chain */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
         for (size_t c = lo; c < hi; c++) {
@@ -496,6 +557,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             ntask[c] = cnt; nslot[c] = slots; hascand[c] = cand ? 1 : 0;
         }
     });
+    const double tt3 = now_ms();
     if (bad_rid) { delete R; return LF_ERR_BAD_ARG; }
     for (size_t c = 0; c < n_chains; c++) task_base[c + 1] = task_base[c] + ntask[c];
     const size_t n1 = task_base[n_chains];
@@ -510,6 +572,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<uint32_t> cand_ti, cand_ext;   /* speculative round 2: candidate round-1 tasks (ascending) and their first extension */
     std::vector<lf_extend_task> se2;
     lf_extend_result *sx2 = nullptr;
+    const double tt4 = now_ms();
     /* pass B: fill */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
         for (size_t c = lo; c < hi; c++) {
@@ -543,6 +606,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             }
         }
     });
+    const double tt5 = now_ms();
     /* round-1 task ti of chain c, from the chain itself (the order of pass B / k_chain_tasks: head, gaps, tail) */
     auto task_at = [&](size_t c, size_t ti) -> lf_align_task {
         if (!dev_tasks) return t1[ti];
@@ -567,7 +631,6 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         const int32_t b = (int32_t)readLen - (int32_t)qs;
         return mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand, LF_MODE_SHW);
     };
-    auto chain_of = [&](size_t ti) -> size_t { return (size_t)(std::upper_bound(task_base.begin(), task_base.end(), (uint64_t)ti) - task_base.begin() - 1); };
     /* per-chain inputs of the GPU emit that are known now */
     std::vector<uint64_t> slot_base;   /* a chain of n anchors has n + 1 slots: head, n - 1 gaps, tail */
     std::vector<uint8_t> guards;
@@ -580,14 +643,19 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         n_slots = (size_t)slot_base[n_chains];
         if (S.d_task_base.reserve((n_chains + 1) * 8) || S.d_slot_base.reserve((n_chains + 1) * 8) || S.d_guards.reserve(n_chains + 64)
             || S.d_slot_info.reserve((n_slots + 1) * sizeof(LfSlotInfo)) || S.d_slot_task.reserve((n_slots + 1) * 4)) { delete R; return LF_ERR_NOMEM; }
-        if (lfb_h2d(S.d_task_base.p, task_base.data(), (n_chains + 1) * 8, d.stream) || lfb_h2d(S.d_slot_base.p, slot_base.data(), (n_chains + 1) * 8, d.stream)
-            || lfb_h2d(S.d_guards.p, guards.data(), n_chains, d.stream)) { delete R; return LF_ERR_CUDA; }
+        /* through pinned memory: a copy from pageable memory blocks the host until the stream (busy with the reads) gets to it */
+        char *ms = (char *)S.meta_stage.reserve((n_chains + 1) * 16 + n_chains + 64);
+        if (!ms) { delete R; return LF_ERR_NOMEM; }
+        memcpy(ms, task_base.data(), (n_chains + 1) * 8); memcpy(ms + (n_chains + 1) * 8, slot_base.data(), (n_chains + 1) * 8); memcpy(ms + (n_chains + 1) * 16, guards.data(), n_chains);
+        if (lfb_h2d(S.d_task_base.p, ms, (n_chains + 1) * 8, d.stream) || lfb_h2d(S.d_slot_base.p, ms + (n_chains + 1) * 8, (n_chains + 1) * 8, d.stream)
+            || lfb_h2d(S.d_guards.p, ms + (n_chains + 1) * 16, n_chains, d.stream)) { delete R; return LF_ERR_CUDA; }
     }
     size_t cap1 = 64;
     for (size_t c = 0; c < n_chains; c++) cap1 += nslot[c] * 4;
     uint8_t *ops1 = gpu_emit ? nullptr : (uint8_t *)S.ops1.reserve(cap1 + 64);
     if (!gpu_emit && !ops1) { delete R; return LF_ERR_NOMEM; }
     const double tm1 = now_ms();
+    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] tasks: upload_reads call %.2f, seed staging %.2f, pass A %.2f, prefix %.2f, pass B %.2f, emit inputs %.2f\n", tt1 - tm0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, tm1 - tt5);
     if (n1) {
         if (dev_tasks) {
             DevState &d = ctx->devs[0];
