@@ -299,64 +299,6 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* traceback walk shared by the thread-per-task kernels                                        */
-/* ------------------------------------------------------------------------------------------ */
-/* The op stream of a task is written back to front (the walk starts at the last op), 16 two-bit ops per word, the
- * first op met going to the top bits of the slot's last word.  `cur` collects a word below a sentinel bit, so one
- * shift-or and one bit test per op replace a shift count, an op counter and their updates. */
-struct LfOpSink { uint32_t *wptr; uint32_t cur; };
-__device__ __forceinline__ void lf_sink_init(LfOpSink &k, uint32_t *wlast) { k.wptr = wlast; k.cur = 1u; }
-__device__ __forceinline__ void lf_sink_put(LfOpSink &k, uint32_t op)
-{
-    const bool full = (k.cur & 0x40000000u) != 0u;   /* 15 ops below the sentinel: this one completes the word */
-    k.cur = (k.cur << 2) | op;
-    if (full) { *k.wptr-- = k.cur; k.cur = 1u; }
-}
-__device__ __forceinline__ uint32_t lf_sink_count(const LfOpSink &k, const uint32_t *wlast)
-{
-    return 16u * (uint32_t)(wlast - k.wptr) + (uint32_t)((31 - __clz((int)k.cur)) >> 1);
-}
-__device__ __forceinline__ uint32_t lf_sink_finish(LfOpSink &k, const uint32_t *wlast)
-{   /* stores the partial word (ops at its top bits, as the complete words have them); returns the number of ops */
-    const int nb = 31 - __clz((int)k.cur);
-    if (nb) *k.wptr = (k.cur ^ (1u << nb)) << (32 - nb);
-    return 16u * (uint32_t)(wlast - k.wptr) + (uint32_t)(nb >> 1);
-}
-/* Walks Up > Left > Diagonal (edlib.cpp:950, :984, :1015) from cell (i-1, j-1) through the op planes of one block in
- * shared memory -- sm[((col - c0) * WIN + (word - wtop)) * 256 + plane * 128], this thread's column of it -- until it
- * leaves the block (j == c0) or the window (row < 32 * wtop).  plane0 = up | diagonal-mismatch, plane1 = left |
- * diagonal-mismatch, so the two bits ARE the op (0 match, 1 insert, 2 delete, 3 mismatch). */
-template <int WIN>
-__device__ __forceinline__ void lf_walk_block(const uint32_t *sm, int c0, int wtop, int &i, int &j, LfOpSink &sink)
-{
-    constexpr int CS = WIN * 2 * 128;
-    constexpr int LOG = WIN == 1 ? 8 : 9;
-    static_assert(WIN == 1 || WIN == 2, "");
-    const int rowmin = wtop * 32;
-    while (i > 0 && j > c0 && (i - 1) >= rowmin) {
-        const int wrow = (i - 1) >> 5;
-        int idx = ((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * 128;   /* the column is idx >> LOG; negative once left of the block */
-        int b = (i - 1) & 31;
-        uint32_t cur = sink.cur, full;
-        do {   /* also left when the op word is complete: the store stays out of the loop (inside, the compiler
-                  predicates it and every op pays for nine masked instructions) */
-            const uint32_t x0 = sm[idx] >> b, x1 = sm[idx + 128] >> b;
-            const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
-            const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
-            const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
-            full = cur & 0x40000000u;
-            cur = (cur << 2) | op;
-            b += stay_row - 1;
-            idx += stay_col * CS - CS;
-        } while (b >= 0 && idx >= 0 && !full);
-        if (full) { *sink.wptr-- = cur; cur = 1u; }
-        sink.cur = cur;
-        j = c0 + 1 + (idx >> LOG);
-        i = wrow * 32 + b + 1;
-    }
-}
-
-/* ------------------------------------------------------------------------------------------ */
 /* k_myers_small: thread-per-task, NW words of 32 rows in registers                            */
 /* ------------------------------------------------------------------------------------------ */
 template <int NW>
@@ -579,7 +521,6 @@ __device__ __forceinline__ void lf_k1_recompute(uint32_t (&Pv)[NW], uint32_t (&M
     }
 }
 
-static_assert(LF_K1_BLOCK == 128, "lf_walk_block addresses the op planes of a 128-thread block");
 template <int NW, bool SHW>
 __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, const uint32_t *__restrict__ retry_count)
 {
@@ -640,11 +581,13 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
 
     /* ---- traceback: recompute 16-column blocks from their checkpoint, keep a WIN-word window of
      *      the op planes in shared memory, walk Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
-    uint32_t *const wlast = d.ops + (slot_hi >> 4) - 1; /* word the first (right-most) ops go to */
-    LfOpSink sink;
-    lf_sink_init(sink, wlast);
+    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1; /* word the next (right-most free) op goes to */
+    uint32_t cur = 0, nops = 0;
+    int sh = 30;
+#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
     int i = q, j = end + 1;
     uint32_t *smt = smem + tid;
+    constexpr int CS = WIN * 2 * LF_K1_BLOCK; /* shared-memory words per column */
     while (i > 0 && j > 0) {
         const int c1 = j, c0 = ((j - 1) / C) * C;
         const int whi = (i - 1) >> 5;
@@ -668,12 +611,31 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
             else if (NW > 3 * G && whi < 3 * G) lf_k1_recompute<NW, (3 * G < NW ? 3 * G : NW), WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
             else lf_k1_recompute<NW, NW, WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
         }
-        lf_walk_block<WIN>(smt, c0, wtop, i, j, sink);   /* inside the window, one word-row at a time */
+        /* walk inside the window, one word-row at a time */
+        const int rowmin = wtop * 32;
+        while (i > 0 && j > c0 && (i - 1) >= rowmin) {
+            const int wrow = (i - 1) >> 5;
+            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * LF_K1_BLOCK;
+            int b = (i - 1) & 31;
+            do {
+                const uint32_t x0 = cell[0] >> b, x1 = cell[LF_K1_BLOCK] >> b;
+                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
+                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
+                LF_EMIT(op);
+                b -= 1 - stay_row;
+                j -= 1 - stay_col;
+                cell -= (1 - stay_col) * CS;
+            } while (b >= 0 && j > c0);
+            i = wrow * 32 + b + 1;
+        }
     }
-    while (i > 0) { lf_sink_put(sink, 1u); i--; } /* left column: the rest of the query is inserted   */
-    while (j > 0) { lf_sink_put(sink, 2u); j--; } /* top row: the rest of the target is deleted        */
-    const uint32_t nops = lf_sink_finish(sink, wlast);
-    r.ops_off = slot_hi - nops; r.ops_len = nops;
+    while (i > 0) { LF_EMIT(1u); i--; } /* left column: the rest of the query is inserted   */
+    while (j > 0) { LF_EMIT(2u); j--; } /* top row: the rest of the target is deleted        */
+    if (sh != 30) *wptr = cur;
+#undef LF_EMIT
+    const uint64_t p = slot_hi - nops;
+    r.ops_off = p; r.ops_len = (uint32_t)(slot_hi - p);
     d.res[ti] = r;
 }
 
@@ -1981,11 +1943,13 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
     if (task.flags & LF_F_NO_PATH) { d.res[ti] = r; return; }
 
     /* ---- traceback over the stored planes: Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
-    uint32_t *const wlast = d.ops + (slot_hi >> 4) - 1;
-    LfOpSink sink;
-    lf_sink_init(sink, wlast);
+    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1;
+    uint32_t cur = 0, nops = 0;
+    int sh = 30;
+#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
     int i = q, j = end + 1;
     uint32_t *smt = smem + tid;
+    constexpr int CS = WIN * 2 * 128;
     bool lost = false;
     /* plane words of one block (C columns x WIN words) travel global -> registers -> shared memory; the registers
      * for the NEXT block are requested before the current block is walked, so the HBM/L2 latency hides behind
@@ -2030,13 +1994,30 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
             pre_c0 = c0 - C;
             load_block(pre_c0, C, pre_wtop);
         } else pre_c0 = -1;
-        lf_walk_block<WIN>(smt, c0, wtop, i, j, sink);
-        if (lf_sink_count(sink, wlast) > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
+        const int rowmin = wtop * 32;
+        while (i > 0 && j > c0 && (i - 1) >= rowmin) {
+            const int wrow = (i - 1) >> 5;
+            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * 128;
+            int b = (i - 1) & 31;
+            do {
+                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
+                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+                const int stay_col = (int)(x0 & ~x1 & 1u);
+                const int stay_row = (int)(x1 & ~x0 & 1u);
+                LF_EMIT(op);
+                b -= 1 - stay_row;
+                j -= 1 - stay_col;
+                cell -= (1 - stay_col) * CS;
+            } while (b >= 0 && j > c0);
+            i = wrow * 32 + b + 1;
+        }
+        if (nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
     }
+    while (i > 0 && !lost) { LF_EMIT(1u); i--; }
+    while (j > 0 && !lost) { LF_EMIT(2u); j--; }
+    if (sh != 30) *wptr = cur;
+#undef LF_EMIT
     if (lost) { retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
-    while (i > 0) { lf_sink_put(sink, 1u); i--; }
-    while (j > 0) { lf_sink_put(sink, 2u); j--; }
-    const uint32_t nops = lf_sink_finish(sink, wlast);
     r.ops_off = slot_hi - nops; r.ops_len = nops;
     d.res[ti] = r;
 }
@@ -2196,7 +2177,8 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
                                                        uint32_t *retry_list, uint32_t *retry_count, int nwmax)
 {
     constexpr int C = 8;
-    LF_DYN_SMEM(uint32_t, smem);    /* window planes [C columns][2 window words][2 planes][128 threads] */
+    constexpr int CS = 2 * 2 * 128; /* shared-memory words per column: [2 window words][2 planes][128 threads] */
+    LF_DYN_SMEM(uint32_t, smem);    /* window planes [C][2][2][128] */
     const uint32_t tid = threadIdx.x;
     const uint32_t gi = blockIdx.x * 128u + tid;
     if (gi >= count) return;
@@ -2264,9 +2246,10 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     if (task.flags & LF_F_NO_PATH) { r.ops_off = slot_hi; r.ops_len = 0; d.res[ti] = r; return; }
 
     /* ---- traceback: Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
-    uint32_t *const wlast = d.ops + (slot_hi >> 4) - 1;
-    LfOpSink sink;
-    lf_sink_init(sink, wlast);
+    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1;
+    uint32_t cur = 0, nops = 0;
+    int sh = 30;
+#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
     int i = q, j = t;
     const int q8 = (int)((8u * (uint32_t)q) / (uint32_t)t), r8 = (int)((8u * (uint32_t)q) % (uint32_t)t);
     int bc0 = ((t - 1) / C) * C;                 /* block the band bookkeeping below refers to */
@@ -2312,13 +2295,31 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         else if (N2 < N1 && need <= N2) lf_bandreg_block<NB, N2, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else if (N1 < NB && need <= N1) lf_bandreg_block<NB, N1, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else lf_bandreg_block<NB, NB, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        lf_walk_block<2>(smt, c0, wtop, i, j, sink);   /* inside the window, one word-row at a time */
-        if (lf_sink_count(sink, wlast) > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
+        /* walk inside the window, one word-row at a time */
+        const int rowmin = wtop * 32;
+        while (i > 0 && j > c0 && (i - 1) >= rowmin) {
+            const int wrow = (i - 1) >> 5;
+            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * 2 + (wrow - wtop)) * 2 * 128;
+            int b = (i - 1) & 31;
+            do {
+                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
+                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
+                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
+                LF_EMIT(op);
+                b -= 1 - stay_row;
+                j -= 1 - stay_col;
+                cell -= (1 - stay_col) * CS;
+            } while (b >= 0 && j > c0);
+            i = wrow * 32 + b + 1;
+        }
+        if (nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
     }
+    while (i > 0 && !lost) { LF_EMIT(1u); i--; }
+    while (j > 0 && !lost) { LF_EMIT(2u); j--; }
+    if (sh != 30) *wptr = cur;
+#undef LF_EMIT
     if (lost) { retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
-    while (i > 0) { lf_sink_put(sink, 1u); i--; }
-    while (j > 0) { lf_sink_put(sink, 2u); j--; }
-    const uint32_t nops = lf_sink_finish(sink, wlast);
     r.ops_off = slot_hi - nops; r.ops_len = nops;
     d.res[ti] = r;
 }
