@@ -459,6 +459,17 @@ template <> __device__ __forceinline__ void lf_add_chain_cin<8>(const uint32_t (
 }
 #endif
 
+/* max of v over the lanes of the warp that execute this together (any superset value is valid for the callers: they
+ * pick a code variant that covers at least what every lane needs) */
+__device__ __forceinline__ int lf_converged_max(int v)
+{
+#if defined(__CUDA_ARCH__)
+    return __reduce_max_sync(__activemask(), v);
+#else
+    return v;
+#endif
+}
+
 /* Advance the whole column by one target symbol (Myers 1999 / Hyyro 2003 recurrences on one long
  * word; the per-block hin/hout of edlib's calculateBlock, edlib.cpp:335-370, become the add carry
  * and the bits funnel-shifted between words): 12 integer instructions per word.
@@ -606,9 +617,12 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
             constexpr int G = NW >= 8 ? NW / 4 : NW == 6 ? 2 : 1;
             constexpr int SPAN = G + 1 < NW ? G + 1 : NW;
             const int ncols = c1 - c0;
-            if (NW > G && whi < G) lf_k1_recompute<NW, G, WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
-            else if (NW > 2 * G && whi < 2 * G) lf_k1_recompute<NW, (2 * G < NW ? 2 * G : NW), WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
-            else if (NW > 3 * G && whi < 3 * G) lf_k1_recompute<NW, (3 * G < NW ? 3 * G : NW), WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
+            /* one variant for the lanes that are here together (the deepest row among them decides): lanes choosing
+             * different variants would run them one after the other */
+            const int ws = lf_converged_max(whi);
+            if (NW > G && ws < G) lf_k1_recompute<NW, G, WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
+            else if (NW > 2 * G && ws < 2 * G) lf_k1_recompute<NW, (2 * G < NW ? 2 * G : NW), WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
+            else if (NW > 3 * G && ws < 3 * G) lf_k1_recompute<NW, (3 * G < NW ? 3 * G : NW), WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
             else lf_k1_recompute<NW, NW, WIN, SPAN>(Pv, Mv, qlo, qhi, qnn, tc, ncols, smt, wtop);
         }
         /* walk inside the window, one word-row at a time */
@@ -2291,9 +2305,10 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         ts.init(d.pac, tv.t0 + (int64_t)tv.dir * c0, tv.dir);
         const uint32_t tb = ts.peek();
         constexpr int N1 = NB > 2 ? NB - 1 : NB, N2 = NB > 3 ? NB - 2 : N1;
-        if (c1 - c0 != C) lf_bandreg_block<NB, NB, false, true, false>(Pv, Mv, qlo, qhi, qnn, tb, c0, c1 - c0, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        else if (N2 < N1 && need <= N2) lf_bandreg_block<NB, N2, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        else if (N1 < NB && need <= N1) lf_bandreg_block<NB, N1, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        const int ns = lf_converged_max(c1 - c0 != C ? NB : need);   /* one variant for the lanes that are here together */
+        if (ns > N1) lf_bandreg_block<NB, NB, false, true, false>(Pv, Mv, qlo, qhi, qnn, tb, c0, c1 - c0, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else if (N2 < N1 && ns <= N2) lf_bandreg_block<NB, N2, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else if (N1 < NB && ns <= N1) lf_bandreg_block<NB, N1, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else lf_bandreg_block<NB, NB, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         /* walk inside the window, one word-row at a time */
         const int rowmin = wtop * 32;

@@ -85,10 +85,14 @@ uint32_t bandreg_on()
     return e ? (uint32_t)strtoul(e, nullptr, 0) & 15u : (uint32_t)LF_BANDREG_DEFAULT;
 }
 
+/* Global-mode tasks of q <= 128 in k_myers_bandreg (the band is the whole column: no slides, no certificate, nothing per
+ * column in HBM) instead of k_myers_band (op planes of every column to HBM).  On since the recompute variant is chosen
+ * per warp: 1.72 vs 1.77 ms (sv 0.0) and 2.57 vs 2.62 ms (sv 0.1) per config-2 step, and 3.9 GB less HBM traffic
+ * (profiles/r02c section 6).  LF_BANDREG_SMALL=0 restores the plane store. */
 bool bandreg_small()
 {
     const char *e = getenv("LF_BANDREG_SMALL");
-    return e && atoi(e) != 0;
+    return !e || atoi(e) != 0;
 }
 
 LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
@@ -272,7 +276,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     {
         uint32_t first = 0, g = 0;
         for (int cls = 0; cls < LF_CLS_LARGE; cls++) {
-            gc.first[cls] = first; gc.count[cls] = ht->cnt.hist[cls]; gc.gbase[cls] = g; gc.nb[cls] = (bmask >> cls & 1u) ? (uint32_t)band_nb(cls) : 0u;
+            gc.first[cls] = first; gc.count[cls] = ht->cnt.hist[cls]; gc.gbase[cls] = g; gc.nb[cls] = ((bmask >> cls & 1u) && !(bandreg_small() && cls < 8 && !(cls & 1))) ? (uint32_t)band_nb(cls) : 0u;
             first += ht->cnt.hist[cls]; g += (ht->cnt.hist[cls] + 31) / 32;
         }
         gc.gbase[LF_CLS_LARGE] = g;

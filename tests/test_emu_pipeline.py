@@ -162,6 +162,8 @@ def test_emu_banded_classes_certificate_and_retry(emu_lib, monkeypatch):
     certified tasks and tasks redone full-width must both match the oracle."""
     import ctypes as C
     monkeypatch.setenv("LF_BAND_MASK", "0xffff")
+    monkeypatch.setenv("LF_BANDREG", "0")        # the register-band kernel would take these classes otherwise
+    monkeypatch.setenv("LF_BANDREG_SMALL", "0")
     rng = np.random.default_rng(4)
     ref = sim.make_reference(200_000, 5)
     reads, tasks = _band_stress_batch(rng, ref, 300)

@@ -49,12 +49,14 @@ def test_gpu_random_tasks_all_flags():
     g.close()
 
 
-@pytest.mark.parametrize("band_mask", [None, "0x0", "0xffff"])
-def test_gpu_similar_pairs_every_length(band_mask, monkeypatch):
+@pytest.mark.parametrize("band_mask,small,bandreg", [(None, None, None), ("0x0", "0", "0"), ("0xffff", "0", "0"), ("0xff", "0", "0xf")])
+def test_gpu_similar_pairs_every_length(band_mask, small, bandreg, monkeypatch):
     """query = mutated target for every q from 1 to 560 (all register classes and their edges); with the
-    default kernel mapping, with k_myers_small everywhere and with k_myers_band (banded + retry) everywhere."""
-    if band_mask is not None:
-        monkeypatch.setenv("LF_BAND_MASK", band_mask)
+    default kernel mapping, with k_myers_small everywhere, with k_myers_band (plane store; banded + retry) everywhere,
+    and with the plane store for q <= 128 plus k_myers_bandreg for every class above."""
+    for k, v in (("LF_BAND_MASK", band_mask), ("LF_BANDREG_SMALL", small), ("LF_BANDREG", bandreg)):
+        if v is not None:
+            monkeypatch.setenv(k, v)
     rng = np.random.default_rng(77)
     ref = sim.make_reference(400_000, 9)
     reads, tasks, pos = [], [], 1000
