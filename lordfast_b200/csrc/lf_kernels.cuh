@@ -145,6 +145,59 @@ struct LfTCursor {
     }
 };
 
+/* The 2-bit reference as a stream in task order: the next 16 symbols are the top 32 bits of a 64-bit window
+ * (first symbol at bits 31:30), whatever the strand; the word after next is requested one refill ahead. */
+struct LfTStream {
+    const uint32_t *p32; int64_t widx; uint32_t cur, nxt; int off, dir;
+    __device__ __forceinline__ uint32_t norm(uint32_t v) const
+    {
+        v = __byte_perm(v, 0u, 0x0123u);   /* base j of the word at bits 31-2j .. 30-2j */
+        if (dir < 0) { v = __brev(v); v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); } /* base 15 first */
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t *pac, int64_t l, int d)
+    {
+        p32 = (const uint32_t *)pac; dir = d; widx = l >> 4;
+        const int j = (int)(l & 15);
+        cur = norm(__ldg(p32 + widx));
+        off = d > 0 ? 2 * j : 2 * (15 - j);
+        widx += d;
+        nxt = norm(__ldg(p32 + (widx < 0 ? 0 : widx)));
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, (uint32_t)off); }
+    __device__ __forceinline__ void advance(int n)
+    { /* n <= 16 symbols consumed */
+        off += 2 * n;
+        if (off >= 32) { off -= 32; cur = nxt; widx += dir; nxt = norm(__ldg(p32 + (widx < 0 ? 0 : widx))); }
+    }
+};
+
+/* ... read one column at a time (k_myers_small): 16 symbols buffered, one test per column */
+struct LfTStreamCol {
+    LfTStream ts; uint32_t buf; int left;
+    __device__ __forceinline__ void init(const uint8_t *pac, int64_t l, int d) { ts.init(pac, l, d); left = 0; buf = 0; }
+    __device__ __forceinline__ void next_masks(uint32_t &slo, uint32_t &shi)
+    { /* all-ones / all-zeros masks of the two bits of the next symbol */
+        if (left == 0) { buf = ts.peek(); ts.advance(16); left = 16; }
+        shi = (uint32_t)((int32_t)buf >> 31); slo = (uint32_t)((int32_t)(buf << 1) >> 31);
+        buf <<= 2; left--;
+    }
+};
+
+/* not-Eq of 32 query rows against one target symbol: two 3-input LOP3s (the compiler's own association of
+ * the five inputs costs three) */
+__device__ __forceinline__ uint32_t lf_neq(uint32_t qlo, uint32_t qhi, uint32_t qnn, uint32_t slo, uint32_t shi)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t x, r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xbe;" : "=r"(x) : "r"(qlo), "r"(slo), "r"(qnn)); /* (a ^ b) | c */
+    asm("lop3.b32 %0, %1, %2, %3, 0xf6;" : "=r"(r) : "r"(x), "r"(qhi), "r"(shi));   /* a | (b ^ c) */
+    return r;
+#else
+    return (qlo ^ slo) | qnn | (qhi ^ shi);
+#endif
+}
+
 struct LfQView { int64_t bit0; int dir; uint32_t comp; }; /* element k lives at plane bit bit0 + dir*k */
 struct LfTView { int64_t t0; int dir; };                   /* element k is pac base t0 + dir*k */
 
@@ -485,7 +538,7 @@ __device__ __forceinline__ void lf_k1_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[
     uint32_t Eq[NW], a[NW], sum[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        Eq[w] = ~((qlo[w] ^ slo) | (qhi[w] ^ shi) | qnn[w]);
+        Eq[w] = ~lf_neq(qlo[w], qhi[w], qnn[w], slo, shi);   /* two LOP3s; the negation folds into the users */
         a[w] = Eq[w] & Pv[w];
     }
     lf_add_chain<NW>(a, Pv, sum);
@@ -516,7 +569,7 @@ __device__ __forceinline__ void lf_k1_column(uint32_t (&Pv)[NW], uint32_t (&Mv)[
 /* Recompute columns [c0, c1) from the state in Pv/Mv, touching only the first NWC words. */
 template <int NW, int NWC, int WIN, int SPAN>
 __device__ __forceinline__ void lf_k1_recompute(uint32_t (&Pv)[NW], uint32_t (&Mv)[NW], const uint32_t (&qlo)[NW], const uint32_t (&qhi)[NW],
-                                                const uint32_t (&qnn)[NW], LfTCursor &tc, int ncols, uint32_t *smt, int wtop)
+                                                const uint32_t (&qnn)[NW], LfTStreamCol &tc, int ncols, uint32_t *smt, int wtop)
 {
     static_assert(NWC <= NW, "");
     uint32_t (&P)[NWC] = reinterpret_cast<uint32_t (&)[NWC]>(Pv);
@@ -561,7 +614,7 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
     uint2 *ck = (uint2 *)(d.scratch + d.scr_off[ti]);
 
     /* ---- forward pass: distance (+ first best prefix for SHW), checkpoints every C columns ---- */
-    LfTCursor tc;
+    LfTStreamCol tc;
     tc.init(d.pac, tv.t0, tv.dir);
     for (int c = 0; c < t; c++) {
         if ((c & (C - 1)) == 0 && c) {
@@ -2052,47 +2105,6 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
  *              2-word window written to shared memory, walk Up > Left > Diagonal inside the window.
  * Tasks that fail the certificate are appended to the retry list and redone full width by k_myers_small.
  * k_align_prep routes only tasks with 3*|q-t| <= 32*(NB-1)-7 here (classes LF_CLS_BANDREG0..+3). */
-/* The 2-bit reference as a stream in task order: the next 16 symbols are the top 32 bits of a 64-bit window
- * (first symbol at bits 31:30), whatever the strand; the word after next is requested one refill ahead. */
-struct LfTStream {
-    const uint32_t *p32; int64_t widx; uint32_t cur, nxt; int off, dir;
-    __device__ __forceinline__ uint32_t norm(uint32_t v) const
-    {
-        v = __byte_perm(v, 0u, 0x0123u);   /* base j of the word at bits 31-2j .. 30-2j */
-        if (dir < 0) { v = __brev(v); v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); } /* base 15 first */
-        return v;
-    }
-    __device__ __forceinline__ void init(const uint8_t *pac, int64_t l, int d)
-    {
-        p32 = (const uint32_t *)pac; dir = d; widx = l >> 4;
-        const int j = (int)(l & 15);
-        cur = norm(__ldg(p32 + widx));
-        off = d > 0 ? 2 * j : 2 * (15 - j);
-        widx += d;
-        nxt = norm(__ldg(p32 + (widx < 0 ? 0 : widx)));
-    }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, (uint32_t)off); }
-    __device__ __forceinline__ void advance(int n)
-    { /* n <= 16 symbols consumed */
-        off += 2 * n;
-        if (off >= 32) { off -= 32; cur = nxt; widx += dir; nxt = norm(__ldg(p32 + (widx < 0 ? 0 : widx))); }
-    }
-};
-
-/* not-Eq of 32 query rows against one target symbol: two 3-input LOP3s (the compiler's own association of
- * the five inputs costs three) */
-__device__ __forceinline__ uint32_t lf_neq(uint32_t qlo, uint32_t qhi, uint32_t qnn, uint32_t slo, uint32_t shi)
-{
-#if defined(__CUDA_ARCH__)
-    uint32_t x, r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xbe;" : "=r"(x) : "r"(qlo), "r"(slo), "r"(qnn)); /* (a ^ b) | c */
-    asm("lop3.b32 %0, %1, %2, %3, 0xf6;" : "=r"(r) : "r"(x), "r"(qhi), "r"(shi));   /* a | (b ^ c) */
-    return r;
-#else
-    return (qlo ^ slo) | qnn | (qhi ^ shi);
-#endif
-}
-
 template <int NB, bool STORE>
 __device__ __forceinline__ void lf_bandreg_column(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], const uint32_t (&qlo)[NB], const uint32_t (&qhi)[NB],
                                                   const uint32_t (&qnn)[NB], uint32_t slo, uint32_t shi, uint32_t *sm, int wrel0)
