@@ -11,11 +11,20 @@
  *                     checkpoints every 16 columns and a windowed recompute for the traceback.
  *                     Replaces edlibAlign for tasks below the 1 MiB rule (edlib.cpp:101-221,
  *                     :657-858 distance, :872-1071 traceback).
+ *   k_myers_band<NB>  the same with the op planes of every column written to HBM and a walk over them instead
+ *                     of the recompute (prefix-mode tasks of q <= 128; optionally a sliding band + retry).
+ *   k_myers_bandreg<NB>  thread-per-task with a band of NB words in registers: the whole column for global-mode
+ *                     tasks of q <= 128, a sliding band with a certificate (Ukkonen's argument, edlib.cpp:722-760)
+ *                     for near-diagonal ones up to 512 rows; checkpoints + banded recompute, nothing per column in HBM.
  *   k_myers_large     warp-per-task wavefront (lane = 32-row word, lane-skewed columns, hin/hout
  *                     by __shfl_up) for everything else, including the Hirschberg recursion with
  *                     edlib's split rule (edlib.cpp:1090-1143, :1161-1330).
  *   k_ksw_extend      ksw_extend2 (lib/bwa/ksw.c:380-479) with its adaptive band, z-drop and
  *                     stale-cell behaviour kept exactly; int32 scores.
+ *
+ *   k_chain_tasks / k_chain_triggers / k_emit_slots   the chain operator's device side: round-1 task list from the
+ *                     chains, clip / split trigger tests (src/LordFAST.cpp:1840, :1952, :2175), run-length CIGAR / MD /
+ *                     record assembly (edlibCigar_*, edlibMD_*, :1570-1763).
  *
  * The results every kernel must reproduce are pure functions of the two strings (SURVEY.md
  * Appendix A/B): Levenshtein distance; for SHW the first target prefix (incl. the empty one, -1)
