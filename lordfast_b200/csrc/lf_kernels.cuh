@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
         {
             /* words 0..whi only, in compile-time sized variants (a quarter of the class width each) */
             constexpr int G = NW >= 8 ? NW / 4 : NW == 6 ? 2 : 1;
-            constexpr int SPAN = G + 1 < NW ? G + 1 : NW;
+            constexpr int SPAN = NW;   /* every computed word may hold the window: the variant is the warp's, not the smallest that covers this lane's row */
             const int ncols = c1 - c0;
             /* one variant for the lanes that are here together (the deepest row among them decides): lanes choosing
              * different variants would run them one after the other */
