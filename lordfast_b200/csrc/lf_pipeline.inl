@@ -336,8 +336,14 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         const bool serial = getenv("LF_SERIAL") != nullptr;
         int nstreams = getenv("LF_STREAMS") ? atoi(getenv("LF_STREAMS")) : LF_NSUB - 1;   /* class kernels in flight at once */
         if (nstreams < 1 || nstreams > LF_NSUB - 1) nstreams = LF_NSUB - 1;
-        for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
-        for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) seq[nseq++] = cls;
+        if (!getenv("LF_ORDER_BAND_FIRST")) {   /* the full-width classes (few, long tasks: the tail of the step) before the sliding-band ones */
+            for (int cls = LF_CLS_LARGE - 1; cls >= 8; cls--) seq[nseq++] = cls;
+            for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
+            for (int cls = 7; cls >= 0; cls--) seq[nseq++] = cls;
+        } else {
+            for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
+            for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) seq[nseq++] = cls;
+        }
         for (int si = 0; si < nseq; si++) {
             const int cls = seq[si];
             const uint32_t count = ht->cnt.hist[cls];
