@@ -59,6 +59,24 @@ def test_glue_sam_identical_on_emulator(tmp_path):
     assert any(f & 16 for f in flags) and any(not (f & 16) for f in flags)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference") and not os.path.exists(EMU_BIN), reason="glue binaries are built where the reference sources are")
+def test_glue_unmapped_and_short_reads_on_emulator(tmp_path):
+    """Reads below --minReadLen, reads without a candidate window and a homopolymer go through the unmapped branches of the
+    glue (mapSeq :484-496, :515-524) and must print exactly as the reference prints them."""
+    import numpy as np
+    from _common import build_emu
+    build_emu()
+    _dataset(tmp_path, ref_len=300_000, reads=20, read_len=3000, sv_frac=0.3, seed=9)
+    rng = np.random.default_rng(5)
+    with open(os.path.join(tmp_path, "reads.fa"), "a") as f:
+        for name, n in (("short1", 300), ("short2", 999), ("junk1", 5000), ("junk2", 2500)):
+            f.write(">%s\n%s\n" % (name, "".join(rng.choice(list("ACGT"), size=n))))
+        f.write(">polyA\n" + "A" * 3000 + "\n")
+    for threads in (1, 3):
+        recs = _compare(EMU_BIN, tmp_path, threads)
+        assert sum(1 for r in recs if int(r[1]) == 4) >= 4
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,kw,threads,extra", [
     ("config1", dict(ref_len=1_000_000, reads=200, read_len=10_000, err=[0.15, 0.15], seed=1), 4, ()),
