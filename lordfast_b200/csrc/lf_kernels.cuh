@@ -2163,7 +2163,7 @@ __device__ __forceinline__ int lf_bandreg_next_slide(int k, int kmax, int q, int
  * slides at this very column.
  * FWD accumulates the vertical deltas that leave through the top of the band (the distance needs them); STORE
  * writes the window planes. */
-template <int NBF, int NB, bool FWD, bool STORE, bool FULL>
+template <int NBF, int NB, bool FWD, bool STORE, bool FULL, bool SL = true>
 __device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv_)[NBF], uint32_t (&Mv_)[NBF], uint32_t (&qlo_)[NBF], uint32_t (&qhi_)[NBF], uint32_t (&qnn_)[NBF],
                                                  uint32_t tb, int c, int n, int &k, int &cslide, int &top, int q, int t, int kmax,
                                                  const LfDev &d, const LfQView &qv, uint32_t *smt, int wtop)
@@ -2182,7 +2182,7 @@ __device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv_)[NBF], uint32_t 
      * instruction cache when the classes run concurrently, and fully unrolled 8-column bodies (13-50 KB per kernel)
      * made all of them stall on instruction fetches. */
     int e = 0;
-    int stop = (unsigned)es < (unsigned)nn ? es : nn;
+    int stop = (SL && (unsigned)es < (unsigned)nn) ? es : nn;   /* !SL: the band is the whole column, it never slides */
     for (;;) {
 #pragma unroll 2
         for (; e < stop; e++) {
@@ -2204,10 +2204,10 @@ __device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv_)[NBF], uint32_t 
     }
     /* slides are more than 8 columns apart (q < 4t: 32 rows of the line take more than 8 columns), so a block holds
      * at most one and the next one is looked up once, here */
-    if ((unsigned)es < (unsigned)n) cslide = lf_bandreg_next_slide<NBF>(k, kmax, q, t);
+    if (SL && (unsigned)es < (unsigned)n) cslide = lf_bandreg_next_slide<NBF>(k, kmax, q, t);
 }
 
-template <int NB>
+template <int NB, bool SLIDE>
 __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count,
                                                        uint32_t *retry_list, uint32_t *retry_count, int nwmax)
 {
@@ -2221,10 +2221,10 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     const lf_align_task task = d.tasks[ti];
     const int q = (int)task.q_len, t = (int)task.t_len;
     const int nw = (q + 31) >> 5;
-    const int kmax = nw > NB ? nw - NB : 0;   /* 0: the band is the whole column and the result needs no certificate */
+    const int kmax = SLIDE ? (nw > NB ? nw - NB : 0) : 0;   /* 0: the band is the whole column and the result needs no certificate (!SLIDE: known at compile time, the slide code goes away) */
     const int dlt = q > t ? q - t : t - q;
     const int cert = 32 * (NB - 1) - 7 - dlt;
-    if (nw > nwmax || (kmax > 0 && (q >= 4 * t || cert < 0))) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
+    if (nw > nwmax || (!SLIDE && nw > NB) || (kmax > 0 && (q >= 4 * t || cert < 0))) { LF_BAND_COUNT(lf_emu_band_retry); retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
     LfQView qv; LfTView tv;
     lf_task_views(d, task, qv, tv);
 
@@ -2254,7 +2254,7 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         }
         const uint32_t tb = ts.peek();
         ts.advance(C);
-        lf_bandreg_block<NB, NB, true, false, true>(Pv, Mv, qlo, qhi, qnn, tb, c, C, k, cslide, top, q, t, kmax, d, qv, nullptr, 0);
+        lf_bandreg_block<NB, NB, true, false, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c, C, k, cslide, top, q, t, kmax, d, qv, nullptr, 0);
     }
     if (c < t) {
         if (c) {
@@ -2262,7 +2262,7 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
 #pragma unroll
             for (int w = 0; w < NB; w++) dst[w] = make_uint2(Pv[w], Mv[w]);
         }
-        lf_bandreg_block<NB, NB, true, false, false>(Pv, Mv, qlo, qhi, qnn, ts.peek(), c, t - c, k, cslide, top, q, t, kmax, d, qv, nullptr, 0);
+        lf_bandreg_block<NB, NB, true, false, false, SLIDE>(Pv, Mv, qlo, qhi, qnn, ts.peek(), c, t - c, k, cslide, top, q, t, kmax, d, qv, nullptr, 0);
     }
     int ed = t + top;
 #pragma unroll
@@ -2294,9 +2294,9 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     while (i > 0 && j > 0) {
         const int c1 = j, c0 = ((j - 1) / C) * C;
         while (bc0 > c0) { bc0 -= C; rl0 -= q8; ra0 -= r8; if (ra0 < 0) { ra0 += t; rl0--; } }
-        int k0 = (rl0 - 16 * NB + 16) >> 5;       /* band position after column c0-1: floor(c0*q/t) decides */
+        int k0 = SLIDE ? (rl0 - 16 * NB + 16) >> 5 : 0;       /* band position after column c0-1: floor(c0*q/t) decides */
         k0 = k0 < 0 ? 0 : k0 > kmax ? kmax : k0;
-        while (k != k0) { /* bring the query words of that band position into the registers (one word per ~32 columns) */
+        while (SLIDE && k != k0) { /* bring the query words of that band position into the registers (one word per ~32 columns) */
             if (k > k0) {
                 k--;
 #pragma unroll
@@ -2327,10 +2327,10 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         const uint32_t tb = ts.peek();
         constexpr int N1 = NB > 2 ? NB - 1 : NB, N2 = NB > 3 ? NB - 2 : N1;
         const int ns = lf_converged_max(c1 - c0 != C ? NB : need);   /* one variant for the lanes that are here together */
-        if (ns > N1) lf_bandreg_block<NB, NB, false, true, false>(Pv, Mv, qlo, qhi, qnn, tb, c0, c1 - c0, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        else if (N2 < N1 && ns <= N2) lf_bandreg_block<NB, N2, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        else if (N1 < NB && ns <= N1) lf_bandreg_block<NB, N1, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        else lf_bandreg_block<NB, NB, false, true, true>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        if (ns > N1) lf_bandreg_block<NB, NB, false, true, false, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, c1 - c0, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else if (N2 < N1 && ns <= N2) lf_bandreg_block<NB, N2, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else if (N1 < NB && ns <= N1) lf_bandreg_block<NB, N1, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
+        else lf_bandreg_block<NB, NB, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         /* walk inside the window, one word-row at a time */
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {

@@ -126,11 +126,11 @@ void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_
     LFB_LAUNCH(kern, grid, LF_K1_BLOCK, smem, s, v, order, first, count, retry_count);
 }
 
-template <int NB>
+template <int NB, bool SLIDE = true>
 void launch_bandreg(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, uint32_t *retry_list, uint32_t *retry_count, int nwmax)
 {   /* shared memory: the window planes of 8 columns, as much as the other size-class kernels use */
     const size_t smem = (size_t)8 * 2 * 2 * 128 * sizeof(uint32_t);
-    auto kern = k_myers_bandreg<NB>;
+    auto kern = k_myers_bandreg<NB, SLIDE>;
     LFB_LAUNCH(kern, (count + 127) / 128, 128, smem, s, v, order, first, count, retry_list, retry_count, nwmax);
 }
 
@@ -172,10 +172,10 @@ void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t
 {   /* rl: retry list (indexed like `order`), rc: this class's retry counter */
     if (cls < 8 && !(cls & 1) && bandreg_small()) {   /* global-mode tasks of q <= 128: the band is the whole column (no slides, no certificate) */
         switch (cls) {
-        case 0: launch_bandreg<1>(v, order, first, count, s, rl, rc, 1); return;
-        case 2: launch_bandreg<2>(v, order, first, count, s, rl, rc, 2); return;
-        case 4: launch_bandreg<3>(v, order, first, count, s, rl, rc, 3); return;
-        case 6: launch_bandreg<4>(v, order, first, count, s, rl, rc, 4); return;
+        case 0: launch_bandreg<1, false>(v, order, first, count, s, rl, rc, 1); return;
+        case 2: launch_bandreg<2, false>(v, order, first, count, s, rl, rc, 2); return;
+        case 4: launch_bandreg<3, false>(v, order, first, count, s, rl, rc, 3); return;
+        case 6: launch_bandreg<4, false>(v, order, first, count, s, rl, rc, 4); return;
         }
     }
     if (cls < LF_CLS_LARGE && band_nb(cls) && (bmask >> cls & 1u)) {
