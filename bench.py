@@ -349,7 +349,7 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum summed over the 23 alignment kernels of one config-2 step, one ncu --set full
                          # capture (profiles/r02i_ncu_full_alignment_kernels_final.txt): bytes per launch set, like `achieved`; 2.0 GB of it
                          # are the scattered per-task accesses of the 2.2 M tasks of q <= 128, 1.2 GB the large-task kernel plane scratch
-                         "traffic": 3.83e9 if wl_name == "config2_4.6Mbp_20kx10k" and a.sv_frac == 0.10 else None, "traffic_unit": "B per launch set",
+                         "traffic": 3.82e9 if wl_name == "config2_4.6Mbp_20kx10k" and a.sv_frac == 0.10 else None, "traffic_unit": "B per launch set",
                          "algorithmic_ops_per_launch_set": 16.0 * main_wc, "kernel_ms": mk_ms,
                          "peak_source": "lf_gpu_int32_peak (IADD3 stream, 64 SASS-verified ops/iteration) measured in this run", "int32_peaks_tops": peaks},
             "clocks": clocks,
