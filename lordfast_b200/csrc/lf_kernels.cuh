@@ -305,9 +305,14 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
     if (threadIdx.x == 0) { s_maxq = 0; s_maxt = 0; s_maxp = 0; s_cells = 0; s_wc = 0; s_swc = 0; }
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    /* this thread's contributions; reduced over the warp below (256 threads hitting the same shared counters with 64-bit
+     * atomics made this kernel 10x slower than its 110 MB of traffic) */
+    unsigned long long my_cells = 0, my_wc = 0, my_swc = 0, my_maxp = 0;
+    uint32_t my_maxq = 0, my_maxt = 0;
+    int cls = -1;
     if (i < d.n_tasks) {
         lf_align_task t = d.tasks[i];
-        int cls = LF_CLS_BAD;
+        cls = LF_CLS_BAD;
         uint32_t scr = 0, slot = 0;
         bool ok = t.q_len >= 1 && t.t_len >= 1 && t.read_id < d.n_reads && t.mode <= LF_MODE_SHW;
         if (ok) {
@@ -322,21 +327,18 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
                 cls = 2 * sc + (t.mode == LF_MODE_SHW ? 1 : 0);
                 if (sc >= 4 && (d.bandreg >> (sc - 4) & 1u) && t.mode == LF_MODE_NW && lf_bandreg_eligible(t.q_len, t.t_len, sc)) cls = LF_CLS_BANDREG0 + sc - 4;
                 scr = lf_k1_ckpt_bytes(t.t_len, lf_small_nw(sc));
-                atomicAdd(&s_swc, (unsigned long long)nwords * t.t_len);
+                my_swc = (unsigned long long)nwords * t.t_len;
             } else {
                 cls = LF_CLS_LARGE;
-                atomicMax(&s_maxq, t.q_len);
-                atomicMax(&s_maxt, t.t_len);
-                atomicMax(&s_maxp, lf_large_planes_bytes(t.q_len, t.t_len));
+                my_maxq = t.q_len; my_maxt = t.t_len; my_maxp = lf_large_planes_bytes(t.q_len, t.t_len);
             }
             slot = (t.flags & LF_F_NO_PATH) ? 0u : (t.q_len + t.t_len + 15u) >> 4;
-            atomicAdd(&s_cells, (unsigned long long)t.q_len * t.t_len);
-            atomicAdd(&s_wc, (unsigned long long)nwords * t.t_len);
+            my_cells = (unsigned long long)t.q_len * t.t_len;
+            my_wc = (unsigned long long)nwords * t.t_len;
         } else {
             lf_align_result r; r.edit_distance = -1; r.end_location = -1; r.ops_off = 0; r.ops_len = 0; r.status = LF_ERR_BAD_ARG;
             d.res[i] = r;
         }
-        atomicAdd(&s_hist[cls], 1u);
         /* class-major, long targets first; the target length is quantised to 1/8 octave so that a warp's
          * 32 tasks run nearly the same number of columns, and inside a bucket the (stable) sort keeps the
          * submission order, i.e. neighbouring lanes work on neighbouring reads and result slots */
@@ -347,6 +349,32 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
         idx[i] = i;
         slot_words[i] = slot;
         scr_bytes[i] = scr;
+    }
+    {   /* warp reduction, then one shared-memory atomic per warp and counter */
+        const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            my_cells += __shfl_down_sync(LF_FULL, my_cells, o);
+            my_wc += __shfl_down_sync(LF_FULL, my_wc, o);
+            my_swc += __shfl_down_sync(LF_FULL, my_swc, o);
+            const unsigned long long p = __shfl_down_sync(LF_FULL, my_maxp, o);
+            const uint32_t mq = __shfl_down_sync(LF_FULL, my_maxq, o), mt = __shfl_down_sync(LF_FULL, my_maxt, o);
+            my_maxp = p > my_maxp ? p : my_maxp; my_maxq = mq > my_maxq ? mq : my_maxq; my_maxt = mt > my_maxt ? mt : my_maxt;
+        }
+        if (lane == 0) {
+            if (my_cells) atomicAdd(&s_cells, my_cells);
+            if (my_wc) atomicAdd(&s_wc, my_wc);
+            if (my_swc) atomicAdd(&s_swc, my_swc);
+            if (my_maxq) atomicMax(&s_maxq, my_maxq);
+            if (my_maxt) atomicMax(&s_maxt, my_maxt);
+            if (my_maxp) atomicMax(&s_maxp, my_maxp);
+        }
+#if defined(__CUDA_ARCH__)
+        const unsigned same = __match_any_sync(LF_FULL, cls);   /* the lanes of this warp that are in the same class */
+        if (cls >= 0 && lane == (uint32_t)(__ffs((int)same) - 1)) atomicAdd(&s_hist[cls], (uint32_t)__popc(same));
+#else
+        if (cls >= 0) atomicAdd(&s_hist[cls], 1u);
+#endif
     }
     __syncthreads();
     if (threadIdx.x < LF_NCLS && s_hist[threadIdx.x]) atomicAdd(&cnt->hist[threadIdx.x], s_hist[threadIdx.x]);
