@@ -146,7 +146,7 @@ void launch_band(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t
 }
 
 #ifndef LF_BAND_MASK_DEFAULT
-#define LF_BAND_MASK_DEFAULT 0x00ff
+#define LF_BAND_MASK_DEFAULT 0x0000
 #endif
 /* band width (32-row words) the class is run with by k_myers_band; 0 = full-width k_myers_small only */
 int band_nb(int cls)
@@ -158,9 +158,10 @@ int band_nb(int cls)
 }
 
 /* Which classes run k_myers_band (bit = class id); the others run the full-width k_myers_small.  Measured on B200
- * (profiles/r01g_band_mask_sweep.txt): keeping the op planes in HBM instead of recomputing them is a small win for
- * the unbanded classes (q <= 128), while the banded variant + full-width retry loses to the full-width kernel on
- * the SV-rich workload, so it stays off by default.  LF_BAND_MASK overrides (tests run 0xffff on the emulator). */
+ * (profiles/r01g_band_mask_sweep.txt): keeping the op planes in HBM instead of recomputing them was a small win for
+ * the unbanded classes (q <= 128) until k_myers_bandreg took their global-mode tasks; for the prefix-mode ones that
+ * are left (1.5 % of the tasks) it makes no difference, and without any plane class the step saves a kernel, a scan
+ * and a host round trip, so the default is none.  LF_BAND_MASK overrides (tests run 0xff / 0xffff). */
 uint32_t band_mask()
 {
     const char *e = getenv("LF_BAND_MASK");
@@ -281,7 +282,8 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         }
         gc.gbase[LF_CLS_LARGE] = g;
     }
-    const uint32_t ngroups = gc.gbase[LF_CLS_LARGE];
+    uint32_t ngroups = gc.gbase[LF_CLS_LARGE];
+    { uint32_t any = 0; for (int cls = 0; cls < LF_CLS_LARGE; cls++) any |= gc.count[cls] ? gc.nb[cls] : 0u; if (!any) ngroups = 0; }   /* no class stores op planes: no regions, no second host round trip */
     if (ngroups) {
         LF_TRY(d.gbytes.reserve((size_t)ngroups * 4 + 64)); LF_TRY(d.goff.reserve(((size_t)ngroups + 1) * 8));
         v = make_dev(ctx, d);
