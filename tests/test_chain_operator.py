@@ -174,3 +174,32 @@ def test_gpu_chain_operator_fallback_paths(monkeypatch, env):
     _crafted(None)
     _golden(None)
     _simulated(None, 200, 6_000, 1_000_000)
+
+
+def _edge_cases(lib_path):
+    """Empty chain list, a chain without any gap / head / tail task (one merged match run), a chain naming a read that does
+    not exist (rejected with LF_ERR_BAD_ARG, nothing aligned)."""
+    ref = sim.make_reference(50_000, 3)
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=lib_path)
+    reads = ref[1000:3000].copy()
+    off = np.array([0, 2000], dtype=np.uint64)
+    recs, text, st = g.align_chains(reads, off, [0], [len(ref)], np.zeros(0, dtype=api.SEED), np.zeros(0, dtype=api.CHAIN))
+    assert len(recs) == 0 and st.round1_tasks == 0
+    seeds = np.array([(1000, 0, 1000), (2000, 1000, 1000)], dtype=api.SEED)
+    recs, text, st = g.align_chains(reads, off, [0], [len(ref)], seeds, np.array([(0, 2, 0, 0, 0)], dtype=api.CHAIN))
+    got = api.records_to_dicts(recs, text)
+    idx = O.RefIndex(ref.tobytes())
+    exp, _ = O.oracle_align_chain(idx, [(1000, 0, 1000), (2000, 1000, 1000)], reads.tobytes(), 0)
+    assert [{k: v for k, v in r.items() if k != "chain"} for r in got] == exp
+    with pytest.raises(api.LfGpuError):
+        g.align_chains(reads, off, [0], [len(ref)], seeds, np.array([(0, 2, 5, 0, 0)], dtype=api.CHAIN))
+    g.close()
+
+
+def test_emu_chain_operator_edge_cases():
+    _edge_cases(build_emu())
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_edge_cases():
+    _edge_cases(None)
