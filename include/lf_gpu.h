@@ -153,9 +153,10 @@ int lf_gpu_download_extend(lf_gpu_ctx *ctx, lf_extend_result *res);
 
 /* alignChain_edlib (src/LordFAST.cpp:1765-2258, reached through the reference's hook
  * `void (*alignChain)(Chain_t&, char*, int32_t, int, SamList_t&)`, :107) for a whole chunk of
- * candidate chains: round-1 alignments, the clip / split triggers (evaluated on the host with the
- * reference's float expressions), ksw extensions, follow-up alignments, and the reference's
- * CIGAR / MD accumulation.  One lf_sam_record per Sam_t the reference would push to map.samList,
+ * candidate chains: round-1 alignments (the task list is derived from the chains on the device), the
+ * clip / split triggers (the reference's float expressions, evaluated on the device; the split /
+ * inversion decisions that need follow-up distances on the host), ksw extensions, follow-up
+ * alignments, and the reference's CIGAR / MD accumulation (on the device for single-device contexts).  One lf_sam_record per Sam_t the reference would push to map.samList,
  * in chain order.  The caller (lordFAST's alignWin, :1063-1083) computes alnScore / totalScore from
  * nmCount, qStart, qEnd exactly as today. */
 typedef struct { uint32_t tPos, qPos, len; } lf_seed;      /* Seed_t (src/LordFAST.h:30-35), bit-fields unpacked */
