@@ -354,8 +354,7 @@ def main():
                          "algorithmic_ops_per_launch_set": 16.0 * main_wc, "kernel_ms": mk_ms,
                          "peak_source": "lf_gpu_int32_peak (IADD3 stream, 64 SASS-verified ops/iteration) measured in this run", "int32_peaks_tops": peaks},
             "clocks": clocks,
-            "class_timeline_ms": {("large" if c == 16 else f"band{[3,4,4,5][c - 18]}_NW{[6,8,12,16][c - 18]}" if c >= 18 else f"NW{[1,2,3,4,6,8,12,16][c // 2]}{'_shw' if c % 2 else ''}"):
-                                  [round(float(tl_start[c]), 3), round(float(tl_end[c]), 3)] for c in range(len(tl_end)) if c != 17 and tl_end[c] >= 0},
+            "class_timeline_ms": {api.CLASS_NAMES[c]: [round(float(tl_start[c]), 3), round(float(tl_end[c]), 3)] for c in range(len(tl_end)) if c != 17 and tl_end[c] >= 0},
         }
         if not a.no_cpu_baseline:
             v, kind, cores, sample = cpu_reference_rate(w, os.cpu_count() or 1, max_chains=4000)

@@ -204,8 +204,13 @@ int lf_gpu_get_stats(const lf_gpu_ctx *ctx, lf_gpu_stats *out);
 
 /* Timeline of the last lf_gpu_run_align on device 0: start / end (ms after the first launch) of each size-class
  * kernel; index 2*i+shw for the register classes (NW = 1,2,3,4,6,8,12,16), 16 = large-task kernel, 18..21 = the
- * banded register classes (near-diagonal global tasks of NW = 6,8,12,16); -1 = not run.  n >= 22. */
+ * banded register classes (near-diagonal global tasks of NW = 6,8,12,16), 22..28 = the lane-group classes; -1 = not run.
+ * n >= 29. */
 int lf_gpu_class_timeline(lf_gpu_ctx *ctx, float *start_ms, float *end_ms, int n);
+
+/* Tasks per size class of the last lf_gpu_run_align on device 0 (same indices as lf_gpu_class_timeline; 22..28 = the
+ * lane-group classes of k_myers_group: path 9-16 / 17-32 / 33-64 words, distance-only 17-32 / 33-64 / 65-128 / 129-256 words). */
+int lf_gpu_class_counts(lf_gpu_ctx *ctx, uint32_t *counts, int n);
 
 /* INT32 issue-rate microbenchmarks on device 0 (dependent-free streams on all SMs); Top/s.
  * which: 0 = LOP3 only, 1 = IADD3 only, 2 = LOP3+IADD3 mix, 3 = LOP3 + IMAD mix */

@@ -11,7 +11,10 @@ import os
 
 import numpy as np
 
-N_CLASSES = 22  # LF_NCLS: 16 register classes, large, bad, 4 banded register classes
+N_CLASSES = 29  # LF_NCLS: 16 register classes, large, bad, 4 banded register classes, 7 lane-group classes
+CLASS_NAMES = ([f"NW{w}{s}" for w in (1, 2, 3, 4, 6, 8, 12, 16) for s in ("", "_shw")] + ["large", "bad"]
+               + [f"band{b}_NW{w}" for b, w in ((3, 6), (4, 8), (4, 12), (5, 16))]
+               + ["group_path16", "group_path32", "group_path64", "group_dist32", "group_dist64", "group_dist128", "group_dist256"])
 # the size-class kernels run on 18 streams; give each its own hardware queue (must be set before CUDA starts)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
@@ -61,7 +64,7 @@ EXPORTS = ["lf_gpu_init", "lf_gpu_prewarm", "lf_gpu_destroy", "lf_gpu_last_error
            "lf_gpu_ops_capacity", "lf_gpu_align_batch", "lf_gpu_extend_batch", "lf_gpu_upload_reads",
            "lf_gpu_upload_align_tasks", "lf_gpu_run_align", "lf_gpu_sync", "lf_gpu_download_align",
            "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",
-           "lf_gpu_int32_peak", "lf_gpu_class_timeline", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
+           "lf_gpu_int32_peak", "lf_gpu_class_timeline", "lf_gpu_class_counts", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
            "lf_chain_results_stats", "lf_chain_results_free"]
 
 
@@ -100,6 +103,7 @@ def load(lib_path: str | None = None) -> C.CDLL:
     lib.lf_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.lf_gpu_int32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.lf_gpu_class_timeline.argtypes = [vp, vp, vp, C.c_int]
+    lib.lf_gpu_class_counts.argtypes = [vp, vp, C.c_int]
     lib.lf_gpu_align_chains.argtypes = [vp, C.POINTER(Reads), C.POINTER(Contigs), vp, vp, sz, vp, C.POINTER(vp)]
     lib.lf_chain_results_records.argtypes = [vp, C.POINTER(sz)]
     lib.lf_chain_results_records.restype = vp
@@ -249,6 +253,12 @@ class LfGpu:
         a = np.zeros(N_CLASSES, dtype=np.float32); b = np.zeros(N_CLASSES, dtype=np.float32)
         self._check(self.lib.lf_gpu_class_timeline(self.ctx, _ptr(a), _ptr(b), N_CLASSES), "lf_gpu_class_timeline")
         return a, b
+
+    def class_counts(self) -> dict:
+        """tasks per size class of the last run_align (names: api.CLASS_NAMES)"""
+        a = np.zeros(N_CLASSES, dtype=np.uint32)
+        self._check(self.lib.lf_gpu_class_counts(self.ctx, _ptr(a), N_CLASSES), "lf_gpu_class_counts")
+        return {CLASS_NAMES[c]: int(a[c]) for c in range(N_CLASSES) if a[c]}
 
     def int32_peak(self, which: int) -> float:
         v = C.c_double()

@@ -10,13 +10,15 @@ from __future__ import annotations
 
 import numpy as np
 
-from .api import ALIGN_TASK, LF_F_READ_REV, LF_F_REVERSE_BOTH, LF_MODE_NW, LF_MODE_SHW
+from .api import ALIGN_TASK, LF_F_NO_PATH, LF_F_READ_REV, LF_F_REVERSE_BOTH, LF_MODE_NW, LF_MODE_SHW
+
+CLIP_LEN = 500  # _pf_clipLen (src/LordFAST.cpp:88)
 
 KIND_HEAD, KIND_GAP, KIND_TAIL = 0, 1, 2
 
 
 def round1_tasks(seeds: np.ndarray, seed_off: np.ndarray, is_rev: np.ndarray, read_len: np.ndarray,
-                 contig_off: np.ndarray, contig_len: np.ndarray, read_id: np.ndarray | None = None):
+                 contig_off: np.ndarray, contig_len: np.ndarray, read_id: np.ndarray | None = None, long_ends_nopath: bool = True):
     """seeds uint32[m,3] (tPos,qPos,len); one chain per entry of seed_off[:-1].
     Returns (tasks, chain_of_task, kind_of_task) with tasks in chain order: head, gaps, tail."""
     n = len(seed_off) - 1
@@ -57,7 +59,9 @@ def round1_tasks(seeds: np.ndarray, seed_off: np.ndarray, is_rev: np.ndarray, re
     head = np.zeros(len(hc), dtype=ALIGN_TASK)
     head["read_id"], head["q_off"], head["q_len"] = read_id[hc], 0, a[hc]
     head["t_off"], head["t_len"] = s[first[hc], 0] - (a[hc] + 20), a[hc] + 20
-    head["flags"], head["mode"] = strand[hc] | LF_F_REVERSE_BOTH, LF_MODE_SHW
+    # heads / tails longer than _pf_clipLen: distance and end only in round 1, as lf_gpu_align_chains issues them (their
+    # path is thrown away whenever the clip test fires and the extension shortens them; otherwise round 3 computes it)
+    head["flags"], head["mode"] = strand[hc] | LF_F_REVERSE_BOTH | np.where((a[hc] > CLIP_LEN) & long_ends_nopath, LF_F_NO_PATH, 0).astype(np.uint16), LF_MODE_SHW
 
     # tail
     qs_t = s[last, 1] + s[last, 2]
@@ -68,7 +72,7 @@ def round1_tasks(seeds: np.ndarray, seed_off: np.ndarray, is_rev: np.ndarray, re
     tail = np.zeros(len(tc), dtype=ALIGN_TASK)
     tail["read_id"], tail["q_off"], tail["q_len"] = read_id[tc], qs_t[tc], b[tc]
     tail["t_off"], tail["t_len"] = ts_t[tc], b[tc] + 20
-    tail["flags"], tail["mode"] = strand[tc], LF_MODE_SHW
+    tail["flags"], tail["mode"] = strand[tc] | np.where((b[tc] > CLIP_LEN) & long_ends_nopath, LF_F_NO_PATH, 0).astype(np.uint16), LF_MODE_SHW
 
     tasks = np.concatenate([head, gap, tail])
     chain = np.concatenate([hc, gc, tc])
@@ -78,7 +82,7 @@ def round1_tasks(seeds: np.ndarray, seed_off: np.ndarray, is_rev: np.ndarray, re
     return np.ascontiguousarray(tasks[order]), chain[order], kind[order]
 
 
-def workload_tasks(w):
-    """Round-1 tasks of a sim.Workload (one chain per read)."""
+def workload_tasks(w, long_ends_nopath: bool = True):
+    """Round-1 tasks of a sim.Workload (one chain per read); long_ends_nopath=False asks for the path of every task."""
     read_len = np.diff(w.read_off)
-    return round1_tasks(w.seeds, w.seed_off, w.is_rev, read_len, w.contig_off, w.contig_len)
+    return round1_tasks(w.seeds, w.seed_off, w.is_rev, read_len, w.contig_off, w.contig_len, long_ends_nopath=long_ends_nopath)

@@ -106,10 +106,15 @@ inline lf_align_task mk_task(uint32_t rid, uint32_t qo, uint32_t ql, uint32_t to
     t.read_id = rid; t.q_off = qo; t.q_len = ql; t.t_off = to; t.t_len = tl; t.flags = (uint16_t)flags; t.mode = (uint8_t)mode; t.reserved = 0;
     return t;
 }
+/* Heads / tails longer than _pf_clipLen are asked for distance and end only in round 1 (k_chain_tasks does the same):
+ * the reference throws their path away whenever the clip test fires and the extension shortens them (:1850-1853,
+ * :2181-2184) -- every junk end -- and otherwise round 3 computes it. */
+inline unsigned long_end(int32_t len) { return len > kClipLen ? (unsigned)LF_F_NO_PATH : 0u; }
+
 inline lf_extend_task mk_ext(uint32_t rid, uint32_t qo, uint32_t ql, uint32_t to, uint32_t tl, unsigned flags, bool clip)
 {
     lf_extend_task t;
-    t.read_id = rid; t.q_off = qo; t.q_len = ql; t.t_off = to; t.t_len = tl; t.flags = (uint16_t)flags; t.matrix = LF_MAT_CLIP; t.reserved = 0;
+    t.read_id = rid; t.q_off = qo; t.q_len = ql; t.t_off = to; t.t_len = tl; t.flags = (uint16_t)(flags & (LF_F_READ_REV | LF_F_REVERSE_BOTH)); t.matrix = LF_MAT_CLIP; t.reserved = 0;
     if (clip) { t.o_del = 0; t.e_del = 1; t.o_ins = 0; t.e_ins = 1; t.w = 40; t.zdrop = 40; }   /* :1848, :2180 */
     else { t.o_del = 8; t.e_del = 1; t.o_ins = 4; t.e_ins = 1; t.w = 100; t.zdrop = 200; }      /* :1971, :1981 */
     t.h0 = (int32_t)ql;
@@ -544,7 +549,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             const int32_t a = (int32_t)s[0].qPos;
             p.head_guard = a > 0 && (int64_t)s[0].tPos - (a + 20) >= (int64_t)p.chrBeg;                       /* :1823-1825 */
             bool cand = false;
-            if (p.head_guard) { cnt++; slots += ((uint64_t)(2 * a + 20) + 15) >> 4; cand |= a > kClipLen; }
+            if (p.head_guard) { cnt++; if (a <= kClipLen) slots += ((uint64_t)(2 * a + 20) + 15) >> 4; cand |= a > kClipLen; }
             for (uint32_t i = 0; i + 1 < n; i++) {
                 const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
                 const int32_t ql = (int32_t)(s[i + 1].qPos - qs), tl = (int32_t)(s[i + 1].tPos - ts);
@@ -553,7 +558,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
             const int32_t b = (int32_t)readLen - (int32_t)qs;
             p.tail_guard = b > 0 && s[n - 1].tPos + s[n - 1].len + (uint32_t)(b + 20) - 1 <= p.chrEnd;         /* :2161-2163 */
-            if (p.tail_guard) { cnt++; slots += ((uint64_t)(2 * b + 20) + 15) >> 4; cand |= b > kClipLen; }
+            if (p.tail_guard) { cnt++; if (b <= kClipLen) slots += ((uint64_t)(2 * b + 20) + 15) >> 4; cand |= b > kClipLen; }
             ntask[c] = cnt; nslot[c] = slots; hascand[c] = cand ? 1 : 0;
         }
     });
@@ -591,7 +596,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             }
             if (p.head_guard) {
                 p.head_task = (int32_t)k;
-                t1[k++] = mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH, LF_MODE_SHW);
+                t1[k++] = mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH | long_end(a), LF_MODE_SHW);
             }
             for (uint32_t i = 0; i + 1 < n; i++) {
                 const uint32_t qs = s[i].qPos + s[i].len, ts = s[i].tPos + s[i].len;
@@ -602,7 +607,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                 const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
                 const int32_t b = (int32_t)readLen - (int32_t)qs;
                 p.tail_task = (int32_t)k;
-                t1[k++] = mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand, LF_MODE_SHW);
+                t1[k++] = mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand | long_end(b), LF_MODE_SHW);
             }
         }
     });
@@ -618,7 +623,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         size_t k = task_base[c];
         if (p.head_guard) {
             const int32_t a = (int32_t)s[0].qPos;
-            if (k == ti) return mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH, LF_MODE_SHW);
+            if (k == ti) return mk_task(ch.read_id, 0, (uint32_t)a, s[0].tPos - (uint32_t)(a + 20), (uint32_t)(a + 20), strand | LF_F_REVERSE_BOTH | long_end(a), LF_MODE_SHW);
             k++;
         }
         for (uint32_t i = 0; i + 1 < n; i++) {
@@ -629,7 +634,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
         const uint32_t qs = s[n - 1].qPos + s[n - 1].len;
         const int32_t b = (int32_t)readLen - (int32_t)qs;
-        return mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand, LF_MODE_SHW);
+        return mk_task(ch.read_id, qs, (uint32_t)b, s[n - 1].tPos + s[n - 1].len, (uint32_t)(b + 20), strand | long_end(b), LF_MODE_SHW);
     };
     /* per-chain inputs of the GPU emit that are known now */
     std::vector<uint64_t> slot_base;   /* a chain of n anchors has n + 1 slots: head, n - 1 gaps, tail */
@@ -781,12 +786,30 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<SplitInfo> splits;
     std::vector<int32_t> gap_split(gpu_emit ? 0 : total_seeds, -1);   /* per (chain, seed i): index into splits, host emit only */
     std::vector<uint32_t> dirty_list, clean_list;   /* chains a trigger fired for (ascending), and the others */
-    {   /* the few thousand hits, in task (= chain, then head / gaps / tail) order: the order of the serial scan */
+    {   /* the few thousand hits, in task (= chain, then head / gaps / tail) order: the order of the serial scan; with
+         * them the long heads / tails round 1 only measured (long_end): whatever the clip test says, round 3 has
+         * something to do for them */
+        std::vector<uint32_t> ev;
+        {
+            std::vector<uint32_t> long_tasks;
+            for (size_t c = 0; c < n_chains; c++) {
+                if (!hascand[c]) continue;
+                const ChainPlan &p = plan[c];
+                const lf_seed *sd = seeds + chains[c].seed_off;
+                if (p.head_task >= 0 && (int32_t)sd[0].qPos > kClipLen) long_tasks.push_back((uint32_t)p.head_task);
+                if (p.tail_task >= 0) {
+                    const uint32_t n = chains[c].n_seeds;
+                    const uint32_t readLen = (uint32_t)(reads->offsets[chains[c].read_id + 1] - reads->offsets[chains[c].read_id]);
+                    if ((int32_t)readLen - (int32_t)(sd[n - 1].qPos + sd[n - 1].len) > kClipLen) long_tasks.push_back((uint32_t)p.tail_task);
+                }
+            }
+            ev.resize(trig.size() + long_tasks.size());
+            ev.resize((size_t)(std::set_union(trig.begin(), trig.end(), long_tasks.begin(), long_tasks.end(), ev.begin()) - ev.begin()));
+        }
         size_t k = 0;
-        while (k < trig.size()) {
-            const uint32_t c = (uint32_t)(std::upper_bound(task_base.begin(), task_base.end(), (uint64_t)trig[k]) - task_base.begin() - 1);
+        while (k < ev.size()) {
+            const uint32_t c = (uint32_t)(std::upper_bound(task_base.begin(), task_base.end(), (uint64_t)ev[k]) - task_base.begin() - 1);
             const lf_chain &ch = chains[c];
-            const uint32_t n = ch.n_seeds;
             const unsigned strand = ch.is_rev ? LF_F_READ_REV : 0;
             ChainPlan &p = plan[c];
             dirty_list.push_back(c);
@@ -794,19 +817,18 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             const lf_seed *sd = seeds + ch.seed_off;
             uint32_t gi = 0;   /* gaps are visited in order: the chain's hits are ascending too */
             int64_t gtask = (int64_t)task_base[c] + (p.head_task >= 0 ? 1 : 0) - 1;   /* task of the last gap passed */
-            for (; k < trig.size() && trig[k] < task_base[c + 1]; k++) {
-                const int32_t ti = (int32_t)trig[k];
+            for (; k < ev.size() && ev[k] < task_base[c + 1]; k++) {
+                const int32_t ti = (int32_t)ev[k];
+                const bool fired = std::binary_search(trig.begin(), trig.end(), (uint32_t)ti);
                 const lf_align_task t = task_at(c, (size_t)ti);
                 if (ti == p.head_task) {
                     p.head_clip = (int32_t)clips.size();
-                    clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
-                    e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, true));
-                    e2_src.push_back(2u * (uint32_t)ti);
+                    clips.push_back(ClipInfo{ fired ? (int32_t)e2.size() : -1, -1, 0, 0 });
+                    if (fired) { e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand | LF_F_REVERSE_BOTH, true)); e2_src.push_back(2u * (uint32_t)ti); }
                 } else if (ti == p.tail_task) {
                     p.tail_clip = (int32_t)clips.size();
-                    clips.push_back(ClipInfo{ (int32_t)e2.size(), -1, 0, 0 });
-                    e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true));
-                    e2_src.push_back(2u * (uint32_t)ti);
+                    clips.push_back(ClipInfo{ fired ? (int32_t)e2.size() : -1, -1, 0, 0 });
+                    if (fired) { e2.push_back(mk_ext(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, strand, true)); e2_src.push_back(2u * (uint32_t)ti); }
                 } else {
                     for (;; gi++) {   /* the gap whose task this is: gaps get their tasks in order */
                         const int32_t ql = (int32_t)(sd[gi + 1].qPos - (sd[gi].qPos + sd[gi].len)), tl = (int32_t)(sd[gi + 1].tPos - (sd[gi].tPos + sd[gi].len));
@@ -897,11 +919,14 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         if (p.head_clip >= 0) {
             ClipInfo &ci = clips[(size_t)p.head_clip];
             const lf_align_task t = task_at(c, (size_t)p.head_task);
-            ci.qle = x2[(size_t)ci.ext].qle; ci.tle = x2[(size_t)ci.ext].tle;
-            if (ci.qle > 0 && ci.qle < (int32_t)t.q_len) {                                         /* :1850-1853 */
-                ci.t3 = (int32_t)t3.size();
+            if (ci.ext >= 0) { ci.qle = x2[(size_t)ci.ext].qle; ci.tle = x2[(size_t)ci.ext].tle; }
+            ci.t3 = (int32_t)t3.size();
+            if (ci.ext >= 0 && ci.qle > 0 && ci.qle < (int32_t)t.q_len)                            /* :1850-1853 */
                 t3.push_back(mk_task(ch.read_id, t.q_len - (uint32_t)ci.qle, (uint32_t)ci.qle, s[0].tPos - (uint32_t)ci.tle, (uint32_t)ci.tle,
                                      strand | LF_F_REVERSE_BOTH, LF_MODE_NW));
+            else {   /* "use the already calculated results" (:1869-1886): the prefix-mode alignment itself, now with its path */
+                ci.qle = (int32_t)t.q_len; ci.tle = (int32_t)t.t_len;
+                t3.push_back(mk_task(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, t.flags & ~(unsigned)LF_F_NO_PATH, LF_MODE_SHW));
             }
         }
         for (int32_t sx = p.split_lo; sx < p.split_hi; sx++) {
@@ -931,10 +956,13 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         if (p.tail_clip >= 0) {
             ClipInfo &ci = clips[(size_t)p.tail_clip];
             const lf_align_task t = task_at(c, (size_t)p.tail_task);
-            ci.qle = x2[(size_t)ci.ext].qle; ci.tle = x2[(size_t)ci.ext].tle;
-            if (ci.qle > 0 && ci.qle < (int32_t)t.q_len) {                                         /* :2181-2184 */
-                ci.t3 = (int32_t)t3.size();
+            if (ci.ext >= 0) { ci.qle = x2[(size_t)ci.ext].qle; ci.tle = x2[(size_t)ci.ext].tle; }
+            ci.t3 = (int32_t)t3.size();
+            if (ci.ext >= 0 && ci.qle > 0 && ci.qle < (int32_t)t.q_len)                            /* :2181-2184 */
                 t3.push_back(mk_task(ch.read_id, t.q_off, (uint32_t)ci.qle, t.t_off, (uint32_t)ci.tle, strand, LF_MODE_NW));
+            else {   /* :2196-2217 */
+                ci.qle = (int32_t)t.q_len; ci.tle = (int32_t)t.t_len;
+                t3.push_back(mk_task(ch.read_id, t.q_off, t.q_len, t.t_off, t.t_len, t.flags & ~(unsigned)LF_F_NO_PATH, LF_MODE_SHW));
             }
         }
     }

@@ -54,9 +54,19 @@
 #define LF_CLS_LARGE 16   /* class id of k_myers_large tasks (small classes are 2*i + shw) */
 #define LF_CLS_BAD 17
 #define LF_CLS_BANDREG0 18 /* 18..21: global-mode tasks of size classes 4..7 that k_myers_bandreg runs in a sliding band */
-#define LF_NCLS 22
+/* 22..28: k_myers_group classes (LANES lanes per task).  GPnn: with path, leaves of up to nn words; GDnn: distance only */
+#define LF_CLS_GP16 22    /*   9 ..  16 words: 4 lanes x 4 words (off-diagonal / prefix-mode tasks of 257 .. 512 rows) */
+#define LF_CLS_GP32 23    /*  17 ..  32 words: 8 x 4 */
+#define LF_CLS_GP64 24    /*  33 ..  64 words: 8 x 8 */
+#define LF_CLS_GD32 25    /*  17 ..  32 words: 8 x 4 */
+#define LF_CLS_GD64 26    /*  33 ..  64 words: 8 x 8 */
+#define LF_CLS_GD128 27   /*  65 .. 128 words: 16 x 8 */
+#define LF_CLS_GD256 28   /* 129 .. 256 words: 32 x 8 */
+#define LF_NGROUPCLS 7
+#define LF_NCLS 29
 #define LF_KEY_SHIFT 19    /* sort keys use bits [19,32): 5 bits of class, 8 bits of length bucket */
 #define LF_LARGE_STACK 96 /* Hirschberg stack entries per warp (depth <= log2(t)+2) */
+#define LF_CLIP_LEN 500   /* _pf_clipLen, src/LordFAST.cpp:88: heads / tails longer than this are first asked for their distance only */
 
 __host__ __device__ __forceinline__ int lf_small_nw(int i)
 { /* words of 32 rows held in registers by size class i */
@@ -102,11 +112,13 @@ struct LfDev {
     uint8_t *scratch;
     uint8_t *planes;                       /* op planes of k_myers_band, one region per warp group */
     uint32_t bandreg;                      /* bit i: near-diagonal global tasks of size class 4+i (128 < q <= 512) go to k_myers_bandreg */
+    uint32_t groupk;                       /* k_myers_group classes in use: bit 0 distance-only (GDnn), bit 1 GP32 / GP64, bit 2 GP16 */
 };
 
 struct LfCounters { /* written by k_align_prep, read back by the host (one small D2H per batch) */
     uint32_t hist[LF_NCLS];
     uint32_t max_q, max_t;
+    uint32_t gmax_t[LF_NGROUPCLS + 1];     /* longest target per k_myers_group class (sizes the plane scratch) */
     unsigned long long max_planes, cells, word_columns, small_word_columns;
 };
 
@@ -323,16 +335,25 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
         if (ok) {
             uint32_t nwords = (t.q_len + 31u) >> 5;
             int sc = lf_small_class(nwords);
-            if (sc >= 0 && lf_is_leaf(t.q_len, t.t_len)) {
+            const bool leaf = lf_is_leaf(t.q_len, t.t_len), nopath = (t.flags & LF_F_NO_PATH) != 0;
+            if (sc >= 0 && leaf) {
                 cls = 2 * sc + (t.mode == LF_MODE_SHW ? 1 : 0);
-                if (sc >= 4 && (d.bandreg >> (sc - 4) & 1u) && t.mode == LF_MODE_NW && lf_bandreg_eligible(t.q_len, t.t_len, sc)) cls = LF_CLS_BANDREG0 + sc - 4;
+                const bool br = sc >= 4 && (d.bandreg >> (sc - 4) & 1u) && t.mode == LF_MODE_NW && lf_bandreg_eligible(t.q_len, t.t_len, sc);
+                if (br) cls = LF_CLS_BANDREG0 + sc - 4;
                 scr = lf_k1_ckpt_bytes(t.t_len, lf_small_nw(sc));
                 my_swc = (unsigned long long)nwords * t.t_len;
+                /* 257 .. 512 rows off the diagonal or in prefix mode: a few long tasks, one thread each would be the tail of the step */
+                if (!br && !nopath && sc >= 6 && (d.groupk & 4u)) { cls = LF_CLS_GP16; scr = 0; }
+            } else if (nopath && (d.groupk & 1u) && nwords > 16u && nwords <= 256u) {
+                cls = nwords <= 32u ? LF_CLS_GD32 : nwords <= 64u ? LF_CLS_GD64 : nwords <= 128u ? LF_CLS_GD128 : LF_CLS_GD256;
+            } else if (!nopath && leaf && (d.groupk & 2u) && nwords > 16u && nwords <= 64u) {
+                cls = nwords <= 32u ? LF_CLS_GP32 : LF_CLS_GP64;
             } else {
                 cls = LF_CLS_LARGE;
                 my_maxq = t.q_len; my_maxt = t.t_len; my_maxp = lf_large_planes_bytes(t.q_len, t.t_len);
             }
-            slot = (t.flags & LF_F_NO_PATH) ? 0u : (t.q_len + t.t_len + 15u) >> 4;
+            if (cls >= LF_CLS_GP16 && cls <= LF_CLS_GP64) atomicMax(&cnt->gmax_t[cls - LF_CLS_GP16], t.t_len);   /* a few thousand tasks per chunk */
+            slot = nopath ? 0u : (t.q_len + t.t_len + 15u) >> 4;
             my_cells = (unsigned long long)t.q_len * t.t_len;
             my_wc = (unsigned long long)nwords * t.t_len;
         } else {
@@ -558,6 +579,13 @@ __device__ __forceinline__ int lf_converged_max(int v)
 #else
     return v;
 #endif
+}
+
+__device__ __forceinline__ int lf_warp_max(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const int t = __shfl_xor_sync(LF_FULL, v, o); v = t > v ? t : v; }
+    return v;
 }
 
 /* Advance the whole column by one target symbol (Myers 1999 / Hyyro 2003 recurrences on one long
@@ -895,14 +923,147 @@ __device__ __forceinline__ LfPassOut lf_wave_pass_t(const LfDev &d, const LfQVie
     return o;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* lf_gwave: the wavefront pass for a GROUP of LANES lanes (4, 8, 16 or 32), flags at compile time   */
+/* ------------------------------------------------------------------------------------------ */
+/* Same recurrences and lane skew as lf_wave_pass_t, rebuilt for instruction count: the pass variant (store planes /
+ * prefix-mode score / last column) is a template argument instead of a run-time test per word; every lane reads the
+ * target as a stream (16 symbols per funnel shift); hout travels as two bits (Ph, Mh of the lane's bottom row) per
+ * column; Eq is two LOP3s.  A warp holds 32 / LANES groups, each on its own (query, target): all 32 lanes call this
+ * together, the step count is the warp's maximum, ql == 0 marks an idle group.  One strip only: the query must fit
+ * LANES * WPL words.  Per word-column: 14 instructions of recurrence + 4 when the planes are stored + 2 for the
+ * prefix-mode score, and ~12 per lane and column of bookkeeping, amortised over WPL words.
+ * Planes layout (as lf_wave_pass_t with one strip): uint2 at planes[(column * nv + lane) * WPL + k]. */
+template <int LANES, int WPL, int FLAGS>
+__device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, uint2 *planes, int32_t *col)
+{
+    constexpr int CB = LF_WAVE_CB;
+    const int gl = (int)(threadIdx.x & (LANES - 1));
+    const int n = (ql + 31) >> 5;
+    const int nv = (n + WPL - 1) / WPL;
+    const bool valid = gl < nv;
+    const int w0 = gl * WPL;
+    const int wl = ql > 0 ? (ql - 1) >> 5 : -1;
+    const uint32_t bl = (uint32_t)(ql - 1) & 31u;
+    const int nblocks = (tl + CB - 1) / CB;
+    const int nsteps = lf_warp_max(ql > 0 ? nblocks + nv - 1 : 0);
+    uint32_t lo[WPL], hi[WPL], nn[WPL], Pv[WPL], Mv[WPL], wm[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; k++) {
+        lo[k] = 0; hi[k] = 0; nn[k] = 0xffffffffu;
+        if (valid && w0 + k < n) lf_q32(d, qv, (int64_t)(w0 + k) * 32, lo[k], hi[k], nn[k]);
+        Pv[k] = 0xffffffffu; Mv[k] = 0u;
+        wm[k] = ((FLAGS & LF_PASS_SHW) && w0 + k == wl) ? 1u << bl : 0u;   /* the bit of row ql-1 */
+    }
+    int score = ql, best = ql, bestc = -1;     /* followed by the lane that owns row ql-1 */
+    LfTStream ts;
+    ts.init(d.pac, ql > 0 ? tv.t0 : 0, ql > 0 ? tv.dir : 1);
+    uint32_t pay = 0;                          /* (Ph, Mh) of this lane's bottom row for the columns of its last block */
+    for (int step = 0; step < nsteps; step++) {
+        uint32_t in = __shfl_up_sync(LF_FULL, pay, 1, LANES);
+        const int cb = step - gl;
+        pay = 0;
+        if (valid && cb >= 0 && cb < nblocks) {
+            if (gl == 0) in = 0x5555u;         /* row 0 of a global alignment grows by one per column */
+            const int cbase = cb * CB;
+            const int ncol = tl - cbase < CB ? tl - cbase : CB;
+            uint32_t tb = ts.peek();
+            ts.advance(ncol);
+            uint2 *dst = (FLAGS & LF_PASS_STORE) ? planes + ((size_t)cbase * nv + gl) * WPL : nullptr;
+            int sh2 = 0;
+            for (int ci = 0; ci < ncol; ci++) {
+                const uint32_t shi = (uint32_t)((int32_t)tb >> 31), slo = (uint32_t)((int32_t)(tb << 1) >> 31);
+                tb <<= 2;
+                const uint32_t hp = in & 1u, hm = (in >> 1) & 1u;   /* hin = +1 / -1 */
+                in >>= 2;
+                uint32_t nEq[WPL], a[WPL], sum[WPL];
+#pragma unroll
+                for (int k = 0; k < WPL; k++) {
+                    nEq[k] = lf_neq(lo[k], hi[k], nn[k], slo, shi);
+                    a[k] = Pv[k] & ~nEq[k];
+                }
+                lf_add_chain_cin<WPL>(a, Pv, sum, hm);             /* hin = -1 enters as the carry-in */
+                uint32_t pPh = hp << 31, pMh = hm << 31;
+                uint32_t phs = 0, mhs = 0;
+#pragma unroll
+                for (int k = 0; k < WPL; k++) {
+                    const uint32_t Xh = (sum[k] ^ Pv[k]) | ~nEq[k] | (k == 0 ? hm : 0u);
+                    const uint32_t Ph = Mv[k] | ~(Xh | Pv[k]);
+                    const uint32_t Mh = Pv[k] & Xh;
+                    const uint32_t Xv = ~nEq[k] | Mv[k];
+                    if (FLAGS & LF_PASS_SHW) { phs |= Ph & wm[k]; mhs |= Mh & wm[k]; }
+                    const uint32_t Phs = __funnelshift_l(pPh, Ph, 1), Mhs = __funnelshift_l(pMh, Mh, 1);
+                    pPh = Ph; pMh = Mh;
+                    const uint32_t nPv = Mhs | ~(Xv | Phs);
+                    const uint32_t nMv = Phs & Xv;
+                    if (FLAGS & LF_PASS_STORE) {
+                        const uint32_t diagx = ~(nPv | Ph) & nEq[k];
+                        dst[k] = make_uint2(nPv | diagx, (~nPv & Ph) | diagx);
+                    }
+                    Pv[k] = nPv; Mv[k] = nMv;
+                }
+                if (FLAGS & LF_PASS_SHW) {
+                    score += (int)(phs != 0u) - (int)(mhs != 0u);
+                    if (score < best) { best = score; bestc = cbase + ci; }
+                }
+                pay |= ((pPh >> 31) | ((pMh >> 31) << 1)) << sh2;
+                sh2 += 2;
+                if (FLAGS & LF_PASS_STORE) dst += (size_t)nv * WPL;
+            }
+        }
+    }
+    /* last column: vertical deltas -> D(ql, tl), and D(x, tl) for every x if asked */
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < WPL; k++) {
+        const int w = w0 + k;
+        const uint32_t m = !valid ? 0u : w < wl ? 0xffffffffu : w == wl ? (0xffffffffu >> (31u - bl)) : 0u;
+        cnt += __popc(Pv[k] & m) - __popc(Mv[k] & m);
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < LANES; o <<= 1) { const int v = __shfl_up_sync(LF_FULL, incl, o, LANES); if (gl >= o) incl += v; }
+    if (FLAGS & LF_PASS_COL) {
+        if (gl == 0 && ql > 0) col[0] = tl;
+        if (valid) {
+            int v = tl + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < WPL; k++) {
+                const int w = w0 + k;
+                const int rows = ql - w * 32 < 32 ? ql - w * 32 : 32;
+                for (int b = 0; b < rows; b++) { v += (int)((Pv[k] >> b) & 1u) - (int)((Mv[k] >> b) & 1u); col[w * 32 + b + 1] = v; }
+            }
+        }
+    }
+    LfPassOut o;
+    o.ed = tl + __shfl_sync(LF_FULL, incl, LANES - 1, LANES);
+    const int owner = wl >= 0 ? wl / WPL : 0;
+    o.best = __shfl_sync(LF_FULL, best, owner, LANES);
+    o.bestc = __shfl_sync(LF_FULL, bestc, owner, LANES);
+    return o;
+}
+
+template <int WPL>
+__device__ __forceinline__ LfPassOut lf_wave_pass_w(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
+                                                    uint2 *planes, int8_t *hb, int32_t *col)
+{
+    if (((ql + 31) >> 5) > 32 * WPL) return lf_wave_pass_t<WPL>(d, qv, ql, tv, tl, flags, planes, hb, col);   /* several strips (queries above 8192 rows) */
+    switch (flags) {
+    case LF_PASS_STORE: return lf_gwave<32, WPL, LF_PASS_STORE>(d, qv, ql, tv, tl, planes, col);
+    case LF_PASS_SHW: return lf_gwave<32, WPL, LF_PASS_SHW>(d, qv, ql, tv, tl, planes, col);
+    case LF_PASS_COL: return lf_gwave<32, WPL, LF_PASS_COL>(d, qv, ql, tv, tl, planes, col);
+    default: return lf_gwave<32, WPL, 0>(d, qv, ql, tv, tl, planes, col);
+    }
+}
+
 __device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
                                                   uint2 *planes, int8_t *hb, int32_t *col)
 {
     switch (lf_wpl(ql)) {
-    case 1: return lf_wave_pass_t<1>(d, qv, ql, tv, tl, flags, planes, hb, col);
-    case 2: return lf_wave_pass_t<2>(d, qv, ql, tv, tl, flags, planes, hb, col);
-    case 4: return lf_wave_pass_t<4>(d, qv, ql, tv, tl, flags, planes, hb, col);
-    default: return lf_wave_pass_t<8>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    case 1: return lf_wave_pass_w<1>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    case 2: return lf_wave_pass_w<2>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    case 4: return lf_wave_pass_w<4>(d, qv, ql, tv, tl, flags, planes, hb, col);
+    default: return lf_wave_pass_w<8>(d, qv, ql, tv, tl, flags, planes, hb, col);
     }
 }
 
@@ -1085,6 +1246,100 @@ __global__ void __launch_bounds__(32) k_myers_large(LfDev d, const uint32_t *__r
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* k_myers_group: LANES lanes per task, 32 / LANES tasks per warp                                */
+/* ------------------------------------------------------------------------------------------ */
+/* Tasks too long for one thread (their latency would be the tail of the step) and too short for a whole warp (most
+ * lanes would idle): prefix-mode heads / tails and far-off-diagonal gaps of 257 .. 2048 rows with their path (PATH:
+ * leaves of edlib's size rule only, op planes in the group's scratch, canonical walk), and distance-only tasks of up to
+ * 8192 rows (!PATH: the junk heads / tails the chain operator only needs the clip test for, src/LordFAST.cpp:1840,
+ * :2175, and the forward half of the inversion test, :2037).  A warp takes 32 / LANES consecutive tasks of the sorted
+ * class list at a time (same length bucket), runs them in lockstep through lf_gwave and walks the paths together. */
+struct LfGroupRun { uint8_t *base; unsigned long long stride; uint32_t *queue; };
+
+/* Canonical traceback (Up > Left > Diagonal, edlib.cpp:950, :984, :1015) of every group of the warp over its stored
+ * planes.  The 32 columns left of the current position, current word-row, are fetched into the group's shared-memory
+ * tile by its lanes together; every lane of the group then walks the same path out of the tile, lane 0 packs the ops
+ * (16 per word) right-aligned below slot_hi.  Returns the number of ops. */
+template <int LANES>
+__device__ __forceinline__ uint32_t lf_group_walk(const uint2 *planes, int nvw, int ql, int j0, uint2 *tile, uint32_t *ops, uint64_t slot_hi, bool active)
+{
+    const int gl = (int)(threadIdx.x & (LANES - 1));
+    int i = active ? ql : 0, j = active ? j0 : 0;
+    uint32_t *wptr = ops + (slot_hi >> 4) - 1;
+    uint32_t cur = 0, nops = 0;
+    int sh = 30;
+#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { if (gl == 0) *wptr = cur; wptr--; cur = 0; sh = 30; } else sh -= 2; } while (0)
+    while (__any_sync(LF_FULL, i > 0 && j > 0)) {
+        const bool go = i > 0 && j > 0;
+        const int w = go ? (i - 1) >> 5 : 0;
+        const int clo = j > 32 ? j - 32 : 0;
+        if (go) for (int x = gl; x < j - clo; x += LANES) tile[x] = planes[(size_t)(clo + x) * nvw + w];
+        __syncwarp();
+        if (go) {
+            const int rowlo = w * 32;
+            while (i > rowlo && j > clo) {
+                const uint2 v = tile[j - 1 - clo];
+                const uint32_t b = (uint32_t)(i - 1) & 31u;
+                const uint32_t op = ((v.x >> b) & 1u) | (((v.y >> b) & 1u) << 1);
+                LF_EMIT(op);
+                i -= (op != 2u);
+                j -= (op != 1u);
+            }
+        }
+        __syncwarp();
+    }
+    while (i > 0) { LF_EMIT(1u); i--; }
+    while (j > 0) { LF_EMIT(2u); j--; }
+    if (gl == 0 && sh != 30) *wptr = cur;
+#undef LF_EMIT
+    return nops;
+}
+
+template <int LANES, int WPL, bool PATH>
+__global__ void __launch_bounds__(128) k_myers_group(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, LfGroupRun cfg)
+{
+    constexpr int G = 32 / LANES;
+    __shared__ uint2 s_tile[PATH ? 4 * G * 32 : 1];
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5), g = lane / LANES, gl = lane & (LANES - 1);
+    const unsigned long long slot = ((unsigned long long)blockIdx.x * 4ull + (unsigned)warp) * (unsigned)G + (unsigned)g;
+    uint2 *planes = PATH ? (uint2 *)(cfg.base + slot * cfg.stride) : nullptr;
+    uint2 *tile = s_tile + (PATH ? (warp * G + g) * 32 : 0);
+    for (;;) {
+        uint32_t k0 = 0;
+        if (lane == 0) k0 = atomicAdd(cfg.queue, (uint32_t)G);
+        k0 = __shfl_sync(LF_FULL, k0, 0);
+        if (k0 >= count) break;
+        const bool have = k0 + (uint32_t)g < count;
+        uint32_t ti = 0;
+        lf_align_task task;
+        task.read_id = 0; task.q_off = 0; task.q_len = 0; task.t_off = 0; task.t_len = 0; task.flags = 0; task.mode = 0; task.reserved = 0;
+        LfQView qv; LfTView tv;
+        qv.bit0 = 0; qv.dir = 1; qv.comp = 0; tv.t0 = 0; tv.dir = 1;
+        if (have) { ti = order[first + k0 + (uint32_t)g]; task = d.tasks[ti]; lf_task_views(d, task, qv, tv); }
+        const int q = (int)task.q_len, t = (int)task.t_len;
+        const bool shw = have && task.mode == LF_MODE_SHW;
+        LfPassOut o;
+        if (__any_sync(LF_FULL, shw)) o = lf_gwave<LANES, WPL, (PATH ? LF_PASS_STORE : 0) | LF_PASS_SHW>(d, qv, q, tv, t, planes, nullptr);
+        else o = lf_gwave<LANES, WPL, (PATH ? LF_PASS_STORE : 0)>(d, qv, q, tv, t, planes, nullptr);
+        const int ed = shw ? o.best : o.ed, end = shw ? o.bestc : t - 1;
+        const uint64_t slot_hi = have ? d.slot_end[ti] * 16ull : 0ull;
+        uint32_t nops = 0;
+        if (PATH) {
+            const bool want = have && !(task.flags & LF_F_NO_PATH);
+            const int nvw = (((q + 31) >> 5) + WPL - 1) / WPL * WPL;
+            __syncwarp();
+            nops = lf_group_walk<LANES>(planes, nvw, q, end + 1, tile, d.ops, slot_hi, want);
+        }
+        if (have && gl == 0) {
+            lf_align_result r;
+            r.edit_distance = ed; r.end_location = end; r.status = 0; r.ops_off = slot_hi - nops; r.ops_len = nops;
+            d.res[ti] = r;
+        }
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* k_ksw_extend: ksw_extend2 (lib/bwa/ksw.c:380-479), one thread per task                      */
 /* ------------------------------------------------------------------------------------------ */
 struct LfExtDev {
@@ -1112,13 +1367,6 @@ __global__ void k_extend_prep(LfExtDev d, uint32_t *scr_items)
         ok = (uint64_t)t.q_off + t.q_len <= L && (int64_t)t.t_off + (int64_t)t.t_len <= d.l_pac;
     }
     scr_items[i] = ok ? t.q_len + 1u + (t.q_len + 7u) / 8u + 1u : 0u; /* eh[] + one query code byte per column */
-}
-
-__device__ __forceinline__ int lf_warp_max(int v)
-{
-#pragma unroll
-    for (int o = 16; o; o >>= 1) { const int t = __shfl_xor_sync(LF_FULL, v, o); v = t > v ? t : v; }
-    return v;
 }
 
 /* One warp per task.  The reference's row loop is kept row by row (band re-trim, m==0 and z-drop exits
@@ -1818,7 +2066,9 @@ __global__ void __launch_bounds__(LF_EMIT_BLOCK) k_emit_slots(LfEmitDev d)
  * constant.  Head and tail tasks are the prefix-mode ones.  Triggered task indices are appended to `list`
  * (unordered; the host sorts the few thousand entries). */
 /* Round-1 tasks of a chunk of chains, written where k_align_prep expects them (alignChain_edlib's own calls: head SHW
- * :1827-1833, one NW per gap with query and target bases :1936-1941, tail SHW :2164-2168).  One warp per chain; the
+ * :1827-1833, one NW per gap with query and target bases :1936-1941, tail SHW :2164-2168).  Heads and tails longer than
+ * _pf_clipLen are asked for distance and end only: their path is used only if the clip test fails or the extension
+ * does not shorten them (:1840-1878, :2175-2209), and then round 3 computes it.  One warp per chain; the
  * host has only counted (task_base) and decided the chromosome-boundary guards.  59 MB of tasks per config-2 chunk
  * neither get built on host threads nor cross PCIe. */
 __global__ void __launch_bounds__(128) k_chain_tasks(const lf_chain *__restrict__ chains, const lf_seed *__restrict__ seeds, const uint64_t *__restrict__ read_off,
@@ -1838,7 +2088,7 @@ __global__ void __launch_bounds__(128) k_chain_tasks(const lf_chain *__restrict_
     if (g & 1u) {
         if (lane == 0) {
             const uint32_t a = s[0].qPos;
-            t.q_off = 0; t.q_len = a; t.t_off = s[0].tPos - (a + 20u); t.t_len = a + 20u; t.flags = (uint16_t)(strand | LF_F_REVERSE_BOTH); t.mode = LF_MODE_SHW;
+            t.q_off = 0; t.q_len = a; t.t_off = s[0].tPos - (a + 20u); t.t_len = a + 20u; t.flags = (uint16_t)(strand | LF_F_REVERSE_BOTH | (a > LF_CLIP_LEN ? LF_F_NO_PATH : 0)); t.mode = LF_MODE_SHW;
             out[k] = t;
         }
         k++;
@@ -1861,7 +2111,7 @@ __global__ void __launch_bounds__(128) k_chain_tasks(const lf_chain *__restrict_
         const lf_seed sl = s[n - 1];
         const uint32_t qs = sl.qPos + sl.len;
         const uint32_t b = (uint32_t)(read_off[ch.read_id + 1] - read_off[ch.read_id]) - qs;
-        t.q_off = qs; t.q_len = b; t.t_off = sl.tPos + sl.len; t.t_len = b + 20u; t.flags = (uint16_t)strand; t.mode = LF_MODE_SHW;
+        t.q_off = qs; t.q_len = b; t.t_off = sl.tPos + sl.len; t.t_len = b + 20u; t.flags = (uint16_t)(strand | (b > LF_CLIP_LEN ? LF_F_NO_PATH : 0)); t.mode = LF_MODE_SHW;
         out[k] = t;
     }
 }

@@ -34,9 +34,11 @@ struct DevState {
     lfb_event sub_ev[LF_NSUB] = {};
     lfb_event cls_ev[LF_NCLS][2] = {};   /* start / end of every class kernel (timeline hook) */
     bool cls_ran[LF_NCLS] = {};
+    uint32_t cls_count[LF_NCLS] = {};
     LfbBuf pac, bases, read_off, plo, phi, pnn;
     LfbBuf planes, gbytes, goff;   /* k_myers_band: plane regions per warp group */
     LfbBuf retry_scr;              /* warp slots of the k_myers_large instances that redo what k_myers_bandreg could not certify */
+    LfbBuf group_scr;              /* plane scratch of the k_myers_group path classes, one region per class */
     LfbBuf res_keep, ops_keep;   /* lf_chain.inl parks the round-1 results / op stream here while round 3 runs */
     LfbBuf tasks, res, ops, keys, keys2, idx, idx2, slot_words, scr_bytes, slot_end, scr_off, scratch, large_scr, counters, queue;
     LfbBuf etasks, eres, escr_items, escr_off, escr;
@@ -85,6 +87,15 @@ uint32_t bandreg_on()
     return e ? (uint32_t)strtoul(e, nullptr, 0) & 15u : (uint32_t)LF_BANDREG_DEFAULT;
 }
 
+/* k_myers_group classes in use (LF_GROUPK overrides): bit 0 distance-only tasks of 513 .. 8192 rows, bit 1 path tasks of
+ * 513 .. 2048 rows (leaves), bit 2 path tasks of 257 .. 512 rows that are off the diagonal or in prefix mode.  0 sends
+ * all of them where they went before: k_myers_large / k_myers_small<12|16>. */
+uint32_t groupk_on()
+{
+    const char *e = getenv("LF_GROUPK");
+    return e ? (uint32_t)strtoul(e, nullptr, 0) & 7u : 7u;
+}
+
 /* Global-mode tasks of q <= 128 in k_myers_bandreg (the band is the whole column: no slides, no certificate, nothing per
  * column in HBM) instead of k_myers_band (op planes of every column to HBM).  On since the recompute variant is chosen
  * per warp: 1.72 vs 1.77 ms (sv 0.0) and 2.57 vs 2.62 ms (sv 0.1) per config-2 step, and 3.9 GB less HBM traffic
@@ -109,6 +120,7 @@ LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
     v.scratch = d.scratch.as<uint8_t>();
     v.planes = d.planes.as<uint8_t>();
     v.bandreg = bandreg_on();
+    v.groupk = groupk_on();
     return v;
 }
 
@@ -143,6 +155,40 @@ void launch_band(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t
     const uint32_t grid = (count + 127) / 128;
     auto kern = k_myers_band<NB, BANDED, SHW>;
     LFB_LAUNCH(kern, grid, 128, smem, s, v, order, first, count, gbase, goff, retry_list, retry_count);
+}
+
+template <int LANES, int WPL, bool PATH>
+void launch_group(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, const LfGroupRun &run, unsigned blocks)
+{
+    auto kern = k_myers_group<LANES, WPL, PATH>;
+    LFB_LAUNCH(kern, blocks, 128, 0, s, v, order, first, count, run);
+}
+/* lanes per task, words per lane and path / distance-only of a k_myers_group class */
+struct GroupShape { int lanes, wpl; bool path; };
+GroupShape group_shape(int cls)
+{
+    switch (cls) {
+    case LF_CLS_GP16: return GroupShape{4, 4, true};
+    case LF_CLS_GP32: return GroupShape{8, 4, true};
+    case LF_CLS_GP64: return GroupShape{8, 8, true};
+    case LF_CLS_GD32: return GroupShape{8, 4, false};
+    case LF_CLS_GD64: return GroupShape{8, 8, false};
+    case LF_CLS_GD128: return GroupShape{16, 8, false};
+    default: return GroupShape{32, 8, false};
+    }
+}
+void launch_group_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, const LfGroupRun &run, unsigned blocks)
+{
+    switch (cls) {
+    case LF_CLS_GP16: launch_group<4, 4, true>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GP32: launch_group<8, 4, true>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GP64: launch_group<8, 8, true>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GD32: launch_group<8, 4, false>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GD64: launch_group<8, 8, false>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GD128: launch_group<16, 8, false>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GD256: launch_group<32, 8, false>(v, order, first, count, s, run, blocks); break;
+    default: break;
+    }
 }
 
 #ifndef LF_BAND_MASK_DEFAULT
@@ -327,6 +373,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][1], d.sub[0]);
 #endif
     }
+    for (int c = 0; c < LF_NCLS; c++) d.cls_count[c] = ht->cnt.hist[c];
     for (int c = 0; c < LF_NCLS; c++) d.cls_ran[c] = c == LF_CLS_BAD ? false : c == LF_CLS_LARGE ? nlarge != 0 : ht->cnt.hist[c] != 0;
     /* thread-per-task classes, the ones with the longest tasks first, spread over the other streams */
     {
@@ -338,13 +385,42 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         const bool serial = getenv("LF_SERIAL") != nullptr;
         int nstreams = getenv("LF_STREAMS") ? atoi(getenv("LF_STREAMS")) : LF_NSUB - 1;   /* class kernels in flight at once */
         if (nstreams < 1 || nstreams > LF_NSUB - 1) nstreams = LF_NSUB - 1;
+        /* k_myers_group classes first (their tasks are the longest after the large ones), longest rows first */
+        for (int cls = LF_CLS_GD256; cls >= LF_CLS_GP16; cls--) seq[nseq++] = cls;
         if (!getenv("LF_ORDER_BAND_FIRST")) {   /* the full-width classes (few, long tasks: the tail of the step) before the sliding-band ones */
             for (int cls = LF_CLS_LARGE - 1; cls >= 8; cls--) seq[nseq++] = cls;
-            for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
+            for (int cls = LF_CLS_BANDREG0 + 3; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
             for (int cls = 7; cls >= 0; cls--) seq[nseq++] = cls;
         } else {
-            for (int cls = LF_NCLS - 1; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
+            for (int cls = LF_CLS_BANDREG0 + 3; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
             for (int cls = LF_CLS_LARGE - 1; cls >= 0; cls--) seq[nseq++] = cls;
+        }
+        /* plane scratch of the group path classes: one slot per group of lanes of the persistent grid */
+        unsigned gblocks[LF_NCLS] = {};
+        LfGroupRun grun[LF_NCLS] = {};
+        {
+            size_t off = 0, offs[LF_NCLS] = {};
+            for (int cls = LF_CLS_GP16; cls <= LF_CLS_GD256; cls++) {
+                const uint32_t count = ht->cnt.hist[cls];
+                if (!count) continue;
+                const GroupShape gs = group_shape(cls);
+                const unsigned per_block = 4u * (32u / (unsigned)gs.lanes);   /* tasks a block works on at a time */
+                unsigned blocks = (count + per_block - 1) / per_block;
+                if (blocks > 148u * 4u) blocks = 148u * 4u;
+                size_t stride = 0;
+                if (gs.path) {
+                    stride = align_up((size_t)ht->cnt.gmax_t[cls - LF_CLS_GP16] * (size_t)(gs.lanes * gs.wpl) * 8 + 256, 256);
+                    const size_t budget = (size_t)3 << 30;
+                    while (blocks > 1 && (size_t)blocks * per_block * stride > budget) blocks = (blocks + 1) / 2;
+                }
+                gblocks[cls] = blocks; grun[cls].stride = stride; offs[cls] = off;
+                off += (size_t)blocks * per_block * stride;
+            }
+            if (off) LF_TRY(d.group_scr.reserve(off + 256));
+            for (int cls = LF_CLS_GP16; cls <= LF_CLS_GD256; cls++) {
+                grun[cls].base = d.group_scr.as<uint8_t>() + offs[cls];
+                grun[cls].queue = d.queue.as<uint32_t>() + 40 + (cls - LF_CLS_GP16);
+            }
         }
         for (int si = 0; si < nseq; si++) {
             const int cls = seq[si];
@@ -354,9 +430,10 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
-            launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, cls < LF_CLS_LARGE ? gc.gbase[cls] : 0u, d.goff.as<unsigned long long>(), st,
+            if (cls >= LF_CLS_GP16) launch_group_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, st, grun[cls], gblocks[cls]);
+            else launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, cls < LF_CLS_LARGE ? gc.gbase[cls] : 0u, d.goff.as<unsigned long long>(), st,
                                d.idx.as<uint32_t>() /* input of the sort, free by now */, d.queue.as<uint32_t>() + 1 + cls, bmask);
-            if (cls >= LF_CLS_BANDREG0) {   /* the uncertified few: warp per task, on the same stream */
+            if (cls >= LF_CLS_BANDREG0 && cls < LF_CLS_GP16) {   /* the uncertified few: warp per task, on the same stream */
                 const int bi = cls - LF_CLS_BANDREG0;
                 LfLargeCfg rcfg = large_cfg(512, 640, (size_t)lf_large_planes_bytes(512, 640));   /* eligible tasks: q <= 512, |q-t| <= 40 */
                 const size_t rslots = 148;
@@ -447,7 +524,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
     if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
     for (DevState &d : ctx->devs) {
         set_dev(d);
-        LfbBuf *bufs[] = { &d.planes, &d.gbytes, &d.goff, &d.res_keep, &d.ops_keep, &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
+        LfbBuf *bufs[] = { &d.retry_scr, &d.group_scr, &d.planes, &d.gbytes, &d.goff, &d.res_keep, &d.ops_keep, &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
                            &d.slot_words, &d.scr_bytes, &d.slot_end, &d.scr_off, &d.scratch, &d.large_scr, &d.counters, &d.queue,
                            &d.etasks, &d.eres, &d.escr_items, &d.escr_off, &d.escr };
         for (LfbBuf *b : bufs) b->release();
@@ -729,6 +806,13 @@ int lf_gpu_class_timeline(lf_gpu_ctx *ctx, float *start_ms, float *end_ms, int n
         cudaEventElapsedTime(&end_ms[c], d.ev[2], d.cls_ev[c][1]);
     }
 #endif
+    return LF_OK;
+}
+
+int lf_gpu_class_counts(lf_gpu_ctx *ctx, uint32_t *counts, int n)
+{
+    if (!ctx || !counts || n < LF_NCLS) return LF_ERR_BAD_ARG;
+    for (int c = 0; c < n; c++) counts[c] = c < LF_NCLS ? ctx->devs[0].cls_count[c] : 0u;
     return LF_OK;
 }
 

@@ -128,3 +128,39 @@ CRAFTED_REF = (40_000, 12)  # sim.make_reference(length, seed) of the crafted ch
 
 def load_crafted():
     return json.load(open(os.path.join(GOLDEN, "chains_crafted.json")))
+
+
+def group_class_batch(seed=21, big=True):
+    """Tasks for every k_myers_group class (lordfast_b200/csrc/lf_kernels.cuh): path tasks of 257 .. 2048 rows off the
+    diagonal, in prefix mode and near the diagonal, distance-only tasks of 513 .. 8192+ rows, lengths on both sides of
+    every class boundary, NW and SHW mixed inside a warp's bundle, an SHW task whose best prefix is the empty one."""
+    rng = np.random.default_rng(seed)
+    ref = sim.make_reference(60000, 8)
+    reads, tasks = [], []
+    junk = lambda m: sim.ACGT[rng.integers(0, 4, size=m, dtype=np.uint8)]
+    qlens = [257, 300, 384, 385, 512, 513, 700, 1000, 1024, 1025, 1500, 2047, 2048]
+    for k, ql in enumerate(qlens):
+        s = int(rng.integers(100, 30000))
+        similar = sim.mutate_pair(ref[s:s + int(ql / 1.05)], 0.15, rng)[:ql]
+        if len(similar) < ql:
+            similar = np.concatenate([similar, junk(ql - len(similar))])
+        for q, to, tl, flags, mode in (
+                (similar, s, int(ql / 1.05), 0, 0),                           # near the diagonal
+                (similar, s, int(ql / 1.05) + 20, 0, 1),                      # prefix mode, similar
+                (junk(ql), int(rng.integers(0, 30000)), ql + 20, 2, 1),       # junk head: prefix mode, both reversed
+                (junk(ql), int(rng.integers(0, 30000)), max(2, ql // 3), 1, 0),   # off the diagonal, reverse strand
+                (junk(ql), int(rng.integers(0, 30000)), ql + 20, 8, 1),       # distance only
+                (similar, s, int(ql / 1.05), 8 | 4, 0)):                      # distance only, global, RC query
+            if not O.is_leaf(len(q), tl) and not (flags & 8):
+                continue
+            reads.append(q)
+            tasks.append((len(reads) - 1, 0, len(q), to, tl, flags, mode, 0))
+    if big:
+        for ql, tl, flags, mode in ((2049, 2069, 8, 1), (4096, 300, 8, 0), (4097, 200, 8 | 2, 1), (8192, 150, 8, 1), (8193, 150, 8, 1), (3000, 100, 0, 0), (5000, 60, 0, 1)):
+            reads.append(junk(ql))
+            tasks.append((len(reads) - 1, 0, ql, int(rng.integers(0, 30000)), tl, flags, mode, 0))
+    # the empty prefix is the best one: an all-T query against an all-A stretch cannot exist in a random reference, so plant it
+    ref[50000:50400] = ord("A")
+    reads.append(np.full(600, ord("T"), dtype=np.uint8))
+    tasks.append((len(reads) - 1, 0, 600, 50000, 400, 0, 1, 0))
+    return ref, reads, np.array(tasks, dtype=api.ALIGN_TASK)

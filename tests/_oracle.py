@@ -79,6 +79,11 @@ def ref():
     return _ref
 
 
+def is_leaf(q: int, t: int) -> bool:
+    """edlib's choice of full traceback over Hirschberg (lib/edlib/edlib.cpp:1117-1119)"""
+    return 20 * ((q + 63) // 64) * t + 8 * t < (1 << 20) or t < 2
+
+
 def oracle_align(q: bytes, t: bytes, mode: int, want_path=True):
     out = AlignOut()
     ops = C.create_string_buffer(len(q) + len(t) + 1)

@@ -123,14 +123,15 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 
-template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int = 32)
-{ uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, src & 31); T r; memcpy(&r, &x, sizeof(T)); return r; }
-template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32)
-{ int l = emu::lane_id(); int src = l - (int)d; uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, src < 0 ? l : src); T r; memcpy(&r, &x, sizeof(T)); return r; }
-template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32)
-{ int l = emu::lane_id(); int src = l + (int)d; uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, src > 31 ? l : src); T r; memcpy(&r, &x, sizeof(T)); return r; }
-template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32)
-{ int l = emu::lane_id(); uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, l ^ m); T r; memcpy(&r, &x, sizeof(T)); return r; }
+/* width w (a power of two): the exchange stays inside the lane's segment of w lanes */
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int w = 32)
+{ int l = emu::lane_id(); int s = (l & ~(w - 1)) | (src & (w - 1)); uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, s); T r; memcpy(&r, &x, sizeof(T)); return r; }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int w = 32)
+{ int l = emu::lane_id(); int lw = l & (w - 1); int src = lw >= (int)d ? l - (int)d : l; uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, src); T r; memcpy(&r, &x, sizeof(T)); return r; }
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int w = 32)
+{ int l = emu::lane_id(); int lw = l & (w - 1); int src = lw + (int)d < w ? l + (int)d : l; uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, src); T r; memcpy(&r, &x, sizeof(T)); return r; }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int w = 32)
+{ int l = emu::lane_id(); int src = l ^ m; if ((src & ~(w - 1)) != (l & ~(w - 1))) src = l; uint64_t x = 0; memcpy(&x, &v, sizeof(T)); x = emu::warp_exchange(x, src); T r; memcpy(&r, &x, sizeof(T)); return r; }
 static inline unsigned __ballot_sync(unsigned, int p) { return emu::warp_ballot(p); }
 static inline int __any_sync(unsigned, int p) { return emu::warp_ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) { return emu::warp_ballot(!p) == 0; }

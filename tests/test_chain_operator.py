@@ -71,6 +71,51 @@ def _crafted(lib_path):
     g.close()
 
 
+def _long_ends(lib_path, n_reads=10, read_len=4000):
+    """Heads / tails longer than _pf_clipLen that are NOT junk: round 1 only measures them (distance), the clip test
+    fails (similarity >= 0.75) or the extension keeps all of them, and round 3 has to deliver the prefix-mode path
+    (src/LordFAST.cpp:1869-1886, :2196-2217).  Made by dropping the outer anchors of simulated chains."""
+    w = sim.make_workload(150_000, n_reads, read_len, 0.05, 0.15, seed=33, sv_frac=0.3, sv_kinds=("junk_head", "junk_tail"))
+    seeds, chains = api.workload_chains(w)
+    keep, new_chains = [], []
+    for i in range(w.n_reads):
+        lo, hi = int(w.seed_off[i]), int(w.seed_off[i + 1])
+        cut = (7, 7) if i % 3 == 0 else (9, 0) if i % 3 == 1 else (0, 12)
+        if hi - lo - cut[0] - cut[1] < 2:
+            cut = (0, 0)
+        new_chains.append((len(keep), hi - lo - cut[0] - cut[1], i, int(w.is_rev[i]), 0))
+        keep.extend(range(lo + cut[0], hi - cut[1]))
+    seeds = seeds[np.array(keep)]
+    chains = np.array(new_chains, dtype=api.CHAIN)
+    g = api.LfGpu(w.pac, len(w.ref), lib_path=lib_path)
+    recs, text, st = g.align_chains(w.reads, w.read_off.astype(np.uint64), w.contig_off, w.contig_len, seeds, chains)
+    got = api.records_to_dicts(recs, text)
+    idx = O.RefIndex(w.ref.tobytes())
+    exp, long_kept = [], 0
+    for i, c in enumerate(chains):
+        sd = [(int(x["tPos"]), int(x["qPos"]), int(x["len"])) for x in seeds[int(c["seed_off"]):int(c["seed_off"]) + int(c["n_seeds"])]]
+        a, _ = O.oracle_align_chain(idx, sd, w.oriented(i).tobytes(), int(w.is_rev[i]))
+        for r in a:
+            d = dict(chain=i); d.update(r); exp.append(d)
+        long_kept += sum(1 for r in a if sd[0][1] > 500 and r["qStart"] == 0)
+    assert got == exp
+    assert long_kept > 0 and st.round3_tasks > 0   # a long head was kept whole: its path came from round 3
+    g.close()
+
+
+def test_emu_chain_operator_long_ends(monkeypatch):
+    _long_ends(build_emu())
+    monkeypatch.setenv("LF_CHAIN_HOST_EMIT", "1")
+    _long_ends(build_emu())
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_long_ends(monkeypatch):
+    _long_ends(None, 60, 8000)
+    monkeypatch.setenv("LF_CHAIN_NO_SPEC", "1")
+    _long_ends(None, 60, 8000)
+
+
 def test_oracle_crafted_chains():
     ref = sim.make_reference(*CRAFTED_REF)
     idx = O.RefIndex(ref.tobytes())

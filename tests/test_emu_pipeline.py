@@ -3,7 +3,7 @@ This is a debugging aid for a container without a GPU; the parity tests proper a
 import numpy as np
 import pytest
 
-from _common import CODE, build_emu, check_align, load_ksw, load_pairs, pairs_as_batch
+from _common import CODE, build_emu, check_align, group_class_batch, load_ksw, load_pairs, pairs_as_batch
 import _oracle as O
 from lordfast_b200 import api, sim
 from lordfast_b200.chain_tasks import workload_tasks
@@ -124,6 +124,22 @@ def test_emu_large_and_hirschberg_tasks(emu_lib):
     tasks = np.array(tasks, dtype=api.ALIGN_TASK)
     bad, _, _ = check_align(g, reads, ref, tasks)
     assert not bad, bad
+    g.close()
+
+
+@pytest.mark.parametrize("groupk", ["7", "0", "3"])
+def test_emu_group_classes(emu_lib, monkeypatch, groupk):
+    """k_myers_group (LANES lanes per task) against the oracle; LF_GROUPK=0 routes the same tasks to the older kernels."""
+    monkeypatch.setenv("LF_GROUPK", groupk)
+    ref, reads, tasks = group_class_batch(big=groupk == "7")
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
+    bad, res, _ = check_align(g, reads, ref, tasks)
+    assert not bad, bad
+    cc = g.class_counts()
+    if groupk == "7":
+        assert all(cc.get(k, 0) > 0 for k in ("group_path16", "group_path32", "group_path64", "group_dist32", "group_dist64", "group_dist128", "group_dist256", "large")), cc
+    if groupk == "0":
+        assert not any(k.startswith("group") for k in cc), cc
     g.close()
 
 

@@ -169,7 +169,7 @@ def test_gpu_full_size_properties():
     paths, exact agreement with the oracle on a sample, run-to-run identity, and independence from
     how the chunk is split into batches."""
     w = sim.make_workload(4_600_000, 2000, 10_000, 0.12, 0.15, seed=100, sv_frac=0.10)
-    tasks, chain, kind = workload_tasks(w)
+    tasks, chain, kind = workload_tasks(w, long_ends_nopath=False)   # every task with its path, the junk heads / tails too
     g = api.LfGpu(w.pac, len(w.ref))
     ro = w.read_off.astype(np.uint64)
     res, ops = g.align_batch(w.reads, ro, tasks)
@@ -197,6 +197,26 @@ def test_gpu_full_size_properties():
         rr, oo, k = (ra, oa, i) if i < half else (rb, ob, i - half)
         assert np.array_equal(api.decode_ops(oo, int(rr[k]["ops_off"]), int(rr[k]["ops_len"])),
                               api.decode_ops(ops, int(res[i]["ops_off"]), int(res[i]["ops_len"])))
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("groupk", ["7", "0"])
+def test_gpu_group_classes(groupk, monkeypatch):
+    """k_myers_group (LANES lanes per task: path tasks of 257 .. 2048 rows, distance-only tasks up to 8192 rows) on both
+    sides of every class boundary, NW / SHW mixed in a warp's bundle; LF_GROUPK=0 sends the same tasks to the older
+    kernels.  Bit-exact against the oracle both ways, and the classes really ran."""
+    from _common import group_class_batch
+    monkeypatch.setenv("LF_GROUPK", groupk)
+    ref, reads, tasks = group_class_batch()
+    g = api.LfGpu(sim.pack_pac(ref), len(ref))
+    bad, _, _ = check_align(g, reads, ref, tasks)
+    assert not bad, bad[:10]
+    cc = g.class_counts()
+    if groupk == "7":
+        assert all(cc.get(k, 0) > 0 for k in ("group_path16", "group_path32", "group_path64", "group_dist32", "group_dist64", "group_dist128", "group_dist256", "large")), cc
+    else:
+        assert not any(k.startswith("group") for k in cc), cc
     g.close()
 
 
