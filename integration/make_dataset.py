@@ -15,17 +15,7 @@ from lordfast_b200 import sim  # noqa: E402
 
 
 def make_ref(ref_len, seed, dups, n_contigs=1):
-    ref = sim.make_reference(ref_len, seed)
-    if dups:
-        rng = np.random.default_rng(seed + 31)
-        for _ in range(dups):  # copy a 20-50 kbp segment elsewhere at 2-5 % divergence (substitutions)
-            L = int(rng.integers(20_000, 50_000)) if ref_len > 400_000 else int(rng.integers(4_000, 9_000))
-            a, b = int(rng.integers(0, ref_len - L)), int(rng.integers(0, ref_len - L))
-            seg = ref[a:a + L].copy()
-            hit = rng.random(L) < rng.uniform(0.02, 0.05)
-            seg[hit] = sim.ACGT[(np.searchsorted(sim.ACGT, seg[hit]) + rng.integers(1, 4, size=int(hit.sum()))) % 4]
-            ref[b:b + L] = seg
-    return ref
+    return sim.make_reference_dups(ref_len, seed, dups)
 
 
 def write(outdir, ref, w, n_contigs=1):

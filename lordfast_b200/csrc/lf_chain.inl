@@ -25,7 +25,8 @@
 /* Result text is ~1.2 bytes per read base (240 MB per 20k x 10 kbp chunk); mapping that much fresh memory costs more
  * in page faults than filling it, so freed result buffers are parked here and reused by the next call. */
 struct LfBufPool {
-    bool pinned = false;   /* pinned host memory (D2H target of the GPU emit) or plain malloc */
+    const bool pinned;     /* pinned host memory (D2H target of the GPU emit) or plain malloc */
+    explicit LfBufPool(bool pin) : pinned(pin) { }
     void *raw_alloc(size_t n) { return pinned ? lfb_host_alloc(n) : malloc(n); }
     void raw_free(void *p) { if (pinned) lfb_host_free(p); else free(p); }
     std::mutex mu;
@@ -50,15 +51,23 @@ struct LfBufPool {
         items.push_back(Item{p, cap});
     }
 };
-static LfBufPool g_result_pool;
-static LfBufPool g_result_pool_pinned;
+static LfBufPool g_result_pool(false);
+static LfBufPool g_result_pool_pinned(true);
 
 struct lf_chain_results {
     lf_sam_record *recs = nullptr; size_t n_recs = 0, recs_cap = 0;
     char *text = nullptr; size_t text_bytes = 0, text_cap = 0;
     lf_chain_stats stats;
     bool pinned = false;
-    ~lf_chain_results() { LfBufPool &P = pinned ? g_result_pool_pinned : g_result_pool; P.put(recs, recs_cap); P.put(text, text_cap); }
+    bool text_borrowed = false;   /* a lane's result: the text sits in the arena of the call that runs the lanes */
+    ~lf_chain_results() { LfBufPool &P = pinned ? g_result_pool_pinned : g_result_pool; P.put(recs, recs_cap); if (!text_borrowed) P.put(text, text_cap); }
+};
+
+/* What a lane of a pipelined lf_gpu_align_chains call gets from the call: its slice of the one result text buffer
+ * (records carry offsets into that buffer) and its share of the host threads. */
+struct LaneIO {
+    char *arena = nullptr; size_t off = 0, cap = 0;
+    unsigned nthreads = 1;
 };
 
 namespace {
@@ -466,17 +475,19 @@ int emit_write(EmitSet &es, LfEmitDev &E, char *text_dst, uint64_t out_base)
 struct EarlyEmit {
     std::thread th;
     char *text = nullptr; size_t cap = 0;
+    bool borrowed = false;
     int rc = 0;
     void join() { if (th.joinable()) th.join(); }
-    ~EarlyEmit() { join(); if (text) g_result_pool_pinned.put(text, cap); }
+    ~EarlyEmit() { join(); if (text && !borrowed) g_result_pool_pinned.put(text, cap); }
 };
 
 } // namespace
 
 extern "C" {
 
-int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs *contigs, const lf_seed *seeds,
-                        const lf_chain *chains, size_t n_chains, const uint8_t *pac_host, lf_chain_results **out)
+/* alignChain_edlib for one batch of chains on one context (the whole call, or one lane of it) */
+static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs *contigs, const lf_seed *seeds,
+                            const lf_chain *chains, size_t n_chains, const uint8_t *pac_host, lf_chain_results **out, const LaneIO *io)
 {
     if (!ctx || !reads || !contigs || !seeds || (!chains && n_chains) || !pac_host || !out || contigs->n < 1) return LF_ERR_BAD_ARG;
     *out = nullptr;
@@ -491,6 +502,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         if (e && atoi(e) > 0) nthreads = (unsigned)atoi(e);
         else if (lw && atoi(lw) > 1) nthreads = nthreads / (unsigned)atoi(lw);
     }
+    if (io) nthreads = io->nthreads;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
     int rc;
@@ -499,7 +511,6 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     /* CIGAR / MD assembly runs on the GPU (k_emit_slots) when the context drives one device; a context over
      * several devices assembles on host threads from the 2-bit op stream (LF_CHAIN_HOST_EMIT=1 forces that). */
     const bool gpu_emit = ctx->devs.size() == 1 && !getenv("LF_CHAIN_HOST_EMIT");
-    g_result_pool_pinned.pinned = true;
     LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
     const double tt1 = now_ms();
     if (gpu_emit) {
@@ -530,7 +541,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     std::vector<uint32_t> ntask(n_chains, 0);
     std::vector<uint8_t> hascand(n_chains, 0);   /* the chain holds a task whose lengths qualify for a clip / split trigger */
     std::vector<uint64_t> nslot(n_chains, 0); /* op-slot words of the chain's round-1 tasks */
-    bool bad_rid = false;
+    std::atomic<bool> bad_rid(false);   /* a chain the reference's chaining could not have produced (or a contig lookup that failed) */
     const double tt2 = now_ms();
     /* pass A: boundaries, guards and task counts per chain */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
@@ -542,6 +553,14 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             ChainPlan &p = plan[c];
             int rid = pos2rid(contigs, ((int64_t)s[0].tPos + (int64_t)s[n - 1].tPos) >> 1, ctx->l_pac); /* BWT.cpp:653-660 */
             if (rid < 0) { bad_rid = true; continue; }
+            {   /* seeds inside the read and the reference, in order, without overlap (Chain.cpp:258-266 guarantees it) */
+                bool okc = true;
+                for (uint32_t i = 0; i < n && okc; i++) {
+                    okc = s[i].len >= 1 && (uint64_t)s[i].qPos + s[i].len <= readLen && (int64_t)s[i].tPos + s[i].len <= ctx->l_pac;
+                    if (okc && i + 1 < n) okc = s[i + 1].qPos >= s[i].qPos + s[i].len && s[i + 1].tPos >= s[i].tPos + s[i].len;
+                }
+                if (!okc) { bad_rid = true; continue; }
+            }
             p.chrBeg = (uint32_t)contigs->offset[rid];
             p.chrEnd = (uint32_t)(contigs->offset[rid] + contigs->len[rid] - 1);
             uint32_t cnt = 0;
@@ -877,9 +896,10 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
             /* one text buffer for both lists: the late list is appended, its size estimated from this one */
             const size_t bytes = es.ncig + es.nmd;
             const size_t est_late = dirty_slots ? (size_t)((double)bytes * ((double)dirty_slots / (double)(clean_slots ? clean_slots : 1)) * 1.5) + (1u << 16) : 0;
-            early.text = (char *)g_result_pool_pinned.get(bytes + est_late + 1, &early.cap);
+            if (io && bytes + est_late + 1 <= io->cap) { early.text = io->arena + io->off; early.cap = io->cap; early.borrowed = true; }
+            else early.text = (char *)g_result_pool_pinned.get(bytes + est_late + 1, &early.cap);
             if (!early.text) { early.rc = LF_ERR_NOMEM; return; }
-            if ((early.rc = emit_write(es, E, early.text, 0)) != 0) return;
+            if ((early.rc = emit_write(es, E, early.text, early.borrowed ? io->off : 0)) != 0) return;
             if (lfb_sync(es.st)) early.rc = LF_ERR_CUDA;
         };
 #ifndef LF_EMU
@@ -1035,18 +1055,23 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         if (early.rc != 0) { delete R; return fail(ctx, early.rc, "early emit"); }
         const size_t bytes0 = es0.n ? es0.ncig + es0.nmd : 0, bytes1 = es1.ncig + es1.nmd;
         R->pinned = true;
-        R->text = early.text; R->text_cap = early.cap; early.text = nullptr;
+        R->text = early.text; R->text_cap = early.cap; R->text_borrowed = early.borrowed; early.text = nullptr;
+        if (!R->text && io && bytes1 + 1 <= io->cap) { R->text = io->arena + io->off; R->text_cap = io->cap; R->text_borrowed = true; }   /* no early list */
         if (!R->text || bytes0 + bytes1 + 1 > R->text_cap) {   /* the estimate fell short (or there was no early list): move to a bigger buffer */
             size_t cap = 0;
             char *nt = (char *)g_result_pool_pinned.get(bytes0 + bytes1 + 1, &cap);
             if (!nt) { delete R; return LF_ERR_NOMEM; }
             if (R->text) {
                 parallel_for(bytes0, nthreads, [&](unsigned, size_t lo, size_t hi) { memcpy(nt + lo, R->text + lo, hi - lo); }, 1 << 20);
-                g_result_pool_pinned.put(R->text, R->text_cap);
+                if (!R->text_borrowed) g_result_pool_pinned.put(R->text, R->text_cap);
+                else {   /* the early records point into the arena: re-base them to the lane's own buffer */
+                    lf_sam_record *a = (lf_sam_record *)es0.h_recs.p;
+                    for (size_t k = 0; k < (es0.n ? es0.nrec : 0); k++) { a[k].cigar_off -= io->off; a[k].md_off -= io->off; }
+                }
             }
-            R->text = nt; R->text_cap = cap;
+            R->text = nt; R->text_cap = cap; R->text_borrowed = false;
         }
-        if (n_dirty) { LF_G(emit_write(es1, E1, R->text + bytes0, bytes0)); LF_G(lfb_sync(st)); }
+        if (n_dirty) { LF_G(emit_write(es1, E1, R->text + bytes0, (R->text_borrowed ? io->off : 0) + bytes0)); LF_G(lfb_sync(st)); }
         LF_G(lfb_last_error());
 #undef LF_G
         /* records of the two lists, merged back into chain order */
@@ -1249,6 +1274,185 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] tasks %.2f r1 %.2f r23 %.2f emit %.2f gather %.2f (threads %u, recs %zu, text bound %zu MB)\n",
                                           tm1 - tm0, tm2 - tm1, tm3 - tm2, tm3b - tm3, tm4 - tm3b, nthreads, R->n_recs, R->text_bytes >> 20);
     R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm3b - tm3); R->stats.ms_merge = (float)(tm4 - tm3b);
+    *out = R;
+    return LF_OK;
+}
+
+/* One lane per sub-batch: a single-device child context with its own streams, buffers and host thread.  Lane j lives on
+ * device j % n_devices and borrows that device's copy of the reference. */
+static lf_gpu_ctx *lane_ctx(lf_gpu_ctx *ctx, size_t j)
+{
+    while (ctx->lanes.size() <= j) {
+        DevState &pd = ctx->devs[ctx->lanes.size() % ctx->devs.size()];
+        lf_gpu_ctx *c = new lf_gpu_ctx();
+        c->l_pac = ctx->l_pac;
+        c->devs.resize(1);
+        DevState &d = c->devs[0];
+        d.dev = pd.dev;
+        d.pac.p = pd.pac.p; d.pac.cap = pd.pac.cap; d.pac_borrowed = true;
+        if (set_dev(d) || init_dev_streams(d) || !(d.pinned = lfb_host_alloc(sizeof(HostTotals)))) { lf_gpu_destroy(c); return nullptr; }
+        ctx->lanes.push_back(c);
+    }
+    return ctx->lanes[j];
+}
+
+/* The call the reference side makes.  A chunk is cut into sub-batches of consecutive chains that run as a software
+ * pipeline, each on a lane: the reads of the sub-batches are copied to the device(s) one after the other on one
+ * stream, so that the first lane aligns while the others' reads are still in flight, and the CIGAR / MD text of a
+ * lane goes back over PCIe (k_emit_slots writes it straight to pinned memory) while the next lanes compute.  With
+ * several devices in the context the lanes are spread over them: reads sharded by contiguous ranges, every device
+ * holding the whole reference, records merged in chain order -- the data-parallel loop of
+ * src/LordFAST.cpp:295-316.  LF_CHAIN_LANES overrides the number of lanes (1: no pipeline). */
+int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs *contigs, const lf_seed *seeds,
+                        const lf_chain *chains, size_t n_chains, const uint8_t *pac_host, lf_chain_results **out)
+{
+    if (!ctx || !reads || !reads->offsets || !contigs || !seeds || (!chains && n_chains) || !pac_host || !out || contigs->n < 1) return LF_ERR_BAD_ARG;
+    const size_t ndev = ctx->devs.size();
+    size_t K = ndev == 1 ? 4 : 2 * ndev;
+    if (const char *e = getenv("LF_CHAIN_LANES")) { if (atoi(e) > 0) K = (size_t)atoi(e); }
+    else { const size_t by_size = n_chains / 1500; if (K > by_size) K = by_size > ndev ? by_size : ndev; }   /* small chunks: the fixed cost of a lane outweighs the overlap */
+    if (K > 64) K = 64;
+    if (K > n_chains) K = n_chains ? n_chains : 1;
+    if (K < 1) K = 1;
+    if (ndev == 1 && K == 1) return align_chains_one(ctx, reads, contigs, seeds, chains, n_chains, pac_host, out, nullptr);
+    *out = nullptr;
+    for (size_t c = 0; c < n_chains; c++) if (chains[c].read_id >= reads->n_reads || chains[c].n_seeds < 2) return LF_ERR_BAD_ARG;
+    /* ---- sub-batches: consecutive chains, balanced by seeds; the reads each of them touches ---- */
+    struct Sub { size_t c0, c1, smin, smax; uint32_t rmin, rmax; size_t est; std::vector<lf_chain> ch; lf_reads rd; lf_chain_results *R = nullptr; int rc = 0; LaneIO io; };
+    std::vector<Sub> sub(K);
+    {
+        uint64_t total = 0;
+        for (size_t c = 0; c < n_chains; c++) total += chains[c].n_seeds;
+        size_t c = 0; uint64_t acc = 0;
+        for (size_t k = 0; k < K; k++) {
+            Sub &s = sub[k];
+            s.c0 = c;
+            const uint64_t target = total * (k + 1) / K;
+            while (c < n_chains && (acc < target || k + 1 == K)) acc += chains[c++].n_seeds;
+            if (c == s.c0 && c < n_chains) acc += chains[c++].n_seeds;
+            s.c1 = c;
+        }
+        while (!sub.empty() && sub.back().c0 == sub.back().c1) sub.pop_back();
+        K = sub.size();
+    }
+    uint64_t lane_bytes = 0;
+    for (Sub &s : sub) {
+        s.rmin = 0xffffffffu; s.rmax = 0; s.smin = (size_t)-1; s.smax = 0; s.est = (size_t)1 << 18;
+        for (size_t c = s.c0; c < s.c1; c++) {
+            const lf_chain &ch = chains[c];
+            if (ch.read_id < s.rmin) s.rmin = ch.read_id;
+            if (ch.read_id > s.rmax) s.rmax = ch.read_id;
+            if (ch.seed_off < s.smin) s.smin = (size_t)ch.seed_off;
+            if (ch.seed_off + ch.n_seeds > s.smax) s.smax = (size_t)(ch.seed_off + ch.n_seeds);
+            s.est += (size_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);   /* ~0.55 B of CIGAR + MD per aligned read base at 13 % error */
+        }
+        lane_bytes += reads->offsets[s.rmax + 1] - reads->offsets[s.rmin];
+    }
+    if (ndev == 1 && lane_bytes > reads->offsets[reads->n_reads] + reads->offsets[reads->n_reads] / 3)   /* chains not in read order: every lane would upload most of the reads */
+        return align_chains_one(ctx, reads, contigs, seeds, chains, n_chains, pac_host, out, nullptr);
+    unsigned nthreads = std::thread::hardware_concurrency();
+    {
+        const char *e = getenv("LF_HOST_THREADS"), *lw = getenv("LOCAL_WORLD_SIZE");
+        if (e && atoi(e) > 0) nthreads = (unsigned)atoi(e);
+        else if (lw && atoi(lw) > 1) nthreads = nthreads / (unsigned)atoi(lw);
+    }
+    /* ---- one text buffer for the whole call, a slice per lane ---- */
+    size_t arena_bytes = 0;
+    for (Sub &s : sub) { s.io.off = arena_bytes; s.io.cap = s.est; arena_bytes += (s.est + 255) & ~(size_t)255; }
+    size_t arena_cap = 0;
+    char *arena = (char *)g_result_pool_pinned.get(arena_bytes + 1, &arena_cap);
+    if (!arena) return LF_ERR_NOMEM;
+    ChainScratch &S = chain_scratch(ctx);
+    /* ---- the reads of every lane, in lane order, on the parent's stream of the lane's device ---- */
+    size_t noff = 0;
+    for (Sub &s : sub) noff += (size_t)(s.rmax - s.rmin) + 2;
+    uint64_t *offs = (uint64_t *)S.meta_stage.reserve(noff * 8 + 64);
+    if (!offs) { g_result_pool_pinned.put(arena, arena_cap); return LF_ERR_NOMEM; }
+    int rc = LF_OK;
+    {
+        size_t o = 0;
+        for (size_t k = 0; k < K && rc == LF_OK; k++) {
+            Sub &s = sub[k];
+            lf_gpu_ctx *lc = lane_ctx(ctx, k);
+            if (!lc) { rc = LF_ERR_NOMEM; break; }
+            DevState &pd = ctx->devs[k % ndev], &d = lc->devs[0];
+            const uint32_t nr = s.rmax - s.rmin + 1;
+            const uint64_t b0 = reads->offsets[s.rmin], nb = reads->offsets[s.rmax + 1] - b0;
+            uint64_t *lo = offs + o;
+            for (uint32_t r = 0; r <= nr; r++) lo[r] = reads->offsets[s.rmin + r] - b0;
+            o += (size_t)nr + 1;
+            s.rd.bases = reads->bases + b0; s.rd.offsets = lo; s.rd.n_reads = nr;
+            s.ch.assign(chains + s.c0, chains + s.c1);
+            for (lf_chain &ch : s.ch) { ch.read_id -= s.rmin; ch.seed_off -= s.smin; }
+            s.io.arena = arena; s.io.nthreads = nthreads / (unsigned)K ? nthreads / (unsigned)K : 1u;
+            if (set_dev(d) || d.bases.reserve(nb + 64) || d.read_off.reserve(((size_t)nr + 1) * 8)
+                || lfb_h2d(d.bases.p, s.rd.bases, nb, pd.stream) || lfb_h2d(d.read_off.p, lo, ((size_t)nr + 1) * 8, pd.stream)) { rc = LF_ERR_CUDA; break; }
+#ifndef LF_EMU
+            cudaEventRecord(d.up_ev, pd.stream);
+#endif
+            d.reads_preloaded = true;
+        }
+    }
+    /* ---- the lanes, a host thread each ---- */
+    if (rc == LF_OK) {
+        auto run_lane = [&](size_t k) {
+            Sub &s = sub[k];
+            s.rc = align_chains_one(ctx->lanes[k], &s.rd, contigs, seeds + s.smin, s.ch.data(), s.ch.size(), pac_host, &s.R, &s.io);
+        };
+#ifndef LF_EMU
+        std::vector<std::thread> th;
+        for (size_t k = 1; k < K; k++) th.emplace_back(run_lane, k);
+        run_lane(0);
+        for (auto &t : th) t.join();
+#else
+        for (size_t k = 0; k < K; k++) run_lane(k);   /* the emulator is single-threaded */
+#endif
+        for (size_t k = 0; k < K; k++) if (sub[k].rc != LF_OK && rc == LF_OK) { rc = sub[k].rc; ctx->err = "lane " + std::to_string(k) + ": " + ctx->lanes[k]->err; }
+    }
+    for (size_t k = 0; k < ctx->lanes.size(); k++) ctx->lanes[k]->devs[0].reads_preloaded = false;
+    if (rc != LF_OK) {
+        for (Sub &s : sub) delete s.R;
+        g_result_pool_pinned.put(arena, arena_cap);
+        return rc;
+    }
+    /* ---- merge: records in chain order (lane order), text already in place ---- */
+    lf_chain_results *R = new lf_chain_results();
+    memset(&R->stats, 0, sizeof R->stats);
+    R->pinned = true;
+    size_t nrec = 0, text_end = 0;
+    bool all_in_arena = true;
+    for (Sub &s : sub) { nrec += s.R->n_recs; all_in_arena &= s.R->text_borrowed || s.R->text_bytes == 0; }
+    R->recs = (lf_sam_record *)g_result_pool_pinned.get((nrec + 1) * sizeof(lf_sam_record), &R->recs_cap);
+    if (!R->recs) { for (Sub &s : sub) delete s.R; g_result_pool_pinned.put(arena, arena_cap); delete R; return LF_ERR_NOMEM; }
+    if (!all_in_arena) {   /* a lane's text outgrew its slice (it moved to a buffer of its own): gather everything into a new buffer */
+        size_t total = 0;
+        for (Sub &s : sub) total += s.R->text_bytes;
+        size_t cap = 0;
+        char *nt = (char *)g_result_pool_pinned.get(total + 1, &cap);
+        if (!nt) { for (Sub &s : sub) delete s.R; g_result_pool_pinned.put(arena, arena_cap); delete R; return LF_ERR_NOMEM; }
+        size_t o = 0;
+        for (Sub &s : sub) {
+            const char *src = s.R->text_borrowed ? arena + s.io.off : s.R->text;
+            if (s.R->text_bytes) memcpy(nt + o, src, s.R->text_bytes);
+            const uint64_t from = s.R->text_borrowed ? s.io.off : 0;
+            for (size_t i = 0; i < s.R->n_recs; i++) { s.R->recs[i].cigar_off += o - from; s.R->recs[i].md_off += o - from; }
+            o += s.R->text_bytes;
+        }
+        g_result_pool_pinned.put(arena, arena_cap);
+        arena = nt; arena_cap = cap; text_end = total;
+    } else for (Sub &s : sub) if (s.R->text_bytes && s.io.off + s.R->text_bytes > text_end) text_end = s.io.off + s.R->text_bytes;
+    size_t o = 0;
+    for (Sub &s : sub) {
+        for (size_t i = 0; i < s.R->n_recs; i++) { lf_sam_record r = s.R->recs[i]; r.chain_id += (uint32_t)s.c0; R->recs[o++] = r; }
+        const lf_chain_stats &a = s.R->stats;
+        R->stats.round1_tasks += a.round1_tasks; R->stats.round2_extends += a.round2_extends; R->stats.round3_tasks += a.round3_tasks; R->stats.records += a.records;
+        R->stats.ms_tasks = std::max(R->stats.ms_tasks, a.ms_tasks); R->stats.ms_round1 = std::max(R->stats.ms_round1, a.ms_round1);
+        R->stats.ms_rounds23 = std::max(R->stats.ms_rounds23, a.ms_rounds23); R->stats.ms_emit = std::max(R->stats.ms_emit, a.ms_emit); R->stats.ms_merge = std::max(R->stats.ms_merge, a.ms_merge);
+        delete s.R;
+    }
+    R->n_recs = nrec;
+    R->text = arena; R->text_cap = arena_cap; R->text_bytes = text_end;
+    ctx->stats.kernel_launches = lfb_launches;
     *out = R;
     return LF_OK;
 }

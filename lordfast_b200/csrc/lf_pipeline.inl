@@ -48,10 +48,14 @@ struct DevState {
     size_t task_first = 0; uint32_t n_tasks = 0; uint64_t ops_words = 0;
     size_t etask_first = 0; uint32_t n_etasks = 0;
     bool ran = false;
+    bool pac_borrowed = false;      /* a lane of lf_gpu_align_chains: the reference belongs to the parent context's DevState */
+    lfb_event up_ev = 0;            /* lane: its reads have arrived (recorded on the parent's upload stream) */
+    bool reads_preloaded = false;   /* lane: the parent has enqueued the H2D copy of the reads; upload_reads only waits and packs */
 };
 
 struct lf_gpu_ctx {
     std::vector<DevState> devs;
+    std::vector<lf_gpu_ctx *> lanes;   /* lf_chain.inl: single-device child contexts that pipeline the sub-batches of one call */
     void *chain_scratch = nullptr; /* lf_chain.inl: pinned staging kept between calls */
     void (*chain_scratch_free)(void *) = nullptr;
     int64_t l_pac = 0;
@@ -77,7 +81,7 @@ int fail(lf_gpu_ctx *c, int code, const char *msg)
 #define LF_TRY(expr) do { int rc_ = (expr); if (rc_ != 0) return fail(ctx, rc_ == -5 ? LF_ERR_NOMEM : LF_ERR_CUDA, #expr); } while (0)
 
 #ifndef LF_BANDREG_DEFAULT
-#define LF_BANDREG_DEFAULT 0xe   /* NW = 8, 12, 16 classes; measured neutral for NW = 6 in the config-2 mix (profiles/r02c) */
+#define LF_BANDREG_DEFAULT 0xf   /* NW = 6, 8, 12, 16 classes (round 2: with the uncertified retries no longer behind a slow warp kernel, the NW = 6 class gains too: 1.88 vs 1.92 ms per config-2 step) */
 #endif
 /* Size classes whose near-diagonal global tasks run in k_myers_bandreg (LF_BANDREG overrides; the other tasks of
  * 128 < q <= 512 run full width in k_myers_small, which is also the retry path of the tasks the band cannot certify) */
@@ -467,6 +471,27 @@ static std::thread g_prewarm;
 static bool g_prewarm_started = false;
 #endif
 
+/* streams and events of one device state (the caller has made d.dev current) */
+static int init_dev_streams(DevState &d)
+{
+#ifndef LF_EMU
+    if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
+    {   /* highest priority: its few long-latency warps must not queue behind the round-1 grids */
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&d.ext_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return -1;
+    }
+    cudaEventCreateWithFlags(&d.ext_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&d.up_ev, cudaEventDisableTiming);
+    for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking) != cudaSuccess) return -1; cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
+    for (int c = 0; c < LF_NCLS; c++) { cudaEventCreate(&d.cls_ev[c][0]); cudaEventCreate(&d.cls_ev[c][1]); }
+#else
+    (void)d;
+#endif
+    return 0;
+}
+
 extern "C" {
 
 int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *devices, int n_devices)
@@ -498,18 +523,7 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
         DevState &d = ctx->devs[i];
         d.dev = devs[i];
         if (set_dev(d)) { delete ctx; return LF_ERR_NO_DEVICE; }
-#ifndef LF_EMU
-        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; }
-        for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
-        {   /* highest priority: its few long-latency warps must not queue behind the round-1 grids */
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            if (cudaStreamCreateWithPriority(&d.ext_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; }
-        }
-        cudaEventCreateWithFlags(&d.ext_ev, cudaEventDisableTiming);
-        for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LF_ERR_CUDA; } cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
-        for (int c = 0; c < LF_NCLS; c++) { cudaEventCreate(&d.cls_ev[c][0]); cudaEventCreate(&d.cls_ev[c][1]); }
-#endif
+        if (init_dev_streams(d)) { delete ctx; return LF_ERR_CUDA; }
         d.pinned = lfb_host_alloc(sizeof(HostTotals));
         if (!d.pinned || d.pac.reserve(pac_bytes + 16)) { lf_gpu_destroy(ctx); return LF_ERR_NOMEM; }
         if (lfb_memset(d.pac.p, 0, pac_bytes + 16, d.stream) || lfb_h2d(d.pac.p, pac, pac_bytes, d.stream) || lfb_sync(d.stream)) { lf_gpu_destroy(ctx); return LF_ERR_CUDA; }
@@ -521,9 +535,12 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
 void lf_gpu_destroy(lf_gpu_ctx *ctx)
 {
     if (!ctx) return;
+    for (lf_gpu_ctx *l : ctx->lanes) lf_gpu_destroy(l);
+    ctx->lanes.clear();
     if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
     for (DevState &d : ctx->devs) {
         set_dev(d);
+        if (d.pac_borrowed) { d.pac.p = nullptr; d.pac.cap = 0; }
         LfbBuf *bufs[] = { &d.retry_scr, &d.group_scr, &d.planes, &d.gbytes, &d.goff, &d.res_keep, &d.ops_keep, &d.pac, &d.bases, &d.read_off, &d.plo, &d.phi, &d.pnn, &d.tasks, &d.res, &d.ops, &d.keys, &d.keys2, &d.idx, &d.idx2,
                            &d.slot_words, &d.scr_bytes, &d.slot_end, &d.scr_off, &d.scratch, &d.large_scr, &d.counters, &d.queue,
                            &d.etasks, &d.eres, &d.escr_items, &d.escr_off, &d.escr };
@@ -534,6 +551,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
         for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         for (int k = 0; k < LF_NSUB; k++) { if (d.sub_ev[k]) cudaEventDestroy(d.sub_ev[k]); if (d.sub[k]) cudaStreamDestroy(d.sub[k]); }
         if (d.ext_ev) cudaEventDestroy(d.ext_ev);
+        if (d.up_ev) cudaEventDestroy(d.up_ev);
         if (d.ext_stream) cudaStreamDestroy(d.ext_stream);
         for (int c = 0; c < LF_NCLS; c++) { if (d.cls_ev[c][0]) cudaEventDestroy(d.cls_ev[c][0]); if (d.cls_ev[c][1]) cudaEventDestroy(d.cls_ev[c][1]); }
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -576,14 +594,22 @@ int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads)
 {
     if (!ctx || !reads || !reads->offsets || (!reads->bases && reads->n_reads)) return LF_ERR_BAD_ARG;
     const uint32_t nr = reads->n_reads;
-    const uint64_t total = reads->offsets[nr];
+    const uint64_t total = reads->offsets[nr] - reads->offsets[0];
     const size_t pwords = (size_t)(total >> 5) + 3 * (size_t)nr + 8;
     for (DevState &d : ctx->devs) {
         if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
-        LF_TRY(d.bases.reserve(total + 64)); LF_TRY(d.read_off.reserve(((size_t)nr + 1) * 8));
         LF_TRY(d.plo.reserve(pwords * 4)); LF_TRY(d.phi.reserve(pwords * 4)); LF_TRY(d.pnn.reserve(pwords * 4));
-        LF_TRY(lfb_h2d(d.bases.p, reads->bases, total, d.stream));
-        LF_TRY(lfb_h2d(d.read_off.p, reads->offsets, ((size_t)nr + 1) * 8, d.stream));
+        if (d.reads_preloaded) {   /* lf_chain.inl lanes: the parent enqueued the copies in lane order on its upload stream */
+#ifndef LF_EMU
+            cudaStreamWaitEvent(d.stream, d.up_ev, 0);
+#endif
+            d.reads_preloaded = false;
+        } else {
+            if (reads->offsets[0] != 0) return fail(ctx, LF_ERR_BAD_ARG, "read offsets must start at 0");
+            LF_TRY(d.bases.reserve(total + 64)); LF_TRY(d.read_off.reserve(((size_t)nr + 1) * 8));
+            LF_TRY(lfb_h2d(d.bases.p, reads->bases, total, d.stream));
+            LF_TRY(lfb_h2d(d.read_off.p, reads->offsets, ((size_t)nr + 1) * 8, d.stream));
+        }
         LF_TRY(lfb_memset(d.plo.p, 0, pwords * 4, d.stream)); LF_TRY(lfb_memset(d.phi.p, 0, pwords * 4, d.stream));
         LF_TRY(lfb_memset(d.pnn.p, 0xff, pwords * 4, d.stream));
         d.n_reads = nr; d.total_bases = total;

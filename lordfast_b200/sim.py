@@ -34,6 +34,22 @@ def make_reference(n: int, seed: int = 1) -> np.ndarray:
     return ACGT[rng.integers(0, 4, size=n, dtype=np.uint8)]
 
 
+def make_reference_dups(n: int, seed: int = 1, dups: int = 0) -> np.ndarray:
+    """make_reference plus `dups` segments of 20-50 kbp (4-9 kbp in small references) copied elsewhere at 2-5 %
+    divergence, so that several candidate windows tie and lordFAST's fine mode / --numMap path is taken."""
+    ref = make_reference(n, seed)
+    if dups:
+        rng = np.random.default_rng(seed + 31)
+        for _ in range(dups):
+            L = int(rng.integers(20_000, 50_000)) if n > 400_000 else int(rng.integers(4_000, 9_000))
+            a, b = int(rng.integers(0, n - L)), int(rng.integers(0, n - L))
+            seg = ref[a:a + L].copy()
+            hit = rng.random(L) < rng.uniform(0.02, 0.05)
+            seg[hit] = ACGT[(np.searchsorted(ACGT, seg[hit]) + rng.integers(1, 4, size=int(hit.sum()))) % 4]
+            ref[b:b + L] = seg
+    return ref
+
+
 def revcomp(a: np.ndarray) -> np.ndarray:
     return _COMP[a[::-1]]
 

@@ -188,8 +188,11 @@ double ref_replay_chains(int n_chains, const int64_t *seed_off, const lfo_seed *
 /* a recorder that forwards to alignChain_edlib and logs each chain and the records it yields.  */
 /* ------------------------------------------------------------------------------------------ */
 #ifdef LF_CHAINDUMP_MAIN
+#include <zlib.h>
 static FILE *g_dump = NULL;
 static pthread_mutex_t g_dump_lock = PTHREAD_MUTEX_INITIALIZER;
+static int g_dump_hash = 0;      /* LF_CHAIN_DUMP_HASH=1: per record the lengths and zlib CRC-32 of CIGAR and MD instead of the strings */
+static long g_dump_full = 0;     /* ... but the strings too for reads named r<k> with k < LF_CHAIN_DUMP_FULL */
 
 static void dump_hook(Chain_t &chain, char *query, int32_t readLen, int isRev, SamList_t &map)
 {
@@ -203,10 +206,16 @@ static void dump_hook(Chain_t &chain, char *query, int32_t readLen, int isRev, S
     for (uint32_t i = 0; i < chain.chainLen; i++)
         fprintf(g_dump, "%u,%u,%u;", chain.seeds[i].tPos, (unsigned)chain.seeds[i].qPos, (unsigned)chain.seeds[i].len);
     fprintf(g_dump, "\n");
+    const bool full = !g_dump_hash || (name[0] == 'r' && atol(name + 1) < g_dump_full);
     for (size_t i = before; i < map.samList.size(); i++) {
         const Sam_t &s = map.samList[i];
-        fprintf(g_dump, "S\t%u\t%u\t%u\t%u\t%u\t%d\t%s\t%s\n", (unsigned)s.flag, s.pos, s.posEnd, s.qStart, s.qEnd, s.nmCount,
-                s.cigar.c_str(), s.md.c_str());
+        if (g_dump_hash)
+            fprintf(g_dump, "H\t%u\t%u\t%u\t%u\t%u\t%d\t%zu\t%lu\t%zu\t%lu\n", (unsigned)s.flag, s.pos, s.posEnd, s.qStart, s.qEnd, s.nmCount,
+                    s.cigar.size(), (unsigned long)crc32(0L, (const Bytef *)s.cigar.data(), (uInt)s.cigar.size()),
+                    s.md.size(), (unsigned long)crc32(0L, (const Bytef *)s.md.data(), (uInt)s.md.size()));
+        if (full)
+            fprintf(g_dump, "S\t%u\t%u\t%u\t%u\t%u\t%d\t%s\t%s\n", (unsigned)s.flag, s.pos, s.posEnd, s.qStart, s.qEnd, s.nmCount,
+                    s.cigar.c_str(), s.md.c_str());
     }
     pthread_mutex_unlock(&g_dump_lock);
 }
@@ -214,6 +223,8 @@ static void dump_hook(Chain_t &chain, char *query, int32_t readLen, int isRev, S
 int main(int argc, char *argv[])
 {
     const char *path = getenv("LF_CHAIN_DUMP");
+    g_dump_hash = getenv("LF_CHAIN_DUMP_HASH") && atoi(getenv("LF_CHAIN_DUMP_HASH"));
+    g_dump_full = getenv("LF_CHAIN_DUMP_FULL") ? atol(getenv("LF_CHAIN_DUMP_FULL")) : 0;
     if (parseCommandLine(argc, argv)) return EXIT_FAILURE;
     if (indexingMode) return bwt_index(refFile) ? EXIT_FAILURE : 0;
     g_dump = fopen(path ? path : "chains.txt", "w");

@@ -139,6 +139,20 @@ class RefIndex:
         self.cref = Ref(C.cast(self.pac, C.c_void_p), len(seq), self.n, self.off, self.len)
 
 
+class PacIndex(RefIndex):
+    """RefIndex over an existing 2-bit reference (numpy uint8, bwa .pac layout) and contig table."""
+
+    def __init__(self, pac, l_pac, contig_off, contig_len):
+        self.keep = (pac, )
+        self.seq = None
+        self.l_pac = int(l_pac)
+        self.pac = C.cast(pac.ctypes.data, C.c_void_p)
+        self.n = len(contig_off)
+        self.off = (C.c_int64 * self.n)(*[int(x) for x in contig_off])
+        self.len = (C.c_int32 * self.n)(*[int(x) for x in contig_len])
+        self.cref = Ref(self.pac, self.l_pac, self.n, self.off, self.len)
+
+
 def _sam_list(arr, n):
     out = []
     for i in range(n):
@@ -161,7 +175,7 @@ def oracle_align_chain(idx: RefIndex, seeds, query: bytes, is_rev: int):
 
 
 def ref_align_chain(idx: RefIndex, seeds, query: bytes, is_rev: int):
-    ref().ref_set_index(C.cast(idx.pac, C.c_void_p), len(idx.seq), idx.n, idx.off, idx.len)
+    ref().ref_set_index(C.cast(idx.pac, C.c_void_p), len(idx.seq) if idx.seq is not None else idx.l_pac, idx.n, idx.off, idx.len)
     arr = (Seed * len(seeds))(*[Seed(*s) for s in seeds])
     sam = (Sam * 64)()
     n = C.c_int(0)
