@@ -406,6 +406,45 @@ double now_ms()
     struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
+static double g_trace_t0 = 0;   /* LF_CHAIN_TRACE: start of the lf_gpu_align_chains call the lanes belong to */
+/* LF_CHAIN_TRACE=2: GPU-side timeline.  Events recorded behind the phases of a call, printed against the reference event
+ * the call recorded first (all on one device). */
+#ifndef LF_EMU
+struct TraceMarks {
+    std::mutex mu;
+    std::vector<std::pair<std::string, cudaEvent_t>> ev;
+    cudaEvent_t ref = nullptr;
+};
+static TraceMarks g_marks;
+static bool trace_gpu() { const char *e = getenv("LF_CHAIN_TRACE"); return e && atoi(e) >= 2; }
+static void trace_ref(lfb_stream s)
+{
+    if (!trace_gpu()) return;
+    std::lock_guard<std::mutex> g(g_marks.mu);
+    for (auto &m : g_marks.ev) cudaEventDestroy(m.second);
+    g_marks.ev.clear();
+    if (!g_marks.ref) cudaEventCreate(&g_marks.ref);
+    cudaEventRecord(g_marks.ref, s);
+}
+static void trace_mark(const lf_gpu_ctx *ctx, const char *name, lfb_stream s)
+{
+    if (!trace_gpu()) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+    char buf[96]; snprintf(buf, sizeof buf, "%p %s", (const void *)ctx, name);
+    std::lock_guard<std::mutex> g(g_marks.mu);
+    g_marks.ev.push_back({buf, e});
+}
+static void trace_print()
+{
+    if (!trace_gpu()) return;
+    std::lock_guard<std::mutex> g(g_marks.mu);
+    for (auto &m : g_marks.ev) { float ms = -1; cudaEventSynchronize(m.second); cudaEventElapsedTime(&ms, g_marks.ref, m.second); fprintf(stderr, "[gpu +%.2f] %s\n", ms, m.first.c_str()); }
+}
+#else
+static void trace_ref(lfb_stream) { }
+static void trace_mark(const lf_gpu_ctx *, const char *, lfb_stream) { }
+static void trace_print() { }
+#endif
 
 void chain_scratch_free_fn(void *p)
 {
@@ -428,7 +467,7 @@ ChainScratch &chain_scratch(lf_gpu_ctx *ctx)
 
 
 /* ---- GPU emit of one list of chains: k_emit_slots sizing pass -> scans -> writing pass ---- */
-int emit_size(EmitSet &es, LfEmitDev &E, const uint32_t *list, size_t n)
+int emit_size(DevState &d, EmitSet &es, LfEmitDev &E, const uint32_t *list, size_t n)
 {
     lfb_stream st = es.st;
     es.n = n; es.nrec = es.ncig = es.nmd = 0;
@@ -437,7 +476,7 @@ int emit_size(EmitSet &es, LfEmitDev &E, const uint32_t *list, size_t n)
         || es.d_rec_off.reserve((n + 1) * 8) || es.d_cig_off.reserve((n + 1) * 8) || es.d_md_off.reserve((n + 1) * 8)) return LF_ERR_NOMEM;
     unsigned long long *tot = (unsigned long long *)es.tot.reserve(64);
     if (!tot) return LF_ERR_NOMEM;
-    if (lfb_h2d(es.d_list.p, list, n * 4, st)) return LF_ERR_CUDA;
+    if (h2d_k(d, es.d_list.p, list, n * 4, st, true)) return LF_ERR_CUDA;   /* `list` is pinned staging of the caller's thread (stage_get is not thread-safe) */
     E.chain_list = es.d_list.as<uint32_t>(); E.n_chains = (uint32_t)n;
     E.nrec = es.d_nrec.as<uint32_t>(); E.cig_bytes = es.d_cigb.as<uint32_t>(); E.md_bytes = es.d_mdb.as<uint32_t>();
     { auto kern = k_emit_slots<false>; LFB_LAUNCH(kern, (unsigned)n, LF_EMIT_BLOCK, 0, st, E); }   /* one block per chain, one thread per slot */
@@ -503,6 +542,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         else if (lw && atoi(lw) > 1) nthreads = nthreads / (unsigned)atoi(lw);
     }
     if (io) nthreads = io->nthreads;
+    for (DevState &dd : ctx->devs) stage_reset(dd);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
     int rc;
@@ -511,7 +551,9 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     /* CIGAR / MD assembly runs on the GPU (k_emit_slots) when the context drives one device; a context over
      * several devices assembles on host threads from the 2-bit op stream (LF_CHAIN_HOST_EMIT=1 forces that). */
     const bool gpu_emit = ctx->devs.size() == 1 && !getenv("LF_CHAIN_HOST_EMIT");
+    if (!io) trace_ref(ctx->devs[0].stream);
     LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
+    trace_mark(ctx, "reads packed", ctx->devs[0].stream);
     const double tt1 = now_ms();
     if (gpu_emit) {
         DevState &d = ctx->devs[0];
@@ -520,12 +562,13 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         if (S.d_chains.reserve(n_chains * sizeof(lf_chain) + 64) || S.d_seeds.reserve(ns * sizeof(lf_seed) + 64)) { delete R; return LF_ERR_NOMEM; }
         /* the caller's seed array is ordinary (pageable) memory: stage it through pinned memory with all host
          * threads so that the copy to the device is asynchronous and overlaps the task generation */
-        char *stage = (char *)S.seeds_stage.reserve(ns * sizeof(lf_seed) + n_chains * sizeof(lf_chain) + 64);
+        char *stage = (char *)S.seeds_stage.reserve(ns * sizeof(lf_seed) + n_chains * sizeof(lf_chain) + 128);
         if (!stage) { delete R; return LF_ERR_NOMEM; }
-        const size_t sb = ns * sizeof(lf_seed);
+        const size_t sb = ns * sizeof(lf_seed), cb = (sb + 63) & ~(size_t)63;
         parallel_for(sb, nthreads, [&](unsigned, size_t lo, size_t hi) { memcpy(stage + lo, (const char *)seeds + lo, hi - lo); }, 1 << 20);
-        memcpy(stage + sb, chains, n_chains * sizeof(lf_chain));
-        if (lfb_h2d(S.d_seeds.p, stage, sb, d.stream) || lfb_h2d(S.d_chains.p, stage + sb, n_chains * sizeof(lf_chain), d.stream)) { delete R; return LF_ERR_CUDA; }
+        memcpy(stage + cb, chains, n_chains * sizeof(lf_chain));
+        /* by kernel, not by the copy engine: there the copy would wait behind the reads of all lanes of the call */
+        if (h2d_k(d, S.d_seeds.p, stage, sb, d.stream, true) || h2d_k(d, S.d_chains.p, stage + cb, n_chains * sizeof(lf_chain), d.stream, true)) { delete R; return LF_ERR_CUDA; }
     }
 
     /* ---------------- round 1: tasks known from the chains alone ---------------- */
@@ -665,21 +708,22 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         for (size_t c = 0; c <= n_chains; c++) slot_base[c] = gap_base[c] + c;
         for (size_t c = 0; c < n_chains; c++) guards[c] = (uint8_t)((plan[c].head_guard ? 1 : 0) | (plan[c].tail_guard ? 2 : 0));
         n_slots = (size_t)slot_base[n_chains];
-        if (S.d_task_base.reserve((n_chains + 1) * 8) || S.d_slot_base.reserve((n_chains + 1) * 8) || S.d_guards.reserve(n_chains + 64)
+        if (S.d_task_base.reserve((n_chains + 1) * 8 + 64) || S.d_slot_base.reserve((n_chains + 1) * 8 + 64) || S.d_guards.reserve(n_chains + 64)
             || S.d_slot_info.reserve((n_slots + 1) * sizeof(LfSlotInfo)) || S.d_slot_task.reserve((n_slots + 1) * 4)) { delete R; return LF_ERR_NOMEM; }
         /* through pinned memory: a copy from pageable memory blocks the host until the stream (busy with the reads) gets to it */
-        char *ms = (char *)S.meta_stage.reserve((n_chains + 1) * 16 + n_chains + 64);
+        const size_t mb = ((n_chains + 1) * 8 + 63) & ~(size_t)63;
+        char *ms = (char *)S.meta_stage.reserve(2 * mb + n_chains + 128);
         if (!ms) { delete R; return LF_ERR_NOMEM; }
-        memcpy(ms, task_base.data(), (n_chains + 1) * 8); memcpy(ms + (n_chains + 1) * 8, slot_base.data(), (n_chains + 1) * 8); memcpy(ms + (n_chains + 1) * 16, guards.data(), n_chains);
-        if (lfb_h2d(S.d_task_base.p, ms, (n_chains + 1) * 8, d.stream) || lfb_h2d(S.d_slot_base.p, ms + (n_chains + 1) * 8, (n_chains + 1) * 8, d.stream)
-            || lfb_h2d(S.d_guards.p, ms + (n_chains + 1) * 16, n_chains, d.stream)) { delete R; return LF_ERR_CUDA; }
+        memcpy(ms, task_base.data(), (n_chains + 1) * 8); memcpy(ms + mb, slot_base.data(), (n_chains + 1) * 8); memcpy(ms + 2 * mb, guards.data(), n_chains);
+        if (h2d_k(d, S.d_task_base.p, ms, (n_chains + 1) * 8, d.stream, true) || h2d_k(d, S.d_slot_base.p, ms + mb, (n_chains + 1) * 8, d.stream, true)
+            || h2d_k(d, S.d_guards.p, ms + 2 * mb, n_chains, d.stream, true)) { delete R; return LF_ERR_CUDA; }
     }
     size_t cap1 = 64;
     for (size_t c = 0; c < n_chains; c++) cap1 += nslot[c] * 4;
     uint8_t *ops1 = gpu_emit ? nullptr : (uint8_t *)S.ops1.reserve(cap1 + 64);
     if (!gpu_emit && !ops1) { delete R; return LF_ERR_NOMEM; }
     const double tm1 = now_ms();
-    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] tasks: upload_reads call %.2f, seed staging %.2f, pass A %.2f, prefix %.2f, pass B %.2f, emit inputs %.2f\n", tt1 - tm0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, tm1 - tt5);
+    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain %p +%.2f] ", (void *)ctx, now_ms() - g_trace_t0), fprintf(stderr, "tasks: upload_reads call %.2f, seed staging %.2f, pass A %.2f, prefix %.2f, pass B %.2f, emit inputs %.2f\n", tt1 - tm0, tt2 - tt1, tt3 - tt2, tt4 - tt3, tt5 - tt4, tm1 - tt5);
     if (n1) {
         if (dev_tasks) {
             DevState &d = ctx->devs[0];
@@ -690,6 +734,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         } else LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
         const double tr0 = now_ms();
         LF_CH(lf_gpu_run_align(ctx));   /* returns once the class kernels are launched (its class-count sync has waited for the uploads) */
+        trace_mark(ctx, "round-1 kernels done", ctx->devs[0].stream);
         if (spec) {
             /* Speculative round 2: the clip / split triggers can only fire for tasks whose LENGTHS qualify (:1840 / :2175
              * ql > 500, :1952 |ql - tl| >= 80), which is known now.  Their extensions (a superset of what round 2 will
@@ -755,9 +800,10 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
                 if (!pe || !sx2) { delete R; return LF_ERR_NOMEM; }
                 memcpy(pe, se2.data(), se2.size() * sizeof(lf_extend_task));
                 LF_CH(spec_extend_start(ctx, pe, se2.size(), sx2));
+                trace_mark(ctx, "speculative extensions done", ctx->devs[0].ext_stream);
             }
         }
-        if (getenv("LF_CHAIN_TRACE")) { const double tr1 = now_ms(); lf_gpu_sync(ctx); fprintf(stderr, "[lf_chain] r1: enqueue uploads %.2f, run_align returns after %.2f (its class-count sync waits for the uploads), kernels drained after %.2f more\n", tr0 - tm1, tr1 - tr0, now_ms() - tr1); }
+        if (getenv("LF_CHAIN_TRACE") && atoi(getenv("LF_CHAIN_TRACE")) == 1) { const double tr1 = now_ms(); lf_gpu_sync(ctx); fprintf(stderr, "[lf_chain %p +%.2f] ", (void *)ctx, now_ms() - g_trace_t0), fprintf(stderr, "r1: enqueue uploads %.2f, run_align returns after %.2f (its class-count sync waits for the uploads), kernels drained after %.2f more\n", tr0 - tm1, tr1 - tr0, now_ms() - tr1); }
         if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r1, ops1, cap1));
         else { /* results and ops stay in HBM; the trigger tests run there and only the hits come back */
             DevState &d = ctx->devs[0];
@@ -889,10 +935,14 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         if (!es.have_stream) { if (cudaStreamCreateWithFlags(&es.st, cudaStreamNonBlocking) != cudaSuccess) { delete R; return LF_ERR_CUDA; } es.have_stream = true; }
 #endif
         const size_t dirty_slots = n_slots - clean_slots;
-        auto run_early = [&, dirty_slots]() {
+        uint32_t *clean_pinned = (uint32_t *)stage_get(d, clean_list.size() * 4 + 16);
+        if (!clean_pinned) { delete R; return LF_ERR_NOMEM; }
+        if (!clean_list.empty()) memcpy(clean_pinned, clean_list.data(), clean_list.size() * 4);
+        auto run_early = [&, dirty_slots, clean_pinned]() {
             if (set_dev(d)) { early.rc = LF_ERR_CUDA; return; }
             LfEmitDev E = E0;
-            if ((early.rc = emit_size(es, E, clean_list.data(), clean_list.size())) != 0) return;
+            if ((early.rc = emit_size(d, es, E, clean_pinned, clean_list.size())) != 0) return;
+            trace_mark(ctx, "early emit sized", es.st);
             /* one text buffer for both lists: the late list is appended, its size estimated from this one */
             const size_t bytes = es.ncig + es.nmd;
             const size_t est_late = dirty_slots ? (size_t)((double)bytes * ((double)dirty_slots / (double)(clean_slots ? clean_slots : 1)) * 1.5) + (1u << 16) : 0;
@@ -900,6 +950,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
             else early.text = (char *)g_result_pool_pinned.get(bytes + est_late + 1, &early.cap);
             if (!early.text) { early.rc = LF_ERR_NOMEM; return; }
             if ((early.rc = emit_write(es, E, early.text, early.borrowed ? io->off : 0)) != 0) return;
+            trace_mark(ctx, "early emit written", es.st);
             if (lfb_sync(es.st)) early.rc = LF_ERR_CUDA;
         };
 #ifndef LF_EMU
@@ -997,15 +1048,17 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         std::swap(d.res, d.res_keep); std::swap(d.ops, d.ops_keep);
     }
     if (n3) {
-        LF_CH(lf_gpu_upload_align_tasks(ctx, t3.data(), n3));
+        if (gpu_emit) LF_CH(upload_align_tasks_k(ctx, t3.data(), n3));
+        else LF_CH(lf_gpu_upload_align_tasks(ctx, t3.data(), n3));
         LF_CH(lf_gpu_run_align(ctx));
+        trace_mark(ctx, "round-3 kernels done", ctx->devs[0].stream);
         if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r3, ops3, cap3));
         else { DevState &d = ctx->devs[0]; if (lfb_d2h(r3, d.res.p, n3 * sizeof(lf_align_result), d.stream)) { delete R; return LF_ERR_CUDA; } }
     }
     LF_CH(lf_gpu_sync(ctx));
     R->stats.round3_tasks = n3;
     const double tm3 = now_ms();
-    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] r23: trigger scan %.2f, early-emit start %.2f, round 2 %.2f, round-3 tasks %.2f, round 3 %.2f\n", tq0 - tm2, tq1 - tq0, tq2 - tq1, tq3 - tq2, tm3 - tq3);
+    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain %p +%.2f] ", (void *)ctx, now_ms() - g_trace_t0), fprintf(stderr, "r23: trigger scan %.2f, early-emit start %.2f, round 2 %.2f, round-3 tasks %.2f, round 3 %.2f\n", tq0 - tm2, tq1 - tq0, tq2 - tq1, tq3 - tq2, tm3 - tq3);
 #undef LF_CH
 
     if (gpu_emit) {
@@ -1044,12 +1097,15 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
                 }
             }
             split_begin[n_chains] = (uint32_t)sdev.size();
-            LF_G(S.d_clip.reserve(4 * n_chains * 4 + 64)); LF_G(S.d_split_begin.reserve((n_chains + 1) * 4)); LF_G(S.d_splits.reserve((sdev.size() + 1) * sizeof(LfSplitDev)));
-            LF_G(lfb_h2d(S.d_clip.p, clipv.data(), 4 * n_chains * 4, st)); LF_G(lfb_h2d(S.d_split_begin.p, split_begin.data(), (n_chains + 1) * 4, st));
-            if (!sdev.empty()) LF_G(lfb_h2d(S.d_splits.p, sdev.data(), sdev.size() * sizeof(LfSplitDev), st));
+            LF_G(S.d_clip.reserve(4 * n_chains * 4 + 64)); LF_G(S.d_split_begin.reserve((n_chains + 1) * 4 + 64)); LF_G(S.d_splits.reserve((sdev.size() + 1) * sizeof(LfSplitDev) + 64));
+            LF_G(h2d_k(d, S.d_clip.p, clipv.data(), 4 * n_chains * 4, st, false)); LF_G(h2d_k(d, S.d_split_begin.p, split_begin.data(), (n_chains + 1) * 4, st, false));
+            if (!sdev.empty()) LF_G(h2d_k(d, S.d_splits.p, sdev.data(), sdev.size() * sizeof(LfSplitDev), st, false));
             E1.clip = S.d_clip.as<int32_t>(); E1.split_begin = S.d_split_begin.as<uint32_t>(); E1.splits = S.d_splits.as<LfSplitDev>();
             E1.r3 = d.res.as<lf_align_result>(); E1.ops3 = d.ops.as<uint32_t>();
-            LF_G(emit_size(es1, E1, dirty_list.data(), n_dirty));
+            uint32_t *dirty_pinned = (uint32_t *)stage_get(d, n_dirty * 4 + 16);
+            if (!dirty_pinned) { delete R; return LF_ERR_NOMEM; }
+            memcpy(dirty_pinned, dirty_list.data(), n_dirty * 4);
+            LF_G(emit_size(d, es1, E1, dirty_pinned, n_dirty));
         } else { es1.n = es1.nrec = es1.ncig = es1.nmd = 0; }
         early.join();
         if (early.rc != 0) { delete R; return fail(ctx, early.rc, "early emit"); }
@@ -1071,7 +1127,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
             }
             R->text = nt; R->text_cap = cap; R->text_borrowed = false;
         }
-        if (n_dirty) { LF_G(emit_write(es1, E1, R->text + bytes0, (R->text_borrowed ? io->off : 0) + bytes0)); LF_G(lfb_sync(st)); }
+        if (n_dirty) { LF_G(emit_write(es1, E1, R->text + bytes0, (R->text_borrowed ? io->off : 0) + bytes0)); trace_mark(ctx, "late emit written", st); LF_G(lfb_sync(st)); }
         LF_G(lfb_last_error());
 #undef LF_G
         /* records of the two lists, merged back into chain order */
@@ -1095,8 +1151,9 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         R->stats.records = nrec;
         const double tm4 = now_ms();
         R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm4 - tm3); R->stats.ms_merge = 0.f;
-        if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] gpu emit: tasks %.2f r1 %.2f r23 %.2f late emit %.2f (chains %zu early + %zu late, recs %zu, text %zu MB)\n",
+        if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain %p +%.2f] ", (void *)ctx, now_ms() - g_trace_t0), fprintf(stderr, "gpu emit: tasks %.2f r1 %.2f r23 %.2f late emit %.2f (chains %zu early + %zu late, recs %zu, text %zu MB)\n",
                                               tm1 - tm0, tm2 - tm1, tm3 - tm2, tm4 - tm3, clean_list.size(), n_dirty, nrec, (bytes0 + bytes1) >> 20);
+        if (!io) trace_print();
         *out = R;
         return LF_OK;
     }
@@ -1271,7 +1328,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     for (Emit &E : parts) { if (!E.recs.empty()) memcpy(R->recs + nrec, E.recs.data(), E.recs.size() * sizeof(lf_sam_record)); nrec += E.recs.size(); }
     R->stats.records = R->n_recs;
     const double tm4 = now_ms();
-    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain] tasks %.2f r1 %.2f r23 %.2f emit %.2f gather %.2f (threads %u, recs %zu, text bound %zu MB)\n",
+    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain %p +%.2f] ", (void *)ctx, now_ms() - g_trace_t0), fprintf(stderr, "tasks %.2f r1 %.2f r23 %.2f emit %.2f gather %.2f (threads %u, recs %zu, text bound %zu MB)\n",
                                           tm1 - tm0, tm2 - tm1, tm3 - tm2, tm3b - tm3, tm4 - tm3b, nthreads, R->n_recs, R->text_bytes >> 20);
     R->stats.ms_tasks = (float)(tm1 - tm0); R->stats.ms_round1 = (float)(tm2 - tm1); R->stats.ms_rounds23 = (float)(tm3 - tm2); R->stats.ms_emit = (float)(tm3b - tm3); R->stats.ms_merge = (float)(tm4 - tm3b);
     *out = R;
@@ -1296,13 +1353,22 @@ static lf_gpu_ctx *lane_ctx(lf_gpu_ctx *ctx, size_t j)
     return ctx->lanes[j];
 }
 
-/* The call the reference side makes.  A chunk is cut into sub-batches of consecutive chains that run as a software
- * pipeline, each on a lane: the reads of the sub-batches are copied to the device(s) one after the other on one
- * stream, so that the first lane aligns while the others' reads are still in flight, and the CIGAR / MD text of a
- * lane goes back over PCIe (k_emit_slots writes it straight to pinned memory) while the next lanes compute.  With
- * several devices in the context the lanes are spread over them: reads sharded by contiguous ranges, every device
- * holding the whole reference, records merged in chain order -- the data-parallel loop of
- * src/LordFAST.cpp:295-316.  LF_CHAIN_LANES overrides the number of lanes (1: no pipeline). */
+/* The call the reference side makes.  A chunk is cut into sub-batches that run as a software pipeline, each on a lane:
+ *
+ *   the slow lane   the chains that can keep a lane busy for milliseconds whatever the batch size -- a gap, head or tail
+ *                   long enough for the lane-group / large kernels or for a clip / split trigger (src/LordFAST.cpp:1840,
+ *                   :1952, :2175), i.e. every chain that can reach rounds 2 and 3.  A few percent of a chunk; their reads
+ *                   are gathered into pinned staging and go to the device FIRST, so that their long chain of dependent
+ *                   launches (round 1 with 1 - 2 kbp tasks, extensions, round 3, the walk over long garbage alignments in
+ *                   the emit) runs while the bulk of the reads is still crossing PCIe;
+ *   the fast lanes  the other chains, as consecutive ranges balanced by seeds; no task above 256 rows, no trigger
+ *                   candidate, so a lane is upload -> round 1 -> emit.  Their reads follow in lane order on one stream:
+ *                   the first lane aligns while the others' reads are in flight, and the CIGAR / MD text of a lane goes
+ *                   back over PCIe (k_emit_slots writes it straight to pinned memory) while the next lanes compute.
+ *
+ * With several devices in the context the lanes are spread over them: reads sharded by contiguous ranges, every device
+ * holding the whole reference, records merged in chain order -- the data-parallel loop of src/LordFAST.cpp:295-316.
+ * LF_CHAIN_LANES overrides the number of lanes (1: no pipeline), LF_CHAIN_SLOW_LANE=0 switches the slow lane off. */
 int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs *contigs, const lf_seed *seeds,
                         const lf_chain *chains, size_t n_chains, const uint8_t *pac_host, lf_chain_results **out)
 {
@@ -1314,47 +1380,158 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     if (K > 64) K = 64;
     if (K > n_chains) K = n_chains ? n_chains : 1;
     if (K < 1) K = 1;
+    g_trace_t0 = now_ms();
     if (ndev == 1 && K == 1) return align_chains_one(ctx, reads, contigs, seeds, chains, n_chains, pac_host, out, nullptr);
     *out = nullptr;
     for (size_t c = 0; c < n_chains; c++) if (chains[c].read_id >= reads->n_reads || chains[c].n_seeds < 2) return LF_ERR_BAD_ARG;
-    /* ---- sub-batches: consecutive chains, balanced by seeds; the reads each of them touches ---- */
-    struct Sub { size_t c0, c1, smin, smax; uint32_t rmin, rmax; size_t est; std::vector<lf_chain> ch; lf_reads rd; lf_chain_results *R = nullptr; int rc = 0; LaneIO io; };
-    std::vector<Sub> sub(K);
-    {
-        uint64_t total = 0;
-        for (size_t c = 0; c < n_chains; c++) total += chains[c].n_seeds;
-        size_t c = 0; uint64_t acc = 0;
-        for (size_t k = 0; k < K; k++) {
-            Sub &s = sub[k];
-            s.c0 = c;
-            const uint64_t target = total * (k + 1) / K;
-            while (c < n_chains && (acc < target || k + 1 == K)) acc += chains[c++].n_seeds;
-            if (c == s.c0 && c < n_chains) acc += chains[c++].n_seeds;
-            s.c1 = c;
-        }
-        while (!sub.empty() && sub.back().c0 == sub.back().c1) sub.pop_back();
-        K = sub.size();
-    }
-    uint64_t lane_bytes = 0;
-    for (Sub &s : sub) {
-        s.rmin = 0xffffffffu; s.rmax = 0; s.smin = (size_t)-1; s.smax = 0; s.est = (size_t)1 << 18;
-        for (size_t c = s.c0; c < s.c1; c++) {
-            const lf_chain &ch = chains[c];
-            if (ch.read_id < s.rmin) s.rmin = ch.read_id;
-            if (ch.read_id > s.rmax) s.rmax = ch.read_id;
-            if (ch.seed_off < s.smin) s.smin = (size_t)ch.seed_off;
-            if (ch.seed_off + ch.n_seeds > s.smax) s.smax = (size_t)(ch.seed_off + ch.n_seeds);
-            s.est += (size_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);   /* ~0.55 B of CIGAR + MD per aligned read base at 13 % error */
-        }
-        lane_bytes += reads->offsets[s.rmax + 1] - reads->offsets[s.rmin];
-    }
-    if (ndev == 1 && lane_bytes > reads->offsets[reads->n_reads] + reads->offsets[reads->n_reads] / 3)   /* chains not in read order: every lane would upload most of the reads */
-        return align_chains_one(ctx, reads, contigs, seeds, chains, n_chains, pac_host, out, nullptr);
+    ChainScratch &S = chain_scratch(ctx);
+    if (!S.workers) S.workers = new LfWorkers();
+    struct WorkersScope { LfWorkers *prev; WorkersScope(LfWorkers *w) : prev(tl_workers) { tl_workers = w; } ~WorkersScope() { tl_workers = prev; } } workers_scope(S.workers);
     unsigned nthreads = std::thread::hardware_concurrency();
     {
         const char *e = getenv("LF_HOST_THREADS"), *lw = getenv("LOCAL_WORLD_SIZE");
         if (e && atoi(e) > 0) nthreads = (unsigned)atoi(e);
         else if (lw && atoi(lw) > 1) nthreads = nthreads / (unsigned)atoi(lw);
+    }
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+
+    /* ---- which chains go to the slow lane ---- */
+    std::vector<uint8_t> slow(n_chains, 0);
+    const bool want_slow = K >= 2 && !(getenv("LF_CHAIN_SLOW_LANE") && atoi(getenv("LF_CHAIN_SLOW_LANE")) == 0);
+    size_t n_slow = 0;
+    if (want_slow) {
+        parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
+            for (size_t c = lo; c < hi; c++) {
+                const lf_chain &ch = chains[c];
+                const lf_seed *s = seeds + ch.seed_off;
+                const uint32_t n = ch.n_seeds;
+                const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
+                bool sl = s[0].qPos > 256u || (int64_t)readLen - (int64_t)(s[n - 1].qPos + s[n - 1].len) > 256;
+                for (uint32_t i = 0; i + 1 < n && !sl; i++) {
+                    const int64_t ql = (int64_t)s[i + 1].qPos - (int64_t)(s[i].qPos + s[i].len), tl = (int64_t)s[i + 1].tPos - (int64_t)(s[i].tPos + s[i].len);
+                    sl = ql > 256 || tl > 384 || (ql > 0 && tl > 0 && (ql - tl >= kSplitLen || tl - ql >= kSplitLen));
+                }
+                slow[c] = sl ? 1 : 0;
+            }
+        }, 1024);
+        for (size_t c = 0; c < n_chains; c++) n_slow += slow[c];
+        if (n_slow * 3 > n_chains || n_slow == 0) { n_slow = 0; std::fill(slow.begin(), slow.end(), 0); }   /* mostly slow chains: plain consecutive lanes */
+    }
+    const bool have_slow = n_slow > 0;
+    const size_t KF = have_slow ? K - 1 : K;      /* fast lanes */
+
+    struct Sub {
+        std::vector<uint32_t> ids;       /* global index of the lane's chains, ascending */
+        std::vector<lf_chain> ch;        /* ... re-based to the lane's reads and seeds */
+        std::vector<lf_seed> own_seeds;  /* slow lane: its chains' seeds, gathered */
+        const lf_seed *seeds = nullptr;
+        lf_reads rd; size_t est = (size_t)1 << 18;
+        const uint8_t *src = nullptr; uint64_t nbytes = 0; uint64_t *offs = nullptr;
+        lf_chain_results *R = nullptr; int rc = 0; LaneIO io;
+    };
+    std::vector<Sub> sub(K);
+    /* fast lanes: consecutive chains, balanced by seeds */
+    {
+        uint64_t total = 0;
+        for (size_t c = 0; c < n_chains; c++) if (!slow[c]) total += chains[c].n_seeds;
+        size_t c = 0; uint64_t acc = 0;
+        for (size_t k = 0; k < KF; k++) {
+            Sub &s = sub[(have_slow ? 1 : 0) + k];
+            const uint64_t target = total * (k + 1) / KF;
+            while (c < n_chains && (acc < target || k + 1 == KF)) { if (!slow[c]) { s.ids.push_back((uint32_t)c); acc += chains[c].n_seeds; } c++; }
+        }
+        if (have_slow) for (size_t cc = 0; cc < n_chains; cc++) if (slow[cc]) sub[0].ids.push_back((uint32_t)cc);
+    }
+    {   /* drop empty lanes */
+        std::vector<Sub> keep;
+        for (Sub &s : sub) if (!s.ids.empty()) keep.push_back(std::move(s));
+        sub.swap(keep);
+        K = sub.size();
+    }
+    /* ---- per lane: reads it touches, chains re-based, upload source ---- */
+    size_t noff = 0;
+    uint64_t lane_bytes = 0, slow_bytes = 0;
+    std::vector<uint32_t> slow_rid;                 /* slow lane: the distinct reads of its chains, ascending */
+    for (size_t k = 0; k < K; k++) {
+        Sub &s = sub[k];
+        const bool is_slow = have_slow && k == 0;
+        if (is_slow) {
+            std::vector<uint32_t> r;
+            r.reserve(s.ids.size());
+            for (uint32_t c : s.ids) r.push_back(chains[c].read_id);
+            std::sort(r.begin(), r.end());
+            r.erase(std::unique(r.begin(), r.end()), r.end());
+            slow_rid.swap(r);
+            for (uint32_t rid : slow_rid) slow_bytes += reads->offsets[rid + 1] - reads->offsets[rid];
+            s.nbytes = slow_bytes; s.rd.n_reads = (uint32_t)slow_rid.size();
+            noff += slow_rid.size() + 1;
+        } else {
+            uint32_t rmin = 0xffffffffu, rmax = 0;
+            for (uint32_t c : s.ids) { const uint32_t r = chains[c].read_id; if (r < rmin) rmin = r; if (r > rmax) rmax = r; }
+            s.src = reads->bases + reads->offsets[rmin];
+            s.nbytes = reads->offsets[rmax + 1] - reads->offsets[rmin];
+            s.rd.n_reads = rmax - rmin + 1;
+            s.rd.bases = s.src;
+            s.est = rmin;   /* parked: first read of the lane */
+            noff += (size_t)s.rd.n_reads + 1;
+            lane_bytes += s.nbytes;
+        }
+    }
+    if (ndev == 1 && lane_bytes > reads->offsets[reads->n_reads] + reads->offsets[reads->n_reads] / 3)   /* chains not in read order: every lane would upload most of the reads */
+        return align_chains_one(ctx, reads, contigs, seeds, chains, n_chains, pac_host, out, nullptr);
+    uint64_t *offs = (uint64_t *)S.meta_stage.reserve(noff * 8 + 64);
+    uint8_t *slow_stage = have_slow ? (uint8_t *)S.t1.reserve((size_t)slow_bytes + 64) : nullptr;
+    if (!offs || (have_slow && !slow_stage)) return LF_ERR_NOMEM;
+    {
+        size_t o = 0;
+        for (size_t k = 0; k < K; k++) {
+            Sub &s = sub[k];
+            const bool is_slow = have_slow && k == 0;
+            s.offs = offs + o;
+            s.ch.resize(s.ids.size());
+            if (is_slow) {
+                uint64_t b = 0;
+                for (size_t i = 0; i < slow_rid.size(); i++) { s.offs[i] = b; b += reads->offsets[slow_rid[i] + 1] - reads->offsets[slow_rid[i]]; }
+                s.offs[slow_rid.size()] = b;
+                parallel_for(slow_rid.size(), nthreads, [&](unsigned, size_t lo, size_t hi) {
+                    for (size_t i = lo; i < hi; i++) memcpy(slow_stage + s.offs[i], reads->bases + reads->offsets[slow_rid[i]], (size_t)(s.offs[i + 1] - s.offs[i]));
+                }, 64);
+                s.src = slow_stage; s.rd.bases = slow_stage;
+                size_t ns = 0;
+                for (uint32_t c : s.ids) ns += chains[c].n_seeds;
+                s.own_seeds.resize(ns);
+                size_t so = 0;
+                s.est = (size_t)1 << 18;
+                for (size_t i = 0; i < s.ids.size(); i++) {
+                    const lf_chain &g = chains[s.ids[i]];
+                    memcpy(s.own_seeds.data() + so, seeds + g.seed_off, (size_t)g.n_seeds * sizeof(lf_seed));
+                    lf_chain &ch = s.ch[i];
+                    ch = g; ch.seed_off = so;
+                    ch.read_id = (uint32_t)(std::lower_bound(slow_rid.begin(), slow_rid.end(), g.read_id) - slow_rid.begin());
+                    so += g.n_seeds;
+                    s.est += (size_t)(reads->offsets[g.read_id + 1] - reads->offsets[g.read_id]);
+                }
+                s.seeds = s.own_seeds.data();
+                o += slow_rid.size() + 1;
+            } else {
+                const uint32_t rmin = (uint32_t)s.est;
+                const uint64_t b0 = reads->offsets[rmin];
+                for (uint32_t r = 0; r <= s.rd.n_reads; r++) s.offs[r] = reads->offsets[rmin + r] - b0;
+                uint64_t smin = (uint64_t)-1;
+                for (uint32_t c : s.ids) if (chains[c].seed_off < smin) smin = chains[c].seed_off;
+                s.est = (size_t)1 << 18;
+                for (size_t i = 0; i < s.ids.size(); i++) {
+                    const lf_chain &g = chains[s.ids[i]];
+                    lf_chain &ch = s.ch[i];
+                    ch = g; ch.seed_off = g.seed_off - smin; ch.read_id = g.read_id - rmin;
+                    s.est += (size_t)(reads->offsets[g.read_id + 1] - reads->offsets[g.read_id]);   /* ~0.55 B of CIGAR + MD per aligned read base at 13 % error */
+                }
+                s.seeds = seeds + smin;
+                o += (size_t)s.rd.n_reads + 1;
+            }
+            s.rd.offsets = s.offs;
+        }
     }
     /* ---- one text buffer for the whole call, a slice per lane ---- */
     size_t arena_bytes = 0;
@@ -1362,42 +1539,28 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     size_t arena_cap = 0;
     char *arena = (char *)g_result_pool_pinned.get(arena_bytes + 1, &arena_cap);
     if (!arena) return LF_ERR_NOMEM;
-    ChainScratch &S = chain_scratch(ctx);
-    /* ---- the reads of every lane, in lane order, on the parent's stream of the lane's device ---- */
-    size_t noff = 0;
-    for (Sub &s : sub) noff += (size_t)(s.rmax - s.rmin) + 2;
-    uint64_t *offs = (uint64_t *)S.meta_stage.reserve(noff * 8 + 64);
-    if (!offs) { g_result_pool_pinned.put(arena, arena_cap); return LF_ERR_NOMEM; }
+    trace_ref(ctx->devs[0].stream);
+    /* ---- the reads of every lane, in lane order (slow lane first), on the parent's stream of the lane's device ---- */
     int rc = LF_OK;
-    {
-        size_t o = 0;
-        for (size_t k = 0; k < K && rc == LF_OK; k++) {
-            Sub &s = sub[k];
-            lf_gpu_ctx *lc = lane_ctx(ctx, k);
-            if (!lc) { rc = LF_ERR_NOMEM; break; }
-            DevState &pd = ctx->devs[k % ndev], &d = lc->devs[0];
-            const uint32_t nr = s.rmax - s.rmin + 1;
-            const uint64_t b0 = reads->offsets[s.rmin], nb = reads->offsets[s.rmax + 1] - b0;
-            uint64_t *lo = offs + o;
-            for (uint32_t r = 0; r <= nr; r++) lo[r] = reads->offsets[s.rmin + r] - b0;
-            o += (size_t)nr + 1;
-            s.rd.bases = reads->bases + b0; s.rd.offsets = lo; s.rd.n_reads = nr;
-            s.ch.assign(chains + s.c0, chains + s.c1);
-            for (lf_chain &ch : s.ch) { ch.read_id -= s.rmin; ch.seed_off -= s.smin; }
-            s.io.arena = arena; s.io.nthreads = nthreads / (unsigned)K ? nthreads / (unsigned)K : 1u;
-            if (set_dev(d) || d.bases.reserve(nb + 64) || d.read_off.reserve(((size_t)nr + 1) * 8)
-                || lfb_h2d(d.bases.p, s.rd.bases, nb, pd.stream) || lfb_h2d(d.read_off.p, lo, ((size_t)nr + 1) * 8, pd.stream)) { rc = LF_ERR_CUDA; break; }
+    for (size_t k = 0; k < K && rc == LF_OK; k++) {
+        Sub &s = sub[k];
+        lf_gpu_ctx *lc = lane_ctx(ctx, k);
+        if (!lc) { rc = LF_ERR_NOMEM; break; }
+        DevState &pd = ctx->devs[k % ndev], &d = lc->devs[0];
+        const uint32_t nr = s.rd.n_reads;
+        s.io.arena = arena; s.io.nthreads = nthreads / (unsigned)K ? nthreads / (unsigned)K : 1u;
+        if (set_dev(d) || d.bases.reserve((size_t)s.nbytes + 64) || d.read_off.reserve(((size_t)nr + 1) * 8)
+            || lfb_h2d(d.bases.p, s.src, (size_t)s.nbytes, pd.stream) || lfb_h2d(d.read_off.p, s.offs, ((size_t)nr + 1) * 8, pd.stream)) { rc = LF_ERR_CUDA; break; }
 #ifndef LF_EMU
-            cudaEventRecord(d.up_ev, pd.stream);
+        cudaEventRecord(d.up_ev, pd.stream);
 #endif
-            d.reads_preloaded = true;
-        }
+        d.reads_preloaded = true;
     }
     /* ---- the lanes, a host thread each ---- */
     if (rc == LF_OK) {
         auto run_lane = [&](size_t k) {
             Sub &s = sub[k];
-            s.rc = align_chains_one(ctx->lanes[k], &s.rd, contigs, seeds + s.smin, s.ch.data(), s.ch.size(), pac_host, &s.R, &s.io);
+            s.rc = align_chains_one(ctx->lanes[k], &s.rd, contigs, s.seeds, s.ch.data(), s.ch.size(), pac_host, &s.R, &s.io);
         };
 #ifndef LF_EMU
         std::vector<std::thread> th;
@@ -1410,12 +1573,13 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         for (size_t k = 0; k < K; k++) if (sub[k].rc != LF_OK && rc == LF_OK) { rc = sub[k].rc; ctx->err = "lane " + std::to_string(k) + ": " + ctx->lanes[k]->err; }
     }
     for (size_t k = 0; k < ctx->lanes.size(); k++) ctx->lanes[k]->devs[0].reads_preloaded = false;
+    trace_print();
     if (rc != LF_OK) {
         for (Sub &s : sub) delete s.R;
         g_result_pool_pinned.put(arena, arena_cap);
         return rc;
     }
-    /* ---- merge: records in chain order (lane order), text already in place ---- */
+    /* ---- merge: records in chain order, text already in place ---- */
     lf_chain_results *R = new lf_chain_results();
     memset(&R->stats, 0, sizeof R->stats);
     R->pinned = true;
@@ -1441,14 +1605,18 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         g_result_pool_pinned.put(arena, arena_cap);
         arena = nt; arena_cap = cap; text_end = total;
     } else for (Sub &s : sub) if (s.R->text_bytes && s.io.off + s.R->text_bytes > text_end) text_end = s.io.off + s.R->text_bytes;
-    size_t o = 0;
-    for (Sub &s : sub) {
-        for (size_t i = 0; i < s.R->n_recs; i++) { lf_sam_record r = s.R->recs[i]; r.chain_id += (uint32_t)s.c0; R->recs[o++] = r; }
-        const lf_chain_stats &a = s.R->stats;
-        R->stats.round1_tasks += a.round1_tasks; R->stats.round2_extends += a.round2_extends; R->stats.round3_tasks += a.round3_tasks; R->stats.records += a.records;
-        R->stats.ms_tasks = std::max(R->stats.ms_tasks, a.ms_tasks); R->stats.ms_round1 = std::max(R->stats.ms_round1, a.ms_round1);
-        R->stats.ms_rounds23 = std::max(R->stats.ms_rounds23, a.ms_rounds23); R->stats.ms_emit = std::max(R->stats.ms_emit, a.ms_emit); R->stats.ms_merge = std::max(R->stats.ms_merge, a.ms_merge);
-        delete s.R;
+    {   /* every lane's records are ascending in chain index; a lane's chains are a subset of the call's: merge by global index */
+        std::vector<uint32_t> first(n_chains + 1, 0);   /* records per chain -> where each chain's records start */
+        for (Sub &s : sub) for (size_t i = 0; i < s.R->n_recs; i++) first[s.ids[s.R->recs[i].chain_id] + 1]++;
+        for (size_t c = 0; c < n_chains; c++) first[c + 1] += first[c];
+        for (Sub &s : sub) {
+            for (size_t i = 0; i < s.R->n_recs; i++) { lf_sam_record r = s.R->recs[i]; r.chain_id = s.ids[r.chain_id]; R->recs[first[r.chain_id]++] = r; }
+            const lf_chain_stats &a = s.R->stats;
+            R->stats.round1_tasks += a.round1_tasks; R->stats.round2_extends += a.round2_extends; R->stats.round3_tasks += a.round3_tasks; R->stats.records += a.records;
+            R->stats.ms_tasks = std::max(R->stats.ms_tasks, a.ms_tasks); R->stats.ms_round1 = std::max(R->stats.ms_round1, a.ms_round1);
+            R->stats.ms_rounds23 = std::max(R->stats.ms_rounds23, a.ms_rounds23); R->stats.ms_emit = std::max(R->stats.ms_emit, a.ms_emit); R->stats.ms_merge = std::max(R->stats.ms_merge, a.ms_merge);
+            delete s.R;
+        }
     }
     R->n_recs = nrec;
     R->text = arena; R->text_cap = arena_cap; R->text_bytes = text_end;

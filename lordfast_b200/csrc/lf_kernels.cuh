@@ -273,6 +273,17 @@ __device__ __forceinline__ void lf_q32(const LfDev &d, const LfQView &v, int64_t
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* k_copy16: host (pinned, mapped) -> device copy done by a kernel                             */
+/* ------------------------------------------------------------------------------------------ */
+/* The small uploads of a call (seeds, per-chain metadata, follow-up task lists) must not queue in the copy engine
+ * behind the hundreds of MB of reads the other lanes of the call have in flight: a kernel reads the pinned source
+ * over PCIe itself.  16-byte units; both pointers 16-byte aligned. */
+__global__ void __launch_bounds__(256) k_copy16(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* k_pack_reads                                                                               */
 /* ------------------------------------------------------------------------------------------ */
 __global__ void k_pack_reads(LfDev d)
@@ -1378,6 +1389,126 @@ __global__ void k_extend_prep(LfExtDev d, uint32_t *scr_items)
  * column and the column one ring length later are then never live together; columns are initialised with the
  * first-row values, ksw.c:395-397, when the band first reaches them), else the task's global scratch. */
 #define LF_KSW_RING 256
+/* Row loop of ksw_extend2 (ksw.c:416-470) with C consecutive columns per lane; eh[] is the shared-memory ring.  Same
+ * arithmetic, band, exits and stale-cell behaviour as the generic loop in k_ksw_extend, cell for cell. */
+template <int C, typename FirstRow>
+__device__ __forceinline__ void lf_ksw_rows_blk(int2 *eh, const uint8_t *qcode, LfTCursor &tcur, int qlen, int tlen, int w, int h0, int o_del, int e_del,
+                                                int oe_del, int oe_ins, int e_ins, int zdrop, int smatch, int smis, const FirstRow &first_row,
+                                                int &best, int &best_i, int &best_j)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    const uint32_t jm = (uint32_t)(LF_KSW_RING - 1);
+    const int NEG = -(1 << 29);
+    int beg = 0, end = qlen, hi_init = 0;
+    for (int r = 0; r < tlen; r++) {
+        const uint32_t tc = tcur.next();
+        if (beg < r - w) beg = r - w;
+        if (end > r + w + 1) end = r + w + 1;
+        if (end > qlen) end = qlen;
+        if (hi_init < end) {
+            for (int j = hi_init + lane; j < end; j += 32) eh[(uint32_t)j & jm] = first_row(j);
+            hi_init = end;
+            __syncwarp();
+        }
+        int h1 = 0;
+        if (beg == 0) { h1 = h0 - (o_del + e_del * (r + 1)); if (h1 < 0) h1 = 0; }
+        const int width = end - beg;            /* <= 2w + 1 <= 32 C */
+        const int rr0 = lane * C;
+        int M[C], e[C], g[C];
+        int agg = NEG;                          /* max over the lane's cells of g + (rr + 1) e_ins */
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const int rr = rr0 + k, j = beg + rr;
+            M[k] = 0; e[k] = 0; g[k] = 0;
+            if (rr < width) {
+                const int2 c = eh[(uint32_t)j & jm];
+                const uint32_t qc = qcode[j];
+                const int sc = qc > 3u ? 0 : (qc == tc ? smatch : smis);
+                M[k] = c.x ? c.x + sc : 0;
+                e[k] = c.y;
+                int t = M[k] - oe_ins; t = t > 0 ? t : 0;
+                g[k] = t;
+                const int v = t + (rr + 1) * e_ins;
+                agg = v > agg ? v : agg;
+            }
+        }
+        int incl = agg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(LF_FULL, incl, o); if (lane >= o && x > incl) incl = x; }
+        int excl = __shfl_up_sync(LF_FULL, incl, 1);
+        int f = lane == 0 ? 0 : excl - rr0 * e_ins;   /* F of the lane's first cell (excl >= rr0 e_ins whenever a cell precedes it) */
+        if (lane != 0 && excl == NEG) f = 0;
+        int h[C], en[C];
+        int lmax = -1, lmax_k = 0;
+        uint32_t nzmask = 0;
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const int rr = rr0 + k;
+            int hh = M[k] > e[k] ? M[k] : e[k];
+            hh = hh > f ? hh : f;
+            h[k] = hh;
+            if (rr < width) {
+                if (hh >= lmax) { lmax = hh; lmax_k = k; }
+                int t = M[k] - oe_del; t = t > 0 ? t : 0;
+                int x = e[k] - e_del; x = x > t ? x : t;
+                en[k] = x;
+            } else en[k] = 0;
+            const int fn = f - e_ins;
+            f = fn > g[k] ? fn : g[k];
+        }
+        /* H of the previous column of this row, for the diagonal feed of the next row */
+        int nact = width - rr0; nact = nact < 0 ? 0 : nact > C ? C : nact;   /* the lane's active cells */
+        int mylast = h1;
+#pragma unroll
+        for (int k = 0; k < C; k++) if (k == nact - 1) mylast = h[k];
+        int prevlast = __shfl_up_sync(LF_FULL, mylast, 1);
+        if (lane == 0) prevlast = h1;
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const int rr = rr0 + k, j = beg + rr;
+            const int hprev = k == 0 ? prevlast : h[k - 1];
+            if (rr < width) {
+                eh[(uint32_t)j & jm] = int2{hprev, en[k]};
+                if (hprev != 0 || en[k] != 0) nzmask |= 1u << k;
+            }
+        }
+        /* row maximum, ties to the later column (ksw.c:437); cells that stay non-zero (ksw.c:466-469) */
+        const int rowmax_all = lf_warp_max(lmax);
+        int rowmax = 0, rowmax_j = -1;
+        if (rowmax_all >= 0) {
+            const uint32_t bal = __ballot_sync(LF_FULL, nact > 0 && lmax == rowmax_all);
+            const int src = 31 - __clz((int)bal);
+            rowmax = rowmax_all;
+            rowmax_j = beg + __shfl_sync(LF_FULL, rr0 + lmax_k, src);
+        }
+        const uint32_t nzb = __ballot_sync(LF_FULL, nzmask != 0u);
+        int first_nz = -1, last_nz = -1;
+        if (nzb) {
+            const int lf = __ffs((int)nzb) - 1, ll = 31 - __clz((int)nzb);
+            const int kf = __ffs((int)nzmask) - 1, kl = 31 - __clz((int)nzmask);
+            first_nz = beg + __shfl_sync(LF_FULL, rr0 + kf, lf);
+            last_nz = beg + __shfl_sync(LF_FULL, rr0 + kl, ll);
+        }
+        const int h_last = __shfl_sync(LF_FULL, mylast, width > 0 ? (width - 1) / C : 0);
+        if (lane == 0) eh[(uint32_t)end & jm] = int2{width > 0 ? h_last : h1, 0};
+        if (hi_init < end + 1) hi_init = end + 1;
+        __syncwarp();
+        if (rowmax == 0) break;
+        if (rowmax > best) { best = rowmax; best_i = r; best_j = rowmax_j; }
+        else if (zdrop > 0) {
+            const int di = r - best_i, dj = rowmax_j - best_j;
+            if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) break; }
+            else { if (best - rowmax - (dj - di) * e_ins > zdrop) break; }
+        }
+        const int hl = width > 0 ? h_last : h1;
+        if (hl != 0) last_nz = end;
+        const int nbeg = first_nz >= 0 ? first_nz : end;
+        const int jl = last_nz >= nbeg ? last_nz : nbeg - 1;
+        beg = nbeg;
+        end = jl + 2 < qlen ? jl + 2 : qlen;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
 {
     const int lane = threadIdx.x & 31;
@@ -1435,87 +1566,96 @@ __global__ void __launch_bounds__(128) k_ksw_extend(LfExtDev d)
     int best = h0, best_i = -1, best_j = -1, beg = 0, end = qlen;
     LfTCursor tcur;
     tcur.init(d.pac, t0, tdir);
+    /* Bands of up to 96 / 224 columns (the clip and split parameter sets: w = 40 / 100): every lane owns C consecutive
+     * columns of the row, so a row is one round -- one prefix-max scan, one row-maximum reduction, two ballots -- instead
+     * of one round per 32 columns; the per-task latency of a junk tail (as many rows as the tail is long) is what the
+     * chain operator's round 2 waits for. */
+    const int bandw = 2 * w + 1;
+    if (ring && bandw <= 96) lf_ksw_rows_blk<3>(eh, qcode, tcur, qlen, tlen, w, h0, o_del, e_del, oe_del, oe_ins, e_ins, zdrop, smatch, smis, first_row, best, best_i, best_j);
+    else if (ring && bandw <= 224) lf_ksw_rows_blk<7>(eh, qcode, tcur, qlen, tlen, w, h0, o_del, e_del, oe_del, oe_ins, e_ins, zdrop, smatch, smis, first_row, best, best_i, best_j);
+    else {
     for (int r = 0; r < tlen; r++) {
-        const uint32_t tc = tcur.next();
-        if (beg < r - w) beg = r - w;
-        if (end > r + w + 1) end = r + w + 1;
-        if (end > qlen) end = qlen;
-        if (ring && hi_init < end) {
-            for (int j = hi_init + lane; j < end; j += 32) eh[(uint32_t)j & jm] = first_row(j);
-            hi_init = end;
+            const uint32_t tc = tcur.next();
+            if (beg < r - w) beg = r - w;
+            if (end > r + w + 1) end = r + w + 1;
+            if (end > qlen) end = qlen;
+            if (ring && hi_init < end) {
+                for (int j = hi_init + lane; j < end; j += 32) eh[(uint32_t)j & jm] = first_row(j);
+                hi_init = end;
+                __syncwarp();
+            }
+            int h1 = 0;
+            if (beg == 0) { h1 = h0 - (o_del + e_del * (r + 1)); if (h1 < 0) h1 = 0; }
+            int carry_u = 0;            /* u = F + (j-beg)*e_ins at the start of the round; F(i,beg) = 0 */
+            int prev_h = h1;            /* H(i, j-1) for the first lane of the round */
+            int rowmax = 0, rowmax_j = -1, first_nz = -1, last_nz = -1, h_last = h1;
+            const int width = end - beg;
+            for (int k0 = 0; k0 < width; k0 += 32) {
+                const int rr = k0 + lane, j = beg + rr;
+                const bool act = rr < width;
+                int M = 0, e = 0;
+                if (act) {
+                    const int2 c = eh[(uint32_t)j & jm];
+                    const uint32_t qc = qcode[j];
+                    const int sc = qc > 3u ? 0 : (qc == tc ? smatch : smis);
+                    M = c.x ? c.x + sc : 0;
+                    e = c.y;
+                }
+                int g = M - oe_ins; g = g > 0 ? g : 0;
+                const int v = act ? g + (rr + 1) * e_ins : NEG;
+                int incl = v;
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(LF_FULL, incl, o); if (lane >= o && x > incl) incl = x; }
+                int excl = __shfl_up_sync(LF_FULL, incl, 1);
+                if (lane == 0) excl = NEG;
+                const int u = carry_u > excl ? carry_u : excl;
+                const int f = u - rr * e_ins;
+                const int tot = __shfl_sync(LF_FULL, incl, 31);
+                carry_u = carry_u > tot ? carry_u : tot;
+                int h = M > e ? M : e;
+                h = h > f ? h : f;
+                if (!act) h = -1;
+                int hprev = __shfl_up_sync(LF_FULL, h, 1);
+                if (lane == 0) hprev = prev_h;
+                int en = 0;
+                if (act) {
+                    int tt = M - oe_del; tt = tt > 0 ? tt : 0;
+                    en = e - e_del; en = en > tt ? en : tt;
+                    eh[(uint32_t)j & jm] = int2{hprev, en};
+                }
+                /* row maximum, ties to the later column (ksw.c:437) */
+                const int mk = lf_warp_max(h);
+                if (mk >= rowmax && mk >= 0) {
+                    const uint32_t bal = __ballot_sync(LF_FULL, act && h == mk);
+                    rowmax_j = beg + k0 + (31 - __clz((int)bal));
+                    rowmax = mk;
+                }
+                /* cells that stay non-zero, for the band re-trim (ksw.c:466-469) */
+                const uint32_t nzb = __ballot_sync(LF_FULL, act && (hprev != 0 || en != 0));
+                if (nzb) {
+                    if (first_nz < 0) first_nz = beg + k0 + __ffs((int)nzb) - 1;
+                    last_nz = beg + k0 + (31 - __clz((int)nzb));
+                }
+                const int nact = width - k0 < 32 ? width - k0 : 32;
+                h_last = __shfl_sync(LF_FULL, h, nact - 1);
+                prev_h = h_last;
+            }
+            if (lane == 0) eh[(uint32_t)end & jm] = int2{h_last, 0};
+            if (hi_init < end + 1) hi_init = end + 1;
             __syncwarp();
+            if (rowmax == 0) break;
+            if (rowmax > best) { best = rowmax; best_i = r; best_j = rowmax_j; }
+            else if (zdrop > 0) {
+                const int di = r - best_i, dj = rowmax_j - best_j;
+                if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) break; }
+                else { if (best - rowmax - (dj - di) * e_ins > zdrop) break; }
+            }
+            if (h_last != 0) last_nz = end;
+            const int nbeg = first_nz >= 0 ? first_nz : end;
+            const int jl = last_nz >= nbeg ? last_nz : nbeg - 1;
+            beg = nbeg;
+            end = jl + 2 < qlen ? jl + 2 : qlen;
         }
-        int h1 = 0;
-        if (beg == 0) { h1 = h0 - (o_del + e_del * (r + 1)); if (h1 < 0) h1 = 0; }
-        int carry_u = 0;            /* u = F + (j-beg)*e_ins at the start of the round; F(i,beg) = 0 */
-        int prev_h = h1;            /* H(i, j-1) for the first lane of the round */
-        int rowmax = 0, rowmax_j = -1, first_nz = -1, last_nz = -1, h_last = h1;
-        const int width = end - beg;
-        for (int k0 = 0; k0 < width; k0 += 32) {
-            const int rr = k0 + lane, j = beg + rr;
-            const bool act = rr < width;
-            int M = 0, e = 0;
-            if (act) {
-                const int2 c = eh[(uint32_t)j & jm];
-                const uint32_t qc = qcode[j];
-                const int sc = qc > 3u ? 0 : (qc == tc ? smatch : smis);
-                M = c.x ? c.x + sc : 0;
-                e = c.y;
-            }
-            int g = M - oe_ins; g = g > 0 ? g : 0;
-            const int v = act ? g + (rr + 1) * e_ins : NEG;
-            int incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(LF_FULL, incl, o); if (lane >= o && x > incl) incl = x; }
-            int excl = __shfl_up_sync(LF_FULL, incl, 1);
-            if (lane == 0) excl = NEG;
-            const int u = carry_u > excl ? carry_u : excl;
-            const int f = u - rr * e_ins;
-            const int tot = __shfl_sync(LF_FULL, incl, 31);
-            carry_u = carry_u > tot ? carry_u : tot;
-            int h = M > e ? M : e;
-            h = h > f ? h : f;
-            if (!act) h = -1;
-            int hprev = __shfl_up_sync(LF_FULL, h, 1);
-            if (lane == 0) hprev = prev_h;
-            int en = 0;
-            if (act) {
-                int tt = M - oe_del; tt = tt > 0 ? tt : 0;
-                en = e - e_del; en = en > tt ? en : tt;
-                eh[(uint32_t)j & jm] = int2{hprev, en};
-            }
-            /* row maximum, ties to the later column (ksw.c:437) */
-            const int mk = lf_warp_max(h);
-            if (mk >= rowmax && mk >= 0) {
-                const uint32_t bal = __ballot_sync(LF_FULL, act && h == mk);
-                rowmax_j = beg + k0 + (31 - __clz((int)bal));
-                rowmax = mk;
-            }
-            /* cells that stay non-zero, for the band re-trim (ksw.c:466-469) */
-            const uint32_t nzb = __ballot_sync(LF_FULL, act && (hprev != 0 || en != 0));
-            if (nzb) {
-                if (first_nz < 0) first_nz = beg + k0 + __ffs((int)nzb) - 1;
-                last_nz = beg + k0 + (31 - __clz((int)nzb));
-            }
-            const int nact = width - k0 < 32 ? width - k0 : 32;
-            h_last = __shfl_sync(LF_FULL, h, nact - 1);
-            prev_h = h_last;
-        }
-        if (lane == 0) eh[(uint32_t)end & jm] = int2{h_last, 0};
-        if (hi_init < end + 1) hi_init = end + 1;
-        __syncwarp();
-        if (rowmax == 0) break;
-        if (rowmax > best) { best = rowmax; best_i = r; best_j = rowmax_j; }
-        else if (zdrop > 0) {
-            const int di = r - best_i, dj = rowmax_j - best_j;
-            if (di > dj) { if (best - rowmax - (di - dj) * e_del > zdrop) break; }
-            else { if (best - rowmax - (dj - di) * e_ins > zdrop) break; }
-        }
-        if (h_last != 0) last_nz = end;
-        const int nbeg = first_nz >= 0 ? first_nz : end;
-        const int jl = last_nz >= nbeg ? last_nz : nbeg - 1;
-        beg = nbeg;
-        end = jl + 2 < qlen ? jl + 2 : qlen;
     }
     out.score = best; out.qle = best_j + 1; out.tle = best_i + 1;
     if (lane == 0) d.res[i] = out;

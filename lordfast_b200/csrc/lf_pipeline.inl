@@ -48,6 +48,8 @@ struct DevState {
     size_t task_first = 0; uint32_t n_tasks = 0; uint64_t ops_words = 0;
     size_t etask_first = 0; uint32_t n_etasks = 0;
     bool ran = false;
+    std::vector<std::pair<void *, size_t>> stage_chunks;   /* pinned staging for h2d_k from pageable sources, recycled per call */
+    size_t stage_chunk = 0, stage_used = 0;
     bool pac_borrowed = false;      /* a lane of lf_gpu_align_chains: the reference belongs to the parent context's DevState */
     lfb_event up_ev = 0;            /* lane: its reads have arrived (recorded on the parent's upload stream) */
     bool reads_preloaded = false;   /* lane: the parent has enqueued the H2D copy of the reads; upload_reads only waits and packs */
@@ -131,6 +133,41 @@ LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
 size_t align_up(size_t v, size_t a);
 LfLargeCfg large_cfg(size_t mq, size_t mt, size_t max_planes);
 
+/* Pinned staging of one call: regions stay valid until stage_reset() at the start of the next call. */
+void stage_reset(DevState &d) { d.stage_chunk = 0; d.stage_used = 0; }
+void *stage_get(DevState &d, size_t n)
+{
+    n = (n + 63) & ~(size_t)63;
+    while (d.stage_chunk < d.stage_chunks.size()) {
+        auto &c = d.stage_chunks[d.stage_chunk];
+        if (d.stage_used + n <= c.second) { void *p = (char *)c.first + d.stage_used; d.stage_used += n; return p; }
+        d.stage_chunk++; d.stage_used = 0;
+    }
+    const size_t cap = n > ((size_t)4 << 20) ? n : ((size_t)4 << 20);
+    void *p = lfb_host_alloc(cap);
+    if (!p) return nullptr;
+    d.stage_chunks.push_back({p, cap});
+    d.stage_chunk = d.stage_chunks.size() - 1; d.stage_used = n;
+    return p;
+}
+/* Upload of n bytes by kernel (k_copy16) on stream s.  src_pinned: src is pinned host memory, 16-byte aligned and readable
+ * up to the next multiple of 16; else it is staged.  dst: a device buffer with 16 bytes of slack. */
+int h2d_k(DevState &d, void *dst, const void *src, size_t n, lfb_stream s, bool src_pinned)
+{
+    if (!n) return 0;
+    if (!src_pinned || ((uintptr_t)src & 15u)) {
+        void *st = stage_get(d, n + 16);
+        if (!st) return -5;
+        memcpy(st, src, n);
+        src = st;
+    }
+    const size_t n16 = (n + 15) >> 4;
+    unsigned grid = (unsigned)((n16 + 255) / 256);
+    if (grid > 296u) grid = 296u;
+    LFB_LAUNCH(k_copy16, grid, 256, 0, s, (uint4 *)dst, (const uint4 *)src, n16);
+    return 0;
+}
+
 template <int CI, bool SHW>
 void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, const uint32_t *retry_count)
 {
@@ -167,29 +204,32 @@ void launch_group(const LfDev &v, const uint32_t *order, uint32_t first, uint32_
     auto kern = k_myers_group<LANES, WPL, PATH>;
     LFB_LAUNCH(kern, blocks, 128, 0, s, v, order, first, count, run);
 }
-/* lanes per task, words per lane and path / distance-only of a k_myers_group class */
+/* lanes per task, words per lane and path / distance-only of a k_myers_group class.  wide: a class with few tasks gives
+ * every task a whole warp (or half of one) -- the step waits for its longest task, and 400 inversion-sized tasks on 8 lanes
+ * each took 1.4 ms of a 1.9 ms step; with many tasks (the config-5 sweep) the narrow shape is the efficient one
+ * (15 instead of 19-24 instructions per word-column). */
 struct GroupShape { int lanes, wpl; bool path; };
-GroupShape group_shape(int cls)
+GroupShape group_shape(int cls, bool wide)
 {
     switch (cls) {
-    case LF_CLS_GP16: return GroupShape{4, 4, true};
-    case LF_CLS_GP32: return GroupShape{8, 4, true};
-    case LF_CLS_GP64: return GroupShape{8, 8, true};
-    case LF_CLS_GD32: return GroupShape{8, 4, false};
-    case LF_CLS_GD64: return GroupShape{8, 8, false};
-    case LF_CLS_GD128: return GroupShape{16, 8, false};
+    case LF_CLS_GP16: return wide ? GroupShape{16, 1, true} : GroupShape{4, 4, true};
+    case LF_CLS_GP32: return wide ? GroupShape{32, 1, true} : GroupShape{8, 4, true};
+    case LF_CLS_GP64: return wide ? GroupShape{32, 2, true} : GroupShape{8, 8, true};
+    case LF_CLS_GD32: return wide ? GroupShape{32, 1, false} : GroupShape{8, 4, false};
+    case LF_CLS_GD64: return wide ? GroupShape{32, 2, false} : GroupShape{8, 8, false};
+    case LF_CLS_GD128: return wide ? GroupShape{32, 4, false} : GroupShape{16, 8, false};
     default: return GroupShape{32, 8, false};
     }
 }
-void launch_group_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, const LfGroupRun &run, unsigned blocks)
+void launch_group_class(int cls, bool wide, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, const LfGroupRun &run, unsigned blocks)
 {
     switch (cls) {
-    case LF_CLS_GP16: launch_group<4, 4, true>(v, order, first, count, s, run, blocks); break;
-    case LF_CLS_GP32: launch_group<8, 4, true>(v, order, first, count, s, run, blocks); break;
-    case LF_CLS_GP64: launch_group<8, 8, true>(v, order, first, count, s, run, blocks); break;
-    case LF_CLS_GD32: launch_group<8, 4, false>(v, order, first, count, s, run, blocks); break;
-    case LF_CLS_GD64: launch_group<8, 8, false>(v, order, first, count, s, run, blocks); break;
-    case LF_CLS_GD128: launch_group<16, 8, false>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GP16: if (wide) launch_group<16, 1, true>(v, order, first, count, s, run, blocks); else launch_group<4, 4, true>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GP32: if (wide) launch_group<32, 1, true>(v, order, first, count, s, run, blocks); else launch_group<8, 4, true>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GP64: if (wide) launch_group<32, 2, true>(v, order, first, count, s, run, blocks); else launch_group<8, 8, true>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GD32: if (wide) launch_group<32, 1, false>(v, order, first, count, s, run, blocks); else launch_group<8, 4, false>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GD64: if (wide) launch_group<32, 2, false>(v, order, first, count, s, run, blocks); else launch_group<8, 8, false>(v, order, first, count, s, run, blocks); break;
+    case LF_CLS_GD128: if (wide) launch_group<32, 4, false>(v, order, first, count, s, run, blocks); else launch_group<16, 8, false>(v, order, first, count, s, run, blocks); break;
     case LF_CLS_GD256: launch_group<32, 8, false>(v, order, first, count, s, run, blocks); break;
     default: break;
     }
@@ -401,13 +441,16 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         }
         /* plane scratch of the group path classes: one slot per group of lanes of the persistent grid */
         unsigned gblocks[LF_NCLS] = {};
+        bool gwide[LF_NCLS] = {};
         LfGroupRun grun[LF_NCLS] = {};
+        const uint32_t wide_below = getenv("LF_GROUP_WIDE") ? (uint32_t)atoi(getenv("LF_GROUP_WIDE")) : 0u;   /* class sizes up to this go wide; measured on the config-2 step: off (0) 1.87 ms, 2048 1.99 ms -- the wide shapes run 4x the warps for the same columns and the step is bound by issue slots, not by the longest task */
         {
             size_t off = 0, offs[LF_NCLS] = {};
             for (int cls = LF_CLS_GP16; cls <= LF_CLS_GD256; cls++) {
                 const uint32_t count = ht->cnt.hist[cls];
                 if (!count) continue;
-                const GroupShape gs = group_shape(cls);
+                gwide[cls] = count <= wide_below;
+                const GroupShape gs = group_shape(cls, gwide[cls]);
                 const unsigned per_block = 4u * (32u / (unsigned)gs.lanes);   /* tasks a block works on at a time */
                 unsigned blocks = (count + per_block - 1) / per_block;
                 if (blocks > 148u * 4u) blocks = 148u * 4u;
@@ -434,7 +477,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
-            if (cls >= LF_CLS_GP16) launch_group_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, st, grun[cls], gblocks[cls]);
+            if (cls >= LF_CLS_GP16) launch_group_class(cls, gwide[cls], v, d.idx2.as<uint32_t>(), firsts[cls], count, st, grun[cls], gblocks[cls]);
             else launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, cls < LF_CLS_LARGE ? gc.gbase[cls] : 0u, d.goff.as<unsigned long long>(), st,
                                d.idx.as<uint32_t>() /* input of the sort, free by now */, d.queue.as<uint32_t>() + 1 + cls, bmask);
             if (cls >= LF_CLS_BANDREG0 && cls < LF_CLS_GP16) {   /* the uncertified few: warp per task, on the same stream */
@@ -547,6 +590,8 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
         for (LfbBuf *b : bufs) b->release();
         lfb_free(d.tmp.p);
         lfb_host_free(d.pinned);
+        for (auto &c : d.stage_chunks) lfb_host_free(c.first);
+        d.stage_chunks.clear();
 #ifndef LF_EMU
         for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
         for (int k = 0; k < LF_NSUB; k++) { if (d.sub_ev[k]) cudaEventDestroy(d.sub_ev[k]); if (d.sub[k]) cudaStreamDestroy(d.sub[k]); }
@@ -645,6 +690,17 @@ static lf_align_task *resident_tasks_alloc(lf_gpu_ctx *ctx, size_t n)
     if (d.tasks.reserve((n + 1) * sizeof(lf_align_task))) return nullptr;
     d.task_first = 0; d.n_tasks = (uint32_t)n; d.ran = false;
     return d.tasks.as<lf_align_task>();
+}
+
+/* Chain operator, single-device contexts: the follow-up (round-3) tasks, uploaded by kernel (see k_copy16). */
+static int upload_align_tasks_k(lf_gpu_ctx *ctx, const lf_align_task *tasks, size_t n)
+{
+    DevState &d = ctx->devs[0];
+    if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+    d.task_first = 0; d.n_tasks = (uint32_t)n; d.ran = false;
+    LF_TRY(d.tasks.reserve(n * sizeof(lf_align_task) + 64));
+    LF_TRY(h2d_k(d, d.tasks.p, tasks, n * sizeof(lf_align_task), d.stream, false));
+    return LF_OK;
 }
 
 int lf_gpu_run_align(lf_gpu_ctx *ctx)
@@ -772,10 +828,10 @@ static int spec_extend_start(lf_gpu_ctx *ctx, const lf_extend_task *tasks, size_
     if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
     d.etask_first = 0; d.n_etasks = (uint32_t)n;
     if (!n) return LF_OK;
-    LF_TRY(d.etasks.reserve(n * sizeof(lf_extend_task)));
+    LF_TRY(d.etasks.reserve(n * sizeof(lf_extend_task) + 64));
     /* no wait on the main stream: the caller starts this after lf_gpu_run_align, whose class-count sync has already
      * waited for the reads and tasks to arrive, and waiting now would put the extensions behind the round-1 kernels */
-    LF_TRY(lfb_h2d(d.etasks.p, tasks, n * sizeof(lf_extend_task), d.ext_stream));
+    LF_TRY(h2d_k(d, d.etasks.p, tasks, n * sizeof(lf_extend_task), d.ext_stream, true));   /* `tasks` is the caller's pinned staging */
     size_t bound = 0;
     for (size_t i = 0; i < n; i++) bound += (size_t)tasks[i].q_len + 1u + ((size_t)tasks[i].q_len + 7u) / 8u + 1u;   /* k_extend_prep's figure */
     int rc = run_extend_dev(ctx, d, d.ext_stream, bound);

@@ -29,8 +29,8 @@ def _golden(lib_path):
     g.close()
 
 
-def _simulated(lib_path, n_reads, read_len, ref_len, need_inversion=True):
-    w = sim.make_workload(ref_len, n_reads, read_len, 0.12, 0.15, seed=21, sv_frac=0.6, sv_kinds=sim.SV_KINDS + ("inversion_del", "inversion_del"))
+def _simulated(lib_path, n_reads, read_len, ref_len, need_inversion=True, sv_frac=0.6):
+    w = sim.make_workload(ref_len, n_reads, read_len, 0.12, 0.15, seed=21, sv_frac=sv_frac, sv_kinds=sim.SV_KINDS + ("inversion_del", "inversion_del"))
     g = api.LfGpu(w.pac, len(w.ref), lib_path=lib_path)
     seeds, chains = api.workload_chains(w)
     recs, text, st = g.align_chains(w.reads, w.read_off.astype(np.uint64), w.contig_off, w.contig_len, seeds, chains)
@@ -148,6 +148,26 @@ def test_emu_chain_operator_golden():
 
 def test_emu_chain_operator_simulated():
     _simulated(build_emu(), 14, 3000, 120_000)
+
+
+@pytest.mark.parametrize("lanes,slow", [("3", "1"), ("2", "0")])
+def test_emu_chain_operator_lanes(monkeypatch, lanes, slow):
+    """One call cut into pipelined lanes (lf_chain.inl): the chains that can reach rounds 2 / 3 or hold long tasks go to the
+    slow lane, whose reads are gathered and uploaded first; the others to consecutive fast lanes.  Records come back in
+    chain order whatever the split."""
+    monkeypatch.setenv("LF_CHAIN_LANES", lanes)
+    monkeypatch.setenv("LF_CHAIN_SLOW_LANE", slow)
+    _simulated(build_emu(), 24, 3000, 200_000, need_inversion=False, sv_frac=0.2)
+    _golden(build_emu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes,slow", [("4", "1"), ("3", "0"), ("1", "1")])
+def test_gpu_chain_operator_lanes(monkeypatch, lanes, slow):
+    monkeypatch.setenv("LF_CHAIN_LANES", lanes)
+    monkeypatch.setenv("LF_CHAIN_SLOW_LANE", slow)
+    _simulated(None, 400, 8000, 1_500_000, sv_frac=0.15)
+    _golden(None)
 
 
 def test_emu_chain_operator_host_emit(monkeypatch):

@@ -127,10 +127,12 @@ def test_emu_large_and_hirschberg_tasks(emu_lib):
     g.close()
 
 
-@pytest.mark.parametrize("groupk", ["7", "0", "3"])
-def test_emu_group_classes(emu_lib, monkeypatch, groupk):
-    """k_myers_group (LANES lanes per task) against the oracle; LF_GROUPK=0 routes the same tasks to the older kernels."""
+@pytest.mark.parametrize("groupk,wide", [("7", "2048"), ("7", "0"), ("0", "2048"), ("3", "0")])
+def test_emu_group_classes(emu_lib, monkeypatch, groupk, wide):
+    """k_myers_group (LANES lanes per task) against the oracle, in the narrow shapes (many tasks) and the wide ones (few tasks:
+    LF_GROUP_WIDE is the task count below which a class goes wide); LF_GROUPK=0 routes the same tasks to the older kernels."""
     monkeypatch.setenv("LF_GROUPK", groupk)
+    monkeypatch.setenv("LF_GROUP_WIDE", wide)
     ref, reads, tasks = group_class_batch(big=groupk == "7")
     g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=emu_lib)
     bad, res, _ = check_align(g, reads, ref, tasks)

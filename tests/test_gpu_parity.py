@@ -201,13 +201,14 @@ def test_gpu_full_size_properties():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("groupk", ["7", "0"])
-def test_gpu_group_classes(groupk, monkeypatch):
+@pytest.mark.parametrize("groupk,wide", [("7", "2048"), ("7", "0"), ("0", "2048")])
+def test_gpu_group_classes(groupk, wide, monkeypatch):
     """k_myers_group (LANES lanes per task: path tasks of 257 .. 2048 rows, distance-only tasks up to 8192 rows) on both
     sides of every class boundary, NW / SHW mixed in a warp's bundle; LF_GROUPK=0 sends the same tasks to the older
     kernels.  Bit-exact against the oracle both ways, and the classes really ran."""
     from _common import group_class_batch
     monkeypatch.setenv("LF_GROUPK", groupk)
+    monkeypatch.setenv("LF_GROUP_WIDE", wide)   # task count below which a class gives every task a whole warp
     ref, reads, tasks = group_class_batch()
     g = api.LfGpu(sim.pack_pac(ref), len(ref))
     bad, _, _ = check_align(g, reads, ref, tasks)

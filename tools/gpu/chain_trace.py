@@ -12,8 +12,8 @@ seeds, chains = api.workload_chains(w)
 pb = api.PinnedArray(g.lib, w.reads.nbytes); hb = pb.view(np.uint8, len(w.reads)); hb[:] = w.reads
 ro = w.read_off.astype(np.uint64)
 for it in range(5):
-    if it == 3:
-        os.environ["LF_CHAIN_TRACE"] = "1"
+    if it == 4:
+        os.environ["LF_CHAIN_TRACE"] = os.environ.get("TRACE_LEVEL", "1")
     t0 = time.perf_counter()
     recs, text, st = g.align_chains(hb, ro, w.contig_off, w.contig_len, seeds, chains, want_text=False)
     print("call %d: %.2f ms, %d records" % (it, (time.perf_counter() - t0) * 1e3, len(recs)), flush=True)
