@@ -639,6 +639,8 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     std::vector<uint32_t> cand_ti, cand_ext;   /* speculative round 2: candidate round-1 tasks (ascending) and their first extension */
     std::vector<lf_extend_task> se2;
     lf_extend_result *sx2 = nullptr;
+    /* an early return must not leave the speculative extensions (and their D2H into pinned staging) in flight */
+    struct ExtGuard { lf_gpu_ctx *c; ~ExtGuard() { if (c) { DevState &d = c->devs[0]; if (!set_dev(d)) lfb_sync(d.ext_stream); } } } ext_guard{nullptr};
     const double tt4 = now_ms();
     /* pass B: fill */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
@@ -734,6 +736,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         } else LF_CH(lf_gpu_upload_align_tasks(ctx, t1, n1));
         const double tr0 = now_ms();
         LF_CH(lf_gpu_run_align(ctx));   /* returns once the class kernels are launched (its class-count sync has waited for the uploads) */
+        for (DevState &dd : ctx->devs) if (dd.cls_count[LF_CLS_BAD]) { delete R; return fail(ctx, LF_ERR_BAD_ARG, "a chain yields an alignment task outside its read or the reference"); }
         trace_mark(ctx, "round-1 kernels done", ctx->devs[0].stream);
         if (spec) {
             /* Speculative round 2: the clip / split triggers can only fire for tasks whose LENGTHS qualify (:1840 / :2175
@@ -799,6 +802,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
                 sx2 = (lf_extend_result *)S.x2.reserve((se2.size() + 1) * sizeof(lf_extend_result));
                 if (!pe || !sx2) { delete R; return LF_ERR_NOMEM; }
                 memcpy(pe, se2.data(), se2.size() * sizeof(lf_extend_task));
+                ext_guard.c = ctx;
                 LF_CH(spec_extend_start(ctx, pe, se2.size(), sx2));
                 trace_mark(ctx, "speculative extensions done", ctx->devs[0].ext_stream);
             }
@@ -1043,14 +1047,19 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     lf_align_result *r3 = (lf_align_result *)S.r3.reserve((n3 + 1) * sizeof(lf_align_result));
     uint8_t *ops3 = gpu_emit ? nullptr : (uint8_t *)S.ops3.reserve(cap3 + 64);
     if (!r3 || (!gpu_emit && !ops3)) { delete R; return LF_ERR_NOMEM; }
-    if (gpu_emit) { /* keep the round-1 results and op stream in HBM: round 3 gets its own pair of buffers */
+    /* keep the round-1 results and op stream in HBM: round 3 gets its own pair of buffers; whatever way the call ends,
+     * the pairs are swapped back */
+    struct SwapGuard { DevState *d; ~SwapGuard() { if (d) { std::swap(d->res, d->res_keep); std::swap(d->ops, d->ops_keep); } } } swap_guard{nullptr};
+    if (gpu_emit) {
         DevState &d = ctx->devs[0];
         std::swap(d.res, d.res_keep); std::swap(d.ops, d.ops_keep);
+        swap_guard.d = &d;
     }
     if (n3) {
         if (gpu_emit) LF_CH(upload_align_tasks_k(ctx, t3.data(), n3));
         else LF_CH(lf_gpu_upload_align_tasks(ctx, t3.data(), n3));
         LF_CH(lf_gpu_run_align(ctx));
+        for (DevState &dd : ctx->devs) if (dd.cls_count[LF_CLS_BAD]) { delete R; return fail(ctx, LF_ERR_BAD_ARG, "a follow-up alignment task is outside its read or the reference"); }
         trace_mark(ctx, "round-3 kernels done", ctx->devs[0].stream);
         if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r3, ops3, cap3));
         else { DevState &d = ctx->devs[0]; if (lfb_d2h(r3, d.res.p, n3 * sizeof(lf_align_result), d.stream)) { delete R; return LF_ERR_CUDA; } }
@@ -1146,7 +1155,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
             if (ia < na) { memcpy(R->recs + o, a + ia, (na - ia) * sizeof(lf_sam_record)); o += na - ia; }
             if (ib < nb) { memcpy(R->recs + o, b + ib, (nb - ib) * sizeof(lf_sam_record)); o += nb - ib; }
         }
-        std::swap(d.res, d.res_keep); std::swap(d.ops, d.ops_keep); /* hand the bigger pair back to the next round 1 */
+        /* (swap_guard hands the bigger pair back to the next round 1) */
         ctx->stats.kernel_launches = lfb_launches;
         R->stats.records = nrec;
         const double tm4 = now_ms();
@@ -1361,7 +1370,8 @@ static lf_gpu_ctx *lane_ctx(lf_gpu_ctx *ctx, size_t j)
  *                   are gathered into pinned staging and go to the device FIRST, so that their long chain of dependent
  *                   launches (round 1 with 1 - 2 kbp tasks, extensions, round 3, the walk over long garbage alignments in
  *                   the emit) runs while the bulk of the reads is still crossing PCIe;
- *   the fast lanes  the other chains, as consecutive ranges balanced by seeds; no task above 256 rows, no trigger
+ *   the fast lanes  the other chains, as consecutive ranges balanced by seeds; no task above 512 rows (14 % of a config-2
+ *                   chunk's chains hold one; at 256 rows it would be 86 %), no trigger
  *                   candidate, so a lane is upload -> round 1 -> emit.  Their reads follow in lane order on one stream:
  *                   the first lane aligns while the others' reads are in flight, and the CIGAR / MD text of a lane goes
  *                   back over PCIe (k_emit_slots writes it straight to pinned memory) while the next lanes compute.
@@ -1374,9 +1384,12 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
 {
     if (!ctx || !reads || !reads->offsets || !contigs || !seeds || (!chains && n_chains) || !pac_host || !out || contigs->n < 1) return LF_ERR_BAD_ARG;
     const size_t ndev = ctx->devs.size();
-    size_t K = ndev == 1 ? 4 : 2 * ndev;
+    /* One device: one lane by default.  Measured on a config-2 chunk (profiles/r03_e2e_lanes.txt): the dependent launches of a
+     * lane (round 1 with its 1.5 kbp tasks, extensions, round 3, emit) take ~9 ms whatever the batch size, so 2 - 8 lanes
+     * only moved a call from 15.2 to 14.0 - 14.9 ms; callers that want the PCIe link busy keep two calls in flight on two
+     * contexts instead (10.5 ms per chunk).  Several devices: a lane per device. */
+    size_t K = ndev;
     if (const char *e = getenv("LF_CHAIN_LANES")) { if (atoi(e) > 0) K = (size_t)atoi(e); }
-    else { const size_t by_size = n_chains / 1500; if (K > by_size) K = by_size > ndev ? by_size : ndev; }   /* small chunks: the fixed cost of a lane outweighs the overlap */
     if (K > 64) K = 64;
     if (K > n_chains) K = n_chains ? n_chains : 1;
     if (K < 1) K = 1;
@@ -1407,10 +1420,10 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
                 const lf_seed *s = seeds + ch.seed_off;
                 const uint32_t n = ch.n_seeds;
                 const uint32_t readLen = (uint32_t)(reads->offsets[ch.read_id + 1] - reads->offsets[ch.read_id]);
-                bool sl = s[0].qPos > 256u || (int64_t)readLen - (int64_t)(s[n - 1].qPos + s[n - 1].len) > 256;
+                bool sl = s[0].qPos > 512u || (int64_t)readLen - (int64_t)(s[n - 1].qPos + s[n - 1].len) > 512;
                 for (uint32_t i = 0; i + 1 < n && !sl; i++) {
                     const int64_t ql = (int64_t)s[i + 1].qPos - (int64_t)(s[i].qPos + s[i].len), tl = (int64_t)s[i + 1].tPos - (int64_t)(s[i].tPos + s[i].len);
-                    sl = ql > 256 || tl > 384 || (ql > 0 && tl > 0 && (ql - tl >= kSplitLen || tl - ql >= kSplitLen));
+                    sl = ql > 512 || tl > 768 || (ql > 0 && tl > 0 && (ql - tl >= kSplitLen || tl - ql >= kSplitLen));
                 }
                 slow[c] = sl ? 1 : 0;
             }

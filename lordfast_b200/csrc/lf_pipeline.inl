@@ -22,7 +22,9 @@
 #include "lf_backend.h"
 
 #ifndef LF_NSUB
-#define LF_NSUB 24
+#define LF_NSUB 16   /* class streams per context.  24 was marginally better for one context alone (1.87 vs 1.88 ms per config-2 step), but two
+                      * contexts in flight then hold 54 streams on the device's 32 hardware queues and their kernels falsely serialise:
+                      * 14.6 ms per chunk with two lf_gpu_align_chains calls in flight, 10.7 ms with 16 streams each (profiles/r03) */
 #endif
 struct DevState {
     int dev = 0;
@@ -512,6 +514,9 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 static std::mutex g_prewarm_mu;
 static std::thread g_prewarm;
 static bool g_prewarm_started = false;
+/* a process that calls lf_gpu_prewarm() and exits without ever reaching lf_gpu_init() (bad command line, empty input) must
+ * not die in std::terminate() on the still-joinable thread: join it when the library's statics are torn down */
+static struct PrewarmGuard { ~PrewarmGuard() { std::lock_guard<std::mutex> g(g_prewarm_mu); if (g_prewarm.joinable()) g_prewarm.join(); } } g_prewarm_guard;
 #endif
 
 /* streams and events of one device state (the caller has made d.dev current) */

@@ -90,3 +90,37 @@ def test_lordfast_gpu_sam_identical(tmp_path, name, kw, threads, extra):
     _dataset(tmp_path, **kw)
     recs = _compare(GPU_BIN, tmp_path, threads, extra)
     assert len(recs) >= kw["reads"]
+
+
+@pytest.mark.gpu
+def test_lordfast_gpu_sam_identical_config2_full(tmp_path):
+    """BASELINE configs[1] at full size (4.6 Mbp reference, 20 000 x 10 kbp reads, 10 % SV mix) through the whole program:
+    every SAM record of the GPU build against the reference binary's (20 000+ records)."""
+    if not (os.path.exists(GPU_BIN) and os.path.exists(REF_BIN)):
+        pytest.fail("integration/_build/lordfast_gpu or oracle/_ref/lordfast missing: run __graft_entry__.build() where /root/reference exists")
+    _dataset(tmp_path, ref_len=4_600_000, reads=20_000, read_len=10_000, err=[0.12, 0.15], seed=100, sv_frac=0.10)
+    recs = _compare(GPU_BIN, tmp_path, os.cpu_count() or 4)
+    assert len(recs) >= 20_000
+
+
+def _n_gpus():
+    try:
+        return len(subprocess.check_output(["nvidia-smi", "-L"], text=True).strip().splitlines())
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+def test_lordfast_gpu_multi_device_sam_identical(tmp_path, monkeypatch):
+    """LF_GPU_DEVICES=0,1,...: one context over every GPU of the box; lf_gpu_align_chains shards the chunk's chains by
+    contiguous ranges over a lane per device (every device holds the reference) and merges the records in chain order
+    (the data-parallel loop of src/LordFAST.cpp:295-316).  Needs two GPUs (`gpurun --gpus 2`); skipped on one."""
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("one GPU visible")
+    if not (os.path.exists(GPU_BIN) and os.path.exists(REF_BIN)):
+        pytest.fail("integration/_build/lordfast_gpu or oracle/_ref/lordfast missing")
+    monkeypatch.setenv("LF_GPU_DEVICES", ",".join(str(i) for i in range(n)))
+    _dataset(tmp_path, ref_len=2_000_000, reads=1500, read_len=8_000, err=[0.12, 0.15], seed=2, sv_frac=0.2, dups=20, contigs=3)
+    recs = _compare(GPU_BIN, tmp_path, 8)
+    assert len(recs) >= 1500
