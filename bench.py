@@ -1,23 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- aligned Mbp/s of the per-candidate alignment stage on B200 (BASELINE.json metric).
+"""bench.py -- aligned Mbp/s of lordFAST's per-candidate alignment stage on B200 (BASELINE.json metric).
 
-A step = one pass of the stage over one chunk of synthetic reads (configs[1]: 4.6 Mbp reference,
-20k x 10 kbp reads at 12-15 % error, one candidate chain per read, 10 % SV mix) whose round-1 tasks
-(head SHW, gap NW, tail SHW, all with CIGAR path) are resident in HBM when the timed region starts.
+A step = one pass of the stage over one chunk of reads: every candidate chain the reference's own front-end (seeding,
+window selection, chaining) produced for the reads of a BASELINE config goes through alignChain_edlib's work -- head /
+gap / tail alignments with CIGAR paths, clip / split extensions, follow-ups, CIGAR / MD / NM records.
 
-  value      whole-job Mbp/s, kernels only (prep, sort, scans, all alignment kernels; inputs in HBM)
-  e2e        the same through lf_gpu_align_batch with pinned HOST buffers: H2D of reads+tasks and
-             D2H of results + 2-bit op stream inside the timed region
-  roofline   k_myers_small (the dominant kernels): 16 INT32 ops per (32-row word x column),
-             single-pass full-matrix count, against the LOP3/IADD3 issue rate
-             measured live by lf_gpu_int32_peak (MEASURED_PEAKS.json has no INT32 figure)
-  cpu_baseline  the reference's own alignChain_edlib (oracle/_ref) replayed over the same chains on
-             the host cores (kind "reference"), or the oracle port if oracle/_ref is absent
+Workloads (--workload; config.workload in the output line):
+  config2_real   configs[1]: 4.6 Mbp reference, 20 000 x 10 kbp reads at 12-15 %, 10 % SV mix; chains dumped from the
+                 reference front-end (fixtures/config2.npz, tools/make_fixtures.py).  The default when the fixture exists.
+  config3_real   configs[2]: 64 Mbp reference, 15 kbp reads at 15 % (10 000 of the 100 000 reads)
+  config4_real   configs[3] shape: 256 Mbp reference with duplicated segments, 20 kbp reads, --numMap 10 (5 000 reads)
+  config2_model  the same reads as config2_real with chains from the front-end MODEL of lordfast_b200/sim.py (round-1
+                 workload; the default when no fixture travelled); config1_model: configs[0]
 
-`--impl reference` times only that CPU arm.  N > 1: one process per GPU (torchrun), reads sharded by
-rank (weak scaling: every rank gets a chunk of the same size), no collective on the data path.
+  value      whole-job Mbp/s with the chunk resident in HBM: k_pack_reads + k_align_prep + sort + scans + every alignment
+             kernel of round 1 (the task list lf_gpu_align_chains issues: heads / tails above _pf_clipLen distance-only)
+  e2e        the reference-facing operator lf_gpu_align_chains with HOST buffers: reads + seeds + chains in (H2D), CIGAR /
+             MD text + records out (D2H), all rounds inside.  value = steady state with `in_flight` calls on as many
+             contexts (the ABI allows concurrent calls on distinct contexts); single_call = one call at a time
+  roofline   all alignment kernels of a step (they run concurrently): 16 INT32 ops per (32-row word x column), single
+             pass, full matrix against the LOP3 / IADD3 issue rate measured live by lf_gpu_int32_peak;
+             traffic and the per-family figures come from the committed ncu pass of the same command (profiles/)
+  cpu_baseline  the reference's own alignChain_edlib (oracle/_ref) over the same chains on the host cores
+
+`--impl reference` times only that CPU arm on the same workload.  N > 1: one process per GPU (torchrun), every rank a
+chunk of the same size (weak scaling), no collective on the data path.
 """
 import argparse
+import csv
 import ctypes as C
 import json
 import os
@@ -30,14 +40,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per size-class stream; before torch starts CUDA
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per class stream; before torch starts CUDA
 
-WORKLOADS = {
+MODEL_WORKLOADS = {
     # name: (ref_len, n_reads, read_len, err_lo, err_hi)
-    "config1_1Mbp_200x10k": (1_000_000, 200, 10_000, 0.15, 0.15),
-    "config2_4.6Mbp_20kx10k": (4_600_000, 20_000, 10_000, 0.12, 0.15),
-    "config2_small_4.6Mbp_2kx10k": (4_600_000, 2_000, 10_000, 0.12, 0.15),
+    "config1_model": (1_000_000, 200, 10_000, 0.15, 0.15),
+    "config2_model": (4_600_000, 20_000, 10_000, 0.12, 0.15),
 }
+REAL_WORKLOADS = {"config2_real": "config2", "config3_real": "config3", "config4_real": "config4", "mini3_real": "mini3", "mini4_real": "mini4"}
+NCU_CSV = os.path.join(ROOT, "profiles", "r03_ncu_step_metrics.csv")      # tools/gpu/ncu_step.sh on the default workload
+SWEEP = os.path.join(ROOT, "profiles", "r03_kernel_microbench_config5.jsonl")
 
 
 def parse():
@@ -46,11 +58,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2_4.6Mbp_20kx10k", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=list(MODEL_WORKLOADS) + list(REAL_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sv-frac", type=float, default=0.10, help="fraction of SV/chimera reads (0.10 = the configured mix)")
-    ap.add_argument("--e2e-calls", type=int, default=0, help="e2e: the chunk goes through this many concurrent lf_gpu_align_chains calls (contexts) per step; 1 = one call; "
-                    "0 = one per 4 host cores this rank can count on, at most 4 (measured: 4 calls 14.4 vs 16.4 ms on 16 cores / 1 GPU, but 32.9 vs 29.3 ms on 32 cores / 8 GPUs)")
+    ap.add_argument("--sv-frac", type=float, default=0.10, help="model workloads: fraction of SV/chimera reads (0.10 = the configured mix)")
+    ap.add_argument("--in-flight", type=int, default=0, help="e2e: lf_gpu_align_chains calls in flight (contexts); 0 = 2, or 1 when this rank has fewer than 8 host cores")
+    ap.add_argument("--e2e-calls", type=int, default=None, help=argparse.SUPPRESS)   # round-1 name of --in-flight
     return ap.parse_args()
 
 
@@ -91,49 +103,168 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(name, seed, sv_frac=0.10):
-    from lordfast_b200 import sim
-    from lordfast_b200.chain_tasks import workload_tasks
-    ref_len, n_reads, read_len, e0, e1 = WORKLOADS[name]
-    w = sim.make_workload(ref_len, n_reads, read_len, e0, e1, seed=seed, sv_frac=sv_frac)
-    tasks, chain, kind = workload_tasks(w)
-    return w, tasks
+class StageInput:
+    """What the stage is handed for one chunk: reads, the 2-bit reference, candidate chains (+ their round-1 tasks)."""
+
+    def __init__(self, name, a, rank):
+        from lordfast_b200 import api, fixtures, sim
+        from lordfast_b200.chain_tasks import round1_tasks
+        self.name = name
+        if name in REAL_WORKLOADS:
+            fx = fixtures.load(REAL_WORKLOADS[name])
+            self.ref_len, self.pac, self.reads, self.read_off = len(fx.ref), fx.pac, fx.reads, fx.read_off
+            self.seeds, self.chains = fx.seeds, fx.chains
+            self.chains_from = "reference front-end (oracle/_ref/lordfast_chaindump), " + fx.params["what"]
+            self.read_len = fx.params["read_len"]
+            self.fixture = fx
+        else:
+            ref_len, n_reads, read_len, e0, e1 = MODEL_WORKLOADS[name]
+            w = sim.make_workload(ref_len, n_reads, read_len, e0, e1, seed=100 + rank, sv_frac=a.sv_frac)
+            self.ref_len, self.pac, self.reads, self.read_off = len(w.ref), w.pac, w.reads, w.read_off.astype(np.uint64)
+            self.seeds, self.chains = api.workload_chains(w)
+            self.chains_from = "front-end model (lordfast_b200/sim.py), SV fraction %.2f" % a.sv_frac
+            self.read_len = read_len
+            self.fixture = None
+        self.n_reads = len(self.read_off) - 1
+        self.total_bases = int(self.read_off[-1])
+        self.contig_off, self.contig_len = np.array([0], dtype=np.int64), np.array([self.ref_len], dtype=np.int32)
+        s3 = np.stack([self.seeds["tPos"], self.seeds["qPos"], self.seeds["len"]], axis=1)
+        seed_off = np.concatenate([self.chains["seed_off"], [len(self.seeds)]]).astype(np.int64)
+        rl = np.diff(self.read_off.astype(np.int64))[self.chains["read_id"]]
+        self.tasks, _, _ = round1_tasks(s3, seed_off, self.chains["is_rev"].astype(np.uint8), rl, self.contig_off, self.contig_len,
+                                        read_id=self.chains["read_id"].astype(np.uint32))
 
 
-def cpu_reference_rate(w, nthreads, max_chains=None):
-    """Mbp/s of the reference's alignChain_edlib (oracle/_ref) over this workload's chains."""
+def default_workload():
+    from lordfast_b200 import fixtures
+    return "config2_real" if fixtures.available("config2") else "config2_model"
+
+
+def cpu_reference_rate(si, nthreads, max_chains=None):
+    """Mbp/s of the reference's alignChain_edlib (oracle/_ref) over this workload's chains (reads counted once)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as O
-    n = w.n_reads if max_chains is None else min(w.n_reads, max_chains)
+    from lordfast_b200 import sim
+    n = len(si.chains) if max_chains is None else min(len(si.chains), max_chains)
+    ch = si.chains[:n]
+    rids = ch["read_id"].astype(np.int64)
+    ro = si.read_off.astype(np.int64)
+    bases = int(sum(int(ro[r + 1] - ro[r]) for r in np.unique(rids)))
     if O.have_ref():
         lib = O.ref()
         idx_off = (C.c_int64 * 1)(0)
-        idx_len = (C.c_int32 * 1)(len(w.ref))
-        lib.ref_set_index(w.pac.ctypes.data, len(w.ref), 1, idx_off, idx_len)
-        oriented = [np.ascontiguousarray(w.oriented(i)).tobytes() for i in range(n)]
+        idx_len = (C.c_int32 * 1)(si.ref_len)
+        lib.ref_set_index(si.pac.ctypes.data, si.ref_len, 1, idx_off, idx_len)
+        oriented = []
+        for c in ch:
+            r = si.reads[ro[c["read_id"]]:ro[c["read_id"] + 1]]
+            oriented.append(np.ascontiguousarray(sim.revcomp(r) if c["is_rev"] else r).tobytes())
         qptr = (C.c_char_p * n)(*oriented)
-        seeds = np.ascontiguousarray(w.seeds[: int(w.seed_off[n])], dtype=np.uint32)
-        seed_off = np.ascontiguousarray(w.seed_off[: n + 1], dtype=np.int64)
+        s_hi = int(ch["seed_off"][-1] + ch["n_seeds"][-1])
+        seeds = np.ascontiguousarray(np.stack([si.seeds["tPos"][:s_hi], si.seeds["qPos"][:s_hi], si.seeds["len"][:s_hi]], axis=1), dtype=np.uint32)
+        seed_off = np.ascontiguousarray(np.concatenate([ch["seed_off"], [s_hi]]), dtype=np.int64)
         rl = np.array([len(o) for o in oriented], dtype=np.int32)
-        isrev = np.ascontiguousarray(w.is_rev[:n], dtype=np.uint8)
+        isrev = np.ascontiguousarray(ch["is_rev"], dtype=np.uint8)
         nsam = C.c_int64()
         lib.ref_replay_chains.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        lib.ref_replay_chains.restype = C.c_double
         secs = lib.ref_replay_chains(n, seed_off.ctypes.data, seeds.ctypes.data, C.cast(qptr, C.c_void_p), rl.ctypes.data,
                                      isrev.ctypes.data, nthreads, C.byref(nsam))
-        bases = int(rl.sum())
-        return bases / secs / 1e6, "reference", nthreads, f"{n} chains / {bases / 1e6:.1f} Mbp through the reference's alignChain_edlib (oracle/_ref), {nthreads} threads"
-    # oracle port, single thread, small sample
+        return bases / secs / 1e6, "reference", nthreads, f"{n} chains / {bases / 1e6:.1f} Mbp of reads through the reference's alignChain_edlib (oracle/_ref), {nthreads} threads"
+    # oracle/_ref absent: the oracle port, single thread, small sample
     n = min(n, 100)
-    idx = O.RefIndex(w.ref.tobytes())
+    idx = O.PacIndex(si.pac, si.ref_len, si.contig_off, si.contig_len)
     t0 = time.time()
-    bases = 0
-    for i in range(n):
-        seeds = [tuple(int(x) for x in s) for s in w.chain(i)]
-        q = w.oriented(i).tobytes()
-        O.oracle_align_chain(idx, seeds, q, int(w.is_rev[i]))
-        bases += len(q)
+    seen, bases = set(), 0
+    for c in ch[:n]:
+        rid = int(c["read_id"])
+        r = si.reads[ro[rid]:ro[rid + 1]]
+        q = (sim.revcomp(r) if c["is_rev"] else r).tobytes()
+        sd = si.seeds[int(c["seed_off"]):int(c["seed_off"]) + int(c["n_seeds"])]
+        O.oracle_align_chain(idx, [(int(x["tPos"]), int(x["qPos"]), int(x["len"])) for x in sd], q, int(c["is_rev"]))
+        if rid not in seen:
+            seen.add(rid); bases += len(q)
     secs = time.time() - t0
     return bases / secs / 1e6, "port", 1, f"{n} chains / {bases / 1e6:.1f} Mbp through oracle/lf_oracle.c (scalar O(q*t) port), 1 thread"
+
+
+def ncu_figures(counts):
+    """Per-kernel figures of the committed ncu metrics pass (same workload, one resident step): DRAM bytes per step, time
+    of each kernel family run alone, warp instructions.  None if the file is absent."""
+    if not os.path.exists(NCU_CSV):
+        return None
+    rows = list(csv.reader(open(NCU_CSV)))
+    hdr, per, prep_ids = None, {}, []
+    for r in rows:
+        if "Kernel Name" in r:
+            hdr = r
+            continue
+        if not hdr or len(r) != len(hdr):
+            continue
+        d = dict(zip(hdr, r))
+        name = d["Kernel Name"].split("(LfDev")[0].replace("void ", "")
+        if d["Metric Name"] == "gpu__time_duration.sum" and name.startswith("k_align_prep"):
+            prep_ids.append(int(d["ID"]))
+        if not name.startswith("k_myers"):
+            continue
+        key = (name, d["ID"])
+        v = float(d["Metric Value"].replace(",", ""))
+        if d["Metric Name"] == "gpu__time_duration.sum":
+            u = d["Metric Unit"]
+            v = v / 1e6 if u == "ns" else v / 1e3 if u == "us" else v
+        per.setdefault(key, {})[d["Metric Name"]] = v
+    # the first resident step = the launches before any kernel name repeats beyond what one step holds
+    fam = {"q<=128 (k_myers_bandreg<1..4,false>, k_myers_small<1..4,shw>)": ["bandreg<1, 0>", "bandreg<2, 0>", "bandreg<3, 0>", "bandreg<4, 0>", "small<1,", "small<2,", "small<3,", "small<4,"],
+           "129..512 rows near the diagonal (k_myers_bandreg<3..5,true>)": ["bandreg<3, 1>", "bandreg<4, 1>", "bandreg<5, 1>"],
+           "129..512 rows, other (k_myers_small<6..16>, k_myers_group<4,4>)": ["small<6,", "small<8,", "small<12,", "small<16,", "group<4, 4", "group<16, 1"],
+           "above 512 rows (k_myers_group, k_myers_large)": ["group<8,", "group<16, 8", "group<32,", "k_myers_large"]}
+    # one resident step = the alignment kernels between the first k_align_prep and the next one
+    prep_ids.sort()
+    lo = prep_ids[0] if prep_ids else -1
+    hi = prep_ids[1] if len(prep_ids) > 1 else 1 << 30
+    out = {"traffic": 0.0, "families": {}, "warp_instructions": 0.0}
+    step_ids = [k for k in per if lo < int(k[1]) < hi]
+    for key in step_ids:
+        m = per[key]
+        out["traffic"] += m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
+        out["warp_instructions"] += m.get("smsp__inst_executed.sum", 0)
+        for f, pats in fam.items():
+            if any(p in key[0] for p in pats):
+                e = out["families"].setdefault(f, {"alone_ms": 0.0, "warp_instructions": 0.0, "dram_bytes": 0.0})
+                e["alone_ms"] += m.get("gpu__time_duration.sum", 0)
+                e["warp_instructions"] += m.get("smsp__inst_executed.sum", 0)
+                e["dram_bytes"] += m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
+                break
+    return out
+
+
+def family_word_columns(tasks):
+    """algorithmic word-columns (ceil(q/32) * t) of the round-1 tasks per kernel family, by the routing rules of k_align_prep"""
+    q, t = tasks["q_len"].astype(np.int64), tasks["t_len"].astype(np.int64)
+    nw = (q + 31) // 32
+    wc = nw * t
+    dlt = np.abs(q - t)
+    sc_nb = np.where(nw <= 6, 3, np.where(nw <= 12, 4, 5))
+    near = (tasks["mode"] == 0) & (3 * dlt <= 32 * (sc_nb - 1) - 7) & (q // np.maximum(t, 1) < 32)
+    leaf = (20 * ((q + 63) // 64) * t + 8 * t < (1 << 20)) | (t < 2)
+    small = (nw <= 4) & leaf
+    mid = (nw > 4) & (nw <= 16) & leaf
+    return {"q<=128 (k_myers_bandreg<1..4,false>, k_myers_small<1..4,shw>)": int(wc[small].sum()),
+            "129..512 rows near the diagonal (k_myers_bandreg<3..5,true>)": int(wc[mid & near].sum()),
+            "129..512 rows, other (k_myers_small<6..16>, k_myers_group<4,4>)": int(wc[mid & ~near].sum()),
+            "above 512 rows (k_myers_group, k_myers_large)": int(wc[~small & ~mid].sum())}
+
+
+def sweep_summary():
+    if not os.path.exists(SWEEP):
+        return None
+    pts = [json.loads(l) for l in open(SWEEP) if l.strip().startswith("{")]
+    nw = [p for p in pts if p.get("kind") == "nw" and "frac" in p]
+    if not nw:
+        return None
+    lo, hi = min(nw, key=lambda p: p["frac"]), max(nw, key=lambda p: p["frac"])
+    brief = lambda p: {k: p[k] for k in ("L", "d", "pairs", "kernel_ms", "gcups", "frac") if k in p}
+    return {"source": os.path.relpath(SWEEP, ROOT), "points": len(nw), "worst": brief(lo), "best": brief(hi)}
 
 
 def main():
@@ -141,24 +272,30 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl_name = a.workload
+    wl_name = a.workload or default_workload()
+    if a.e2e_calls is not None:
+        a.in_flight = a.e2e_calls
 
     if a.impl == "reference":
         if rank != 0:
             return
-        w, tasks = make_inputs("config2_small_4.6Mbp_2kx10k" if wl_name.startswith("config2") else wl_name, seed=100)
+        si = StageInput(wl_name, a, 0)
         nthreads = os.cpu_count() or 1
+        # each step = the whole chunk's chains (the same ones the GPU arm aligns) unless that takes over ~8 s
+        r0, kind, cores, sample = cpu_reference_rate(si, nthreads, max_chains=2000)
+        full_s = si.total_bases / 1e6 / r0
+        max_chains = None if full_s * (a.steps + a.warmup) < 200 else max(2000, int(len(si.chains) * 200 / (full_s * (a.steps + a.warmup))))
         rates = []
         for it in range(a.warmup + a.steps):
-            r, kind, cores, sample = cpu_reference_rate(w, nthreads)
+            r, kind, cores, sample = cpu_reference_rate(si, nthreads, max_chains=max_chains)
             if it >= a.warmup:
                 rates.append(r)
         v = float(np.mean(rates))
-        ms = w.total_bases / 1e6 / v * 1e3
+        ms = si.total_bases / 1e6 / v * 1e3
         print(json.dumps({"impl": "reference", "metric": "aligned Mbp/s (alignment stage)", "value": v, "unit": "Mbp/s", "n_gpus": a.gpus,
                           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                          "config": {"workload": wl_name, "sample": sample},
+                          "config": {"workload": wl_name, "chains": si.chains_from, "reads_per_gpu": si.n_reads, "read_len": si.read_len, "sample": sample},
                           "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -172,19 +309,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from lordfast_b200 import api
 
-    w, tasks = make_inputs(wl_name, seed=100 + rank, sv_frac=a.sv_frac)  # every rank gets its own chunk of the same size
-    g = api.LfGpu(w.pac, len(w.ref))
+    si = StageInput(wl_name, a, rank)
+    tasks = si.tasks
+    g = api.LfGpu(si.pac, si.ref_len)
     n = len(tasks)
-    total_bases = w.total_bases
-    read_off = w.read_off.astype(np.uint64)
+    total_bases = si.total_bases
+    read_off = si.read_off.astype(np.uint64)
 
-    # pinned host staging for the e2e arm
-    cap = g.lib.lf_gpu_ops_capacity(tasks.ctypes.data, n)
     p_tasks = api.PinnedArray(g.lib, tasks.nbytes); h_tasks = p_tasks.view(api.ALIGN_TASK, n); h_tasks[:] = tasks
-    p_bases = api.PinnedArray(g.lib, w.reads.nbytes); h_bases = p_bases.view(np.uint8, len(w.reads)); h_bases[:] = w.reads
-    p_res = api.PinnedArray(g.lib, n * api.ALIGN_RESULT.itemsize); h_res = p_res.view(api.ALIGN_RESULT, n)
-    p_ops = api.PinnedArray(g.lib, cap); h_ops = p_ops.view(np.uint8, cap)
-    reads_struct = api.Reads(h_bases.ctypes.data, read_off.ctypes.data, w.n_reads)
+    p_bases = api.PinnedArray(g.lib, si.reads.nbytes); h_bases = p_bases.view(np.uint8, len(si.reads)); h_bases[:] = si.reads
+    reads_struct = api.Reads(h_bases.ctypes.data, read_off.ctypes.data, si.n_reads)
 
     def barrier():
         torch.cuda.synchronize()
@@ -192,132 +326,92 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident arm (value) ----
+    # ---- resident arm (value): bit planes + round-1 alignment of the chunk, inputs in HBM ----
     g.upload_reads(h_bases, read_off)
     g.upload_align_tasks(h_tasks)
     g.sync()
-    for _ in range(a.warmup):
-        g.run_align(); g.sync()
+    for _ in range(max(3, a.warmup)):
+        g.pack_reads(); g.run_align(); g.sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = g.stats().kernel_launches
     barrier()
     t0 = time.perf_counter()
-    dev_ms, main_ms = [], []
+    main_ms = []
     for _ in range(a.steps):
-        g.run_align(); g.sync()
-        st = g.stats()
-        dev_ms.append(st.last_run_ms); main_ms.append(st.last_main_kernel_ms)
+        g.pack_reads(); g.run_align(); g.sync()
+        main_ms.append(g.stats().last_main_kernel_ms)
     barrier()
     wall = time.perf_counter() - t0
     st = g.stats()
     tl_start, tl_end = g.class_timeline()
+    class_counts = g.class_counts()
     launches = int(st.kernel_launches - l0)
     main_wc = int(st.last_main_word_columns)
-    # device-event time per step (prep + sort + scans + kernels, on the library's stream)
-    step_ms = float(np.mean(dev_ms))
 
-    # ---- e2e arm: host buffers in, host buffers out ----
-    def e2e_step():
-        rc = g.lib.lf_gpu_align_batch(g.ctx, C.byref(reads_struct), h_tasks.ctypes.data, n, h_res.ctypes.data, h_ops.ctypes.data, cap)
-        if rc != 0:
-            raise SystemExit(f"lf_gpu_align_batch failed: {rc} {g.lib.lf_gpu_last_error(g.ctx).decode()}")
-    for _ in range(max(1, a.warmup // 2)):
-        e2e_step()
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(a.steps):
-        e2e_step()
-    barrier()
-    e2e_wall = time.perf_counter() - t1
-    # ---- chain-level e2e: lf_gpu_align_chains (the batched alignChain_edlib): chains in, Sam_t records out ----
-    seeds_a, chains_a = api.workload_chains(w)
-    cg = api.Contigs(w.contig_off.ctypes.data, w.contig_len.ctypes.data, len(w.contig_off))
-    pac_ptr = g.pac.ctypes.data
+    # ---- e2e: lf_gpu_align_chains (the batched alignChain_edlib), host buffers in, records + text out ----
+    cg = api.Contigs(si.contig_off.ctypes.data, si.contig_len.ctypes.data, len(si.contig_off))
+    seeds_a, chains_a = np.ascontiguousarray(si.seeds), np.ascontiguousarray(si.chains)
 
-    def chain_step():
+    def chain_call(gk):
         out = C.c_void_p()
-        rc = g.lib.lf_gpu_align_chains(g.ctx, C.byref(reads_struct), C.byref(cg), seeds_a.ctypes.data, chains_a.ctypes.data, len(chains_a), pac_ptr, C.byref(out))
+        rc = gk.lib.lf_gpu_align_chains(gk.ctx, C.byref(reads_struct), C.byref(cg), seeds_a.ctypes.data, chains_a.ctypes.data, len(chains_a), gk.pac.ctypes.data, C.byref(out))
         if rc != 0:
-            raise SystemExit(f"lf_gpu_align_chains failed: {rc} {g.lib.lf_gpu_last_error(g.ctx).decode()}")
+            raise SystemExit(f"lf_gpu_align_chains failed: {rc} {gk.lib.lf_gpu_last_error(gk.ctx).decode()}")
         nrec, tbytes = C.c_size_t(), C.c_size_t()
-        g.lib.lf_chain_results_records(out, C.byref(nrec))
-        g.lib.lf_chain_results_text(out, C.byref(tbytes))
+        gk.lib.lf_chain_results_records(out, C.byref(nrec))
+        gk.lib.lf_chain_results_text(out, C.byref(tbytes))
         cst = api.ChainStats()
-        g.lib.lf_chain_results_stats(out, C.byref(cst))
-        g.lib.lf_chain_results_free(out)
+        gk.lib.lf_chain_results_stats(out, C.byref(cst))
+        gk.lib.lf_chain_results_free(out)
         return nrec.value, cst, tbytes.value
-    chain_step()
+
+    nsingle = max(3, a.steps // 3)
+    chain_call(g); chain_call(g)
     barrier()
     t2 = time.perf_counter()
-    nrec, cst, chain_text_bytes = 0, None, 0
-    for _ in range(max(2, a.steps // 4)):
-        nrec, cst, chain_text_bytes = chain_step()
+    for _ in range(nsingle):
+        nrec, cst, chain_text_bytes = chain_call(g)
     barrier()
-    chain_ms = (time.perf_counter() - t2) / max(2, a.steps // 4) * 1e3
-    # ---- the same chunk as K concurrent calls on K contexts of this GPU (the ABI allows calls on distinct contexts from
-    #      different host threads): uploads, kernels, emit and downloads of the sub-chunks overlap ----
-    K = a.e2e_calls if a.e2e_calls > 0 else max(1, min(4, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) // 4))
-    chainK_ms = None
-    if K > 1:
-        from concurrent.futures import ThreadPoolExecutor
-        ctxs = [g] + [api.LfGpu(w.pac, len(w.ref)) for _ in range(K - 1)]
-        subs = []
-        for k in range(K):
-            lo, hi = w.n_reads * k // K, w.n_reads * (k + 1) // K
-            offs = np.ascontiguousarray(read_off[lo:hi + 1] - read_off[lo])
-            ch = chains_a[lo:hi].copy()
-            s_lo = int(ch["seed_off"][0])
-            ch["seed_off"] -= s_lo
-            ch["read_id"] -= lo
-            rs = api.Reads(h_bases.ctypes.data + int(read_off[lo]), offs.ctypes.data, hi - lo)
-            subs.append((ctxs[k], rs, offs, ch, seeds_a.ctypes.data + s_lo * seeds_a.itemsize))
-        os.environ["LF_HOST_THREADS"] = str(max(2, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))) // K))
+    single_ms = (time.perf_counter() - t2) / nsingle * 1e3
+    cores_here = (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    P = a.in_flight if a.in_flight > 0 else (2 if cores_here >= 8 else 1)
+    flight_ms = single_ms
+    if P > 1:
+        ctxs = [g] + [api.LfGpu(si.pac, si.ref_len) for _ in range(P - 1)]
+        os.environ["LF_HOST_THREADS"] = str(max(2, cores_here // P))
+        per = max(2, (a.steps + P - 1) // P)
 
-        def sub_call(k):
-            gk, rs, offs, ch, sp = subs[k]
-            out = C.c_void_p()
-            rc = gk.lib.lf_gpu_align_chains(gk.ctx, C.byref(rs), C.byref(cg), sp, ch.ctypes.data, len(ch), pac_ptr, C.byref(out))
-            if rc != 0:
-                raise SystemExit(f"lf_gpu_align_chains failed: {rc} {gk.lib.lf_gpu_last_error(gk.ctx).decode()}")
-            nr, tb = C.c_size_t(), C.c_size_t()
-            gk.lib.lf_chain_results_records(out, C.byref(nr))
-            gk.lib.lf_chain_results_text(out, C.byref(tb))
-            gk.lib.lf_chain_results_free(out)
-            return nr.value, tb.value
-        pool = ThreadPoolExecutor(K)
-        for _ in range(2):
-            resK = list(pool.map(sub_call, range(K)))
+        def worker(gk, k):
+            for _ in range(k):
+                chain_call(gk)
+        for gk in ctxs[1:]:
+            chain_call(gk); chain_call(gk)
         barrier()
         t3 = time.perf_counter()
-        for _ in range(max(2, a.steps // 4)):
-            resK = list(pool.map(sub_call, range(K)))
+        th = [threading.Thread(target=worker, args=(gk, per)) for gk in ctxs]
+        [t.start() for t in th]
+        [t.join() for t in th]
         barrier()
-        chainK_ms = (time.perf_counter() - t3) / max(2, a.steps // 4) * 1e3
-        assert sum(r[0] for r in resK) == nrec and sum(r[1] for r in resK) == chain_text_bytes, "sub-chunk calls returned different totals"
+        flight_ms = (time.perf_counter() - t3) / (P * per) * 1e3
         os.environ.pop("LF_HOST_THREADS", None)
         for gk in ctxs[1:]:
             gk.close()
     clocks = sampler.finish() if rank == 0 else None
-    ops_bytes = int(h_res["ops_len"].astype(np.int64).sum() // 4)
-    h2d = int(w.reads.nbytes + read_off.nbytes + tasks.nbytes)
-    d2h = int(n * api.ALIGN_RESULT.itemsize + int(st_ops_words(g, h_res)) * 4)
 
     # max over ranks
-    tt = torch.tensor([step_ms, e2e_wall / a.steps * 1e3, wall / a.steps * 1e3, chain_ms, chainK_ms if chainK_ms is not None else chain_ms], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([wall / a.steps * 1e3, single_ms, flight_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     bases_all = torch.tensor([float(total_bases)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(bases_all, op=dist.ReduceOp.SUM)
-    step_ms_max, e2e_ms_max, wall_ms_max, chain_ms_max, chainK_ms_max = [float(x) for x in tt.tolist()]
+    wall_ms_max, single_ms_max, flight_ms_max = [float(x) for x in tt.tolist()]
     bases_sum = float(bases_all.item())
 
     if rank == 0:
-        value = bases_sum / 1e6 / (wall_ms_max * 1e-3)        # Mbp/s, wall time of run+sync per step
-        e2e_v = bases_sum / 1e6 / (e2e_ms_max * 1e-3)
-        # roofline of the dominant kernels (rank 0's own launches)
+        value = bases_sum / 1e6 / (wall_ms_max * 1e-3)
         try:
             peaks = {name: g.int32_peak(k) for k, name in enumerate(["lop3", "iadd3", "lop3_iadd3", "lop3_imad"])}
         except Exception as e:  # pragma: no cover
@@ -326,51 +420,55 @@ def main():
         mk_ms = float(np.mean(main_ms))
         achieved = 16.0 * main_wc / (mk_ms * 1e-3) / 1e12 if mk_ms > 0 else 0.0
         cells = int(tasks["q_len"].astype(np.int64) @ tasks["t_len"].astype(np.int64))
+        roof = {"bound": "int32", "kernel": "alignment kernels of a step (k_myers_bandreg / k_myers_small size classes, k_myers_group, k_myers_large; concurrent streams)",
+                "achieved": achieved, "peak": peak, "unit": "Top/s", "frac": achieved / peak if peak else None, "traffic": None, "traffic_unit": "B per launch set",
+                "algorithmic_ops_per_launch_set": 16.0 * main_wc, "kernel_ms": mk_ms,
+                "peak_source": "lf_gpu_int32_peak (IADD3 stream, 64 SASS-verified ops/iteration) measured in this run", "int32_peaks_tops": peaks}
+        nf = ncu_figures(class_counts) if wl_name == "config2_real" else None
+        if nf:
+            roof["traffic"] = nf["traffic"]
+            roof["traffic_source"] = os.path.relpath(NCU_CSV, ROOT) + " (dram__bytes_read.sum + dram__bytes_write.sum over the alignment kernels of one step, ncu --metrics pass of this command)"
+            roof["executed_warp_instructions"] = nf["warp_instructions"]
+            fw = family_word_columns(tasks)
+            roof["families"] = {f: {"word_columns": fw.get(f, 0), "alone_ms": round(e["alone_ms"], 4), "warp_instructions": e["warp_instructions"], "dram_bytes": e["dram_bytes"],
+                                    "frac_alone": (16.0 * fw.get(f, 0) / (e["alone_ms"] * 1e-3) / 1e12 / peak) if e["alone_ms"] > 0 and peak else None,
+                                    "executed_per_algorithmic_instruction": e["warp_instructions"] * 32 / (16.0 * fw[f]) if fw.get(f) else None}
+                                for f, e in nf["families"].items()}
+            roof["families_note"] = "alone_ms: the family's kernels timed one at a time under ncu (cold, serialised); in a step they overlap, so the fractions do not add up to `frac`"
+        sw = sweep_summary()
         out = {
             "metric": "aligned Mbp/s (alignment stage)", "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": wall_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": wl_name, "reads_per_gpu": w.n_reads, "read_len": WORKLOADS[wl_name][2], "tasks_per_gpu": n,
-                       "cells_per_gpu": cells, "l2": "inputs+outputs of a step (>300 MB) exceed the 126 MB L2; no explicit flush",
-                       "device_ms_per_step": step_ms_max},
+            "config": {"workload": wl_name, "chains": si.chains_from, "reads_per_gpu": si.n_reads, "read_len": si.read_len, "chains_per_gpu": int(len(si.chains)),
+                       "tasks_per_gpu": n, "cells_per_gpu": cells, "word_columns_per_gpu": main_wc,
+                       "step": "k_pack_reads + k_align_prep + sort + scans + all round-1 alignment kernels, chunk resident in HBM",
+                       "l2": "inputs+outputs of a step (>300 MB) exceed the 126 MB L2; no explicit flush"},
             "gcups": cells * world / (wall_ms_max * 1e-3) / 1e9,
             # headline: the reference-facing operator (batched alignChain_edlib), host buffers in, CIGAR/MD/NM records out
-            "e2e": {"value": bases_sum / 1e6 / (chainK_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chainK_ms_max, "calls_per_step": K,
-                    "single_call": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "ms_per_step": chain_ms_max},
+            "e2e": {"value": bases_sum / 1e6 / (flight_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": flight_ms_max, "calls_in_flight": P,
+                    "single_call": {"value": bases_sum / 1e6 / (single_ms_max * 1e-3), "ms_per_step": single_ms_max},
                     # in: reads + offsets + seeds + chains + 17 B of per-chain bases / guards (the round-1 tasks are generated on the device); out: CIGAR/MD text + records
-                    "h2d_bytes_per_step": int(w.reads.nbytes + read_off.nbytes + seeds_a.nbytes + chains_a.nbytes) + 17 * len(chains_a), "d2h_bytes_per_step": int(chain_text_bytes) + int(nrec) * 56, "call": "lf_gpu_align_chains"},
-            "e2e_align_batch": {"value": e2e_v, "unit": "Mbp/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max,
-                                "call": "lf_gpu_align_batch (round-1 tasks only: task list in, distances + 2-bit op stream out)"},
-            "e2e_chains": {"value": bases_sum / 1e6 / (chain_ms_max * 1e-3), "unit": "Mbp/s", "ms_per_step": chain_ms_max, "records_per_gpu": int(nrec),
-                           "host_phase_ms": {"tasks": round(cst.ms_tasks, 2), "round1": round(cst.ms_round1, 2), "rounds2_3": round(cst.ms_rounds23, 2), "emit": round(cst.ms_emit, 2), "merge": round(cst.ms_merge, 2)},
-                           "rounds": {"round1_tasks": int(cst.round1_tasks), "round2_extends": int(cst.round2_extends), "round3_tasks": int(cst.round3_tasks)},
-                           "what": "lf_gpu_align_chains: chains + reads from host memory in, CIGAR/MD/NM records out (3 GPU rounds + host emit)"},
+                    "h2d_bytes_per_step": int(si.reads.nbytes + read_off.nbytes + seeds_a.nbytes + chains_a.nbytes) + 17 * len(chains_a),
+                    "d2h_bytes_per_step": int(chain_text_bytes) + int(nrec) * 56, "call": "lf_gpu_align_chains",
+                    "records_per_gpu": int(nrec),
+                    "host_phase_ms": {"tasks": round(cst.ms_tasks, 2), "round1": round(cst.ms_round1, 2), "rounds2_3": round(cst.ms_rounds23, 2), "emit": round(cst.ms_emit, 2)},
+                    "rounds": {"round1_tasks": int(cst.round1_tasks), "round2_extends": int(cst.round2_extends), "round3_tasks": int(cst.round3_tasks)}},
             "gpu_launches": launches,
-            "roofline": {"bound": "int32", "kernel": "alignment kernels of a step (k_myers_band / k_myers_bandreg / k_myers_small size classes + k_myers_large, concurrent streams)", "achieved": achieved, "peak": peak,
-                         "unit": "Top/s", "frac": achieved / peak if peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum summed over the 23 alignment kernels of one config-2 step, one ncu --set full
-                         # capture (profiles/r02i_ncu_full_alignment_kernels_final.txt): bytes per launch set, like `achieved`; 2.0 GB of it
-                         # are the scattered per-task accesses of the 2.2 M tasks of q <= 128, 1.2 GB the large-task kernel plane scratch
-                         "traffic": 3.82e9 if wl_name == "config2_4.6Mbp_20kx10k" and a.sv_frac == 0.10 else None, "traffic_unit": "B per launch set",
-                         "algorithmic_ops_per_launch_set": 16.0 * main_wc, "kernel_ms": mk_ms,
-                         "peak_source": "lf_gpu_int32_peak (IADD3 stream, 64 SASS-verified ops/iteration) measured in this run", "int32_peaks_tops": peaks},
+            "roofline": roof,
             "clocks": clocks,
+            "class_tasks": class_counts,
             "class_timeline_ms": {api.CLASS_NAMES[c]: [round(float(tl_start[c]), 3), round(float(tl_end[c]), 3)] for c in range(len(tl_end)) if c != 17 and tl_end[c] >= 0},
         }
+        if sw:
+            out["config5_sweep"] = sw
         if not a.no_cpu_baseline:
-            v, kind, cores, sample = cpu_reference_rate(w, os.cpu_count() or 1, max_chains=4000)
+            v, kind, cores, sample = cpu_reference_rate(si, os.cpu_count() or 1, max_chains=4000)
             out["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(out))
-    for p in (p_tasks, p_bases, p_res, p_ops):
-        p.free()
+    p_tasks.free(); p_bases.free()
     g.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-def st_ops_words(g, h_res):
-    """bytes of op stream copied back per step = slot words (16 ops each)"""
-    # the library copies the whole used slot range; recompute it from the results' slot layout
-    return int((h_res["ops_off"].astype(np.int64) + h_res["ops_len"].astype(np.int64)).max() // 16 + 1) if len(h_res) else 0
 
 
 if __name__ == "__main__":

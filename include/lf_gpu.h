@@ -141,6 +141,7 @@ int lf_gpu_extend_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_extend_
 /* The same path split into its three phases, so that a caller (and bench.py) can keep a batch
  * resident in HBM: upload -> run (any number of times) -> download. */
 int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads);
+int lf_gpu_pack_reads(lf_gpu_ctx *ctx);   /* rebuilds the bit planes of the resident reads (k_pack_reads; part of every upload, callable on its own for timing) */
 int lf_gpu_upload_align_tasks(lf_gpu_ctx *ctx, const lf_align_task *tasks, size_t n);
 int lf_gpu_run_align(lf_gpu_ctx *ctx);  /* kernels only, on the resident batch; asynchronous */
 int lf_gpu_sync(lf_gpu_ctx *ctx);

@@ -61,7 +61,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["lf_gpu_init", "lf_gpu_prewarm", "lf_gpu_destroy", "lf_gpu_last_error", "lf_gpu_host_alloc", "lf_gpu_host_free",
-           "lf_gpu_ops_capacity", "lf_gpu_align_batch", "lf_gpu_extend_batch", "lf_gpu_upload_reads",
+           "lf_gpu_ops_capacity", "lf_gpu_align_batch", "lf_gpu_extend_batch", "lf_gpu_upload_reads", "lf_gpu_pack_reads",
            "lf_gpu_upload_align_tasks", "lf_gpu_run_align", "lf_gpu_sync", "lf_gpu_download_align",
            "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",
            "lf_gpu_int32_peak", "lf_gpu_class_timeline", "lf_gpu_class_counts", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
@@ -93,6 +93,7 @@ def load(lib_path: str | None = None) -> C.CDLL:
     lib.lf_gpu_align_batch.argtypes = [vp, C.POINTER(Reads), vp, sz, vp, vp, sz]
     lib.lf_gpu_extend_batch.argtypes = [vp, C.POINTER(Reads), vp, sz, vp]
     lib.lf_gpu_upload_reads.argtypes = [vp, C.POINTER(Reads)]
+    lib.lf_gpu_pack_reads.argtypes = [vp]
     lib.lf_gpu_upload_align_tasks.argtypes = [vp, vp, sz]
     lib.lf_gpu_run_align.argtypes = [vp]
     lib.lf_gpu_sync.argtypes = [vp]
@@ -234,6 +235,9 @@ class LfGpu:
     def upload_align_tasks(self, tasks: np.ndarray):
         assert tasks.dtype == ALIGN_TASK and tasks.flags["C_CONTIGUOUS"]
         self._check(self.lib.lf_gpu_upload_align_tasks(self.ctx, _ptr(tasks), len(tasks)), "lf_gpu_upload_align_tasks")
+
+    def pack_reads(self):
+        self._check(self.lib.lf_gpu_pack_reads(self.ctx), "lf_gpu_pack_reads")
 
     def run_align(self):
         self._check(self.lib.lf_gpu_run_align(self.ctx), "lf_gpu_run_align")

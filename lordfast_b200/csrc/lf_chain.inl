@@ -1562,8 +1562,8 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
         DevState &pd = ctx->devs[k % ndev], &d = lc->devs[0];
         const uint32_t nr = s.rd.n_reads;
         s.io.arena = arena; s.io.nthreads = nthreads / (unsigned)K ? nthreads / (unsigned)K : 1u;
-        if (set_dev(d) || d.bases.reserve((size_t)s.nbytes + 64) || d.read_off.reserve(((size_t)nr + 1) * 8)
-            || lfb_h2d(d.bases.p, s.src, (size_t)s.nbytes, pd.stream) || lfb_h2d(d.read_off.p, s.offs, ((size_t)nr + 1) * 8, pd.stream)) { rc = LF_ERR_CUDA; break; }
+        if (set_dev(d) || d.bases.reserve((size_t)s.nbytes + 64) || d.read_off.reserve(((size_t)nr + 1) * 8 + 64)
+            || h2d_k(pd, d.read_off.p, s.offs, ((size_t)nr + 1) * 8, pd.stream, true) || lfb_h2d(d.bases.p, s.src, (size_t)s.nbytes, pd.stream)) { rc = LF_ERR_CUDA; break; }
 #ifndef LF_EMU
         cudaEventRecord(d.up_ev, pd.stream);
 #endif

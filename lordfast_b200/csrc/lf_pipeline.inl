@@ -475,7 +475,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
             const int cls = seq[si];
             const uint32_t count = ht->cnt.hist[cls];
             if (!count) continue;
-            lfb_stream st = serial ? d.sub[1] : d.sub[1 + (k % nstreams)];   /* LF_SERIAL=1: one class at a time (per-class durations for profiling) */
+            lfb_stream st = serial ? d.sub[1] : d.sub[1 + (k++ % nstreams)];   /* LF_SERIAL=1: one class at a time (per-class durations for profiling) */
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
@@ -494,7 +494,6 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
             cudaEventRecord(d.cls_ev[cls][1], st);
 #endif
-            k++;
         }
     }
 #ifndef LF_EMU
@@ -648,6 +647,7 @@ int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads)
     const size_t pwords = (size_t)(total >> 5) + 3 * (size_t)nr + 8;
     for (DevState &d : ctx->devs) {
         if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        stage_reset(d);   /* a new batch starts here */
         LF_TRY(d.plo.reserve(pwords * 4)); LF_TRY(d.phi.reserve(pwords * 4)); LF_TRY(d.pnn.reserve(pwords * 4));
         if (d.reads_preloaded) {   /* lf_chain.inl lanes: the parent enqueued the copies in lane order on its upload stream */
 #ifndef LF_EMU
@@ -656,9 +656,12 @@ int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads)
             d.reads_preloaded = false;
         } else {
             if (reads->offsets[0] != 0) return fail(ctx, LF_ERR_BAD_ARG, "read offsets must start at 0");
-            LF_TRY(d.bases.reserve(total + 64)); LF_TRY(d.read_off.reserve(((size_t)nr + 1) * 8));
+            LF_TRY(d.bases.reserve(total + 64)); LF_TRY(d.read_off.reserve(((size_t)nr + 1) * 8 + 64));
+            /* the offsets first and through pinned staging: a cudaMemcpyAsync from pageable memory blocks the calling thread
+             * (and, it turned out, other threads' CUDA calls) until everything queued on the stream before it -- 200 MB of
+             * bases -- has gone through */
+            LF_TRY(h2d_k(d, d.read_off.p, reads->offsets, ((size_t)nr + 1) * 8, d.stream, false));
             LF_TRY(lfb_h2d(d.bases.p, reads->bases, total, d.stream));
-            LF_TRY(lfb_h2d(d.read_off.p, reads->offsets, ((size_t)nr + 1) * 8, d.stream));
         }
         LF_TRY(lfb_memset(d.plo.p, 0, pwords * 4, d.stream)); LF_TRY(lfb_memset(d.phi.p, 0, pwords * 4, d.stream));
         LF_TRY(lfb_memset(d.pnn.p, 0xff, pwords * 4, d.stream));
@@ -667,6 +670,18 @@ int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads)
             LfDev v = make_dev(ctx, d);
             LFB_LAUNCH(k_pack_reads, nr, 128, 0, d.stream, v);
         }
+    }
+    return LF_OK;
+}
+
+int lf_gpu_pack_reads(lf_gpu_ctx *ctx)
+{
+    if (!ctx) return LF_ERR_BAD_ARG;
+    for (DevState &d : ctx->devs) {
+        if (set_dev(d)) return fail(ctx, LF_ERR_CUDA, "cudaSetDevice");
+        if (!d.n_reads) continue;
+        LfDev v = make_dev(ctx, d);
+        LFB_LAUNCH(k_pack_reads, d.n_reads, 128, 0, d.stream, v);
     }
     return LF_OK;
 }

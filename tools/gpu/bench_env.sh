@@ -7,7 +7,7 @@ import json,sys
 f='gpurun_out/%s.json'%sys.argv[1]
 try:
     d=json.loads(open(f).read().strip().splitlines()[-1])
-    print(sys.argv[1], 'ms/step',round(d['ms_per_step'],3),'kernel_ms',round(d['roofline']['kernel_ms'],3),'frac',round(d['roofline']['frac'],3),'e2e ms',round(d['e2e']['ms_per_step'],2),'single',round(d['e2e']['single_call']['ms_per_step'],2), d['e2e_chains']['host_phase_ms'])
+    print(sys.argv[1], 'ms/step',round(d['ms_per_step'],3),'kernel_ms',round(d['roofline']['kernel_ms'],3),'frac',round(d['roofline']['frac'],3),'e2e ms',round(d['e2e']['ms_per_step'],2),'single',round(d['e2e']['single_call']['ms_per_step'],2), d['e2e']['host_phase_ms'], d['config']['workload'])
     print('   ', {k:v[1] for k,v in d['class_timeline_ms'].items()})
 except Exception as e: print(f, 'ERR', e, open('gpurun_out/%s.err'%sys.argv[1]).read()[-2000:])
 P
