@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--workload", default=None, choices=list(MODEL_WORKLOADS) + list(REAL_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sv-frac", type=float, default=0.10, help="model workloads: fraction of SV/chimera reads (0.10 = the configured mix)")
-    ap.add_argument("--in-flight", type=int, default=0, help="e2e: lf_gpu_align_chains calls in flight (contexts); 0 = 2, or 1 when this rank has fewer than 8 host cores")
+    ap.add_argument("--in-flight", type=int, default=0, help="e2e: lf_gpu_align_chains calls in flight (contexts); 0 = one per 4 host cores of this rank, at most 4")
     ap.add_argument("--e2e-calls", type=int, default=None, help=argparse.SUPPRESS)   # round-1 name of --in-flight
     return ap.parse_args()
 
@@ -376,7 +376,7 @@ def main():
     barrier()
     single_ms = (time.perf_counter() - t2) / nsingle * 1e3
     cores_here = (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    P = a.in_flight if a.in_flight > 0 else (2 if cores_here >= 8 else 1)
+    P = a.in_flight if a.in_flight > 0 else (4 if cores_here >= 16 else 2 if cores_here >= 8 else 1)
     flight_ms = single_ms
     if P > 1:
         ctxs = [g] + [api.LfGpu(si.pac, si.ref_len) for _ in range(P - 1)]

@@ -64,7 +64,10 @@
 #define LF_CLS_GD256 28   /* 129 .. 256 words: 32 x 8 */
 #define LF_NGROUPCLS 7
 #define LF_NCLS 29
-#define LF_KEY_SHIFT 19    /* sort keys use bits [19,32): 5 bits of class, 8 bits of length bucket */
+#ifndef LF_BUCKET_BITS
+#define LF_BUCKET_BITS 5   /* target-length buckets of the task sort: 2^-LF_BUCKET_BITS octave wide (1/8 octave: 1.834 ms per config-2 step, 1/32: 1.808) */
+#endif
+#define LF_KEY_SHIFT (32 - 5 - 5 - LF_BUCKET_BITS)   /* sort keys use the top bits: 5 of class, 5 + LF_BUCKET_BITS of length bucket */
 #define LF_LARGE_STACK 96 /* Hirschberg stack entries per warp (depth <= log2(t)+2) */
 #define LF_CLIP_LEN 500   /* _pf_clipLen, src/LordFAST.cpp:88: heads / tails longer than this are first asked for their distance only */
 
@@ -388,8 +391,9 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
          * submission order, i.e. neighbouring lanes work on neighbouring reads and result slots */
         const uint32_t tl = t.t_len ? t.t_len : 1u;
         const uint32_t e = 31u - (uint32_t)__clz((int)tl);
-        const uint32_t m = e >= 3u ? (tl >> (e - 3u)) & 7u : (tl << (3u - e)) & 7u;
-        keys[i] = ((uint32_t)cls << 27) | ((255u - (e * 8u + m)) << LF_KEY_SHIFT);
+        constexpr uint32_t MB = LF_BUCKET_BITS, MM = (1u << MB) - 1u;
+        const uint32_t m = e >= MB ? (tl >> (e - MB)) & MM : (tl << (MB - e)) & MM;
+        keys[i] = ((uint32_t)cls << 27) | ((((32u << MB) - 1u) - ((e << MB) + m)) << LF_KEY_SHIFT);
         idx[i] = i;
         slot_words[i] = slot;
         scr_bytes[i] = scr;
@@ -1079,8 +1083,14 @@ __device__ __forceinline__ LfPassOut lf_wave_pass_w(const LfDev &d, const LfQVie
     }
 }
 
-__device__ __forceinline__ LfPassOut lf_wave_pass(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
-                                                  uint2 *planes, int8_t *hb, int32_t *col)
+#ifdef LF_EMU
+#define LF_NOINLINE
+#else
+#define LF_NOINLINE __noinline__
+#endif
+/* one copy per kernel (k_myers_large calls it from eight places and it holds 20 instantiations of the pass) */
+__device__ LF_NOINLINE LfPassOut lf_wave_pass(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
+                                              uint2 *planes, int8_t *hb, int32_t *col)
 {
     switch (lf_wpl(ql)) {
     case 1: return lf_wave_pass_w<1>(d, qv, ql, tv, tl, flags, planes, hb, col);
@@ -1142,129 +1152,205 @@ __device__ __forceinline__ void lf_warp_move_down(uint8_t *buf, long long dst, l
     }
 }
 
-__device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const LfLargeCfg &cfg, uint8_t *scr)
+/* Scratch regions of one warp slot of k_myers_large */
+struct LfLargeScr {
+    uint2 *planes; int8_t *hb; int32_t *Lc, *Rc; uint8_t *opsb; int32_t *stack;
+    __device__ __forceinline__ LfLargeScr(uint8_t *scr, const LfLargeCfg &cfg)
+        : planes((uint2 *)scr), hb((int8_t *)(scr + cfg.off_hb)), Lc((int32_t *)(scr + cfg.off_L)), Rc((int32_t *)(scr + cfg.off_R)), opsb(scr + cfg.off_opsb),
+          stack((int32_t *)(scr + cfg.off_stack)) { }
+};
+
+/* Split of (query [qo, qo+ql), target [to, to+tl)) at target column tl/2 (edlib.cpp:1176-1289): the smallest interior row x
+ * with L[x] + R[x] == best, then the top boundary, then the bottom one.  Lc / Rc hold D(x, lw) of the left half and of the
+ * reversed right half.  best < 0: not known yet -- the minimum over all rows is the distance of the piece (returned in
+ * best).  Returns x, or -1 if no row fits (cannot happen for a correct distance).  One warp. */
+__device__ __forceinline__ int lf_large_split_row(const int32_t *Lc, const int32_t *Rc, int ql, int lw, int rw, int &best, int &ls, int &rs)
 {
     const int lane = threadIdx.x & 31;
-    const lf_align_task task = d.tasks[ti];
-    const int q = (int)task.q_len, t = (int)task.t_len;
-    LfQView qv; LfTView tv;
-    lf_task_views(d, task, qv, tv);
-    uint2 *planes = (uint2 *)scr;
-    int8_t *hb = (int8_t *)(scr + cfg.off_hb);
-    int32_t *Lc = (int32_t *)(scr + cfg.off_L), *Rc = (int32_t *)(scr + cfg.off_R);
-    uint8_t *opsb = scr + cfg.off_opsb;
-    int32_t *stack = (int32_t *)(scr + cfg.off_stack);
-
-    const bool shw = task.mode == LF_MODE_SHW;
-    const bool want = !(task.flags & LF_F_NO_PATH);
-    int ed, end;
-    bool stored = false; /* planes of the whole task are already in `planes` */
-    bool ed_known = true;
-    if (!shw && want && lf_is_leaf((uint32_t)q, (uint32_t)t)) {
-        LfPassOut o = lf_wave_pass(d, qv, q, tv, t, LF_PASS_STORE, planes, hb, nullptr);
-        ed = o.ed; end = t - 1; stored = true;
-    } else if (!shw && want) {
-        ed = -1; end = t - 1; ed_known = false; /* the first split yields min_x L[x]+R[x] = the distance */
-    } else {
-        LfPassOut o = lf_wave_pass(d, qv, q, tv, t, shw ? LF_PASS_SHW : 0, planes, hb, nullptr);
-        if (shw) { ed = o.best; end = o.bestc; } else { ed = o.ed; end = t - 1; }
+    if (best < 0) {
+        int m = 0x7fffffff;
+        for (int x0 = lane; x0 <= ql; x0 += 32) { const int v = Lc[x0] + Rc[ql - x0]; m = v < m ? v : m; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { const int v = __shfl_xor_sync(LF_FULL, m, o); m = v < m ? v : m; }
+        best = m;
     }
-    const uint64_t slot_hi = d.slot_end[ti] * 16ull;
-    lf_align_result r;
-    r.edit_distance = ed; r.end_location = end; r.status = 0; r.ops_len = 0; r.ops_off = slot_hi;
-    if (!want) { if (lane == 0) d.res[ti] = r; return; }
+    int x = -1;
+    for (int x0 = 1; x0 <= ql - 1 && x < 0; x0 += 32) {
+        const int xx = x0 + lane;
+        const bool hit = xx <= ql - 1 && Lc[xx] + Rc[ql - xx] == best;
+        const uint32_t bal = __ballot_sync(LF_FULL, hit);
+        if (bal) x = x0 + __ffs((int)bal) - 1;
+    }
+    if (x >= 0) { ls = Lc[x]; rs = Rc[ql - x]; }
+    else if (lw + Rc[ql] == best) { x = 0; ls = lw; rs = Rc[ql]; }
+    else if (Lc[ql] + rw == best) { x = ql; ls = Lc[ql]; rs = rw; }
+    return x;
+}
 
-    /* ---- path: obtainAlignment (edlib.cpp:1090-1143) with an explicit stack ---- */
-    const int teff = end + 1;
+/* obtainAlignment (edlib.cpp:1090-1143) of (query [q0, q0+qlen), target [t0, t0+tlen)) of the task's views with an explicit
+ * stack, by ONE warp in its own scratch: byte ops land in S.opsb[0, return value).  stored: the planes of the whole piece are
+ * already in S.planes (a leaf whose store pass has run). */
+__device__ __forceinline__ long long lf_large_path(const LfDev &d, const LfQView &qv, const LfTView &tv, int q0, int qlen, int t0, int tlen, int best0,
+                                                   const LfLargeScr &S, bool stored, int &ed_io, int &status)
+{
+    const int lane = threadIdx.x & 31;
     long long outpos = 0;
     int sp = 0;
-    if (lane == 0) { stack[0] = 0; stack[1] = q; stack[2] = 0; stack[3] = teff; stack[4] = ed; }
+    if (lane == 0) { S.stack[0] = q0; S.stack[1] = qlen; S.stack[2] = t0; S.stack[3] = tlen; S.stack[4] = best0; }
     sp = 1;
     __syncwarp();
-    int status = 0;
+    bool first = true;
     while (sp > 0) {
         sp--;
-        const int qo = stack[sp * 5 + 0], ql = stack[sp * 5 + 1], to = stack[sp * 5 + 2], tl = stack[sp * 5 + 3], best_in = stack[sp * 5 + 4];
+        const int qo = S.stack[sp * 5 + 0], ql = S.stack[sp * 5 + 1], to = S.stack[sp * 5 + 2], tl = S.stack[sp * 5 + 3], best_in = S.stack[sp * 5 + 4];
         __syncwarp();
-        if (ql == 0) { lf_warp_fill(opsb + outpos, tl, 2); outpos += tl; continue; }
-        if (tl == 0) { lf_warp_fill(opsb + outpos, ql, 1); outpos += ql; continue; }
+        if (ql == 0) { lf_warp_fill(S.opsb + outpos, tl, 2); outpos += tl; first = false; continue; }
+        if (tl == 0) { lf_warp_fill(S.opsb + outpos, ql, 1); outpos += ql; first = false; continue; }
         if (lf_is_leaf((uint32_t)ql, (uint32_t)tl)) {
-            if (!stored) {
+            if (!(stored && first)) {
                 LfQView sq = lf_qsub(qv, qo, ql, false);
                 LfTView st = lf_tsub(tv, to, tl, false);
-                lf_wave_pass(d, sq, ql, st, tl, LF_PASS_STORE, planes, hb, nullptr);
+                lf_wave_pass(d, sq, ql, st, tl, LF_PASS_STORE, S.planes, S.hb, nullptr);
                 __syncwarp();
             }
-            const long long hi_pos = (long long)qo + to + ql + tl;
-            const int nops = lf_large_traceback(planes, ql, tl, opsb, hi_pos);
-            lf_warp_move_down(opsb, outpos, hi_pos - nops, nops);
+            const long long hi_pos = (long long)(qo - q0) + (to - t0) + ql + tl;
+            const int nops = lf_large_traceback(S.planes, ql, tl, S.opsb, hi_pos);
+            lf_warp_move_down(S.opsb, outpos, hi_pos - nops, nops);
             outpos += nops;
-            stored = false;
+            first = false;
             continue;
         }
+        first = false;
         /* split at column tl/2 (edlib.cpp:1176-1196) */
         const int lw = tl / 2, rw = tl - lw;
-        lf_wave_pass(d, lf_qsub(qv, qo, ql, false), ql, lf_tsub(tv, to, lw, false), lw, LF_PASS_COL, planes, hb, Lc);
-        lf_wave_pass(d, lf_qsub(qv, qo, ql, true), ql, lf_tsub(tv, to + lw, rw, true), rw, LF_PASS_COL, planes, hb, Rc);
+        lf_wave_pass(d, lf_qsub(qv, qo, ql, false), ql, lf_tsub(tv, to, lw, false), lw, LF_PASS_COL, S.planes, S.hb, S.Lc);
+        lf_wave_pass(d, lf_qsub(qv, qo, ql, true), ql, lf_tsub(tv, to + lw, rw, true), rw, LF_PASS_COL, S.planes, S.hb, S.Rc);
         __syncwarp();
-        int best = best_in;
-        if (!ed_known) { /* distance of the whole task = min over all split rows */
-            int m = 0x7fffffff;
-            for (int x0 = lane; x0 <= ql; x0 += 32) { const int v = Lc[x0] + Rc[ql - x0]; m = v < m ? v : m; }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) { const int v = __shfl_xor_sync(LF_FULL, m, o); m = v < m ? v : m; }
-            best = m; ed = m; ed_known = true;
-        }
-        /* smallest interior row, then the top boundary, then the bottom one (edlib.cpp:1257-1289) */
-        int x = -1;
-        for (int x0 = 1; x0 <= ql - 1 && x < 0; x0 += 32) {
-            const int xx = x0 + lane;
-            const bool hit = xx <= ql - 1 && Lc[xx] + Rc[ql - xx] == best;
-            const uint32_t bal = __ballot_sync(LF_FULL, hit);
-            if (bal) x = x0 + __ffs((int)bal) - 1;
-        }
-        int ls, rs;
-        if (x >= 0) { ls = Lc[x]; rs = Rc[ql - x]; }
-        else if (lw + Rc[ql] == best) { x = 0; ls = lw; rs = Rc[ql]; }
-        else if (Lc[ql] + rw == best) { x = ql; ls = Lc[ql]; rs = rw; }
-        else { status = LF_ERR_CUDA; break; } /* cannot happen for a correct distance */
+        int best = best_in, ls = 0, rs = 0;
+        const int x = lf_large_split_row(S.Lc, S.Rc, ql, lw, rw, best, ls, rs);
+        if (best_in < 0) ed_io = best;   /* distance of the whole piece = min over all split rows */
+        if (x < 0) { status = LF_ERR_CUDA; break; } /* cannot happen for a correct distance */
         __syncwarp();
         if (sp + 2 > LF_LARGE_STACK) { status = LF_ERR_NOMEM; break; }
         if (lane == 0) {
-            stack[sp * 5 + 0] = qo + x; stack[sp * 5 + 1] = ql - x; stack[sp * 5 + 2] = to + lw; stack[sp * 5 + 3] = rw; stack[sp * 5 + 4] = rs;
-            stack[sp * 5 + 5] = qo; stack[sp * 5 + 6] = x; stack[sp * 5 + 7] = to; stack[sp * 5 + 8] = lw; stack[sp * 5 + 9] = ls;
+            S.stack[sp * 5 + 0] = qo + x; S.stack[sp * 5 + 1] = ql - x; S.stack[sp * 5 + 2] = to + lw; S.stack[sp * 5 + 3] = rw; S.stack[sp * 5 + 4] = rs;
+            S.stack[sp * 5 + 5] = qo; S.stack[sp * 5 + 6] = x; S.stack[sp * 5 + 7] = to; S.stack[sp * 5 + 8] = lw; S.stack[sp * 5 + 9] = ls;
         }
         sp += 2;
         __syncwarp();
     }
+    return outpos;
+}
+
+/* One task on a block of one or two warps (blockDim.x = 32 | 64).  With two warps a task above edlib's size rule is split
+ * once at the top by both of them -- the left half pass on warp 0, the reversed right half pass on warp 1 -- and each warp
+ * then aligns its own side of the split (lf_large_path); the op strings are joined when both are done.  The top-level
+ * passes are half of a Hirschberg alignment's work and the two sides the other half, so a multi-kbp task (the
+ * wrong-candidate gaps of configs[3]: one warp needed ~10 ms for 5 kbp x 5 kbp) takes about half as long.  Everything
+ * else -- leaves, distance-only tasks -- runs on warp 0 alone. */
+__device__ __forceinline__ void lf_large_task(const LfDev &d, uint32_t ti, const LfLargeCfg &cfg, uint8_t *scr0, uint8_t *scr1, int32_t *sh)
+{
+    const int lane = threadIdx.x & 31, warp = (int)(threadIdx.x >> 5);
+    const bool two = blockDim.x > 32;
+    const lf_align_task task = d.tasks[ti];
+    const int q = (int)task.q_len, t = (int)task.t_len;
+    LfQView qv; LfTView tv;
+    lf_task_views(d, task, qv, tv);
+    const LfLargeScr S0(scr0, cfg), S1(two ? scr1 : scr0, cfg);
+    const LfLargeScr &S = warp == 0 ? S0 : S1;
+
+    const bool shw = task.mode == LF_MODE_SHW;
+    const bool want = !(task.flags & LF_F_NO_PATH);
+    int ed = -1, end = t - 1;
+    bool stored = false; /* planes of the whole task are already in `planes` */
+    if (warp == 0) {
+        if (!shw && want && lf_is_leaf((uint32_t)q, (uint32_t)t)) {
+            LfPassOut o = lf_wave_pass(d, qv, q, tv, t, LF_PASS_STORE, S.planes, S.hb, nullptr);
+            ed = o.ed; stored = true;
+        } else if (!shw && want) {
+            ed = -1; /* the first split yields min_x L[x]+R[x] = the distance */
+        } else {
+            LfPassOut o = lf_wave_pass(d, qv, q, tv, t, shw ? LF_PASS_SHW : 0, S.planes, S.hb, nullptr);
+            if (shw) { ed = o.best; end = o.bestc; } else ed = o.ed;
+        }
+    }
+    if (two) {   /* warp 1 needs the prefix-mode end column and the distance */
+        if (warp == 0 && lane == 0) { sh[0] = ed; sh[1] = end; }
+        __syncthreads();
+        ed = sh[0]; end = sh[1];
+        __syncthreads();
+    }
+    const uint64_t slot_hi = d.slot_end[ti] * 16ull;
+    lf_align_result r;
+    r.edit_distance = ed; r.end_location = end; r.status = 0; r.ops_len = 0; r.ops_off = slot_hi;
+    if (!want) { if (warp == 0 && lane == 0) d.res[ti] = r; return; }
+
+    const int teff = end + 1;
+    int status = 0;
+    long long n0 = 0, n1 = 0;
+    const bool par = two && q > 0 && teff > 1 && !lf_is_leaf((uint32_t)q, (uint32_t)teff);
+    if (!par) {
+        if (warp == 0) n0 = lf_large_path(d, qv, tv, 0, q, 0, teff, ed, S0, stored, ed, status);
+    } else {
+        const int lw = teff / 2, rw = teff - lw;
+        if (warp == 0) lf_wave_pass(d, qv, q, lf_tsub(tv, 0, lw, false), lw, LF_PASS_COL, S0.planes, S0.hb, S0.Lc);
+        else lf_wave_pass(d, lf_qsub(qv, 0, q, true), q, lf_tsub(tv, lw, rw, true), rw, LF_PASS_COL, S1.planes, S1.hb, S0.Rc);
+        __syncthreads();
+        int best = ed, ls = 0, rs = 0;
+        const int x = lf_large_split_row(S0.Lc, S0.Rc, q, lw, rw, best, ls, rs);   /* both warps, same answer */
+        ed = best;
+        __syncthreads();   /* S0.Lc / S0.Rc are free again */
+        if (x < 0) status = LF_ERR_CUDA;
+        else if (warp == 0) n0 = lf_large_path(d, qv, tv, 0, x, 0, lw, ls, S0, false, ls, status);
+        else n1 = lf_large_path(d, qv, tv, x, q - x, lw, rw, rs, S1, false, rs, status);
+    }
+    if (two) {
+        if (lane == 0) { sh[2 + warp] = (int32_t)(warp == 0 ? n0 : n1); sh[4 + warp] = status; }
+        __syncthreads();
+        n0 = sh[2]; n1 = sh[3]; status = sh[4] ? sh[4] : sh[5];
+    }
     /* pack one byte per op into the 2-bit stream, left-aligned in the task's slot */
+    const long long outpos = n0 + n1;
     const uint64_t slot_lo_w = d.slot_end[ti] - ((uint32_t)(q + t + 15) >> 4);
     const long long nwords = (outpos + 15) >> 4;
-    for (long long wi = lane; wi < nwords; wi += 32) {
+    for (long long wi = threadIdx.x; wi < nwords; wi += blockDim.x) {
         uint32_t word = 0;
-        for (int k = 0; k < 16; k++) { long long pp = wi * 16 + k; if (pp < outpos) word |= (uint32_t)opsb[pp] << (2 * k); }
+        for (int k = 0; k < 16; k++) {
+            const long long pp = wi * 16 + k;
+            if (pp < outpos) word |= (uint32_t)(pp < n0 ? S0.opsb[pp] : S1.opsb[pp - n0]) << (2 * k);
+        }
         d.ops[slot_lo_w + (uint64_t)wi] = word;
     }
     r.edit_distance = ed;
     r.ops_off = slot_lo_w * 16ull; r.ops_len = (uint32_t)outpos; r.status = status;
-    if (lane == 0) d.res[ti] = r;
-    __syncwarp();
+    if (warp == 0 && lane == 0) d.res[ti] = r;
+    if (two) __syncthreads(); else __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) k_myers_large(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, LfLargeCfg cfg,
+__global__ void __launch_bounds__(64) k_myers_large(LfDev d, const uint32_t *__restrict__ order, uint32_t first, uint32_t count, LfLargeCfg cfg,
                                                     const uint32_t *__restrict__ count_ptr)
 {   /* count_ptr != nullptr: `order + first` is a dense list whose length a previous kernel on the stream left there (the
      * tasks k_myers_bandreg could not certify: a warp finishes one of them in a fraction of the time a single thread
      * of the full-width kernel would, and that latency is the tail of the step) */
-    const int lane = threadIdx.x & 31;
+    __shared__ int32_t s_sh[8];
+    __shared__ uint32_t s_k;
+    const bool two = blockDim.x > 32;
     if (count_ptr) count = *count_ptr;
-    uint8_t *scr = cfg.base + (unsigned long long)blockIdx.x * cfg.stride;
+    uint8_t *scr0 = cfg.base + (unsigned long long)blockIdx.x * (two ? 2ull : 1ull) * cfg.stride;
+    uint8_t *scr1 = scr0 + cfg.stride;
     for (;;) {
         uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(cfg.queue, 1u);
-        k = __shfl_sync(LF_FULL, k, 0);
+        if (two) {
+            if (threadIdx.x == 0) s_k = atomicAdd(cfg.queue, 1u);
+            __syncthreads();
+            k = s_k;
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0) k = atomicAdd(cfg.queue, 1u);
+            k = __shfl_sync(LF_FULL, k, 0);
+        }
         if (k >= count) break;
-        lf_large_task(d, order[first + k], cfg, scr);
+        lf_large_task(d, order[first + k], cfg, scr0, scr1, s_sh);
     }
 }
 
@@ -2308,12 +2394,13 @@ static unsigned long lf_emu_band_ok = 0, lf_emu_band_retry = 0; /* test-only vis
 #define LF_BAND_C 8
 
 __host__ __device__ __forceinline__ uint32_t lf_bucket_hi(uint32_t t)
-{ /* largest target length in t's sort bucket (1/8 octave, see k_align_prep) */
-    if (t < 8u) return t ? t : 1u;
+{ /* largest target length in t's sort bucket (see k_align_prep) */
+    constexpr uint32_t MB = LF_BUCKET_BITS;
+    if (t < (1u << MB)) return t ? t : 1u;
     uint32_t e = 31u;
     while (!(t >> e)) e--;
-    const uint32_t m = (t >> (e - 3u)) & 7u;
-    return ((9u + m) << (e - 3u)) - 1u;
+    const uint32_t m = (t >> (e - MB)) & ((1u << MB) - 1u);
+    return (((1u << MB) + m + 1u) << (e - MB)) - 1u;
 }
 
 struct LfGroupCfg { uint32_t first[LF_CLS_LARGE], count[LF_CLS_LARGE], gbase[LF_CLS_LARGE + 1], nb[LF_CLS_LARGE]; };
@@ -2711,10 +2798,15 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     if (task.flags & LF_F_NO_PATH) { r.ops_off = slot_hi; r.ops_len = 0; d.res[ti] = r; return; }
 
     /* ---- traceback: Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
+    /* Ops are packed 16 per word, last op first, into the top word of a 64-bit accumulator at bit `sh`; a word that is
+     * complete is stored and the accumulator moves up.  LF_EMITK appends nz matches (op 0) and then, if `has`, one op. */
     uint32_t *wptr = d.ops + (slot_hi >> 4) - 1;
-    uint32_t cur = 0, nops = 0;
+    unsigned long long acc = 0;
+    uint32_t nops = 0;
     int sh = 30;
-#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
+#define LF_EMITK(nz, op, has) do { int p_ = sh - 2 * (int)(nz); if (has) { acc |= (unsigned long long)(op) << (32 + p_); p_ -= 2; } nops += (uint32_t)(nz) + ((has) ? 1u : 0u); \
+        if (p_ < 0) { *wptr-- = (uint32_t)(acc >> 32); acc <<= 32; p_ += 32; } sh = p_; } while (0)
+#define LF_EMIT(op) LF_EMITK(0, op, true)
     int i = q, j = t;
     const int q8 = (int)((8u * (uint32_t)q) / (uint32_t)t), r8 = (int)((8u * (uint32_t)q) % (uint32_t)t);
     int bc0 = ((t - 1) / C) * C;                 /* block the band bookkeeping below refers to */
@@ -2761,21 +2853,38 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         else if (N2 < N1 && ns <= N2) lf_bandreg_block<NB, N2, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else if (N1 < NB && ns <= N1) lf_bandreg_block<NB, N1, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else lf_bandreg_block<NB, NB, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        /* walk inside the window, one word-row at a time */
+        /* Walk inside the window, one word-row at a time.  Most ops are matches on a diagonal: an iteration first counts
+         * how many of the next three diagonal cells (inside this word-row and block) are matches, emits them together, and
+         * then takes one general step -- branch-free, so that the lanes of a warp (each on its own task) stay together:
+         * 3.2 ops per iteration at 15 % divergence for ~2.2x the instructions of the one-op step. */
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
             const int wrow = (i - 1) >> 5;
             const uint32_t *cell = smt + (size_t)((j - 1 - c0) * 2 + (wrow - wtop)) * 2 * 128;
             int b = (i - 1) & 31;
             do {
-                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
+                const int jj = j - 1 - c0;                                   /* columns of the block to the left of this cell */
+                const uint32_t *c1p = cell - (jj >= 1 ? CS : 0), *c2p = cell - (jj >= 2 ? 2 * CS : 0);
+                /* bit b of m_k: cell k of the diagonal is not a match (or lies above row 0 of this word-row) */
+                const uint32_t m0 = cell[0] | cell[128];
+                const uint32_t m1 = ((c1p[0] | c1p[128]) << 1) | 1u;
+                const uint32_t m2 = ((c2p[0] | c2p[128]) << 2) | 3u;
+                uint32_t nm = ((m0 >> b) & 1u) | (((m1 >> b) & 1u) << 1) | (((m2 >> b) & 1u) << 2) | 8u;
+                nm |= jj < 2 ? (jj < 1 ? 2u : 4u) : 0u;                      /* ... or left of the block */
+                const int nz = __ffs((int)nm) - 1;                           /* 0 .. 3 matches */
+                b -= nz; j -= nz; cell -= nz * CS;
+                const bool has = b >= 0 && j > c0;
+                const uint32_t *cg = has ? cell : smt;
+                const uint32_t x0 = cg[0] >> (b & 31), x1 = cg[128] >> (b & 31);
                 const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
                 const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
                 const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
-                LF_EMIT(op);
-                b -= 1 - stay_row;
-                j -= 1 - stay_col;
-                cell -= (1 - stay_col) * CS;
+                LF_EMITK(nz, op, has);
+                if (has) {
+                    b -= 1 - stay_row;
+                    j -= 1 - stay_col;
+                    cell -= (1 - stay_col) * CS;
+                }
             } while (b >= 0 && j > c0);
             i = wrow * 32 + b + 1;
         }
@@ -2783,8 +2892,9 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     }
     while (i > 0 && !lost) { LF_EMIT(1u); i--; }
     while (j > 0 && !lost) { LF_EMIT(2u); j--; }
-    if (sh != 30) *wptr = cur;
+    if (sh != 30) *wptr = (uint32_t)(acc >> 32);
 #undef LF_EMIT
+#undef LF_EMITK
     if (lost) { retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
     r.ops_off = slot_hi - nops; r.ops_len = nops;
     d.res[ti] = r;

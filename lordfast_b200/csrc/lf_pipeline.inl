@@ -403,18 +403,19 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     if (nlarge) {
         LfLargeCfg cfg = large_cfg(ht->cnt.max_q, ht->cnt.max_t, ht->cnt.max_planes);
         /* persistent grid of warp slots; bounded so that the scratch stays within a few GB */
-        size_t slots = 148 * 16;
+        /* blocks of two warps (two scratch slots each): a task above edlib's size rule is split once by both */
+        size_t slots = 148 * 8;
         const size_t budget = (size_t)8 << 30;
-        if (slots * cfg.stride > budget) slots = budget / cfg.stride;
+        if (slots * 2 * cfg.stride > budget) slots = budget / (2 * cfg.stride);
         if (slots < 1) slots = 1;
         if (slots > nlarge) slots = nlarge;
-        LF_TRY(d.large_scr.reserve(slots * cfg.stride));
+        LF_TRY(d.large_scr.reserve(slots * 2 * cfg.stride));
         cfg.base = d.large_scr.as<uint8_t>();
         cfg.queue = d.queue.as<uint32_t>();
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][0], d.sub[0]);
 #endif
-        LFB_LAUNCH(k_myers_large, (unsigned)slots, 32, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg, (const uint32_t *)nullptr);
+        LFB_LAUNCH(k_myers_large, (unsigned)slots, 64, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg, (const uint32_t *)nullptr);
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][1], d.sub[0]);
 #endif
