@@ -961,18 +961,29 @@ __device__ __forceinline__ LfPassOut lf_wave_pass_t(const LfDev &d, const LfQVie
  * LANES * WPL words.  Per word-column: 14 instructions of recurrence + 4 when the planes are stored + 2 for the
  * prefix-mode score, and ~12 per lane and column of bookkeeping, amortised over WPL words.
  * Planes layout (as lf_wave_pass_t with one strip): uint2 at planes[(column * nv + lane) * WPL + k]. */
-template <int LANES, int WPL, int FLAGS>
-__device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, uint2 *planes, int32_t *col)
+template <int LANES, int WPL, int FLAGS, bool MULTI = false>
+__device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, uint2 *planes, int32_t *col, int8_t *hb = nullptr)
 {
+    /* MULTI: queries of more than LANES * WPL words run as strips of that many words one after the other, chained through
+     * hb[] (hout of a strip's bottom row per column) -- the junk heads / tails of 10+ kbp that wrong-candidate chains of
+     * 20 kbp reads leave (configs[3]); planes are not stored in this form. */
+    static_assert(!(MULTI && (FLAGS & LF_PASS_STORE)), "");
     constexpr int CB = LF_WAVE_CB;
+    constexpr int SW = LANES * WPL;
     const int gl = (int)(threadIdx.x & (LANES - 1));
     const int n = (ql + 31) >> 5;
-    const int nv = (n + WPL - 1) / WPL;
-    const bool valid = gl < nv;
-    const int w0 = gl * WPL;
+    const int S = MULTI ? (n + SW - 1) / SW : 1;
     const int wl = ql > 0 ? (ql - 1) >> 5 : -1;
     const uint32_t bl = (uint32_t)(ql - 1) & 31u;
     const int nblocks = (tl + CB - 1) / CB;
+    int score = ql, best = ql, bestc = -1;     /* followed by the lane that owns row ql-1 */
+    int colbase = tl;                          /* D(first row of the strip, tl) */
+    if ((FLAGS & LF_PASS_COL) && gl == 0 && ql > 0) col[0] = tl;
+    for (int s = 0; s < S; s++) {
+    const int nvw = MULTI ? (n - s * SW < SW ? n - s * SW : SW) : n;
+    const int nv = (nvw + WPL - 1) / WPL;
+    const bool valid = gl < nv;
+    const int w0 = (s * LANES + gl) * WPL;
     const int nsteps = lf_warp_max(ql > 0 ? nblocks + nv - 1 : 0);
     uint32_t lo[WPL], hi[WPL], nn[WPL], Pv[WPL], Mv[WPL], wm[WPL];
 #pragma unroll
@@ -982,7 +993,6 @@ __device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv,
         Pv[k] = 0xffffffffu; Mv[k] = 0u;
         wm[k] = ((FLAGS & LF_PASS_SHW) && w0 + k == wl) ? 1u << bl : 0u;   /* the bit of row ql-1 */
     }
-    int score = ql, best = ql, bestc = -1;     /* followed by the lane that owns row ql-1 */
     LfTStream ts;
     ts.init(d.pac, ql > 0 ? tv.t0 : 0, ql > 0 ? tv.dir : 1);
     uint32_t pay = 0;                          /* (Ph, Mh) of this lane's bottom row for the columns of its last block */
@@ -991,12 +1001,19 @@ __device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv,
         const int cb = step - gl;
         pay = 0;
         if (valid && cb >= 0 && cb < nblocks) {
-            if (gl == 0) in = 0x5555u;         /* row 0 of a global alignment grows by one per column */
             const int cbase = cb * CB;
             const int ncol = tl - cbase < CB ? tl - cbase : CB;
+            if (gl == 0) {
+                in = 0x5555u;                  /* row 0 of a global alignment grows by one per column */
+                if (MULTI && s > 0) {          /* ... or continues the strip above */
+                    in = 0;
+                    for (int ci = 0; ci < ncol; ci++) { const int h = hb[cbase + ci]; in |= ((h > 0 ? 1u : 0u) | (h < 0 ? 2u : 0u)) << (2 * ci); }
+                }
+            }
             uint32_t tb = ts.peek();
             ts.advance(ncol);
             uint2 *dst = (FLAGS & LF_PASS_STORE) ? planes + ((size_t)cbase * nv + gl) * WPL : nullptr;
+            const bool feed = MULTI && gl == nv - 1 && s + 1 < S;   /* this lane's bottom row is the next strip's top */
             int sh2 = 0;
             for (int ci = 0; ci < ncol; ci++) {
                 const uint32_t shi = (uint32_t)((int32_t)tb >> 31), slo = (uint32_t)((int32_t)(tb << 1) >> 31);
@@ -1035,6 +1052,7 @@ __device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv,
                 }
                 pay |= ((pPh >> 31) | ((pMh >> 31) << 1)) << sh2;
                 sh2 += 2;
+                if (feed) hb[cbase + ci] = (int8_t)((int)(pPh >> 31) - (int)(pMh >> 31));
                 if (FLAGS & LF_PASS_STORE) dst += (size_t)nv * WPL;
             }
         }
@@ -1051,9 +1069,8 @@ __device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv,
 #pragma unroll
     for (int o = 1; o < LANES; o <<= 1) { const int v = __shfl_up_sync(LF_FULL, incl, o, LANES); if (gl >= o) incl += v; }
     if (FLAGS & LF_PASS_COL) {
-        if (gl == 0 && ql > 0) col[0] = tl;
         if (valid) {
-            int v = tl + incl - cnt;
+            int v = colbase + incl - cnt;
 #pragma unroll
             for (int k = 0; k < WPL; k++) {
                 const int w = w0 + k;
@@ -1062,9 +1079,12 @@ __device__ __forceinline__ LfPassOut lf_gwave(const LfDev &d, const LfQView &qv,
             }
         }
     }
+    colbase += __shfl_sync(LF_FULL, incl, LANES - 1, LANES);
+    if (MULTI) __syncwarp();                   /* hb[] written by the last lane is read by lane 0 of the next strip */
+    }
     LfPassOut o;
-    o.ed = tl + __shfl_sync(LF_FULL, incl, LANES - 1, LANES);
-    const int owner = wl >= 0 ? wl / WPL : 0;
+    o.ed = colbase;
+    const int owner = wl >= 0 ? (wl % SW) / WPL : 0;
     o.best = __shfl_sync(LF_FULL, best, owner, LANES);
     o.bestc = __shfl_sync(LF_FULL, bestc, owner, LANES);
     return o;
@@ -1074,7 +1094,14 @@ template <int WPL>
 __device__ __forceinline__ LfPassOut lf_wave_pass_w(const LfDev &d, const LfQView &qv, int ql, const LfTView &tv, int tl, int flags,
                                                     uint2 *planes, int8_t *hb, int32_t *col)
 {
-    if (((ql + 31) >> 5) > 32 * WPL) return lf_wave_pass_t<WPL>(d, qv, ql, tv, tl, flags, planes, hb, col);   /* several strips (queries above 8192 rows) */
+    if constexpr (WPL == 8) if (((ql + 31) >> 5) > 32 * WPL) {   /* several strips (queries above 8192 rows) */
+        switch (flags) {
+        case LF_PASS_SHW: return lf_gwave<32, WPL, LF_PASS_SHW, true>(d, qv, ql, tv, tl, planes, col, hb);
+        case LF_PASS_COL: return lf_gwave<32, WPL, LF_PASS_COL, true>(d, qv, ql, tv, tl, planes, col, hb);
+        case 0: return lf_gwave<32, WPL, 0, true>(d, qv, ql, tv, tl, planes, col, hb);
+        default: return lf_wave_pass_t<WPL>(d, qv, ql, tv, tl, flags, planes, hb, col);   /* planes of a leaf that tall: the general form */
+        }
+    }
     switch (flags) {
     case LF_PASS_STORE: return lf_gwave<32, WPL, LF_PASS_STORE>(d, qv, ql, tv, tl, planes, col);
     case LF_PASS_SHW: return lf_gwave<32, WPL, LF_PASS_SHW>(d, qv, ql, tv, tl, planes, col);
@@ -2853,15 +2880,28 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         else if (N2 < N1 && ns <= N2) lf_bandreg_block<NB, N2, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else if (N1 < NB && ns <= N1) lf_bandreg_block<NB, N1, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else lf_bandreg_block<NB, NB, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        /* Walk inside the window, one word-row at a time.  Most ops are matches on a diagonal: an iteration first counts
-         * how many of the next three diagonal cells (inside this word-row and block) are matches, emits them together, and
-         * then takes one general step -- branch-free, so that the lanes of a warp (each on its own task) stay together:
-         * 3.2 ops per iteration at 15 % divergence for ~2.2x the instructions of the one-op step. */
+        /* Walk inside the window, one word-row at a time, one op per iteration (28 SASS instructions).
+         * LF_WALK_LOOKAHEAD (measured, not the default): an iteration first counts how many of the next three diagonal cells
+         * (inside this word-row and block) are matches, emits them together, and then takes one general step -- branch-free,
+         * 3.2 ops per iteration at 15 % divergence for 80 instructions, i.e. 25 per op.  On the config-2 step it was 3.5 %
+         * SLOWER (1.879 vs 1.813 ms): the lanes of a warp then leave the inner loop after different numbers of iterations more
+         * often, and the eight shared-memory loads per iteration queue behind each other. */
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
             const int wrow = (i - 1) >> 5;
             const uint32_t *cell = smt + (size_t)((j - 1 - c0) * 2 + (wrow - wtop)) * 2 * 128;
             int b = (i - 1) & 31;
+#ifndef LF_WALK_LOOKAHEAD
+            do {
+                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
+                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
+                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
+                LF_EMIT(op);
+                b -= 1 - stay_row;
+                j -= 1 - stay_col;
+                cell -= (1 - stay_col) * CS;
+#else
             do {
                 const int jj = j - 1 - c0;                                   /* columns of the block to the left of this cell */
                 const uint32_t *c1p = cell - (jj >= 1 ? CS : 0), *c2p = cell - (jj >= 2 ? 2 * CS : 0);
@@ -2885,6 +2925,7 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
                     j -= 1 - stay_col;
                     cell -= (1 - stay_col) * CS;
                 }
+#endif
             } while (b >= 0 && j > c0);
             i = wrow * 32 + b + 1;
         }

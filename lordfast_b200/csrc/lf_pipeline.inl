@@ -415,7 +415,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][0], d.sub[0]);
 #endif
-        LFB_LAUNCH(k_myers_large, (unsigned)slots, 64, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg, (const uint32_t *)nullptr);
+        LFB_LAUNCH(k_myers_large, (unsigned)slots, getenv("LF_LARGE_ONE_WARP") ? 32 : 64, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg, (const uint32_t *)nullptr);
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][1], d.sub[0]);
 #endif
