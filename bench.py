@@ -259,11 +259,11 @@ def sweep_summary():
     if not os.path.exists(SWEEP):
         return None
     pts = [json.loads(l) for l in open(SWEEP) if l.strip().startswith("{")]
-    nw = [p for p in pts if p.get("kind") == "nw" and "frac" in p]
+    nw = [p for p in pts if p.get("kind") in ("NW", "SHW") and "roofline_frac" in p]
     if not nw:
         return None
-    lo, hi = min(nw, key=lambda p: p["frac"]), max(nw, key=lambda p: p["frac"])
-    brief = lambda p: {k: p[k] for k in ("L", "d", "pairs", "kernel_ms", "gcups", "frac") if k in p}
+    lo, hi = min(nw, key=lambda p: p["roofline_frac"]), max(nw, key=lambda p: p["roofline_frac"])
+    brief = lambda p: {k: p[k] for k in ("kind", "L", "div", "pairs", "kernel_ms", "gcups", "roofline_frac", "oracle_mismatches") if k in p}
     return {"source": os.path.relpath(SWEEP, ROOT), "points": len(nw), "worst": brief(lo), "best": brief(hi)}
 
 

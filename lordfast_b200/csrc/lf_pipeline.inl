@@ -456,7 +456,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
                 const GroupShape gs = group_shape(cls, gwide[cls]);
                 const unsigned per_block = 4u * (32u / (unsigned)gs.lanes);   /* tasks a block works on at a time */
                 unsigned blocks = (count + per_block - 1) / per_block;
-                if (blocks > 148u * 4u) blocks = 148u * 4u;
+                if (blocks > 148u * 6u) blocks = 148u * 6u;
                 size_t stride = 0;
                 if (gs.path) {
                     stride = align_up((size_t)ht->cnt.gmax_t[cls - LF_CLS_GP16] * (size_t)(gs.lanes * gs.wpl) * 8 + 256, 256);
