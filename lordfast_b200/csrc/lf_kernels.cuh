@@ -2658,7 +2658,7 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
  *              2-word window written to shared memory, walk Up > Left > Diagonal inside the window.
  * Tasks that fail the certificate are appended to the retry list and redone full width by k_myers_small.
  * k_align_prep routes only tasks with 3*|q-t| <= 32*(NB-1)-7 here (classes LF_CLS_BANDREG0..+3). */
-template <int NB, bool STORE>
+template <int NB, bool STORE, int WIN = 2>
 __device__ __forceinline__ void lf_bandreg_column(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], const uint32_t (&qlo)[NB], const uint32_t (&qhi)[NB],
                                                   const uint32_t (&qnn)[NB], uint32_t slo, uint32_t shi, uint32_t *sm, int wrel0)
 { /* STORE: band words wrel0, wrel0+1 are the window words 0, 1 of this column */
@@ -2682,7 +2682,7 @@ __device__ __forceinline__ void lf_bandreg_column(uint32_t (&Pv)[NB], uint32_t (
         const uint32_t nMv = Phs & Xv;
         if (STORE) {
             const unsigned wi = (unsigned)(w - wrel0);
-            if (wi < 2u) {
+            if (wi < (unsigned)WIN) {
                 const uint32_t diagx = ~(nPv | Ph) & nEq[w];          /* diagonal step over a mismatch */
                 sm[(wi * 2 + 0) * 128] = nPv | diagx;               /* ops 1, 3 */
                 sm[(wi * 2 + 1) * 128] = (~nPv & Ph) | diagx;       /* ops 2, 3 */
@@ -2719,7 +2719,8 @@ __device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv_)[NBF], uint32_t 
     uint32_t (&qlo)[NB] = reinterpret_cast<uint32_t (&)[NB]>(qlo_);
     uint32_t (&qhi)[NB] = reinterpret_cast<uint32_t (&)[NB]>(qhi_);
     uint32_t (&qnn)[NB] = reinterpret_cast<uint32_t (&)[NB]>(qnn_);
-    constexpr int CS = 2 * 2 * 128;
+    constexpr int WIN = NBF < 2 ? 1 : 2;
+    constexpr int CS = WIN * 2 * 128;
     const int es = cslide - c;                         /* the block slides before its column es, if 0 <= es < n */
     const int nn = FULL ? 8 : n;
     /* One copy of the column body (unrolled by two) and one of the slide: ~20 size-class kernels share an SM's
@@ -2732,7 +2733,7 @@ __device__ __forceinline__ void lf_bandreg_block(uint32_t (&Pv_)[NBF], uint32_t 
         for (; e < stop; e++) {
             const uint32_t shi = (uint32_t)((int32_t)tb >> 31), slo = (uint32_t)((int32_t)(tb << 1) >> 31);
             tb <<= 2;
-            lf_bandreg_column<NB, STORE>(Pv, Mv, qlo, qhi, qnn, slo, shi, STORE ? smt + e * CS : nullptr, wtop - k);
+            lf_bandreg_column<NB, STORE, WIN>(Pv, Mv, qlo, qhi, qnn, slo, shi, STORE ? smt + e * CS : nullptr, wtop - k);
         }
         if (e >= nn) break;
         /* slide one word down: the top word's vertical deltas move into `top` */
@@ -2756,7 +2757,8 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
                                                        uint32_t *retry_list, uint32_t *retry_count, int nwmax)
 {
     constexpr int C = 8;
-    constexpr int CS = 2 * 2 * 128; /* shared-memory words per column: [2 window words][2 planes][128 threads] */
+    constexpr int WIN = NB < 2 ? 1 : 2;   /* one-word tasks need one window word: half the shared memory, twice the resident blocks */
+    constexpr int CS = WIN * 2 * 128; /* shared-memory words per column: [window words][2 planes][128 threads] */
     LF_DYN_SMEM(uint32_t, smem);    /* window planes [C][2][2][128] */
     const uint32_t tid = threadIdx.x;
     const uint32_t gi = blockIdx.x * 128u + tid;
@@ -2862,7 +2864,7 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         if (ks != k0) { ks = k0; cs_of_ks = lf_bandreg_next_slide<NB>(k0, kmax, q, t); }
         cslide = cs_of_ks;
         const int whi = (i - 1) >> 5;
-        const int wtop = whi - 1 > 0 ? whi - 1 : 0;
+        const int wtop = whi - WIN + 1 > 0 ? whi - WIN + 1 : 0;
         const int need = whi - k0 + 1;            /* band words down to the row the walk stands on */
         if (c0 == 0) {
 #pragma unroll
@@ -2889,7 +2891,7 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
             const int wrow = (i - 1) >> 5;
-            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * 2 + (wrow - wtop)) * 2 * 128;
+            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * 128;
             int b = (i - 1) & 31;
 #ifndef LF_WALK_LOOKAHEAD
             do {

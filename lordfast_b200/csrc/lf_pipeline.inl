@@ -184,7 +184,7 @@ void launch_small(const LfDev &v, const uint32_t *order, uint32_t first, uint32_
 template <int NB, bool SLIDE = true>
 void launch_bandreg(const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, lfb_stream s, uint32_t *retry_list, uint32_t *retry_count, int nwmax)
 {   /* shared memory: the window planes of 8 columns, as much as the other size-class kernels use */
-    const size_t smem = (size_t)8 * 2 * 2 * 128 * sizeof(uint32_t);
+    const size_t smem = (size_t)8 * (NB < 2 ? 1 : 2) * 2 * 128 * sizeof(uint32_t);
     auto kern = k_myers_bandreg<NB, SLIDE>;
     LFB_LAUNCH(kern, (count + 127) / 128, 128, smem, s, v, order, first, count, retry_list, retry_count, nwmax);
 }
