@@ -352,7 +352,9 @@ def main():
 
     # ---- e2e: lf_gpu_align_chains (the batched alignChain_edlib), host buffers in, records + text out ----
     cg = api.Contigs(si.contig_off.ctypes.data, si.contig_len.ctypes.data, len(si.contig_off))
-    seeds_a, chains_a = np.ascontiguousarray(si.seeds), np.ascontiguousarray(si.chains)
+    # seeds and chains in pinned memory, as the glue keeps them (integration/lordfast_gpu_glue.cpp): the library reads them as they are
+    p_seeds = api.PinnedArray(g.lib, si.seeds.nbytes + 64); seeds_a = p_seeds.view(api.SEED, len(si.seeds)); seeds_a[:] = si.seeds
+    p_chains = api.PinnedArray(g.lib, si.chains.nbytes + 64); chains_a = p_chains.view(api.CHAIN, len(si.chains)); chains_a[:] = si.chains
 
     def chain_call(gk):
         out = C.c_void_p()
@@ -465,7 +467,7 @@ def main():
             v, kind, cores, sample = cpu_reference_rate(si, os.cpu_count() or 1, max_chains=4000)
             out["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(out))
-    p_tasks.free(); p_bases.free()
+    p_tasks.free(); p_bases.free(); p_seeds.free(); p_chains.free()
     g.close()
     if world > 1:
         dist.destroy_process_group()

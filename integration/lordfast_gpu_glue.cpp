@@ -271,8 +271,12 @@ void mapSeqMT()
     /* merge the workers' lists; gather the chunk's reads (each its own malloc block, src/Reads.cpp:84-90) */
     uint64_t ns = 0, nc = 0;
     for (Worker &W : g_workers) { W.seed_base = ns; W.chain_base = nc; ns += W.seeds.size(); nc += W.chains.size(); }
-    std::vector<lf_seed> seeds(ns);
-    std::vector<lf_chain> chains(nc);
+    /* seeds and chains of the chunk in pinned memory kept between chunks: the library then reads them over PCIe as they are
+     * (from pageable memory it would first stage them, one more pass over 12 B per seed) */
+    static lf_seed *seeds = nullptr; static lf_chain *chains = nullptr;
+    static size_t seeds_cap = 0, chains_cap = 0;
+    if (ns + 2 > seeds_cap) { if (seeds) lf_gpu_host_free(seeds); seeds_cap = (ns + 2) * 5 / 4; seeds = (lf_seed *)lf_gpu_host_alloc(seeds_cap * sizeof(lf_seed)); if (!seeds) die("lf_gpu_host_alloc", LF_ERR_NOMEM); }
+    if (nc + 2 > chains_cap) { if (chains) lf_gpu_host_free(chains); chains_cap = (nc + 2) * 5 / 4; chains = (lf_chain *)lf_gpu_host_alloc(chains_cap * sizeof(lf_chain)); if (!chains) die("lf_gpu_host_alloc", LF_ERR_NOMEM); }
     for (Worker &W : g_workers) {
         if (!W.seeds.empty()) memcpy(&seeds[W.seed_base], W.seeds.data(), W.seeds.size() * sizeof(lf_seed));
         for (size_t k = 0; k < W.chains.size(); k++) { lf_chain c = W.chains[k]; c.seed_off += W.seed_base; chains[W.chain_base + k] = c; }
@@ -307,7 +311,7 @@ void mapSeqMT()
     size_t nrec = 0;
     g_rec = nullptr; g_text = nullptr;
     if (nc) {
-        int rc = lf_gpu_align_chains(g_ctx, &rd, &cg, seeds.data(), chains.data(), chains.size(), _fmd_index->pac, &res);
+        int rc = lf_gpu_align_chains(g_ctx, &rd, &cg, seeds, chains, (size_t)nc, _fmd_index->pac, &res);
         if (rc != LF_OK) die("lf_gpu_align_chains", rc);
         g_rec = lf_chain_results_records(res, &nrec);
         g_text = lf_chain_results_text(res, nullptr);

@@ -57,6 +57,8 @@ static inline int lfb_memset(void *d, int v, size_t n, lfb_stream s) { LFB_CHECK
 static inline int lfb_sync(lfb_stream s) { LFB_CHECK(cudaStreamSynchronize(s)); return 0; }
 static inline int lfb_last_error() { LFB_CHECK(cudaGetLastError()); return 0; }
 static inline void *lfb_host_alloc(size_t n) { void *p = NULL; return cudaMallocHost(&p, n ? n : 1) == cudaSuccess ? p : NULL; }
+/* is p pinned host memory (cudaMallocHost / lf_gpu_host_alloc) that a kernel may read directly? */
+static inline bool lfb_is_pinned(const void *p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; }
 static inline void lfb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 struct LfbTemp { void *p = nullptr; size_t cap = 0; };
@@ -95,6 +97,7 @@ static inline int lfb_memset(void *d, int v, size_t n, lfb_stream) { memset(d, v
 static inline int lfb_sync(lfb_stream) { return 0; }
 static inline int lfb_last_error() { return 0; }
 static inline void *lfb_host_alloc(size_t n) { return malloc(n ? n : 1); }
+static inline bool lfb_is_pinned(const void *) { return false; }
 static inline void lfb_host_free(void *p) { free(p); }
 struct LfbTemp { void *p = nullptr; size_t cap = 0; };
 static inline int lfb_sort_pairs(LfbTemp &, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, size_t n, lfb_stream)

@@ -336,6 +336,7 @@ struct ChainScratch {
     std::vector<Emit> *parts = nullptr;
     /* device side of the GPU emit */
     EmitSet es[2];          /* [0]: chains no trigger fired for (emitted while rounds 2-3 run), [1]: the rest */
+    LfbBuf d_ntask, d_contigs;
     LfbBuf d_chains, d_seeds, d_task_base, d_guards, d_clip, d_split_begin, d_splits, d_nrec, d_cigb, d_mdb, d_rec_off, d_cig_off, d_md_off, d_recs, d_text, d_ed, d_slot_base, d_slot_info, d_slot_task;
 };
 ChainScratch &chain_scratch(lf_gpu_ctx *ctx);
@@ -451,7 +452,7 @@ void chain_scratch_free_fn(void *p)
     ChainScratch *s = (ChainScratch *)p;
     PinBuf *all[] = { &s->t1, &s->r1, &s->ops1, &s->t3, &s->r3, &s->ops3, &s->e2, &s->x2, &s->ed1, &s->seeds_stage, &s->meta_stage };
     for (PinBuf *b : all) b->release();
-    LfbBuf *dall[] = { &s->d_chains, &s->d_seeds, &s->d_task_base, &s->d_guards, &s->d_clip, &s->d_split_begin, &s->d_splits, &s->d_nrec, &s->d_cigb, &s->d_mdb,
+    LfbBuf *dall[] = { &s->d_ntask, &s->d_contigs, &s->d_chains, &s->d_seeds, &s->d_task_base, &s->d_guards, &s->d_clip, &s->d_split_begin, &s->d_splits, &s->d_nrec, &s->d_cigb, &s->d_mdb,
                        &s->d_rec_off, &s->d_cig_off, &s->d_md_off, &s->d_recs, &s->d_text, &s->d_ed, &s->d_slot_base, &s->d_slot_info, &s->d_slot_task };
     for (LfbBuf *b : dall) b->release();
     s->es[0].release(); s->es[1].release();
@@ -560,15 +561,20 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         size_t ns = 0;
         for (size_t c = 0; c < n_chains; c++) { const size_t e = (size_t)chains[c].seed_off + chains[c].n_seeds; if (e > ns) ns = e; }
         if (S.d_chains.reserve(n_chains * sizeof(lf_chain) + 64) || S.d_seeds.reserve(ns * sizeof(lf_seed) + 64)) { delete R; return LF_ERR_NOMEM; }
-        /* the caller's seed array is ordinary (pageable) memory: stage it through pinned memory with all host
-         * threads so that the copy to the device is asynchronous and overlaps the task generation */
-        char *stage = (char *)S.seeds_stage.reserve(ns * sizeof(lf_seed) + n_chains * sizeof(lf_chain) + 128);
-        if (!stage) { delete R; return LF_ERR_NOMEM; }
+        /* A seed array in ordinary (pageable) memory is staged through pinned memory with all host threads, so that the copy
+         * to the device is asynchronous; a caller that keeps its seeds and chains in pinned memory (lf_gpu_host_alloc) saves
+         * that pass over 12 B per seed.  Either way the device reads them by kernel, not by the copy engine: there the copy
+         * would wait behind the reads. */
         const size_t sb = ns * sizeof(lf_seed), cb = (sb + 63) & ~(size_t)63;
-        parallel_for(sb, nthreads, [&](unsigned, size_t lo, size_t hi) { memcpy(stage + lo, (const char *)seeds + lo, hi - lo); }, 1 << 20);
-        memcpy(stage + cb, chains, n_chains * sizeof(lf_chain));
-        /* by kernel, not by the copy engine: there the copy would wait behind the reads of all lanes of the call */
-        if (h2d_k(d, S.d_seeds.p, stage, sb, d.stream, true) || h2d_k(d, S.d_chains.p, stage + cb, n_chains * sizeof(lf_chain), d.stream, true)) { delete R; return LF_ERR_CUDA; }
+        const char *src_seeds = (const char *)seeds, *src_chains = (const char *)chains;
+        if (!(lfb_is_pinned(seeds) && !((uintptr_t)seeds & 15u)) || !(lfb_is_pinned(chains) && !((uintptr_t)chains & 15u))) {
+            char *stage = (char *)S.seeds_stage.reserve(ns * sizeof(lf_seed) + n_chains * sizeof(lf_chain) + 128);
+            if (!stage) { delete R; return LF_ERR_NOMEM; }
+            parallel_for(sb, nthreads, [&](unsigned, size_t lo, size_t hi) { memcpy(stage + lo, (const char *)seeds + lo, hi - lo); }, 1 << 20);
+            memcpy(stage + cb, chains, n_chains * sizeof(lf_chain));
+            src_seeds = stage; src_chains = stage + cb;
+        }
+        if (h2d_k(d, S.d_seeds.p, src_seeds, sb, d.stream, true) || h2d_k(d, S.d_chains.p, src_chains, n_chains * sizeof(lf_chain), d.stream, true)) { delete R; return LF_ERR_CUDA; }
     }
 
     /* ---------------- round 1: tasks known from the chains alone ---------------- */
@@ -586,6 +592,40 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     std::vector<uint64_t> nslot(n_chains, 0); /* op-slot words of the chain's round-1 tasks */
     std::atomic<bool> bad_rid(false);   /* a chain the reference's chaining could not have produced (or a contig lookup that failed) */
     const double tt2 = now_ms();
+    /* single-device contexts: the task list is generated on the device (k_chain_tasks); the host only needs the few
+     * tasks a trigger fires for, and re-derives those from the chain (task_at below) */
+    const bool dev_tasks = gpu_emit && !getenv("LF_CHAIN_HOST_TASKS");
+    /* ... and so is pass A (k_chain_plan): boundaries, guards, task counts, trigger candidates, validation.  What comes back
+     * is 9 B per chain.  LF_CHAIN_HOST_PLAN=1: the host loop below instead (also the path of the multi-device host emit). */
+    const bool dev_plan = dev_tasks && !getenv("LF_CHAIN_HOST_PLAN");
+    if (dev_plan) {
+        DevState &d = ctx->devs[0];
+        const size_t nc = (size_t)contigs->n;
+        if (S.d_task_base.reserve((n_chains + 1) * 8 + 64) || S.d_guards.reserve(n_chains + 64) || S.d_ntask.reserve(n_chains * 4 + 64)
+            || S.d_contigs.reserve(nc * 12 + 128)) { delete R; return LF_ERR_NOMEM; }
+        const size_t co_b = (nc * 8 + 63) & ~(size_t)63;
+        char *cs = (char *)stage_get(d, co_b + nc * 4 + 64);
+        const size_t back_b = (n_chains + 1) * 8 + n_chains + 64;
+        char *back = (char *)S.r1.reserve(back_b);   /* pinned landing zone: task_base, guards, bad flag */
+        if (!cs || !back) { delete R; return LF_ERR_NOMEM; }
+        memcpy(cs, contigs->offset, nc * 8); memcpy(cs + co_b, contigs->len, nc * 4);
+        uint32_t *d_bad = d.queue.as<uint32_t>();   /* the work-counter block is idle until run_align clears it */
+        if (d.queue.reserve(256) || h2d_k(d, S.d_contigs.p, cs, co_b + nc * 4, d.stream, true) || lfb_memset((d_bad = d.queue.as<uint32_t>()) + 60, 0, 4, d.stream)) { delete R; return LF_ERR_CUDA; }
+        LFB_LAUNCH(k_chain_plan, (unsigned)((n_chains + 3) / 4), 128, 0, d.stream, S.d_chains.as<lf_chain>(), S.d_seeds.as<lf_seed>(), d.read_off.as<uint64_t>(), reads->n_reads,
+                   (const int64_t *)S.d_contigs.p, (const int32_t *)((const char *)S.d_contigs.p + co_b), (int)nc, ctx->l_pac, (uint32_t)n_chains,
+                   S.d_guards.as<uint8_t>(), S.d_ntask.as<uint32_t>(), d_bad + 60);
+        if (lfb_scan_excl_total(d.tmp, S.d_ntask.as<uint32_t>(), S.d_task_base.as<unsigned long long>(), n_chains, d.stream)
+            || lfb_d2h(back, S.d_task_base.p, (n_chains + 1) * 8, d.stream) || lfb_d2h(back + (n_chains + 1) * 8, S.d_guards.p, n_chains, d.stream)
+            || lfb_d2h(back + (n_chains + 1) * 8 + n_chains + (8 - n_chains % 8) % 8, d_bad + 60, 4, d.stream) || lfb_sync(d.stream)) { delete R; return LF_ERR_CUDA; }
+        uint32_t badflag; memcpy(&badflag, back + (n_chains + 1) * 8 + n_chains + (8 - n_chains % 8) % 8, 4);
+        if (badflag) bad_rid = true;
+        memcpy(task_base.data(), back, (n_chains + 1) * 8);
+        const uint8_t *gd = (const uint8_t *)back + (n_chains + 1) * 8;
+        for (size_t c = 0; c < n_chains; c++) {
+            plan[c].head_guard = (gd[c] & 1) != 0; plan[c].tail_guard = (gd[c] & 2) != 0; hascand[c] = (gd[c] >> 2) & 1;
+            ntask[c] = (uint32_t)(task_base[c + 1] - task_base[c]);
+        }
+    } else
     /* pass A: boundaries, guards and task counts per chain */
     parallel_for(n_chains, nthreads, [&](unsigned, size_t lo, size_t hi) {
         for (size_t c = lo; c < hi; c++) {
@@ -625,12 +665,9 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         }
     });
     const double tt3 = now_ms();
-    if (bad_rid) { delete R; return LF_ERR_BAD_ARG; }
-    for (size_t c = 0; c < n_chains; c++) task_base[c + 1] = task_base[c] + ntask[c];
+    if (bad_rid) { delete R; return fail(ctx, LF_ERR_BAD_ARG, "a chain is not one the reference's chaining can produce (seeds out of order, overlapping, or outside the read / reference)"); }
+    if (!dev_plan) for (size_t c = 0; c < n_chains; c++) task_base[c + 1] = task_base[c] + ntask[c];
     const size_t n1 = task_base[n_chains];
-    /* single-device contexts: the task list is generated on the device (k_chain_tasks); the host only needs the few
-     * tasks a trigger fires for, and re-derives those from the chain (task_at below) */
-    const bool dev_tasks = gpu_emit && !getenv("LF_CHAIN_HOST_TASKS");
     lf_align_task *t1 = dev_tasks ? nullptr : (lf_align_task *)S.t1.reserve((n1 + 1) * sizeof(lf_align_task));
     lf_align_result *r1 = gpu_emit ? nullptr : (lf_align_result *)S.r1.reserve((n1 + 1) * sizeof(lf_align_result));
     if ((!dev_tasks && !t1) || (!gpu_emit && !r1)) { delete R; return LF_ERR_NOMEM; }
@@ -717,8 +754,8 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         char *ms = (char *)S.meta_stage.reserve(2 * mb + n_chains + 128);
         if (!ms) { delete R; return LF_ERR_NOMEM; }
         memcpy(ms, task_base.data(), (n_chains + 1) * 8); memcpy(ms + mb, slot_base.data(), (n_chains + 1) * 8); memcpy(ms + 2 * mb, guards.data(), n_chains);
-        if (h2d_k(d, S.d_task_base.p, ms, (n_chains + 1) * 8, d.stream, true) || h2d_k(d, S.d_slot_base.p, ms + mb, (n_chains + 1) * 8, d.stream, true)
-            || h2d_k(d, S.d_guards.p, ms + 2 * mb, n_chains, d.stream, true)) { delete R; return LF_ERR_CUDA; }
+        if (h2d_k(d, S.d_slot_base.p, ms + mb, (n_chains + 1) * 8, d.stream, true)) { delete R; return LF_ERR_CUDA; }
+        if (!dev_plan && (h2d_k(d, S.d_task_base.p, ms, (n_chains + 1) * 8, d.stream, true) || h2d_k(d, S.d_guards.p, ms + 2 * mb, n_chains, d.stream, true))) { delete R; return LF_ERR_CUDA; }   /* dev_plan: k_chain_plan left them there */
     }
     size_t cap1 = 64;
     for (size_t c = 0; c < n_chains; c++) cap1 += nslot[c] * 4;

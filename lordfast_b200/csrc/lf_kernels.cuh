@@ -2381,6 +2381,69 @@ __global__ void __launch_bounds__(128) k_chain_tasks(const lf_chain *__restrict_
     }
 }
 
+/* Pass A of the chain operator on the device (round 2; it was a loop over every seed of the chunk on the host threads, 9 ms
+ * of a call on the 4 cores a rank has on an 8-GPU box): per chain the contig it lies in (bns_pos2rid on the midpoint of
+ * the first and last seed, src/BWT.cpp:653-660), the head / tail guards (:1825, :2163), the number of round-1 tasks,
+ * whether a task's lengths qualify for a clip / split trigger, and the validation of the chain (seeds inside the read and
+ * the reference, in order, without overlap: Chain.cpp:258-266 guarantees it).  One warp per chain.
+ * guards[c]: bit 0 head aligned, bit 1 tail aligned, bit 2 trigger candidate. */
+__global__ void __launch_bounds__(128) k_chain_plan(const lf_chain *__restrict__ chains, const lf_seed *__restrict__ seeds, const uint64_t *__restrict__ read_off,
+                                                    uint32_t n_reads, const int64_t *__restrict__ coff, const int32_t *__restrict__ clen, int nctg, int64_t l_pac,
+                                                    uint32_t n_chains, uint8_t *guards, uint32_t *ntask, uint32_t *bad)
+{
+    const uint32_t c = blockIdx.x * 4u + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (c >= n_chains) return;
+    const lf_chain ch = chains[c];
+    const uint32_t n = ch.n_seeds;
+    if (n < 2u || ch.read_id >= n_reads) { if (lane == 0) { atomicOr(bad, 1u); guards[c] = 0; ntask[c] = 0; } return; }
+    const lf_seed *s = seeds + ch.seed_off;
+    const uint32_t readLen = (uint32_t)(read_off[ch.read_id + 1] - read_off[ch.read_id]);
+    uint32_t cnt = 0;
+    bool cand = false, good = true;
+    for (uint32_t i = lane; i < n; i += 32u) {
+        const lf_seed a = s[i];
+        good = good && a.len >= 1u && (uint64_t)a.qPos + a.len <= readLen && (int64_t)a.tPos + a.len <= l_pac;
+        if (i + 1u < n) {
+            const lf_seed b = s[i + 1];
+            good = good && b.qPos >= a.qPos + a.len && b.tPos >= a.tPos + a.len;
+            const int32_t ql = (int32_t)(b.qPos - (a.qPos + a.len)), tl = (int32_t)(b.tPos - (a.tPos + a.len));
+            if (ql > 0 && tl > 0) { cnt++; cand = cand || ql - tl >= 80 || tl - ql >= 80; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(LF_FULL, cnt, o);
+    cand = __any_sync(LF_FULL, cand);
+    good = __all_sync(LF_FULL, good);
+    if (lane == 0) {
+        const lf_seed s0 = s[0], sl = s[n - 1];
+        const int64_t pos = ((int64_t)s0.tPos + (int64_t)sl.tPos) >> 1;
+        int left = 0, mid = 0, right = nctg;   /* bns_pos2rid, lib/bwa/bntseq.c:349-363 */
+        bool found = pos < l_pac;
+        while (found && left < right) {
+            mid = (left + right) >> 1;
+            if (pos >= coff[mid]) {
+                if (mid == nctg - 1) break;
+                if (pos < coff[mid + 1]) break;
+                left = mid + 1;
+            } else right = mid;
+        }
+        uint32_t g = 0;
+        if (found && good) {
+            const int64_t chrBeg = coff[mid], chrEnd = coff[mid] + clen[mid] - 1;
+            const int32_t a = (int32_t)s0.qPos;
+            const int32_t b = (int32_t)readLen - (int32_t)(sl.qPos + sl.len);
+            const bool hg = a > 0 && (int64_t)s0.tPos - (a + 20) >= (int64_t)(uint32_t)chrBeg;
+            const bool tg = b > 0 && sl.tPos + sl.len + (uint32_t)(b + 20) - 1u <= (uint32_t)chrEnd;
+            cand = cand || (hg && a > LF_CLIP_LEN) || (tg && b > LF_CLIP_LEN);
+            g = (hg ? 1u : 0u) | (tg ? 2u : 0u) | (cand ? 4u : 0u);
+            cnt += (hg ? 1u : 0u) + (tg ? 1u : 0u);
+        } else { atomicOr(bad, 1u); cnt = 0; }
+        guards[c] = (uint8_t)g;
+        ntask[c] = cnt;
+    }
+}
+
 __global__ void k_chain_triggers(const lf_align_task *tasks, const lf_align_result *res, uint32_t n, uint32_t *list, uint32_t *count, uint32_t cap)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -223,7 +223,7 @@ def test_gpu_chain_operator_two_contigs_edges():
     g.close()
 
 
-@pytest.mark.parametrize("env", ["LF_CHAIN_NO_SPEC", "LF_CHAIN_HOST_TASKS", "LF_EMIT_NO_ZEROCOPY"])
+@pytest.mark.parametrize("env", ["LF_CHAIN_NO_SPEC", "LF_CHAIN_HOST_TASKS", "LF_CHAIN_HOST_PLAN", "LF_EMIT_NO_ZEROCOPY"])
 def test_emu_chain_operator_fallback_paths(monkeypatch, env):
     """The non-default variants of the single-device path: round 2 as its own GPU round trip instead of the speculative
     extensions, round-1 tasks built on host threads instead of by k_chain_tasks, emit text through a staging copy."""
@@ -233,7 +233,7 @@ def test_emu_chain_operator_fallback_paths(monkeypatch, env):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", ["LF_CHAIN_NO_SPEC", "LF_CHAIN_HOST_TASKS", "LF_EMIT_NO_ZEROCOPY"])
+@pytest.mark.parametrize("env", ["LF_CHAIN_NO_SPEC", "LF_CHAIN_HOST_TASKS", "LF_CHAIN_HOST_PLAN", "LF_EMIT_NO_ZEROCOPY"])
 def test_gpu_chain_operator_fallback_paths(monkeypatch, env):
     monkeypatch.setenv(env, "1")
     _crafted(None)
@@ -258,7 +258,20 @@ def _edge_cases(lib_path):
     assert [{k: v for k, v in r.items() if k != "chain"} for r in got] == exp
     with pytest.raises(api.LfGpuError):
         g.align_chains(reads, off, [0], [len(ref)], seeds, np.array([(0, 2, 5, 0, 0)], dtype=api.CHAIN))
+    # chains the reference's chaining cannot produce are rejected, not aligned: overlapping seeds, seeds out of order, a seed past
+    # the end of the read, a seed past the end of the reference (k_chain_plan, or the host loop with LF_CHAIN_HOST_PLAN=1)
+    for bad in ([(1000, 0, 1000), (1900, 900, 1000)], [(2000, 1000, 500), (1000, 0, 500)], [(1000, 0, 1000), (2000, 1000, 1001)],
+                [(1000, 0, 1000), (len(ref) - 500, 1000, 1000)]):
+        with pytest.raises(api.LfGpuError):
+            g.align_chains(reads, off, [0], [len(ref)], np.array(bad, dtype=api.SEED), np.array([(0, 2, 0, 0, 0)], dtype=api.CHAIN))
+    recs, text, st = g.align_chains(reads, off, [0], [len(ref)], seeds, np.array([(0, 2, 0, 0, 0)], dtype=api.CHAIN))   # and the context is still usable
+    assert len(recs) == 1
     g.close()
+
+
+def test_emu_chain_operator_edge_cases_host_plan(monkeypatch):
+    monkeypatch.setenv("LF_CHAIN_HOST_PLAN", "1")
+    _edge_cases(build_emu())
 
 
 def test_emu_chain_operator_edge_cases():
