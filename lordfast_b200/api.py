@@ -131,8 +131,9 @@ class PinnedArray:
         self.buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
 
     def view(self, dtype, count=None):
-        a = np.frombuffer(self.buf, dtype=dtype)
-        return a if count is None else a[:count]
+        dt = np.dtype(dtype)
+        n = self.nbytes // dt.itemsize if count is None else int(count)
+        return np.frombuffer(self.buf, dtype=np.uint8, count=n * dt.itemsize).view(dt)
 
     def free(self):
         if self.ptr:

@@ -556,6 +556,18 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
     trace_mark(ctx, "reads packed", ctx->devs[0].stream);
     const double tt1 = now_ms();
+    /* single-device contexts: the task list is generated on the device (k_chain_tasks); the host only needs the few
+     * tasks a trigger fires for, and re-derives those from the chain (task_at below) */
+    const bool dev_tasks = gpu_emit && !getenv("LF_CHAIN_HOST_TASKS");
+    /* ... and so is pass A (k_chain_plan): boundaries, guards, task counts, trigger candidates, validation.  What comes back
+     * is 9 B per chain.  LF_CHAIN_HOST_PLAN=1: the host loop instead (also the path of the multi-device host emit).  The
+     * seeds, the plan kernel and its answer go through the extension stream (idle until round 1 is under way): on the
+     * main stream the host would wait for the 200 MB of reads queued before them. */
+    const bool dev_plan = dev_tasks && n_chains > 0 && !getenv("LF_CHAIN_HOST_PLAN");
+    lfb_stream ps = dev_plan ? ctx->devs[0].ext_stream : ctx->devs[0].stream;
+#ifndef LF_EMU
+    if (dev_plan) cudaStreamWaitEvent(ps, ctx->devs[0].off_ev, 0);
+#endif
     if (gpu_emit) {
         DevState &d = ctx->devs[0];
         size_t ns = 0;
@@ -574,7 +586,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
             memcpy(stage + cb, chains, n_chains * sizeof(lf_chain));
             src_seeds = stage; src_chains = stage + cb;
         }
-        if (h2d_k(d, S.d_seeds.p, src_seeds, sb, d.stream, true) || h2d_k(d, S.d_chains.p, src_chains, n_chains * sizeof(lf_chain), d.stream, true)) { delete R; return LF_ERR_CUDA; }
+        if (h2d_k(d, S.d_seeds.p, src_seeds, sb, ps, true) || h2d_k(d, S.d_chains.p, src_chains, n_chains * sizeof(lf_chain), ps, true)) { delete R; return LF_ERR_CUDA; }
     }
 
     /* ---------------- round 1: tasks known from the chains alone ---------------- */
@@ -592,12 +604,6 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     std::vector<uint64_t> nslot(n_chains, 0); /* op-slot words of the chain's round-1 tasks */
     std::atomic<bool> bad_rid(false);   /* a chain the reference's chaining could not have produced (or a contig lookup that failed) */
     const double tt2 = now_ms();
-    /* single-device contexts: the task list is generated on the device (k_chain_tasks); the host only needs the few
-     * tasks a trigger fires for, and re-derives those from the chain (task_at below) */
-    const bool dev_tasks = gpu_emit && !getenv("LF_CHAIN_HOST_TASKS");
-    /* ... and so is pass A (k_chain_plan): boundaries, guards, task counts, trigger candidates, validation.  What comes back
-     * is 9 B per chain.  LF_CHAIN_HOST_PLAN=1: the host loop below instead (also the path of the multi-device host emit). */
-    const bool dev_plan = dev_tasks && !getenv("LF_CHAIN_HOST_PLAN");
     if (dev_plan) {
         DevState &d = ctx->devs[0];
         const size_t nc = (size_t)contigs->n;
@@ -610,13 +616,17 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         if (!cs || !back) { delete R; return LF_ERR_NOMEM; }
         memcpy(cs, contigs->offset, nc * 8); memcpy(cs + co_b, contigs->len, nc * 4);
         uint32_t *d_bad = d.queue.as<uint32_t>();   /* the work-counter block is idle until run_align clears it */
-        if (d.queue.reserve(256) || h2d_k(d, S.d_contigs.p, cs, co_b + nc * 4, d.stream, true) || lfb_memset((d_bad = d.queue.as<uint32_t>()) + 60, 0, 4, d.stream)) { delete R; return LF_ERR_CUDA; }
-        LFB_LAUNCH(k_chain_plan, (unsigned)((n_chains + 3) / 4), 128, 0, d.stream, S.d_chains.as<lf_chain>(), S.d_seeds.as<lf_seed>(), d.read_off.as<uint64_t>(), reads->n_reads,
+        if (d.queue.reserve(256) || h2d_k(d, S.d_contigs.p, cs, co_b + nc * 4, ps, true) || lfb_memset((d_bad = d.queue.as<uint32_t>()) + 60, 0, 4, ps)) { delete R; return LF_ERR_CUDA; }
+        LFB_LAUNCH(k_chain_plan, (unsigned)((n_chains + 3) / 4), 128, 0, ps, S.d_chains.as<lf_chain>(), S.d_seeds.as<lf_seed>(), d.read_off.as<uint64_t>(), reads->n_reads,
                    (const int64_t *)S.d_contigs.p, (const int32_t *)((const char *)S.d_contigs.p + co_b), (int)nc, ctx->l_pac, (uint32_t)n_chains,
                    S.d_guards.as<uint8_t>(), S.d_ntask.as<uint32_t>(), d_bad + 60);
-        if (lfb_scan_excl_total(d.tmp, S.d_ntask.as<uint32_t>(), S.d_task_base.as<unsigned long long>(), n_chains, d.stream)
-            || lfb_d2h(back, S.d_task_base.p, (n_chains + 1) * 8, d.stream) || lfb_d2h(back + (n_chains + 1) * 8, S.d_guards.p, n_chains, d.stream)
-            || lfb_d2h(back + (n_chains + 1) * 8 + n_chains + (8 - n_chains % 8) % 8, d_bad + 60, 4, d.stream) || lfb_sync(d.stream)) { delete R; return LF_ERR_CUDA; }
+        if (lfb_scan_excl_total(d.tmp, S.d_ntask.as<uint32_t>(), S.d_task_base.as<unsigned long long>(), n_chains, ps)
+            || lfb_d2h(back, S.d_task_base.p, (n_chains + 1) * 8, ps) || lfb_d2h(back + (n_chains + 1) * 8, S.d_guards.p, n_chains, ps)
+            || lfb_d2h(back + (n_chains + 1) * 8 + n_chains + (8 - n_chains % 8) % 8, d_bad + 60, 4, ps) || lfb_sync(ps)) { delete R; return LF_ERR_CUDA; }
+#ifndef LF_EMU
+        cudaEventRecord(d.ext_ev, ps);               /* what the main stream launches next reads the seeds and the plan */
+        cudaStreamWaitEvent(d.stream, d.ext_ev, 0);
+#endif
         uint32_t badflag; memcpy(&badflag, back + (n_chains + 1) * 8 + n_chains + (8 - n_chains % 8) % 8, 4);
         if (badflag) bad_rid = true;
         memcpy(task_base.data(), back, (n_chains + 1) * 8);

@@ -54,6 +54,7 @@ struct DevState {
     size_t stage_chunk = 0, stage_used = 0;
     bool pac_borrowed = false;      /* a lane of lf_gpu_align_chains: the reference belongs to the parent context's DevState */
     lfb_event up_ev = 0;            /* lane: its reads have arrived (recorded on the parent's upload stream) */
+    lfb_event off_ev = 0;           /* the read offsets of the batch are on the device (the bases may still be in flight) */
     bool reads_preloaded = false;   /* lane: the parent has enqueued the H2D copy of the reads; upload_reads only waits and packs */
 };
 
@@ -532,6 +533,7 @@ static int init_dev_streams(DevState &d)
     }
     cudaEventCreateWithFlags(&d.ext_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d.up_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&d.off_ev, cudaEventDisableTiming);
     for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking) != cudaSuccess) return -1; cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
     for (int c = 0; c < LF_NCLS; c++) { cudaEventCreate(&d.cls_ev[c][0]); cudaEventCreate(&d.cls_ev[c][1]); }
 #else
@@ -602,6 +604,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
         for (int k = 0; k < LF_NSUB; k++) { if (d.sub_ev[k]) cudaEventDestroy(d.sub_ev[k]); if (d.sub[k]) cudaStreamDestroy(d.sub[k]); }
         if (d.ext_ev) cudaEventDestroy(d.ext_ev);
         if (d.up_ev) cudaEventDestroy(d.up_ev);
+        if (d.off_ev) cudaEventDestroy(d.off_ev);
         if (d.ext_stream) cudaStreamDestroy(d.ext_stream);
         for (int c = 0; c < LF_NCLS; c++) { if (d.cls_ev[c][0]) cudaEventDestroy(d.cls_ev[c][0]); if (d.cls_ev[c][1]) cudaEventDestroy(d.cls_ev[c][1]); }
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -653,6 +656,7 @@ int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads)
         if (d.reads_preloaded) {   /* lf_chain.inl lanes: the parent enqueued the copies in lane order on its upload stream */
 #ifndef LF_EMU
             cudaStreamWaitEvent(d.stream, d.up_ev, 0);
+            cudaEventRecord(d.off_ev, d.stream);
 #endif
             d.reads_preloaded = false;
         } else {
@@ -662,6 +666,9 @@ int lf_gpu_upload_reads(lf_gpu_ctx *ctx, const lf_reads *reads)
              * (and, it turned out, other threads' CUDA calls) until everything queued on the stream before it -- 200 MB of
              * bases -- has gone through */
             LF_TRY(h2d_k(d, d.read_off.p, reads->offsets, ((size_t)nr + 1) * 8, d.stream, false));
+#ifndef LF_EMU
+            cudaEventRecord(d.off_ev, d.stream);
+#endif
             LF_TRY(lfb_h2d(d.bases.p, reads->bases, total, d.stream));
         }
         LF_TRY(lfb_memset(d.plo.p, 0, pwords * 4, d.stream)); LF_TRY(lfb_memset(d.phi.p, 0, pwords * 4, d.stream));
