@@ -437,6 +437,46 @@ __global__ void __launch_bounds__(256) k_align_prep(LfDev d, uint32_t *keys, uin
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* op stream of the thread-per-task kernels                                                    */
+/* ------------------------------------------------------------------------------------------ */
+/* 2-bit ops, 16 per word, written from the end of the task's slot towards its start (the walk finds the last op of the
+ * alignment first).  The accumulator takes each op at its low end (one LEA); every 16th op the word is complete with the
+ * first of them on top.  Word indices are 32-bit: the host refuses batches of 2^32 op words. */
+struct LfOpSink {
+    uint32_t acc, nops, widx;
+    __device__ __forceinline__ void init(uint64_t slot_hi) { acc = 0; nops = 0; widx = (uint32_t)(slot_hi >> 4); }
+    __device__ __forceinline__ void emit(uint32_t *__restrict__ ops, uint32_t op)
+    {
+        acc = (acc << 2) | op;
+        if ((++nops & 15u) == 0u) ops[--widx] = acc;
+    }
+    __device__ __forceinline__ void finish(uint32_t *__restrict__ ops) { if (nops & 15u) ops[widx - 1] = acc << (32u - 2u * (nops & 15u)); }
+};
+
+/* Walk inside one word-row of a block's window in shared memory (planes [column][window word][2][STRIDE threads], CS words
+ * per column): one op per iteration, Up > Left > Diagonal, until the walk leaves the word-row or the block.  cell0 is the
+ * index of column c0's plane word for this thread and word-row; the column is carried by the cell index alone.
+ * (Counting the matches of the next three diagonal cells first and emitting them together -- 3.2 ops per iteration for 80
+ * instructions -- was 3.5 % slower on the config-2 step: lanes leave the loop after different numbers of iterations.) */
+template <int STRIDE, int CS>
+__device__ __forceinline__ void lf_walk_row(const uint32_t *smem, int cell0, int wrow, int c0, int &i, int &j, LfOpSink &sink, uint32_t *__restrict__ ops)
+{
+    int cell = cell0 + (j - 1 - c0) * CS;
+    int b = (i - 1) & 31;
+    do {
+        const uint32_t x0 = smem[cell] >> b, x1 = smem[cell + STRIDE] >> b;
+        const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
+        const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
+        const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
+        sink.emit(ops, op);
+        b = b + stay_row - 1;
+        cell = cell + stay_col * CS - CS;
+    } while (b >= 0 && cell >= cell0);
+    j = c0 + (cell - cell0 + CS) / CS;   /* cell0 - CS (one column left of the block) gives c0 */
+    i = wrow * 32 + b + 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* k_myers_small: thread-per-task, NW words of 32 rows in registers                            */
 /* ------------------------------------------------------------------------------------------ */
 template <int NW>
@@ -737,10 +777,8 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
 
     /* ---- traceback: recompute 16-column blocks from their checkpoint, keep a WIN-word window of
      *      the op planes in shared memory, walk Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
-    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1; /* word the next (right-most free) op goes to */
-    uint32_t cur = 0, nops = 0;
-    int sh = 30;
-#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
+    LfOpSink sink;
+    sink.init(slot_hi);
     int i = q, j = end + 1;
     uint32_t *smt = smem + tid;
     constexpr int CS = WIN * 2 * LF_K1_BLOCK; /* shared-memory words per column */
@@ -774,25 +812,13 @@ __global__ void __launch_bounds__(LF_K1_BLOCK) k_myers_small(LfDev d, const uint
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
             const int wrow = (i - 1) >> 5;
-            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * LF_K1_BLOCK;
-            int b = (i - 1) & 31;
-            do {
-                const uint32_t x0 = cell[0] >> b, x1 = cell[LF_K1_BLOCK] >> b;
-                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
-                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
-                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
-                LF_EMIT(op);
-                b -= 1 - stay_row;
-                j -= 1 - stay_col;
-                cell -= (1 - stay_col) * CS;
-            } while (b >= 0 && j > c0);
-            i = wrow * 32 + b + 1;
+            lf_walk_row<LF_K1_BLOCK, CS>(smem, (int)tid + (wrow - wtop) * 2 * LF_K1_BLOCK, wrow, c0, i, j, sink, d.ops);
         }
     }
-    while (i > 0) { LF_EMIT(1u); i--; } /* left column: the rest of the query is inserted   */
-    while (j > 0) { LF_EMIT(2u); j--; } /* top row: the rest of the target is deleted        */
-    if (sh != 30) *wptr = cur;
-#undef LF_EMIT
+    while (i > 0) { sink.emit(d.ops, 1u); i--; } /* left column: the rest of the query is inserted   */
+    while (j > 0) { sink.emit(d.ops, 2u); j--; } /* top row: the rest of the target is deleted        */
+    sink.finish(d.ops);
+    const uint32_t nops = sink.nops;
     const uint64_t p = slot_hi - nops;
     r.ops_off = p; r.ops_len = (uint32_t)(slot_hi - p);
     d.res[ti] = r;
@@ -2626,10 +2652,8 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
     if (task.flags & LF_F_NO_PATH) { d.res[ti] = r; return; }
 
     /* ---- traceback over the stored planes: Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
-    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1;
-    uint32_t cur = 0, nops = 0;
-    int sh = 30;
-#define LF_EMIT(op) do { cur |= (uint32_t)(op) << sh; nops++; if (sh == 0) { *wptr-- = cur; cur = 0; sh = 30; } else sh -= 2; } while (0)
+    LfOpSink sink;
+    sink.init(slot_hi);
     int i = q, j = end + 1;
     uint32_t *smt = smem + tid;
     constexpr int CS = WIN * 2 * 128;
@@ -2680,27 +2704,15 @@ __global__ void __launch_bounds__(128) k_myers_band(LfDev d, const uint32_t *__r
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
             const int wrow = (i - 1) >> 5;
-            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * 128;
-            int b = (i - 1) & 31;
-            do {
-                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
-                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
-                const int stay_col = (int)(x0 & ~x1 & 1u);
-                const int stay_row = (int)(x1 & ~x0 & 1u);
-                LF_EMIT(op);
-                b -= 1 - stay_row;
-                j -= 1 - stay_col;
-                cell -= (1 - stay_col) * CS;
-            } while (b >= 0 && j > c0);
-            i = wrow * 32 + b + 1;
+            lf_walk_row<128, CS>(smem, (int)tid + (wrow - wtop) * 2 * 128, wrow, c0, i, j, sink, d.ops);
         }
-        if (nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
+        if (sink.nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
     }
-    while (i > 0 && !lost) { LF_EMIT(1u); i--; }
-    while (j > 0 && !lost) { LF_EMIT(2u); j--; }
-    if (sh != 30) *wptr = cur;
-#undef LF_EMIT
+    while (i > 0 && !lost) { sink.emit(d.ops, 1u); i--; }
+    while (j > 0 && !lost) { sink.emit(d.ops, 2u); j--; }
+    sink.finish(d.ops);
     if (lost) { retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
+    const uint32_t nops = sink.nops;
     r.ops_off = slot_hi - nops; r.ops_len = nops;
     d.res[ti] = r;
 }
@@ -2890,15 +2902,8 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
     if (task.flags & LF_F_NO_PATH) { r.ops_off = slot_hi; r.ops_len = 0; d.res[ti] = r; return; }
 
     /* ---- traceback: Up > Left > Diagonal (edlib.cpp:950, :984, :1015) ---- */
-    /* Ops are packed 16 per word, last op first, into the top word of a 64-bit accumulator at bit `sh`; a word that is
-     * complete is stored and the accumulator moves up.  LF_EMITK appends nz matches (op 0) and then, if `has`, one op. */
-    uint32_t *wptr = d.ops + (slot_hi >> 4) - 1;
-    unsigned long long acc = 0;
-    uint32_t nops = 0;
-    int sh = 30;
-#define LF_EMITK(nz, op, has) do { int p_ = sh - 2 * (int)(nz); if (has) { acc |= (unsigned long long)(op) << (32 + p_); p_ -= 2; } nops += (uint32_t)(nz) + ((has) ? 1u : 0u); \
-        if (p_ < 0) { *wptr-- = (uint32_t)(acc >> 32); acc <<= 32; p_ += 32; } sh = p_; } while (0)
-#define LF_EMIT(op) LF_EMITK(0, op, true)
+    LfOpSink sink;
+    sink.init(slot_hi);
     int i = q, j = t;
     const int q8 = (int)((8u * (uint32_t)q) / (uint32_t)t), r8 = (int)((8u * (uint32_t)q) % (uint32_t)t);
     int bc0 = ((t - 1) / C) * C;                 /* block the band bookkeeping below refers to */
@@ -2945,63 +2950,19 @@ __global__ void __launch_bounds__(128) k_myers_bandreg(LfDev d, const uint32_t *
         else if (N2 < N1 && ns <= N2) lf_bandreg_block<NB, N2, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else if (N1 < NB && ns <= N1) lf_bandreg_block<NB, N1, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
         else lf_bandreg_block<NB, NB, false, true, true, SLIDE>(Pv, Mv, qlo, qhi, qnn, tb, c0, C, k, cslide, top, q, t, kmax, d, qv, smt, wtop);
-        /* Walk inside the window, one word-row at a time, one op per iteration (28 SASS instructions).
-         * LF_WALK_LOOKAHEAD (measured, not the default): an iteration first counts how many of the next three diagonal cells
-         * (inside this word-row and block) are matches, emits them together, and then takes one general step -- branch-free,
-         * 3.2 ops per iteration at 15 % divergence for 80 instructions, i.e. 25 per op.  On the config-2 step it was 3.5 %
-         * SLOWER (1.879 vs 1.813 ms): the lanes of a warp then leave the inner loop after different numbers of iterations more
-         * often, and the eight shared-memory loads per iteration queue behind each other. */
+        /* walk inside the window, one word-row at a time */
         const int rowmin = wtop * 32;
         while (i > 0 && j > c0 && (i - 1) >= rowmin) {
             const int wrow = (i - 1) >> 5;
-            const uint32_t *cell = smt + (size_t)((j - 1 - c0) * WIN + (wrow - wtop)) * 2 * 128;
-            int b = (i - 1) & 31;
-#ifndef LF_WALK_LOOKAHEAD
-            do {
-                const uint32_t x0 = cell[0] >> b, x1 = cell[128] >> b;
-                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
-                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
-                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
-                LF_EMIT(op);
-                b -= 1 - stay_row;
-                j -= 1 - stay_col;
-                cell -= (1 - stay_col) * CS;
-#else
-            do {
-                const int jj = j - 1 - c0;                                   /* columns of the block to the left of this cell */
-                const uint32_t *c1p = cell - (jj >= 1 ? CS : 0), *c2p = cell - (jj >= 2 ? 2 * CS : 0);
-                /* bit b of m_k: cell k of the diagonal is not a match (or lies above row 0 of this word-row) */
-                const uint32_t m0 = cell[0] | cell[128];
-                const uint32_t m1 = ((c1p[0] | c1p[128]) << 1) | 1u;
-                const uint32_t m2 = ((c2p[0] | c2p[128]) << 2) | 3u;
-                uint32_t nm = ((m0 >> b) & 1u) | (((m1 >> b) & 1u) << 1) | (((m2 >> b) & 1u) << 2) | 8u;
-                nm |= jj < 2 ? (jj < 1 ? 2u : 4u) : 0u;                      /* ... or left of the block */
-                const int nz = __ffs((int)nm) - 1;                           /* 0 .. 3 matches */
-                b -= nz; j -= nz; cell -= nz * CS;
-                const bool has = b >= 0 && j > c0;
-                const uint32_t *cg = has ? cell : smt;
-                const uint32_t x0 = cg[0] >> (b & 31), x1 = cg[128] >> (b & 31);
-                const uint32_t op = (x0 & 1u) | ((x1 & 1u) << 1);
-                const int stay_col = (int)(x0 & ~x1 & 1u);  /* op 1: up    */
-                const int stay_row = (int)(x1 & ~x0 & 1u);  /* op 2: left  */
-                LF_EMITK(nz, op, has);
-                if (has) {
-                    b -= 1 - stay_row;
-                    j -= 1 - stay_col;
-                    cell -= (1 - stay_col) * CS;
-                }
-#endif
-            } while (b >= 0 && j > c0);
-            i = wrow * 32 + b + 1;
+            lf_walk_row<128, CS>(smem, (int)tid + (wrow - wtop) * 2 * 128, wrow, c0, i, j, sink, d.ops);
         }
-        if (nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
+        if (sink.nops > (uint32_t)(q + t)) { lost = true; break; } /* cannot happen on a certified band */
     }
-    while (i > 0 && !lost) { LF_EMIT(1u); i--; }
-    while (j > 0 && !lost) { LF_EMIT(2u); j--; }
-    if (sh != 30) *wptr = (uint32_t)(acc >> 32);
-#undef LF_EMIT
-#undef LF_EMITK
+    while (i > 0 && !lost) { sink.emit(d.ops, 1u); i--; }
+    while (j > 0 && !lost) { sink.emit(d.ops, 2u); j--; }
+    sink.finish(d.ops);
     if (lost) { retry_list[first + atomicAdd(retry_count, 1u)] = ti; return; }
+    const uint32_t nops = sink.nops;
     r.ops_off = slot_hi - nops; r.ops_len = nops;
     d.res[ti] = r;
 }

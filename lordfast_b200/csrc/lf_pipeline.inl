@@ -361,6 +361,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     LF_TRY(lfb_d2h(&ht->slot_total, d.slot_end.as<unsigned long long>() + (n - 1), 8, s));
     LF_TRY(lfb_d2h(&ht->scr_total, d.scr_off.as<unsigned long long>() + n, 8, s));
     LF_TRY(lfb_sync(s)); /* the one host round trip of a batch: class sizes decide the launches */
+    if (ht->slot_total >> 32) return fail(ctx, LF_ERR_BAD_ARG, "batch needs 2^32 or more op words: split it");   /* the kernels index op words with 32 bits */
     d.ops_words = ht->slot_total;
     LF_TRY(d.ops.reserve((size_t)ht->slot_total * 4 + 64));
     LF_TRY(d.scratch.reserve((size_t)ht->scr_total + 64));
