@@ -190,6 +190,43 @@ const char *lf_chain_results_text(const lf_chain_results *r, size_t *bytes);
 int  lf_chain_results_stats(const lf_chain_results *r, lf_chain_stats *out);
 void lf_chain_results_free(lf_chain_results *r);
 
+/* ---- FM-index seeding ---------------------------------------------- */
+/* getLocs_extend_whole_step (src/BWT.cpp:312-394), the seeding step mapSeq runs per read (src/LordFAST.cpp:507), for a
+ * batch of reads: SAMPLING_COUNT sample positions per read, at each the longest exact match of at least MIN_ANCHOR_LEN
+ * bases against bwa's FM index of reference + reverse complement (bwt_count_exact_cached, src/BWT.cpp:265-298, on
+ * lib/bwa/bwt.c:86-143), kept if it has fewer than MAX_REF_HITS occurrences and is not contained in the previous kept
+ * match, every occurrence located through the sampled suffix array (bwt_sa, lib/bwa/bwt.c:86-98) and appended to the
+ * forward or to the reverse seed list of the read, in the reference's order. */
+typedef struct { uint64_t beg, end; } lf_fm_cache_entry;     /* bwtCache_t, src/BWT.h:41-46 */
+typedef struct {                /* the members of bwa's bwt_t (lib/bwa/bwt.h:44-57) that seeding reads, and bns->l_pac */
+    const uint32_t *bwt;        /* bwt_t::bwt: per 128 bases four 64-bit occurrence counts, then eight words of 16 bases */
+    uint64_t bwt_size;          /* 32-bit words in bwt */
+    uint64_t primary, L2[5], seq_len;
+    const uint64_t *sa;         /* bwt_t::sa, n_sa entries, sa[0] = (uint64_t)-1 */
+    uint64_t n_sa;
+    int32_t  sa_intv;           /* power of two */
+    int32_t  k_cache;           /* kCache (src/BWT.cpp:34): 12 in the reference; <= min_anchor_len */
+    const lf_fm_cache_entry *cache; /* _fmd_cacheTable, 4^k_cache entries; NULL: derived from bwt on the device (the
+                                       table bwt_cache_gen would write, src/BWT.cpp:60-138) */
+    int64_t  l_pac;             /* bns->l_pac: suffix positions >= l_pac are on the reverse strand */
+} lf_fm_index;
+typedef struct { int32_t min_anchor_len, sampling_count, max_ref_hits; } lf_seed_params; /* MIN_ANCHOR_LEN, SAMPLING_COUNT, MAX_REF_HITS */
+typedef struct lf_seed_results lf_seed_results;   /* library-owned; valid until the next lf_gpu_seed_batch on the context or lf_seed_results_free */
+
+/* Copies the index to device 0 of the context (and builds the k-mer table there if fm->cache is NULL). */
+int lf_gpu_seed_init(lf_gpu_ctx *ctx, const lf_fm_index *fm);
+/* reads == NULL: the reads of the last lf_gpu_upload_reads / lf_gpu_seed_batch are still resident and are used again.
+ * Bases other than ACGTacgt end a match, as does the end of the read (the reference reads the NUL there). */
+int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_params *params, lf_seed_results **out);
+/* reverse = 0: seedForward lists, 1: seedReverse lists.  offsets: n_reads + 1 entries into the returned array.
+ * qPos and len carry Seed_t's bit-field widths (20 and 12 bits, src/LordFAST.h:30-35). */
+const lf_seed *lf_seed_results_list(const lf_seed_results *r, int reverse, const uint64_t **offsets, size_t *n);
+void lf_seed_results_free(lf_seed_results *r);
+/* The k-mer table in use on the device (4^k_cache entries), for checks against _fmd_cacheTable. */
+int lf_gpu_seed_cache_download(lf_gpu_ctx *ctx, lf_fm_cache_entry *out, size_t n);
+/* CUDA-event time of the kernels of the last lf_gpu_seed_batch (search / filter / locate + scatter), ms. */
+int lf_gpu_seed_timing(lf_gpu_ctx *ctx, float *search_ms, float *locate_ms, uint64_t *positions, uint64_t *hits);
+
 /* ---- measurement hooks -------------------------------------------------------------------- */
 
 typedef struct {

@@ -54,6 +54,15 @@ class ChainStats(C.Structure):
                 ("ms_tasks", C.c_float), ("ms_round1", C.c_float), ("ms_rounds23", C.c_float), ("ms_emit", C.c_float), ("ms_merge", C.c_float), ("reserved", C.c_float)]
 
 
+class FmIndexC(C.Structure):   # lf_fm_index
+    _fields_ = [("bwt", C.c_void_p), ("bwt_size", C.c_uint64), ("primary", C.c_uint64), ("L2", C.c_uint64 * 5), ("seq_len", C.c_uint64),
+                ("sa", C.c_void_p), ("n_sa", C.c_uint64), ("sa_intv", C.c_int32), ("k_cache", C.c_int32), ("cache", C.c_void_p), ("l_pac", C.c_int64)]
+
+
+class SeedParams(C.Structure):   # lf_seed_params: MIN_ANCHOR_LEN, SAMPLING_COUNT, MAX_REF_HITS (src/CommandLineParser.cpp:51-55)
+    _fields_ = [("min_anchor_len", C.c_int32), ("sampling_count", C.c_int32), ("max_ref_hits", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("align_tasks", C.c_uint64), ("extend_tasks", C.c_uint64),
                 ("cells", C.c_uint64), ("word_columns", C.c_uint64), ("last_run_ms", C.c_float),
@@ -65,7 +74,8 @@ EXPORTS = ["lf_gpu_init", "lf_gpu_prewarm", "lf_gpu_destroy", "lf_gpu_last_error
            "lf_gpu_upload_align_tasks", "lf_gpu_run_align", "lf_gpu_sync", "lf_gpu_download_align",
            "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",
            "lf_gpu_int32_peak", "lf_gpu_class_timeline", "lf_gpu_class_counts", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
-           "lf_chain_results_stats", "lf_chain_results_free"]
+           "lf_chain_results_stats", "lf_chain_results_free",
+           "lf_gpu_seed_init", "lf_gpu_seed_batch", "lf_seed_results_list", "lf_seed_results_free", "lf_gpu_seed_cache_download", "lf_gpu_seed_timing"]
 
 
 class LfGpuError(RuntimeError):
@@ -113,6 +123,14 @@ def load(lib_path: str | None = None) -> C.CDLL:
     lib.lf_chain_results_stats.argtypes = [vp, C.POINTER(ChainStats)]
     lib.lf_chain_results_free.argtypes = [vp]
     lib.lf_chain_results_free.restype = None
+    lib.lf_gpu_seed_init.argtypes = [vp, C.POINTER(FmIndexC)]
+    lib.lf_gpu_seed_batch.argtypes = [vp, C.POINTER(Reads), C.POINTER(SeedParams), C.POINTER(vp)]
+    lib.lf_seed_results_list.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    lib.lf_seed_results_list.restype = vp
+    lib.lf_seed_results_free.argtypes = [vp]
+    lib.lf_seed_results_free.restype = None
+    lib.lf_gpu_seed_cache_download.argtypes = [vp, vp, sz]
+    lib.lf_gpu_seed_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -227,6 +245,52 @@ class LfGpu:
         self.lib.lf_chain_results_stats(out, C.byref(st))
         self.lib.lf_chain_results_free(out)
         return recs, text, st
+
+    # ---- FM-index seeding (getLocs_extend_whole_step for a batch of reads) ----
+    def seed_init(self, fm):
+        """fm: lordfast_b200.fmindex.FmIndex (or anything with its fields) holding bwa's arrays."""
+        bwt = np.ascontiguousarray(fm.bwt, dtype=np.uint32)
+        sa = np.ascontiguousarray(fm.sa, dtype=np.uint64)
+        cache = None if fm.cache is None else np.ascontiguousarray(fm.cache, dtype=np.uint64)
+        c = FmIndexC(_ptr(bwt), len(bwt), int(fm.primary), (C.c_uint64 * 5)(*[int(x) for x in fm.L2]), int(fm.seq_len), _ptr(sa), len(sa),
+                     int(fm.sa_intv), int(fm.k_cache), None if cache is None else _ptr(cache), int(fm.l_pac))
+        self._check(self.lib.lf_gpu_seed_init(self.ctx, C.byref(c)), "lf_gpu_seed_init")
+        self._k_cache = int(fm.k_cache)
+
+    def seed_batch(self, bases, offsets, min_anchor_len=14, sampling_count=1000, max_ref_hits=1000, copy=True):
+        """Returns (fwd seeds, fwd offsets, rev seeds, rev offsets); offsets have n_reads + 1 entries.  bases = None: the resident reads."""
+        prm = SeedParams(min_anchor_len, sampling_count, max_ref_hits)
+        out = C.c_void_p()
+        if bases is None:
+            rc = self.lib.lf_gpu_seed_batch(self.ctx, None, C.byref(prm), C.byref(out))
+        else:
+            r = self._reads(bases, offsets)
+            rc = self.lib.lf_gpu_seed_batch(self.ctx, C.byref(r), C.byref(prm), C.byref(out))
+        self._check(rc, "lf_gpu_seed_batch")
+        res = []
+        nr = None
+        for rev in (0, 1):
+            op, n = C.c_void_p(), C.c_size_t()
+            lp = self.lib.lf_seed_results_list(out, rev, C.byref(op), C.byref(n))
+            if nr is None:
+                nr = len(offsets) - 1 if offsets is not None else self._last_n_reads
+            off = np.frombuffer((C.c_uint8 * ((nr + 1) * 8)).from_address(op.value), dtype=np.uint64)
+            lst = np.frombuffer((C.c_uint8 * (n.value * SEED.itemsize)).from_address(lp), dtype=SEED) if n.value else np.zeros(0, dtype=SEED)
+            res += [lst.copy() if copy else lst, off.copy() if copy else off]
+        self._last_n_reads = nr
+        self.lib.lf_seed_results_free(out)
+        return tuple(res)
+
+    def seed_cache(self) -> np.ndarray:
+        n = 4 ** self._k_cache
+        out = np.zeros((n, 2), dtype=np.uint64)
+        self._check(self.lib.lf_gpu_seed_cache_download(self.ctx, _ptr(out), n), "lf_gpu_seed_cache_download")
+        return out
+
+    def seed_timing(self):
+        a, b, p, h = C.c_float(), C.c_float(), C.c_uint64(), C.c_uint64()
+        self.lib.lf_gpu_seed_timing(self.ctx, C.byref(a), C.byref(b), C.byref(p), C.byref(h))
+        return {"search_ms": a.value, "locate_ms": b.value, "positions": p.value, "hits": h.value}
 
     # ---- phased forms (keep a batch resident in HBM) ----
     def upload_reads(self, bases, offsets):

@@ -63,6 +63,8 @@ struct lf_gpu_ctx {
     std::vector<lf_gpu_ctx *> lanes;   /* lf_chain.inl: single-device child contexts that pipeline the sub-batches of one call */
     void *chain_scratch = nullptr; /* lf_chain.inl: pinned staging kept between calls */
     void (*chain_scratch_free)(void *) = nullptr;
+    void *seed_state = nullptr;    /* lf_seed.inl: the FM index on device 0 and the buffers of lf_gpu_seed_batch */
+    void (*seed_state_free)(void *) = nullptr;
     int64_t l_pac = 0;
     std::string err;
     lf_gpu_stats stats = {};
@@ -589,6 +591,7 @@ void lf_gpu_destroy(lf_gpu_ctx *ctx)
     for (lf_gpu_ctx *l : ctx->lanes) lf_gpu_destroy(l);
     ctx->lanes.clear();
     if (ctx->chain_scratch && ctx->chain_scratch_free) ctx->chain_scratch_free(ctx->chain_scratch);
+    if (ctx->seed_state && ctx->seed_state_free) { if (!ctx->devs.empty()) set_dev(ctx->devs[0]); ctx->seed_state_free(ctx->seed_state); }
     for (DevState &d : ctx->devs) {
         set_dev(d);
         if (d.pac_borrowed) { d.pac.p = nullptr; d.pac.cap = 0; }
@@ -962,3 +965,4 @@ int lf_gpu_int32_peak(lf_gpu_ctx *ctx, int which, double *tops)
 } /* extern "C" */
 
 #include "lf_chain.inl"
+#include "lf_seed.inl"

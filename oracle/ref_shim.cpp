@@ -99,6 +99,79 @@ void ref_set_index(const uint8_t *pac, int64_t l_pac, int n_contigs, const int64
     init_tables();
 }
 
+/* ---- FM-index seeding: the reference's own index build / load and getLocs_extend_whole_step ---- */
+extern bwtCache_t *_fmd_cacheTable;                              /* src/BWT.cpp:33 */
+extern int32_t kCache;                                           /* src/BWT.cpp:34 */
+static bwaidx_t *g_fm = NULL;
+
+/* fasta: a FASTA file in a scratch directory; k_cache: the k of the k-mer table the index is built with (12 in the program) */
+int ref_fm_load(const char *fasta, int k_cache)
+{
+    kCache = k_cache;
+    if (bwt_load((char *)fasta)) return 1;   /* src/BWT.cpp:190: builds the index files next to the FASTA if they are missing */
+    g_fm = _fmd_index;
+    return 0;
+}
+int ref_fm_info(uint64_t *scalars /* primary, L2[5], seq_len, bwt_size, n_sa, sa_intv, l_pac, k_cache: 12 values */,
+                const uint32_t **bwt, const uint64_t **sa, const void **cache)
+{
+    if (!g_fm) return 1;
+    const bwt_t *b = g_fm->bwt;
+    scalars[0] = b->primary; for (int i = 0; i < 5; i++) scalars[1 + i] = b->L2[i];
+    scalars[6] = b->seq_len; scalars[7] = b->bwt_size; scalars[8] = b->n_sa; scalars[9] = (uint64_t)b->sa_intv;
+    scalars[10] = (uint64_t)g_fm->bns->l_pac; scalars[11] = (uint64_t)kCache;
+    *bwt = b->bwt; *sa = b->sa; *cache = _fmd_cacheTable;
+    return 0;
+}
+/* one read through getLocs_extend_whole_step (src/BWT.cpp:312-394); q is NUL-terminated as Reads.cpp leaves it */
+int ref_fm_seed(const char *q, uint32_t qlen, uint32_t hash_count, int min_anchor_len, int max_ref_hits,
+                lfo_seed *fwd, int *n_fwd, lfo_seed *rev, int *n_rev)
+{
+    if (!g_fm) return 1;
+    _fmd_index = g_fm;
+    MIN_ANCHOR_LEN = min_anchor_len; MAX_REF_HITS = max_ref_hits;
+    SeedList f, r;
+    std::vector<Seed_t> fl((size_t)hash_count * max_ref_hits + 1), rl((size_t)hash_count * max_ref_hits + 1);   /* src/LordFAST.cpp:136-137 */
+    f.list = fl.data(); r.list = rl.data(); f.num = r.num = 0;
+    getLocs_extend_whole_step((char *)q, qlen, hash_count, &f, &r);
+    for (uint32_t i = 0; i < f.num; i++) { fwd[i].tPos = fl[i].tPos; fwd[i].qPos = fl[i].qPos; fwd[i].len = fl[i].len; }
+    for (uint32_t i = 0; i < r.num; i++) { rev[i].tPos = rl[i].tPos; rev[i].qPos = rl[i].qPos; rev[i].len = rl[i].len; }
+    *n_fwd = (int)f.num; *n_rev = (int)r.num;
+    return 0;
+}
+/* a batch on `threads` host threads (the program's own parallelism is one read per thread, src/LordFAST.cpp:295-316);
+ * returns seconds; counts only (the lists are dropped) */
+struct FmBatchArg { const char *const *q; const uint32_t *qlen; int lo, hi; uint32_t hash_count, cap; uint64_t hits; };
+static void *fm_batch_worker(void *p)
+{
+    FmBatchArg *a = (FmBatchArg *)p;
+    SeedList f, r;
+    std::vector<Seed_t> fl(a->cap), rl(a->cap);
+    f.list = fl.data(); r.list = rl.data();
+    for (int i = a->lo; i < a->hi; i++) { getLocs_extend_whole_step((char *)a->q[i], a->qlen[i], a->hash_count, &f, &r); a->hits += f.num + r.num; }
+    return NULL;
+}
+double ref_fm_seed_batch(int n, const char *const *q, const uint32_t *qlen, uint32_t hash_count, int min_anchor_len, int max_ref_hits, int threads, uint64_t *hits)
+{
+    if (!g_fm) return -1;
+    _fmd_index = g_fm;
+    MIN_ANCHOR_LEN = min_anchor_len; MAX_REF_HITS = max_ref_hits;
+    std::vector<FmBatchArg> args((size_t)threads);
+    std::vector<pthread_t> th((size_t)threads);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        args[t].q = q; args[t].qlen = qlen; args[t].lo = (int)((long long)n * t / threads); args[t].hi = (int)((long long)n * (t + 1) / threads);
+        args[t].hash_count = hash_count; args[t].cap = hash_count * (uint32_t)max_ref_hits + 1; args[t].hits = 0;
+        pthread_create(&th[t], NULL, fm_batch_worker, &args[t]);
+    }
+    uint64_t tot = 0;
+    for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); tot += args[t].hits; }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (hits) *hits = tot;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 static void fill_chain(Chain_t &c, std::vector<Seed_t> &store, const lfo_seed *seeds, int n)
 {
     store.resize((size_t)n);

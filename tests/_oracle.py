@@ -75,6 +75,12 @@ def ref():
         lib.ref_set_index.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         lib.ref_align_chain.argtypes = [C.POINTER(Seed), C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(Sam), C.c_int, C.POINTER(C.c_int)]
         lib.ref_replay_chains.restype = C.c_double
+        if hasattr(lib, "ref_fm_load"):
+            lib.ref_fm_load.argtypes = [C.c_char_p, C.c_int]
+            lib.ref_fm_info.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+            lib.ref_fm_seed.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+            lib.ref_fm_seed_batch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+            lib.ref_fm_seed_batch.restype = C.c_double
         _ref = lib
     return _ref
 
@@ -187,3 +193,44 @@ def ref_align_chain(idx: RefIndex, seeds, query: bytes, is_rev: int):
         libc.free(sam[i].cigar)
         libc.free(sam[i].md)
     return out
+
+
+# ---- FM-index seeding through the reference's own code (oracle/_ref/libref_shim.so) ----
+import numpy as np  # noqa: E402
+
+SEED_DT = np.dtype([("tPos", "<u4"), ("qPos", "<u4"), ("len", "<u4")])
+
+
+def write_fasta(path: str, ref_ascii: np.ndarray, name: str = "chr1"):
+    with open(path, "wb") as f:
+        f.write(b">" + name.encode() + b"\n")
+        b = np.asarray(ref_ascii, dtype=np.uint8).tobytes()
+        for i in range(0, len(b), 80):
+            f.write(b[i:i + 80] + b"\n")
+
+
+def ref_fm_load(fasta_path: str, k_cache: int = 12):
+    """bwa index + lordFAST's k-mer table, built and loaded by the reference's own code.  Returns an FmIndex-like
+    namespace whose arrays are copies of the reference's in-memory arrays."""
+    import types
+    lib = ref()
+    if lib.ref_fm_load(fasta_path.encode(), k_cache):
+        raise RuntimeError("ref_fm_load failed")
+    sc = (C.c_uint64 * 12)()
+    bwt, sa, cache = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    lib.ref_fm_info(sc, C.byref(bwt), C.byref(sa), C.byref(cache))
+    primary, L2, seq_len, bwt_size, n_sa, sa_intv, l_pac, kc = sc[0], list(sc[1:6]), sc[6], sc[7], sc[8], sc[9], sc[10], sc[11]
+    grab = lambda p, n, dt: np.frombuffer((C.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(p.value), dtype=dt).copy()
+    return types.SimpleNamespace(bwt=grab(bwt, bwt_size, np.uint32), sa=grab(sa, n_sa, np.uint64), primary=int(primary),
+                                 L2=np.array(L2, dtype=np.uint64), seq_len=int(seq_len), sa_intv=int(sa_intv), l_pac=int(l_pac),
+                                 k_cache=int(kc), cache=grab(cache, 2 * 4 ** int(kc), np.uint64).reshape(-1, 2))
+
+
+def ref_fm_seed(read: bytes, sampling_count=1000, min_anchor_len=14, max_ref_hits=1000):
+    lib = ref()
+    cap = sampling_count * max_ref_hits + 1
+    f = np.zeros(cap, dtype=SEED_DT); r = np.zeros(cap, dtype=SEED_DT)
+    nf, nr = C.c_int(), C.c_int()
+    if lib.ref_fm_seed(read + b"\0", len(read), sampling_count, min_anchor_len, max_ref_hits, f.ctypes.data, C.byref(nf), r.ctypes.data, C.byref(nr)):
+        raise RuntimeError("ref_fm_seed: no index loaded")
+    return f[:nf.value].copy(), r[:nr.value].copy()
