@@ -224,8 +224,16 @@ const lf_seed *lf_seed_results_list(const lf_seed_results *r, int reverse, const
 void lf_seed_results_free(lf_seed_results *r);
 /* The k-mer table in use on the device (4^k_cache entries), for checks against _fmd_cacheTable. */
 int lf_gpu_seed_cache_download(lf_gpu_ctx *ctx, lf_fm_cache_entry *out, size_t n);
-/* CUDA-event time of the kernels of the last lf_gpu_seed_batch (search / filter / locate + scatter), ms. */
-int lf_gpu_seed_timing(lf_gpu_ctx *ctx, float *search_ms, float *locate_ms, uint64_t *positions, uint64_t *hits);
+/* Work and CUDA-event times of the last lf_gpu_seed_batch on the context. */
+typedef struct {
+    float    search_ms;      /* positions + longest-match search + containment filter + hit offsets */
+    float    locate_ms;      /* locate + strand split */
+    uint64_t positions;      /* n_reads * sampling_count */
+    uint64_t hits;           /* seeds written (both lists) */
+    uint64_t search_steps;   /* backward-search steps taken: two occurrence lookups (one or two 64-byte bwt blocks) each */
+    uint64_t locate_steps;   /* inverse-psi steps taken by bwt_sa: one bwt block each */
+} lf_seed_stats;
+int lf_gpu_seed_stats(lf_gpu_ctx *ctx, lf_seed_stats *out);
 
 /* ---- measurement hooks -------------------------------------------------------------------- */
 

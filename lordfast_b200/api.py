@@ -63,6 +63,11 @@ class SeedParams(C.Structure):   # lf_seed_params: MIN_ANCHOR_LEN, SAMPLING_COUN
     _fields_ = [("min_anchor_len", C.c_int32), ("sampling_count", C.c_int32), ("max_ref_hits", C.c_int32)]
 
 
+class SeedStats(C.Structure):   # lf_seed_stats
+    _fields_ = [("search_ms", C.c_float), ("locate_ms", C.c_float), ("positions", C.c_uint64), ("hits", C.c_uint64),
+                ("search_steps", C.c_uint64), ("locate_steps", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("align_tasks", C.c_uint64), ("extend_tasks", C.c_uint64),
                 ("cells", C.c_uint64), ("word_columns", C.c_uint64), ("last_run_ms", C.c_float),
@@ -75,7 +80,7 @@ EXPORTS = ["lf_gpu_init", "lf_gpu_prewarm", "lf_gpu_destroy", "lf_gpu_last_error
            "lf_gpu_upload_extend_tasks", "lf_gpu_run_extend", "lf_gpu_download_extend", "lf_gpu_get_stats",
            "lf_gpu_int32_peak", "lf_gpu_class_timeline", "lf_gpu_class_counts", "lf_gpu_align_chains", "lf_chain_results_records", "lf_chain_results_text",
            "lf_chain_results_stats", "lf_chain_results_free",
-           "lf_gpu_seed_init", "lf_gpu_seed_batch", "lf_seed_results_list", "lf_seed_results_free", "lf_gpu_seed_cache_download", "lf_gpu_seed_timing"]
+           "lf_gpu_seed_init", "lf_gpu_seed_batch", "lf_seed_results_list", "lf_seed_results_free", "lf_gpu_seed_cache_download", "lf_gpu_seed_stats"]
 
 
 class LfGpuError(RuntimeError):
@@ -130,7 +135,7 @@ def load(lib_path: str | None = None) -> C.CDLL:
     lib.lf_seed_results_free.argtypes = [vp]
     lib.lf_seed_results_free.restype = None
     lib.lf_gpu_seed_cache_download.argtypes = [vp, vp, sz]
-    lib.lf_gpu_seed_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.lf_gpu_seed_stats.argtypes = [vp, C.POINTER(SeedStats)]
     return lib
 
 
@@ -287,10 +292,10 @@ class LfGpu:
         self._check(self.lib.lf_gpu_seed_cache_download(self.ctx, _ptr(out), n), "lf_gpu_seed_cache_download")
         return out
 
-    def seed_timing(self):
-        a, b, p, h = C.c_float(), C.c_float(), C.c_uint64(), C.c_uint64()
-        self.lib.lf_gpu_seed_timing(self.ctx, C.byref(a), C.byref(b), C.byref(p), C.byref(h))
-        return {"search_ms": a.value, "locate_ms": b.value, "positions": p.value, "hits": h.value}
+    def seed_stats(self) -> dict:
+        st = SeedStats()
+        self.lib.lf_gpu_seed_stats(self.ctx, C.byref(st))
+        return {k: getattr(st, k) for k, _ in SeedStats._fields_}
 
     # ---- phased forms (keep a batch resident in HBM) ----
     def upload_reads(self, bases, offsets):

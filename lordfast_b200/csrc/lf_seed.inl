@@ -9,9 +9,10 @@
  *   sample positions   seed_pos += step in double precision, truncated: one thread per read repeats exactly those adds
  *                      (k_seed_positions); everything after that is parallel over (read, sample).
  *   longest match      the reference tries lengths MIN_ANCHOR_LEN, +1, +2 ... with a fresh backward search each, until
- *                      one fails.  k_seed_search does the same searches, one thread per sample: the interval of a length
- *                      is a property of the index, not of the order of the probes, and a search is a handful of
- *                      dependent 64-byte reads, which is what a GPU hides best with many threads in flight.
+ *                      one fails.  k_seed_search runs the same kind of search, one thread per sample, but picks the
+ *                      lengths by doubling and bisection ("length L occurs" is monotone): the interval of a length is a
+ *                      property of the index, not of the order of the probes, and a search is a handful of dependent
+ *                      64-byte reads, which is what a GPU hides best with many threads in flight.
  *   containment filter "kept if pos + m > last_pos" where last_pos is the end of the last kept sample: kept samples have
  *                      strictly increasing ends and a dropped one ends at or before last_pos, so last_pos is the running
  *                      maximum of the ends of all earlier samples with an acceptable hit count -- a prefix maximum, one
@@ -39,56 +40,93 @@ __device__ __forceinline__ uint32_t lf_fm_nt4(uint32_t ch)
     return ((0x54474341u >> (8u * code)) & 0xffu) == uc ? code : 4u;
 }
 
-__device__ __forceinline__ int lf_fm_occ_aux(unsigned long long y, uint32_t c)
-{ /* __occ_aux, lib/bwa/bwt.c:100-108: bases equal to c among the 32 of y */
-    y = ((c & 2u) ? y : ~y) >> 1 & ((c & 1u) ? y : ~y) & 0x5555555555555555ull;
-    return __popcll(y);
+__device__ __forceinline__ unsigned long long lf_fm_L2(const LfFmDev &fm, uint32_t c)
+{ /* L2[c], c = 0..4, without indexing the kernel parameter dynamically (that would copy it to local memory) */
+    return c == 0 ? fm.L2[0] : c == 1 ? fm.L2[1] : c == 2 ? fm.L2[2] : c == 3 ? fm.L2[3] : fm.L2[4];
+}
+
+/* One 64-byte block of bwt_t::bwt: four 64-bit running counts, then 128 bases in eight words, first base on top. */
+struct LfFmBlock { uint4 c01, c23, b0, b1; };
+__device__ __forceinline__ LfFmBlock lf_fm_block(const LfFmDev &fm, unsigned long long k)
+{
+    const uint4 *p = (const uint4 *)(fm.bwt + ((k >> 7) << 4));
+    LfFmBlock b;
+    b.c01 = __ldg(p); b.c23 = __ldg(p + 1); b.b0 = __ldg(p + 2); b.b1 = __ldg(p + 3);
+    return b;
+}
+/* bases equal to c among the first nb (0..16) of a word: what __occ_aux (lib/bwa/bwt.c:100-108) counts, with the mask
+ * applied after the comparison (so the correction for masked-out bases that look like A, :129, is not needed) */
+__device__ __forceinline__ uint32_t lf_fm_word_count(uint32_t x, uint32_t m1, uint32_t m2, int nb)
+{
+    const uint32_t t = ((x ^ m2) >> 1) & (x ^ m1) & 0x55555555u;
+    const int n = nb < 0 ? 0 : nb > 16 ? 16 : nb;
+    return (uint32_t)__popc(t & (uint32_t)(0xffffffff00000000ull >> (2 * n)));
+}
+/* occurrences of c in rows 0..k of the block that holds k (k already without the $ row) */
+__device__ __forceinline__ unsigned long long lf_fm_block_occ(const LfFmBlock &b, unsigned long long k, uint32_t c)
+{
+    const uint32_t lo = c == 0 ? b.c01.x : c == 1 ? b.c01.z : c == 2 ? b.c23.x : b.c23.z;
+    const uint32_t hi = c == 0 ? b.c01.y : c == 1 ? b.c01.w : c == 2 ? b.c23.y : b.c23.w;
+    const uint32_t m1 = (c & 1u) ? 0u : 0xffffffffu, m2 = (c & 2u) ? 0u : 0xffffffffu;
+    const int kk = (int)(k & 127ull) + 1;      /* bases of the block to count */
+    uint32_t n = lf_fm_word_count(b.b0.x, m1, m2, kk) + lf_fm_word_count(b.b0.y, m1, m2, kk - 16) + lf_fm_word_count(b.b0.z, m1, m2, kk - 32) + lf_fm_word_count(b.b0.w, m1, m2, kk - 48)
+               + lf_fm_word_count(b.b1.x, m1, m2, kk - 64) + lf_fm_word_count(b.b1.y, m1, m2, kk - 80) + lf_fm_word_count(b.b1.z, m1, m2, kk - 96) + lf_fm_word_count(b.b1.w, m1, m2, kk - 112);
+    return ((unsigned long long)hi << 32 | lo) + n;
 }
 
 __device__ __forceinline__ unsigned long long lf_fm_occ(const LfFmDev &fm, unsigned long long k, uint32_t c)
 { /* bwt_occ, lib/bwa/bwt.c:110-132 */
-    if (k == fm.seq_len) return fm.L2[c + 1] - fm.L2[c];
+    if (k == fm.seq_len) return lf_fm_L2(fm, c + 1u) - lf_fm_L2(fm, c);
     if (k == ~0ull) return 0;
     k -= (k >= fm.primary) ? 1ull : 0ull;
-    const uint32_t *p = fm.bwt + ((k >> 7) << 4);
-    unsigned long long n = __ldg((const unsigned long long *)p + c);
-    p += 8;
-    const int nfull = (int)((k & 127ull) >> 5);
-    for (int w = 0; w < nfull; w++) n += (unsigned long long)lf_fm_occ_aux((unsigned long long)__ldg(p + 2 * w) << 32 | __ldg(p + 2 * w + 1), c);
-    const unsigned long long y = ((unsigned long long)__ldg(p + 2 * nfull) << 32 | __ldg(p + 2 * nfull + 1)) & ~((1ull << ((~k & 31ull) << 1)) - 1ull);
-    n += (unsigned long long)lf_fm_occ_aux(y, c);
-    if (c == 0) n -= ~k & 31ull;
-    return n;
+    return lf_fm_block_occ(lf_fm_block(fm, k), k, c);
 }
 
-/* one backward-search step: the interval [k, l] of a pattern becomes that of c + pattern (src/BWT.cpp:287-291;
- * bwt_2occ, lib/bwa/bwt.c:135-166, is two bwt_occ that share a block) */
+/* one backward-search step: the interval [k, l] of a pattern becomes that of c + pattern (src/BWT.cpp:287-291).
+ * As in bwt_2occ (lib/bwa/bwt.c:135-166) the two lookups share the block when both rows lie in it -- the usual case once
+ * the interval is small. */
 __device__ __forceinline__ void lf_fm_step(const LfFmDev &fm, unsigned long long &k, unsigned long long &l, uint32_t c)
 {
-    const unsigned long long ok = lf_fm_occ(fm, k - 1ull, c), ol = lf_fm_occ(fm, l, c);
-    k = fm.L2[c] + ok + 1ull;
-    l = fm.L2[c] + ol;
+    unsigned long long ok, ol;
+    const unsigned long long k1 = k - 1ull;
+    const unsigned long long ka = k1 - ((k1 >= fm.primary) ? 1ull : 0ull), la = l - ((l >= fm.primary) ? 1ull : 0ull);
+    if (k1 != ~0ull && l != fm.seq_len && k1 != fm.seq_len && (ka >> 7) == (la >> 7)) {
+        const LfFmBlock b = lf_fm_block(fm, ka);
+        ok = lf_fm_block_occ(b, ka, c); ol = lf_fm_block_occ(b, la, c);
+    } else { ok = lf_fm_occ(fm, k1, c); ol = lf_fm_occ(fm, l, c); }
+    const unsigned long long base = lf_fm_L2(fm, c);
+    k = base + ok + 1ull;
+    l = base + ol;
 }
 
 __device__ __forceinline__ unsigned long long lf_fm_inv_psi(const LfFmDev &fm, unsigned long long k)
 { /* bwt_invPsi, lib/bwa/bwt.c:52-58 */
     const unsigned long long x = k - ((k > fm.primary) ? 1ull : 0ull);
     const uint32_t c = (__ldg(fm.bwt + ((x >> 7) << 4) + 8 + ((x & 127ull) >> 4)) >> ((~x & 15ull) << 1)) & 3u;
-    const unsigned long long r = fm.L2[c] + lf_fm_occ(fm, k, c);
+    const unsigned long long r = lf_fm_L2(fm, c) + lf_fm_occ(fm, k, c);
     return k == fm.primary ? 0ull : r;
 }
 
-__device__ __forceinline__ unsigned long long lf_fm_sa(const LfFmDev &fm, unsigned long long k)
+/* sum over the warp, added once to a global counter (work statistics of a batch) */
+__device__ __forceinline__ void lf_seed_count(unsigned long long *ctr, uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(LF_FULL, v, o);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(ctr, (unsigned long long)v);
+}
+
+__device__ __forceinline__ unsigned long long lf_fm_sa(const LfFmDev &fm, unsigned long long k, uint32_t &steps)
 { /* bwt_sa, lib/bwa/bwt.c:86-98 */
     unsigned long long sa = 0;
     while (k & fm.sa_mask) { ++sa; k = lf_fm_inv_psi(fm, k); }
+    steps = (uint32_t)sa;
     return sa + __ldg(fm.sa + (k >> fm.sa_shift));
 }
 
 /* bwt_count_exact_cached (src/BWT.cpp:265-298) on the bases s[0 .. len): the last k_cache of them index the k-mer table,
  * the others extend to the left one by one.  Positions at or past `avail` read as the NUL the reference finds there.
  * Returns the number of occurrences (0: none, k and l untouched as in the reference). */
-__device__ __forceinline__ long long lf_fm_count(const LfFmDev &fm, const uint8_t *__restrict__ s, long long avail, int len, unsigned long long &k_out, unsigned long long &l_out)
+__device__ __forceinline__ long long lf_fm_count(const LfFmDev &fm, const uint8_t *__restrict__ s, long long avail, int len, unsigned long long &k_out, unsigned long long &l_out, uint32_t &steps)
 {
     if ((long long)len > avail) return 0;          /* a base past the end of the read is not ACGT */
     uint32_t idx = 0;
@@ -104,6 +142,7 @@ __device__ __forceinline__ long long lf_fm_count(const LfFmDev &fm, const uint8_
         const uint32_t c = lf_fm_nt4(__ldg(s + i));
         if (c > 3u) return 0;
         lf_fm_step(fm, k, l, c);
+        steps++;
         if (k > l) return 0;
     }
     k_out = k; l_out = l;
@@ -150,23 +189,42 @@ __global__ void __launch_bounds__(128) k_seed_positions(const uint64_t *__restri
 /* longest match at one sample (src/BWT.cpp:328-342): one thread per (read, sample) */
 __global__ void __launch_bounds__(128) k_seed_search(LfFmDev fm, const uint8_t *__restrict__ bases, const uint64_t *__restrict__ read_off, uint32_t n_reads, uint32_t S,
                                                      int min_len, long long max_hits, const uint32_t *__restrict__ pos, uint32_t *__restrict__ mlen,
-                                                     unsigned long long *__restrict__ sp_out, uint32_t *__restrict__ cnt)
+                                                     unsigned long long *__restrict__ sp_out, uint32_t *__restrict__ cnt, unsigned long long *__restrict__ ctr)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (size_t)n_reads * S) return;
-    const uint32_t r = (uint32_t)(g / S);
-    const uint64_t ro = read_off[r];
-    const long long qlen = (long long)(read_off[r + 1] - ro);
-    const uint32_t p = pos[g];
-    const uint8_t *s = bases + ro + p;
-    const long long avail = qlen - (long long)p;
-    int m = min_len;
-    unsigned long long sp = 0, ep = 0, k2 = 0, l2 = 0;
-    long long occ = lf_fm_count(fm, s, avail, m, sp, ep), o2;
-    while ((o2 = lf_fm_count(fm, s, avail, m + 1, k2, l2)) > 0) { occ = o2; sp = k2; ep = l2; m++; }
-    mlen[g] = (uint32_t)m;
-    sp_out[g] = sp;
-    cnt[g] = (occ > 0 && occ < max_hits) ? (uint32_t)occ : 0u;
+    uint32_t steps = 0;
+    if (g < (size_t)n_reads * S) {
+        const uint32_t r = (uint32_t)(g / S);
+        const uint64_t ro = read_off[r];
+        const long long qlen = (long long)(read_off[r + 1] - ro);
+        const uint32_t p = pos[g];
+        const uint8_t *s = bases + ro + p;
+        const long long avail = qlen - (long long)p;
+        /* The reference lengthens the match one base at a time until a search fails.  "Length L occurs" is monotone in L
+         * (a longer pattern contains the shorter one, a bad base or the end of the read stays inside it), so the same
+         * last success is found by doubling the increment until a search fails and bisecting the gap: about 2 (m - 12)
+         * search steps instead of (m - 12)^2 / 2, and the interval kept is the one of the last successful search. */
+        int m = min_len;
+        unsigned long long sp = 0, ep = 0, k2 = 0, l2 = 0;
+        long long occ = lf_fm_count(fm, s, avail, m, sp, ep, steps), o2;
+        if (occ > 0) {
+            int hi, inc = 1;
+            for (;;) {
+                const int L = m + inc;
+                if ((o2 = lf_fm_count(fm, s, avail, L, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = L; inc <<= 1; }
+                else { hi = L; break; }
+            }
+            while (hi - m > 1) {
+                const int mid = (m + hi) >> 1;
+                if ((o2 = lf_fm_count(fm, s, avail, mid, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = mid; }
+                else hi = mid;
+            }
+        }
+        mlen[g] = (uint32_t)m;
+        sp_out[g] = sp;
+        cnt[g] = (occ > 0 && occ < max_hits) ? (uint32_t)occ : 0u;
+    }
+    lf_seed_count(ctr, steps);   /* backward-search steps: two occurrence lookups each */
 }
 
 /* containment filter (src/BWT.cpp:345, :387): cnt[i] stays only where pos + m exceeds the ends of all earlier
@@ -197,10 +255,10 @@ __global__ void __launch_bounds__(128) k_seed_filter(uint32_t n_reads, uint32_t 
  * exclusive hit offset is the last one <= h (found read first, then sample: both searches stay in cache) */
 __global__ void __launch_bounds__(128) k_seed_locate(LfFmDev fm, const uint64_t *__restrict__ read_off, uint32_t n_reads, uint32_t S, const unsigned long long *__restrict__ hoff /* n_reads*S + 1 */,
                                                      const uint32_t *__restrict__ pos, const uint32_t *__restrict__ mlen, const unsigned long long *__restrict__ sp,
-                                                     unsigned long long n_hits, lf_seed *__restrict__ hits, uint32_t *__restrict__ is_rev)
+                                                     unsigned long long n_hits, lf_seed *__restrict__ hits, uint32_t *__restrict__ is_rev, unsigned long long *__restrict__ ctr)
 {
     const unsigned long long h = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= n_hits) return;
+    if (h >= n_hits) { lf_seed_count(ctr, 0u); return; }   /* the whole warp takes part in the count */
     uint32_t lo = 0, hi = n_reads;                 /* last read r with hoff[r*S] <= h */
     while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (hoff[(size_t)mid * S] <= h) lo = mid; else hi = mid; }
     const uint32_t r = lo;
@@ -210,7 +268,8 @@ __global__ void __launch_bounds__(128) k_seed_locate(LfFmDev fm, const uint64_t 
     const size_t g = (size_t)r * S + lo;
     const uint32_t m = mlen[g], p = pos[g];
     const uint32_t qlen = (uint32_t)(read_off[r + 1] - read_off[r]);
-    unsigned long long sapos = lf_fm_sa(fm, sp[g] + (h - ho[lo]));
+    uint32_t steps = 0;
+    unsigned long long sapos = lf_fm_sa(fm, sp[g] + (h - ho[lo]), steps);
     lf_seed sd;
     uint32_t rev = 0;
     if (sapos >= (unsigned long long)fm.l_pac) { /* reverse strand */
@@ -222,6 +281,7 @@ __global__ void __launch_bounds__(128) k_seed_locate(LfFmDev fm, const uint64_t 
     sd.len = m & 0xfffu;                          /* Seed_t: qPos is a 20-bit and len a 12-bit field (src/LordFAST.h:30-35) */
     hits[h] = sd;
     is_rev[h] = rev;
+    lf_seed_count(ctr, steps);   /* inverse-psi steps: one base + one occurrence lookup each */
 }
 
 /* stable split into the two lists: rbefore[h] = reverse hits before h */
@@ -265,10 +325,9 @@ struct SeedState {
     LfFmDev fm = {};
     bool ready = false;
     size_t n_cache = 0;
-    LfbBuf bwt, sa, cache, pos, mlen, sp, cnt, hoff, hits, is_rev, rbefore, fwd, rev, fwd_off, rev_off;
+    LfbBuf bwt, sa, cache, pos, mlen, sp, cnt, hoff, hits, is_rev, rbefore, fwd, rev, fwd_off, rev_off, ctr;
     PinnedBuf h_fwd, h_rev, h_off, h_tot;
-    float search_ms = 0, locate_ms = 0;
-    uint64_t positions = 0, n_hits = 0;
+    lf_seed_stats st = {};
 #ifndef LF_EMU
     cudaEvent_t ev[4] = {};
 #endif
@@ -277,7 +336,7 @@ struct SeedState {
 void seed_state_free_fn(void *p)
 {
     SeedState *s = (SeedState *)p;
-    LfbBuf *bufs[] = { &s->bwt, &s->sa, &s->cache, &s->pos, &s->mlen, &s->sp, &s->cnt, &s->hoff, &s->hits, &s->is_rev, &s->rbefore, &s->fwd, &s->rev, &s->fwd_off, &s->rev_off };
+    LfbBuf *bufs[] = { &s->bwt, &s->sa, &s->cache, &s->pos, &s->mlen, &s->sp, &s->cnt, &s->hoff, &s->hits, &s->is_rev, &s->rbefore, &s->fwd, &s->rev, &s->fwd_off, &s->rev_off, &s->ctr };
     for (LfbBuf *b : bufs) b->release();
     s->h_fwd.release(); s->h_rev.release(); s->h_off.release(); s->h_tot.release();
 #ifndef LF_EMU
@@ -366,13 +425,14 @@ int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_para
     if (np >> 31) { delete res; return fail(ctx, LF_ERR_BAD_ARG, "lf_gpu_seed_batch: n_reads * sampling_count >= 2^31: split the batch"); }
     lfb_stream s = d.stream;
     auto bail = [&](int code, const char *msg) { delete res; return fail(ctx, code, msg); };
-    if (S.pos.reserve(np * 4) || S.mlen.reserve(np * 4) || S.sp.reserve(np * 8) || S.cnt.reserve(np * 4) || S.hoff.reserve((np + 1) * 8)) return bail(LF_ERR_NOMEM, "seed samples");
+    if (S.pos.reserve(np * 4) || S.mlen.reserve(np * 4) || S.sp.reserve(np * 8) || S.cnt.reserve(np * 4) || S.hoff.reserve((np + 1) * 8) || S.ctr.reserve(16)) return bail(LF_ERR_NOMEM, "seed samples");
+    if (lfb_memset(S.ctr.p, 0, 16, s)) return bail(LF_ERR_CUDA, "seed counters");
 #ifndef LF_EMU
     cudaEventRecord(S.ev[0], s);
 #endif
     LFB_LAUNCH(k_seed_positions, (n_reads + 127) / 128, 128, 0, s, d.read_off.as<uint64_t>(), n_reads, SC, S.pos.as<uint32_t>());
     LFB_LAUNCH(k_seed_search, (unsigned)((np + 127) / 128), 128, 0, s, S.fm, d.bases.as<uint8_t>(), d.read_off.as<uint64_t>(), n_reads, SC, (int)prm->min_anchor_len, (long long)prm->max_ref_hits,
-               S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.sp.as<unsigned long long>(), S.cnt.as<uint32_t>());
+               S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.sp.as<unsigned long long>(), S.cnt.as<uint32_t>(), S.ctr.as<unsigned long long>());
     LFB_LAUNCH(k_seed_filter, (n_reads + 3) / 4, 128, 0, s, n_reads, SC, S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.cnt.as<uint32_t>());
     if (lfb_scan_excl_total(d.tmp, S.cnt.as<uint32_t>(), S.hoff.as<unsigned long long>(), np, s)) return bail(LF_ERR_CUDA, "seed scan");
 #ifndef LF_EMU
@@ -390,7 +450,7 @@ int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_para
 #endif
     if (H) {
         LFB_LAUNCH(k_seed_locate, (unsigned)((H + 127) / 128), 128, 0, s, S.fm, d.read_off.as<uint64_t>(), n_reads, SC, S.hoff.as<unsigned long long>(), S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(),
-                   S.sp.as<unsigned long long>(), H, S.hits.as<lf_seed>(), S.is_rev.as<uint32_t>());
+                   S.sp.as<unsigned long long>(), H, S.hits.as<lf_seed>(), S.is_rev.as<uint32_t>(), S.ctr.as<unsigned long long>() + 1);
         if (lfb_scan_excl_total(d.tmp, S.is_rev.as<uint32_t>(), S.rbefore.as<unsigned long long>(), (size_t)H, s)) return bail(LF_ERR_CUDA, "seed strand scan");
         LFB_LAUNCH(k_seed_scatter, (unsigned)((H + 255) / 256), 256, 0, s, S.hits.as<lf_seed>(), S.is_rev.as<uint32_t>(), S.rbefore.as<unsigned long long>(), H, S.fwd.as<lf_seed>(), S.rev.as<lf_seed>());
     } else if (lfb_memset(S.rbefore.p, 0, 8, s)) return bail(LF_ERR_CUDA, "seed memset");
@@ -400,7 +460,7 @@ int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_para
     cudaEventRecord(S.ev[3], s);
 #endif
     if (lfb_last_error()) return bail(LF_ERR_CUDA, "seed kernels");
-    if (lfb_d2h(h_fwd_off, S.fwd_off.p, off_bytes, s) || lfb_d2h(h_rev_off, S.rev_off.p, off_bytes, s) || lfb_d2h(h_tot + 1, S.rbefore.as<unsigned long long>() + H, 8, s) || lfb_sync(s))
+    if (lfb_d2h(h_fwd_off, S.fwd_off.p, off_bytes, s) || lfb_d2h(h_rev_off, S.rev_off.p, off_bytes, s) || lfb_d2h(h_tot + 1, S.rbefore.as<unsigned long long>() + H, 8, s) || lfb_d2h(h_tot + 2, S.ctr.p, 16, s) || lfb_sync(s))
         return bail(LF_ERR_CUDA, "seed offsets download");
     const unsigned long long n_rev = h_tot[1], n_fwd = H - n_rev;
     if (S.h_fwd.reserve((size_t)n_fwd * sizeof(lf_seed) + 16) || S.h_rev.reserve((size_t)n_rev * sizeof(lf_seed) + 16)) return bail(LF_ERR_NOMEM, "seed lists (pinned)");
@@ -408,10 +468,10 @@ int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_para
         return bail(LF_ERR_CUDA, "seed lists download");
     res->fwd = (const lf_seed *)S.h_fwd.p; res->rev = (const lf_seed *)S.h_rev.p;
     res->n_fwd = (size_t)n_fwd; res->n_rev = (size_t)n_rev;
-    S.positions = np; S.n_hits = H;
+    S.st.positions = np; S.st.hits = H; S.st.search_steps = h_tot[2]; S.st.locate_steps = h_tot[3];
 #ifndef LF_EMU
-    cudaEventElapsedTime(&S.search_ms, S.ev[0], S.ev[1]);
-    cudaEventElapsedTime(&S.locate_ms, S.ev[2], S.ev[3]);
+    cudaEventElapsedTime(&S.st.search_ms, S.ev[0], S.ev[1]);
+    cudaEventElapsedTime(&S.st.locate_ms, S.ev[2], S.ev[3]);
 #endif
     *out = res;
     return LF_OK;
@@ -427,14 +487,10 @@ const lf_seed *lf_seed_results_list(const lf_seed_results *r, int reverse, const
 
 void lf_seed_results_free(lf_seed_results *r) { delete r; }
 
-int lf_gpu_seed_timing(lf_gpu_ctx *ctx, float *search_ms, float *locate_ms, uint64_t *positions, uint64_t *hits)
+int lf_gpu_seed_stats(lf_gpu_ctx *ctx, lf_seed_stats *out)
 {
-    if (!ctx) return LF_ERR_BAD_ARG;
-    SeedState &S = seed_state(ctx);
-    if (search_ms) *search_ms = S.search_ms;
-    if (locate_ms) *locate_ms = S.locate_ms;
-    if (positions) *positions = S.positions;
-    if (hits) *hits = S.n_hits;
+    if (!ctx || !out) return LF_ERR_BAD_ARG;
+    *out = seed_state(ctx).st;
     return LF_OK;
 }
 

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared():
     text = open(os.path.join(ROOT, "include", "lf_gpu.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(lf_(?:gpu|chain_results)_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(lf_(?:gpu|chain_results|seed_results)_\w+)\s*\(", text)))
 
 
 def test_header_and_binding_agree():
