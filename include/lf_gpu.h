@@ -182,7 +182,9 @@ typedef struct {
 } lf_chain_stats;
 typedef struct lf_chain_results lf_chain_results;         /* library-owned, free with lf_chain_results_free */
 
-/* pac_host: the same 2-bit reference that was given to lf_gpu_init (MD strings need reference bases). */
+/* pac_host: the same 2-bit reference that was given to lf_gpu_init (MD strings need reference bases).
+ * reads->bases == NULL (offsets and n_reads still given): the reads are the ones the last lf_gpu_upload_reads /
+ * lf_gpu_seed_batch left on the device -- no second trip over PCIe for a chunk that was just seeded (single device). */
 int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs *contigs, const lf_seed *seeds,
                         const lf_chain *chains, size_t n_chains, const uint8_t *pac_host, lf_chain_results **out);
 const lf_sam_record *lf_chain_results_records(const lf_chain_results *r, size_t *n);

@@ -7,7 +7,9 @@
  * copied into this repository) with its chunk driver `mapSeqMT` (src/LordFAST.cpp:305-316) renamed,
  * and defines a batched `mapSeqMT` of its own, so the stock main() (src/baseFAST.cpp:32-84) calls it:
  *
- *   phase 1  host threads, stock front-end per read: getLocs_extend_whole_step, findTopWins_coarse /
+ *   phase 0  ONE lf_gpu_seed_batch call for the chunk: getLocs_extend_whole_step (src/BWT.cpp:312-394) of every read,
+ *            on bwa's index as the program loaded it (LF_GPU_SEED=0 keeps the stock per-read call in phase 1).
+ *   phase 1  host threads, stock front-end per read: the seed lists of phase 0, findTopWins_coarse /
  *            findTopWins_fine, the coarse / fine decision of mapSeq (:535-568), and per window the
  *            seed selection + chain_seeds_n2 | chain_seeds_clasp of alignWin (:994-1059 / :1090-1144).
  *            Where alignWin would call the hook `alignChain` (:107, :1066 / :1151) the chain is
@@ -31,6 +33,7 @@
 #include "lf_gpu.h"
 
 extern bwaidx_t *_fmd_index; /* src/BWT.cpp:32 */
+extern int32_t kCache;       /* src/BWT.cpp:34: k of the k-mer table the index was built with */
 
 /* CUDA start-up (seconds on a cold box) overlaps the index load: this runs before main() of src/baseFAST.cpp */
 __attribute__((constructor)) static void lfglue_prewarm(int argc, char **argv, char **)
@@ -77,6 +80,11 @@ static std::vector<uint64_t> g_rec_first; /* per merged chain: first record, rec
 static const lf_sam_record *g_rec = nullptr;
 static const char *g_text = nullptr;
 static double g_ms[4];
+static bool g_seed_ok = false;               /* lf_gpu_seed_init succeeded: chunks are seeded on the GPU */
+static int g_ndev = 0;
+static bool g_seed_gpu = false;              /* phase 0 ran: the seed lists of the chunk are in g_sd* */
+static const lf_seed *g_sd[2] = {nullptr, nullptr};
+static const uint64_t *g_sd_off[2] = {nullptr, nullptr};
 
 static double now_ms()
 {
@@ -150,7 +158,14 @@ static void *collect(void *idp)
         P.n_win = 0;
         P.kind = RK_UNMAPPED;
         if (readLen < (uint32_t)MIN_READ_LEN) continue;
-        getLocs_extend_whole_step(read->seq, readLen, SAMPLING_COUNT, _pf_seedsForward + id, _pf_seedsReverse + id);
+        if (g_seed_gpu) {   /* the lists lf_gpu_seed_batch wrote for read t, into the worker's SeedLists (Seed_t packs qPos and len) */
+            SeedList *dst[2] = {_pf_seedsForward + id, _pf_seedsReverse + id};
+            for (int k = 0; k < 2; k++) {
+                const uint64_t a = g_sd_off[k][t], b = g_sd_off[k][t + 1];
+                for (uint64_t i = a; i < b; i++) { Seed_t &o = dst[k]->list[i - a]; o.tPos = g_sd[k][i].tPos; o.qPos = g_sd[k][i].qPos; o.len = g_sd[k][i].len; }
+                dst[k]->num = (uint32_t)(b - a);
+            }
+        } else getLocs_extend_whole_step(read->seq, readLen, SAMPLING_COUNT, _pf_seedsForward + id, _pf_seedsReverse + id);
         WinList &top = _pf_topWins[id];
         top.num = 0;
         findTopWins_coarse(readLen, _pf_seedsForward + id, 0, t + 1, id);
@@ -261,26 +276,25 @@ void mapSeqMT()
         int rc = lf_gpu_init(&g_ctx, _fmd_index->pac, _fmd_index->bns->l_pac, ndev ? devs : nullptr, ndev);
         if (rc != LF_OK) die("lf_gpu_init", rc);
         fprintf(stderr, "[lordfast-gpu: lf_gpu_init %.1f ms] ", now_ms() - ti);
+        g_ndev = ndev;
+        const char *e = getenv("LF_GPU_SEED");
+        if (!e || atoi(e) != 0) {   /* the FM index as bwa_idx_load and bwt_cache_load left it (src/BWT.cpp:190-224); the k-mer table is derived on the device */
+            const bwt_t *b = _fmd_index->bwt;
+            lf_fm_index fm;
+            memset(&fm, 0, sizeof fm);
+            fm.bwt = b->bwt; fm.bwt_size = b->bwt_size; fm.primary = b->primary;
+            for (int i = 0; i < 5; i++) fm.L2[i] = b->L2[i];
+            fm.seq_len = b->seq_len; fm.sa = b->sa; fm.n_sa = b->n_sa; fm.sa_intv = b->sa_intv;
+            fm.k_cache = kCache; fm.cache = nullptr; fm.l_pac = _fmd_index->bns->l_pac;
+            const double ts = now_ms();
+            rc = lf_gpu_seed_init(g_ctx, &fm);
+            if (rc != LF_OK) die("lf_gpu_seed_init", rc);
+            g_seed_ok = true;
+            fprintf(stderr, "[lordfast-gpu: lf_gpu_seed_init %.1f ms] ", now_ms() - ts);
+        }
     }
     const double t0 = now_ms();
-    g_workers.assign(THREAD_COUNT, Worker());
-    g_plan.assign(_pf_seqListSize, ReadPlan());
-    run_threads(collect);
-    const double t1 = now_ms();
-
-    /* merge the workers' lists; gather the chunk's reads (each its own malloc block, src/Reads.cpp:84-90) */
-    uint64_t ns = 0, nc = 0;
-    for (Worker &W : g_workers) { W.seed_base = ns; W.chain_base = nc; ns += W.seeds.size(); nc += W.chains.size(); }
-    /* seeds and chains of the chunk in pinned memory kept between chunks: the library then reads them over PCIe as they are
-     * (from pageable memory it would first stage them, one more pass over 12 B per seed) */
-    static lf_seed *seeds = nullptr; static lf_chain *chains = nullptr;
-    static size_t seeds_cap = 0, chains_cap = 0;
-    if (ns + 2 > seeds_cap) { if (seeds) lf_gpu_host_free(seeds); seeds_cap = (ns + 2) * 5 / 4; seeds = (lf_seed *)lf_gpu_host_alloc(seeds_cap * sizeof(lf_seed)); if (!seeds) die("lf_gpu_host_alloc", LF_ERR_NOMEM); }
-    if (nc + 2 > chains_cap) { if (chains) lf_gpu_host_free(chains); chains_cap = (nc + 2) * 5 / 4; chains = (lf_chain *)lf_gpu_host_alloc(chains_cap * sizeof(lf_chain)); if (!chains) die("lf_gpu_host_alloc", LF_ERR_NOMEM); }
-    for (Worker &W : g_workers) {
-        if (!W.seeds.empty()) memcpy(&seeds[W.seed_base], W.seeds.data(), W.seeds.size() * sizeof(lf_seed));
-        for (size_t k = 0; k < W.chains.size(); k++) { lf_chain c = W.chains[k]; c.seed_off += W.seed_base; chains[W.chain_base + k] = c; }
-    }
+    /* gather the chunk's reads (each its own malloc block, src/Reads.cpp:84-90) into pinned memory kept between chunks */
     std::vector<uint64_t> off(_pf_seqListSize + 1, 0);
     for (int r = 0; r < _pf_seqListSize; r++) off[r + 1] = off[r] + *_pf_seqList[r].length;
     static uint8_t *bases = nullptr;   /* pinned, kept between chunks (pinning 100 MB costs tens of ms) */
@@ -300,11 +314,42 @@ void mapSeqMT()
         });
         for (auto &t : th) t.join();
     }
+    lf_reads rd = {bases, off.data(), (uint32_t)_pf_seqListSize};
+    /* phase 0: seeding of the whole chunk on the GPU */
+    lf_seed_results *sres = nullptr;
+    g_seed_gpu = false;
+    if (g_seed_ok && _pf_seqListSize > 0) {
+        const lf_seed_params sp = {MIN_ANCHOR_LEN, SAMPLING_COUNT, MAX_REF_HITS};
+        int rc = lf_gpu_seed_batch(g_ctx, &rd, &sp, &sres);
+        if (rc != LF_OK) die("lf_gpu_seed_batch", rc);
+        for (int k = 0; k < 2; k++) g_sd[k] = lf_seed_results_list(sres, k, &g_sd_off[k], nullptr);
+        g_seed_gpu = true;
+    }
+    const double t0s = now_ms();
+    g_workers.assign(THREAD_COUNT, Worker());
+    g_plan.assign(_pf_seqListSize, ReadPlan());
+    run_threads(collect);
+    if (sres) lf_seed_results_free(sres);
+    const double t1 = now_ms();
+
+    /* merge the workers' lists */
+    uint64_t ns = 0, nc = 0;
+    for (Worker &W : g_workers) { W.seed_base = ns; W.chain_base = nc; ns += W.seeds.size(); nc += W.chains.size(); }
+    /* seeds and chains of the chunk in pinned memory kept between chunks: the library then reads them over PCIe as they are
+     * (from pageable memory it would first stage them, one more pass over 12 B per seed) */
+    static lf_seed *seeds = nullptr; static lf_chain *chains = nullptr;
+    static size_t seeds_cap = 0, chains_cap = 0;
+    if (ns + 2 > seeds_cap) { if (seeds) lf_gpu_host_free(seeds); seeds_cap = (ns + 2) * 5 / 4; seeds = (lf_seed *)lf_gpu_host_alloc(seeds_cap * sizeof(lf_seed)); if (!seeds) die("lf_gpu_host_alloc", LF_ERR_NOMEM); }
+    if (nc + 2 > chains_cap) { if (chains) lf_gpu_host_free(chains); chains_cap = (nc + 2) * 5 / 4; chains = (lf_chain *)lf_gpu_host_alloc(chains_cap * sizeof(lf_chain)); if (!chains) die("lf_gpu_host_alloc", LF_ERR_NOMEM); }
+    for (Worker &W : g_workers) {
+        if (!W.seeds.empty()) memcpy(&seeds[W.seed_base], W.seeds.data(), W.seeds.size() * sizeof(lf_seed));
+        for (size_t k = 0; k < W.chains.size(); k++) { lf_chain c = W.chains[k]; c.seed_off += W.seed_base; chains[W.chain_base + k] = c; }
+    }
+    if (g_seed_gpu && g_ndev <= 1 && !getenv("LF_CHAIN_LANES")) rd.bases = nullptr;   /* the reads are still on the device from phase 0 */
     const bntseq_t *bns = _fmd_index->bns;
     std::vector<int64_t> coff(bns->n_seqs);
     std::vector<int32_t> clen(bns->n_seqs);
     for (int i = 0; i < bns->n_seqs; i++) { coff[i] = bns->anns[i].offset; clen[i] = bns->anns[i].len; }
-    lf_reads rd = {bases, off.data(), (uint32_t)_pf_seqListSize};
     lf_contigs cg = {coff.data(), clen.data(), bns->n_seqs};
 
     lf_chain_results *res = nullptr;
@@ -325,6 +370,6 @@ void mapSeqMT()
     if (res) lf_chain_results_free(res);
     const double t3 = now_ms();
     g_ms[0] += t1 - t0; g_ms[1] += t2 - t1; g_ms[2] += t3 - t2;
-    fprintf(stderr, "[lordfast-gpu: %llu chains, front-end %.1f ms, GPU alignment stage %.1f ms, scoring+SAM %.1f ms] ",
-            (unsigned long long)nc, t1 - t0, t2 - t1, t3 - t2);
+    fprintf(stderr, "[lordfast-gpu: %llu chains, gather + GPU seeding %.1f ms, front-end %.1f ms, GPU alignment stage %.1f ms, scoring+SAM %.1f ms] ",
+            (unsigned long long)nc, t0s - t0, t1 - t0s, t2 - t1, t3 - t2);
 }

@@ -553,7 +553,9 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
      * several devices assembles on host threads from the 2-bit op stream (LF_CHAIN_HOST_EMIT=1 forces that). */
     const bool gpu_emit = ctx->devs.size() == 1 && !getenv("LF_CHAIN_HOST_EMIT");
     if (!io) trace_ref(ctx->devs[0].stream);
-    LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
+    if (reads->bases) LF_CH(lf_gpu_upload_reads(ctx, reads)); /* asynchronous: overlaps the task generation below */
+    else if (io || ctx->devs.size() != 1 || ctx->devs[0].n_reads != reads->n_reads || !ctx->devs[0].n_reads) { delete R; return fail(ctx, LF_ERR_BAD_ARG, "lf_gpu_align_chains: bases == NULL needs the same reads resident on a single-device context"); }
+    /* (bases == NULL: the reads lf_gpu_seed_batch / lf_gpu_upload_reads left on the device, bit planes included, are used as they are) */
     trace_mark(ctx, "reads packed", ctx->devs[0].stream);
     const double tt1 = now_ms();
     /* single-device contexts: the task list is generated on the device (k_chain_tasks); the host only needs the few
@@ -1442,6 +1444,7 @@ int lf_gpu_align_chains(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_contigs
     if (K < 1) K = 1;
     g_trace_t0 = now_ms();
     if (ndev == 1 && K == 1) return align_chains_one(ctx, reads, contigs, seeds, chains, n_chains, pac_host, out, nullptr);
+    if (!reads->bases) return fail(ctx, LF_ERR_BAD_ARG, "lf_gpu_align_chains: resident reads (bases == NULL) need a single device and a single lane");
     *out = nullptr;
     for (size_t c = 0; c < n_chains; c++) if (chains[c].read_id >= reads->n_reads || chains[c].n_seeds < 2) return LF_ERR_BAD_ARG;
     ChainScratch &S = chain_scratch(ctx);
