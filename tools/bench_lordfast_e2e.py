@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """End-to-end `lordfast --search -t N`: the unmodified reference (oracle/_ref/lordfast, CPU) beside the same program
-with the alignment stage on the GPU (integration/_build/lordfast_gpu), on the same synthetic input, on this box.
+with seeding and the alignment stage on the GPU (integration/_build/lordfast_gpu; LF_GPU_SEED=0 in the environment: alignment stage only), on the same synthetic input, on this box.
 Wall time = sum of the program's own "mapping... done in" lines; the SAM files are compared (sorted).
 Prints one JSON line.  Nothing here reads /root/reference.
 
@@ -27,8 +27,9 @@ def run(binary, tmp, out, threads, extra):
     wall = time.time() - t0
     mapping = sum(float(x) for x in re.findall(r"done in ([0-9.]+) seconds", p.stderr))
     phases = [tuple(float(v) for v in m) for m in re.findall(r"front-end ([0-9.]+) ms, GPU alignment stage ([0-9.]+) ms, scoring\+SAM ([0-9.]+) ms", p.stderr)]
+    seeding = [float(v) for v in re.findall(r"gather \+ GPU seeding ([0-9.]+) ms", p.stderr)]
     init = re.findall(r"lf_gpu_init ([0-9.]+) ms", p.stderr)
-    return wall, mapping, phases, float(init[0]) if init else 0.0
+    return wall, mapping, phases, float(init[0]) if init else 0.0, seeding
 
 
 def main():
@@ -74,7 +75,7 @@ def main():
         "gpu": {"mapping_s": best["gpu"][1], "wall_s": round(best["gpu"][0], 2), "mbp_per_s": round(bases / 1e6 / best["gpu"][1], 2),
                 "chunks": len(ph), "lf_gpu_init_ms": best["gpu"][3],
                 "gpu_stage_ms_per_chunk": [p[1] for p in ph],
-                "phases_ms": {"front_end_cpu": sum(p[0] for p in ph), "gpu_alignment_stage": sum(p[1] for p in ph), "scoring_and_sam_cpu": sum(p[2] for p in ph)}},
+                "phases_ms": {"gather_and_gpu_seeding": sum(best["gpu"][4]), "front_end_cpu": sum(p[0] for p in ph), "gpu_alignment_stage": sum(p[1] for p in ph), "scoring_and_sam_cpu": sum(p[2] for p in ph)}},
         "speedup_mapping": round(best["cpu"][1] / best["gpu"][1], 2),
         "sam_records": len(sa), "sam_identical_sorted": sa == sb,
     }))
