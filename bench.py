@@ -467,9 +467,20 @@ def main():
         if not a.no_cpu_baseline:
             v, kind, cores, sample = cpu_reference_rate(si, os.cpu_count() or 1, max_chains=4000)
             out["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(out))
     p_tasks.free(); p_bases.free(); p_seeds.free(); p_chains.free()
     g.close()
+    if rank == 0:
+        if world == 1 and wl_name == "config2_real" and not os.environ.get("LF_BENCH_NO_SEEDING"):
+            # the stage in front of this one, on the same reads: key figures of bench_seed.py (its own line has the rest)
+            try:
+                import bench_seed
+                sd = bench_seed.measure(steps=5, warmup=3, cpu_sample=200, cpu_baseline=not a.no_cpu_baseline,
+                                        data=(si.fixture.ref, np.ascontiguousarray(si.reads, dtype=np.uint8), si.read_off.astype(np.uint64), "config2_real reads (fixtures/config2.npz)"))
+                out["seeding"] = {"metric": sd["metric"], "value": sd["value"], "unit": sd["unit"], "ms_per_step": sd["ms_per_step"], "e2e": sd["e2e"],
+                                  "kernels": sd["kernels"], "roofline": sd["roofline"], "cpu_baseline": sd.get("cpu_baseline"), "call": "lf_gpu_seed_batch"}
+            except Exception as e:   # noqa: BLE001 -- the alignment line must not depend on it
+                out["seeding"] = {"unavailable": repr(e)}
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

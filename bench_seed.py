@@ -122,18 +122,11 @@ def cpu_reference(ref, reads, off, sample, gpu_lists):
             "gpu_lists_checked": min(n, 64), "gpu_list_mismatches": mism}, None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=0, help="first N reads of the workload (0 = all 20 000)")
-    ap.add_argument("--cpu-sample", type=int, default=400)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    a = ap.parse_args()
+def measure(steps=10, warmup=3, n_reads=0, cpu_sample=400, cpu_baseline=True, data=None):
     import torch   # device memory / stream plumbing of the process; the kernels are the library's
     if not torch.cuda.is_available():
         raise SystemExit("bench_seed.py needs a CUDA device (there is no CPU path for the seeding stage)")
-    ref, reads, off, name = workload(a.reads)
+    ref, reads, off, name = data if data is not None else workload(n_reads)   # data: (reference ASCII, read bases, offsets, name) already in memory
     fm = fm_for(ref)
     g = api.LfGpu(sim.pack_pac(ref), len(ref))
     t0 = time.perf_counter()
@@ -143,17 +136,17 @@ def main():
     hb = pin.view(np.uint8, len(reads)); hb[:] = reads
     bases = int(off[-1])
     first = g.seed_batch(hb, off)
-    for _ in range(max(a.warmup, 3) - 1):
+    for _ in range(max(warmup, 3) - 1):
         g.seed_batch(None, off, copy=False)
     t = []
-    for _ in range(a.steps):
+    for _ in range(steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         g.seed_batch(None, off, copy=False)
         t.append(time.perf_counter() - t0)
     st = g.seed_stats()
     te = []
-    for _ in range(a.steps):
+    for _ in range(steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         g.seed_batch(hb, off, copy=False)
@@ -164,7 +157,7 @@ def main():
     peak, src = hbm_peak_gbs()
     ach = blocks * 64 / (kern_ms * 1e-3) / 1e9
     line = {"metric": "seeded Mbp/s (FM-index seeding stage, getLocs_extend_whole_step)", "value": bases / (ms * 1e-3) / 1e6, "unit": "Mbp/s", "n_gpus": 1,
-            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "u64", "data": "synthetic",
+            "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "u64", "data": "synthetic",
             "config": {"workload": name, "reads": len(off) - 1, "read_bases": bases, "reference_bp": len(ref), "min_anchor_len": 14, "sampling_count": 1000, "max_ref_hits": 1000,
                        "k_cache": 12, "sa_intv": fm.sa_intv, "l2": "index (bwt %.1f MB, sa %.1f MB, k-mer table 268 MB) + 202 MB of reads: the k-mer table and the reads exceed L2, the bwt of a 4.6 Mbp reference does not"
                        % (fm.bwt.nbytes / 1e6, fm.sa.nbytes / 1e6)},
@@ -175,10 +168,23 @@ def main():
             "roofline": {"bound": "hbm (random 64-byte blocks)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
                          "blocks_per_step": blocks, "note": "2 bwt blocks per backward-search step + 1 per inverse-psi step, counted by the kernels; a 4.6 Mbp index is L2-resident, so this is an L2/latency figure, not DRAM"},
             "gpu_launches": 8}
-    if not a.no_cpu_baseline:
-        cb, why = cpu_reference(ref, reads, off, a.cpu_sample, first)
+    if cpu_baseline:
+        cb, why = cpu_reference(ref, reads, off, cpu_sample, first)
         line["cpu_baseline"] = cb if cb else {"unavailable": why}
-    print(json.dumps(line))
+    pin.free()
+    g.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=0, help="first N reads of the workload (0 = all 20 000)")
+    ap.add_argument("--cpu-sample", type=int, default=400)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    print(json.dumps(measure(a.steps, a.warmup, a.reads, a.cpu_sample, not a.no_cpu_baseline)))
 
 
 if __name__ == "__main__":
