@@ -9,10 +9,11 @@
  *   sample positions   seed_pos += step in double precision, truncated: one thread per read repeats exactly those adds
  *                      (k_seed_positions); everything after that is parallel over (read, sample).
  *   longest match      the reference tries lengths MIN_ANCHOR_LEN, +1, +2 ... with a fresh backward search each, until
- *                      one fails.  k_seed_search runs the same kind of search, one thread per sample, but picks the
- *                      lengths by doubling and bisection ("length L occurs" is monotone): the interval of a length is a
- *                      property of the index, not of the order of the probes, and a search is a handful of dependent
- *                      64-byte reads, which is what a GPU hides best with many threads in flight.
+ *                      one fails.  k_seed_probe runs the first search for every sample, k_seed_extend lengthens the
+ *                      matches that exist, one thread each, picking the lengths by doubling and bisection ("length L
+ *                      occurs" is monotone): the interval of a length is a property of the index, not of the order of
+ *                      the probes, and a search is a handful of dependent 64-byte reads, which is what a GPU hides
+ *                      best with many threads in flight.
  *   containment filter "kept if pos + m > last_pos" where last_pos is the end of the last kept sample: kept samples have
  *                      strictly increasing ends and a dropped one ends at or before last_pos, so last_pos is the running
  *                      maximum of the ends of all earlier samples with an acceptable hit count -- a prefix maximum, one
@@ -186,45 +187,79 @@ __global__ void __launch_bounds__(128) k_seed_positions(const uint64_t *__restri
     }
 }
 
-/* longest match at one sample (src/BWT.cpp:328-342): one thread per (read, sample) */
-__global__ void __launch_bounds__(128) k_seed_search(LfFmDev fm, const uint8_t *__restrict__ bases, const uint64_t *__restrict__ read_off, uint32_t n_reads, uint32_t S,
-                                                     int min_len, long long max_hits, const uint32_t *__restrict__ pos, uint32_t *__restrict__ mlen,
-                                                     unsigned long long *__restrict__ sp_out, uint32_t *__restrict__ cnt, unsigned long long *__restrict__ ctr)
+/* Longest match at one sample (src/BWT.cpp:328-342), in two kernels so that the lanes of a warp have the same kind of work:
+ * k_seed_probe   one thread per (read, sample): the first search (MIN_ANCHOR_LEN bases).  Five samples in six of a noisy
+ *                read end here; the others are appended to a dense list.
+ * k_seed_extend  one thread per listed sample: lengthen the match.  The reference adds one base at a time until a search
+ *                fails.  "Length L occurs" is monotone in L (a longer pattern contains the shorter one, a bad base or the
+ *                end of the read stays inside it), so the same last success is found by doubling the increment until a
+ *                search fails and bisecting the gap: about 2 (m - 12) search steps instead of (m - 12)^2 / 2, and the
+ *                interval kept is the one of the last successful search. */
+__global__ void __launch_bounds__(128) k_seed_probe(LfFmDev fm, const uint8_t *__restrict__ bases, const uint64_t *__restrict__ read_off, uint32_t n_reads, uint32_t S,
+                                                    int min_len, long long max_hits, const uint32_t *__restrict__ pos, uint32_t *__restrict__ mlen,
+                                                    unsigned long long *__restrict__ sp_out, uint32_t *__restrict__ cnt, uint32_t *__restrict__ list, uint32_t *__restrict__ n_list,
+                                                    unsigned long long *__restrict__ ctr)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0;
+    bool more = false;
     if (g < (size_t)n_reads * S) {
         const uint32_t r = (uint32_t)(g / S);
         const uint64_t ro = read_off[r];
-        const long long qlen = (long long)(read_off[r + 1] - ro);
+        const uint32_t p = pos[g];
+        unsigned long long sp = 0, ep = 0;
+        const long long occ = lf_fm_count(fm, bases + ro + p, (long long)(read_off[r + 1] - ro) - (long long)p, min_len, sp, ep, steps);
+        mlen[g] = (uint32_t)min_len;
+        sp_out[g] = sp;
+        cnt[g] = (occ > 0 && occ < max_hits) ? (uint32_t)occ : 0u;   /* final if the match cannot be lengthened */
+        more = occ > 0;
+    }
+    /* dense list of the samples that matched: one atomic per warp */
+    const uint32_t bal = __ballot_sync(LF_FULL, more), lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0 && bal) base = atomicAdd(n_list, (uint32_t)__popc(bal));
+    base = __shfl_sync(LF_FULL, base, 0);
+    if (more) list[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint32_t)g;
+    lf_seed_count(ctr, steps);   /* backward-search steps: two occurrence lookups each */
+}
+
+__global__ void __launch_bounds__(128) k_seed_extend(LfFmDev fm, const uint8_t *__restrict__ bases, const uint64_t *__restrict__ read_off, uint32_t S,
+                                                     long long max_hits, const uint32_t *__restrict__ pos, uint32_t *__restrict__ mlen,
+                                                     unsigned long long *__restrict__ sp_out, uint32_t *__restrict__ cnt, const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list,
+                                                     unsigned long long *__restrict__ ctr)
+{
+    const uint32_t n = *n_list;
+    uint32_t steps = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t g = list[i];
+        const uint32_t r = g / S;
+        const uint64_t ro = read_off[r];
         const uint32_t p = pos[g];
         const uint8_t *s = bases + ro + p;
-        const long long avail = qlen - (long long)p;
-        /* The reference lengthens the match one base at a time until a search fails.  "Length L occurs" is monotone in L
-         * (a longer pattern contains the shorter one, a bad base or the end of the read stays inside it), so the same
-         * last success is found by doubling the increment until a search fails and bisecting the gap: about 2 (m - 12)
-         * search steps instead of (m - 12)^2 / 2, and the interval kept is the one of the last successful search. */
-        int m = min_len;
-        unsigned long long sp = 0, ep = 0, k2 = 0, l2 = 0;
-        long long occ = lf_fm_count(fm, s, avail, m, sp, ep, steps), o2;
-        if (occ > 0) {
-            int hi, inc = 1;
-            for (;;) {
-                const int L = m + inc;
-                if ((o2 = lf_fm_count(fm, s, avail, L, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = L; inc <<= 1; }
-                else { hi = L; break; }
-            }
-            while (hi - m > 1) {
-                const int mid = (m + hi) >> 1;
-                if ((o2 = lf_fm_count(fm, s, avail, mid, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = mid; }
-                else hi = mid;
-            }
+        const long long avail = (long long)(read_off[r + 1] - ro) - (long long)p;
+        int m = (int)mlen[g];
+        unsigned long long sp = sp_out[g], ep = 0, k2 = 0, l2 = 0;
+        long long occ = -1, o2;              /* -1: the first search's count is already in cnt[g] */
+        int hi, inc = 1;
+        for (;;) {
+            const int L = m + inc;
+            if ((o2 = lf_fm_count(fm, s, avail, L, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = L; inc <<= 1; }
+            else { hi = L; break; }
         }
-        mlen[g] = (uint32_t)m;
-        sp_out[g] = sp;
-        cnt[g] = (occ > 0 && occ < max_hits) ? (uint32_t)occ : 0u;
+        while (hi - m > 1) {
+            const int mid = (m + hi) >> 1;
+            if ((o2 = lf_fm_count(fm, s, avail, mid, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = mid; }
+            else hi = mid;
+        }
+        if (occ >= 0) {
+            mlen[g] = (uint32_t)m;
+            sp_out[g] = sp;
+            cnt[g] = occ < max_hits ? (uint32_t)occ : 0u;
+        }
+        (void)ep;
     }
-    lf_seed_count(ctr, steps);   /* backward-search steps: two occurrence lookups each */
+    /* every thread of the (full) blocks reaches this point */
+    lf_seed_count(ctr, steps);
 }
 
 /* containment filter (src/BWT.cpp:345, :387): cnt[i] stays only where pos + m exceeds the ends of all earlier
@@ -325,7 +360,7 @@ struct SeedState {
     LfFmDev fm = {};
     bool ready = false;
     size_t n_cache = 0;
-    LfbBuf bwt, sa, cache, pos, mlen, sp, cnt, hoff, hits, is_rev, rbefore, fwd, rev, fwd_off, rev_off, ctr;
+    LfbBuf bwt, sa, cache, pos, mlen, sp, cnt, hoff, hits, is_rev, rbefore, fwd, rev, fwd_off, rev_off, ctr, list;
     PinnedBuf h_fwd, h_rev, h_off, h_tot;
     lf_seed_stats st = {};
 #ifndef LF_EMU
@@ -336,7 +371,7 @@ struct SeedState {
 void seed_state_free_fn(void *p)
 {
     SeedState *s = (SeedState *)p;
-    LfbBuf *bufs[] = { &s->bwt, &s->sa, &s->cache, &s->pos, &s->mlen, &s->sp, &s->cnt, &s->hoff, &s->hits, &s->is_rev, &s->rbefore, &s->fwd, &s->rev, &s->fwd_off, &s->rev_off, &s->ctr };
+    LfbBuf *bufs[] = { &s->bwt, &s->sa, &s->cache, &s->pos, &s->mlen, &s->sp, &s->cnt, &s->hoff, &s->hits, &s->is_rev, &s->rbefore, &s->fwd, &s->rev, &s->fwd_off, &s->rev_off, &s->ctr, &s->list };
     for (LfbBuf *b : bufs) b->release();
     s->h_fwd.release(); s->h_rev.release(); s->h_off.release(); s->h_tot.release();
 #ifndef LF_EMU
@@ -425,14 +460,19 @@ int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_para
     if (np >> 31) { delete res; return fail(ctx, LF_ERR_BAD_ARG, "lf_gpu_seed_batch: n_reads * sampling_count >= 2^31: split the batch"); }
     lfb_stream s = d.stream;
     auto bail = [&](int code, const char *msg) { delete res; return fail(ctx, code, msg); };
-    if (S.pos.reserve(np * 4) || S.mlen.reserve(np * 4) || S.sp.reserve(np * 8) || S.cnt.reserve(np * 4) || S.hoff.reserve((np + 1) * 8) || S.ctr.reserve(16)) return bail(LF_ERR_NOMEM, "seed samples");
-    if (lfb_memset(S.ctr.p, 0, 16, s)) return bail(LF_ERR_CUDA, "seed counters");
+    if (S.pos.reserve(np * 4) || S.mlen.reserve(np * 4) || S.sp.reserve(np * 8) || S.cnt.reserve(np * 4) || S.hoff.reserve((np + 1) * 8) || S.ctr.reserve(32) || S.list.reserve(np * 4 + 16)) return bail(LF_ERR_NOMEM, "seed samples");
+    if (lfb_memset(S.ctr.p, 0, 32, s)) return bail(LF_ERR_CUDA, "seed counters");
 #ifndef LF_EMU
     cudaEventRecord(S.ev[0], s);
 #endif
     LFB_LAUNCH(k_seed_positions, (n_reads + 127) / 128, 128, 0, s, d.read_off.as<uint64_t>(), n_reads, SC, S.pos.as<uint32_t>());
-    LFB_LAUNCH(k_seed_search, (unsigned)((np + 127) / 128), 128, 0, s, S.fm, d.bases.as<uint8_t>(), d.read_off.as<uint64_t>(), n_reads, SC, (int)prm->min_anchor_len, (long long)prm->max_ref_hits,
-               S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.sp.as<unsigned long long>(), S.cnt.as<uint32_t>(), S.ctr.as<unsigned long long>());
+    LFB_LAUNCH(k_seed_probe, (unsigned)((np + 127) / 128), 128, 0, s, S.fm, d.bases.as<uint8_t>(), d.read_off.as<uint64_t>(), n_reads, SC, (int)prm->min_anchor_len, (long long)prm->max_ref_hits,
+               S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.sp.as<unsigned long long>(), S.cnt.as<uint32_t>(), S.list.as<uint32_t>(), (uint32_t *)(S.ctr.as<unsigned long long>() + 2), S.ctr.as<unsigned long long>());
+    {   /* persistent grid over the dense list (its length stays on the device) */
+        const unsigned blocks = (unsigned)std::min<size_t>((np + 127) / 128, (size_t)148 * 16);
+        LFB_LAUNCH(k_seed_extend, blocks, 128, 0, s, S.fm, d.bases.as<uint8_t>(), d.read_off.as<uint64_t>(), SC, (long long)prm->max_ref_hits,
+                   S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.sp.as<unsigned long long>(), S.cnt.as<uint32_t>(), S.list.as<uint32_t>(), (const uint32_t *)(S.ctr.as<unsigned long long>() + 2), S.ctr.as<unsigned long long>());
+    }
     LFB_LAUNCH(k_seed_filter, (n_reads + 3) / 4, 128, 0, s, n_reads, SC, S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.cnt.as<uint32_t>());
     if (lfb_scan_excl_total(d.tmp, S.cnt.as<uint32_t>(), S.hoff.as<unsigned long long>(), np, s)) return bail(LF_ERR_CUDA, "seed scan");
 #ifndef LF_EMU
