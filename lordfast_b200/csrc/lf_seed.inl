@@ -116,14 +116,6 @@ __device__ __forceinline__ void lf_seed_count(unsigned long long *ctr, uint32_t 
     if ((threadIdx.x & 31u) == 0 && v) atomicAdd(ctr, (unsigned long long)v);
 }
 
-__device__ __forceinline__ unsigned long long lf_fm_sa(const LfFmDev &fm, unsigned long long k, uint32_t &steps)
-{ /* bwt_sa, lib/bwa/bwt.c:86-98 */
-    unsigned long long sa = 0;
-    while (k & fm.sa_mask) { ++sa; k = lf_fm_inv_psi(fm, k); }
-    steps = (uint32_t)sa;
-    return sa + __ldg(fm.sa + (k >> fm.sa_shift));
-}
-
 /* bwt_count_exact_cached (src/BWT.cpp:265-298) on the bases s[0 .. len): the last k_cache of them index the k-mer table,
  * the others extend to the left one by one.  Positions at or past `avail` read as the NUL the reference finds there.
  * Returns the number of occurrences (0: none, k and l untouched as in the reference). */
@@ -223,42 +215,71 @@ __global__ void __launch_bounds__(128) k_seed_probe(LfFmDev fm, const uint8_t *_
     lf_seed_count(ctr, steps);   /* backward-search steps: two occurrence lookups each */
 }
 
+/* Lanes of a warp would otherwise wait for the one whose match is longest (5 of 32 lanes busy on a noisy-read chunk).
+ * Every lane instead runs a small state machine -- take a sample from the list, start a search (k-mer table), take ONE
+ * backward-search step, decide the next length -- so that each pass of the loop is the same step for all lanes that are in
+ * the middle of a search, and a lane that has finished its sample takes the next one at once. */
+#define LF_SEED_NONE 0xffffffffu
+__device__ __forceinline__ uint32_t lf_seed_take(uint32_t *next, bool need)
+{ /* index of the next work item for the lanes that need one (one atomic per warp) */
+    const uint32_t bal = __ballot_sync(LF_FULL, need), lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (bal == 0u) return LF_SEED_NONE;
+    if (lane == (uint32_t)(__ffs((int)bal) - 1)) base = atomicAdd(next, (uint32_t)__popc(bal));
+    base = __shfl_sync(LF_FULL, base, __ffs((int)bal) - 1);
+    return need ? base + (uint32_t)__popc(bal & ((1u << lane) - 1u)) : LF_SEED_NONE;
+}
+
 __global__ void __launch_bounds__(128) k_seed_extend(LfFmDev fm, const uint8_t *__restrict__ bases, const uint64_t *__restrict__ read_off, uint32_t S,
                                                      long long max_hits, const uint32_t *__restrict__ pos, uint32_t *__restrict__ mlen,
                                                      unsigned long long *__restrict__ sp_out, uint32_t *__restrict__ cnt, const uint32_t *__restrict__ list, const uint32_t *__restrict__ n_list,
-                                                     unsigned long long *__restrict__ ctr)
+                                                     uint32_t *__restrict__ next, unsigned long long *__restrict__ ctr)
 {
     const uint32_t n = *n_list;
-    uint32_t steps = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t g = list[i];
-        const uint32_t r = g / S;
-        const uint64_t ro = read_off[r];
-        const uint32_t p = pos[g];
-        const uint8_t *s = bases + ro + p;
-        const long long avail = (long long)(read_off[r + 1] - ro) - (long long)p;
-        int m = (int)mlen[g];
-        unsigned long long sp = sp_out[g], ep = 0, k2 = 0, l2 = 0;
-        long long occ = -1, o2;              /* -1: the first search's count is already in cnt[g] */
-        int hi, inc = 1;
-        for (;;) {
-            const int L = m + inc;
-            if ((o2 = lf_fm_count(fm, s, avail, L, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = L; inc <<= 1; }
-            else { hi = L; break; }
+    uint32_t g = LF_SEED_NONE, steps = 0;
+    const uint8_t *s = bases;
+    long long avail = 0, occ = -1;
+    int m = 0, inc = 1, hi = 0, L = 0, i = 0;
+    unsigned long long k = 0, l = 0, sp = 0;
+    bool searching = false;
+    for (;;) {
+        const uint32_t item = lf_seed_take(next, g == LF_SEED_NONE);
+        if (item != LF_SEED_NONE && item < n) {
+            g = list[item];
+            const uint32_t r = g / S;
+            const uint64_t ro = read_off[r];
+            const uint32_t p = pos[g];
+            s = bases + ro + p;
+            avail = (long long)(read_off[r + 1] - ro) - (long long)p;
+            m = (int)mlen[g]; sp = sp_out[g]; occ = -1; inc = 1; hi = 0; searching = false;   /* occ -1: the first search's count is already in cnt[g] */
         }
-        while (hi - m > 1) {
-            const int mid = (m + hi) >> 1;
-            if ((o2 = lf_fm_count(fm, s, avail, mid, k2, l2, steps)) > 0) { occ = o2; sp = k2; ep = l2; m = mid; }
-            else hi = mid;
+        if (__all_sync(LF_FULL, g == LF_SEED_NONE)) break;
+        if (g == LF_SEED_NONE) continue;
+        if (searching) {   /* one step of the current search */
+            const uint32_t c = lf_fm_nt4(__ldg(s + i));
+            bool fail = c > 3u;
+            if (!fail) { lf_fm_step(fm, k, l, c); steps++; fail = k > l; }
+            if (fail) { hi = L; searching = false; }
+            else if (--i < 0) { occ = (long long)(l - k + 1ull); sp = k; m = L; if (!hi) inc <<= 1; searching = false; }
+        } else if (hi && hi - m <= 1) {   /* the last success is final */
+            if (occ >= 0) { mlen[g] = (uint32_t)m; sp_out[g] = sp; cnt[g] = occ < max_hits ? (uint32_t)occ : 0u; }
+            g = LF_SEED_NONE;
+        } else {   /* next length: doubling until a search fails, then bisection; start the search at the k-mer table */
+            L = hi ? (m + hi) >> 1 : m + inc;
+            bool ok = (long long)L <= avail;
+            uint32_t idx = 0;
+            for (int j = L - 1; ok && j >= L - fm.k_cache; --j) {
+                const uint32_t c = lf_fm_nt4(__ldg(s + j));
+                if (c > 3u) ok = false;
+                idx = idx * 4u + c;
+            }
+            if (ok) { const lf_fm_cache_entry e = fm.cache[idx]; k = e.beg; l = e.end; ok = k <= l; }
+            i = L - fm.k_cache - 1;
+            if (!ok) hi = L;
+            else if (i < 0) { occ = (long long)(l - k + 1ull); sp = k; m = L; if (!hi) inc <<= 1; }
+            else searching = true;
         }
-        if (occ >= 0) {
-            mlen[g] = (uint32_t)m;
-            sp_out[g] = sp;
-            cnt[g] = occ < max_hits ? (uint32_t)occ : 0u;
-        }
-        (void)ep;
     }
-    /* every thread of the (full) blocks reaches this point */
     lf_seed_count(ctr, steps);
 }
 
@@ -286,36 +307,49 @@ __global__ void __launch_bounds__(128) k_seed_filter(uint32_t n_reads, uint32_t 
     }
 }
 
-/* locate (src/BWT.cpp:348-384): one thread per hit of a kept sample; hit h of the batch belongs to the sample whose
- * exclusive hit offset is the last one <= h (found read first, then sample: both searches stay in cache) */
+/* locate (src/BWT.cpp:348-384; bwt_sa, lib/bwa/bwt.c:86-98).  Hit h of the batch belongs to the sample whose exclusive hit
+ * offset is the last one <= h (found read first, then sample: both searches stay in cache).  The walk to the next sampled
+ * row takes a geometrically distributed number of inverse-psi steps (mean sa_intv, maximum of a warp ~4x that), so the
+ * lanes take hits from a queue and every pass of the loop is one step for all of them. */
 __global__ void __launch_bounds__(128) k_seed_locate(LfFmDev fm, const uint64_t *__restrict__ read_off, uint32_t n_reads, uint32_t S, const unsigned long long *__restrict__ hoff /* n_reads*S + 1 */,
                                                      const uint32_t *__restrict__ pos, const uint32_t *__restrict__ mlen, const unsigned long long *__restrict__ sp,
-                                                     unsigned long long n_hits, lf_seed *__restrict__ hits, uint32_t *__restrict__ is_rev, unsigned long long *__restrict__ ctr)
+                                                     uint32_t n_hits, lf_seed *__restrict__ hits, uint32_t *__restrict__ is_rev, uint32_t *__restrict__ next, unsigned long long *__restrict__ ctr)
 {
-    const unsigned long long h = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= n_hits) { lf_seed_count(ctr, 0u); return; }   /* the whole warp takes part in the count */
-    uint32_t lo = 0, hi = n_reads;                 /* last read r with hoff[r*S] <= h */
-    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (hoff[(size_t)mid * S] <= h) lo = mid; else hi = mid; }
-    const uint32_t r = lo;
-    const unsigned long long *ho = hoff + (size_t)r * S;
-    lo = 0; hi = S;                                /* last sample i with ho[i] <= h (empty samples share an offset with their successor: take the last) */
-    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (ho[mid] <= h) lo = mid; else hi = mid; }
-    const size_t g = (size_t)r * S + lo;
-    const uint32_t m = mlen[g], p = pos[g];
-    const uint32_t qlen = (uint32_t)(read_off[r + 1] - read_off[r]);
-    uint32_t steps = 0;
-    unsigned long long sapos = lf_fm_sa(fm, sp[g] + (h - ho[lo]), steps);
-    lf_seed sd;
-    uint32_t rev = 0;
-    if (sapos >= (unsigned long long)fm.l_pac) { /* reverse strand */
-        sapos = ((unsigned long long)fm.l_pac << 1) - sapos - m;
-        sd.qPos = (qlen - p - m) & 0xfffffu;
-        rev = 1;
-    } else sd.qPos = p & 0xfffffu;
-    sd.tPos = (uint32_t)sapos;
-    sd.len = m & 0xfffu;                          /* Seed_t: qPos is a 20-bit and len a 12-bit field (src/LordFAST.h:30-35) */
-    hits[h] = sd;
-    is_rev[h] = rev;
+    uint32_t h = LF_SEED_NONE, g = 0, steps = 0;
+    unsigned long long k = 0, sa = 0;
+    for (;;) {
+        const uint32_t item = lf_seed_take(next, h == LF_SEED_NONE);
+        if (item != LF_SEED_NONE && item < n_hits) {
+            h = item;
+            uint32_t lo = 0, hi = n_reads;                 /* last read r with hoff[r*S] <= h */
+            while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (hoff[(size_t)mid * S] <= h) lo = mid; else hi = mid; }
+            const unsigned long long *ho = hoff + (size_t)lo * S;
+            const uint32_t r = lo;
+            lo = 0; hi = S;                                /* last sample i with ho[i] <= h (empty samples share an offset with their successor: take the last) */
+            while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (ho[mid] <= h) lo = mid; else hi = mid; }
+            g = r * S + lo;
+            k = sp[g] + (h - ho[lo]);
+            sa = 0;
+        }
+        if (__all_sync(LF_FULL, h == LF_SEED_NONE)) break;
+        if (h == LF_SEED_NONE) continue;
+        if (k & fm.sa_mask) { ++sa; k = lf_fm_inv_psi(fm, k); steps++; continue; }
+        unsigned long long sapos = sa + __ldg(fm.sa + (k >> fm.sa_shift));
+        const uint32_t r = g / S, m = mlen[g], p = pos[g];
+        const uint32_t qlen = (uint32_t)(read_off[r + 1] - read_off[r]);
+        lf_seed sd;
+        uint32_t rev = 0;
+        if (sapos >= (unsigned long long)fm.l_pac) { /* reverse strand */
+            sapos = ((unsigned long long)fm.l_pac << 1) - sapos - m;
+            sd.qPos = (qlen - p - m) & 0xfffffu;
+            rev = 1;
+        } else sd.qPos = p & 0xfffffu;
+        sd.tPos = (uint32_t)sapos;
+        sd.len = m & 0xfffu;                          /* Seed_t: qPos is a 20-bit and len a 12-bit field (src/LordFAST.h:30-35) */
+        hits[h] = sd;
+        is_rev[h] = rev;
+        h = LF_SEED_NONE;
+    }
     lf_seed_count(ctr, steps);   /* inverse-psi steps: one base + one occurrence lookup each */
 }
 
@@ -471,7 +505,7 @@ int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_para
     {   /* persistent grid over the dense list (its length stays on the device) */
         const unsigned blocks = (unsigned)std::min<size_t>((np + 127) / 128, (size_t)148 * 16);
         LFB_LAUNCH(k_seed_extend, blocks, 128, 0, s, S.fm, d.bases.as<uint8_t>(), d.read_off.as<uint64_t>(), SC, (long long)prm->max_ref_hits,
-                   S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.sp.as<unsigned long long>(), S.cnt.as<uint32_t>(), S.list.as<uint32_t>(), (const uint32_t *)(S.ctr.as<unsigned long long>() + 2), S.ctr.as<unsigned long long>());
+                   S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.sp.as<unsigned long long>(), S.cnt.as<uint32_t>(), S.list.as<uint32_t>(), (const uint32_t *)(S.ctr.as<unsigned long long>() + 2), (uint32_t *)(S.ctr.as<unsigned long long>() + 3), S.ctr.as<unsigned long long>());
     }
     LFB_LAUNCH(k_seed_filter, (n_reads + 3) / 4, 128, 0, s, n_reads, SC, S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(), S.cnt.as<uint32_t>());
     if (lfb_scan_excl_total(d.tmp, S.cnt.as<uint32_t>(), S.hoff.as<unsigned long long>(), np, s)) return bail(LF_ERR_CUDA, "seed scan");
@@ -489,8 +523,8 @@ int lf_gpu_seed_batch(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_seed_para
     cudaEventRecord(S.ev[2], s);
 #endif
     if (H) {
-        LFB_LAUNCH(k_seed_locate, (unsigned)((H + 127) / 128), 128, 0, s, S.fm, d.read_off.as<uint64_t>(), n_reads, SC, S.hoff.as<unsigned long long>(), S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(),
-                   S.sp.as<unsigned long long>(), H, S.hits.as<lf_seed>(), S.is_rev.as<uint32_t>(), S.ctr.as<unsigned long long>() + 1);
+        LFB_LAUNCH(k_seed_locate, (unsigned)std::min<size_t>((size_t)((H + 127) / 128), (size_t)148 * 16), 128, 0, s, S.fm, d.read_off.as<uint64_t>(), n_reads, SC, S.hoff.as<unsigned long long>(), S.pos.as<uint32_t>(), S.mlen.as<uint32_t>(),
+                   S.sp.as<unsigned long long>(), (uint32_t)H, S.hits.as<lf_seed>(), S.is_rev.as<uint32_t>(), (uint32_t *)(S.ctr.as<unsigned long long>() + 3) + 1, S.ctr.as<unsigned long long>() + 1);
         if (lfb_scan_excl_total(d.tmp, S.is_rev.as<uint32_t>(), S.rbefore.as<unsigned long long>(), (size_t)H, s)) return bail(LF_ERR_CUDA, "seed strand scan");
         LFB_LAUNCH(k_seed_scatter, (unsigned)((H + 255) / 256), 256, 0, s, S.hits.as<lf_seed>(), S.is_rev.as<uint32_t>(), S.rbefore.as<unsigned long long>(), H, S.fwd.as<lf_seed>(), S.rev.as<lf_seed>());
     } else if (lfb_memset(S.rbefore.p, 0, 8, s)) return bail(LF_ERR_CUDA, "seed memset");
