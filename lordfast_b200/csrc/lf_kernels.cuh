@@ -289,35 +289,83 @@ __global__ void __launch_bounds__(256) k_copy16(uint4 *__restrict__ dst, const u
 /* ------------------------------------------------------------------------------------------ */
 /* k_pack_reads                                                                               */
 /* ------------------------------------------------------------------------------------------ */
-/* One block per read, a warp per 128 bases and iteration: lane l takes bases l, 32 + l, 64 + l, 96 + l of the piece, so that
- * a ballot over the lanes IS the plane word; the 2-bit code is ((c >> 1) ^ (c >> 2)) & 3 (A 0, C 1, G 2, T 3) and a byte is
- * valid if it equals "ACGT"[code] (one PRMT).  Four byte loads are in flight per lane; lanes 0-2 store the three planes of
- * a word.  (Round 1: one base per lane and iteration with 64-bit indices, 2.0 warp instructions per base -- 0.53 ms for a
- * config-2 chunk, 8 % of the HBM bound; now 0.6 per base.) */
+/* One block per read, 2048 bases per pass: the pass's bytes come in as aligned 16-byte loads (coalesced, whatever the
+ * read's own alignment) through shared memory; every thread then turns its 16 bases into 16 bits of each plane with
+ * word-wide arithmetic -- the 2-bit code is ((c >> 1) ^ (c >> 2)) & 3 (A 0, C 1, G 2, T 3) for four bytes at a time, a
+ * byte is valid if it equals "ACGT"[code] (one PRMT for four bytes), and four flag bits at byte positions 0, 8, 16, 24
+ * are gathered into a nibble by one multiplication -- and pairs of threads store whole plane words.
+ * History: one base per lane and ballot, 64-bit indices: 2.0 warp instructions per base (0.53 ms for a config-2 chunk,
+ * 8 % of the HBM bound); four bases per lane in flight: 0.6 per base (0.29 ms); this version: ~0.2 per base. */
+__device__ __forceinline__ uint32_t lf_gather4(uint32_t y)
+{ /* bits 0, 8, 16, 24 of y -> bits 0..3 */
+    return (y * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ void lf_pack4(uint32_t x, uint32_t &lo, uint32_t &hi, uint32_t &nn)
+{ /* four bases (bytes of x, first base in the low byte) -> four bits of each plane */
+    const uint32_t t = (x >> 1) ^ (x >> 2);
+    lo = lf_gather4(t & 0x01010101u);
+    hi = ((t & 0x02020202u) * 0x00810204u) >> 24;                          /* the same gather for bits 1, 9, 17, 25 */
+    const uint32_t u = t & 0x03030303u;                                   /* codes, one per byte */
+    const uint32_t v = u | (u >> 4);                                      /* bytes 0 and 2 hold the selector nibble pairs */
+    const uint32_t sel = (v & 0xffu) | ((v >> 8) & 0xff00u);              /* PRMT selector: nibble k = code of byte k */
+    const uint32_t diff = x ^ __byte_perm(0x54474341u, 0u, sel);          /* zero bytes where the base is upper-case ACGT */
+    const uint32_t nz = (diff | ((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7; /* bit 0 of each byte: the byte of diff is not zero */
+    nn = lf_gather4(nz & 0x01010101u);
+}
 __global__ void __launch_bounds__(128) k_pack_reads(LfDev d)
 {
+    __shared__ uint4 s_tile[130];
     const uint32_t r = blockIdx.x;
     if (r >= d.n_reads) return;
     const uint64_t b0 = d.read_off[r];
     const uint32_t L = (uint32_t)(d.read_off[r + 1] - b0);
     const uint64_t po = lf_plane_word_off(b0, r);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint8_t *__restrict__ src = d.bases + b0;
-    uint32_t *__restrict__ dst = lane == 0 ? d.plo + po : lane == 1 ? d.phi + po : d.pnn + po;
+    const uint32_t tid = threadIdx.x, mis = (uint32_t)(b0 & 15ull);
+    const uint4 *__restrict__ src = (const uint4 *)(d.bases + (b0 - mis));   /* the allocation is 256-byte aligned and 64 bytes longer than the reads */
+    const uint32_t *s_words = (const uint32_t *)s_tile;
     const uint32_t nw = (L + 31u) >> 5;
-    for (uint32_t w0 = warp * 4u; w0 < nw; w0 += nwarps * 4u) {
-        uint32_t c[4];
+    for (uint32_t t0 = 0; t0 < L; t0 += 2048u) {
+        const uint32_t c0 = t0 >> 4, nchunk = ((L - t0 < 2048u ? L - t0 : 2048u) + mis + 15u) >> 4;   /* aligned chunks that hold bases of this pass */
+        if (tid < nchunk) s_tile[tid] = __ldg(src + c0 + tid);
+        if (tid == 0 && nchunk > 128u) s_tile[128] = __ldg(src + c0 + 128u);
+        __syncthreads();
+        const uint32_t i0 = t0 + 16u * tid;                     /* first base of this thread */
+        uint32_t lo = 0, hi = 0, nn = 0xffffu;
+        if (i0 < L) {
+            const uint32_t wi = (mis >> 2) + 4u * tid, sh = 8u * (mis & 3u);
+            uint32_t a[5];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const uint32_t i = (w0 + (uint32_t)k) * 32u + lane; c[k] = i < L ? src[i] : 0u; }
+            for (int j = 0; j < 5; j++) a[j] = s_words[wi + (uint32_t)j];
+            const uint32_t left = L - i0;                       /* bases from i0 to the end of the read */
+            lo = 0; hi = 0; nn = 0;
+            if (left >= 16u) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t t = (c[k] >> 1) ^ (c[k] >> 2);
-            const uint32_t lo = __ballot_sync(LF_FULL, t & 1u);
-            const uint32_t hi = __ballot_sync(LF_FULL, t & 2u);
-            const uint32_t nn = __ballot_sync(LF_FULL, __byte_perm(0x54474341u, 0u, 0x4440u | (t & 3u)) != c[k]);   /* not upper-case ACGT (or past the end) */
-            const uint32_t v = lane == 0 ? lo : lane == 1 ? hi : nn;
-            if (lane < 3u && w0 + (uint32_t)k < nw) dst[w0 + (uint32_t)k] = v;
+                for (int j = 0; j < 4; j++) {
+                    uint32_t l4, h4, n4;
+                    lf_pack4(__funnelshift_r(a[j], a[j + 1], sh), l4, h4, n4);
+                    lo |= l4 << (4 * j); hi |= h4 << (4 * j); nn |= n4 << (4 * j);
+                }
+            } else {   /* the last bases of the read: bytes past its end count as byte 0, i.e. code 0 and not a base */
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t x = __funnelshift_r(a[j], a[j + 1], sh);
+                    const uint32_t have = left > 4u * (uint32_t)j ? left - 4u * (uint32_t)j : 0u;
+                    if (have < 4u) x &= (1u << (8u * have)) - 1u;
+                    uint32_t l4, h4, n4;
+                    lf_pack4(x, l4, h4, n4);
+                    lo |= l4 << (4 * j); hi |= h4 << (4 * j); nn |= n4 << (4 * j);
+                }
+            }
         }
+        /* even threads own a plane word: their 16 bits and the next thread's */
+        const uint32_t lo2 = __shfl_down_sync(LF_FULL, lo, 1), hi2 = __shfl_down_sync(LF_FULL, hi, 1), nn2 = __shfl_down_sync(LF_FULL, nn, 1);
+        const uint32_t w = (t0 >> 5) + (tid >> 1);
+        if (!(tid & 1u) && w < nw) {
+            d.plo[po + w] = lo | (lo2 << 16);
+            d.phi[po + w] = hi | (hi2 << 16);
+            d.pnn[po + w] = nn | (nn2 << 16);
+        }
+        __syncthreads();
     }
 }
 
