@@ -141,17 +141,35 @@ int ref_fm_seed(const char *q, uint32_t qlen, uint32_t hash_count, int min_ancho
 }
 /* a batch on `threads` host threads (the program's own parallelism is one read per thread, src/LordFAST.cpp:295-316);
  * returns seconds; counts only (the lists are dropped) */
-struct FmBatchArg { const char *const *q; const uint32_t *qlen; int lo, hi; uint32_t hash_count, cap; uint64_t hits; };
+/* order-sensitive 64-bit digest of a seed list: sum over i of (i + 1) * mix(seed i); tests compute the same from the GPU's lists */
+static inline uint64_t fm_seed_mix(uint32_t tPos, uint32_t qPos, uint32_t len)
+{
+    return (uint64_t)tPos * 0x9E3779B97F4A7C15ull + (uint64_t)qPos * 0xC2B2AE3D27D4EB4Full + (uint64_t)len * 0x165667B19E3779F9ull + 0x27D4EB2F165667C5ull;
+}
+static uint64_t fm_list_digest(const Seed_t *l, uint32_t n)
+{
+    uint64_t h = 0;
+    for (uint32_t i = 0; i < n; i++) h += (uint64_t)(i + 1) * fm_seed_mix(l[i].tPos, l[i].qPos, l[i].len);
+    return h;
+}
+struct FmBatchArg { const char *const *q; const uint32_t *qlen; int lo, hi; uint32_t hash_count, cap; uint64_t hits; uint64_t *dig; uint32_t *cnt; };
 static void *fm_batch_worker(void *p)
 {
     FmBatchArg *a = (FmBatchArg *)p;
     SeedList f, r;
     std::vector<Seed_t> fl(a->cap), rl(a->cap);
     f.list = fl.data(); r.list = rl.data();
-    for (int i = a->lo; i < a->hi; i++) { getLocs_extend_whole_step((char *)a->q[i], a->qlen[i], a->hash_count, &f, &r); a->hits += f.num + r.num; }
+    for (int i = a->lo; i < a->hi; i++) {
+        getLocs_extend_whole_step((char *)a->q[i], a->qlen[i], a->hash_count, &f, &r);
+        a->hits += f.num + r.num;
+        if (a->dig) { a->dig[2 * i] = fm_list_digest(f.list, f.num); a->dig[2 * i + 1] = fm_list_digest(r.list, r.num); a->cnt[2 * i] = f.num; a->cnt[2 * i + 1] = r.num; }
+    }
     return NULL;
 }
-double ref_fm_seed_batch(int n, const char *const *q, const uint32_t *qlen, uint32_t hash_count, int min_anchor_len, int max_ref_hits, int threads, uint64_t *hits)
+/* a batch on `threads` host threads (the program's own parallelism is one read per thread, src/LordFAST.cpp:295-316);
+ * returns seconds.  digests / counts (2 per read: forward, reverse) may be NULL: then only the total is kept. */
+double ref_fm_seed_batch_digest(int n, const char *const *q, const uint32_t *qlen, uint32_t hash_count, int min_anchor_len, int max_ref_hits, int threads, uint64_t *hits,
+                                uint64_t *digests, uint32_t *counts)
 {
     if (!g_fm) return -1;
     _fmd_index = g_fm;
@@ -162,7 +180,7 @@ double ref_fm_seed_batch(int n, const char *const *q, const uint32_t *qlen, uint
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++) {
         args[t].q = q; args[t].qlen = qlen; args[t].lo = (int)((long long)n * t / threads); args[t].hi = (int)((long long)n * (t + 1) / threads);
-        args[t].hash_count = hash_count; args[t].cap = hash_count * (uint32_t)max_ref_hits + 1; args[t].hits = 0;
+        args[t].hash_count = hash_count; args[t].cap = hash_count * (uint32_t)max_ref_hits + 1; args[t].hits = 0; args[t].dig = digests; args[t].cnt = counts;
         pthread_create(&th[t], NULL, fm_batch_worker, &args[t]);
     }
     uint64_t tot = 0;
@@ -170,6 +188,10 @@ double ref_fm_seed_batch(int n, const char *const *q, const uint32_t *qlen, uint
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (hits) *hits = tot;
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+double ref_fm_seed_batch(int n, const char *const *q, const uint32_t *qlen, uint32_t hash_count, int min_anchor_len, int max_ref_hits, int threads, uint64_t *hits)
+{
+    return ref_fm_seed_batch_digest(n, q, qlen, hash_count, min_anchor_len, max_ref_hits, threads, hits, NULL, NULL);
 }
 
 static void fill_chain(Chain_t &c, std::vector<Seed_t> &store, const lfo_seed *seeds, int n)

@@ -81,6 +81,9 @@ def ref():
             lib.ref_fm_seed.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
             lib.ref_fm_seed_batch.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
             lib.ref_fm_seed_batch.restype = C.c_double
+            if hasattr(lib, "ref_fm_seed_batch_digest"):
+                lib.ref_fm_seed_batch_digest.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+                lib.ref_fm_seed_batch_digest.restype = C.c_double
         _ref = lib
     return _ref
 
@@ -234,3 +237,32 @@ def ref_fm_seed(read: bytes, sampling_count=1000, min_anchor_len=14, max_ref_hit
     if lib.ref_fm_seed(read + b"\0", len(read), sampling_count, min_anchor_len, max_ref_hits, f.ctypes.data, C.byref(nf), r.ctypes.data, C.byref(nr)):
         raise RuntimeError("ref_fm_seed: no index loaded")
     return f[:nf.value].copy(), r[:nr.value].copy()
+
+
+def seed_list_digests(seeds: np.ndarray, off: np.ndarray) -> np.ndarray:
+    """per read: sum over i of (i + 1) * mix(seed i) mod 2^64 -- the digest ref_fm_seed_batch_digest computes (oracle/ref_shim.cpp)"""
+    off = off.astype(np.int64)
+    n = len(off) - 1
+    if len(seeds) == 0:
+        return np.zeros(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        mix = (seeds["tPos"].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + seeds["qPos"].astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+               + seeds["len"].astype(np.uint64) * np.uint64(0x165667B19E3779F9) + np.uint64(0x27D4EB2F165667C5))
+        rank = (np.arange(len(seeds), dtype=np.int64) - np.repeat(off[:-1], np.diff(off)) + 1).astype(np.uint64)
+        w = mix * rank
+        cs = np.concatenate([[np.uint64(0)], np.cumsum(w, dtype=np.uint64)])
+        return cs[off[1:]] - cs[off[:-1]]
+
+
+def ref_fm_seed_digests(reads: np.ndarray, off: np.ndarray, sampling_count=1000, min_anchor_len=14, max_ref_hits=1000, threads=None):
+    """(digests[n, 2], counts[n, 2], seconds) of the reference's seed lists (forward, reverse) for every read, on all host threads"""
+    lib = ref()
+    n = len(off) - 1
+    rb = np.asarray(reads, dtype=np.uint8).tobytes()
+    qs = [rb[int(off[i]):int(off[i + 1])] + b"\0" for i in range(n)]
+    arr = (C.c_char_p * n)(*qs)
+    ql = (C.c_uint32 * n)(*[len(q) - 1 for q in qs])
+    dig = np.zeros((n, 2), dtype=np.uint64); cnt = np.zeros((n, 2), dtype=np.uint32)
+    hits = C.c_uint64()
+    sec = lib.ref_fm_seed_batch_digest(n, arr, ql, sampling_count, min_anchor_len, max_ref_hits, threads or (os.cpu_count() or 1), C.byref(hits), dig.ctypes.data, cnt.ctypes.data)
+    return dig, cnt, sec

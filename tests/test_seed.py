@@ -258,3 +258,28 @@ def test_gpu_seeding_program_parameters_against_reference():
                 f, r = _oracle.ref_fm_seed(rb[int(off[i]):int(off[i + 1])])
                 assert np.array_equal(f, fwd[int(fo[i]):int(fo[i + 1])]), i
                 assert np.array_equal(r, rev[int(ro[i]):int(ro[i + 1])]), i
+
+
+@pytest.mark.gpu
+def test_gpu_seeding_config2_chunk_every_read_against_reference():
+    """The whole config-2 chunk (20 000 reads of ~10 kbp, 20 M samples, 3.2 M seeds): per read and strand the number of
+    seeds and an order-sensitive digest of the list against the reference's own getLocs_extend_whole_step."""
+    from lordfast_b200 import fixtures
+    if not fixtures.available("config2"):
+        pytest.skip("fixtures/config2.npz not present")
+    if not (_oracle.have_ref() and hasattr(_oracle.ref(), "ref_fm_seed_batch_digest")):
+        pytest.skip("reference shim with the seeding exports not on this box")
+    fx = fixtures.load("config2")
+    ref, reads, off = fx.ref, np.ascontiguousarray(fx.reads, dtype=np.uint8), fx.read_off.astype(np.uint64)
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "r.fa")
+        _oracle.write_fasta(fa, ref)
+        theirs = _oracle.ref_fm_load(fa, 12)
+    g = api.LfGpu(fx.pac, len(ref))
+    theirs.cache = None                      # the library derives the k-mer table; the arrays are bwa's own
+    g.seed_init(theirs)
+    fwd, fo, rev, ro = g.seed_batch(reads, off)
+    dig, cnt, _ = _oracle.ref_fm_seed_digests(reads, off)
+    assert np.array_equal(np.diff(fo.astype(np.int64)), cnt[:, 0]) and np.array_equal(np.diff(ro.astype(np.int64)), cnt[:, 1])
+    assert np.array_equal(_oracle.seed_list_digests(fwd, fo), dig[:, 0]) and np.array_equal(_oracle.seed_list_digests(rev, ro), dig[:, 1])
+    assert len(fwd) + len(rev) > 2_000_000
