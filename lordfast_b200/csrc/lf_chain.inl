@@ -1104,10 +1104,13 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
         std::swap(d.res, d.res_keep); std::swap(d.ops, d.ops_keep);
         swap_guard.d = &d;
     }
+    double t3a = tq3, t3b = tq3;
     if (n3) {
         if (gpu_emit) LF_CH(upload_align_tasks_k(ctx, t3.data(), n3));
         else LF_CH(lf_gpu_upload_align_tasks(ctx, t3.data(), n3));
+        t3a = now_ms();
         LF_CH(lf_gpu_run_align(ctx));
+        t3b = now_ms();
         for (DevState &dd : ctx->devs) if (dd.cls_count[LF_CLS_BAD]) { delete R; return fail(ctx, LF_ERR_BAD_ARG, "a follow-up alignment task is outside its read or the reference"); }
         trace_mark(ctx, "round-3 kernels done", ctx->devs[0].stream);
         if (!gpu_emit) LF_CH(lf_gpu_download_align(ctx, r3, ops3, cap3));
@@ -1116,7 +1119,7 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
     LF_CH(lf_gpu_sync(ctx));
     R->stats.round3_tasks = n3;
     const double tm3 = now_ms();
-    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain %p +%.2f] ", (void *)ctx, now_ms() - g_trace_t0), fprintf(stderr, "r23: trigger scan %.2f, early-emit start %.2f, round 2 %.2f, round-3 tasks %.2f, round 3 %.2f\n", tq0 - tm2, tq1 - tq0, tq2 - tq1, tq3 - tq2, tm3 - tq3);
+    if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain %p +%.2f] ", (void *)ctx, now_ms() - g_trace_t0), fprintf(stderr, "r23: trigger scan %.2f, early-emit start %.2f, round 2 %.2f, round-3 tasks %.2f, round 3 %.2f (upload %.2f, prep + sort + class counts + launches %.2f, kernels + results %.2f)\n", tq0 - tm2, tq1 - tq0, tq2 - tq1, tq3 - tq2, tm3 - tq3, t3a - tq3, t3b - t3a, tm3 - t3b);
 #undef LF_CH
 
     if (gpu_emit) {

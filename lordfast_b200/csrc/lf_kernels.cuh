@@ -287,6 +287,25 @@ __global__ void __launch_bounds__(256) k_copy16(uint4 *__restrict__ dst, const u
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* k_readback: a few device words -> pinned host memory, written by a kernel                   */
+/* ------------------------------------------------------------------------------------------ */
+/* The class counts and totals the host waits for once per batch are ~200 bytes.  As a D2H copy they queue in the copy
+ * engine behind whatever else is leaving the device -- the 110 MB of CIGAR / MD text of the early emit while round 3
+ * starts cost it 1.5 ms -- so a kernel stores them over PCIe itself (dst is pinned, mapped host memory). */
+__global__ void k_readback(const uint32_t *__restrict__ words, uint32_t n_words, const unsigned long long *__restrict__ a, const unsigned long long *__restrict__ b,
+                           uint32_t *dst, uint32_t off_a /* in 8-byte units */, uint32_t off_b)
+{
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = words[i];
+    if (threadIdx.x == 0) {
+        if (a) ((unsigned long long *)dst)[off_a] = *a;
+        if (b) ((unsigned long long *)dst)[off_b] = *b;
+    }
+#if defined(__CUDA_ARCH__)
+    __threadfence_system();
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* k_pack_reads                                                                               */
 /* ------------------------------------------------------------------------------------------ */
 /* One block per read, 2048 bases per pass: the pass's bytes come in as aligned 16-byte loads (coalesced, whatever the

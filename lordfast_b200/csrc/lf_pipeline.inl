@@ -12,6 +12,7 @@
  * A batch is split over the context's devices by contiguous task ranges; the reference and the
  * reads are replicated, no collective is involved.
  */
+#include <stddef.h>
 #include <stdio.h>
 #include <mutex>
 #include <string>
@@ -359,9 +360,9 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     LF_TRY(lfb_scan_incl(d.tmp, d.slot_words.as<uint32_t>(), d.slot_end.as<unsigned long long>(), n, s));
     LF_TRY(lfb_scan_excl_total(d.tmp, d.scr_bytes.as<uint32_t>(), d.scr_off.as<unsigned long long>(), n, s));
     HostTotals *ht = (HostTotals *)d.pinned;
-    LF_TRY(lfb_d2h(&ht->cnt, d.counters.p, sizeof(LfCounters), s));
-    LF_TRY(lfb_d2h(&ht->slot_total, d.slot_end.as<unsigned long long>() + (n - 1), 8, s));
-    LF_TRY(lfb_d2h(&ht->scr_total, d.scr_off.as<unsigned long long>() + n, 8, s));
+    static_assert(sizeof(LfCounters) % 8 == 0 && offsetof(HostTotals, cnt) == 0, "k_readback writes HostTotals in place");
+    LFB_LAUNCH(k_readback, 1, 64, 0, s, (const uint32_t *)d.counters.p, (uint32_t)(sizeof(LfCounters) / 4), d.slot_end.as<unsigned long long>() + (n - 1), d.scr_off.as<unsigned long long>() + n,
+               (uint32_t *)ht, (uint32_t)(offsetof(HostTotals, slot_total) / 8), (uint32_t)(offsetof(HostTotals, scr_total) / 8));
     LF_TRY(lfb_sync(s)); /* the one host round trip of a batch: class sizes decide the launches */
     if (ht->slot_total >> 32) return fail(ctx, LF_ERR_BAD_ARG, "batch needs 2^32 or more op words: split it");   /* the kernels index op words with 32 bits */
     d.ops_words = ht->slot_total;
@@ -385,7 +386,8 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         v = make_dev(ctx, d);
         LFB_LAUNCH(k_group_scratch, (ngroups + 255) / 256, 256, 0, s, v, d.idx2.as<uint32_t>(), gc, d.gbytes.as<uint32_t>());
         LF_TRY(lfb_scan_excl_total(d.tmp, d.gbytes.as<uint32_t>(), d.goff.as<unsigned long long>(), ngroups, s));
-        LF_TRY(lfb_d2h(&ht->scr_total, d.goff.as<unsigned long long>() + ngroups, 8, s));
+        LFB_LAUNCH(k_readback, 1, 64, 0, s, (const uint32_t *)nullptr, 0u, (const unsigned long long *)nullptr, d.goff.as<unsigned long long>() + ngroups,
+                   (uint32_t *)ht, 0u, (uint32_t)(offsetof(HostTotals, scr_total) / 8));
         LF_TRY(lfb_sync(s));
         LF_TRY(d.planes.reserve((size_t)ht->scr_total + 256));
     }
@@ -527,17 +529,20 @@ static struct PrewarmGuard { ~PrewarmGuard() { std::lock_guard<std::mutex> g(g_p
 static int init_dev_streams(DevState &d)
 {
 #ifndef LF_EMU
-    if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    /* Three priority levels.  Highest: the extension stream (its few long-latency warps must not queue behind the round-1
+     * grids).  Middle: the main stream and the class streams -- above the default level, at which the chain operator's
+     * early emit runs: the blocks of a kernel launched later are only dispatched once every block of the earlier kernels of
+     * the same level has been, so round 3's first tiny kernel used to wait ~2 ms for the early emit's 18 000 blocks. */
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const int mid = hi < lo ? lo - 1 : lo;   /* numerically lower = more urgent */
+    if (cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, mid) != cudaSuccess) return -1;
     for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
-    {   /* highest priority: its few long-latency warps must not queue behind the round-1 grids */
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&d.ext_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return -1;
-    }
+    if (cudaStreamCreateWithPriority(&d.ext_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return -1;
     cudaEventCreateWithFlags(&d.ext_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d.up_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&d.off_ev, cudaEventDisableTiming);
-    for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithFlags(&d.sub[k], cudaStreamNonBlocking) != cudaSuccess) return -1; cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
+    for (int k = 0; k < LF_NSUB; k++) { if (cudaStreamCreateWithPriority(&d.sub[k], cudaStreamNonBlocking, mid) != cudaSuccess) return -1; cudaEventCreateWithFlags(&d.sub_ev[k], cudaEventDisableTiming); }
     for (int c = 0; c < LF_NCLS; c++) { cudaEventCreate(&d.cls_ev[c][0]); cudaEventCreate(&d.cls_ev[c][1]); }
 #else
     (void)d;

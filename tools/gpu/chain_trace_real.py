@@ -19,8 +19,9 @@ for it in range(5):
     t0 = time.perf_counter()
     recs, text, st = g.align_chains(hb, ro, co, cl, fx.seeds, fx.chains, want_text=False)
     print("call %d: %.2f ms, %d records, round3 tasks %d" % (it, (time.perf_counter() - t0) * 1e3, len(recs), st.round3_tasks), flush=True)
-tl = g.class_timeline()
+st, en = g.class_timeline()
 cc = g.class_counts()
 print("last batch (round 3):")
-for k, v in sorted(tl.items(), key=lambda kv: kv[1][0]):
-    print("  %-14s %6.3f -> %6.3f  tasks %d" % (k, v[0], v[1], cc.get(k, 0)))
+for c in sorted(range(len(en)), key=lambda c: st[c]):
+    if en[c] >= 0 and c != 17:
+        print("  %-14s %6.3f -> %6.3f  tasks %d" % (api.CLASS_NAMES[c], st[c], en[c], cc.get(api.CLASS_NAMES[c], 0)))
