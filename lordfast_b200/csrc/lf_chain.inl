@@ -1168,7 +1168,9 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
             memcpy(dirty_pinned, dirty_list.data(), n_dirty * 4);
             LF_G(emit_size(d, es1, E1, dirty_pinned, n_dirty));
         } else { es1.n = es1.nrec = es1.ncig = es1.nmd = 0; }
+        const double te1 = now_ms();
         early.join();
+        const double te2 = now_ms();
         if (early.rc != 0) { delete R; return fail(ctx, early.rc, "early emit"); }
         const size_t bytes0 = es0.n ? es0.ncig + es0.nmd : 0, bytes1 = es1.ncig + es1.nmd;
         R->pinned = true;
@@ -1189,6 +1191,8 @@ static int align_chains_one(lf_gpu_ctx *ctx, const lf_reads *reads, const lf_con
             R->text = nt; R->text_cap = cap; R->text_borrowed = false;
         }
         if (n_dirty) { LF_G(emit_write(es1, E1, R->text + bytes0, (R->text_borrowed ? io->off : 0) + bytes0)); trace_mark(ctx, "late emit written", st); LF_G(lfb_sync(st)); }
+        const double te3 = now_ms();
+        if (getenv("LF_CHAIN_TRACE")) fprintf(stderr, "[lf_chain %p +%.2f] late emit: inputs + size pass %.2f, wait for the early emit %.2f, write pass + download %.2f (%zu bytes)\n", (void *)ctx, now_ms() - g_trace_t0, te1 - tm3, te2 - te1, te3 - te2, bytes1);
         LF_G(lfb_last_error());
 #undef LF_G
         /* records of the two lists, merged back into chain order */
