@@ -535,7 +535,7 @@ static int init_dev_streams(DevState &d)
      * the same level has been, so round 3's first tiny kernel used to wait ~2 ms for the early emit's 18 000 blocks. */
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    const int mid = hi < lo ? lo - 1 : lo;   /* numerically lower = more urgent */
+    const int mid = (hi < lo && !(getenv("LF_STREAM_PRIO") && atoi(getenv("LF_STREAM_PRIO")) == 0)) ? lo - 1 : lo;   /* numerically lower = more urgent; LF_STREAM_PRIO=0: one level for everything but the extensions */
     if (cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, mid) != cudaSuccess) return -1;
     for (int k = 0; k < 4; k++) cudaEventCreate(&d.ev[k]);
     if (cudaStreamCreateWithPriority(&d.ext_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return -1;
