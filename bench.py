@@ -378,7 +378,7 @@ def main():
     barrier()
     single_ms = (time.perf_counter() - t2) / nsingle * 1e3
     cores_here = (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    P = a.in_flight if a.in_flight > 0 else (4 if cores_here >= 16 else 2 if cores_here >= 8 else 1)
+    P = a.in_flight if a.in_flight > 0 else (4 if cores_here >= 16 else 2 if cores_here >= 4 else 1)
     flight_ms = single_ms
     tried = []
     for Pk in ([P] if (a.in_flight > 0 or P < 4) else [4, 2]):   # auto: four calls in flight, then two; the better one counts
