@@ -1407,6 +1407,7 @@ static lf_gpu_ctx *lane_ctx(lf_gpu_ctx *ctx, size_t j)
     while (ctx->lanes.size() <= j) {
         DevState &pd = ctx->devs[ctx->lanes.size() % ctx->devs.size()];
         lf_gpu_ctx *c = new lf_gpu_ctx();
+        c->rt = ctx->rt;
         c->l_pac = ctx->l_pac;
         c->devs.resize(1);
         DevState &d = c->devs[0];

@@ -59,7 +59,15 @@ struct DevState {
     bool reads_preloaded = false;   /* lane: the parent has enqueued the H2D copy of the reads; upload_reads only waits and packs */
 };
 
+/* Kernel routing and scheduling switches: environment overrides read ONCE, when the context is created (a batch never
+ * calls getenv); the defaults are the measured choices documented next to each reader below. */
+struct LfRouting {
+    uint32_t bandreg = 0, groupk = 0, band_mask = 0, group_wide = 0;
+    bool bandreg_small = true, large_one_warp = false, serial = false, order_band_first = false;
+    int nstreams = 0;
+};
 struct lf_gpu_ctx {
+    LfRouting rt;
     std::vector<DevState> devs;
     std::vector<lf_gpu_ctx *> lanes;   /* lf_chain.inl: single-device child contexts that pipeline the sub-batches of one call */
     void *chain_scratch = nullptr; /* lf_chain.inl: pinned staging kept between calls */
@@ -131,8 +139,8 @@ LfDev make_dev(lf_gpu_ctx *ctx, DevState &d)
     v.scr_off = d.scr_off.as<uint64_t>();
     v.scratch = d.scratch.as<uint8_t>();
     v.planes = d.planes.as<uint8_t>();
-    v.bandreg = bandreg_on();
-    v.groupk = groupk_on();
+    v.bandreg = ctx->rt.bandreg;
+    v.groupk = ctx->rt.groupk;
     return v;
 }
 
@@ -264,10 +272,25 @@ uint32_t band_mask()
     return e ? (uint32_t)strtoul(e, nullptr, 0) : (uint32_t)LF_BAND_MASK_DEFAULT;
 }
 
-void launch_small_class(int cls, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase,
+LfRouting read_routing()
+{
+    LfRouting r;
+    r.bandreg = bandreg_on(); r.groupk = groupk_on(); r.bandreg_small = bandreg_small(); r.band_mask = band_mask();
+    r.large_one_warp = getenv("LF_LARGE_ONE_WARP") != nullptr;   /* one warp per large task instead of two */
+    r.serial = getenv("LF_SERIAL") != nullptr;                    /* one class kernel at a time (per-class durations for profiling) */
+    r.order_band_first = getenv("LF_ORDER_BAND_FIRST") != nullptr;
+    r.nstreams = getenv("LF_STREAMS") ? atoi(getenv("LF_STREAMS")) : LF_NSUB - 1;   /* class kernels in flight at once */
+    if (r.nstreams < 1 || r.nstreams > LF_NSUB - 1) r.nstreams = LF_NSUB - 1;
+    /* class sizes up to this go wide; measured on the config-2 step: off (0) 1.87 ms, 2048 1.99 ms -- the wide shapes run 4x the
+     * warps for the same columns and the step is bound by issue slots, not by the longest task */
+    r.group_wide = getenv("LF_GROUP_WIDE") ? (uint32_t)atoi(getenv("LF_GROUP_WIDE")) : 0u;
+    return r;
+}
+
+void launch_small_class(int cls, const LfRouting &rt, const LfDev &v, const uint32_t *order, uint32_t first, uint32_t count, uint32_t gbase,
                         const unsigned long long *goff, lfb_stream s, uint32_t *rl, uint32_t *rc, uint32_t bmask)
 {   /* rl: retry list (indexed like `order`), rc: this class's retry counter */
-    if (cls < 8 && !(cls & 1) && bandreg_small()) {   /* global-mode tasks of q <= 128: the band is the whole column (no slides, no certificate) */
+    if (cls < 8 && !(cls & 1) && rt.bandreg_small) {   /* global-mode tasks of q <= 128: the band is the whole column (no slides, no certificate) */
         switch (cls) {
         case 0: launch_bandreg<1, false>(v, order, first, count, s, rl, rc, 1); return;
         case 2: launch_bandreg<2, false>(v, order, first, count, s, rl, rc, 2); return;
@@ -370,11 +393,12 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
     LF_TRY(d.scratch.reserve((size_t)ht->scr_total + 64));
     /* plane regions of k_myers_band: one per warp group (32 consecutive sorted tasks of a class) */
     LfGroupCfg gc;
-    const uint32_t bmask = band_mask();
+    const LfRouting &rt = ctx->rt;
+    const uint32_t bmask = rt.band_mask;
     {
         uint32_t first = 0, g = 0;
         for (int cls = 0; cls < LF_CLS_LARGE; cls++) {
-            gc.first[cls] = first; gc.count[cls] = ht->cnt.hist[cls]; gc.gbase[cls] = g; gc.nb[cls] = ((bmask >> cls & 1u) && !(bandreg_small() && cls < 8 && !(cls & 1))) ? (uint32_t)band_nb(cls) : 0u;
+            gc.first[cls] = first; gc.count[cls] = ht->cnt.hist[cls]; gc.gbase[cls] = g; gc.nb[cls] = ((bmask >> cls & 1u) && !(rt.bandreg_small && cls < 8 && !(cls & 1))) ? (uint32_t)band_nb(cls) : 0u;
             first += ht->cnt.hist[cls]; g += (ht->cnt.hist[cls] + 31) / 32;
         }
         gc.gbase[LF_CLS_LARGE] = g;
@@ -421,7 +445,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][0], d.sub[0]);
 #endif
-        LFB_LAUNCH(k_myers_large, (unsigned)slots, getenv("LF_LARGE_ONE_WARP") ? 32 : 64, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg, (const uint32_t *)nullptr);
+        LFB_LAUNCH(k_myers_large, (unsigned)slots, rt.large_one_warp ? 32 : 64, 0, d.sub[0], v, d.idx2.as<uint32_t>(), nsmall, nlarge, cfg, (const uint32_t *)nullptr);
 #ifndef LF_EMU
         cudaEventRecord(d.cls_ev[LF_CLS_LARGE][1], d.sub[0]);
 #endif
@@ -435,12 +459,11 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         for (int cls = 0; cls < LF_NCLS; cls++) { firsts[cls] = first; first += ht->cnt.hist[cls]; }   /* sorted order = class id order */
         int k = 0;
         int seq[LF_NCLS], nseq = 0;
-        const bool serial = getenv("LF_SERIAL") != nullptr;
-        int nstreams = getenv("LF_STREAMS") ? atoi(getenv("LF_STREAMS")) : LF_NSUB - 1;   /* class kernels in flight at once */
-        if (nstreams < 1 || nstreams > LF_NSUB - 1) nstreams = LF_NSUB - 1;
+        const bool serial = rt.serial;
+        const int nstreams = rt.nstreams;
         /* k_myers_group classes first (their tasks are the longest after the large ones), longest rows first */
         for (int cls = LF_CLS_GD256; cls >= LF_CLS_GP16; cls--) seq[nseq++] = cls;
-        if (!getenv("LF_ORDER_BAND_FIRST")) {   /* the full-width classes (few, long tasks: the tail of the step) before the sliding-band ones */
+        if (!rt.order_band_first) {   /* the full-width classes (few, long tasks: the tail of the step) before the sliding-band ones */
             for (int cls = LF_CLS_LARGE - 1; cls >= 8; cls--) seq[nseq++] = cls;
             for (int cls = LF_CLS_BANDREG0 + 3; cls >= LF_CLS_BANDREG0; cls--) seq[nseq++] = cls;
             for (int cls = 7; cls >= 0; cls--) seq[nseq++] = cls;
@@ -452,7 +475,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
         unsigned gblocks[LF_NCLS] = {};
         bool gwide[LF_NCLS] = {};
         LfGroupRun grun[LF_NCLS] = {};
-        const uint32_t wide_below = getenv("LF_GROUP_WIDE") ? (uint32_t)atoi(getenv("LF_GROUP_WIDE")) : 0u;   /* class sizes up to this go wide; measured on the config-2 step: off (0) 1.87 ms, 2048 1.99 ms -- the wide shapes run 4x the warps for the same columns and the step is bound by issue slots, not by the longest task */
+        const uint32_t wide_below = rt.group_wide;
         {
             size_t off = 0, offs[LF_NCLS] = {};
             for (int cls = LF_CLS_GP16; cls <= LF_CLS_GD256; cls++) {
@@ -487,7 +510,7 @@ int run_align_dev(lf_gpu_ctx *ctx, DevState &d)
             cudaEventRecord(d.cls_ev[cls][0], st);
 #endif
             if (cls >= LF_CLS_GP16) launch_group_class(cls, gwide[cls], v, d.idx2.as<uint32_t>(), firsts[cls], count, st, grun[cls], gblocks[cls]);
-            else launch_small_class(cls, v, d.idx2.as<uint32_t>(), firsts[cls], count, cls < LF_CLS_LARGE ? gc.gbase[cls] : 0u, d.goff.as<unsigned long long>(), st,
+            else launch_small_class(cls, rt, v, d.idx2.as<uint32_t>(), firsts[cls], count, cls < LF_CLS_LARGE ? gc.gbase[cls] : 0u, d.goff.as<unsigned long long>(), st,
                                d.idx.as<uint32_t>() /* input of the sort, free by now */, d.queue.as<uint32_t>() + 1 + cls, bmask);
             if (cls >= LF_CLS_BANDREG0 && cls < LF_CLS_GP16) {   /* the uncertified few: warp per task, on the same stream */
                 const int bi = cls - LF_CLS_BANDREG0;
@@ -574,6 +597,7 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
     devs.push_back(0);
 #endif
     lf_gpu_ctx *ctx = new lf_gpu_ctx();
+    ctx->rt = read_routing();
     ctx->l_pac = l_pac;
     ctx->devs.resize(devs.size());
     const size_t pac_bytes = (size_t)(l_pac / 4 + 1);
