@@ -49,7 +49,7 @@ __attribute__((constructor)) static void lfglue_prewarm(int argc, char **argv, c
                 setenv("LF_GPU_DEVICES", r.c_str(), 1);
             }
         }
-        lf_gpu_prewarm();
+        if (!getenv("LF_NO_PREWARM")) lf_gpu_prewarm();
         return;
     }
 }

@@ -14,6 +14,7 @@
  */
 #include <stddef.h>
 #include <stdio.h>
+#include <time.h>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -579,7 +580,10 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
 {
     if (!out || !pac || l_pac <= 0) return LF_ERR_BAD_ARG;
 #ifndef LF_EMU
+    const bool init_trace = getenv("LF_INIT_TRACE") != nullptr;
+    struct timespec its0; clock_gettime(CLOCK_MONOTONIC, &its0);
     { std::lock_guard<std::mutex> g(g_prewarm_mu); if (g_prewarm.joinable()) g_prewarm.join(); }
+    if (init_trace) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "[lf_gpu_init: waited %.0f ms for the prewarm thread]\n", (ts.tv_sec - its0.tv_sec) * 1e3 + (ts.tv_nsec - its0.tv_nsec) * 1e-6); }
 #endif
     *out = nullptr;
     lfb_errbuf[0] = 0;
@@ -610,6 +614,9 @@ int lf_gpu_init(lf_gpu_ctx **out, const uint8_t *pac, int64_t l_pac, const int *
         if (!d.pinned || d.pac.reserve(pac_bytes + 16)) { lf_gpu_destroy(ctx); return LF_ERR_NOMEM; }
         if (lfb_memset(d.pac.p, 0, pac_bytes + 16, d.stream) || lfb_h2d(d.pac.p, pac, pac_bytes, d.stream) || lfb_sync(d.stream)) { lf_gpu_destroy(ctx); return LF_ERR_CUDA; }
     }
+#ifndef LF_EMU
+    if (init_trace) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "[lf_gpu_init: %.0f ms in all (streams, events, reference upload after the wait)]\n", (ts.tv_sec - its0.tv_sec) * 1e3 + (ts.tv_nsec - its0.tv_nsec) * 1e-6); }
+#endif
     *out = ctx;
     return LF_OK;
 }
@@ -656,11 +663,17 @@ void lf_gpu_prewarm(void)
     g_prewarm_started = true;
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     g_prewarm = std::thread([] {
+        const bool tr = getenv("LF_INIT_TRACE") != nullptr;
+        auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+        const double t0 = now();
         cudaFree(nullptr);                                  /* driver + primary context */
+        const double t1 = now();
         cudaFuncAttributes a;
         cudaFuncGetAttributes(&a, (const void *)k_pack_reads);   /* module load */
+        const double t2 = now();
         void *p = nullptr;                                  /* first pinned allocation maps the host-memory machinery */
         if (cudaMallocHost(&p, 1 << 20) == cudaSuccess) cudaFreeHost(p);
+        if (tr) fprintf(stderr, "[lf_gpu_prewarm: driver + context %.0f ms, module %.0f ms, first pinned allocation %.0f ms]\n", t1 - t0, t2 - t1, now() - t2);
     });
 #endif
 }
