@@ -205,9 +205,13 @@ class LfGpu:
         if rc != 0:
             raise LfGpuError(f"{what} failed with status {rc}: {self.lib.lf_gpu_last_error(self.ctx).decode()}")
 
-    def _reads(self, bases: np.ndarray, offsets: np.ndarray) -> Reads:
-        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    def _reads(self, bases, offsets: np.ndarray) -> Reads:
+        """bases = None: the reads the last upload_reads / seed_batch left on the device (lf_gpu_align_chains accepts that)"""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if bases is None:
+            self._keep = [offsets]
+            return Reads(None, _ptr(offsets), len(offsets) - 1)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
         self._keep = [bases, offsets]
         return Reads(_ptr(bases), _ptr(offsets), len(offsets) - 1)
 

@@ -281,3 +281,28 @@ def test_emu_chain_operator_edge_cases():
 @pytest.mark.gpu
 def test_gpu_chain_operator_edge_cases():
     _edge_cases(None)
+
+
+def _resident_reads(lib_path):
+    """reads->bases == NULL: lf_gpu_align_chains works on the reads an earlier call left on the device (what the drop-in
+    program does after seeding a chunk); a different read count is refused."""
+    w = sim.make_workload(120_000, 10, 2500, 0.12, 0.15, seed=8, sv_frac=0.5)
+    g = api.LfGpu(w.pac, len(w.ref), lib_path=lib_path)
+    seeds, chains = api.workload_chains(w)
+    off = w.read_off.astype(np.uint64)
+    want = g.align_chains(w.reads, off, w.contig_off, w.contig_len, seeds, chains)
+    g.upload_reads(w.reads, off)
+    got = g.align_chains(None, off, w.contig_off, w.contig_len, seeds, chains)
+    assert np.array_equal(got[0], want[0]) and got[1] == want[1] and len(want[0]) > 0
+    with pytest.raises(api.LfGpuError):
+        g.align_chains(None, off[:-1], w.contig_off, w.contig_len, seeds, chains[chains["read_id"] < len(off) - 2])
+    g.close()
+
+
+def test_emu_chain_operator_resident_reads():
+    _resident_reads(build_emu())
+
+
+@pytest.mark.gpu
+def test_gpu_chain_operator_resident_reads():
+    _resident_reads(None)
