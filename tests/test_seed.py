@@ -283,3 +283,60 @@ def test_gpu_seeding_config2_chunk_every_read_against_reference():
     assert np.array_equal(np.diff(fo.astype(np.int64)), cnt[:, 0]) and np.array_equal(np.diff(ro.astype(np.int64)), cnt[:, 1])
     assert np.array_equal(_oracle.seed_list_digests(fwd, fo), dig[:, 0]) and np.array_equal(_oracle.seed_list_digests(rev, ro), dig[:, 1])
     assert len(fwd) + len(rev) > 2_000_000
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emu_seeding_random_cases_against_oracle(seed):
+    """Random small references (with repeats and a palindromic stretch), reads with substitutions, indels, N runs and
+    lower case, random parameters at the edges (one sample, min_anchor_len = k of the table, a single allowed hit)."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1500, 5000))
+    ref = sim.make_reference(n, seed=50 + seed)
+    a = int(rng.integers(0, n - 400)); b = int(rng.integers(0, n - 400))
+    ref[b:b + 200] = ref[a:a + 200]                                  # an exact repeat
+    c = int(rng.integers(0, n - 100)); ref[c + 40:c + 80] = sim.revcomp(ref[c:c + 40])   # a reverse-complement palindrome
+    reads = []
+    for i in range(8):
+        L = int(rng.integers(1, 400))
+        s = int(rng.integers(0, n - L))
+        r = ref[s:s + L].copy()
+        hit = rng.random(L) < rng.uniform(0.0, 0.2)
+        r[hit] = sim.ACGT[rng.integers(0, 4, size=int(hit.sum()))]
+        if L > 30 and i % 3 == 0:
+            p = int(rng.integers(0, L - 10)); r = np.concatenate([r[:p], r[p + int(rng.integers(1, 6)):]])        # deletion
+        if L > 30 and i % 3 == 1:
+            p = int(rng.integers(0, L - 10)); r = np.concatenate([r[:p], sim.ACGT[rng.integers(0, 4, size=3)], r[p:]])   # insertion
+        if len(r) > 20 and i % 4 == 2:
+            p = int(rng.integers(0, len(r) - 5)); r[p:p + int(rng.integers(1, 5))] = ord("N")
+        if i % 5 == 4:
+            r = np.char.lower(r.view("S1")).view(np.uint8).copy()
+        if i & 1:
+            r = sim.revcomp(np.where(np.isin(r, sim.ACGT), r, ord("A")).astype(np.uint8)) if not np.isin(r, sim.ACGT).all() else sim.revcomp(r)
+        reads.append(r.astype(np.uint8))
+    reads.append(np.zeros(0, np.uint8))                               # an empty read in the middle of the batch
+    reads.append(np.full(40, ord("N"), np.uint8))
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    allr = np.concatenate(reads) if sum(len(r) for r in reads) else np.zeros(0, np.uint8)
+    kc = int(rng.integers(4, 8))
+    g = api.LfGpu(sim.pack_pac(ref), len(ref), lib_path=_common.build_emu())
+    g.seed_init(fmindex.build(CODE[ref], sa_intv=int(rng.choice([1, 4, 32])), k_cache=kc))
+    idx = fm_oracle.TextIndex(CODE[ref])
+    have_shim = _oracle.have_ref() and hasattr(_oracle.ref(), "ref_fm_load")
+    if have_shim:
+        with tempfile.TemporaryDirectory() as d:
+            fa = os.path.join(d, "r.fa")
+            _oracle.write_fasta(fa, ref)
+            _oracle.ref_fm_load(fa, kc)
+    for prm in (dict(sampling_count=1, min_anchor_len=kc, max_ref_hits=1000),
+                dict(sampling_count=int(rng.integers(2, 90)), min_anchor_len=int(rng.integers(kc, 20)), max_ref_hits=int(rng.integers(1, 6))),
+                dict(sampling_count=500, min_anchor_len=14, max_ref_hits=1000)):
+        want = fm_oracle.seed_batch(idx, allr, off, **prm)
+        assert lists_equal(g.seed_batch(allr, off, **prm), want), prm
+        if have_shim:                                                 # ... and the reference itself on the same reads
+            rb = allr.tobytes()
+            for i in range(len(off) - 1):
+                f, r = _oracle.ref_fm_seed(rb[int(off[i]):int(off[i + 1])], **prm)
+                assert np.array_equal(f, want[0][int(want[1][i]):int(want[1][i + 1])]) and np.array_equal(r, want[2][int(want[3][i]):int(want[3][i + 1])]), (prm, i)
+    g.close()
