@@ -26,9 +26,12 @@ typedef cudaEvent_t lfb_event;
  * the checkpoints and op planes live on L1 hits, so all-shared is the worst choice.  LF_CARVEOUT overrides (-1 = leave
  * the driver default). */
 static inline int lfb_carveout() { static int v = -2; if (v == -2) { const char *e = getenv("LF_CARVEOUT"); v = e ? atoi(e) : 50; } return v; }
+/* the attribute is per device: once per (kernel, device the launching thread made current with set_dev) */
+static thread_local int lfb_cur_dev = 0;
 #define LFB_LAUNCH(kern, grid, block, smem, stream, ...) do { \
-        static bool lfb_once_ = false; \
-        if (!lfb_once_) { if (lfb_carveout() >= 0) cudaFuncSetAttribute((const void *)(kern), cudaFuncAttributePreferredSharedMemoryCarveout, lfb_carveout()); lfb_once_ = true; } \
+        static std::atomic<unsigned long long> lfb_done_{0}; \
+        const unsigned long long lfb_bit_ = 1ull << (lfb_cur_dev & 63); \
+        if (!(lfb_done_.load(std::memory_order_relaxed) & lfb_bit_)) { if (lfb_carveout() >= 0) cudaFuncSetAttribute((const void *)(kern), cudaFuncAttributePreferredSharedMemoryCarveout, lfb_carveout()); lfb_done_.fetch_or(lfb_bit_); } \
         kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); lfb_launches++; } while (0)
 #else
 #include <algorithm>

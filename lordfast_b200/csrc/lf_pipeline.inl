@@ -85,7 +85,7 @@ namespace {
 struct HostTotals { LfCounters cnt; unsigned long long slot_total, scr_total; };
 
 #ifndef LF_EMU
-int set_dev(const DevState &d) { return cudaSetDevice(d.dev) == cudaSuccess ? 0 : -2; }
+int set_dev(const DevState &d) { if (cudaSetDevice(d.dev) != cudaSuccess) return -2; lfb_cur_dev = d.dev; return 0; }
 #else
 int set_dev(const DevState &) { return 0; }
 #endif
